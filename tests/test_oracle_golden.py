@@ -1,0 +1,80 @@
+"""Pin the CPU oracle (oracle/sqldepth_oracle.py) against outputs of the reference itself.
+
+The golden vectors under tests/golden/ were produced by oracle/make_golden.py, which executes the
+unmodified reference (trainer.py:386-549, networks/depth_decoder_QTR.py:36-74, layers.py) on CPU.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sqldepth_oracle as O
+from _cases import PHOTO_CASES, load_npz, photo_case
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.mark.parametrize("name", PHOTO_CASES)
+def test_photometric_matches_reference(name):
+    kw, leaves, z, fids = photo_case(name)
+    out = O.photometric_losses(**kw)
+    assert abs(float(out["loss"]) - float(z["out_loss"])) < 2e-7
+    for s in kw["scales"]:
+        assert abs(float(out["loss/%d" % s]) - float(z["out_loss_s%d" % s])) < 2e-7
+        np.testing.assert_allclose(out[("depth", 0, s)].detach().numpy(), z["out_depth_s%d" % s], rtol=1e-6, atol=1e-6)
+        if not kw["disable_automasking"]:
+            sel = out["identity_selection/%d" % s].numpy().astype(np.uint8)
+            assert (sel != z["out_idsel_s%d" % s]).mean() < 1e-4
+    s0 = kw["scales"][0]
+    for i, f in enumerate(fids[1:]):
+        np.testing.assert_allclose(out[("sample", i, s0)].detach().numpy(), z["out_sample_%s_s%d" % (f, s0)], atol=2e-6)
+        np.testing.assert_allclose(out[("color", i, s0)].detach().numpy(), z["out_color_%s_s%d" % (f, s0)], atol=2e-5)
+    names = list(leaves)
+    grads = torch.autograd.grad(out["loss"], [leaves[n] for n in names], allow_unused=True)
+    for n, g in zip(names, grads):
+        ref = z["grad_" + n]
+        g = np.zeros_like(ref) if g is None else g.numpy()
+        scale = max(np.abs(ref).max(), 1e-12)
+        assert np.abs(g - ref).max() / scale < 2e-3, n
+
+
+@pytest.mark.parametrize("name", ["decoder_full", "decoder_lite"])
+def test_sql_tail_matches_reference(name):
+    z = load_npz(name)
+    st = load_npz(name + "_state")
+    x = _t(z["x"]).requires_grad_(True)
+    q = _t(z["queries"]).requires_grad_(True)
+    mlp = [_t(st["bins_regressor.%d.%s" % (i, k)]) for i in (0, 2, 4) for k in ("weight", "bias")]
+    D, Q = int(z["D"]), int(z["Q"])
+    Wp = _t(st["convert_to_prob.0.weight"]).reshape(D, Q).clone().requires_grad_(True)
+    bp = _t(st["convert_to_prob.0.bias"]).clone().requires_grad_(True)
+    out = O.sql_tail(x, q, mlp, Wp, bp, float(z["min_val"]), float(z["max_val"]))
+    np.testing.assert_allclose(out["summary"].detach().numpy(), z["out_summary"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["energy"].detach().numpy()[:, :, ::4, ::4], z["out_energy_sample"], rtol=1e-5, atol=1e-5)
+    rel = (out["pred"].detach().numpy() - z["out_pred"]) / z["out_pred"]
+    assert np.abs(rel).max() < 2e-5
+    (out["pred"] * _t(z["gout"])).sum().backward()
+    for got, ref in ((x.grad, z["grad_x"]), (q.grad, z["grad_queries"]), (Wp.grad, z["grad_Wp"]), (bp.grad, z["grad_bp"])):
+        assert np.abs(got.numpy() - ref).max() / np.abs(ref).max() < 1e-3
+
+
+def test_modules_match_reference():
+    z = load_npz("modules")
+    a = _t(z["a"]).requires_grad_(True)
+    ss = O.ssim(a, _t(z["b"]))
+    np.testing.assert_allclose(ss.detach().numpy(), z["out_ssim"], atol=1e-6)
+    (ga,) = torch.autograd.grad((ss * _t(z["g_ssim"])).sum(), a)
+    assert np.abs(ga.numpy() - z["grad_a"]).max() / np.abs(z["grad_a"]).max() < 1e-3
+    aa, tr = _t(z["axisangle"]), _t(z["translation"])
+    np.testing.assert_allclose(O.pose_matrix(aa, tr, False).numpy(), z["out_T"], atol=1e-7)
+    np.testing.assert_allclose(O.pose_matrix(aa, tr, True).numpy(), z["out_T_inv"], atol=1e-7)
+    B, H, W = int(z["B"]), int(z["H"]), int(z["W"])
+    pts = O.backproject(_t(z["depth"]), _t(z["inv_K"]))
+    np.testing.assert_allclose(pts.numpy(), z["out_points"], rtol=1e-6, atol=1e-6)
+    grid = O.project(pts, _t(z["K"]), _t(z["out_T"]), H, W)
+    np.testing.assert_allclose(grid.numpy(), z["out_grid"], atol=2e-6)
+    sm = O.smooth_loss(_t(z["disp"]), _t(z["b"]))
+    assert abs(float(sm) - float(z["out_smooth"])) < 1e-7
+    sil = O.silog_loss(_t(z["silog_pred"]), _t(z["silog_gt"]), mask=_t(z["silog_gt"]) > 1e-3)
+    assert abs(float(sil) - float(z["out_silog"])) < 1e-5

@@ -1,0 +1,23 @@
+# Builds libsqlx.so (sm_100a only) in-tree.  `python -c "import __graft_entry__ as g; g.build()"` calls this.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr
+PKG       := sfmnext-impl_b200
+SRC       := $(wildcard $(PKG)/csrc/*.cu)
+OBJ       := $(patsubst $(PKG)/csrc/%.cu,$(PKG)/build/%.o,$(SRC))
+LIB       := $(PKG)/lib/libsqlx.so
+
+all: $(LIB)
+
+$(PKG)/build/%.o: $(PKG)/csrc/%.cu $(wildcard $(PKG)/csrc/*.cuh) include/sqlx.h
+	@mkdir -p $(PKG)/build
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(PKG)/build/$*.ptxas.log || (cat $(PKG)/build/$*.ptxas.log; exit 1)
+
+$(LIB): $(OBJ)
+	@mkdir -p $(PKG)/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart -lcuda
+
+clean:
+	rm -rf $(PKG)/build $(PKG)/lib
+
+.PHONY: all clean

@@ -1,0 +1,193 @@
+/* sqlx.h -- C ABI of libsqlx.so: the B200 (sm_100a) hot path of SQLdepth self-supervised training.
+ *
+ * The reference (hisfog/SfMNeXt-Impl, pure Python/PyTorch) has no FFI; the drop-in boundary is the
+ * set of nn.Module / Trainer signatures.  This header is what a maintainer binds from
+ * those Python call sites (ctypes).  Each entry point cites the reference lines
+ * (relative to /root/reference) whose device work it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (NCHW for images) unless marked "host";
+ *   - `stream` is a cudaStream_t passed as void*; nothing here synchronises the device or allocates
+ *     persistent device memory: outputs and workspaces are caller-owned (sizes via *_workspace_bytes);
+ *   - return value 0 = success, negative SQLX_E* otherwise; sqlx_last_error() gives a message
+ *     (thread-local).  The library is re-entrant (forward thread + autograd thread).
+ */
+#ifndef SQLX_H_
+#define SQLX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQLX_OK 0
+#define SQLX_EINVAL (-1)      /* bad argument / unsupported shape */
+#define SQLX_ECUDA (-2)       /* CUDA runtime error (launch or sticky) */
+#define SQLX_EWORKSPACE (-3)  /* workspace too small */
+
+/* flags of sqlx_photo_desc.flags  (trainer.py option it mirrors) */
+#define SQLX_AUTOMASK 1u      /* NOT --disable_automasking   trainer.py:478-493,514-519 */
+#define SQLX_AVG_REPROJ 2u    /* --avg_reprojection          trainer.py:489,509 */
+#define SQLX_NO_SSIM 4u       /* --no_ssim                   trainer.py:446-447 */
+
+#define SQLX_MAX_SOURCES 4
+
+typedef struct sqlx_photo_desc {
+  int32_t B, H, W;        /* batch (per GPU), full-resolution height/width (opt.height/opt.width) */
+  int32_t h, w;           /* resolution of the network output at this scale, outputs[("disp",s)] */
+  int32_t S;              /* number of source frames, len(frame_ids)-1, 1..SQLX_MAX_SOURCES */
+  int32_t ssim_radius;    /* 3 = layers.py:19 (7x7, the live SSIM); 1 = calc_layers.py:223 (3x3) */
+  uint32_t flags;         /* SQLX_AUTOMASK | SQLX_AVG_REPROJ | SQLX_NO_SSIM */
+  float w_ssim, w_l1;     /* 0.85 / 0.15, trainer.py:451 */
+  float noise_scale;      /* 1e-5, trainer.py:517 */
+  float eps;              /* Project3D eps 1e-7, layers.py:239 */
+} sqlx_photo_desc;
+
+const char* sqlx_last_error(void);
+int sqlx_version(void);
+/* 1 if the visible device is compute capability 10.x (the only target this library is built for) */
+int sqlx_device_ok(int device);
+
+/* ---------------------------------------------------------------------------------------------
+ * Photometric block
+ * ------------------------------------------------------------------------------------------- */
+
+/* Per-sample statistics of the bilinearly upsampled (align_corners=False) depth:
+ *   stats[b][0] = mean_{HxW} d_up,  stats[b][1] = mean_{HxW} 1/d_up
+ * replaces F.interpolate + (1/depth).mean  (trainer.py:395-396, 417-418) and disp.mean (trainer.py:535).
+ * stats must be zeroed by the caller?  No: the kernel overwrites.  workspace: sqlx_depth_stats_workspace_bytes. */
+size_t sqlx_depth_stats_workspace_bytes(int B, int H, int W);
+int sqlx_depth_stats_fwd(const float* depth_lr, int B, int h, int w, int H, int W,
+                         float* stats /*[B,2]*/, void* workspace, size_t workspace_bytes, void* stream);
+/* d_depth_lr[b,i,j] += g_stats[b][0]*d(mean d)/d(lr) + g_stats[b][1]*d(mean 1/d)/d(lr)   (accumulates) */
+int sqlx_depth_stats_bwd(const float* depth_lr, int B, int h, int w, int H, int W,
+                         const float* g_stats /*[B,2]*/, float* d_depth_lr /*[B,h,w]*/, void* stream);
+
+/* Reprojection loss of two image batches: out[b,0,v,u] = w_ssim*mean_c SSIM(pred,target) + w_l1*mean_c|target-pred|
+ * replaces Trainer.compute_reprojection_loss (trainer.py:441-453) and SSIM.forward (layers.py:31-46).
+ * Used once per step for the identity (auto-mask) losses of every source (trainer.py:480-493). */
+int sqlx_reprojection_loss_fwd(const float* pred, const float* target, int B, int H, int W, int ssim_radius,
+                               float w_ssim, float w_l1, int no_ssim, float* out /*[B,H,W]*/, void* stream);
+
+/* Full SSIM map, module-level drop-in for layers.SSIM.forward (layers.py:31-46): out [B,3,H,W] */
+int sqlx_ssim_fwd(const float* x, const float* y, int B, int C, int H, int W, int ssim_radius,
+                  float* out, void* stream);
+/* gradient wrt x and (optionally, may be NULL) y given g_out [B,C,H,W] */
+int sqlx_ssim_bwd(const float* x, const float* y, const float* g_out, int B, int C, int H, int W,
+                  int ssim_radius, float* gx, float* gy, void* stream);
+
+/* Fused: upsample -> backproject -> project -> border-clamped bilinear gather of S sources ->
+ * SSIM+L1 vs target -> min with identity (+noise) -> sum.
+ * replaces layers.py:210-215,247-258,31-46 + trainer.py:395-396,423-435,444-451,474-532.
+ *   depth_lr  [B,1,h,w]       network output at this scale (this IS depth: trainer.py:399-402)
+ *   target    [B,3,H,W]       inputs[("color",0,0)]
+ *   sources   host array of S device pointers, each [B,3,H,W]   inputs[("color",f,0)]
+ *   K, inv_K  [B,4,4]
+ *   T         [B,S,4,4]       camera transforms (already rescaled by mean inverse depth when posecnn)
+ *   identity  [B,S,H,W] or NULL (no automask): sqlx_reprojection_loss_fwd(source_f, target), WITHOUT noise
+ *   noise     [B,Sn,H,W] or NULL: standard-normal tie-break noise, Sn = 1 if AVG_REPROJ else S (trainer.py:516)
+ * outputs
+ *   loss_sum  [1]  double?  no: float, = sum over b,v,u of the per-pixel minimum (caller divides by B*H*W)
+ *   argmin    [B,H,W] uint8: index into cat(identity, reprojection) exactly as torch.min(combined,dim=1)
+ */
+size_t sqlx_photo_workspace_bytes(const sqlx_photo_desc* desc);
+int sqlx_photo_fwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
+                   const float* const* sources, const float* K, const float* inv_K, const float* T,
+                   const float* identity, const float* noise,
+                   float* loss_sum, uint8_t* argmin, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of sqlx_photo_fwd.  g_loss is a DEVICE scalar (upstream gradient of the per-scale loss);
+ * `scale` is a host multiplier (1/(B*H*W)).
+ *   d_depth_lr [B,h,w]  accumulated (+=) -- caller zeroes
+ *   d_T        [B,S,4,4] overwritten     (gradient wrt T; rows 3 are zero)
+ */
+int sqlx_photo_bwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
+                   const float* const* sources, const float* K, const float* inv_K, const float* T,
+                   const uint8_t* argmin, const float* g_loss, float scale,
+                   float* d_depth_lr, float* d_T, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Warp only (materialises what Trainer.log reads): sample [B,H,W,2] normalised grid (layers.py:255-257),
+ * color [B,3,H,W] warped source (trainer.py:431-435), depth_up [B,1,H,W] (trainer.py:402). Any output may be NULL. */
+int sqlx_warp_fwd(const float* depth_lr, const float* source, const float* K, const float* inv_K,
+                  const float* T /*[B,4,4] with batch stride T_stride floats*/, int T_stride,
+                  int B, int h, int w, int H, int W, float eps,
+                  float* depth_up, float* sample, float* color, void* stream);
+
+/* Module-level geometry drop-ins (the fused path above never materialises these tensors).
+ * BackprojectDepth.forward (layers.py:210-215): depth [B,1,H,W], inv_K [B,4,4] -> points [B,4,H*W] (row 3 = 1). */
+int sqlx_backproject_fwd(const float* depth, const float* inv_K, int B, int H, int W, float* points, void* stream);
+/* d_depth [B,1,H,W] (overwritten) given g_points [B,4,H*W] */
+int sqlx_backproject_bwd(const float* g_points, const float* inv_K, int B, int H, int W, float* d_depth, void* stream);
+/* Project3D.forward (layers.py:247-258): points [B,4,N], K, T [B,4,4] -> normalised grid [B,H,W,2] */
+int sqlx_project_fwd(const float* points, const float* K, const float* T, int B, int H, int W, float eps,
+                     float* grid, void* stream);
+/* d_points [B,4,N] (overwritten, may be NULL) and d_T [B,4,4] (overwritten) given g_grid [B,H,W,2];
+ * workspace: 48*B bytes. */
+int sqlx_project_bwd(const float* points, const float* K, const float* T, const float* g_grid, int B, int H, int W,
+                     float eps, float* d_points, float* d_T, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Edge-aware smoothness (layers.py:267-280 + trainer.py:533-542) of the mean-normalised disparity.
+ * disp_lr [B,1,h,w] is upsampled to the colour resolution [Hc,Wc] when the shapes differ.
+ *   sums [B,3] = { sum_x |dx d| e^{-|dx I|}, sum_y |dy d| e^{-|dy I|}, sum d }   (over the upsampled map)
+ *   loss = sum_b sums[b][0]/(mean_b+1e-7) / (B*Hc*(Wc-1)) + sum_b sums[b][1]/(mean_b+1e-7) / (B*(Hc-1)*Wc)
+ * The tiny [B,3] -> scalar step is done by the host wrapper in torch (differentiable). */
+size_t sqlx_smooth_workspace_bytes(int B, int Hc, int Wc);
+int sqlx_smooth_fwd(const float* disp_lr, const float* color, int B, int h, int w, int Hc, int Wc,
+                    float* sums /*[B,3]*/, void* workspace, size_t workspace_bytes, void* stream);
+/* d_disp_lr += adjoint given g_sums [B,3] (device) */
+int sqlx_smooth_bwd(const float* disp_lr, const float* color, int B, int h, int w, int Hc, int Wc,
+                    const float* g_sums, float* d_disp_lr, void* stream);
+
+/* Pose matrix: T[b] = transformation_from_parameters(axisangle[b], translation[b]*scale[b], invert)
+ * replaces layers.py:75-150 (~60 tiny kernels per call in the reference) and the translation rescale of
+ * trainer.py:417-421.  axisangle, translation [B,3]; scale [B] or NULL (= 1); T [B,4,4]. */
+int sqlx_pose_fwd(const float* axisangle, const float* translation, const float* scale, int B, int invert,
+                  float* T, void* stream);
+/* gradients wrt the three inputs given dT [B,4,4]; d_scale NULL iff scale NULL */
+int sqlx_pose_bwd(const float* axisangle, const float* translation, const float* scale, int B, int invert,
+                  const float* dT, float* d_axisangle, float* d_translation, float* d_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SQL block (Self Query Layer tail of the depth decoder)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Pixel-softmax summaries: summary[b,q,:] = sum_p softmax_p(x^T K)[p,q] * x[:,p]
+ * replaces FullQueryLayer.forward's summary path (networks/layers.py:17-19) without materialising [B,n,Q].
+ *   x [B,E,n] (n = h*w, NCHW view), queries [B,Q,E]
+ *   summary [B,Q,E]; row_max [B,Q], row_sum [B,Q] (softmax statistics, saved for backward)
+ *   energy: optional [B,Q,n] (the module-level drop-in returns it; NULL inside the fused decoder) */
+size_t sqlx_sql_workspace_bytes(int B, int E, int Q, int D, int n);
+int sqlx_sql_summary_fwd(const float* x, const float* queries, int B, int E, int Q, int n,
+                         float* summary, float* row_max, float* row_sum, float* energy,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Depth regression: pred[b,p] = sum_d softmax_d(Wp (x^T K)[p,:] + bp)[d] * centers[b,d]
+ * replaces networks/layers.py:17,20 + depth_decoder_QTR.py:61,70 (1x1 conv, Softmax(dim=1), sum). */
+int sqlx_sql_pred_fwd(const float* x, const float* queries, const float* Wp /*[D,Q]*/, const float* bp /*[D]*/,
+                      const float* centers /*[B,D]*/, int B, int E, int Q, int D, int n,
+                      float* pred /*[B,n]*/, void* stream);
+
+/* Backward pass 1 (pixel reductions):  d_centers [B,D], d_Wp [D,Q], d_bp [D]  (all overwritten) */
+int sqlx_sql_bwd_reduce(const float* x, const float* queries, const float* Wp, const float* bp,
+                        const float* centers, const float* pred, const float* g_pred /*[B,n]*/,
+                        int B, int E, int Q, int D, int n,
+                        float* d_centers, float* d_Wp, float* d_bp,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward pass 2: d_x [B,E,n] (overwritten), d_queries [B,Q,E] (overwritten).
+ *   d_summary [B,Q,E] comes from autograd through the bins MLP (kept in PyTorch);
+ *   g_energy optional [B,Q,n]: extra upstream gradient on the energy maps (module-level FullQueryLayer);
+ *   g_pred may be NULL (then Wp/bp/centers/pred are ignored: pure FullQueryLayer backward). */
+int sqlx_sql_bwd_dx(const float* x, const float* queries, const float* Wp, const float* bp,
+                    const float* centers, const float* pred, const float* g_pred,
+                    const float* summary, const float* row_max, const float* row_sum,
+                    const float* d_summary, const float* g_energy,
+                    int B, int E, int Q, int D, int n,
+                    float* d_x, float* d_queries, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQLX_H_ */

@@ -1,0 +1,12 @@
+"""sqlx -- B200-native hot path of SQLdepth self-supervised training (host side).
+
+Python mirrors of the reference's nn.Module / Trainer signatures on top of libsqlx.so
+(hand-written sm_100a CUDA behind the C ABI in include/sqlx.h).  No CPU / PyTorch fallback.
+"""
+from ._lib import SqlxError, lib, LIB_PATH, exported_symbols  # noqa: F401
+from .photometric import (photometric_losses, reprojection_loss, depth_stats, pose_matrix,  # noqa: F401
+                          smooth_loss_normalised, warp)
+from .layers import (SSIM, BackprojectDepth, Project3D, get_smooth_loss,  # noqa: F401
+                     transformation_from_parameters)
+from .sql import (FullQueryLayer, Depth_Decoder_QueryTr, Lite_Depth_Decoder_QueryTr, sql_tail,  # noqa: F401
+                  bin_centers)

@@ -1,0 +1,129 @@
+"""ctypes binding of libsqlx.so (the C ABI declared in include/sqlx.h).
+
+The product path has NO fallback: if the library is missing or a call fails, this raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsqlx.so")
+
+c_float_p = ctypes.c_void_p   # device pointers are passed as raw addresses
+c_size_t = ctypes.c_size_t
+c_int = ctypes.c_int
+c_float = ctypes.c_float
+c_void_p = ctypes.c_void_p
+
+SQLX_AUTOMASK = 1
+SQLX_AVG_REPROJ = 2
+SQLX_NO_SSIM = 4
+MAX_SOURCES = 4
+
+
+class PhotoDesc(ctypes.Structure):
+    _fields_ = [("B", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
+                ("h", ctypes.c_int32), ("w", ctypes.c_int32), ("S", ctypes.c_int32),
+                ("ssim_radius", ctypes.c_int32), ("flags", ctypes.c_uint32),
+                ("w_ssim", ctypes.c_float), ("w_l1", ctypes.c_float),
+                ("noise_scale", ctypes.c_float), ("eps", ctypes.c_float)]
+
+
+_PROTOS = {
+    "sqlx_last_error": (ctypes.c_char_p, []),
+    "sqlx_version": (c_int, []),
+    "sqlx_device_ok": (c_int, [c_int]),
+    "sqlx_depth_stats_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "sqlx_depth_stats_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sqlx_depth_stats_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "sqlx_reprojection_loss_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p]),
+    "sqlx_ssim_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sqlx_ssim_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "sqlx_photo_workspace_bytes": (c_size_t, [ctypes.POINTER(PhotoDesc)]),
+    "sqlx_photo_fwd": (c_int, [ctypes.POINTER(PhotoDesc), c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sqlx_photo_bwd": (c_int, [ctypes.POINTER(PhotoDesc), c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sqlx_warp_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sqlx_backproject_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sqlx_backproject_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sqlx_project_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "sqlx_project_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                                 c_void_p, c_size_t, c_void_p]),
+    "sqlx_smooth_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "sqlx_smooth_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sqlx_smooth_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "sqlx_pose_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "sqlx_pose_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sqlx_sql_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "sqlx_sql_summary_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_size_t, c_void_p]),
+    "sqlx_sql_pred_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                  c_void_p, c_void_p]),
+    "sqlx_sql_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sqlx_sql_bwd_dx": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                c_void_p, c_size_t, c_void_p]),
+}
+
+_lib = None
+
+
+class SqlxError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    return sorted(_PROTOS)
+
+
+def lib():
+    """Load libsqlx.so (once).  Raises SqlxError when it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise SqlxError("libsqlx.so not found at %s -- build it with `make` (or __graft_entry__.build()); "
+                        "the sqlx hot path has no CPU / PyTorch fallback" % LIB_PATH)
+    handle = ctypes.CDLL(LIB_PATH)
+    missing = []
+    for name, (res, args) in _PROTOS.items():
+        try:
+            fn = getattr(handle, name)
+        except AttributeError:
+            missing.append(name)
+            continue
+        fn.restype = res
+        fn.argtypes = args
+    if missing:                         # header / library mismatch: refuse to run on a partial library
+        raise SqlxError("libsqlx.so at %s lacks symbols declared in include/sqlx.h: %s" % (LIB_PATH, ", ".join(missing)))
+    _lib = handle
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib().sqlx_last_error()
+        raise SqlxError("%s failed (%d): %s" % (what, code, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Device address of a tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    import torch
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise SqlxError("sqlx ops run on CUDA tensors only (got a %s tensor); there is no CPU path" % t.device)
+        if t.dtype not in (torch.float32, torch.uint8):
+            raise SqlxError("sqlx ops are fp32 (got %s)" % t.dtype)

@@ -1,0 +1,144 @@
+"""Module-level drop-ins for the reference's layers.py (same class names, constructor arguments, forward
+signatures and error behaviour), each backed by libsqlx kernels with hand-written backward passes.
+
+  SSIM                             layers.py:13-46
+  transformation_from_parameters   layers.py:75-92 (+ rot_from_axisangle :111-150, get_translation_matrix :95-108)
+  BackprojectDepth                 layers.py:186-215
+  Project3D                        layers.py:236-258
+  get_smooth_loss                  layers.py:267-280
+"""
+import torch
+
+from ._lib import check, lib, ptr, require_cuda, stream_ptr
+from .photometric import _Smooth, _f32c, pose_matrix
+
+
+class _SSIMFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, radius):
+        require_cuda(x, y)
+        xc, yc = _f32c(x), _f32c(y)
+        if xc.shape != yc.shape or xc.dim() != 4:
+            raise RuntimeError("SSIM expects two [B,C,H,W] tensors of the same shape")
+        B, C, H, W = xc.shape
+        out = torch.empty_like(xc)
+        check(lib().sqlx_ssim_fwd(ptr(xc), ptr(yc), B, C, H, W, radius, ptr(out), stream_ptr()), "sqlx_ssim_fwd")
+        ctx.save_for_backward(xc, yc)
+        ctx.radius = radius
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, yc = ctx.saved_tensors
+        B, C, H, W = xc.shape
+        g = g.contiguous().float()
+        gx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(yc) if ctx.needs_input_grad[1] else None
+        if gx is not None or gy is not None:
+            check(lib().sqlx_ssim_bwd(ptr(xc), ptr(yc), ptr(g), B, C, H, W, ctx.radius, ptr(gx), ptr(gy), stream_ptr()),
+                  "sqlx_ssim_bwd")
+        return gx, gy, None
+
+
+class SSIM(torch.nn.Module):
+    """SSIM()(x, y) -> clamp((1 - SSIM) / 2, 0, 1), 7x7 window with reflection padding (layers.py:19-26).
+    `radius=1` gives the 3x3 monodepth2 variant of calc_layers.py:223-229."""
+
+    def __init__(self, radius=3):
+        super().__init__()
+        self.radius = radius
+
+    def forward(self, x, y):
+        return _SSIMFn.apply(x, y, self.radius)
+
+
+def transformation_from_parameters(axisangle, translation, invert=False):
+    """axisangle, translation [B,1,3] -> [B,4,4] (one kernel instead of ~60 tiny ATen launches)."""
+    return pose_matrix(axisangle, translation, None, invert)
+
+
+class _Backproject(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, inv_K, H, W):
+        require_cuda(depth, inv_K)
+        d, iK = _f32c(depth), _f32c(inv_K)
+        B = iK.shape[0]
+        pts = torch.empty(B, 4, H * W, device=d.device, dtype=torch.float32)
+        check(lib().sqlx_backproject_fwd(ptr(d), ptr(iK), B, H, W, ptr(pts), stream_ptr()), "sqlx_backproject_fwd")
+        ctx.save_for_backward(iK)
+        ctx.shape = (depth.shape, H, W)
+        return pts
+
+    @staticmethod
+    def backward(ctx, g):
+        (iK,) = ctx.saved_tensors
+        shape, H, W = ctx.shape
+        B = iK.shape[0]
+        g = g.contiguous().float()
+        dd = torch.empty(B, 1, H, W, device=g.device, dtype=torch.float32)
+        check(lib().sqlx_backproject_bwd(ptr(g), ptr(iK), B, H, W, ptr(dd), stream_ptr()), "sqlx_backproject_bwd")
+        return dd.view(shape), None, None, None
+
+
+class BackprojectDepth(torch.nn.Module):
+    """BackprojectDepth(batch_size, height, width)(depth [B,1,H,W], inv_K [B,4,4]) -> [B,4,H*W].
+    Like the reference (layers.py:212) the batch size is fixed at construction; a mismatching depth raises."""
+
+    def __init__(self, batch_size, height, width):
+        super().__init__()
+        self.batch_size, self.height, self.width = batch_size, height, width
+
+    def forward(self, depth, inv_K):
+        if depth.numel() != self.batch_size * self.height * self.width:
+            raise RuntimeError("shape '[%d, 1, -1]' is invalid for input of size %d" % (self.batch_size, depth.numel()))
+        return _Backproject.apply(depth, inv_K, self.height, self.width)
+
+
+class _Project(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, K, T, H, W, eps):
+        require_cuda(points, K, T)
+        p, Kc, Tc = _f32c(points), _f32c(K), _f32c(T)
+        B = Kc.shape[0]
+        grid = torch.empty(B, H, W, 2, device=p.device, dtype=torch.float32)
+        check(lib().sqlx_project_fwd(ptr(p), ptr(Kc), ptr(Tc), B, H, W, eps, ptr(grid), stream_ptr()), "sqlx_project_fwd")
+        ctx.save_for_backward(p, Kc, Tc)
+        ctx.cfg = (H, W, eps)
+        return grid
+
+    @staticmethod
+    def backward(ctx, g):
+        p, Kc, Tc = ctx.saved_tensors
+        H, W, eps = ctx.cfg
+        B = Kc.shape[0]
+        g = g.contiguous().float()
+        dp = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+        dT = torch.empty_like(Tc)
+        ws = torch.empty(48 * B, device=p.device, dtype=torch.uint8)
+        check(lib().sqlx_project_bwd(ptr(p), ptr(Kc), ptr(Tc), ptr(g), B, H, W, eps, ptr(dp), ptr(dT), ptr(ws), 48 * B,
+                                     stream_ptr()), "sqlx_project_bwd")
+        return dp, None, dT, None, None, None
+
+
+class Project3D(torch.nn.Module):
+    """Project3D(batch_size, height, width, eps=1e-7)(points [B,4,N], K, T [B,4,4]) -> grid [B,H,W,2]."""
+
+    def __init__(self, batch_size, height, width, eps=1e-7):
+        super().__init__()
+        self.batch_size, self.height, self.width, self.eps = batch_size, height, width, eps
+
+    def forward(self, points, K, T):
+        if points.shape[0] != self.batch_size or points.shape[-1] != self.height * self.width:
+            raise RuntimeError("shape '[%d, 2, %d, %d]' is invalid for input of size %d"
+                               % (self.batch_size, self.height, self.width, points.numel() // 2))
+        return _Project.apply(points, K, T, self.height, self.width, self.eps)
+
+
+def get_smooth_loss(disp, img):
+    """Edge-aware smoothness of `disp` [B,1,H,W] against `img` [B,3,H,W] -> scalar (layers.py:267-280)."""
+    if disp.shape[-2:] != img.shape[-2:]:
+        raise RuntimeError("The size of tensor a (%d) must match the size of tensor b (%d)" % (disp.shape[-1], img.shape[-1]))
+    sums = _Smooth.apply(disp, img)
+    B = disp.shape[0]
+    H, W = img.shape[-2:]
+    return sums[:, 0].sum() / float(B * H * (W - 1)) + sums[:, 1].sum() / float(B * (H - 1) * W)

@@ -1,0 +1,262 @@
+"""Photometric reprojection loss on libsqlx kernels (autograd Functions + the functional pipeline).
+
+Mirrors Trainer.generate_images_pred + Trainer.compute_losses of the reference
+(trainer.py:386-439, 455-549): same inputs, same loss, same `identity_selection` masks, gradients
+to the per-scale network outputs and to the pose parameters.  Everything device-side is a call
+into libsqlx.so through ctypes; there is no PyTorch fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import PhotoDesc, check, lib, ptr, require_cuda, stream_ptr
+
+
+def _f32c(t):
+    return t.detach().contiguous().float() if t is not None else None
+
+
+def make_desc(B, H, W, h, w, S, *, ssim_radius=3, automask=True, avg=False, no_ssim=False,
+              w_ssim=0.85, w_l1=0.15, noise_scale=1e-5, eps=1e-7):
+    flags = (_lib.SQLX_AUTOMASK if automask else 0) | (_lib.SQLX_AVG_REPROJ if avg else 0) | \
+            (_lib.SQLX_NO_SSIM if no_ssim else 0)
+    return PhotoDesc(B, H, W, h, w, S, ssim_radius, flags, w_ssim, w_l1, noise_scale, eps)
+
+
+def _src_array(sources):
+    arr = (ctypes.c_void_p * _lib.MAX_SOURCES)()
+    for i, s in enumerate(sources):
+        arr[i] = s.data_ptr()
+    return arr
+
+
+# ----------------------------------------------------------------------------- small ops
+class _DepthStats(torch.autograd.Function):
+    """[B,1,h,w] -> [B,2] = (mean, mean of reciprocal) of the map bilinearly upsampled to HxW."""
+
+    @staticmethod
+    def forward(ctx, depth_lr, H, W):
+        require_cuda(depth_lr)
+        d = _f32c(depth_lr)
+        B, _, h, w = d.shape
+        stats = torch.empty(B, 2, device=d.device, dtype=torch.float32)
+        nbytes = lib().sqlx_depth_stats_workspace_bytes(B, H, W)
+        ws = torch.empty(nbytes, device=d.device, dtype=torch.uint8)
+        check(lib().sqlx_depth_stats_fwd(ptr(d), B, h, w, H, W, ptr(stats), ptr(ws), nbytes, stream_ptr()),
+              "sqlx_depth_stats_fwd")
+        ctx.save_for_backward(d)
+        ctx.hw = (H, W)
+        return stats
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        B, _, h, w = d.shape
+        H, W = ctx.hw
+        out = torch.zeros_like(d)
+        g = g.contiguous().float()
+        check(lib().sqlx_depth_stats_bwd(ptr(d), B, h, w, H, W, ptr(g), ptr(out), stream_ptr()),
+              "sqlx_depth_stats_bwd")
+        return out, None, None
+
+
+def depth_stats(depth_lr, H, W):
+    return _DepthStats.apply(depth_lr, H, W)
+
+
+class _PoseMatrix(torch.autograd.Function):
+    """transformation_from_parameters(axisangle, translation*scale, invert) (layers.py:75-150)."""
+
+    @staticmethod
+    def forward(ctx, axisangle, translation, scale, invert):
+        require_cuda(axisangle, translation, scale)
+        aa = _f32c(axisangle).reshape(-1, 3)
+        tr = _f32c(translation).reshape(-1, 3)
+        sc = _f32c(scale).reshape(-1) if scale is not None else None
+        B = aa.shape[0]
+        T = torch.empty(B, 4, 4, device=aa.device, dtype=torch.float32)
+        check(lib().sqlx_pose_fwd(ptr(aa), ptr(tr), ptr(sc), B, int(bool(invert)), ptr(T), stream_ptr()), "sqlx_pose_fwd")
+        ctx.save_for_backward(aa, tr, sc)
+        ctx.invert = int(bool(invert))
+        ctx.shapes = (axisangle.shape, translation.shape, None if scale is None else scale.shape)
+        return T
+
+    @staticmethod
+    def backward(ctx, dT):
+        aa, tr, sc = ctx.saved_tensors
+        B = aa.shape[0]
+        dT = dT.contiguous().float()
+        daa = torch.empty_like(aa)
+        dtr = torch.empty_like(tr)
+        dsc = torch.empty(B, device=aa.device, dtype=torch.float32) if sc is not None else None
+        check(lib().sqlx_pose_bwd(ptr(aa), ptr(tr), ptr(sc), B, ctx.invert, ptr(dT), ptr(daa), ptr(dtr), ptr(dsc),
+                                  stream_ptr()), "sqlx_pose_bwd")
+        s_aa, s_tr, s_sc = ctx.shapes
+        return daa.reshape(s_aa), dtr.reshape(s_tr), (dsc.reshape(s_sc) if dsc is not None else None), None
+
+
+def pose_matrix(axisangle, translation, scale=None, invert=False):
+    """axisangle, translation: [B,1,3] (or [B,3]); scale: [B] or None -> [B,4,4]."""
+    return _PoseMatrix.apply(axisangle, translation, scale, invert)
+
+
+def reprojection_loss(pred, target, *, no_ssim=False, ssim_radius=3, w_ssim=0.85, w_l1=0.15):
+    """Forward-only compute_reprojection_loss (trainer.py:441-453) -> [B,1,H,W]; used for the identity losses."""
+    require_cuda(pred, target)
+    p, t = _f32c(pred), _f32c(target)
+    B, C, H, W = p.shape
+    assert C == 3 and t.shape == p.shape
+    out = torch.empty(B, 1, H, W, device=p.device, dtype=torch.float32)
+    check(lib().sqlx_reprojection_loss_fwd(ptr(p), ptr(t), B, H, W, ssim_radius, w_ssim, w_l1, int(no_ssim), ptr(out),
+                                           stream_ptr()), "sqlx_reprojection_loss_fwd")
+    return out
+
+
+class _Smooth(torch.autograd.Function):
+    """disp [B,1,h,w] (upsampled to the colour resolution when different), color [B,3,Hc,Wc] -> sums [B,3]."""
+
+    @staticmethod
+    def forward(ctx, disp, color):
+        require_cuda(disp, color)
+        d, c = _f32c(disp), _f32c(color)
+        B, _, h, w = d.shape
+        Hc, Wc = c.shape[-2:]
+        sums = torch.empty(B, 3, device=d.device, dtype=torch.float32)
+        nbytes = lib().sqlx_smooth_workspace_bytes(B, Hc, Wc)
+        ws = torch.empty(nbytes, device=d.device, dtype=torch.uint8)
+        check(lib().sqlx_smooth_fwd(ptr(d), ptr(c), B, h, w, Hc, Wc, ptr(sums), ptr(ws), nbytes, stream_ptr()),
+              "sqlx_smooth_fwd")
+        ctx.save_for_backward(d, c)
+        return sums
+
+    @staticmethod
+    def backward(ctx, g):
+        d, c = ctx.saved_tensors
+        B, _, h, w = d.shape
+        Hc, Wc = c.shape[-2:]
+        out = torch.zeros_like(d)
+        g = g.contiguous().float()
+        check(lib().sqlx_smooth_bwd(ptr(d), ptr(c), B, h, w, Hc, Wc, ptr(g), ptr(out), stream_ptr()), "sqlx_smooth_bwd")
+        return out, None
+
+
+def smooth_loss_normalised(disp, color):
+    """get_smooth_loss(disp / (mean(disp)+1e-7), color) with the upsample of trainer.py:533-534 folded in."""
+    sums = _Smooth.apply(disp, color)
+    B = disp.shape[0]
+    Hc, Wc = color.shape[-2:]
+    mean = sums[:, 2] / float(Hc * Wc)
+    inv = 1.0 / (mean + 1e-7)
+    return (sums[:, 0] * inv).sum() / float(B * Hc * (Wc - 1)) + (sums[:, 1] * inv).sum() / float(B * (Hc - 1) * Wc)
+
+
+# ----------------------------------------------------------------------------- fused photometric loss
+class _PhotoLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth_lr, T, target, K, inv_K, identity, noise, cfg, *sources):
+        require_cuda(depth_lr, T, target, K, inv_K, identity, noise, *sources)
+        d = _f32c(depth_lr)
+        Tm = _f32c(T)
+        B, _, h, w = d.shape
+        H, W = target.shape[-2:]
+        S = len(sources)
+        desc = make_desc(B, H, W, h, w, S, **cfg)
+        srcs = [_f32c(s) for s in sources]
+        tgt, Kc, iKc = _f32c(target), _f32c(K), _f32c(inv_K)
+        ident, nz = _f32c(identity), _f32c(noise)
+        nbytes = lib().sqlx_photo_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(nbytes, device=d.device, dtype=torch.uint8)
+        loss_sum = torch.empty(1, device=d.device, dtype=torch.float32)
+        argmin = torch.empty(B, H, W, device=d.device, dtype=torch.uint8)
+        check(lib().sqlx_photo_fwd(ctypes.byref(desc), ptr(d), ptr(tgt), _src_array(srcs), ptr(Kc), ptr(iKc), ptr(Tm),
+                                   ptr(ident), ptr(nz), ptr(loss_sum), ptr(argmin), ptr(ws), nbytes, stream_ptr()),
+              "sqlx_photo_fwd")
+        ctx.save_for_backward(d, Tm, tgt, Kc, iKc, argmin, *srcs)
+        ctx.desc = desc
+        ctx.mark_non_differentiable(argmin)
+        return loss_sum, argmin
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_argmin):
+        d, Tm, tgt, Kc, iKc, argmin, *srcs = ctx.saved_tensors
+        desc = ctx.desc
+        nbytes = lib().sqlx_photo_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(nbytes, device=d.device, dtype=torch.uint8)
+        d_depth = torch.zeros_like(d)
+        d_T = torch.empty_like(Tm)
+        g = g_loss.contiguous().float()
+        check(lib().sqlx_photo_bwd(ctypes.byref(desc), ptr(d), ptr(tgt), _src_array(srcs), ptr(Kc), ptr(iKc), ptr(Tm),
+                                   ptr(argmin), ptr(g), 1.0, ptr(d_depth), ptr(d_T), ptr(ws), nbytes, stream_ptr()),
+              "sqlx_photo_bwd")
+        return (d_depth, d_T, None, None, None, None, None, None) + (None,) * len(srcs)
+
+
+def warp(depth_lr, source, K, inv_K, T, H, W, *, want_depth=True, want_sample=True, want_color=True, eps=1e-7):
+    """Materialise outputs[("depth",0,s)], ("sample",f,s), ("color",f,s) for logging (no autograd)."""
+    require_cuda(depth_lr, source, K, inv_K, T)
+    d, src, Kc, iKc, Tm = _f32c(depth_lr), _f32c(source), _f32c(K), _f32c(inv_K), _f32c(T)
+    B, _, h, w = d.shape
+    dev = d.device
+    depth_up = torch.empty(B, 1, H, W, device=dev) if want_depth else None
+    sample = torch.empty(B, H, W, 2, device=dev) if want_sample else None
+    color = torch.empty(B, 3, H, W, device=dev) if want_color else None
+    check(lib().sqlx_warp_fwd(ptr(d), ptr(src), ptr(Kc), ptr(iKc), ptr(Tm), 16, B, h, w, H, W, eps,
+                              ptr(depth_up), ptr(sample), ptr(color), stream_ptr()), "sqlx_warp_fwd")
+    return depth_up, sample, color
+
+
+def photometric_losses(disps, target_pyr, sources, K, inv_K, poses, noises, *, height, width, scales=(0,),
+                       disparity_smoothness=1e-3, rescale_translation=True, no_ssim=False, avg_reprojection=False,
+                       disable_automasking=False, ssim_radius=3, materialize=False, identity=None):
+    """generate_images_pred + compute_losses (trainer.py:386-549) on the fused kernels.
+
+    Arguments: see the parameter list of the CPU restatement used by tests/.  `noises[s]` may be None: the tie-break
+    noise is then drawn on the device (the reference draws it on the CPU generator, trainer.py:516).
+    """
+    H, W = height, width
+    S = len(sources)
+    target = target_pyr[0]
+    B = target.shape[0]
+    automask = not disable_automasking
+    cfg = dict(ssim_radius=ssim_radius, automask=automask, avg=avg_reprojection, no_ssim=no_ssim)
+    out = {}
+    if automask and identity is None:
+        identity = torch.cat([reprojection_loss(src, target, no_ssim=no_ssim, ssim_radius=ssim_radius)
+                              for src in sources], 1)
+    total = 0
+    for s in scales:
+        disp = disps[s]
+        stats = depth_stats(disp, H, W) if (rescale_translation and any("T" not in p for p in poses)) else None
+        Ts = []
+        for pose in poses:
+            if "T" in pose:
+                Ts.append(pose["T"].float())
+            else:
+                scale = stats[:, 1] if rescale_translation else None
+                Ts.append(pose_matrix(pose["axisangle"][:, 0], pose["translation"][:, 0], scale, pose["invert"]))
+        T = torch.stack(Ts, 1)
+        noise = None
+        if automask:
+            noise = noises.get(s) if noises is not None else None
+            if noise is None:
+                noise = torch.randn(B, 1 if avg_reprojection else S, H, W, device=target.device)
+        loss_sum, argmin = _PhotoLoss.apply(disp, T, target, K, inv_K, identity, noise, cfg, *sources)
+        loss = loss_sum[0] / float(B * H * W)
+        n_ident = 0 if not automask else (1 if avg_reprojection else S)
+        if automask:
+            out["identity_selection/%d" % s] = (argmin >= n_ident).float()
+        out[("argmin", s)] = argmin
+        sm = smooth_loss_normalised(disp, target_pyr[s])
+        out[("smooth", s)] = sm
+        loss = loss + disparity_smoothness * sm / (2 ** s)
+        out["loss/%d" % s] = loss
+        total = total + loss
+        if materialize:
+            for i, src in enumerate(sources):
+                depth_up, sample, color = warp(disp, src, K, inv_K, T[:, i], H, W)
+                out[("depth", 0, s)] = depth_up
+                out[("sample", i, s)] = sample
+                out[("color", i, s)] = color
+    out["loss"] = total / len(scales)
+    return out

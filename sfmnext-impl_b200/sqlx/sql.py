@@ -1,0 +1,224 @@
+"""Self Query Layer tail of the SQLdepth depth decoder on libsqlx kernels.
+
+Mirrors FullQueryLayer.forward (networks/layers.py:7-21) and the tail of Depth_Decoder_QueryTr.forward
+(networks/depth_decoder_QTR.py:47-74).  The [pixels x queries] self-cost volume and the [D x pixels]
+logits / probabilities never reach HBM: each kernel recomputes them tile by tile on chip.  The tiny bins
+MLP (nn.Linear x3) and the centres arithmetic stay in PyTorch (cuBLAS GEMV-ish work);
+autograd carries d_centers -> d_summary through them between the two backward kernels.
+"""
+import torch
+import torch.nn.functional as F
+
+from ._lib import check, lib, ptr, require_cuda, stream_ptr
+
+
+def _f32c(t):
+    return t.detach().contiguous().float() if t is not None else None
+
+
+def _workspace(B, E, Q, D, n, device):
+    nbytes = lib().sqlx_sql_workspace_bytes(B, E, Q, D, n)
+    return torch.empty(nbytes, device=device, dtype=torch.uint8), nbytes
+
+
+def summary_fwd(x, queries, want_energy=False):
+    """x [B,E,h,w], queries [B,Q,E] -> summary [B,Q,E], row_max [B,Q], row_sum [B,Q], energy [B,Q,h,w] | None."""
+    require_cuda(x, queries)
+    B, E, h, w = x.shape
+    Q = queries.shape[1]
+    if queries.shape[0] != B or queries.shape[2] != E:
+        # same guard as networks/layers.py:16
+        raise AssertionError("Number of channels in x and Embedding dimension (at dim 2) of K matrix must match")
+    n = h * w
+    dev = x.device
+    summary = torch.empty(B, Q, E, device=dev, dtype=torch.float32)
+    row_max = torch.empty(B, Q, device=dev, dtype=torch.float32)
+    row_sum = torch.empty(B, Q, device=dev, dtype=torch.float32)
+    energy = torch.empty(B, Q, h, w, device=dev, dtype=torch.float32) if want_energy else None
+    ws, nbytes = _workspace(B, E, Q, 0, n, dev)
+    check(lib().sqlx_sql_summary_fwd(ptr(x), ptr(queries), B, E, Q, n, ptr(summary), ptr(row_max), ptr(row_sum),
+                                     ptr(energy), ptr(ws), nbytes, stream_ptr()), "sqlx_sql_summary_fwd")
+    return summary, row_max, row_sum, energy
+
+
+def pred_fwd(x, queries, Wp, bp, centers):
+    require_cuda(x, queries, Wp, bp, centers)
+    B, E, h, w = x.shape
+    Q, D = queries.shape[1], Wp.shape[0]
+    pred = torch.empty(B, 1, h, w, device=x.device, dtype=torch.float32)
+    check(lib().sqlx_sql_pred_fwd(ptr(x), ptr(queries), ptr(Wp), ptr(bp), ptr(centers), B, E, Q, D, h * w, ptr(pred),
+                                  stream_ptr()), "sqlx_sql_pred_fwd")
+    return pred
+
+
+def bwd_reduce(x, queries, Wp, bp, centers, g_pred):
+    B, E, h, w = x.shape
+    Q, D = queries.shape[1], Wp.shape[0]
+    dev = x.device
+    d_centers = torch.empty(B, D, device=dev, dtype=torch.float32)
+    d_Wp = torch.empty(D, Q, device=dev, dtype=torch.float32)
+    d_bp = torch.empty(D, device=dev, dtype=torch.float32)
+    ws, nbytes = _workspace(B, E, Q, D, h * w, dev)
+    check(lib().sqlx_sql_bwd_reduce(ptr(x), ptr(queries), ptr(Wp), ptr(bp), ptr(centers), None, ptr(g_pred), B, E, Q, D,
+                                    h * w, ptr(d_centers), ptr(d_Wp), ptr(d_bp), ptr(ws), nbytes, stream_ptr()),
+          "sqlx_sql_bwd_reduce")
+    return d_centers, d_Wp, d_bp
+
+
+def bwd_dx(x, queries, Wp=None, bp=None, centers=None, g_pred=None, summary=None, row_max=None, row_sum=None,
+           d_summary=None, g_energy=None):
+    B, E, h, w = x.shape
+    Q = queries.shape[1]
+    D = Wp.shape[0] if Wp is not None else 0
+    dev = x.device
+    d_x = torch.empty_like(x)
+    d_q = torch.empty_like(queries)
+    ws, nbytes = _workspace(B, E, Q, D, h * w, dev)
+    check(lib().sqlx_sql_bwd_dx(ptr(x), ptr(queries), ptr(Wp), ptr(bp), ptr(centers), None, ptr(g_pred), ptr(summary),
+                                ptr(row_max), ptr(row_sum), ptr(d_summary), ptr(g_energy), B, E, Q, D, h * w,
+                                ptr(d_x), ptr(d_q), ptr(ws), nbytes, stream_ptr()), "sqlx_sql_bwd_dx")
+    return d_x, d_q
+
+
+# ----------------------------------------------------------------------------- module-level FullQueryLayer
+class _FullQuery(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, queries):
+        xc, qc = _f32c(x), _f32c(queries)
+        summary, row_max, row_sum, energy = summary_fwd(xc, qc, want_energy=True)
+        ctx.save_for_backward(xc, qc, summary, row_max, row_sum)
+        return energy, summary
+
+    @staticmethod
+    def backward(ctx, g_energy, g_summary):
+        xc, qc, summary, row_max, row_sum = ctx.saved_tensors
+        d_x, d_q = bwd_dx(xc, qc, summary=summary, row_max=row_max, row_sum=row_sum,
+                          d_summary=_f32c(g_summary), g_energy=_f32c(g_energy))
+        return d_x, d_q
+
+
+class FullQueryLayer(torch.nn.Module):
+    """Drop-in for networks.layers.FullQueryLayer (networks/layers.py:4-21): same signature, same outputs.
+    Materialises the energy maps (the reference API returns them); the fused decoder below does not."""
+
+    def forward(self, x, K):
+        return _FullQuery.apply(x, K)
+
+
+# ----------------------------------------------------------------------------- fused decoder tail
+def bin_centers(raw, min_val, max_val, norm="linear"):
+    """depth_decoder_QTR.py:51-66: regressor output [B,D] -> bin centres [B,D]."""
+    if norm == "linear":
+        y = torch.relu(raw) + 0.1
+    else:
+        y = torch.sigmoid(raw)
+    y = y / y.sum(dim=1, keepdim=True)
+    widths = (max_val - min_val) * y
+    widths = F.pad(widths, (1, 0), mode="constant", value=min_val)
+    edges = torch.cumsum(widths, dim=1)
+    return 0.5 * (edges[:, :-1] + edges[:, 1:])
+
+
+class _SqlTail(torch.autograd.Function):
+    """x, queries, Wp, bp -> pred, with the bins MLP evaluated by a caller-supplied closure.
+
+    forward : summary kernel -> centers = centers_fn(summary) (PyTorch) -> pred kernel
+    backward: reduce kernel (d_centers, d_Wp, d_bp) -> autograd through centers_fn (d_summary, MLP grads)
+              -> dx kernel (d_x, d_queries): two passes over x instead of the reference's ~10.
+    """
+
+    @staticmethod
+    def forward(ctx, x, queries, Wp, bp, centers_fn, n_params, *params):
+        xc, qc, Wc, bc = _f32c(x), _f32c(queries), _f32c(Wp), _f32c(bp)
+        summary, row_max, row_sum, _ = summary_fwd(xc, qc)
+        with torch.enable_grad():
+            s_leaf = summary.detach().requires_grad_(True)
+            centers = centers_fn(s_leaf)
+        cc = _f32c(centers)
+        pred = pred_fwd(xc, qc, Wc, bc, cc)
+        ctx.save_for_backward(xc, qc, Wc, bc, cc, summary, row_max, row_sum)
+        ctx.graph = (s_leaf, centers)
+        ctx.params = params
+        return pred
+
+    @staticmethod
+    def backward(ctx, g_pred):
+        xc, qc, Wc, bc, cc, summary, row_max, row_sum = ctx.saved_tensors
+        s_leaf, centers = ctx.graph
+        g = _f32c(g_pred)
+        d_centers, d_Wp, d_bp = bwd_reduce(xc, qc, Wc, bc, cc, g)
+        need = [p for p in ctx.params if p.requires_grad]
+        grads = torch.autograd.grad(centers, [s_leaf] + need, d_centers, allow_unused=True)
+        d_summary = grads[0]
+        if d_summary is None:
+            d_summary = torch.zeros_like(summary)
+        d_x, d_q = bwd_dx(xc, qc, Wc, bc, cc, g, summary, row_max, row_sum, _f32c(d_summary))
+        it = iter(grads[1:])
+        d_params = tuple((next(it) if p.requires_grad else None) for p in ctx.params)
+        ctx.graph = None
+        return (d_x, d_q, d_Wp.view_as(Wc), d_bp, None, None) + d_params
+
+
+def sql_tail(x, queries, Wp, bp, centers_fn, params=()):
+    """pred [B,1,h,w] = sum_d softmax_d(Wp (x^T K) + bp) * centers_fn(summary(x, K))."""
+    params = tuple(params)
+    return _SqlTail.apply(x, queries, Wp, bp, centers_fn, len(params), *params)
+
+
+class Depth_Decoder_QueryTr(torch.nn.Module):
+    """Drop-in for networks.Depth_Decoder_QueryTr (networks/depth_decoder_QTR.py:6-74): same constructor,
+    same parameter names / shapes (depth.pth strict-loads), same forward contract.  Patch embedding, the
+    4-layer transformer encoder and conv3x3 stay PyTorch (cuDNN/cuBLAS); lines 47-70 run on libsqlx."""
+
+    dim_feedforward = 1024
+
+    def __init__(self, in_channels, embedding_dim=128, patch_size=16, num_heads=4, query_nums=100, dim_out=256,
+                 norm="linear", min_val=0.001, max_val=10):
+        super().__init__()
+        nn = torch.nn
+        self.norm = norm
+        self.embedding_convPxP = nn.Conv2d(in_channels, embedding_dim, kernel_size=patch_size, stride=patch_size,
+                                           padding=0)
+        self.positional_encodings = nn.Parameter(torch.rand(500, embedding_dim), requires_grad=True)
+        layer = nn.TransformerEncoderLayer(embedding_dim, num_heads, dim_feedforward=self.dim_feedforward)
+        self.transformer_encoder = nn.TransformerEncoder(layer, num_layers=4)
+        self.conv3x3 = nn.Conv2d(in_channels, embedding_dim, kernel_size=3, stride=1, padding=1)
+        self.full_query_layer = FullQueryLayer()
+        self.bins_regressor = nn.Sequential(nn.Linear(embedding_dim * query_nums, 16 * query_nums), nn.LeakyReLU(),
+                                            nn.Linear(16 * query_nums, 16 * 16), nn.LeakyReLU(),
+                                            nn.Linear(16 * 16, dim_out))
+        self.convert_to_prob = nn.Sequential(nn.Conv2d(query_nums, dim_out, kernel_size=1, stride=1, padding=0),
+                                             nn.Softmax(dim=1))
+        self.query_nums = query_nums
+        self.min_val = min_val
+        self.max_val = max_val
+
+    def queries_and_features(self, x0):
+        """depth_decoder_QTR.py:37-45 (PyTorch): tokens -> first Q as queries [B,Q,E]; x = conv3x3(x0)."""
+        emb = self.embedding_convPxP(x0).flatten(2)
+        emb = emb + self.positional_encodings[:emb.shape[2], :].T.unsqueeze(0)
+        tokens = self.transformer_encoder(emb.permute(2, 0, 1))
+        x = self.conv3x3(x0)
+        queries = tokens[:self.query_nums, ...].permute(1, 0, 2)
+        return x, queries
+
+    def forward(self, x0):
+        x, queries = self.queries_and_features(x0)
+        if self.norm == "softmax":          # depth_decoder_QTR.py:55-56 returns (softmax(y), energy_maps)
+            energy, summary = self.full_query_layer(x, queries)
+            B, Q, E = summary.shape
+            return torch.softmax(self.bins_regressor(summary.view(B, Q * E)), dim=1), energy
+        conv = self.convert_to_prob[0]
+        Wp = conv.weight.view(conv.out_channels, conv.in_channels)
+
+        def centers_fn(summary):
+            B, Q, E = summary.shape
+            return bin_centers(self.bins_regressor(summary.view(B, Q * E)), self.min_val, self.max_val, self.norm)
+
+        pred = sql_tail(x, queries.contiguous(), Wp, conv.bias, centers_fn, tuple(self.bins_regressor.parameters()))
+        return {("disp", 0): pred}
+
+
+class Lite_Depth_Decoder_QueryTr(Depth_Decoder_QueryTr):
+    """networks/lite_depth_decoder_QTR.py: identical but dim_feedforward=512."""
+    dim_feedforward = 512

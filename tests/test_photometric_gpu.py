@@ -1,0 +1,150 @@
+"""Parity of the fused photometric CUDA path (through the C ABI) against the reference golden vectors
+and against the CPU oracle on seeded synthetic inputs.  Tolerances: loss 1e-5 absolute (BASELINE.json
+north_star), gradients relative to max|grad| (argmin flips make element-wise 1e-5
+meaningless for gradients)."""
+import numpy as np
+import pytest
+import torch
+
+from _cases import PHOTO_CASES, photo_case, synth_photo_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _to_dev(kw):
+    dev = "cuda"
+    out = dict(kw)
+    out["disps"] = {s: v.detach().to(dev).requires_grad_(True) for s, v in kw["disps"].items()}
+    out["target_pyr"] = {s: v.to(dev) for s, v in kw["target_pyr"].items()}
+    out["sources"] = [v.to(dev) for v in kw["sources"]]
+    out["K"], out["inv_K"] = kw["K"].to(dev), kw["inv_K"].to(dev)
+    poses = []
+    for p in kw["poses"]:
+        if "T" in p:
+            poses.append({"T": p["T"].to(dev)})
+        else:
+            poses.append({"axisangle": p["axisangle"].detach().to(dev).requires_grad_(True),
+                          "translation": p["translation"].detach().to(dev).requires_grad_(True),
+                          "invert": p["invert"]})
+    out["poses"] = poses
+    out["noises"] = {s: v.to(dev) for s, v in kw["noises"].items()}
+    return out
+
+
+def _grad_leaves(kw):
+    leaves = [kw["disps"][s] for s in kw["scales"]]
+    for p in kw["poses"]:
+        if "T" not in p:
+            leaves += [p["axisangle"], p["translation"]]
+    return leaves
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()     # (F.cosine_similarity clamps tiny norms to 1e-8)
+    return float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-300))
+
+
+@pytest.mark.parametrize("name", PHOTO_CASES)
+def test_golden(name):
+    import sqlx
+    kw, leaves, z, fids = photo_case(name)
+    g = _to_dev(kw)
+    out = sqlx.photometric_losses(**g, materialize=True)
+    assert abs(float(out["loss"]) - float(z["out_loss"])) < 1e-5
+    for s in kw["scales"]:
+        assert abs(float(out["loss/%d" % s]) - float(z["out_loss_s%d" % s])) < 1e-5
+        if not kw["disable_automasking"]:
+            sel = out["identity_selection/%d" % s].cpu().numpy().astype(np.uint8)
+            assert (sel != z["out_idsel_s%d" % s]).mean() < 2e-3
+        np.testing.assert_allclose(out[("depth", 0, s)].cpu().numpy(), z["out_depth_s%d" % s], rtol=1e-5, atol=1e-5)
+    s0 = kw["scales"][0]
+    for i, f in enumerate(fids[1:]):
+        np.testing.assert_allclose(out[("sample", i, s0)].cpu().numpy(), z["out_sample_%s_s%d" % (f, s0)], atol=1e-5)
+        np.testing.assert_allclose(out[("color", i, s0)].cpu().numpy(), z["out_color_%s_s%d" % (f, s0)], atol=1e-4)
+    gl = _grad_leaves(g)
+    grads = torch.autograd.grad(out["loss"], gl, allow_unused=True)
+    names = ["disp%d" % s for s in kw["scales"]]
+    for f in fids[1:]:
+        if f != "s":
+            names += ["axisangle_%d" % f, "translation_%d" % f]
+    for n, gr in zip(names, grads):
+        ref = torch.from_numpy(z["grad_" + n])
+        gr = torch.zeros_like(ref) if gr is None else gr.cpu()
+        assert _rel(gr, ref) < 2e-2, n
+        cos = _cos(gr, ref)
+        assert cos > 0.9995, n
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(seed=1, B=2, H=64, W=96, S=2, scales=(0,)),
+    dict(seed=2, B=1, H=50, W=70, S=2, scales=(0,)),            # ragged: not a multiple of the tile
+    dict(seed=3, B=2, H=64, W=128, S=3, scales=(0,), stereo=True),
+    dict(seed=4, B=1, H=64, W=96, S=1, scales=(0,)),
+    dict(seed=5, B=1, H=96, W=160, S=2, scales=(0, 1, 2, 3)),
+    dict(seed=6, B=2, H=48, W=64, S=2, scales=(0,), white_noise=True),
+])
+def test_oracle_fp64(cfg):
+    """CUDA fp32 vs the oracle evaluated in float64 on the same seeded inputs."""
+    import sqlx
+    from oracle import sqldepth_oracle as O
+    kw = synth_photo_case(**cfg)
+    g = _to_dev(kw)
+    out = sqlx.photometric_losses(**g)
+
+    def dbl(x):
+        return x.double()
+    kd = dict(kw)
+    kd["disps"] = {s: dbl(v).requires_grad_(True) for s, v in kw["disps"].items()}
+    kd["target_pyr"] = {s: dbl(v) for s, v in kw["target_pyr"].items()}
+    kd["sources"] = [dbl(v) for v in kw["sources"]]
+    kd["K"], kd["inv_K"] = dbl(kw["K"]), dbl(kw["inv_K"])
+    kd["poses"] = [({"T": dbl(p["T"])} if "T" in p else
+                    {"axisangle": dbl(p["axisangle"]).requires_grad_(True),
+                     "translation": dbl(p["translation"]).requires_grad_(True), "invert": p["invert"]})
+                   for p in kw["poses"]]
+    kd["noises"] = {s: dbl(v) for s, v in kw["noises"].items()}
+    ref = O.photometric_losses(**kd)
+    assert abs(float(out["loss"]) - float(ref["loss"])) < 1e-5
+    for s in kw["scales"]:
+        a = out["identity_selection/%d" % s].cpu()
+        b = ref["identity_selection/%d" % s].float()
+        assert float((a != b).float().mean()) < 2e-3
+    gl, rl = _grad_leaves(g), _grad_leaves(kd)
+    gg = torch.autograd.grad(out["loss"], gl)
+    rg = torch.autograd.grad(ref["loss"], rl)
+    for a, b in zip(gg, rg):
+        tol = 0.1 if cfg.get("white_noise") else 3e-2
+        assert _rel(a.cpu().double(), b) < tol
+        cos = _cos(a.cpu(), b)
+        assert cos > (0.99 if cfg.get("white_noise") else 0.999)
+
+
+def test_full_size_properties():
+    """BASELINE config-2 size (B=12, 192x640, S=2): size-independent properties instead of the slow oracle.
+    (1) identical source and target with identity pose => warped == source, reprojection loss == identity loss;
+    (2) the loss is invariant to permuting the batch; (3) gradients vanish where the auto-mask rejects."""
+    import sqlx
+    kw = synth_photo_case(seed=9, B=12, H=192, W=640, S=2)
+    g = _to_dev(kw)
+    out = sqlx.photometric_losses(**g)
+    perm = torch.randperm(12)
+    gp = _to_dev(kw)
+    gp["disps"] = {s: v.detach()[perm.cuda()].requires_grad_(True) for s, v in gp["disps"].items()}
+    gp["target_pyr"] = {s: v[perm.cuda()] for s, v in gp["target_pyr"].items()}
+    gp["sources"] = [v[perm.cuda()] for v in gp["sources"]]
+    gp["noises"] = {s: v[perm.cuda()] for s, v in gp["noises"].items()}
+    for p in gp["poses"]:
+        p["axisangle"] = p["axisangle"].detach()[perm.cuda()]
+        p["translation"] = p["translation"].detach()[perm.cuda()]
+    outp = sqlx.photometric_losses(**gp)
+    assert abs(float(out["loss"]) - float(outp["loss"])) < 1e-6
+    (gd,) = torch.autograd.grad(out["loss"], [g["disps"][0]])
+    assert torch.isfinite(gd).all()
+    # zero motion: warped image equals the source exactly
+    T = torch.eye(4, device="cuda").repeat(12, 1, 1)
+    _, _, color = sqlx.warp(g["disps"][0], g["sources"][0], g["K"], g["inv_K"], T, 192, 640)
+    assert float((color - g["sources"][0]).abs().max()) < 2e-4

@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the SQLdepth training hot path (BASELINE.json metric: train frames/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path (libsqlx)
+  python bench.py --impl reference [...]                         the reference's CPU path (oracle port)
+
+One "step" = SQL decoder tail forward -> photometric losses (4 loss scales) forward -> backward of both, on one
+batch of synthetic KITTI-shape 3-frame inputs (BASELINE config 2: batch 12 per GPU, 192x640, decoder features
+32x96x320, Q = D = 64).  frames/s = target frames processed per second = batch / step time (trainer.py:584).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the byte accounting behind `roofline`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "sfmnext-impl_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+METRIC = "train_frames_per_sec_hot_path_192x640"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="sqlx", choices=["sqlx", "reference"])
+    ap.add_argument("--batch", type=int, default=12, help="batch per GPU (BASELINE config 2: 12)")
+    ap.add_argument("--height", type=int, default=192)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--queries", type=int, default=64)
+    ap.add_argument("--bins", type=int, default=64)
+    ap.add_argument("--scales", type=int, default=4, help="number of loss scales (BASELINE config 2: 4)")
+    ap.add_argument("--no-graph", action="store_true", help="submit the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------- synthetic data
+def make_host_batch(cfg, seed, pin):
+    """Seeded KITTI-shape synthetic batch on the host (SURVEY 8d recipe): smooth frames, KITTI intrinsics,
+    PoseCNN-scale poses, decoder-feature-like x and queries."""
+    from _cases import smooth_images, kitti_K, depth_like
+    g = torch.Generator().manual_seed(seed)
+    c = cfg
+    frames = smooth_images(g, c.B, c.H, c.W, c.S + 1)
+    mid = (c.S + 1) // 2
+    hb = {"target": frames[mid]}
+    for i, fr in enumerate([f for j, f in enumerate(frames) if j != mid]):
+        hb["source%d" % i] = fr
+    hb["K"], hb["inv_K"] = kitti_K(c.B, c.H, c.W)
+    hb["x"] = torch.randn(c.B, c.E, c.h, c.w, generator=g)
+    hb["queries"] = 0.4 * torch.randn(c.B, c.Q, c.E, generator=g)
+    for i in range(c.S):
+        hb["axisangle%d" % i] = 0.01 * torch.randn(c.B, 1, 1, 3, generator=g)
+        hb["translation%d" % i] = 0.01 * torch.randn(c.B, 1, 1, 3, generator=g)
+    for s in c.scales:
+        hb["noise%d" % s] = torch.randn(c.B, c.S, c.H, c.W, generator=g)
+        if s > 0:
+            hs, ws = c.scale_hw(s)
+            hb["disp%d" % s] = depth_like(g, c.B, hs, ws)
+            hb["target%d" % s] = F.interpolate(hb["target"], [c.H // 2 ** s, c.W // 2 ** s], mode="bilinear",
+                                               align_corners=False)
+    hb = {k: v.contiguous().float() for k, v in hb.items()}
+    if pin:
+        hb = {k: v.pin_memory() for k, v in hb.items()}
+    return hb
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step_factory(cfg, hb, mlp_state):
+    """The reference's CPU path for the same step, restated by oracle/sqldepth_oracle.py (same ATen primitives as
+    the reference: matmul, softmax, F.interpolate, F.grid_sample, avg_pool2d), autograd backward included."""
+    from oracle import sqldepth_oracle as O
+    c = cfg
+    leaves = {k: hb[k].clone().requires_grad_(True) for k in ["x", "queries"] +
+              ["disp%d" % s for s in c.scales if s > 0] +
+              ["axisangle%d" % i for i in range(c.S)] + ["translation%d" % i for i in range(c.S)]}
+    params = {k: v.clone().requires_grad_(True) for k, v in mlp_state.items()}
+
+    def step():
+        for t in list(leaves.values()) + list(params.values()):
+            t.grad = None
+        mlp = [params["bins_regressor.%d.%s" % (i, k)] for i in (0, 2, 4) for k in ("weight", "bias")]
+        Wp = params["convert_to_prob.0.weight"].view(c.D, c.Q)
+        tail = O.sql_tail(leaves["x"], leaves["queries"], mlp, Wp, params["convert_to_prob.0.bias"], c.min_depth,
+                          c.max_depth)
+        disps = {s: (tail["pred"] if s == 0 else leaves["disp%d" % s]) for s in c.scales}
+        target_pyr = {s: (hb["target"] if s == 0 else hb["target%d" % s]) for s in c.scales}
+        poses = [{"axisangle": leaves["axisangle%d" % i], "translation": leaves["translation%d" % i], "invert": i == 0}
+                 for i in range(c.S)]
+        out = O.photometric_losses(disps, target_pyr, [hb["source%d" % i] for i in range(c.S)], hb["K"], hb["inv_K"],
+                                   poses, {s: hb["noise%d" % s] for s in c.scales}, height=c.H, width=c.W,
+                                   scales=c.scales, disparity_smoothness=c.disparity_smoothness)
+        out["loss"].backward()
+        return float(out["loss"].detach())
+    return step
+
+
+def time_cpu(cfg_full, args, steps, warmup):
+    from sqlx.hotpath import HotPathConfig
+    c = cfg_full
+    Bs = min(args.cpu_sample_batch, c.B)
+    cs = HotPathConfig(B=Bs, H=c.H, W=c.W, h=c.h, w=c.w, E=c.E, Q=c.Q, D=c.D, S=c.S, scales=c.scales,
+                       min_depth=c.min_depth, max_depth=c.max_depth)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hb = make_host_batch(cs, seed=1234, pin=False)
+    torch.manual_seed(0)
+    nn = torch.nn
+    conv = nn.Conv2d(c.Q, c.D, 1)
+    mlp = nn.Sequential(nn.Linear(c.E * c.Q, 16 * c.Q), nn.LeakyReLU(), nn.Linear(16 * c.Q, 256), nn.LeakyReLU(),
+                        nn.Linear(256, c.D))
+    state = {"convert_to_prob.0.weight": conv.weight.detach(), "convert_to_prob.0.bias": conv.bias.detach()}
+    for k, v in mlp.state_dict().items():
+        state["bins_regressor." + k] = v
+    step = cpu_reference_step_factory(cs, hb, state)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": Bs / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "batch %d of the same workload (%dx%d, %d loss scales, fwd+bwd), %d timed steps, torch CPU fp32 "
+                      "threads=%d" % (Bs, c.H, c.W, len(c.scales), steps, cores),
+            "ms_per_step": dt * 1e3}
+
+
+# --------------------------------------------------------------------------------------------- roofline
+def algorithmic_bytes(c):
+    """Compulsory fp32 bytes per launch of the two photometric kernels (Measurement)."""
+    N, S, B = c.H * c.W, c.S, c.B
+    per = {}
+    for s in c.scales:
+        hs, ws = c.scale_hw(s)
+        n = hs * ws
+        # fwd: depth_lr + target + S sources + S identity + S noise (reads), argmin u8 (write)
+        per[("photo_fwd_kernel", s)] = B * (4 * n + 12 * N + 12 * N * S + 4 * N * S + 4 * N * S + N)
+        # bwd: depth_lr + target + S sources + argmin (reads), d_depth_lr (write)
+        per[("photo_bwd_kernel", s)] = B * (4 * n + 12 * N + 12 * N * S + N + 4 * n)
+    return per
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from sqlx.hotpath import HotPath, HotPathConfig
+    H, W = args.height, args.width
+    cfg = HotPathConfig(B=args.batch, H=H, W=W, h=H // 2, w=W // 2, E=32, Q=args.queries, D=args.bins, S=2,
+                        scales=tuple(range(args.scales)))
+    config = {"workload": "BASELINE config 2 hot path: SQL decoder tail (x0 32x%dx%d, Q=%d, D=%d) + photometric loss "
+                          "(3-frame, %dx%d, %d loss scales: scale 0 = decoder output, coarser scales synthetic "
+                          "since the reference decoder emits scale 0 only), forward+backward"
+                          % (H // 2, W // 2, args.queries, args.bins, H, W, args.scales),
+              "batch_per_gpu": args.batch, "global_batch": args.batch * world, "height": H, "width": W,
+              "source_frames": 2, "loss_scales": args.scales, "parallelism": "dp%d" % world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = time_cpu(cfg, args, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 0,
+                "steps": max(1, args.steps), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": cb["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "gpu_launches": 0,
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import sqlx
+    from sqlx import _lib
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (use --impl reference for the CPU arm)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    assert sqlx.lib().sqlx_device_ok(local_rank) == 1, "libsqlx targets sm_100a (B200) only"
+
+    torch.manual_seed(0)
+    hp = HotPath(cfg, device=dev, use_graph=not args.no_graph)
+    if world > 1:   # identical initial weights on every rank
+        for p in hp.parameters():
+            dist.broadcast(p.data, 0)
+    hb = make_host_batch(cfg, seed=1234 + rank, pin=True)
+    h2d_bytes = hp.load(hb, non_blocking=False)
+    torch.cuda.synchronize()
+
+    # launches of OUR kernels in one step (counted eagerly; a graph replay re-issues the same nodes)
+    n0 = sqlx.lib().sqlx_launch_count()
+    hp.step_eager()
+    torch.cuda.synchronize()
+    launches_per_step = int(sqlx.lib().sqlx_launch_count() - n0)
+    if hp.use_graph:
+        hp.capture()
+
+    flat = None
+
+    def allreduce_grads():
+        nonlocal flat
+        if world == 1:
+            return
+        grads = hp.param_grads()
+        if flat is None:
+            flat = torch.empty(sum(g.numel() for g in grads), device=dev)
+        torch._foreach_copy_(list(flat.split([g.numel() for g in grads])), [g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        torch._foreach_copy_([g.view(-1) for g in grads], list(flat.split([g.numel() for g in grads])))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    def dev_step():
+        hp.step()
+        allreduce_grads()
+
+    loss_host = torch.zeros(1).pin_memory()
+
+    def e2e_step():
+        hp.load(hb, non_blocking=True)
+        hp.step()
+        allreduce_grads()
+        loss_host.copy_(hp.loss.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads the loss every step (trainer.py:242-262)
+
+    for _ in range(max(args.warmup, 3)):
+        dev_step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(dev_step, args.steps)
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-kernel device times: the same steps submitted eagerly with CUDA events around each main kernel
+    _lib.profile_enable(True)
+    for _ in range(min(args.steps, 20)):
+        hp.step_eager()
+    torch.cuda.synchronize()
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    dom = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
+    roofline = None
+    if dom in ("photo_fwd_kernel", "photo_bwd_kernel"):
+        cnt, tot_ms = prof[dom]
+        ab = algorithmic_bytes(cfg)
+        bytes_avg = sum(ab[(dom, s)] for s in cfg.scales) / len(cfg.scales)
+        achieved = bytes_avg / (tot_ms / cnt * 1e-3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "avg_launch_us": tot_ms / cnt * 1e3, "algorithmic_bytes_per_launch": bytes_avg,
+                    "timing": "CUDA events around each launch on the launching stream, eager submission of the same step"}
+    step_ms_kernels = sum(v[1] for v in prof.values()) / max(1, min(args.steps, 20))
+    kernels = {k: {"launches_per_step": v[0] / max(1, min(args.steps, 20)),
+                   "ms_per_step": v[1] / max(1, min(args.steps, 20))} for k, v in sorted(prof.items())}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = time_cpu(cfg, args, steps=3, warmup=1)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    total_bytes = sum(v.numel() * 4 for v in hb.values())
+    config["l2"] = ("no explicit flush: every step streams %.0f MB of inputs plus %.0f MB of gradients through a 126 MB L2"
+                    % (total_bytes / 1e6, (hb["x"].numel() * 4) / 1e6))
+    config["submission"] = "eager" if args.no_graph else "cuda_graph"
+    line = {"metric": METRIC, "value": cfg.B * world / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "e2e": {"value": cfg.B * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4},
+            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "kernels": kernels, "kernel_ms_per_step": step_ms_kernels, "loss": float(hp.loss)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,14 @@ const char* sqlx_last_error(void);
 int sqlx_version(void);
 /* 1 if the visible device is compute capability 10.x (the only target this library is built for) */
 int sqlx_device_ok(int device);
+/* kernels launched by this library in this process so far (bench.py reports the per-step difference) */
+unsigned long long sqlx_launch_count(void);
+
+/* Per-kernel device timing for bench.py's roofline figure: while enabled, every main kernel launch is
+ * bracketed by CUDA events on its stream (skipped during CUDA-graph capture).  sqlx_profile_report waits for
+ * the recorded events and writes "<kernel> <launches> <total_ms>\n" lines into buf; returns bytes written. */
+int sqlx_profile_enable(int on);
+int sqlx_profile_report(char* buf, size_t buf_bytes);
 
 /* ---------------------------------------------------------------------------------------------
  * Photometric block

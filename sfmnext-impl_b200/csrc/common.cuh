@@ -22,6 +22,19 @@ int check_launch(const char* what);
 
 constexpr int kNumSMs = 148;  // B200
 
+// Times the enclosed launches with CUDA events on `st` while sqlx_profile_enable(1) is in effect (core.cu).
+class ProfScope {
+ public:
+  ProfScope(const char* name, cudaStream_t st);
+  ~ProfScope();
+  ProfScope(const ProfScope&) = delete;
+  ProfScope& operator=(const ProfScope&) = delete;
+
+ private:
+  int idx_;
+  cudaStream_t st_;
+};
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // index reflection of nn.ReflectionPad2d: -1 -> 1, n -> n-2  (layers.py:26)

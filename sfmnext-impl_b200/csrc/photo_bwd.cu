@@ -390,6 +390,7 @@ int launch_photo_bwd(const PhotoBwdParams& p, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(ceil_div(p.d.W, kTW), ceil_div(p.d.H, kTH), p.d.B);
+  ProfScope prof("photo_bwd_kernel", st);
   kern<<<grid, kNT, C::smem_bytes, st>>>(p);
   return check_launch("photo_bwd_kernel");
 }
@@ -455,6 +456,7 @@ extern "C" int sqlx_smooth_fwd(const float* disp_lr, const float* color, int B, 
   SQLX_REQUIRE(workspace_bytes >= sqlx_smooth_workspace_bytes(B, Hc, Wc), "workspace too small");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* partial = reinterpret_cast<float*>(workspace);
+  ProfScope prof("smooth_fwd_kernel", st);
   smooth_fwd_kernel<<<dim3(kSmoothBlocksPerSample, B), 256, 0, st>>>(disp_lr, color, h, w, Hc, Wc, partial);
   if (int e = check_launch("smooth_fwd_kernel")) return e;
   reduce_rows_kernel<<<dim3(B, 3), 256, 0, st>>>(partial, kSmoothBlocksPerSample, 3, sums);
@@ -466,6 +468,7 @@ extern "C" int sqlx_smooth_bwd(const float* disp_lr, const float* color, int B, 
   SQLX_REQUIRE(disp_lr && color && g_sums && d_disp_lr, "NULL pointer argument");
   SQLX_REQUIRE(B > 0 && Hc > 1 && Wc > 1 && h > 0 && w > 0 && h <= Hc && w <= Wc, "bad shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ProfScope prof("smooth_bwd_kernel", st);
   smooth_bwd_kernel<<<dim3(kSmoothBlocksPerSample, B), 256, 0, st>>>(disp_lr, color, h, w, Hc, Wc, g_sums, d_disp_lr);
   return check_launch("smooth_bwd_kernel");
 }

@@ -391,6 +391,7 @@ int launch_photo_fwd(const PhotoFwdParams& p, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(ceil_div(p.d.W, kTW), ceil_div(p.d.H, kTH), p.d.B);
+  ProfScope prof("photo_fwd_kernel", st);
   kern<<<grid, kNT, C::smem_bytes, st>>>(p);
   return check_launch("photo_fwd_kernel");
 }
@@ -407,6 +408,7 @@ int launch_reproj(const float* pred, const float* target, int B, int C_, int H, 
     configured = true;
   }
   dim3 grid(ceil_div(W, kTW), ceil_div(H, kTH), B);
+  ProfScope prof("reproj_loss_kernel", st);
   kern<<<grid, kNT, smem, st>>>(pred, target, C_, H, W, w_ssim, w_l1, out);
   return check_launch("reproj_loss_kernel");
 }
@@ -506,6 +508,7 @@ extern "C" int sqlx_depth_stats_fwd(const float* depth_lr, int B, int h, int w, 
   SQLX_REQUIRE(workspace_bytes >= sqlx_depth_stats_workspace_bytes(B, H, W), "workspace too small");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* partial = reinterpret_cast<float*>(workspace);
+  ProfScope prof("depth_stats_kernel", st);
   depth_stats_kernel<<<dim3(kStatsBlocksPerSample, B), 256, 0, st>>>(depth_lr, h, w, H, W, partial);
   if (int e = check_launch("depth_stats_kernel")) return e;
   finalize_rows_kernel<<<dim3(B, 2), 256, 0, st>>>(partial, kStatsBlocksPerSample, 2, stats, 1.f / ((float)H * (float)W));
@@ -517,6 +520,7 @@ extern "C" int sqlx_depth_stats_bwd(const float* depth_lr, int B, int h, int w, 
   SQLX_REQUIRE(depth_lr && g_stats && d_depth_lr, "NULL pointer argument");
   SQLX_REQUIRE(B > 0 && H > 0 && W > 0 && h > 0 && w > 0 && h <= H && w <= W, "bad shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ProfScope prof("depth_stats_bwd_kernel", st);
   depth_stats_bwd_kernel<<<dim3(kStatsBlocksPerSample, B), 256, 0, st>>>(depth_lr, h, w, H, W, g_stats, d_depth_lr);
   return check_launch("depth_stats_bwd_kernel");
 }

@@ -653,7 +653,10 @@ int run_summary(const float* x, const float* queries, int B, int Q, int n, float
   const int QB = round_up(Q, 32), nsl = kNT / QB;
   const size_t smem = sizeof(float) * (size_t)nsl * QB * (E + 2);
   if (int e = set_smem(sql_summary_kernel<E>, smem)) return e;
-  sql_summary_kernel<E><<<dim3(c.chunks, B), kNT, smem, st>>>(x, queries, Q, n, c.tiles_per_chunk, ws);
+  {
+    ProfScope prof("sql_summary_kernel", st);
+    sql_summary_kernel<E><<<dim3(c.chunks, B), kNT, smem, st>>>(x, queries, Q, n, c.tiles_per_chunk, ws);
+  }
   if (int e = check_launch("sql_summary_kernel")) return e;
   sql_summary_combine_kernel<E><<<B, 128, 0, st>>>(ws, Q, c.chunks, summary, row_max, row_sum);
   if (int e = check_launch("sql_summary_combine_kernel")) return e;
@@ -674,6 +677,7 @@ int run_pred(const float* x, const float* queries, const float* Wp, const float*
   const ChunkPlan c = plan_chunks(B, n, 2 * kTileTarget);
   const size_t smem = sizeof(float) * TileSmem<E>::floats(Q, D);
   if (int e = set_smem(sql_pred_kernel<E>, smem)) return e;
+  ProfScope prof("sql_pred_kernel", st);
   sql_pred_kernel<E><<<dim3(c.chunks, B), kNT, smem, st>>>(x, queries, Wp, bp, centers, Q, D, n, c.tiles_per_chunk,
                                                            pred, nullptr);
   return check_launch("sql_pred_kernel");
@@ -690,11 +694,16 @@ int run_bwd_reduce(const float* x, const float* queries, const float* Wp, const 
   float* part_db = part_dc + (size_t)ctas * D;
   const size_t smem = sizeof(float) * (TileSmem<E>::floats(Q, D) + (size_t)kTP * kLD + 8 * 2 * kNJ);
   if (int e = set_smem(sql_bwd_reduce_kernel<E>, smem)) return e;
-  sql_bwd_reduce_kernel<E><<<dim3(c.chunks, B), kNT, smem, st>>>(x, queries, Wp, bp, centers, g_pred, Q, D, n,
-                                                                 c.tiles_per_chunk, part_dW, part_dc, part_db);
+  {
+    ProfScope prof("sql_bwd_reduce_kernel", st);
+    sql_bwd_reduce_kernel<E><<<dim3(c.chunks, B), kNT, smem, st>>>(x, queries, Wp, bp, centers, g_pred, Q, D, n,
+                                                                   c.tiles_per_chunk, part_dW, part_dc, part_db);
+  }
   if (int e = check_launch("sql_bwd_reduce_kernel")) return e;
   sum_partials_kernel<<<dim3(ceil_div(D * Q, 256), 1), 256, 0, st>>>(part_dW, ctas, D * Q, d_Wp);
+  if (int e = check_launch("sum_partials_kernel")) return e;
   sum_partials_kernel<<<dim3(ceil_div(D, 256), 1), 256, 0, st>>>(part_db, ctas, D, d_bp);
+  if (int e = check_launch("sum_partials_kernel")) return e;
   sum_partials_kernel<<<dim3(ceil_div(D, 256), B), 256, 0, st>>>(part_dc, c.chunks, D, d_centers);
   return check_launch("sum_partials_kernel");
 }
@@ -708,9 +717,12 @@ int run_bwd_dx(const float* x, const float* queries, const float* Wp, const floa
   const int Qp = round_up(Q, 8);
   const size_t smem = sizeof(float) * (TileSmem<E>::floats(Q, Wp ? D : 0) + (size_t)kTP * kLD + 2 * (size_t)Qp * E + 3 * kMaxQ);
   if (int e = set_smem(sql_bwd_dx_kernel<E>, smem)) return e;
-  sql_bwd_dx_kernel<E><<<dim3(c.chunks, B), kNT, smem, st>>>(x, queries, Wp, bp, centers, g_pred, summary, row_max,
-                                                             row_sum, d_summary, g_energy, Q, D, n, c.tiles_per_chunk,
-                                                             d_x, ws);
+  {
+    ProfScope prof("sql_bwd_dx_kernel", st);
+    sql_bwd_dx_kernel<E><<<dim3(c.chunks, B), kNT, smem, st>>>(x, queries, Wp, bp, centers, g_pred, summary, row_max,
+                                                               row_sum, d_summary, g_energy, Q, D, n,
+                                                               c.tiles_per_chunk, d_x, ws);
+  }
   if (int e = check_launch("sql_bwd_dx_kernel")) return e;
   sum_partials_kernel<<<dim3(ceil_div(Q * E, 256), B), 256, 0, st>>>(ws, c.chunks, Q * E, d_queries);
   return check_launch("sum_partials_kernel");

@@ -32,6 +32,9 @@ _PROTOS = {
     "sqlx_last_error": (ctypes.c_char_p, []),
     "sqlx_version": (c_int, []),
     "sqlx_device_ok": (c_int, [c_int]),
+    "sqlx_launch_count": (ctypes.c_ulonglong, []),
+    "sqlx_profile_enable": (c_int, [c_int]),
+    "sqlx_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),
     "sqlx_depth_stats_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "sqlx_depth_stats_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sqlx_depth_stats_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -106,6 +109,24 @@ def check(code, what):
     if code != 0:
         msg = lib().sqlx_last_error()
         raise SqlxError("%s failed (%d): %s" % (what, code, msg.decode() if msg else "?"))
+
+
+def profile_enable(on=True):
+    """Bracket every main kernel launch with CUDA events (bench.py roofline leg)."""
+    check(lib().sqlx_profile_enable(int(bool(on))), "sqlx_profile_enable")
+
+
+def profile_report():
+    """{kernel name: (launches, total_ms)} for the launches recorded since the last report."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = lib().sqlx_profile_report(buf, len(buf))
+    if n < 0:
+        check(n, "sqlx_profile_report")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out
 
 
 def ptr(t):

@@ -1,0 +1,140 @@
+"""One training step of the hot path as a user-facing object: SQL decoder tail -> photometric losses ->
+backward, on static device buffers, optionally captured in a CUDA graph (the step is ~100 small launches
+around 10 large ones, so eager submission is CPU-launch-bound on a B200).
+
+What a step covers (reference lines): networks/depth_decoder_QTR.py:47-70, trainer.py:386-439 (generate_images_pred)
+and trainer.py:455-549 (compute_losses), then autograd back to the decoder features x, the queries, the 1x1
+conv / bins-MLP weights, the pose parameters and the coarser-scale depth maps.
+"""
+import torch
+
+from . import photometric as P
+from . import sql as S
+
+
+class HotPathConfig:
+    def __init__(self, B=12, H=192, W=640, h=96, w=320, E=32, Q=64, D=64, S=2, scales=(0, 1, 2, 3),
+                 min_depth=0.001, max_depth=80.0, disparity_smoothness=1e-3):
+        self.B, self.H, self.W, self.h, self.w = B, H, W, h, w
+        self.E, self.Q, self.D, self.S = E, Q, D, S
+        self.scales = tuple(scales)
+        self.min_depth, self.max_depth = min_depth, max_depth
+        self.disparity_smoothness = disparity_smoothness
+
+    def scale_hw(self, s):
+        """resolution of outputs[("disp", s)]: the decoder emits scale 0 at h x w; coarser scales are H/2^s."""
+        return (self.h, self.w) if s == 0 else (self.H // 2 ** s, self.W // 2 ** s)
+
+    def input_shapes(self):
+        c = self
+        shp = {"x": (c.B, c.E, c.h, c.w), "queries": (c.B, c.Q, c.E), "K": (c.B, 4, 4), "inv_K": (c.B, 4, 4),
+               "target": (c.B, 3, c.H, c.W)}
+        for i in range(c.S):
+            shp["source%d" % i] = (c.B, 3, c.H, c.W)
+            shp["axisangle%d" % i] = (c.B, 1, 1, 3)
+            shp["translation%d" % i] = (c.B, 1, 1, 3)
+        for s in c.scales:
+            shp["noise%d" % s] = (c.B, c.S, c.H, c.W)
+            if s > 0:
+                shp["disp%d" % s] = (c.B, 1) + c.scale_hw(s)
+                shp["target%d" % s] = (c.B, 3, c.H // 2 ** s, c.W // 2 ** s)
+        return shp
+
+
+class HotPath(torch.nn.Module):
+    """Parameters: the decoder's 1x1 conv (convert_to_prob.0) and bins_regressor.  Inputs live in static
+    device buffers `self.inp[name]` (see HotPathConfig.input_shapes); `load()` copies a host batch into them."""
+
+    def __init__(self, cfg, device="cuda", use_graph=True):
+        super().__init__()
+        nn = torch.nn
+        self.cfg = cfg
+        c = cfg
+        self.convert_to_prob = nn.Sequential(nn.Conv2d(c.Q, c.D, kernel_size=1), nn.Softmax(dim=1))
+        self.bins_regressor = nn.Sequential(nn.Linear(c.E * c.Q, 16 * c.Q), nn.LeakyReLU(),
+                                            nn.Linear(16 * c.Q, 256), nn.LeakyReLU(), nn.Linear(256, c.D))
+        self.to(device)
+        self.device = torch.device(device)
+        self.inp = {k: torch.zeros(v, device=device, dtype=torch.float32) for k, v in cfg.input_shapes().items()}
+        self.grad_inputs = ["x", "queries"] + ["disp%d" % s for s in c.scales if s > 0] + \
+                           ["axisangle%d" % i for i in range(c.S)] + ["translation%d" % i for i in range(c.S)]
+        for k in self.grad_inputs:
+            self.inp[k].requires_grad_(True)
+        self.use_graph = use_graph
+        self.graph = None
+        self.loss = None
+        self.pred = None
+
+    # ------------------------------------------------------------------ data
+    def load(self, host_batch, non_blocking=True):
+        """host_batch: {name: CPU tensor (pinned for async copies)}; returns the bytes copied."""
+        n = 0
+        with torch.no_grad():
+            for k, v in host_batch.items():
+                self.inp[k].copy_(v, non_blocking=non_blocking)
+                n += v.numel() * v.element_size()
+        return n
+
+    # ------------------------------------------------------------------ one eager step
+    def _centers(self, summary):
+        c = self.cfg
+        return S.bin_centers(self.bins_regressor(summary.reshape(c.B, c.Q * c.E)), c.min_depth, c.max_depth)
+
+    def forward_loss(self):
+        c, I = self.cfg, self.inp
+        conv = self.convert_to_prob[0]
+        pred = S.sql_tail(I["x"], I["queries"], conv.weight.view(c.D, c.Q), conv.bias, self._centers,
+                          tuple(self.bins_regressor.parameters()))
+        disps = {s: (pred if s == 0 else I["disp%d" % s]) for s in c.scales}
+        target_pyr = {s: (I["target"] if s == 0 else I["target%d" % s]) for s in c.scales}
+        sources = [I["source%d" % i] for i in range(c.S)]
+        poses = [{"axisangle": I["axisangle%d" % i], "translation": I["translation%d" % i], "invert": i == 0}
+                 for i in range(c.S)]
+        noises = {s: I["noise%d" % s] for s in c.scales}
+        out = P.photometric_losses(disps, target_pyr, sources, I["K"], I["inv_K"], poses, noises, height=c.H,
+                                   width=c.W, scales=c.scales, disparity_smoothness=c.disparity_smoothness)
+        return out["loss"], pred
+
+    def _zero_grads(self):
+        for p in self.parameters():
+            p.grad = None
+        for k in self.grad_inputs:
+            self.inp[k].grad = None
+
+    def step_eager(self):
+        self._zero_grads()
+        loss, pred = self.forward_loss()
+        loss.backward()
+        self.loss, self.pred = loss.detach(), pred.detach()
+        return self.loss
+
+    # ------------------------------------------------------------------ graph
+    def capture(self, warmup=3):
+        """Capture forward + backward into one CUDA graph (gradients land in static .grad tensors)."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step_eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._zero_grads()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            loss, pred = self.forward_loss()
+            loss.backward()
+            self.loss, self.pred = loss.detach(), pred.detach()
+        self.graph = g
+        return g
+
+    def step(self):
+        """Run one step on whatever is in the static input buffers; returns the (device) loss scalar."""
+        if self.use_graph:
+            if self.graph is None:
+                self.capture()
+            self.graph.replay()
+            return self.loss
+        return self.step_eager()
+
+    def param_grads(self):
+        return [p.grad for p in self.parameters() if p.grad is not None]

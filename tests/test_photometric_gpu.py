@@ -45,6 +45,8 @@ def _rel(a, b):
 
 def _cos(a, b):
     a, b = a.double().flatten(), b.double().flatten()     # (F.cosine_similarity clamps tiny norms to 1e-8)
+    if float(b.norm()) == 0.0:                             # e.g. a source frame the minimum never selects
+        return 1.0 if float(a.norm()) < 1e-12 else 0.0
     return float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-300))
 
 

@@ -191,17 +191,23 @@ def time_cpu(cfg_full, args, steps, warmup):
 
 # --------------------------------------------------------------------------------------------- roofline
 def algorithmic_bytes(c):
-    """Compulsory fp32 bytes per launch of the two photometric kernels (Measurement)."""
-    N, S, B = c.H * c.W, c.S, c.B
-    per = {}
-    for s in c.scales:
-        hs, ws = c.scale_hw(s)
-        n = hs * ws
-        # fwd: depth_lr + target + S sources + S identity + S noise (reads), argmin u8 (write)
-        per[("photo_fwd_kernel", s)] = B * (4 * n + 12 * N + 12 * N * S + 4 * N * S + 4 * N * S + N)
-        # bwd: depth_lr + target + S sources + argmin (reads), d_depth_lr (write)
-        per[("photo_bwd_kernel", s)] = B * (4 * n + 12 * N + 12 * N * S + N + 4 * n)
-    return per
+    """Compulsory fp32 bytes per launch of every main kernel ("Measurement"), averaged over the
+    loss scales for the per-scale kernels."""
+    N, S, B, E = c.H * c.W, c.S, c.B, c.E
+    n0 = c.h * c.w
+    ns = [c.scale_hw(s)[0] * c.scale_hw(s)[1] for s in c.scales]
+    n_avg = sum(ns) / len(ns)
+    return {
+        # depth_lr + target + S sources + S identity + S noise (reads); argmin u8 (write)
+        "photo_fwd_kernel": B * (4 * n_avg + 12 * N + 12 * N * S + 4 * N * S + 4 * N * S + N),
+        # depth_lr + target + S sources + argmin (reads); d_depth_lr (write)
+        "photo_bwd_kernel": B * (4 * n_avg + 12 * N + 12 * N * S + N + 4 * n_avg),
+        "reproj_loss_kernel": B * (24 * N + 4 * N),
+        "sql_summary_kernel": B * 4 * n0 * E,
+        "sql_pred_kernel": B * (4 * n0 * E + 4 * n0),
+        "sql_bwd_reduce_kernel": B * (4 * n0 * E + 4 * n0),
+        "sql_bwd_dx_kernel": B * (4 * n0 * E + 4 * n0 + 4 * n0 * E),
+    }
 
 
 def main():
@@ -261,18 +267,18 @@ def main():
     if hp.use_graph:
         hp.capture()
 
-    flat = None
+    bucket = None
 
     def allreduce_grads():
-        nonlocal flat
+        """the path's one exchange step: a single bucketed NCCL all-reduce (average) of the parameter gradients"""
+        nonlocal bucket
         if world == 1:
             return
         grads = hp.param_grads()
-        if flat is None:
-            flat = torch.empty(sum(g.numel() for g in grads), device=dev)
-        torch._foreach_copy_(list(flat.split([g.numel() for g in grads])), [g.reshape(-1) for g in grads])
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-        torch._foreach_copy_([g.view(-1) for g in grads], list(flat.split([g.numel() for g in grads])))
+        if bucket is None:
+            from sqlx.dist import GradBucket
+            bucket = GradBucket(grads)
+        bucket.allreduce_(grads)
 
     def barrier():
         if world > 1:
@@ -336,20 +342,31 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    dom = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
+    ab = algorithmic_bytes(cfg)
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
+        traffic = {k: v["dram_bytes_per_launch"] for k, v in tj["kernels"].items()}
+    except Exception:
+        pass
+    cand = {k: v for k, v in prof.items() if k in ab}
+    dom = max(cand.items(), key=lambda kv: kv[1][1])[0] if cand else None
     roofline = None
-    if dom in ("photo_fwd_kernel", "photo_bwd_kernel"):
+    if dom is not None:
         cnt, tot_ms = prof[dom]
-        ab = algorithmic_bytes(cfg)
-        bytes_avg = sum(ab[(dom, s)] for s in cfg.scales) / len(cfg.scales)
-        achieved = bytes_avg / (tot_ms / cnt * 1e-3) / 1e9
+        achieved = ab[dom] / (tot_ms / cnt * 1e-3) / 1e9
         roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "avg_launch_us": tot_ms / cnt * 1e3, "algorithmic_bytes_per_launch": bytes_avg,
-                    "timing": "CUDA events around each launch on the launching stream, eager submission of the same step"}
+                    "frac": achieved / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
+                    "avg_launch_us": tot_ms / cnt * 1e3, "algorithmic_bytes_per_launch": ab[dom],
+                    "share_of_kernel_time": tot_ms / sum(v[1] for v in prof.values()),
+                    "timing": "CUDA events around each launch on the launching stream (eager submission of the same "
+                              "steps after the timed region); traffic = dram bytes/launch from the committed ncu "
+                              "capture profiles/traffic_latest.json"}
     step_ms_kernels = sum(v[1] for v in prof.values()) / max(1, min(args.steps, 20))
     kernels = {k: {"launches_per_step": v[0] / max(1, min(args.steps, 20)),
-                   "ms_per_step": v[1] / max(1, min(args.steps, 20))} for k, v in sorted(prof.items())}
+                   "ms_per_step": v[1] / max(1, min(args.steps, 20)),
+                   "hbm_frac": (ab[k] / (v[1] / v[0] * 1e-3) / 1e9 / peak) if k in ab else None}
+               for k, v in sorted(prof.items())}
 
     cpu = None
     if not args.no_cpu_baseline:

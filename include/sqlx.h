@@ -171,6 +171,15 @@ int sqlx_sql_summary_fwd(const float* x, const float* queries, int B, int E, int
                          float* summary, float* row_max, float* row_sum, float* energy,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Tensor-core (tcgen05 / TMEM / TMA) variants.  sqlx_sql_tc_supported returns 1 when the shape is taken by the
+ * tensor-core kernels (E = 32, Q <= 128, D <= 128, n % 4 == 0); the fp32 entry points above/below dispatch to
+ * them automatically, so these are exported mainly for tests and profiling.
+ * sqlx_sql_energy_tc: energy[b,q,p] = sum_e x[b,e,p] queries[b,q,e] as 3xTF32 (networks/layers.py:17,20). */
+int sqlx_sql_tc_supported(int E, int Q, int D, int n);
+/* on = 0 forces the exact-fp32 CUDA-core kernels for every shape (A/B tests); returns the previous setting */
+int sqlx_sql_set_tensor_cores(int on);
+int sqlx_sql_energy_tc(const float* x, const float* queries, int B, int E, int Q, int n, float* energy, void* stream);
+
 /* Depth regression: pred[b,p] = sum_d softmax_d(Wp (x^T K)[p,:] + bp)[d] * centers[b,d]
  * replaces networks/layers.py:17,20 + depth_decoder_QTR.py:61,70 (1x1 conv, Softmax(dim=1), sum). */
 int sqlx_sql_pred_fwd(const float* x, const float* queries, const float* Wp /*[D,Q]*/, const float* bp /*[D]*/,

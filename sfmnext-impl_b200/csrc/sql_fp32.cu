@@ -611,7 +611,17 @@ __global__ void __launch_bounds__(kNT) sql_bwd_dx_kernel(
 // ------------------------------------------------------------------------------------------------
 using namespace sqlx;
 
+namespace sqlx {
+int tc_pred_fwd(const float* x, const float* queries, const float* Wp, const float* bp, const float* centers, int B,
+                int Q, int D, int n, float* pred, cudaStream_t st);
+}
+extern "C" int sqlx_sql_tc_supported(int E, int Q, int D, int n);
+extern "C" int sqlx_sql_set_tensor_cores(int on);
+
 namespace {
+
+int g_use_tc = 1;   // sqlx_sql_set_tensor_cores(0) forces the exact-fp32 CUDA-core kernels (tests, A/B timing)
+bool use_tensor_cores(int E, int Q, int D, int n) { return g_use_tc && sqlx_sql_tc_supported(E, Q, D, n); }
 
 int check_sql_shape(int B, int E, int Q, int D, int n, bool need_d) {
   SQLX_REQUIRE(B > 0 && n > 0, "non-positive shape (B=%d, n=%d)", B, n);
@@ -737,6 +747,12 @@ int run_bwd_dx(const float* x, const float* queries, const float* Wp, const floa
 
 }  // namespace
 
+extern "C" int sqlx_sql_set_tensor_cores(int on) {
+  const int prev = g_use_tc;
+  g_use_tc = on ? 1 : 0;
+  return prev;
+}
+
 extern "C" size_t sqlx_sql_workspace_bytes(int B, int E, int Q, int D, int n) {
   if (B <= 0 || E <= 0 || Q <= 0 || D < 0 || n <= 0) return 0;
   size_t f = summary_ws_floats(B, E, Q, n);
@@ -762,6 +778,7 @@ extern "C" int sqlx_sql_pred_fwd(const float* x, const float* queries, const flo
   if (int e = check_sql_shape(B, E, Q, D, n, true)) return e;
   SQLX_REQUIRE(x && queries && Wp && bp && centers && pred, "NULL pointer argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (use_tensor_cores(E, Q, D, n)) return tc_pred_fwd(x, queries, Wp, bp, centers, B, Q, D, n, pred, st);
   SQLX_DISPATCH_E(E, run_pred<kE>(x, queries, Wp, bp, centers, B, Q, D, n, pred, st));
 }
 

@@ -1,0 +1,471 @@
+// SQL block on the 5th-generation tensor cores (tcgen05 + TMEM), operands staged by TMA.
+//
+// Contractions (per 128-pixel tile, E = 32):
+//   Y[p,q]  = sum_e x[e,p] K[q,e]         A = x tile (MN-major: pixels contiguous, as NCHW holds it), B = K (K-major)
+//   Z[p,d]  = sum_q Y[p,q] Wp[d,q]        A = Y read straight from TMEM, B = Wp (K-major)
+// Precision: the 1e-4 depth bar rules out single-pass TF32 (2e-3), so both contractions
+// run as 3xTF32 (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32 accumulation in TMEM), which reproduces fp32.
+//
+// Reference lines: networks/layers.py:17-20, networks/depth_decoder_QTR.py:61,70.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+
+namespace sqlx {
+
+// ------------------------------------------------------------------------------------------------
+// host: tensor map through the driver entry point (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tensor_map_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                       uint32_t box_cols, int atom32) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) {
+      cudaGetLastError();
+      set_error("cuTensorMapEncodeTiled is not available from the driver");
+      return SQLX_ECUDA;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * sizeof(float)};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) for a [%llu x %llu] fp32 tensor", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols);
+    return SQLX_ECUDA;
+  }
+  return SQLX_OK;
+}
+
+namespace tcsql {
+
+using namespace tc;
+
+constexpr int kE = 32;           // embedding channels (K of the first contraction)
+constexpr int kTile = 128;       // pixels per tile = UMMA M
+constexpr int kThreads = 128;    // 4 warps: warp w owns TMEM lanes [32w, 32w+32)
+constexpr int kXBlock = 32 * kE * 4;         // one [32 e][32 px] SWIZZLE_128B block: 4096 B
+constexpr int kXTile = 4 * kXBlock;          // 128 pixels: 16 KB
+
+// shared-memory carve-up (all operand regions 1024-B aligned for SWIZZLE_128B)
+struct Smem {
+  uint8_t* x_raw;  // TMA landing zone for the NEXT tile (prefetched while the current tile is computed)
+  uint8_t* x_hi;   // [4 blocks][32 e][32 px]   TMA destination (SWIZZLE_128B_ATOM_32B), truncated in place
+  uint8_t* x_lo;   // same layout, x - hi
+  uint8_t* k_hi;   // [Qp rows][32 e]  K-major SW128
+  uint8_t* k_lo;
+  uint8_t* w_hi;   // [Qp/32 k-atoms][Dp rows][32 q]  K-major SW128 (also MN-major view for the transposed product)
+  uint8_t* w_lo;
+  float* bias;     // [Dp]
+  float* cen;      // [Dp]
+  uint64_t* bar_tma;
+  uint64_t* bar_mma;
+  uint32_t* tmem_slot;
+};
+
+__host__ __device__ inline size_t smem_bytes(int Qp, int Dp) {
+  return 1024 /*alignment slack*/ + 3 * kXTile + 2 * (size_t)Qp * 128 + 2 * (size_t)(Qp / 32 + (Qp % 32 ? 1 : 0)) * Dp * 128 +
+         2 * (size_t)(Dp > 0 ? Dp : 1) * sizeof(float) + 64;
+}
+
+__device__ __forceinline__ Smem carve(uint8_t* raw, int Qp, int Dp) {
+  Smem s;
+  uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  s.x_raw = p; p += kXTile;
+  s.x_hi = p; p += kXTile;
+  s.x_lo = p; p += kXTile;
+  s.k_hi = p; p += (size_t)Qp * 128;
+  s.k_lo = p; p += (size_t)Qp * 128;
+  const int katoms = (Qp + 31) / 32;
+  s.w_hi = p; p += (size_t)katoms * Dp * 128;
+  s.w_lo = p; p += (size_t)katoms * Dp * 128;
+  s.bias = reinterpret_cast<float*>(p); p += (size_t)(Dp > 0 ? Dp : 1) * sizeof(float);
+  s.cen = reinterpret_cast<float*>(p); p += (size_t)(Dp > 0 ? Dp : 1) * sizeof(float);
+  p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 7) & ~(uintptr_t)7);
+  s.bar_tma = reinterpret_cast<uint64_t*>(p); p += 8;
+  s.bar_mma = reinterpret_cast<uint64_t*>(p); p += 8;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(p);
+  return s;
+}
+
+// queries [Q][32] -> K-major SW128 hi / lo blocks with Qp rows (rows >= Q zero)
+__device__ __forceinline__ void stage_queries(const Smem& s, const float* __restrict__ qb, int Q, int Qp) {
+  for (int idx = threadIdx.x; idx < Qp * kE; idx += kThreads) {
+    const int q = idx >> 5, e = idx & 31;
+    const float v = q < Q ? __ldg(qb + idx) : 0.f;
+    const float hi = tf32_hi(v);
+    const uint32_t off = sw128_offset(q, e);
+    *reinterpret_cast<float*>(s.k_hi + off) = hi;
+    *reinterpret_cast<float*>(s.k_lo + off) = v - hi;
+  }
+}
+
+// Wp [D][Q] -> [k-atom a = q/32][Dp rows][32 q] SW128 hi / lo (rows >= D and cols >= Q zero)
+__device__ __forceinline__ void stage_wp(const Smem& s, const float* __restrict__ Wp, const float* __restrict__ bp,
+                                         const float* __restrict__ centers_b, int Q, int D, int Qp, int Dp) {
+  const int katoms = (Qp + 31) / 32;
+  for (int idx = threadIdx.x; idx < katoms * Dp * 32; idx += kThreads) {
+    const int a = idx / (Dp * 32), rem = idx - a * Dp * 32;
+    const int d = rem >> 5, c = rem & 31, q = a * 32 + c;
+    const float v = (d < D && q < Q) ? __ldg(Wp + (size_t)d * Q + q) : 0.f;
+    const float hi = tf32_hi(v);
+    const uint32_t off = (uint32_t)a * Dp * 128u + sw128_offset(d, c);
+    *reinterpret_cast<float*>(s.w_hi + off) = hi;
+    *reinterpret_cast<float*>(s.w_lo + off) = v - hi;
+  }
+  for (int d = threadIdx.x; d < Dp; d += kThreads) {
+    s.bias[d] = d < D ? __ldg(bp + d) : -INFINITY;   // padded bins never win the softmax
+    s.cen[d] = d < D ? __ldg(centers_b + d) : 0.f;
+  }
+}
+
+// split the freshly landed x tile (x_raw) into hi and lo operand tiles (same swizzled layout: elementwise)
+__device__ __forceinline__ void split_x_tile(const Smem& s) {
+  const float4* raw = reinterpret_cast<const float4*>(s.x_raw);
+  float4* hi = reinterpret_cast<float4*>(s.x_hi);
+  float4* lo = reinterpret_cast<float4*>(s.x_lo);
+#pragma unroll
+  for (int i = 0; i < kXTile / 16 / kThreads; ++i) {
+    const int idx = threadIdx.x + i * kThreads;
+    const float4 v = raw[idx];
+    float4 h, l;
+    h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+    hi[idx] = h;
+    lo[idx] = l;
+  }
+}
+
+// Y[128 px, Qp] = x^T K as 3xTF32 into TMEM columns [tm_y, tm_y + Qp).  One thread issues.
+__device__ __forceinline__ void issue_y(const Smem& s, uint32_t tm_y, int Qp) {
+  const uint32_t idesc = make_idesc_tf32(kTile, Qp, /*A MN-major*/ 1, /*B K-major*/ 0);
+  const uint32_t xh = smem_u32(s.x_hi), xl = smem_u32(s.x_lo), kh = smem_u32(s.k_hi), kl = smem_u32(s.k_lo);
+  uint32_t acc = 0;
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t xa = pass == 1 ? xl : xh;
+    const uint32_t kb = pass == 2 ? kl : kh;
+#pragma unroll
+    for (int k = 0; k < kE / 8; ++k) {
+      // A: MN-major (SWIZZLE_128B_BASE32B), 8 e-rows = 1024 B per k-step; 32-pixel blocks are 4096 B apart (LBO)
+      const uint64_t da = make_desc_mn32(xa + k * 1024, kXBlock);
+      // B: K-major, 8-row groups 1024 B apart (SBO); 8 e (32 B) per k-step inside the 128-B row
+      const uint64_t db = make_desc_sw128(kb + k * 32, 16, 1024);
+      umma_tf32_ss(tm_y, da, db, idesc, acc);
+      acc = 1;
+    }
+  }
+}
+
+// one 128-pixel x tile = four [32 e][32 px] boxes (out-of-range pixels are zero-filled by TMA)
+__device__ __forceinline__ void issue_x_tma(const Smem& s, const CUtensorMap* xmap, int p0, int row0) {
+  mbar_arrive_expect_tx(s.bar_tma, kXTile);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tma_load_2d(s.x_raw + j * kXBlock, xmap, p0 + 32 * j, row0, s.bar_tma);
+}
+
+// TMEM: split the fp32 accumulator columns [col, col+ncols) into hi (in place) and lo (at col_lo)
+__device__ __forceinline__ void split_tmem(uint32_t lane_base, uint32_t col, uint32_t col_lo, int ncols) {
+  for (int c = 0; c < ncols; c += 16) {
+    float v[16], l[16];
+    tmem_ld16(lane_base + col + c, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float h = tf32_hi(v[i]);
+      l[i] = v[i] - h;
+      v[i] = h;
+    }
+    tmem_st16(lane_base + col + c, v);
+    tmem_st16(lane_base + col_lo + c, l);
+  }
+  tmem_wait_st();
+}
+
+// Z[128 px, Dp] = Y Wp^T as 3xTF32: A = y_hi / y_lo in TMEM (K-major by construction), B = Wp (K-major SW128)
+__device__ __forceinline__ void issue_z(const Smem& s, uint32_t tm_z, uint32_t tm_yhi, uint32_t tm_ylo, int Qp, int Dp) {
+  const uint32_t idesc = make_idesc_tf32(kTile, Dp, 0, 0);
+  const uint32_t wh = smem_u32(s.w_hi), wl = smem_u32(s.w_lo);
+  uint32_t acc = 0;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t ya = pass == 1 ? tm_ylo : tm_yhi;
+    const uint32_t wb = pass == 2 ? wl : wh;
+    for (int k = 0; k < Qp / 8; ++k) {
+      // B: k-atom (32 q) blocks of Dp rows; 8 q (32 B) per k-step inside the 128-B row
+      const uint64_t db = make_desc_sw128(wb + (uint32_t)(k >> 2) * Dp * 128u + (uint32_t)(k & 3) * 32u, 16, 1024);
+      umma_tf32_ts(tm_z, ya + k * 8, db, idesc, acc);
+      acc = 1;
+    }
+  }
+}
+
+// softmax over the Dp logits of this thread's pixel (TMEM lane) and expected bin centre, one pass (online max)
+__device__ __forceinline__ float softmax_expect(const Smem& s, uint32_t lane_base, uint32_t tm_z, int Dp) {
+  float m = -INFINITY, se = 0.f, sc = 0.f;
+  for (int c = 0; c < Dp; c += 16) {
+    float v[16];
+    tmem_ld16(lane_base + tm_z + c, v);
+    tmem_wait_ld();
+    float cm = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      v[i] += s.bias[c + i];
+      cm = fmaxf(cm, v[i]);
+    }
+    if (cm > m) {
+      const float r = __expf(m - cm);
+      se *= r; sc *= r; m = cm;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float e = __expf(v[i] - m);
+      se += e;
+      sc = fmaf(e, s.cen[c + i], sc);
+    }
+  }
+  return sc / se;
+}
+
+// ------------------------------------------------------------------------------------------------
+// depth regression forward: pred[b,p] = sum_d softmax_d(Wp y + bp)[d] * centers[b,d]
+// TMEM columns: [0,Qp) y / y_hi   [Qp,2Qp) y_lo   [2Qp, 2Qp+Dp) logits
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) sql_tc_pred_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                               const float* __restrict__ queries,
+                                                               const float* __restrict__ Wp, const float* __restrict__ bp,
+                                                               const float* __restrict__ centers, int Q, int D, int Qp,
+                                                               int Dp, int n, int tiles_per_chunk, uint32_t tmem_cols,
+                                                               float* __restrict__ pred) {
+  extern __shared__ uint8_t smem_raw[];
+  const Smem s = carve(smem_raw, Qp, Dp);
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&xmap);
+    mbar_init(s.bar_tma, 1);
+    mbar_init(s.bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(s.tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  const int t_begin = blockIdx.x * tiles_per_chunk;
+  const int t_end = min((n + kTile - 1) / kTile, t_begin + tiles_per_chunk);
+  __syncthreads();   // barrier init visible before the first TMA
+  if (threadIdx.x == 0 && t_begin < t_end) issue_x_tma(s, &xmap, t_begin * kTile, b * kE);
+  stage_queries(s, queries + (size_t)b * Q * kE, Q, Qp);
+  stage_wp(s, Wp, bp, centers + (size_t)b * D, Q, D, Qp, Dp);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s.tmem_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tm_y = 0, tm_ylo = Qp, tm_z = 2 * Qp;
+  uint32_t ph_tma = 0, ph_mma = 0;
+  for (int t = t_begin; t < t_end; ++t) {
+    const int p0 = t * kTile;
+    mbar_wait(s.bar_tma, ph_tma); ph_tma ^= 1;
+    split_x_tile(s);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (t + 1 < t_end) issue_x_tma(s, &xmap, p0 + kTile, b * kE);
+      tc_fence_after();
+      issue_y(s, tmem + tm_y, Qp);
+      umma_commit(s.bar_mma);
+    }
+    mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    split_tmem(lane_base, tm_y, tm_ylo, Qp);
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      issue_z(s, tmem + tm_z, tmem + tm_y, tmem + tm_ylo, Qp, Dp);
+      umma_commit(s.bar_mma);
+    }
+    mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    const float pr = softmax_expect(s, lane_base, tm_z, Dp);
+    const int p = p0 + warp * 32 + lane;
+    if (p < n) pred[(size_t)b * n + p] = pr;
+    tc_fence_before();
+    __syncthreads();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// energy maps  y[b,q,p]   (module-level FullQueryLayer output; also the bring-up kernel of this file)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) sql_tc_energy_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                 const float* __restrict__ queries, int Q, int Qp,
+                                                                 int n, int tiles_per_chunk, uint32_t tmem_cols,
+                                                                 float* __restrict__ energy) {
+  extern __shared__ uint8_t smem_raw[];
+  const Smem s = carve(smem_raw, Qp, 0);
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&xmap);
+    mbar_init(s.bar_tma, 1);
+    mbar_init(s.bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(s.tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  const int t_begin = blockIdx.x * tiles_per_chunk;
+  const int t_end = min((n + kTile - 1) / kTile, t_begin + tiles_per_chunk);
+  __syncthreads();   // barrier init visible before the first TMA
+  if (threadIdx.x == 0 && t_begin < t_end) issue_x_tma(s, &xmap, t_begin * kTile, b * kE);
+  stage_queries(s, queries + (size_t)b * Q * kE, Q, Qp);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s.tmem_slot;
+  uint32_t phase = 0;
+  for (int t = t_begin; t < t_end; ++t) {
+    const int p0 = t * kTile;
+    mbar_wait(s.bar_tma, phase);
+    split_x_tile(s);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (t + 1 < t_end) issue_x_tma(s, &xmap, p0 + kTile, b * kE);   // x_raw is free again: prefetch
+      tc_fence_after();
+      issue_y(s, tmem, Qp);
+      umma_commit(s.bar_mma);
+    }
+    mbar_wait(s.bar_mma, phase);
+    tc_fence_after();
+    const int p = p0 + warp * 32 + lane;
+    for (int c = 0; c < Qp; c += 16) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+      tmem_wait_ld();
+      if (p < n) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c + i < Q) energy[((size_t)b * Q + c + i) * n + p] = v[i];
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // TMEM and the operand tiles are reused by the next iteration
+    phase ^= 1;
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+}  // namespace tcsql
+}  // namespace sqlx
+
+using namespace sqlx;
+
+namespace {
+uint32_t pow2_cols(int c) {
+  uint32_t v = 32;
+  while ((int)v < c) v <<= 1;
+  return v;
+}
+}  // namespace
+
+// 1 if the tensor-core kernels take this shape (otherwise the caller uses the fp32 kernels)
+extern "C" int sqlx_sql_tc_supported(int E, int Q, int D, int n) {
+  if (E != tcsql::kE || Q < 1 || Q > 128 || D < 0 || D > 128) return 0;
+  if (n % 4 != 0) return 0;   // TMA needs a 16-byte row pitch
+  return 1;
+}
+
+namespace {
+struct TcPlan {
+  int Qp, Dp, chunks, tpc;
+  uint32_t tmem_cols;
+  size_t smem;
+};
+// ctas_per_sm: how many CTAs of this kernel fit on one SM (shared memory / TMEM), used to size the grid
+TcPlan plan_tc(int B, int Q, int D, int n, int tmem_need_cols) {
+  TcPlan p;
+  p.Qp = (Q + 15) / 16 * 16;
+  p.Dp = D > 0 ? (D + 15) / 16 * 16 : 0;
+  p.tmem_cols = pow2_cols(tmem_need_cols);
+  p.smem = tcsql::smem_bytes(p.Qp, p.Dp);
+  int per_sm = (int)((227 * 1024) / (p.smem + 1024));
+  const int by_tmem = 512 / (int)p.tmem_cols;
+  per_sm = per_sm < by_tmem ? per_sm : by_tmem;
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  const int tiles = ceil_div(n, tcsql::kTile);
+  int chunks = (per_sm * kNumSMs) / B;
+  chunks = chunks < 1 ? 1 : (chunks > tiles ? tiles : chunks);
+  p.tpc = ceil_div(tiles, chunks);
+  p.chunks = ceil_div(tiles, p.tpc);
+  return p;
+}
+template <typename K>
+int raise_smem(K kern) {
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    return check_launch("cudaFuncSetAttribute");
+  return SQLX_OK;
+}
+}  // namespace
+
+namespace sqlx {
+// called by sqlx_sql_pred_fwd (sql_fp32.cu) when the shape is supported
+int tc_pred_fwd(const float* x, const float* queries, const float* Wp, const float* bp, const float* centers, int B,
+                int Q, int D, int n, float* pred, cudaStream_t st) {
+  SQLX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
+  const TcPlan p = plan_tc(B, Q, D, n, 2 * ((Q + 15) / 16 * 16) + (D + 15) / 16 * 16);
+  SQLX_REQUIRE(p.smem <= 227 * 1024 && p.tmem_cols <= 512, "shape exceeds the tensor-core kernel's on-chip budget");
+  CUtensorMap xmap;
+  if (int e = make_tensor_map_2d(&xmap, x, (uint64_t)B * tcsql::kE, (uint64_t)n, 32, 32, 1)) return e;
+  static bool configured = false;
+  if (!configured) {
+    if (int e = raise_smem(tcsql::sql_tc_pred_kernel)) return e;
+    configured = true;
+  }
+  ProfScope prof("sql_tc_pred_kernel", st);
+  tcsql::sql_tc_pred_kernel<<<dim3(p.chunks, B), tcsql::kThreads, p.smem, st>>>(xmap, queries, Wp, bp, centers, Q, D, p.Qp,
+                                                                               p.Dp, n, p.tpc, p.tmem_cols, pred);
+  return check_launch("sql_tc_pred_kernel");
+}
+}  // namespace sqlx
+
+extern "C" int sqlx_sql_energy_tc(const float* x, const float* queries, int B, int E, int Q, int n, float* energy,
+                                  void* stream) {
+  SQLX_REQUIRE(x && queries && energy, "NULL pointer argument");
+  SQLX_REQUIRE(B > 0 && B <= 65535 && n > 0, "bad shape B=%d n=%d", B, n);
+  SQLX_REQUIRE(sqlx_sql_tc_supported(E, Q, 0, n), "shape E=%d Q=%d n=%d is not supported by the tensor-core path", E, Q, n);
+  SQLX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const TcPlan p = plan_tc(B, Q, 0, n, (Q + 15) / 16 * 16);
+  CUtensorMap xmap;
+  if (int e = make_tensor_map_2d(&xmap, x, (uint64_t)B * E, (uint64_t)n, 32, 32, /*atom32=*/1)) return e;
+  static bool configured = false;
+  if (!configured) {
+    if (int e = raise_smem(tcsql::sql_tc_energy_kernel)) return e;
+    configured = true;
+  }
+  ProfScope prof("sql_tc_energy_kernel", st);
+  tcsql::sql_tc_energy_kernel<<<dim3(p.chunks, B), tcsql::kThreads, p.smem, st>>>(xmap, queries, Q, p.Qp, n, p.tpc,
+                                                                                 p.tmem_cols, energy);
+  return check_launch("sql_tc_energy_kernel");
+}

@@ -222,3 +222,18 @@ class Depth_Decoder_QueryTr(torch.nn.Module):
 class Lite_Depth_Decoder_QueryTr(Depth_Decoder_QueryTr):
     """networks/lite_depth_decoder_QTR.py: identical but dim_feedforward=512."""
     dim_feedforward = 512
+
+
+# ----------------------------------------------------------------------------- tensor-core entry points (tests / profiling)
+def tc_supported(E, Q, D, n):
+    return bool(lib().sqlx_sql_tc_supported(E, Q, D, n))
+
+
+def energy_tc(x, queries):
+    """energy [B,Q,h,w] = x^T K on tcgen05 (3xTF32).  Raises when the shape is not supported."""
+    require_cuda(x, queries)
+    B, E, h, w = x.shape
+    Q = queries.shape[1]
+    energy = torch.empty(B, Q, h, w, device=x.device, dtype=torch.float32)
+    check(lib().sqlx_sql_energy_tc(ptr(x), ptr(queries), B, E, Q, h * w, ptr(energy), stream_ptr()), "sqlx_sql_energy_tc")
+    return energy

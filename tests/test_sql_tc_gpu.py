@@ -1,0 +1,64 @@
+"""Tensor-core (tcgen05 / TMEM / TMA) SQL kernels against the float64 oracle and the exact-fp32 CUDA kernels."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, h=24, w=40, Q=64),
+    dict(B=1, h=17, w=20, Q=120),       # ragged last tile, Q padded to 128
+    dict(B=3, h=8, w=12, Q=16),         # fewer pixels than one tile
+    dict(B=2, h=96, w=320, Q=128),
+])
+def test_energy_tc(cfg):
+    from sqlx import sql as S
+    B, h, w, Q = cfg["B"], cfg["h"], cfg["w"], cfg["Q"]
+    g = torch.Generator().manual_seed(7 + Q)
+    x = torch.randn(B, 32, h, w, generator=g)
+    q = 0.5 * torch.randn(B, Q, 32, generator=g)
+    assert S.tc_supported(32, Q, 0, h * w)
+    en = S.energy_tc(x.cuda(), q.cuda())
+    ref = torch.einsum("bep,bqe->bqp", x.double().reshape(B, 32, -1), q.double()).reshape(B, Q, h, w)
+    err = float((en.cpu().double() - ref).abs().max())
+    # 3xTF32 reproduces fp32: |y| <= ~12 here, fp32 dot-product error is ~1e-6; single-pass TF32 would be ~5e-3
+    assert err < 2e-6 * float(ref.abs().max()) + 1e-5, err
+
+
+def _set_tc(on):
+    import sqlx
+    return sqlx.lib().sqlx_sql_set_tensor_cores(int(on))
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, h=24, w=40, Q=64, D=64),
+    dict(B=1, h=17, w=20, Q=120, D=128),      # cfg-1 style: Q padded to 128
+    dict(B=3, h=8, w=12, Q=12, D=16),         # golden-fixture sized
+    dict(B=2, h=96, w=320, Q=128, D=128),     # cfg-3 sized Q, D (one CTA per SM)
+    dict(B=12, h=96, w=320, Q=64, D=64),      # BASELINE config 2 full size
+])
+def test_pred_tc(cfg):
+    """tcgen05 pred kernel vs the float64 oracle (1e-4 relative, the north-star bar) and vs the fp32 CUDA kernel."""
+    from sqlx import sql as S
+    from oracle import sqldepth_oracle as O
+    B, h, w, Q, D = (cfg[k] for k in ("B", "h", "w", "Q", "D"))
+    g = torch.Generator().manual_seed(11 + Q + D)
+    x = torch.randn(B, 32, h, w, generator=g)
+    q = 0.4 * torch.randn(B, Q, 32, generator=g)
+    Wp = 0.3 * torch.randn(D, Q, generator=g)
+    bp = 0.1 * torch.randn(D, generator=g)
+    centers = torch.sort(0.1 + 80 * torch.rand(B, D, generator=g), dim=1).values
+    xc, qc, Wc, bc, cc = (t.cuda() for t in (x, q, Wp, bp, centers))
+    assert S.tc_supported(32, Q, D, h * w)
+    prev = _set_tc(1)
+    try:
+        pred_tc = S.pred_fwd(xc, qc, Wc, bc, cc)
+        _set_tc(0)
+        pred_fp = S.pred_fwd(xc, qc, Wc, bc, cc)
+    finally:
+        _set_tc(prev)
+    assert float(((pred_tc - pred_fp) / pred_fp).abs().max()) < 5e-5
+    if B * h * w <= 100000:
+        energy, _ = O.full_query(x.double(), q.double())
+        ref = O.bins_expectation(energy, Wp.double(), bp.double(), centers.double())
+        assert float(((pred_tc.cpu().double() - ref) / ref).abs().max()) < 1e-4

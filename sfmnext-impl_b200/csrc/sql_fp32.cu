@@ -612,11 +612,16 @@ __global__ void __launch_bounds__(kNT) sql_bwd_dx_kernel(
 using namespace sqlx;
 
 namespace sqlx {
+void tc_summary_plan(int B, int n, int* chunks, int* tiles_per_chunk);
+int tc_summary_partials(const float* x, const float* queries, int B, int Q, int n, float* partial, int* chunks_out,
+                        cudaStream_t st);
 int tc_pred_fwd(const float* x, const float* queries, const float* Wp, const float* bp, const float* centers, int B,
                 int Q, int D, int n, float* pred, cudaStream_t st);
 }
 extern "C" int sqlx_sql_tc_supported(int E, int Q, int D, int n);
 extern "C" int sqlx_sql_set_tensor_cores(int on);
+extern "C" int sqlx_sql_energy_tc(const float* x, const float* queries, int B, int E, int Q, int n, float* energy,
+                                  void* stream);
 
 namespace {
 
@@ -645,7 +650,10 @@ int set_smem(F kern, size_t bytes) {
 
 size_t summary_ws_floats(int B, int E, int Q, int n) {
   const ChunkPlan c = plan_chunks(B, n, kSummaryTarget);
-  return (size_t)B * c.chunks * Q * (E + 2);
+  int tc_chunks = 0, tpc = 0;
+  tc_summary_plan(B, n, &tc_chunks, &tpc);
+  const int chunks = c.chunks > tc_chunks ? c.chunks : tc_chunks;
+  return (size_t)B * chunks * Q * (E + 2);
 }
 size_t reduce_ws_floats(int B, int Q, int D, int n) {
   const ChunkPlan c = plan_chunks(B, n, kTileTarget);
@@ -770,6 +778,14 @@ extern "C" int sqlx_sql_summary_fwd(const float* x, const float* queries, int B,
   SQLX_REQUIRE(workspace && workspace_bytes >= sizeof(float) * summary_ws_floats(B, E, Q, n), "workspace too small");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* ws = reinterpret_cast<float*>(workspace);
+  if (use_tensor_cores(E, Q, 0, n)) {
+    int chunks = 0;
+    if (int e = tc_summary_partials(x, queries, B, Q, n, ws, &chunks, st)) return e;
+    sql_summary_combine_kernel<32><<<B, 128, 0, st>>>(ws, Q, chunks, summary, row_max, row_sum);
+    if (int e = check_launch("sql_summary_combine_kernel")) return e;
+    if (energy) return sqlx_sql_energy_tc(x, queries, B, E, Q, n, energy, stream);
+    return SQLX_OK;
+  }
   SQLX_DISPATCH_E(E, run_summary<kE>(x, queries, B, Q, n, summary, row_max, row_sum, energy, ws, st));
 }
 

@@ -313,6 +313,225 @@ __global__ void __launch_bounds__(kThreads) sql_tc_pred_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// pixel-softmax summaries, flash style with queries on the TMEM lanes:
+//   Y^T[q, px] = K x          A = K (K-major, M = 128 padded queries), B = x tile (MN-major, N = 64 pixels)
+//   S[q, e]    = P x^T        A = P = exp(Y^T - m_q) written back to TMEM (hi / lo), B = x tile (K-major over pixels)
+// thread = query keeps the running (max, sum, acc[32]) in registers; per-CTA partials -> split-softmax combine.
+// TMEM columns: [0,64) Y^T / P_hi   [64,128) P_lo   [128,160) S of the current tile
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileS = 64;                    // pixels per summary tile
+constexpr int kXTileS = 2 * kXBlock;          // 8 KB per layout
+
+struct SmemS {
+  uint8_t* raw_mn;   // TMA landing, SWIZZLE_128B_ATOM_32B (consumed MN-major by the first contraction)
+  uint8_t* raw_k;    // TMA landing, SWIZZLE_128B (consumed K-major over pixels by the second contraction)
+  uint8_t* mn_hi; uint8_t* mn_lo;
+  uint8_t* k_hi_x; uint8_t* k_lo_x;
+  uint8_t* q_hi; uint8_t* q_lo;   // queries [128 rows][32 e] K-major SW128
+  uint64_t* bar_tma; uint64_t* bar_mma;
+  uint32_t* tmem_slot;
+};
+constexpr size_t kSmemSBytes = 1024 + 6 * kXTileS + 2 * 128 * 128 + 64;
+
+__device__ __forceinline__ SmemS carve_s(uint8_t* raw) {
+  SmemS s;
+  uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  s.raw_mn = p; p += kXTileS;
+  s.raw_k = p; p += kXTileS;
+  s.mn_hi = p; p += kXTileS;
+  s.mn_lo = p; p += kXTileS;
+  s.k_hi_x = p; p += kXTileS;
+  s.k_lo_x = p; p += kXTileS;
+  s.q_hi = p; p += 128 * 128;
+  s.q_lo = p; p += 128 * 128;
+  s.bar_tma = reinterpret_cast<uint64_t*>(p); p += 8;
+  s.bar_mma = reinterpret_cast<uint64_t*>(p); p += 8;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(p);
+  return s;
+}
+
+__device__ __forceinline__ void issue_x_tma_s(const SmemS& s, const CUtensorMap* map_mn, const CUtensorMap* map_k, int p0,
+                                              int row0) {
+  mbar_arrive_expect_tx(s.bar_tma, 2 * kXTileS);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    tma_load_2d(s.raw_mn + j * kXBlock, map_mn, p0 + 32 * j, row0, s.bar_tma);
+    tma_load_2d(s.raw_k + j * kXBlock, map_k, p0 + 32 * j, row0, s.bar_tma);
+  }
+}
+
+__device__ __forceinline__ void split_tile(const uint8_t* raw, uint8_t* hi_, uint8_t* lo_, int bytes) {
+  const float4* r = reinterpret_cast<const float4*>(raw);
+  float4* hi = reinterpret_cast<float4*>(hi_);
+  float4* lo = reinterpret_cast<float4*>(lo_);
+  for (int idx = threadIdx.x; idx < bytes / 16; idx += kThreads) {
+    const float4 v = r[idx];
+    float4 h, l;
+    h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+    hi[idx] = h;
+    lo[idx] = l;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) sql_tc_summary_kernel(const __grid_constant__ CUtensorMap map_mn,
+                                                                  const __grid_constant__ CUtensorMap map_k,
+                                                                  const float* __restrict__ queries, int Q, int n,
+                                                                  int tiles_per_chunk,
+                                                                  float* __restrict__ partial /*[B][chunks][Q][34]*/) {
+  extern __shared__ uint8_t smem_raw[];
+  const SmemS s = carve_s(smem_raw);
+  const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  const int warp = threadIdx.x >> 5;
+  constexpr uint32_t kCols = 256;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_mn);
+    tma_prefetch_desc(&map_k);
+    mbar_init(s.bar_tma, 1);
+    mbar_init(s.bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(s.tmem_slot, kCols);
+    tmem_relinquish();
+  }
+  const int ntiles = (n + kTileS - 1) / kTileS;
+  const int t_begin = chunk * tiles_per_chunk;
+  const int t_end = min(ntiles, t_begin + tiles_per_chunk);
+  __syncthreads();
+  if (threadIdx.x == 0 && t_begin < t_end) issue_x_tma_s(s, &map_mn, &map_k, t_begin * kTileS, b * kE);
+  // queries -> [128 rows][32] K-major SW128 hi / lo, rows >= Q zero
+  {
+    const float* qb = queries + (size_t)b * Q * kE;
+    for (int idx = threadIdx.x; idx < 128 * kE; idx += kThreads) {
+      const int q = idx >> 5, e = idx & 31;
+      const float v = q < Q ? __ldg(qb + idx) : 0.f;
+      const float hi = tf32_hi(v);
+      const uint32_t off = sw128_offset(q, e);
+      *reinterpret_cast<float*>(s.q_hi + off) = hi;
+      *reinterpret_cast<float*>(s.q_lo + off) = v - hi;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s.tmem_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t idesc1 = make_idesc_tf32(128, kTileS, 0, 1);   // A = K (K-major), B = x (MN-major)
+  const uint32_t idesc2 = make_idesc_tf32(128, kE, 0, 0);       // A = P (TMEM), B = x (K-major over pixels)
+  float m = -INFINITY, l = 0.f, acc[kE];
+#pragma unroll
+  for (int e = 0; e < kE; ++e) acc[e] = 0.f;
+  uint32_t ph_tma = 0, ph_mma = 0;
+  for (int t = t_begin; t < t_end; ++t) {
+    const int p0 = t * kTileS;
+    mbar_wait(s.bar_tma, ph_tma); ph_tma ^= 1;
+    split_tile(s.raw_mn, s.mn_hi, s.mn_lo, kXTileS);
+    split_tile(s.raw_k, s.k_hi_x, s.k_lo_x, kXTileS);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (t + 1 < t_end) issue_x_tma_s(s, &map_mn, &map_k, p0 + kTileS, b * kE);
+      tc_fence_after();
+      const uint32_t qh = smem_u32(s.q_hi), ql = smem_u32(s.q_lo), xh = smem_u32(s.mn_hi), xl = smem_u32(s.mn_lo);
+      uint32_t a = 0;
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t qa = pass == 1 ? ql : qh;
+        const uint32_t xb = pass == 2 ? xl : xh;
+#pragma unroll
+        for (int k = 0; k < kE / 8; ++k) {
+          umma_tf32_ss(tmem, make_desc_sw128(qa + k * 32, 16, 1024), make_desc_mn32(xb + k * 1024, kXBlock), idesc1, a);
+          a = 1;
+        }
+      }
+      umma_commit(s.bar_mma);
+    }
+    mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    // ---- this thread's query row: tile max, lazy rescale, P = exp(y - m) -> TMEM (hi in place, lo beside it)
+    const int valid = min(kTileS, n - p0);   // pixels >= n were zero-filled by TMA: exclude them
+    float tmax = -INFINITY;
+    for (int c = 0; c < kTileS; c += 16) {
+      float v[16];
+      tmem_ld16(lane_base + c, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (c + i < valid) tmax = fmaxf(tmax, v[i]);
+    }
+    float rs = 1.f;
+    if (tmax > m + 8.f) {          // lazy: the reference point only moves when exceeded by > 8 (exp args <= 8)
+      rs = __expf(m - tmax);       // m = -inf at first: 0
+      m = tmax;
+    }
+    float lsum = 0.f;
+    for (int c = 0; c < kTileS; c += 16) {
+      float v[16], lo[16];
+      tmem_ld16(lane_base + c, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float pe = (c + i < valid) ? __expf(v[i] - m) : 0.f;
+        lsum += pe;
+        const float h = tf32_hi(pe);
+        v[i] = h;
+        lo[i] = pe - h;
+      }
+      tmem_st16(lane_base + c, v);
+      tmem_st16(lane_base + kTileS + c, lo);
+    }
+    tmem_wait_st();
+    l = l * rs + lsum;
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t xh = smem_u32(s.k_hi_x), xl = smem_u32(s.k_lo_x);
+      uint32_t a = 0;
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t pa = tmem + (pass == 1 ? kTileS : 0);
+        const uint32_t xb = pass == 2 ? xl : xh;
+#pragma unroll
+        for (int k = 0; k < kTileS / 8; ++k) {
+          // B: [32 e rows][32 px] K-major blocks (one per 32 pixels); 8 px = 32 B per k-step
+          umma_tf32_ts(tmem + 2 * kTileS, pa + k * 8,
+                       make_desc_sw128(xb + (uint32_t)(k >> 2) * kXBlock + (uint32_t)(k & 3) * 32u, 16, 1024), idesc2, a);
+          a = 1;
+        }
+      }
+      umma_commit(s.bar_mma);
+    }
+    mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    {
+      float v[16];
+      tmem_ld16(lane_base + 2 * kTileS, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], rs, v[i]);
+      tmem_ld16(lane_base + 2 * kTileS + 16, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[16 + i] = fmaf(acc[16 + i], rs, v[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  const int q = threadIdx.x;
+  if (q < Q) {
+    float* out = partial + (((size_t)b * chunks + chunk) * Q + q) * (kE + 2);
+    out[0] = m; out[1] = l;
+#pragma unroll
+    for (int e = 0; e < kE; ++e) out[2 + e] = acc[e];
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kCols);
+}
+
+// ------------------------------------------------------------------------------------------------
 // energy maps  y[b,q,p]   (module-level FullQueryLayer output; also the bring-up kernel of this file)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) sql_tc_energy_kernel(const __grid_constant__ CUtensorMap xmap,
@@ -446,6 +665,40 @@ int tc_pred_fwd(const float* x, const float* queries, const float* Wp, const flo
   tcsql::sql_tc_pred_kernel<<<dim3(p.chunks, B), tcsql::kThreads, p.smem, st>>>(xmap, queries, Wp, bp, centers, Q, D, p.Qp,
                                                                                p.Dp, n, p.tpc, p.tmem_cols, pred);
   return check_launch("sql_tc_pred_kernel");
+}
+}  // namespace sqlx
+
+namespace sqlx {
+// chunk plan of the tensor-core summary kernel (shared with the workspace-size query in sql_fp32.cu)
+void tc_summary_plan(int B, int n, int* chunks, int* tiles_per_chunk) {
+  const int tiles = ceil_div(n, tcsql::kTileS);
+  int c = (2 * kNumSMs) / B;   // 2 CTAs per SM (shared memory 82 KB, 256 TMEM columns each)
+  c = c < 1 ? 1 : (c > tiles ? tiles : c);
+  *tiles_per_chunk = ceil_div(tiles, c);
+  *chunks = ceil_div(tiles, *tiles_per_chunk);
+}
+
+// writes per-chunk partial records [B][chunks][Q][34]; the caller runs the split-softmax combine
+int tc_summary_partials(const float* x, const float* queries, int B, int Q, int n, float* partial, int* chunks_out,
+                        cudaStream_t st) {
+  SQLX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
+  int chunks, tpc;
+  tc_summary_plan(B, n, &chunks, &tpc);
+  CUtensorMap map_mn, map_k;
+  if (int e = make_tensor_map_2d(&map_mn, x, (uint64_t)B * tcsql::kE, (uint64_t)n, 32, 32, 1)) return e;
+  if (int e = make_tensor_map_2d(&map_k, x, (uint64_t)B * tcsql::kE, (uint64_t)n, 32, 32, 0)) return e;
+  static bool configured = false;
+  if (!configured) {
+    if (int e = raise_smem(tcsql::sql_tc_summary_kernel)) return e;
+    configured = true;
+  }
+  {
+    ProfScope prof("sql_tc_summary_kernel", st);
+    tcsql::sql_tc_summary_kernel<<<dim3(chunks, B), tcsql::kThreads, tcsql::kSmemSBytes, st>>>(map_mn, map_k, queries, Q, n,
+                                                                                              tpc, partial);
+  }
+  *chunks_out = chunks;
+  return check_launch("sql_tc_summary_kernel");
 }
 }  // namespace sqlx
 

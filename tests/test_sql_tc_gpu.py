@@ -62,3 +62,37 @@ def test_pred_tc(cfg):
         energy, _ = O.full_query(x.double(), q.double())
         ref = O.bins_expectation(energy, Wp.double(), bp.double(), centers.double())
         assert float(((pred_tc.cpu().double() - ref) / ref).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, h=24, w=40, Q=64),
+    dict(B=1, h=17, w=20, Q=120),        # 340 pixels: ragged last 64-pixel tile
+    dict(B=3, h=2, w=6, Q=12),           # 12 pixels: a single partial tile
+    dict(B=12, h=96, w=320, Q=64),       # BASELINE config 2 full size
+    dict(B=2, h=160, w=512, Q=128),      # cfg-3 sized
+])
+def test_summary_tc(cfg):
+    """tcgen05 flash-style pixel-softmax summaries vs the float64 oracle and the fp32 CUDA kernel."""
+    from sqlx import sql as S
+    from oracle import sqldepth_oracle as O
+    B, h, w, Q = (cfg[k] for k in ("B", "h", "w", "Q"))
+    g = torch.Generator().manual_seed(23 + Q)
+    x = torch.randn(B, 32, h, w, generator=g)
+    q = 0.5 * torch.randn(B, Q, 32, generator=g)
+    xc, qc = x.cuda(), q.cuda()
+    prev = _set_tc(1)
+    try:
+        s_tc, m_tc, l_tc, _ = S.summary_fwd(xc, qc)
+        _set_tc(0)
+        s_fp, m_fp, l_fp, _ = S.summary_fwd(xc, qc)
+    finally:
+        _set_tc(prev)
+    scale = float(s_fp.abs().max())
+    assert float((s_tc - s_fp).abs().max()) < 2e-5 * max(scale, 1.0)
+    # the (max, sum) statistics may use different reference points; log-sum-exp must agree
+    lse_tc = m_tc + torch.log(l_tc)
+    lse_fp = m_fp + torch.log(l_fp)
+    assert float((lse_tc - lse_fp).abs().max()) < 1e-4
+    if B * h * w <= 100000:
+        _, ref = O.full_query(x.double(), q.double())
+        assert float((s_tc.cpu().double() - ref).abs().max()) < 2e-5 * max(scale, 1.0)

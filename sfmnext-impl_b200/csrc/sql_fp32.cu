@@ -617,6 +617,15 @@ int tc_summary_partials(const float* x, const float* queries, int B, int Q, int 
                         cudaStream_t st);
 int tc_pred_fwd(const float* x, const float* queries, const float* Wp, const float* bp, const float* centers, int B,
                 int Q, int D, int n, float* pred, cudaStream_t st);
+bool tc_bwd_supported(int Q, int D);
+void tc_bwd_plan(int B, int n, int* chunks, int* tiles_per_chunk);
+int tc_bwd_dx_partials(const float* x, const float* queries, const float* Wp, const float* bp, const float* centers,
+                       const float* g_pred, const float* summary, const float* row_max, const float* row_sum,
+                       const float* d_summary, int B, int Q, int D, int n, float* d_x, float* part_dK, int chunks, int tpc,
+                       cudaStream_t st);
+int tc_bwd_reduce_partials(const float* x, const float* queries, const float* Wp, const float* bp, const float* centers,
+                           const float* g_pred, int B, int Q, int D, int n, float* part_dW, float* part_dc,
+                           float* part_db, int chunks, int tpc, cudaStream_t st);
 }
 extern "C" int sqlx_sql_tc_supported(int E, int Q, int D, int n);
 extern "C" int sqlx_sql_set_tensor_cores(int on);
@@ -655,14 +664,16 @@ size_t summary_ws_floats(int B, int E, int Q, int n) {
   const int chunks = c.chunks > tc_chunks ? c.chunks : tc_chunks;
   return (size_t)B * chunks * Q * (E + 2);
 }
+int max_bwd_chunks(int B, int n) {
+  const ChunkPlan c = plan_chunks(B, n, kTileTarget);
+  int tc_chunks = 0, tpc = 0;
+  tc_bwd_plan(B, n, &tc_chunks, &tpc);
+  return c.chunks > tc_chunks ? c.chunks : tc_chunks;
+}
 size_t reduce_ws_floats(int B, int Q, int D, int n) {
-  const ChunkPlan c = plan_chunks(B, n, kTileTarget);
-  return (size_t)B * c.chunks * ((size_t)D * Q + 2 * D) + (size_t)2 * D;
+  return (size_t)B * max_bwd_chunks(B, n) * ((size_t)D * Q + 2 * D) + (size_t)2 * D;
 }
-size_t dx_ws_floats(int B, int E, int Q, int n) {
-  const ChunkPlan c = plan_chunks(B, n, kTileTarget);
-  return (size_t)B * c.chunks * Q * E;
-}
+size_t dx_ws_floats(int B, int E, int Q, int n) { return (size_t)B * max_bwd_chunks(B, n) * Q * E; }
 
 template <int E>
 int run_summary(const float* x, const float* queries, int B, int Q, int n, float* summary, float* row_max,
@@ -808,6 +819,23 @@ extern "C" int sqlx_sql_bwd_reduce(const float* x, const float* queries, const f
   SQLX_REQUIRE(workspace && workspace_bytes >= sizeof(float) * reduce_ws_floats(B, Q, D, n), "workspace too small");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* ws = reinterpret_cast<float*>(workspace);
+  if (use_tensor_cores(E, Q, D, n) && tc_bwd_supported(Q, D)) {
+    int chunks = 0, tpc = 0;
+    tc_bwd_plan(B, n, &chunks, &tpc);
+    const int ctas = B * chunks;
+    float* part_dW = ws;
+    float* part_dc = part_dW + (size_t)ctas * D * Q;
+    float* part_db = part_dc + (size_t)ctas * D;
+    if (int e = tc_bwd_reduce_partials(x, queries, Wp, bp, centers, g_pred, B, Q, D, n, part_dW, part_dc, part_db, chunks,
+                                       tpc, st))
+      return e;
+    sum_partials_kernel<<<dim3(ceil_div(D * Q, 256), 1), 256, 0, st>>>(part_dW, ctas, D * Q, d_Wp);
+    if (int e = check_launch("sum_partials_kernel")) return e;
+    sum_partials_kernel<<<dim3(ceil_div(D, 256), 1), 256, 0, st>>>(part_db, ctas, D, d_bp);
+    if (int e = check_launch("sum_partials_kernel")) return e;
+    sum_partials_kernel<<<dim3(ceil_div(D, 256), B), 256, 0, st>>>(part_dc, chunks, D, d_centers);
+    return check_launch("sum_partials_kernel");
+  }
   SQLX_DISPATCH_E(E, run_bwd_reduce<kE>(x, queries, Wp, bp, centers, g_pred, B, Q, D, n, d_centers, d_Wp, d_bp, ws, st));
 }
 
@@ -826,6 +854,15 @@ extern "C" int sqlx_sql_bwd_dx(const float* x, const float* queries, const float
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* ws = reinterpret_cast<float*>(workspace);
   if (!has_pred) { Wp = nullptr; bp = nullptr; centers = nullptr; }
+  if (has_pred && d_summary && !g_energy && use_tensor_cores(E, Q, D, n) && tc_bwd_supported(Q, D)) {
+    int chunks = 0, tpc = 0;
+    tc_bwd_plan(B, n, &chunks, &tpc);
+    if (int e = tc_bwd_dx_partials(x, queries, Wp, bp, centers, g_pred, summary, row_max, row_sum, d_summary, B, Q, D, n,
+                                   d_x, ws, chunks, tpc, st))
+      return e;
+    sum_partials_kernel<<<dim3(ceil_div(Q * E, 256), B), 256, 0, st>>>(ws, chunks, Q * E, d_queries);
+    return check_launch("sum_partials_kernel");
+  }
   SQLX_DISPATCH_E(E, run_bwd_dx<kE>(x, queries, Wp, bp, centers, g_pred, summary, row_max, row_sum, d_summary, g_energy,
                                     B, Q, D, n, d_x, d_queries, ws, st));
 }

@@ -532,6 +532,440 @@ __global__ void __launch_bounds__(kThreads) sql_tc_summary_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
+// backward, Q <= 64 and D <= 64 (both padded to 64): shared pieces
+// ------------------------------------------------------------------------------------------------
+constexpr int kQB = 64, kDB = 64;   // padded query / bin counts of the backward kernels
+
+// softmax over 64 logits held in TMEM columns [tm_z, tm_z+64) of this thread's lane.
+// On return z[d] = softmax probability, and the expected centre is returned.
+__device__ __forceinline__ float softmax64(const float* __restrict__ bias, const float* __restrict__ cen,
+                                           uint32_t lane_base, uint32_t tm_z, float (&z)[kDB]) {
+#pragma unroll
+  for (int c = 0; c < kDB; c += 16) {
+    float v[16];
+    tmem_ld16(lane_base + tm_z + c, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[c + i] = v[i] + bias[c + i];
+  }
+  float m = z[0];
+#pragma unroll
+  for (int d = 1; d < kDB; ++d) m = fmaxf(m, z[d]);
+  float se = 0.f, sc = 0.f;
+#pragma unroll
+  for (int d = 0; d < kDB; ++d) {
+    z[d] = __expf(z[d] - m);
+    se += z[d];
+    sc = fmaf(z[d], cen[d], sc);
+  }
+  const float inv = 1.f / se;
+#pragma unroll
+  for (int d = 0; d < kDB; ++d) z[d] *= inv;
+  return sc * inv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pass 1: d_centers, d_Wp, d_bp.  Per tile: y, logits, softmax as in the forward, then ONE
+// pixel-contraction  [dz^T ; (pi g)^T] (128 x 128 px)  x  [y | 1] (80 x 128 px)^T  accumulated in TMEM over all
+// tiles of the CTA:  rows 0..63 -> d_Wp[d, q] (cols 0..63) and d_bp[d] (col 64); rows 64..127, col 64 -> d_centers[d].
+// TMEM columns: [0,64) y/y_hi  [64,128) y_lo  [128,192) logits  [192,272) accumulator
+// ------------------------------------------------------------------------------------------------
+constexpr int kRedN = kQB + 16;                                   // y columns + ones column (+ padding to 16)
+constexpr size_t kSmemRedBytes = 1024 + 3 * kXTile + 2 * kQB * 128 + 2 * 2 * kDB * 128 + 4 * 128 * 128 +
+                                 4 * kRedN * 128 + 2 * kDB * 4 + 64 + 1024;
+
+__global__ void __launch_bounds__(kThreads) sql_tc_bwd_reduce_kernel(
+    const __grid_constant__ CUtensorMap xmap, const float* __restrict__ queries, const float* __restrict__ Wp,
+    const float* __restrict__ bp, const float* __restrict__ centers, const float* __restrict__ g_pred, int Q, int D,
+    int n, int tiles_per_chunk, float* __restrict__ part_dW, float* __restrict__ part_dc, float* __restrict__ part_db) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem s = carve(smem_raw, kQB, kDB);
+  // extra operand tiles after the common carve-up (1024-aligned)
+  uint8_t* extra = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s.tmem_slot) + 4 + 1023) & ~(uintptr_t)1023);
+  uint8_t* adz = extra;                       // [4 px-atoms][128 rows][32 px]  rows 0..63 dz, 64..127 pi*g
+  uint8_t* by = adz + 4 * 128 * 128;          // [4 px-atoms][80 rows][32 px]   rows 0..63 y, row 64 ones, rest zero
+  const int b = blockIdx.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kCols = 512;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&xmap);
+    mbar_init(s.bar_tma, 1);
+    mbar_init(s.bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(s.tmem_slot, kCols);
+    tmem_relinquish();
+  }
+  const int t_begin = blockIdx.x * tiles_per_chunk;
+  const int t_end = min((n + kTile - 1) / kTile, t_begin + tiles_per_chunk);
+  __syncthreads();
+  if (threadIdx.x == 0 && t_begin < t_end) issue_x_tma(s, &xmap, t_begin * kTile, b * kE);
+  stage_queries(s, queries + (size_t)b * Q * kE, Q, kQB);
+  stage_wp(s, Wp, bp, centers + (size_t)b * D, Q, D, kQB, kDB);
+  for (int i = threadIdx.x; i < 4 * kRedN * 32; i += kThreads) {   // ones row / zero padding of the B tile
+    const int atom = i / (kRedN * 32), rem = i - atom * kRedN * 32, row = rem >> 5, col = rem & 31;
+    *reinterpret_cast<float*>(by + atom * kRedN * 128 + sw128_offset(row, col)) = row == kQB ? 1.f : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s.tmem_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  constexpr uint32_t tm_y = 0, tm_ylo = kQB, tm_z = 2 * kQB, tm_acc = 2 * kQB + kDB;
+  const uint32_t idesc3 = make_idesc_tf32(128, kRedN, 0, 0);
+  uint32_t ph_tma = 0, ph_mma = 0, acc3 = 0;
+  for (int t = t_begin; t < t_end; ++t) {
+    const int p0 = t * kTile;
+    mbar_wait(s.bar_tma, ph_tma); ph_tma ^= 1;
+    split_x_tile(s);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (t + 1 < t_end) issue_x_tma(s, &xmap, p0 + kTile, b * kE);
+      tc_fence_after();
+      issue_y(s, tmem + tm_y, kQB);
+      umma_commit(s.bar_mma);
+    }
+    mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    // y -> transposed B tile (full precision value; the tensor core reads its tf32 part), then hi / lo split in TMEM
+    for (int c = 0; c < kQB; c += 16) {
+      float v[16], lo[16];
+      tmem_ld16(lane_base + tm_y + c, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        *reinterpret_cast<float*>(by + warp * kRedN * 128 + sw128_offset(c + i, lane)) = v[i];
+        const float h = tf32_hi(v[i]);
+        lo[i] = v[i] - h;
+        v[i] = h;
+      }
+      tmem_st16(lane_base + tm_y + c, v);
+      tmem_st16(lane_base + tm_ylo + c, lo);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      issue_z(s, tmem + tm_z, tmem + tm_y, tmem + tm_ylo, kQB, kDB);
+      umma_commit(s.bar_mma);
+    }
+    mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;   // also guarantees the previous tile's accumulation has read adz / by
+    tc_fence_after();
+    {
+      float z[kDB];
+      const float pr = softmax64(s.bias, s.cen, lane_base, tm_z, z);
+      const int p = p0 + warp * 32 + lane;
+      const float g = p < n ? __ldg(g_pred + (size_t)b * n + p) : 0.f;
+#pragma unroll
+      for (int d = 0; d < kDB; ++d) {
+        const float pg = z[d] * g;
+        *reinterpret_cast<float*>(adz + warp * 128 * 128 + sw128_offset(d, lane)) = pg * (s.cen[d] - pr);
+        *reinterpret_cast<float*>(adz + warp * 128 * 128 + sw128_offset(kDB + d, lane)) = pg;
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(adz), b0 = smem_u32(by);
+#pragma unroll
+      for (int k = 0; k < kTile / 8; ++k) {
+        umma_tf32_ss(tmem + tm_acc, make_desc_sw128(a0 + (k >> 2) * 128 * 128 + (k & 3) * 32, 16, 1024),
+                     make_desc_sw128(b0 + (k >> 2) * kRedN * 128 + (k & 3) * 32, 16, 1024), idesc3, acc3);
+        acc3 = 1;
+      }
+      // no commit here: the next commit (next tile's first contraction, or the final one) covers it
+    }
+  }
+  if (threadIdx.x == 0) umma_commit(s.bar_mma);
+  mbar_wait(s.bar_mma, ph_mma);
+  tc_fence_after();
+  if (t_begin < t_end) {
+    const int r = threadIdx.x;   // accumulator row
+    for (int c = 0; c < kRedN; c += 16) {
+      float v[16];
+      tmem_ld16(lane_base + tm_acc + c, v);
+      tmem_wait_ld();
+      if (c < kQB) {
+        if (r < D) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c + i < Q) part_dW[((size_t)cta * D + r) * Q + c + i] = v[i];
+        }
+      } else {
+        if (r < D) part_db[(size_t)cta * D + r] = v[0];
+        if (r >= kDB && r - kDB < D) part_dc[(size_t)cta * D + r - kDB] = v[0];
+      }
+    }
+  } else if (threadIdx.x < D) {   // empty chunk: contribute zeros
+    for (int q = 0; q < Q; ++q) part_dW[((size_t)cta * D + threadIdx.x) * Q + q] = 0.f;
+    part_db[(size_t)cta * D + threadIdx.x] = 0.f;
+    part_dc[(size_t)cta * D + threadIdx.x] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pass 2: d_x, d_queries  (SURVEY Appendix A.1), Q, D <= 64.  Per 128-pixel tile, lane = pixel:
+//   y (3xTF32), t = x^T ds^T, logits (3xTF32) -> softmax -> dz (TMEM) -> dy1 = dz Wp -> dy = dy1 + a (t - delta),
+//   a = exp(y - m_q) / l_q -> d_x tile = dy K + a ds  (A operands dy, a read from TMEM)
+//   d_K += dy^T x   (dy transposed through shared memory, x tile loaded a second time K-major over pixels)
+// TMEM columns: [0,64) y_hi [64,128) y_lo [128,192) logits/dz [192,256) dy1/dy [256,320) t/a [320,352) d_x [352,384) d_K
+// ------------------------------------------------------------------------------------------------
+struct SmemDx {
+  uint8_t* x_k;     // [4 px-atoms][32 e rows][32 px]  TMA (SWIZZLE_128B), K-major over pixels
+  uint8_t* kT;      // [2 q-atoms][32 e rows][32 q]    queries transposed
+  uint8_t* ds;      // [64 q rows][32 e]               d_summary
+  uint8_t* dsT;     // [2 q-atoms][32 e rows][32 q]    d_summary transposed
+  uint8_t* wT;      // [2 d-atoms][64 q rows][32 d]    Wp transposed
+  uint8_t* dyT;     // [4 px-atoms][128 rows][32 px]   dy transposed (rows >= 64 zero)
+  float* mq; float* il; float* dl;
+  uint64_t* bar_xk;
+};
+constexpr size_t kSmemDxBytes = 1024 + 3 * kXTile + 2 * kQB * 128 + 2 * 2 * kDB * 128 + 2 * kDB * 4 + 64 + 1024 +
+                                kXTile + 3 * 2 * 32 * 128 + 2 * kQB * 128 + 4 * 128 * 128 + 3 * kQB * 4 + 16;
+
+__global__ void __launch_bounds__(kThreads) sql_tc_bwd_dx_kernel(
+    const __grid_constant__ CUtensorMap map_mn, const __grid_constant__ CUtensorMap map_k,
+    const float* __restrict__ queries, const float* __restrict__ Wp, const float* __restrict__ bp,
+    const float* __restrict__ centers, const float* __restrict__ g_pred, const float* __restrict__ summary,
+    const float* __restrict__ row_max, const float* __restrict__ row_sum, const float* __restrict__ d_summary, int Q,
+    int D, int n, int tiles_per_chunk, float* __restrict__ d_x, float* __restrict__ part_dK) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem s = carve(smem_raw, kQB, kDB);
+  SmemDx x2;
+  {
+    uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s.tmem_slot) + 4 + 1023) & ~(uintptr_t)1023);
+    x2.x_k = p; p += kXTile;
+    x2.kT = p; p += 2 * 32 * 128;
+    x2.ds = p; p += kQB * 128;
+    x2.dsT = p; p += 2 * 32 * 128;
+    x2.wT = p; p += 2 * kQB * 128;
+    x2.dyT = p; p += 4 * 128 * 128;
+    x2.mq = reinterpret_cast<float*>(p); p += kQB * 4;
+    x2.il = reinterpret_cast<float*>(p); p += kQB * 4;
+    x2.dl = reinterpret_cast<float*>(p); p += kQB * 4;
+    x2.bar_xk = reinterpret_cast<uint64_t*>(p);
+  }
+  const int b = blockIdx.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kCols = 512;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_mn);
+    tma_prefetch_desc(&map_k);
+    mbar_init(s.bar_tma, 1);
+    mbar_init(s.bar_mma, 1);
+    mbar_init(x2.bar_xk, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(s.tmem_slot, kCols);
+    tmem_relinquish();
+  }
+  const int t_begin = blockIdx.x * tiles_per_chunk;
+  const int t_end = min((n + kTile - 1) / kTile, t_begin + tiles_per_chunk);
+  __syncthreads();
+  if (threadIdx.x == 0 && t_begin < t_end) issue_x_tma(s, &map_mn, t_begin * kTile, b * kE);
+  stage_queries(s, queries + (size_t)b * Q * kE, Q, kQB);
+  stage_wp(s, Wp, bp, centers + (size_t)b * D, Q, D, kQB, kDB);
+  {
+    const float* qb = queries + (size_t)b * Q * kE;
+    const float* dsb = d_summary + (size_t)b * Q * kE;
+    for (int idx = threadIdx.x; idx < kQB * kE; idx += kThreads) {
+      const int q = idx >> 5, e = idx & 31;
+      const float kv = q < Q ? __ldg(qb + idx) : 0.f;
+      const float dv = q < Q ? __ldg(dsb + idx) : 0.f;
+      *reinterpret_cast<float*>(x2.ds + sw128_offset(q, e)) = dv;
+      const uint32_t offT = (uint32_t)(q >> 5) * 32u * 128u + sw128_offset(e, q & 31);
+      *reinterpret_cast<float*>(x2.kT + offT) = kv;
+      *reinterpret_cast<float*>(x2.dsT + offT) = dv;
+    }
+    for (int idx = threadIdx.x; idx < kQB * kDB; idx += kThreads) {   // wT[q][d] = Wp[d][q]
+      const int d = idx / kQB, q = idx - d * kQB;
+      const float v = (d < D && q < Q) ? __ldg(Wp + (size_t)d * Q + q) : 0.f;
+      *reinterpret_cast<float*>(x2.wT + (uint32_t)(d >> 5) * kQB * 128u + sw128_offset(q, d & 31)) = v;
+    }
+    for (int idx = threadIdx.x; idx < 4 * 128 * 32; idx += kThreads) reinterpret_cast<float*>(x2.dyT)[idx] = 0.f;
+    for (int q = threadIdx.x; q < kQB; q += kThreads) {
+      float m = 0.f, inv = 0.f, delta = 0.f;
+      if (q < Q) {
+        m = __ldg(row_max + b * Q + q);
+        inv = 1.f / __ldg(row_sum + b * Q + q);
+        for (int e = 0; e < kE; ++e)
+          delta = fmaf(__ldg(dsb + q * kE + e), __ldg(summary + ((size_t)b * Q + q) * kE + e), delta);
+      }
+      x2.mq[q] = m; x2.il[q] = inv; x2.dl[q] = delta;
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s.tmem_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  constexpr uint32_t tm_y = 0, tm_ylo = 64, tm_z = 128, tm_dy = 192, tm_t = 256, tm_dx = 320, tm_dk = 352;
+  const uint32_t id_t = make_idesc_tf32(128, kQB, 1, 0);    // t:   A = x (MN-major), B = ds (K-major)
+  const uint32_t id_64 = make_idesc_tf32(128, 64, 0, 0);    // dy1: A = dz (TMEM), B = wT
+  const uint32_t id_32 = make_idesc_tf32(128, 32, 0, 0);    // d_x, d_K
+  uint32_t ph_tma = 0, ph_mma = 0, ph_xk = 0, acc_dk = 0;
+  float* dxb = d_x + (size_t)b * kE * n;
+  for (int t = t_begin; t < t_end; ++t) {
+    const int p0 = t * kTile;
+    const int p = p0 + warp * 32 + lane;
+    mbar_wait(s.bar_tma, ph_tma); ph_tma ^= 1;
+    split_x_tile(s);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (t + 1 < t_end) issue_x_tma(s, &map_mn, p0 + kTile, b * kE);
+      mbar_arrive_expect_tx(x2.bar_xk, kXTile);   // x_k is free: the previous tile's d_K contraction has completed
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tma_load_2d(x2.x_k + j * kXBlock, &map_k, p0 + 32 * j, b * kE, x2.bar_xk);
+      tc_fence_after();
+      issue_y(s, tmem + tm_y, kQB);
+      const uint32_t xh = smem_u32(s.x_hi), dsa = smem_u32(x2.ds);
+#pragma unroll
+      for (int k = 0; k < kE / 8; ++k)
+        umma_tf32_ss(tmem + tm_t, make_desc_mn32(xh + k * 1024, kXBlock), make_desc_sw128(dsa + k * 32, 16, 1024), id_t,
+                     k > 0);
+      umma_commit(s.bar_mma);
+    }
+    mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    split_tmem(lane_base, tm_y, tm_ylo, kQB);
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      issue_z(s, tmem + tm_z, tmem + tm_y, tmem + tm_ylo, kQB, kDB);
+      umma_commit(s.bar_mma);
+    }
+    mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    {
+      float z[kDB];
+      const float pr = softmax64(s.bias, s.cen, lane_base, tm_z, z);
+      const float g = p < n ? __ldg(g_pred + (size_t)b * n + p) : 0.f;
+#pragma unroll
+      for (int c = 0; c < kDB; c += 16) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = z[c + i] * g * (s.cen[c + i] - pr);
+        tmem_st16(lane_base + tm_z + c, v);
+      }
+      tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t wt = smem_u32(x2.wT);
+#pragma unroll
+      for (int k = 0; k < kDB / 8; ++k)
+        umma_tf32_ts(tmem + tm_dy, tmem + tm_z + k * 8,
+                     make_desc_sw128(wt + (uint32_t)(k >> 2) * kQB * 128u + (uint32_t)(k & 3) * 32u, 16, 1024), id_64, k > 0);
+      umma_commit(s.bar_mma);
+    }
+    mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    for (int c = 0; c < kQB; c += 16) {
+      float dy[16], tt[16], yh[16], yl[16];
+      tmem_ld16(lane_base + tm_dy + c, dy);
+      tmem_ld16(lane_base + tm_t + c, tt);
+      tmem_ld16(lane_base + tm_y + c, yh);
+      tmem_ld16(lane_base + tm_ylo + c, yl);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int q = c + i;
+        const float a = (q < Q && p < n) ? __expf((yh[i] + yl[i]) - x2.mq[q]) * x2.il[q] : 0.f;
+        dy[i] = (p < n) ? fmaf(a, tt[i] - x2.dl[q], dy[i]) : 0.f;
+        tt[i] = a;
+        *reinterpret_cast<float*>(x2.dyT + warp * 128 * 128 + sw128_offset(q, lane)) = dy[i];
+      }
+      tmem_st16(lane_base + tm_dy + c, dy);
+      tmem_st16(lane_base + tm_t + c, tt);
+    }
+    tmem_wait_st();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      mbar_wait(x2.bar_xk, ph_xk);
+      const uint32_t a0 = smem_u32(x2.dyT), xk = smem_u32(x2.x_k), kt = smem_u32(x2.kT), dst = smem_u32(x2.dsT);
+#pragma unroll
+      for (int k = 0; k < kTile / 8; ++k) {   // d_K += dy^T x     (K = 128 pixels)
+        umma_tf32_ss(tmem + tm_dk, make_desc_sw128(a0 + (k >> 2) * 128 * 128 + (k & 3) * 32, 16, 1024),
+                     make_desc_sw128(xk + (k >> 2) * kXBlock + (k & 3) * 32, 16, 1024), id_32, acc_dk);
+        acc_dk = 1;
+      }
+#pragma unroll
+      for (int k = 0; k < kQB / 8; ++k)      // d_x = dy K
+        umma_tf32_ts(tmem + tm_dx, tmem + tm_dy + k * 8,
+                     make_desc_sw128(kt + (k >> 2) * 32 * 128 + (k & 3) * 32, 16, 1024), id_32, k > 0);
+#pragma unroll
+      for (int k = 0; k < kQB / 8; ++k)      //     + a ds
+        umma_tf32_ts(tmem + tm_dx, tmem + tm_t + k * 8,
+                     make_desc_sw128(dst + (k >> 2) * 32 * 128 + (k & 3) * 32, 16, 1024), id_32, 1);
+      umma_commit(s.bar_mma);
+    }
+    ph_xk ^= 1;
+    mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    {
+      float v[16];
+      tmem_ld16(lane_base + tm_dx, v);
+      tmem_wait_ld();
+      if (p < n) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dxb[(size_t)i * n + p] = v[i];
+      }
+      tmem_ld16(lane_base + tm_dx + 16, v);
+      tmem_wait_ld();
+      if (p < n) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dxb[(size_t)(16 + i) * n + p] = v[i];
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  {
+    // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only the real query rows store
+    const int q = threadIdx.x;
+    float* out = part_dK + ((size_t)cta * Q + q) * kE;
+    const bool have = t_begin < t_end;
+#pragma unroll
+    for (int c = 0; c < kE; c += 16) {
+      float v[16];
+      if (have) {
+        tmem_ld16(lane_base + tm_dk + c, v);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      }
+      if (q < Q) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) out[c + i] = v[i];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kCols);
+}
+
+// ------------------------------------------------------------------------------------------------
 // energy maps  y[b,q,p]   (module-level FullQueryLayer output; also the bring-up kernel of this file)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) sql_tc_energy_kernel(const __grid_constant__ CUtensorMap xmap,
@@ -699,6 +1133,56 @@ int tc_summary_partials(const float* x, const float* queries, int B, int Q, int 
   }
   *chunks_out = chunks;
   return check_launch("sql_tc_summary_kernel");
+}
+}  // namespace sqlx
+
+namespace sqlx {
+bool tc_bwd_supported(int Q, int D) { return Q <= tcsql::kQB && D <= tcsql::kDB; }
+
+void tc_bwd_plan(int B, int n, int* chunks, int* tiles_per_chunk) {
+  const int tiles = ceil_div(n, tcsql::kTile);
+  int c = kNumSMs / B;   // one CTA per SM (about 200 KB of shared memory, all 512 TMEM columns)
+  c = c < 1 ? 1 : (c > tiles ? tiles : c);
+  *tiles_per_chunk = ceil_div(tiles, c);
+  *chunks = ceil_div(tiles, *tiles_per_chunk);
+}
+
+// per-CTA partials: part_dW [ctas][D][Q], part_dc [ctas][D], part_db [ctas][D]; ctas = B * chunks (sample-major)
+int tc_bwd_reduce_partials(const float* x, const float* queries, const float* Wp, const float* bp, const float* centers,
+                           const float* g_pred, int B, int Q, int D, int n, float* part_dW, float* part_dc,
+                           float* part_db, int chunks, int tpc, cudaStream_t st) {
+  SQLX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
+  CUtensorMap xmap;
+  if (int e = make_tensor_map_2d(&xmap, x, (uint64_t)B * tcsql::kE, (uint64_t)n, 32, 32, 1)) return e;
+  static bool configured = false;
+  if (!configured) {
+    if (int e = raise_smem(tcsql::sql_tc_bwd_reduce_kernel)) return e;
+    configured = true;
+  }
+  ProfScope prof("sql_tc_bwd_reduce_kernel", st);
+  tcsql::sql_tc_bwd_reduce_kernel<<<dim3(chunks, B), tcsql::kThreads, tcsql::kSmemRedBytes, st>>>(
+      xmap, queries, Wp, bp, centers, g_pred, Q, D, n, tpc, part_dW, part_dc, part_db);
+  return check_launch("sql_tc_bwd_reduce_kernel");
+}
+
+// d_x [B,32,n] (overwritten) and per-CTA partials part_dK [ctas][Q][32]
+int tc_bwd_dx_partials(const float* x, const float* queries, const float* Wp, const float* bp, const float* centers,
+                       const float* g_pred, const float* summary, const float* row_max, const float* row_sum,
+                       const float* d_summary, int B, int Q, int D, int n, float* d_x, float* part_dK, int chunks, int tpc,
+                       cudaStream_t st) {
+  SQLX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
+  CUtensorMap map_mn, map_k;
+  if (int e = make_tensor_map_2d(&map_mn, x, (uint64_t)B * tcsql::kE, (uint64_t)n, 32, 32, 1)) return e;
+  if (int e = make_tensor_map_2d(&map_k, x, (uint64_t)B * tcsql::kE, (uint64_t)n, 32, 32, 0)) return e;
+  static bool configured = false;
+  if (!configured) {
+    if (int e = raise_smem(tcsql::sql_tc_bwd_dx_kernel)) return e;
+    configured = true;
+  }
+  ProfScope prof("sql_tc_bwd_dx_kernel", st);
+  tcsql::sql_tc_bwd_dx_kernel<<<dim3(chunks, B), tcsql::kThreads, tcsql::kSmemDxBytes, st>>>(
+      map_mn, map_k, queries, Wp, bp, centers, g_pred, summary, row_max, row_sum, d_summary, Q, D, n, tpc, d_x, part_dK);
+  return check_launch("sql_tc_bwd_dx_kernel");
 }
 }  // namespace sqlx
 

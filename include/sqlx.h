@@ -123,6 +123,47 @@ int sqlx_warp_fwd(const float* depth_lr, const float* source, const float* K, co
                   int B, int h, int w, int H, int W, float eps,
                   float* depth_up, float* sample, float* color, void* stream);
 
+/* Identity (auto-mask) losses of all S sources, written straight into identity [B,S,H,W]
+ * (trainer.py:480-493: compute_reprojection_loss(inputs[("color",f,0)], target) for every source). */
+int sqlx_identity_losses_fwd(const float* target, const float* const* sources, int S, int B, int H, int W,
+                             int ssim_radius, float w_ssim, float w_l1, int no_ssim, float* identity, void* stream);
+
+/* ---- One whole loss scale (the body of the `for scale in self.opt.scales` loops, trainer.py:390-439 and 461-545)
+ * as one forward and one backward call; the library chains its own kernels on `stream`:
+ *   depth statistics -> pose matrices (posecnn translation rescale, trainer.py:412-421) -> fused photometric
+ *   kernel -> smoothness (trainer.py:533-542) -> loss_s = mean(min) + smooth_weight * smooth
+ * smooth_weight = disparity_smoothness / 2^s (trainer.py:542). */
+typedef struct sqlx_scale_desc {
+  sqlx_photo_desc photo;
+  int32_t Hc, Wc;               /* resolution of inputs[("color",0,s)] used by the smoothness term */
+  float smooth_weight;
+  int32_t rescale_translation;  /* 1: translation *= mean inverse depth (posecnn and not use_stereo) */
+} sqlx_scale_desc;
+
+typedef struct sqlx_pose_inputs {
+  const float* axisangle[SQLX_MAX_SOURCES];    /* [B,3] per source, or NULL when the source uses fixed_T */
+  const float* translation[SQLX_MAX_SOURCES];  /* [B,3] */
+  const float* fixed_T[SQLX_MAX_SOURCES];      /* [B,4,4] (inputs["stereo_T"]) when axisangle is NULL */
+  uint32_t invert_mask;                        /* bit s set: invert=True for source s (frame_id < 0, trainer.py:336) */
+} sqlx_pose_inputs;
+
+/* `saved` (sqlx_scale_saved_bytes) carries T, depth statistics and smoothness sums from forward to backward;
+ * `workspace` (sqlx_scale_workspace_bytes) is scratch.  loss: device scalar [1].  argmin [B,H,W] u8. */
+size_t sqlx_scale_saved_bytes(const sqlx_scale_desc* desc);
+size_t sqlx_scale_workspace_bytes(const sqlx_scale_desc* desc);
+int sqlx_scale_loss_fwd(const sqlx_scale_desc* desc, const float* depth_lr, const float* target,
+                        const float* const* sources, const float* color_s, const float* K, const float* inv_K,
+                        const sqlx_pose_inputs* poses, const float* identity, const float* noise, float* loss,
+                        uint8_t* argmin, void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes,
+                        void* stream);
+/* g_loss: device scalar, upstream gradient of loss.  d_depth_lr [B,h,w] overwritten; d_axisangle[s], d_translation[s]
+ * [B,3] overwritten for pose-net sources (entries may be NULL). */
+int sqlx_scale_loss_bwd(const sqlx_scale_desc* desc, const float* depth_lr, const float* target,
+                        const float* const* sources, const float* color_s, const float* K, const float* inv_K,
+                        const sqlx_pose_inputs* poses, const uint8_t* argmin, const float* g_loss, const void* saved,
+                        float* d_depth_lr, float* const* d_axisangle, float* const* d_translation, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* Module-level geometry drop-ins (the fused path above never materialises these tensors).
  * BackprojectDepth.forward (layers.py:210-215): depth [B,1,H,W], inv_K [B,4,4] -> points [B,4,H*W] (row 3 = 1). */
 int sqlx_backproject_fwd(const float* depth, const float* inv_K, int B, int H, int W, float* points, void* stream);

@@ -228,7 +228,7 @@ __global__ void finalize_rows_kernel(const float* __restrict__ partial, int per_
 template <int R, int TH, int TW, int NT, bool MAP>
 __global__ void __launch_bounds__(NT) reproj_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target,
                                                          int C_, int H, int W, float w_ssim, float w_l1,
-                                                         float* __restrict__ out) {
+                                                         float* __restrict__ out, size_t out_bstride) {
   using C = FwdCfg<R, TH, TW, NT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* xs = reinterpret_cast<float*>(smem_raw);
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(NT) reproj_loss_kernel(const float* __restrict
       float rho;
       if (R > 0) rho = w_ssim * (ssim_acc[k] / (float)C_) + w_l1 * (l1_acc[k] / (float)C_);
       else rho = l1_acc[k] / (float)C_;
-      out[(size_t)b * plane + (size_t)(v0 + prow[k]) * W + (u0 + pcol[k])] = rho;
+      out[(size_t)b * out_bstride + (size_t)(v0 + prow[k]) * W + (u0 + pcol[k])] = rho;
     }
   }
 }
@@ -398,7 +398,8 @@ int launch_photo_fwd(const PhotoFwdParams& p, cudaStream_t st) {
 
 template <int R, bool MAP>
 int launch_reproj(const float* pred, const float* target, int B, int C_, int H, int W, float w_ssim, float w_l1,
-                  float* out, cudaStream_t st) {
+                  float* out, cudaStream_t st, size_t out_bstride = 0) {
+  if (out_bstride == 0) out_bstride = (size_t)H * W;
   using C = FwdCfg<R, kTH, kTW, kNT>;
   auto kern = reproj_loss_kernel<R, kTH, kTW, kNT, MAP>;
   const size_t smem = sizeof(float) * (2 * C::PLANE + 5 * C::HB);
@@ -409,7 +410,7 @@ int launch_reproj(const float* pred, const float* target, int B, int C_, int H, 
   }
   dim3 grid(ceil_div(W, kTW), ceil_div(H, kTH), B);
   ProfScope prof("reproj_loss_kernel", st);
-  kern<<<grid, kNT, smem, st>>>(pred, target, C_, H, W, w_ssim, w_l1, out);
+  kern<<<grid, kNT, smem, st>>>(pred, target, C_, H, W, w_ssim, w_l1, out, out_bstride);
   return check_launch("reproj_loss_kernel");
 }
 }  // namespace
@@ -471,6 +472,27 @@ extern "C" int sqlx_reprojection_loss_fwd(const float* pred, const float* target
   if (r == 3) return launch_reproj<3, false>(pred, target, B, 3, H, W, w_ssim, w_l1, out, st);
   if (r == 1) return launch_reproj<1, false>(pred, target, B, 3, H, W, w_ssim, w_l1, out, st);
   return launch_reproj<0, false>(pred, target, B, 3, H, W, w_ssim, w_l1, out, st);
+}
+
+extern "C" int sqlx_identity_losses_fwd(const float* target, const float* const* sources, int S, int B, int H, int W,
+                                        int ssim_radius, float w_ssim, float w_l1, int no_ssim, float* identity,
+                                        void* stream) {
+  SQLX_REQUIRE(target && sources && identity, "NULL pointer argument");
+  SQLX_REQUIRE(S >= 1 && S <= SQLX_MAX_SOURCES && B > 0 && H > 0 && W > 0, "bad shape");
+  const int r = no_ssim ? 0 : ssim_radius;
+  SQLX_REQUIRE(r == 0 || r == 1 || r == 3, "ssim_radius must be 1 or 3");
+  SQLX_REQUIRE(H > 2 * r && W > 2 * r, "image smaller than the SSIM window");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t plane = (size_t)H * W;
+  for (int s = 0; s < S; ++s) {
+    SQLX_REQUIRE(sources[s], "source %d is NULL", s);
+    float* out = identity + (size_t)s * plane;
+    int e = r == 3 ? launch_reproj<3, false>(sources[s], target, B, 3, H, W, w_ssim, w_l1, out, st, (size_t)S * plane)
+          : r == 1 ? launch_reproj<1, false>(sources[s], target, B, 3, H, W, w_ssim, w_l1, out, st, (size_t)S * plane)
+                   : launch_reproj<0, false>(sources[s], target, B, 3, H, W, w_ssim, w_l1, out, st, (size_t)S * plane);
+    if (e) return e;
+  }
+  return SQLX_OK;
 }
 
 extern "C" int sqlx_ssim_fwd(const float* x, const float* y, int B, int C, int H, int W, int ssim_radius, float* out,

@@ -28,6 +28,16 @@ class PhotoDesc(ctypes.Structure):
                 ("noise_scale", ctypes.c_float), ("eps", ctypes.c_float)]
 
 
+class ScaleDesc(ctypes.Structure):
+    _fields_ = [("photo", PhotoDesc), ("Hc", ctypes.c_int32), ("Wc", ctypes.c_int32),
+                ("smooth_weight", ctypes.c_float), ("rescale_translation", ctypes.c_int32)]
+
+
+class PoseInputs(ctypes.Structure):
+    _fields_ = [("axisangle", ctypes.c_void_p * MAX_SOURCES), ("translation", ctypes.c_void_p * MAX_SOURCES),
+                ("fixed_T", ctypes.c_void_p * MAX_SOURCES), ("invert_mask", ctypes.c_uint32)]
+
+
 _PROTOS = {
     "sqlx_last_error": (ctypes.c_char_p, []),
     "sqlx_version": (c_int, []),
@@ -48,6 +58,16 @@ _PROTOS = {
                                c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sqlx_warp_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sqlx_identity_losses_fwd": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_float,
+                                         c_float, c_int, c_void_p, c_void_p]),
+    "sqlx_scale_saved_bytes": (c_size_t, [ctypes.POINTER(ScaleDesc)]),
+    "sqlx_scale_workspace_bytes": (c_size_t, [ctypes.POINTER(ScaleDesc)]),
+    "sqlx_scale_loss_fwd": (c_int, [ctypes.POINTER(ScaleDesc), c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_void_p,
+                                    c_void_p, c_void_p, ctypes.POINTER(PoseInputs), c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "sqlx_scale_loss_bwd": (c_int, [ctypes.POINTER(ScaleDesc), c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_void_p,
+                                    c_void_p, c_void_p, ctypes.POINTER(PoseInputs), c_void_p, c_void_p, c_void_p, c_void_p,
+                                    ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_void_p, c_size_t, c_void_p]),
     "sqlx_backproject_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sqlx_backproject_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sqlx_project_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),

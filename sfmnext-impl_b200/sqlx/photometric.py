@@ -206,13 +206,106 @@ def warp(depth_lr, source, K, inv_K, T, H, W, *, want_depth=True, want_sample=Tr
     return depth_up, sample, color
 
 
+class _ScaleLoss(torch.autograd.Function):
+    """One loss scale as one library call forward and one backward (csrc/scale_loss.cu)."""
+
+    @staticmethod
+    def forward(ctx, depth_lr, meta, *pose_tensors):
+        (target, color_s, K, inv_K, identity, noise, sources, pose_spec, cfg, smooth_weight, rescale) = meta
+        d = _f32c(depth_lr)
+        B, _, h, w = d.shape
+        H, W = target.shape[-2:]
+        S = len(sources)
+        Hc, Wc = color_s.shape[-2:]
+        desc = _lib.ScaleDesc(make_desc(B, H, W, h, w, S, **cfg), Hc, Wc, float(smooth_weight), int(bool(rescale)))
+        keep = []                                  # contiguous fp32 views that must outlive the call
+        pin = _lib.PoseInputs()
+        mask = 0
+        it = iter(pose_tensors)
+        for i, spec in enumerate(pose_spec):
+            if spec[0] == "fixed":
+                Tm = _f32c(spec[1]); keep.append(Tm)
+                pin.fixed_T[i] = Tm.data_ptr()
+            else:
+                aa = _f32c(next(it)).reshape(B, 3); tr = _f32c(next(it)).reshape(B, 3)
+                keep += [aa, tr]
+                pin.axisangle[i] = aa.data_ptr(); pin.translation[i] = tr.data_ptr()
+                if spec[1]:
+                    mask |= 1 << i
+        pin.invert_mask = mask
+        dev = d.device
+        saved = torch.empty(lib().sqlx_scale_saved_bytes(ctypes.byref(desc)), device=dev, dtype=torch.uint8)
+        nws = lib().sqlx_scale_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(nws, device=dev, dtype=torch.uint8)
+        loss = torch.empty(1, device=dev, dtype=torch.float32)
+        argmin = torch.empty(B, H, W, device=dev, dtype=torch.uint8)
+        srcs = [_f32c(x) for x in sources]
+        tgt, col, Kc, iKc, ident, nz = (_f32c(t) for t in (target, color_s, K, inv_K, identity, noise))
+        check(lib().sqlx_scale_loss_fwd(ctypes.byref(desc), ptr(d), ptr(tgt), _src_array(srcs), ptr(col), ptr(Kc), ptr(iKc),
+                                        ctypes.byref(pin), ptr(ident), ptr(nz), ptr(loss), ptr(argmin), ptr(saved),
+                                        saved.numel(), ptr(ws), nws, stream_ptr()), "sqlx_scale_loss_fwd")
+        ctx.save_for_backward(d, tgt, col, Kc, iKc, argmin, saved, *srcs, *keep)
+        ctx.state = (desc, pose_spec, mask, S, len(keep), [t.shape for t in pose_tensors])
+        ctx.mark_non_differentiable(argmin)
+        return loss.reshape(()), argmin
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_argmin):
+        desc, pose_spec, mask, S, nkeep, shapes = ctx.state
+        d, tgt, col, Kc, iKc, argmin, saved, *rest = ctx.saved_tensors
+        srcs, keep = rest[:S], rest[S:]
+        B = d.shape[0]
+        dev = d.device
+        pin = _lib.PoseInputs()
+        pin.invert_mask = mask
+        d_aa = (ctypes.c_void_p * _lib.MAX_SOURCES)()
+        d_tr = (ctypes.c_void_p * _lib.MAX_SOURCES)()
+        grads = []
+        it = iter(keep)
+        for i, spec in enumerate(pose_spec):
+            if spec[0] == "fixed":
+                pin.fixed_T[i] = next(it).data_ptr()
+            else:
+                aa, tr = next(it), next(it)
+                pin.axisangle[i] = aa.data_ptr(); pin.translation[i] = tr.data_ptr()
+                ga = torch.empty(B, 3, device=dev, dtype=torch.float32)
+                gt = torch.empty(B, 3, device=dev, dtype=torch.float32)
+                d_aa[i] = ga.data_ptr(); d_tr[i] = gt.data_ptr()
+                grads += [ga, gt]
+        nws = lib().sqlx_scale_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(nws, device=dev, dtype=torch.uint8)
+        d_depth = torch.empty_like(d)
+        g = g_loss.contiguous().float().reshape(1)
+        check(lib().sqlx_scale_loss_bwd(ctypes.byref(desc), ptr(d), ptr(tgt), _src_array(srcs), ptr(col), ptr(Kc), ptr(iKc),
+                                        ctypes.byref(pin), ptr(argmin), ptr(g), ptr(saved), ptr(d_depth), d_aa, d_tr,
+                                        ptr(ws), nws, stream_ptr()), "sqlx_scale_loss_bwd")
+        return (d_depth, None) + tuple(gr.reshape(sh) for gr, sh in zip(grads, shapes))
+
+
+def identity_losses(target, sources, *, no_ssim=False, ssim_radius=3, w_ssim=0.85, w_l1=0.15):
+    """[B,S,H,W]: compute_reprojection_loss(source_f, target) for every source (trainer.py:480-493), no torch.cat."""
+    require_cuda(target, *sources)
+    tgt = _f32c(target)
+    srcs = [_f32c(x) for x in sources]
+    B, _, H, W = tgt.shape
+    S = len(srcs)
+    out = torch.empty(B, S, H, W, device=tgt.device, dtype=torch.float32)
+    check(lib().sqlx_identity_losses_fwd(ptr(tgt), _src_array(srcs), S, B, H, W, ssim_radius, w_ssim, w_l1, int(no_ssim),
+                                         ptr(out), stream_ptr()), "sqlx_identity_losses_fwd")
+    return out
+
+
 def photometric_losses(disps, target_pyr, sources, K, inv_K, poses, noises, *, height, width, scales=(0,),
                        disparity_smoothness=1e-3, rescale_translation=True, no_ssim=False, avg_reprojection=False,
                        disable_automasking=False, ssim_radius=3, materialize=False, identity=None):
-    """generate_images_pred + compute_losses (trainer.py:386-549) on the fused kernels.
+    """generate_images_pred + compute_losses (trainer.py:386-549): one fused library call per loss scale.
 
-    Arguments: see the parameter list of the CPU restatement used by tests/.  `noises[s]` may be None: the tie-break
-    noise is then drawn on the device (the reference draws it on the CPU generator, trainer.py:516).
+    disps {s: [B,1,h_s,w_s]} network outputs (these ARE depth, trainer.py:399-402); target_pyr {s: [B,3,H_s,W_s]};
+    sources: list of S [B,3,H,W]; poses: per source {"T": [B,4,4]} or {"axisangle", "translation" [B,1,1,3], "invert"};
+    noises {s: [B,S,H,W]} standard-normal tie-break noise, or None / missing: drawn on the device (the reference draws
+    it on the CPU generator and copies it, trainer.py:516-517).  Returns loss, loss/<s>, identity_selection/<s>
+    (only materialised on request or when automasking... see `materialize`), and with materialize=True the
+    depth / sample / color tensors Trainer.log reads.
     """
     H, W = height, width
     S = len(sources)
@@ -221,42 +314,67 @@ def photometric_losses(disps, target_pyr, sources, K, inv_K, poses, noises, *, h
     automask = not disable_automasking
     cfg = dict(ssim_radius=ssim_radius, automask=automask, avg=avg_reprojection, no_ssim=no_ssim)
     out = {}
+    require_cuda(target, K, inv_K, *sources)
     if automask and identity is None:
-        identity = torch.cat([reprojection_loss(src, target, no_ssim=no_ssim, ssim_radius=ssim_radius)
-                              for src in sources], 1)
+        identity = identity_losses(target, sources, no_ssim=no_ssim, ssim_radius=ssim_radius)
+    pose_spec, pose_tensors = [], []
+    for pose in poses:
+        if "T" in pose:
+            pose_spec.append(("fixed", pose["T"]))
+        else:
+            pose_spec.append(("net", bool(pose["invert"])))
+            pose_tensors += [pose["axisangle"], pose["translation"]]
+    rescale = bool(rescale_translation) and any(sp[0] == "net" for sp in pose_spec)
+    n_ident = 0 if not automask else (1 if avg_reprojection else S)
     total = 0
     for s in scales:
         disp = disps[s]
-        stats = depth_stats(disp, H, W) if (rescale_translation and any("T" not in p for p in poses)) else None
-        Ts = []
-        for pose in poses:
-            if "T" in pose:
-                Ts.append(pose["T"].float())
-            else:
-                scale = stats[:, 1] if rescale_translation else None
-                Ts.append(pose_matrix(pose["axisangle"][:, 0], pose["translation"][:, 0], scale, pose["invert"]))
-        T = torch.stack(Ts, 1)
         noise = None
         if automask:
             noise = noises.get(s) if noises is not None else None
             if noise is None:
                 noise = torch.randn(B, 1 if avg_reprojection else S, H, W, device=target.device)
-        loss_sum, argmin = _PhotoLoss.apply(disp, T, target, K, inv_K, identity, noise, cfg, *sources)
-        loss = loss_sum[0] / float(B * H * W)
-        n_ident = 0 if not automask else (1 if avg_reprojection else S)
-        if automask:
-            out["identity_selection/%d" % s] = (argmin >= n_ident).float()
-        out[("argmin", s)] = argmin
-        sm = smooth_loss_normalised(disp, target_pyr[s])
-        out[("smooth", s)] = sm
-        loss = loss + disparity_smoothness * sm / (2 ** s)
+        meta = (target, target_pyr[s], K, inv_K, identity, noise, list(sources), pose_spec, cfg,
+                disparity_smoothness / (2 ** s), rescale)
+        loss, argmin = _ScaleLoss.apply(disp, meta, *pose_tensors)
         out["loss/%d" % s] = loss
+        out[("argmin", s)] = argmin
+        if automask:
+            out["identity_selection/%d" % s] = _LazyMask(argmin, n_ident)
         total = total + loss
         if materialize:
+            stats = depth_stats(disp.detach(), H, W) if rescale else None
             for i, src in enumerate(sources):
-                depth_up, sample, color = warp(disp, src, K, inv_K, T[:, i], H, W)
+                sp = pose_spec[i]
+                if sp[0] == "fixed":
+                    Ti = sp[1].float()
+                else:
+                    j = sum(1 for q in pose_spec[:i] if q[0] == "net")
+                    Ti = pose_matrix(pose_tensors[2 * j].detach()[:, 0], pose_tensors[2 * j + 1].detach()[:, 0],
+                                     stats[:, 1] if rescale else None, sp[1])
+                depth_up, sample, color = warp(disp.detach(), src, K, inv_K, Ti, H, W)
                 out[("depth", 0, s)] = depth_up
                 out[("sample", i, s)] = sample
                 out[("color", i, s)] = color
+    if materialize and automask:
+        for s in scales:
+            out["identity_selection/%d" % s] = out["identity_selection/%d" % s].float()
     out["loss"] = total / len(scales)
     return out
+
+
+class _LazyMask:
+    """identity_selection mask (trainer.py:529-530) materialised on first use: the training step itself never reads
+    it (only Trainer.log does, every `log_frequency` steps), so the cast kernels are skipped on ordinary steps."""
+
+    def __init__(self, argmin, n_ident):
+        self.argmin, self.n_ident = argmin, n_ident
+
+    def float(self):
+        return (self.argmin >= self.n_ident).float()
+
+    def cpu(self):
+        return self.float().cpu()
+
+    def __getattr__(self, name):            # behave like the float tensor for anything else
+        return getattr(self.float(), name)

@@ -251,12 +251,13 @@ def main():
     assert sqlx.lib().sqlx_device_ok(local_rank) == 1, "libsqlx targets sm_100a (B200) only"
 
     torch.manual_seed(0)
-    hp = HotPath(cfg, device=dev, use_graph=not args.no_graph)
+    hp = HotPath(cfg, device=dev, use_graph=not args.no_graph, num_slots=2)
     if world > 1:   # identical initial weights on every rank
         for p in hp.parameters():
             dist.broadcast(p.data, 0)
     hb = make_host_batch(cfg, seed=1234 + rank, pin=True)
-    h2d_bytes = hp.load(hb, non_blocking=False)
+    h2d_bytes = hp.load(hb, non_blocking=False, slot=0)
+    hp.load(hb, non_blocking=False, slot=1)
     torch.cuda.synchronize()
 
     # launches of OUR kernels in one step (counted eagerly; a graph replay re-issues the same nodes)
@@ -265,7 +266,8 @@ def main():
     torch.cuda.synchronize()
     launches_per_step = int(sqlx.lib().sqlx_launch_count() - n0)
     if hp.use_graph:
-        hp.capture()
+        hp.capture(slot=0)
+        hp.capture(slot=1)
 
     bucket = None
 
@@ -303,13 +305,32 @@ def main():
         allreduce_grads()
 
     loss_host = torch.zeros(1).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    ev_loaded = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_i = [0]
+
+    def enqueue_load(slot):
+        """host -> device copy of one batch into input set `slot` on the copy stream"""
+        copy_stream.wait_event(ev_done[slot])          # the previous step on this set has finished reading it
+        with torch.cuda.stream(copy_stream):
+            hp.load(hb, non_blocking=True, slot=slot)
+            ev_loaded[slot].record(copy_stream)
 
     def e2e_step():
-        hp.load(hb, non_blocking=True)
-        hp.step()
+        """What a training loop with a pinned-memory prefetching loader does: the H2D copy of batch i+1 overlaps the
+        step on batch i (two device input sets); the loss is read back on the host every step (trainer.py:242-262)."""
+        i = e2e_i[0]
+        slot = i & 1
+        enqueue_load(slot ^ 1)                         # prefetch the next batch while this one computes
+        main.wait_event(ev_loaded[slot])
+        hp.step(slot)
         allreduce_grads()
+        ev_done[slot].record(main)
         loss_host.copy_(hp.loss.reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller reads the loss every step (trainer.py:242-262)
+        main.synchronize()
+        e2e_i[0] = i + 1
 
     for _ in range(max(args.warmup, 3)):
         dev_step()
@@ -317,9 +338,13 @@ def main():
     if rank == 0:
         sampler.start()
     ms_dev = timed(dev_step, args.steps)
-    for _ in range(2):
+    for ev in ev_done:
+        ev.record(main)
+    enqueue_load(0)                                    # the very first batch; afterwards every step prefetches the next
+    for _ in range(3):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    copy_stream.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
     # per-kernel device times: the same steps submitted eagerly with CUDA events around each main kernel
@@ -377,6 +402,7 @@ def main():
     config["l2"] = ("no explicit flush: every step streams %.0f MB of inputs plus %.0f MB of gradients through a 126 MB L2"
                     % (total_bytes / 1e6, (hb["x"].numel() * 4) / 1e6))
     config["submission"] = "eager" if args.no_graph else "cuda_graph"
+    config["e2e_pipeline"] = "H2D of batch i+1 on a copy stream overlaps the step on batch i (2 device input sets)"
     line = {"metric": METRIC, "value": cfg.B * world / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,

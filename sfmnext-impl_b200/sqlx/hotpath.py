@@ -45,7 +45,7 @@ class HotPath(torch.nn.Module):
     """Parameters: the decoder's 1x1 conv (convert_to_prob.0) and bins_regressor.  Inputs live in static
     device buffers `self.inp[name]` (see HotPathConfig.input_shapes); `load()` copies a host batch into them."""
 
-    def __init__(self, cfg, device="cuda", use_graph=True):
+    def __init__(self, cfg, device="cuda", use_graph=True, num_slots=1):
         super().__init__()
         nn = torch.nn
         self.cfg = cfg
@@ -55,23 +55,34 @@ class HotPath(torch.nn.Module):
                                             nn.Linear(16 * c.Q, 256), nn.LeakyReLU(), nn.Linear(256, c.D))
         self.to(device)
         self.device = torch.device(device)
-        self.inp = {k: torch.zeros(v, device=device, dtype=torch.float32) for k, v in cfg.input_shapes().items()}
         self.grad_inputs = ["x", "queries"] + ["disp%d" % s for s in c.scales if s > 0] + \
                            ["axisangle%d" % i for i in range(c.S)] + ["translation%d" % i for i in range(c.S)]
-        for k in self.grad_inputs:
-            self.inp[k].requires_grad_(True)
+        # `num_slots` independent device input sets: with 2, the host->device copy of batch i+1 (on a copy stream)
+        # overlaps the step on batch i, as a pinned-memory DataLoader does for the reference (trainer.py:164-171)
+        self.slots = []
+        for _ in range(num_slots):
+            inp = {k: torch.zeros(v, device=device, dtype=torch.float32) for k, v in cfg.input_shapes().items()}
+            for k in self.grad_inputs:
+                inp[k].requires_grad_(True)
+            self.slots.append(inp)
+        self.inp = self.slots[0]
         self.use_graph = use_graph
-        self.graph = None
+        self.graphs = [None] * num_slots
+        self.losses = [None] * num_slots
         self.loss = None
         self.pred = None
+        for p in self.parameters():          # static gradient buffers shared by every captured graph
+            p.grad = torch.zeros_like(p)
 
     # ------------------------------------------------------------------ data
-    def load(self, host_batch, non_blocking=True):
-        """host_batch: {name: CPU tensor (pinned for async copies)}; returns the bytes copied."""
+    def load(self, host_batch, non_blocking=True, slot=0):
+        """host_batch: {name: CPU tensor (pinned for async copies)} -> device input set `slot` on the current
+        stream; returns the bytes copied."""
         n = 0
+        inp = self.slots[slot]
         with torch.no_grad():
             for k, v in host_batch.items():
-                self.inp[k].copy_(v, non_blocking=non_blocking)
+                inp[k].copy_(v, non_blocking=non_blocking)
                 n += v.numel() * v.element_size()
         return n
 
@@ -80,8 +91,8 @@ class HotPath(torch.nn.Module):
         c = self.cfg
         return S.bin_centers(self.bins_regressor(summary.reshape(c.B, c.Q * c.E)), c.min_depth, c.max_depth)
 
-    def forward_loss(self):
-        c, I = self.cfg, self.inp
+    def forward_loss(self, slot=0):
+        c, I = self.cfg, self.slots[slot]
         conv = self.convert_to_prob[0]
         pred = S.sql_tail(I["x"], I["queries"], conv.weight.view(c.D, c.Q), conv.bias, self._centers,
                           tuple(self.bins_regressor.parameters()))
@@ -95,46 +106,53 @@ class HotPath(torch.nn.Module):
                                    width=c.W, scales=c.scales, disparity_smoothness=c.disparity_smoothness)
         return out["loss"], pred
 
-    def _zero_grads(self):
+    def _zero_grads(self, slot=0):
         for p in self.parameters():
-            p.grad = None
+            p.grad.zero_()                    # in place: the buffers are shared with the captured graphs
         for k in self.grad_inputs:
-            self.inp[k].grad = None
+            self.slots[slot][k].grad = None
 
-    def step_eager(self):
-        self._zero_grads()
-        loss, pred = self.forward_loss()
+    def step_eager(self, slot=0):
+        self._zero_grads(slot)
+        loss, pred = self.forward_loss(slot)
         loss.backward()
         self.loss, self.pred = loss.detach(), pred.detach()
+        self.losses[slot] = self.loss
         return self.loss
 
     # ------------------------------------------------------------------ graph
-    def capture(self, warmup=3):
-        """Capture forward + backward into one CUDA graph (gradients land in static .grad tensors)."""
+    def capture(self, warmup=3, slot=0):
+        """Capture zero-grads + forward + backward on input set `slot` into one CUDA graph (parameter gradients
+        land in the shared static .grad buffers, input gradients in the slot's own .grad tensors)."""
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self.step_eager()
+                self.step_eager(slot)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self._zero_grads()
+        for k in self.grad_inputs:
+            self.slots[slot][k].grad = None
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            loss, pred = self.forward_loss()
+            for p in self.parameters():
+                p.grad.zero_()
+            loss, pred = self.forward_loss(slot)
             loss.backward()
-            self.loss, self.pred = loss.detach(), pred.detach()
-        self.graph = g
+            self.losses[slot] = loss.detach()
+            self.pred = pred.detach()
+        self.graphs[slot] = g
         return g
 
-    def step(self):
-        """Run one step on whatever is in the static input buffers; returns the (device) loss scalar."""
+    def step(self, slot=0):
+        """Run one step on whatever is in input set `slot`; returns the (device) loss scalar."""
         if self.use_graph:
-            if self.graph is None:
-                self.capture()
-            self.graph.replay()
+            if self.graphs[slot] is None:
+                self.capture(slot=slot)
+            self.graphs[slot].replay()
+            self.loss = self.losses[slot]
             return self.loss
-        return self.step_eager()
+        return self.step_eager(slot)
 
     def param_grads(self):
         return [p.grad for p in self.parameters() if p.grad is not None]

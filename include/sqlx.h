@@ -99,12 +99,16 @@ int sqlx_ssim_bwd(const float* x, const float* y, const float* g_out, int B, int
  * outputs
  *   loss_sum  [1]  double?  no: float, = sum over b,v,u of the per-pixel minimum (caller divides by B*H*W)
  *   argmin    [B,H,W] uint8: index into cat(identity, reprojection) exactly as torch.min(combined,dim=1)
+ *   ssim_coef [B,S,3,3,H,W] or NULL: d SSIM/d(mean_x, E[x^2], E[xy]) per source / channel / pixel.  When given to
+ *             sqlx_photo_bwd as well, the backward is a cheap adjoint box filter of these planes instead of a
+ *             recomputation of the warp and the box sums on a doubled halo (36*S bytes per pixel of extra traffic).
  */
 size_t sqlx_photo_workspace_bytes(const sqlx_photo_desc* desc);
 int sqlx_photo_fwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
                    const float* const* sources, const float* K, const float* inv_K, const float* T,
                    const float* identity, const float* noise,
-                   float* loss_sum, uint8_t* argmin, void* workspace, size_t workspace_bytes, void* stream);
+                   float* loss_sum, uint8_t* argmin, float* ssim_coef, void* workspace, size_t workspace_bytes,
+                   void* stream);
 
 /* Backward of sqlx_photo_fwd.  g_loss is a DEVICE scalar (upstream gradient of the per-scale loss);
  * `scale` is a host multiplier (1/(B*H*W)).
@@ -113,7 +117,7 @@ int sqlx_photo_fwd(const sqlx_photo_desc* desc, const float* depth_lr, const flo
  */
 int sqlx_photo_bwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
                    const float* const* sources, const float* K, const float* inv_K, const float* T,
-                   const uint8_t* argmin, const float* g_loss, float scale,
+                   const uint8_t* argmin, const float* ssim_coef, const float* g_loss, float scale,
                    float* d_depth_lr, float* d_T, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Warp only (materialises what Trainer.log reads): sample [B,H,W,2] normalised grid (layers.py:255-257),

@@ -24,6 +24,7 @@ struct PhotoFwdParams {
   const float* noise;
   float* partial;      // [gridDim.z*gridDim.y*gridDim.x]
   uint8_t* argmin;
+  float* coef;         // optional [B][S][3 ch][3][H][W]: d SSIM / d(mean_x, E[x^2], E[xy]) for the backward kernel
 };
 
 template <int R, int TH, int TW, int NT>
@@ -154,7 +155,13 @@ __global__ void __launch_bounds__(NT) photo_fwd_kernel(const PhotoFwdParams p) {
           const float Sx = vsum<R, TW>(hb, prow[k], pcol[k]);
           const float Sxx = vsum<R, TW>(hb + C::HB, prow[k], pcol[k]);
           const float Sxy = vsum<R, TW>(hb + 2 * C::HB, prow[k], pcol[k]);
-          ssim_acc[k] += ssim_value(make_stats<R>(Sx, Sy[c][k], Sxx, Syy[c][k], Sxy));
+          const SsimStats st = make_stats<R>(Sx, Sy[c][k], Sxx, Syy[c][k], Sxy);
+          ssim_acc[k] += ssim_value(st);
+          if (p.coef && pin[k]) {   // saved so that the backward never recomputes the box sums (plane-major: coalesced)
+            const SsimGrad g = ssim_grad(st);
+            float* cp = p.coef + ((((size_t)b * S + s) * 3 + c) * 3) * plane + (size_t)(v0 + prow[k]) * W + (u0 + pcol[k]);
+            cp[0] = g.dmx; cp[plane] = g.dexx; cp[2 * plane] = g.dexy;
+          }
         }
         __syncthreads();
       }
@@ -437,7 +444,7 @@ extern "C" size_t sqlx_photo_workspace_bytes(const sqlx_photo_desc* d) {
 extern "C" int sqlx_photo_fwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
                               const float* const* sources, const float* K, const float* inv_K, const float* T,
                               const float* identity, const float* noise, float* loss_sum, uint8_t* argmin,
-                              void* workspace, size_t workspace_bytes, void* stream) {
+                              float* ssim_coef, void* workspace, size_t workspace_bytes, void* stream) {
   if (int e = check_desc(desc)) return e;
   SQLX_REQUIRE(depth_lr && target && sources && K && inv_K && T && loss_sum && argmin, "NULL pointer argument");
   SQLX_REQUIRE(workspace && workspace_bytes >= sqlx_photo_workspace_bytes(desc), "workspace too small");
@@ -451,6 +458,7 @@ extern "C" int sqlx_photo_fwd(const sqlx_photo_desc* desc, const float* depth_lr
   p.K = K; p.invK = inv_K; p.T = T; p.identity = identity; p.noise = noise;
   p.partial = reinterpret_cast<float*>(workspace);
   p.argmin = argmin;
+  p.coef = (desc->flags & SQLX_NO_SSIM) ? nullptr : ssim_coef;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int r = (desc->flags & SQLX_NO_SSIM) ? 0 : desc->ssim_radius;
   int e = r == 3 ? launch_photo_fwd<3>(p, st) : (r == 1 ? launch_photo_fwd<1>(p, st) : launch_photo_fwd<0>(p, st));

@@ -109,6 +109,7 @@ struct ScaleWs {
   float* stats;     // [B,2]
   float* sums;      // [B,3]
   float* loss_sum;  // [1]
+  float* coef;      // [B,S,3,3,H,W] SSIM derivative coefficients (absent with --no_ssim)
   float* g_sums;    // [B,3]
   float* g_stats;   // [B,2]
   float* dT;        // [B,S,16]
@@ -132,7 +133,8 @@ ScaleWs carve_ws(const sqlx_scale_desc* d, void* saved, void* workspace) {
   w.T = reinterpret_cast<float*>(p); p += align256(sizeof(float) * B * S * 16);
   w.stats = reinterpret_cast<float*>(p); p += align256(sizeof(float) * B * 2);
   w.sums = reinterpret_cast<float*>(p); p += align256(sizeof(float) * B * 3);
-  w.loss_sum = reinterpret_cast<float*>(p);
+  w.loss_sum = reinterpret_cast<float*>(p); p += 256;
+  w.coef = (d->photo.flags & SQLX_NO_SSIM) ? nullptr : reinterpret_cast<float*>(p);
   uint8_t* q = reinterpret_cast<uint8_t*>(workspace);   // scratch
   w.g_sums = reinterpret_cast<float*>(q); q += align256(sizeof(float) * B * 3);
   w.g_stats = reinterpret_cast<float*>(q); q += align256(sizeof(float) * B * 2);
@@ -169,7 +171,9 @@ PoseSources to_sources(const sqlx_pose_inputs* poses, int S, float* const* d_aa,
 extern "C" size_t sqlx_scale_saved_bytes(const sqlx_scale_desc* d) {
   if (!d) return 0;
   const int B = d->photo.B, S = d->photo.S;
-  return align256(sizeof(float) * B * S * 16) + align256(sizeof(float) * B * 2) + align256(sizeof(float) * B * 3) + 256;
+  const size_t coef = (d->photo.flags & SQLX_NO_SSIM) ? 0 : sizeof(float) * 9 * (size_t)B * S * d->photo.H * d->photo.W;
+  return align256(sizeof(float) * B * S * 16) + align256(sizeof(float) * B * 2) + align256(sizeof(float) * B * 3) + 256 +
+         align256(coef);
 }
 
 extern "C" size_t sqlx_scale_workspace_bytes(const sqlx_scale_desc* d) {
@@ -202,7 +206,7 @@ extern "C" int sqlx_scale_loss_fwd(const sqlx_scale_desc* d, const float* depth_
                                                              rescale ? ws.stats : nullptr, B, S, ws.T);
   if (int e = check_launch("pose_multi_fwd_kernel")) return e;
   if (int e = sqlx_photo_fwd(&d->photo, depth_lr, target, sources, K, inv_K, ws.T, identity, noise, ws.loss_sum, argmin,
-                             ws.scratch, ws.scratch_bytes, stream))
+                             ws.coef, ws.scratch, ws.scratch_bytes, stream))
     return e;
   if (int e = sqlx_smooth_fwd(depth_lr, color_s, B, h, w, d->Hc, d->Wc, ws.sums, ws.scratch, ws.scratch_bytes, stream))
     return e;
@@ -235,7 +239,7 @@ extern "C" int sqlx_scale_loss_bwd(const sqlx_scale_desc* d, const float* depth_
   if (cudaMemsetAsync(d_depth_lr, 0, sizeof(float) * (size_t)B * h * w, st) != cudaSuccess)
     return check_launch("cudaMemsetAsync(d_depth_lr)");
   if (int e = sqlx_smooth_bwd(depth_lr, color_s, B, h, w, d->Hc, d->Wc, ws.g_sums, d_depth_lr, stream)) return e;
-  if (int e = sqlx_photo_bwd(&d->photo, depth_lr, target, sources, K, inv_K, ws.T, argmin, g_loss,
+  if (int e = sqlx_photo_bwd(&d->photo, depth_lr, target, sources, K, inv_K, ws.T, argmin, ws.coef, g_loss,
                              1.f / ((float)B * H * W), d_depth_lr, ws.dT, ws.scratch, ws.scratch_bytes, stream))
     return e;
   if (any_pose) {

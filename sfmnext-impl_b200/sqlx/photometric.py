@@ -170,7 +170,7 @@ class _PhotoLoss(torch.autograd.Function):
         loss_sum = torch.empty(1, device=d.device, dtype=torch.float32)
         argmin = torch.empty(B, H, W, device=d.device, dtype=torch.uint8)
         check(lib().sqlx_photo_fwd(ctypes.byref(desc), ptr(d), ptr(tgt), _src_array(srcs), ptr(Kc), ptr(iKc), ptr(Tm),
-                                   ptr(ident), ptr(nz), ptr(loss_sum), ptr(argmin), ptr(ws), nbytes, stream_ptr()),
+                                   ptr(ident), ptr(nz), ptr(loss_sum), ptr(argmin), None, ptr(ws), nbytes, stream_ptr()),
               "sqlx_photo_fwd")
         ctx.save_for_backward(d, Tm, tgt, Kc, iKc, argmin, *srcs)
         ctx.desc = desc
@@ -187,7 +187,7 @@ class _PhotoLoss(torch.autograd.Function):
         d_T = torch.empty_like(Tm)
         g = g_loss.contiguous().float()
         check(lib().sqlx_photo_bwd(ctypes.byref(desc), ptr(d), ptr(tgt), _src_array(srcs), ptr(Kc), ptr(iKc), ptr(Tm),
-                                   ptr(argmin), ptr(g), 1.0, ptr(d_depth), ptr(d_T), ptr(ws), nbytes, stream_ptr()),
+                                   ptr(argmin), None, ptr(g), 1.0, ptr(d_depth), ptr(d_T), ptr(ws), nbytes, stream_ptr()),
               "sqlx_photo_bwd")
         return (d_depth, d_T, None, None, None, None, None, None) + (None,) * len(srcs)
 

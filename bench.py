@@ -207,6 +207,11 @@ def algorithmic_bytes(c):
         "sql_pred_kernel": B * (4 * n0 * E + 4 * n0),
         "sql_bwd_reduce_kernel": B * (4 * n0 * E + 4 * n0),
         "sql_bwd_dx_kernel": B * (4 * n0 * E + 4 * n0 + 4 * n0 * E),
+        # tensor-core versions: same compulsory traffic
+        "sql_tc_summary_kernel": B * 4 * n0 * E,
+        "sql_tc_pred_kernel": B * (4 * n0 * E + 4 * n0),
+        "sql_tc_bwd_reduce_kernel": B * (4 * n0 * E + 4 * n0),
+        "sql_tc_bwd_dx_kernel": B * (4 * n0 * E + 4 * n0 + 4 * n0 * E),
     }
 
 

@@ -5,6 +5,8 @@
 // Reference: autograd of layers.py:31-46,210-215,247-258 + trainer.py:395-396,431-435,444-451,526-532.
 #include "photo_tile.cuh"
 
+#include <stdlib.h>
+
 namespace sqlx {
 
 struct PhotoBwdParams {
@@ -287,8 +289,8 @@ struct Bwd2Cfg {
   static constexpr size_t smem_bytes = sizeof(float) * (3 * CF + SCR + 32 + 16) + sizeof(Camera) * SQLX_MAX_SOURCES + CF + 16;
 };
 
-template <int R, int TH, int TW, int NT>
-__global__ void __launch_bounds__(NT) photo_bwd2_kernel(const PhotoBwdParams p, const float* __restrict__ coef) {
+template <int R, int TH, int TW, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) photo_bwd2_kernel(const PhotoBwdParams p, const float* __restrict__ coef) {
   using C = Bwd2Cfg<R, TH, TW, NT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* cf = reinterpret_cast<float*>(smem_raw);   // 3 planes on the R halo
@@ -343,6 +345,11 @@ __global__ void __launch_bounds__(NT) photo_bwd2_kernel(const PhotoBwdParams p, 
   for (int s = 0; s < S; ++s) {
     const float sel_w = avg ? 1.f / (float)S : 1.f;
     const int sel_idx = avg ? n_ident : n_ident + s;
+    {   // nothing on this tile's halo selects source s (auto-masked or won by another source): no gradient at all
+      int any = 0;
+      for (int idx = threadIdx.x; idx < C::CF; idx += NT) any |= (amin[idx] == sel_idx);
+      if (!__syncthreads_or(any)) continue;
+    }
     const Camera& cam = cams[s];
     const float* srcb = p.src[s] + (size_t)b * 3 * plane;
     // own pixels: projection, taps, warped value and its spatial derivatives per channel
@@ -628,10 +635,12 @@ int launch_photo_bwd(const PhotoBwdParams& p, cudaStream_t st) {
 template <int R>
 int launch_photo_bwd2(const PhotoBwdParams& p, const float* coef, cudaStream_t st) {
   using C = Bwd2Cfg<R, kTH, kTW, kNT>;
-  auto kern = photo_bwd2_kernel<R, kTH, kTW, kNT>;
+  static const int minb = getenv("SQLX_BWD_MINB") ? atoi(getenv("SQLX_BWD_MINB")) : 4;  // resident CTAs per SM the register budget is capped for (tuning knob)
   dim3 grid(ceil_div(p.d.W, kTW), ceil_div(p.d.H, kTH), p.d.B);
   ProfScope prof("photo_bwd_kernel", st);
-  kern<<<grid, kNT, C::smem_bytes, st>>>(p, coef);
+  if (minb >= 4) photo_bwd2_kernel<R, kTH, kTW, kNT, 4><<<grid, kNT, C::smem_bytes, st>>>(p, coef);
+  else if (minb == 3) photo_bwd2_kernel<R, kTH, kTW, kNT, 3><<<grid, kNT, C::smem_bytes, st>>>(p, coef);
+  else photo_bwd2_kernel<R, kTH, kTW, kNT, 2><<<grid, kNT, C::smem_bytes, st>>>(p, coef);
   return check_launch("photo_bwd2_kernel");
 }
 

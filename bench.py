@@ -251,6 +251,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        # keep stdout to the single JSON line: NCCL's version banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     assert sqlx.lib().sqlx_device_ok(local_rank) == 1, "libsqlx targets sm_100a (B200) only"

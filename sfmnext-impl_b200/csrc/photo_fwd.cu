@@ -30,7 +30,7 @@ struct PhotoFwdParams {
 template <int R, int TH, int TW, int NT>
 struct FwdCfg {
   static constexpr int PH = TH + 2 * R, PW = TW + 2 * R;
-  static constexpr int LD = (PW + 3) & ~3;
+  static constexpr int LD = ((PW + 3) & ~3) + 2;   // even; 42 for a 32-wide tile: conflict-free 8-byte row accesses
   static constexpr int PLANE = PH * LD;
   static constexpr int HB = PH * TW;
   static constexpr int PPT = (TH * TW) / NT;
@@ -65,14 +65,13 @@ __global__ void __launch_bounds__(NT) photo_fwd_kernel(const PhotoFwdParams p) {
     stage_plane<C::PH, C::PW, C::LD>(p.target + ((size_t)b * 3 + c) * plane, H, W, v0 - R, u0 - R, tg + c * C::PLANE);
   __syncthreads();
 
-  // owned pixels
+  // owned pixels: PPT vertically adjacent rows of one column (the vertical box sums share 2R of their rows)
   int prow[C::PPT], pcol[C::PPT];
   bool pin[C::PPT];
 #pragma unroll
   for (int k = 0; k < C::PPT; ++k) {
-    const int pix = threadIdx.x + k * NT;
-    prow[k] = pix / TW;
-    pcol[k] = pix - prow[k] * TW;
+    prow[k] = (threadIdx.x / TW) * C::PPT + k;
+    pcol[k] = threadIdx.x % TW;
     pin[k] = (v0 + prow[k] < H) && (u0 + pcol[k] < W);
   }
 
@@ -82,21 +81,10 @@ __global__ void __launch_bounds__(NT) photo_fwd_kernel(const PhotoFwdParams p) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float* Y = tg + c * C::PLANE;
-      for (int idx = threadIdx.x; idx < C::PH * TW; idx += NT) {
-        const int r = idx / TW, cc = idx - r * TW;
-        const float* yr = Y + r * C::LD + cc;
-        float sy = 0.f, syy = 0.f;
-#pragma unroll
-        for (int k = 0; k <= 2 * R; ++k) { const float y = yr[k]; sy += y; syy = fmaf(y, y, syy); }
-        hb[idx] = sy;
-        hb[C::HB + idx] = syy;
-      }
+      hpass_blocked<(R > 0 ? R : 1), C::PH, TW, C::LD, TW, false>(nullptr, Y, hb, hb + C::HB, nullptr);
       __syncthreads();
-#pragma unroll
-      for (int k = 0; k < C::PPT; ++k) {
-        Sy[c][k] = vsum<R, TW>(hb, prow[k], pcol[k]);
-        Syy[c][k] = vsum<R, TW>(hb + C::HB, prow[k], pcol[k]);
-      }
+      vsum_multi<R, TW, C::PPT>(hb, prow[0], pcol[0], Sy[c]);
+      vsum_multi<R, TW, C::PPT>(hb + C::HB, prow[0], pcol[0], Syy[c]);
       __syncthreads();
     }
   }
@@ -148,14 +136,15 @@ __global__ void __launch_bounds__(NT) photo_fwd_kernel(const PhotoFwdParams p) {
         l1_acc[k] += fabsf(Y[o] - X[o]);
       }
       if (R > 0) {
-        hpass5<R, C::PH, TW, C::LD, TW, false>(X, Y, hb, hb + C::HB, hb + 2 * C::HB, nullptr, nullptr);
+        hpass_blocked<(R > 0 ? R : 1), C::PH, TW, C::LD, TW, true>(X, Y, hb, hb + C::HB, hb + 2 * C::HB);
         __syncthreads();
+        float Sx[C::PPT], Sxx[C::PPT], Sxy[C::PPT];
+        vsum_multi<R, TW, C::PPT>(hb, prow[0], pcol[0], Sx);
+        vsum_multi<R, TW, C::PPT>(hb + C::HB, prow[0], pcol[0], Sxx);
+        vsum_multi<R, TW, C::PPT>(hb + 2 * C::HB, prow[0], pcol[0], Sxy);
 #pragma unroll
         for (int k = 0; k < C::PPT; ++k) {
-          const float Sx = vsum<R, TW>(hb, prow[k], pcol[k]);
-          const float Sxx = vsum<R, TW>(hb + C::HB, prow[k], pcol[k]);
-          const float Sxy = vsum<R, TW>(hb + 2 * C::HB, prow[k], pcol[k]);
-          const SsimStats st = make_stats<R>(Sx, Sy[c][k], Sxx, Syy[c][k], Sxy);
+          const SsimStats st = make_stats<R>(Sx[k], Sy[c][k], Sxx[k], Syy[c][k], Sxy[k]);
           ssim_acc[k] += ssim_value(st);
           if (p.coef && pin[k]) {   // saved so that the backward never recomputes the box sums (plane-major: coalesced)
             const SsimGrad g = ssim_grad(st);
@@ -249,8 +238,7 @@ __global__ void __launch_bounds__(NT) reproj_loss_kernel(const float* __restrict
   float ssim_acc[C::PPT], l1_acc[C::PPT];
 #pragma unroll
   for (int k = 0; k < C::PPT; ++k) {
-    const int pix = threadIdx.x + k * NT;
-    prow[k] = pix / TW; pcol[k] = pix - prow[k] * TW;
+    prow[k] = (threadIdx.x / TW) * C::PPT + k; pcol[k] = threadIdx.x % TW;
     pin[k] = (v0 + prow[k] < H) && (u0 + pcol[k] < W);
     ssim_acc[k] = 0.f; l1_acc[k] = 0.f;
   }
@@ -264,16 +252,18 @@ __global__ void __launch_bounds__(NT) reproj_loss_kernel(const float* __restrict
       l1_acc[k] += fabsf(ys[o] - xs[o]);
     }
     if (R > 0) {
-      hpass5<R, C::PH, TW, C::LD, TW, true>(xs, ys, hb, hb + C::HB, hb + 2 * C::HB, hb + 3 * C::HB, hb + 4 * C::HB);
+      hpass_blocked<(R > 0 ? R : 1), C::PH, TW, C::LD, TW, true>(xs, ys, hb, hb + C::HB, hb + 2 * C::HB);
+      hpass_blocked<(R > 0 ? R : 1), C::PH, TW, C::LD, TW, false>(nullptr, ys, hb + 3 * C::HB, hb + 4 * C::HB, nullptr);
       __syncthreads();
+      float Sxv[C::PPT], Sxxv[C::PPT], Sxyv[C::PPT], Syv[C::PPT], Syyv[C::PPT];
+      vsum_multi<R, TW, C::PPT>(hb, prow[0], pcol[0], Sxv);
+      vsum_multi<R, TW, C::PPT>(hb + C::HB, prow[0], pcol[0], Sxxv);
+      vsum_multi<R, TW, C::PPT>(hb + 2 * C::HB, prow[0], pcol[0], Sxyv);
+      vsum_multi<R, TW, C::PPT>(hb + 3 * C::HB, prow[0], pcol[0], Syv);
+      vsum_multi<R, TW, C::PPT>(hb + 4 * C::HB, prow[0], pcol[0], Syyv);
 #pragma unroll
       for (int k = 0; k < C::PPT; ++k) {
-        const float Sx = vsum<R, TW>(hb, prow[k], pcol[k]);
-        const float Sxx = vsum<R, TW>(hb + C::HB, prow[k], pcol[k]);
-        const float Sxy = vsum<R, TW>(hb + 2 * C::HB, prow[k], pcol[k]);
-        const float Sy = vsum<R, TW>(hb + 3 * C::HB, prow[k], pcol[k]);
-        const float Syy = vsum<R, TW>(hb + 4 * C::HB, prow[k], pcol[k]);
-        const float v = ssim_value(make_stats<R>(Sx, Sy, Sxx, Syy, Sxy));
+        const float v = ssim_value(make_stats<R>(Sxv[k], Syv[k], Sxxv[k], Syyv[k], Sxyv[k]));
         if (MAP) {
           if (pin[k]) out[((size_t)b * C_ + c) * plane + (size_t)(v0 + prow[k]) * W + (u0 + pcol[k])] = v;
         } else {

@@ -25,7 +25,7 @@ for p in (ROOT, os.path.join(ROOT, "sfmnext-impl_b200"), os.path.join(ROOT, "tes
 import torch  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
-METRIC = "train_frames_per_sec_hot_path_192x640"
+METRIC = "train_frames_per_sec_hot_path"
 UNIT = "frames/s"
 
 
@@ -41,6 +41,10 @@ def parse():
     ap.add_argument("--queries", type=int, default=64)
     ap.add_argument("--bins", type=int, default=64)
     ap.add_argument("--scales", type=int, default=4, help="number of loss scales (BASELINE config 2: 4)")
+    ap.add_argument("--sources", type=int, default=2, help="source frames (2 = [-1,+1]; 3 with --use_stereo)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
+                    help="2 = BASELINE config 2 (default, the bench line); 3 = config 3 shapes: 320x1024, batch 8/GPU, "
+                         "3 sources, Q = D = 128, single loss scale (informational)")
     ap.add_argument("--no-graph", action="store_true", help="submit the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
@@ -221,15 +225,17 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from sqlx.hotpath import HotPath, HotPathConfig
+    if args.config == 3:
+        args.height, args.width, args.batch, args.queries, args.bins, args.sources, args.scales = 320, 1024, 8, 128, 128, 3, 1
     H, W = args.height, args.width
-    cfg = HotPathConfig(B=args.batch, H=H, W=W, h=H // 2, w=W // 2, E=32, Q=args.queries, D=args.bins, S=2,
-                        scales=tuple(range(args.scales)))
-    config = {"workload": "BASELINE config 2 hot path: SQL decoder tail (x0 32x%dx%d, Q=%d, D=%d) + photometric loss "
-                          "(3-frame, %dx%d, %d loss scales: scale 0 = decoder output, coarser scales synthetic "
+    cfg = HotPathConfig(B=args.batch, H=H, W=W, h=H // 2, w=W // 2, E=32, Q=args.queries, D=args.bins, S=args.sources,
+                        scales=tuple(range(args.scales)), min_depth=0.01 if args.config == 3 else 0.001)
+    config = {"workload": "BASELINE config %d hot path: SQL decoder tail (x0 32x%dx%d, Q=%d, D=%d) + photometric loss "
+                          "(%dx%d, %d loss scales: scale 0 = decoder output, coarser scales synthetic "
                           "since the reference decoder emits scale 0 only), forward+backward"
-                          % (H // 2, W // 2, args.queries, args.bins, H, W, args.scales),
+                          % (args.config, H // 2, W // 2, args.queries, args.bins, H, W, args.scales),
               "batch_per_gpu": args.batch, "global_batch": args.batch * world, "height": H, "width": W,
-              "source_frames": 2, "loss_scales": args.scales, "parallelism": "dp%d" % world}
+              "source_frames": args.sources, "loss_scales": args.scales, "parallelism": "dp%d" % world}
 
     if args.impl == "reference":
         if rank != 0:
@@ -318,11 +324,20 @@ def main():
     ev_done = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_i = [0]
 
+    # The auto-mask tie-break noise is NOT shipped from the host in the end-to-end loop: the reference draws it with
+    # the CPU generator and copies it every step (trainer.py:516-517), our API draws it on the device when no noise
+    # tensor is supplied.  Everything else the step consumes (frames, decoder features, queries, intrinsics, poses,
+    # coarser-scale depth maps) crosses PCIe every step.
+    hb_e2e = {k: v for k, v in hb.items() if not k.startswith("noise")}
+    e2e_bytes = sum(v.numel() * v.element_size() for v in hb_e2e.values())
+
     def enqueue_load(slot):
-        """host -> device copy of one batch into input set `slot` on the copy stream"""
+        """host -> device copy of one batch into input set `slot` on the copy stream (+ fresh device noise)"""
         copy_stream.wait_event(ev_done[slot])          # the previous step on this set has finished reading it
         with torch.cuda.stream(copy_stream):
-            hp.load(hb, non_blocking=True, slot=slot)
+            hp.load(hb_e2e, non_blocking=True, slot=slot)
+            for s_ in cfg.scales:
+                hp.slots[slot]["noise%d" % s_].normal_()
             ev_loaded[slot].record(copy_stream)
 
     def e2e_step():
@@ -409,12 +424,13 @@ def main():
     config["l2"] = ("no explicit flush: every step streams %.0f MB of inputs plus %.0f MB of gradients through a 126 MB L2"
                     % (total_bytes / 1e6, (hb["x"].numel() * 4) / 1e6))
     config["submission"] = "eager" if args.no_graph else "cuda_graph"
-    config["e2e_pipeline"] = "H2D of batch i+1 on a copy stream overlaps the step on batch i (2 device input sets)"
+    config["e2e_pipeline"] = ("H2D of batch i+1 on a copy stream overlaps the step on batch i (2 device input sets); "
+                              "tie-break noise drawn on the device instead of copied from the host")
     line = {"metric": METRIC, "value": cfg.B * world / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": cfg.B * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": int(e2e_bytes), "d2h_bytes_per_step": 4},
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "kernels": kernels, "kernel_ms_per_step": step_ms_kernels, "loss": float(hp.loss)}

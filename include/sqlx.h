@@ -225,6 +225,23 @@ int sqlx_sql_tc_supported(int E, int Q, int D, int n);
 int sqlx_sql_set_tensor_cores(int on);
 int sqlx_sql_energy_tc(const float* x, const float* queries, int B, int E, int Q, int n, float* energy, void* stream);
 
+/* Mixed-weight decomposition (tensor cores only; sqlx_sql_tc_supported must hold):
+ *   logits = Wp (K x) + b = (Wp K) x + b = M x + b with M [B,D,E] = Wp . queries computed by the caller (cuBLAS).
+ * The regression and its backward then contract over E = 32 instead of Q and need no Wp tiles on chip:
+ *   sqlx_sql_pred_mix_fwd   pred [B,n]                                  (depth_decoder_QTR.py:61,70)
+ *   sqlx_sql_bwd_pred_mix   d_M [B,D,E], d_bp [D], d_centers [B,D], d_x [B,E,n] (regression path; all overwritten)
+ *   sqlx_sql_bwd_summary    d_x (+)= summary path, d_queries [B,Q,E] = summary-path part of d_K (overwritten)
+ * The caller finishes with d_Wp = sum_b d_M queries^T and d_queries += Wp^T d_M. */
+size_t sqlx_sql_mix_workspace_bytes(int B, int Q, int D, int n);
+int sqlx_sql_pred_mix_fwd(const float* x, const float* Mx, const float* bp, const float* centers, int B, int E, int D,
+                          int n, float* pred, void* stream);
+int sqlx_sql_bwd_pred_mix(const float* x, const float* Mx, const float* bp, const float* centers, const float* g_pred,
+                          int B, int E, int D, int n, float* d_M, float* d_bp, float* d_centers, float* d_x,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int sqlx_sql_bwd_summary(const float* x, const float* queries, const float* summary, const float* row_max,
+                         const float* row_sum, const float* d_summary, int B, int E, int Q, int n, int accumulate,
+                         float* d_x, float* d_queries, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Depth regression: pred[b,p] = sum_d softmax_d(Wp (x^T K)[p,:] + bp)[d] * centers[b,d]
  * replaces networks/layers.py:17,20 + depth_decoder_QTR.py:61,70 (1x1 conv, Softmax(dim=1), sum). */
 int sqlx_sql_pred_fwd(const float* x, const float* queries, const float* Wp /*[D,Q]*/, const float* bp /*[D]*/,

@@ -618,6 +618,14 @@ int tc_summary_partials(const float* x, const float* queries, int B, int Q, int 
 int tc_pred_fwd(const float* x, const float* queries, const float* Wp, const float* bp, const float* centers, int B,
                 int Q, int D, int n, float* pred, cudaStream_t st);
 bool tc_bwd_supported(int Q, int D);
+int tc_pred_mix_fwd(const float* x, const float* Mx, const float* bp, const float* centers, int B, int D, int n,
+                    float* pred, cudaStream_t st);
+int tc_bwd_pred_mix(const float* x, const float* Mx, const float* bp, const float* centers, const float* g_pred, int B,
+                    int D, int n, float* d_x, float* part_dM, float* part_db, float* part_dc, int chunks, int tpc,
+                    cudaStream_t st);
+int tc_bwd_sum(const float* x, const float* queries, const float* summary, const float* row_max, const float* row_sum,
+               const float* d_summary, int B, int Q, int n, int accumulate, float* d_x, float* part_dK, int chunks, int tpc,
+               cudaStream_t st);
 void tc_bwd_plan(int B, int n, int* chunks, int* tiles_per_chunk);
 int tc_bwd_dx_partials(const float* x, const float* queries, const float* Wp, const float* bp, const float* centers,
                        const float* g_pred, const float* summary, const float* row_max, const float* row_sum,
@@ -865,4 +873,66 @@ extern "C" int sqlx_sql_bwd_dx(const float* x, const float* queries, const float
   }
   SQLX_DISPATCH_E(E, run_bwd_dx<kE>(x, queries, Wp, bp, centers, g_pred, summary, row_max, row_sum, d_summary, g_energy,
                                     B, Q, D, n, d_x, d_queries, ws, st));
+}
+
+// ------------------------------------------------------------------------------------------------
+// mixed-weight decomposition (tensor-core only):  logits = (Wp K) x + b = M x + b   -- see sql_tc.cu
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t sqlx_sql_mix_workspace_bytes(int B, int Q, int D, int n) {
+  if (B <= 0 || n <= 0) return 0;
+  int chunks = 0, tpc = 0;
+  tc_bwd_plan(B, n, &chunks, &tpc);
+  const size_t ctas = (size_t)B * chunks;
+  const size_t a = ctas * ((size_t)D * 32 + 2 * D), b = ctas * (size_t)Q * 32;
+  return sizeof(float) * ((a > b ? a : b) + 64);
+}
+
+extern "C" int sqlx_sql_pred_mix_fwd(const float* x, const float* Mx, const float* bp, const float* centers, int B, int E,
+                                     int D, int n, float* pred, void* stream) {
+  SQLX_REQUIRE(x && Mx && bp && centers && pred, "NULL pointer argument");
+  SQLX_REQUIRE(B > 0 && B <= 65535 && n > 0, "bad shape B=%d n=%d", B, n);
+  SQLX_REQUIRE(sqlx_sql_tc_supported(E, 1, D, n), "shape E=%d D=%d n=%d is not supported by the tensor-core path", E, D, n);
+  return tc_pred_mix_fwd(x, Mx, bp, centers, B, D, n, pred, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sqlx_sql_bwd_pred_mix(const float* x, const float* Mx, const float* bp, const float* centers,
+                                     const float* g_pred, int B, int E, int D, int n, float* d_M, float* d_bp,
+                                     float* d_centers, float* d_x, void* workspace, size_t workspace_bytes, void* stream) {
+  SQLX_REQUIRE(x && Mx && bp && centers && g_pred && d_M && d_bp && d_centers && d_x && workspace, "NULL pointer argument");
+  SQLX_REQUIRE(B > 0 && B <= 65535 && n > 0, "bad shape B=%d n=%d", B, n);
+  SQLX_REQUIRE(sqlx_sql_tc_supported(E, 1, D, n), "shape E=%d D=%d n=%d is not supported by the tensor-core path", E, D, n);
+  SQLX_REQUIRE(workspace_bytes >= sqlx_sql_mix_workspace_bytes(B, 1, D, n), "workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int chunks = 0, tpc = 0;
+  tc_bwd_plan(B, n, &chunks, &tpc);
+  const int ctas = B * chunks;
+  float* part_dM = reinterpret_cast<float*>(workspace);
+  float* part_db = part_dM + (size_t)ctas * D * 32;
+  float* part_dc = part_db + (size_t)ctas * D;
+  if (int e = tc_bwd_pred_mix(x, Mx, bp, centers, g_pred, B, D, n, d_x, part_dM, part_db, part_dc, chunks, tpc, st)) return e;
+  sum_partials_kernel<<<dim3(ceil_div(D * 32, 256), B), 256, 0, st>>>(part_dM, chunks, D * 32, d_M);
+  if (int e = check_launch("sum_partials_kernel")) return e;
+  sum_partials_kernel<<<dim3(ceil_div(D, 256), 1), 256, 0, st>>>(part_db, ctas, D, d_bp);
+  if (int e = check_launch("sum_partials_kernel")) return e;
+  sum_partials_kernel<<<dim3(ceil_div(D, 256), B), 256, 0, st>>>(part_dc, chunks, D, d_centers);
+  return check_launch("sum_partials_kernel");
+}
+
+extern "C" int sqlx_sql_bwd_summary(const float* x, const float* queries, const float* summary, const float* row_max,
+                                    const float* row_sum, const float* d_summary, int B, int E, int Q, int n,
+                                    int accumulate, float* d_x, float* d_queries, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  SQLX_REQUIRE(x && queries && summary && row_max && row_sum && d_summary && d_x && d_queries && workspace,
+               "NULL pointer argument");
+  SQLX_REQUIRE(B > 0 && B <= 65535 && n > 0, "bad shape B=%d n=%d", B, n);
+  SQLX_REQUIRE(sqlx_sql_tc_supported(E, Q, 0, n), "shape E=%d Q=%d n=%d is not supported by the tensor-core path", E, Q, n);
+  SQLX_REQUIRE(workspace_bytes >= sqlx_sql_mix_workspace_bytes(B, Q, 0, n), "workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int chunks = 0, tpc = 0;
+  tc_bwd_plan(B, n, &chunks, &tpc);
+  float* part_dK = reinterpret_cast<float*>(workspace);
+  if (int e = tc_bwd_sum(x, queries, summary, row_max, row_sum, d_summary, B, Q, n, accumulate, d_x, part_dK, chunks, tpc, st))
+    return e;
+  sum_partials_kernel<<<dim3(ceil_div(Q * 32, 256), B), 256, 0, st>>>(part_dK, chunks, Q * 32, d_queries);
+  return check_launch("sum_partials_kernel");
 }

@@ -965,6 +965,538 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_dx_kernel(
   if (warp == 0) tmem_dealloc(tmem, kCols);
 }
 
+// ================================================================================================
+// "Mixed-weight" decomposition (all Q, D <= 128):   logits = Wp (K x) + b = (Wp K) x + b = M x + b,  M [D x 32].
+// The depth regression and its backward then contract over E = 32 instead of Q, need no Wp tiles on chip and no
+// y -> logits hand-off; the summary path (which does need y) is independent of Wp.  M = Wp K, dWp = dM K^T and
+// dK_1 = Wp^T dM are tiny per-sample products left to cuBLAS on the host side (sqlx/sql.py).
+//   forward :  pred      = softmax_d(M x + b) . centers                                  sql_tc_pred2_kernel
+//   backward:  pass 1    = dM, d_bp, d_centers, d_x (regression path)                    sql_tc_bwd_pred_kernel
+//              pass 2    = d_x += summary path, d_K_2                                    sql_tc_bwd_sum_kernel
+// ================================================================================================
+
+// M tiles: [DP rows][32 e] K-major SW128, hi / lo
+__device__ __forceinline__ void stage_mix(uint8_t* m_hi, uint8_t* m_lo, const float* __restrict__ Mb, int D, int DP) {
+  for (int idx = threadIdx.x; idx < DP * kE; idx += kThreads) {
+    const int d = idx >> 5, e = idx & 31;
+    const float v = d < D ? __ldg(Mb + idx) : 0.f;
+    const float hi = tf32_hi(v);
+    const uint32_t off = sw128_offset(d, e);
+    *reinterpret_cast<float*>(m_hi + off) = hi;
+    if (m_lo) *reinterpret_cast<float*>(m_lo + off) = v - hi;
+  }
+}
+
+// Z[128 px, DP] = x^T M^T as 3xTF32.  x tiles MN-major (hi / lo), M tiles K-major (hi / lo).
+__device__ __forceinline__ void issue_xm(uint32_t xh, uint32_t xl, uint32_t mh, uint32_t ml, uint32_t tm_z, int DP) {
+  const uint32_t idesc = make_idesc_tf32(kTile, DP, 1, 0);
+  uint32_t acc = 0;
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t xa = pass == 1 ? xl : xh;
+    const uint32_t mb = pass == 2 ? ml : mh;
+#pragma unroll
+    for (int k = 0; k < kE / 8; ++k) {
+      umma_tf32_ss(tm_z, make_desc_mn32(xa + k * 1024, kXBlock), make_desc_sw128(mb + k * 32, 16, 1024), idesc, acc);
+      acc = 1;
+    }
+  }
+}
+
+struct SmemP2 {
+  uint8_t *x_raw, *x_hi, *x_lo, *m_hi, *m_lo;
+  float *bias, *cen;
+  uint64_t *bar_tma, *bar_mma;
+  uint32_t* tmem_slot;
+};
+__host__ __device__ inline size_t smem_p2_bytes(int DP) { return 1024 + 3 * kXTile + 2 * (size_t)DP * 128 + 2 * DP * 4 + 64; }
+
+__global__ void __launch_bounds__(kThreads) sql_tc_pred2_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                const float* __restrict__ Mx /*[B,D,32]*/,
+                                                                const float* __restrict__ bp,
+                                                                const float* __restrict__ centers, int D, int DP, int n,
+                                                                int tiles_per_chunk, uint32_t tmem_cols,
+                                                                float* __restrict__ pred) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem s;   // reuse the field names of the common struct for the helpers (split_x_tile, issue_x_tma, softmax_expect)
+  {
+    uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    s.x_raw = p; p += kXTile;
+    s.x_hi = p; p += kXTile;
+    s.x_lo = p; p += kXTile;
+    s.k_hi = p; p += (size_t)DP * 128;    // M hi
+    s.k_lo = p; p += (size_t)DP * 128;    // M lo
+    s.w_hi = s.w_lo = nullptr;
+    s.bias = reinterpret_cast<float*>(p); p += DP * 4;
+    s.cen = reinterpret_cast<float*>(p); p += DP * 4;
+    s.bar_tma = reinterpret_cast<uint64_t*>(p); p += 8;
+    s.bar_mma = reinterpret_cast<uint64_t*>(p); p += 8;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(p);
+  }
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&xmap);
+    mbar_init(s.bar_tma, 1);
+    mbar_init(s.bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(s.tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  const int t_begin = blockIdx.x * tiles_per_chunk;
+  const int t_end = min((n + kTile - 1) / kTile, t_begin + tiles_per_chunk);
+  __syncthreads();
+  if (threadIdx.x == 0 && t_begin < t_end) issue_x_tma(s, &xmap, t_begin * kTile, b * kE);
+  stage_mix(s.k_hi, s.k_lo, Mx + (size_t)b * D * kE, D, DP);
+  for (int d = threadIdx.x; d < DP; d += kThreads) {
+    s.bias[d] = d < D ? __ldg(bp + d) : -INFINITY;
+    s.cen[d] = d < D ? __ldg(centers + (size_t)b * D + d) : 0.f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s.tmem_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  uint32_t phase = 0;
+  for (int t = t_begin; t < t_end; ++t) {
+    const int p0 = t * kTile;
+    mbar_wait(s.bar_tma, phase);
+    split_x_tile(s);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (t + 1 < t_end) issue_x_tma(s, &xmap, p0 + kTile, b * kE);
+      tc_fence_after();
+      issue_xm(smem_u32(s.x_hi), smem_u32(s.x_lo), smem_u32(s.k_hi), smem_u32(s.k_lo), tmem, DP);
+      umma_commit(s.bar_mma);
+    }
+    mbar_wait(s.bar_mma, phase);
+    tc_fence_after();
+    const float pr = softmax_expect(s, lane_base, 0, DP);
+    const int p = p0 + warp * 32 + lane;
+    if (p < n) pred[(size_t)b * n + p] = pr;
+    tc_fence_before();
+    __syncthreads();
+    phase ^= 1;
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pass 1 (regression path).  TMEM: [0,DP) logits / dz   [DP,DP+32) d_x tile   [DP+32,DP+80) accumulator
+//   accumulator rows d: cols 0..31 = dM[d,e] = sum_p dz[p,d] x[e,p], col 32 = d_bp[d]
+//   d_centers[d] = sum_p pi g is accumulated per thread in registers and reduced across the CTA at the end
+// ------------------------------------------------------------------------------------------------
+constexpr int kAccN = kE + 16;   // x columns + ones column (+ padding to a multiple of 16)
+template <int DP>
+struct BwdPredSmem {
+  static constexpr size_t x_raw = 0, x_hi = kXTile, x_lo = 2 * kXTile, m_hi = 3 * kXTile, m_lo = m_hi + DP * 128,
+                          mT = m_lo + DP * 128,                      // [DP/32 atoms][32 e rows][32 d]
+                          bx = mT + (DP / 32) * 32 * 128,           // [4 px atoms][48 rows][32 px]: x (TMA) | ones
+                          adz = bx + 4 * kAccN * 128,               // [4 px atoms][128 rows][32 px]: dz^T
+                          tail = adz + 4 * 128 * 128 + 1024;        // (+1 KB: the final [128][DP+1] reduction scratch)
+  static constexpr size_t bytes = 1024 + tail + 2 * DP * 4 + 64;
+};
+
+template <int DP>
+__global__ void __launch_bounds__(kThreads) sql_tc_bwd_pred_kernel(
+    const __grid_constant__ CUtensorMap map_mn, const __grid_constant__ CUtensorMap map_k, const float* __restrict__ Mx,
+    const float* __restrict__ bp, const float* __restrict__ centers, const float* __restrict__ g_pred, int D, int n,
+    int tiles_per_chunk, float* __restrict__ d_x, float* __restrict__ part_dM /*[cta][D][32]*/,
+    float* __restrict__ part_db /*[cta][D]*/, float* __restrict__ part_dc /*[cta][D]*/) {
+  using L = BwdPredSmem<DP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Smem s;
+  s.x_raw = base + L::x_raw; s.x_hi = base + L::x_hi; s.x_lo = base + L::x_lo;
+  s.k_hi = base + L::m_hi; s.k_lo = base + L::m_lo;
+  uint8_t* mT = base + L::mT;
+  uint8_t* bx = base + L::bx;
+  uint8_t* adz = base + L::adz;
+  s.bias = reinterpret_cast<float*>(base + L::tail);
+  s.cen = s.bias + DP;
+  s.bar_tma = reinterpret_cast<uint64_t*>(s.cen + DP);
+  s.bar_mma = s.bar_tma + 1;
+  uint64_t* bar_bx = s.bar_tma + 2;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar_tma + 3);
+  const int b = blockIdx.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kCols = 256;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_mn);
+    tma_prefetch_desc(&map_k);
+    mbar_init(s.bar_tma, 1);
+    mbar_init(s.bar_mma, 1);
+    mbar_init(bar_bx, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(s.tmem_slot, kCols);
+    tmem_relinquish();
+  }
+  const int t_begin = blockIdx.x * tiles_per_chunk;
+  const int t_end = min((n + kTile - 1) / kTile, t_begin + tiles_per_chunk);
+  __syncthreads();
+  if (threadIdx.x == 0 && t_begin < t_end) issue_x_tma(s, &map_mn, t_begin * kTile, b * kE);
+  const float* Mb = Mx + (size_t)b * D * kE;
+  stage_mix(s.k_hi, s.k_lo, Mb, D, DP);
+  for (int idx = threadIdx.x; idx < DP * kE; idx += kThreads) {   // mT[e][d] = M[d][e]
+    const int d = idx >> 5, e = idx & 31;
+    const float v = d < D ? __ldg(Mb + idx) : 0.f;
+    *reinterpret_cast<float*>(mT + (uint32_t)(d >> 5) * 32u * 128u + sw128_offset(e, d & 31)) = v;
+  }
+  for (int i = threadIdx.x; i < 4 * 16 * 32; i += kThreads) {      // rows 32..47 of every pixel atom: ones | zeros
+    const int atom = i / (16 * 32), rem = i - atom * 16 * 32, row = kE + (rem >> 5), col = rem & 31;
+    *reinterpret_cast<float*>(bx + atom * kAccN * 128 + sw128_offset(row, col)) = row == kE ? 1.f : 0.f;
+  }
+  for (int i = threadIdx.x; i < 4 * 128 * 32; i += kThreads) reinterpret_cast<float*>(adz)[i] = 0.f;
+  for (int d = threadIdx.x; d < DP; d += kThreads) {
+    s.bias[d] = d < D ? __ldg(bp + d) : -INFINITY;
+    s.cen[d] = d < D ? __ldg(centers + (size_t)b * D + d) : 0.f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s.tmem_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  constexpr uint32_t tm_z = 0, tm_dx = DP, tm_acc = DP + 32;
+  const uint32_t id_acc = make_idesc_tf32(128, kAccN, 0, 0);
+  const uint32_t id_dx = make_idesc_tf32(128, 32, 0, 0);
+  float dc[DP];
+#pragma unroll
+  for (int d = 0; d < DP; ++d) dc[d] = 0.f;
+  uint32_t ph_tma = 0, ph_mma = 0, ph_bx = 0, acc_on = 0;
+  float* dxb = d_x + (size_t)b * kE * n;
+  for (int t = t_begin; t < t_end; ++t) {
+    const int p0 = t * kTile;
+    const int p = p0 + warp * 32 + lane;
+    mbar_wait(s.bar_tma, ph_tma); ph_tma ^= 1;
+    split_x_tile(s);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (t + 1 < t_end) issue_x_tma(s, &map_mn, p0 + kTile, b * kE);
+      mbar_arrive_expect_tx(bar_bx, kXTile);   // the K-major x rows of the accumulator's B tile (free: previous MMAs waited)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tma_load_2d(bx + j * kAccN * 128, &map_k, p0 + 32 * j, b * kE, bar_bx);
+      tc_fence_after();
+      issue_xm(smem_u32(s.x_hi), smem_u32(s.x_lo), smem_u32(s.k_hi), smem_u32(s.k_lo), tmem + tm_z, DP);
+      umma_commit(s.bar_mma);
+    }
+    mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+    // pass A: online max / sum / expectation over the logits
+    float m = -INFINITY, se = 0.f, sc = 0.f;
+#pragma unroll
+    for (int c = 0; c < DP; c += 16) {
+      float v[16];
+      tmem_ld16(lane_base + tm_z + c, v);
+      tmem_wait_ld();
+      float cm = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { v[i] += s.bias[c + i]; cm = fmaxf(cm, v[i]); }
+      if (cm > m) { const float r = __expf(m - cm); se *= r; sc *= r; m = cm; }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { const float e = __expf(v[i] - m); se += e; sc = fmaf(e, s.cen[c + i], sc); }
+    }
+    const float inv = 1.f / se, pr = sc * inv;
+    const float g = p < n ? __ldg(g_pred + (size_t)b * n + p) * inv : 0.f;   // g / sum folded together
+    // pass B: pi g, dz -> registers (d_centers), TMEM (A operand of d_x) and transposed shared memory (A operand of dM)
+#pragma unroll
+    for (int c = 0; c < DP; c += 16) {
+      float v[16];
+      tmem_ld16(lane_base + tm_z + c, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float pg = __expf(v[i] + s.bias[c + i] - m) * g;
+        dc[c + i] += pg;
+        v[i] = pg * (s.cen[c + i] - pr);
+        *reinterpret_cast<float*>(adz + warp * 128 * 128 + sw128_offset(c + i, lane)) = v[i];
+      }
+      tmem_st16(lane_base + tm_z + c, v);
+    }
+    tmem_wait_st();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      mbar_wait(bar_bx, ph_bx);
+      const uint32_t a0 = smem_u32(adz), b0 = smem_u32(bx), mt = smem_u32(mT);
+#pragma unroll
+      for (int k = 0; k < kTile / 8; ++k) {     // accumulator += dz^T [x | 1]      (K = 128 pixels)
+        umma_tf32_ss(tmem + tm_acc, make_desc_sw128(a0 + (k >> 2) * 128 * 128 + (k & 3) * 32, 16, 1024),
+                     make_desc_sw128(b0 + (k >> 2) * kAccN * 128 + (k & 3) * 32, 16, 1024), id_acc, acc_on);
+        acc_on = 1;
+      }
+#pragma unroll
+      for (int k = 0; k < DP / 8; ++k)          // d_x tile = dz M               (K = DP bins, A from TMEM)
+        umma_tf32_ts(tmem + tm_dx, tmem + tm_z + k * 8,
+                     make_desc_sw128(mt + (uint32_t)(k >> 2) * 32u * 128u + (uint32_t)(k & 3) * 32u, 16, 1024), id_dx, k > 0);
+      umma_commit(s.bar_mma);
+    }
+    ph_bx ^= 1;
+    mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < kE; c += 16) {
+      float v[16];
+      tmem_ld16(lane_base + tm_dx + c, v);
+      tmem_wait_ld();
+      if (p < n) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dxb[(size_t)(c + i) * n + p] = v[i];
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  // accumulator rows (lane = bin d): dM, d_bp
+  const int d_row = threadIdx.x;
+  const bool have = t_begin < t_end;
+#pragma unroll
+  for (int c = 0; c < kAccN; c += 16) {
+    float v[16];
+    if (have) {
+      tmem_ld16(lane_base + tm_acc + c, v);
+      tmem_wait_ld();
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    }
+    if (d_row < D) {
+      if (c < kE) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) part_dM[((size_t)cta * D + d_row) * kE + c + i] = v[i];
+      } else {
+        part_db[(size_t)cta * D + d_row] = v[0];
+      }
+    }
+  }
+  // d_centers: reduce the per-thread (per pixel slot) accumulators over the 128 threads through shared memory
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(adz);   // [128 threads][DP], padded row pitch DP+1
+#pragma unroll
+  for (int d = 0; d < DP; ++d) red[threadIdx.x * (DP + 1) + d] = dc[d];
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += kThreads) {
+    float acc = 0.f;
+    for (int tt = 0; tt < kThreads; ++tt) acc += red[tt * (DP + 1) + d];
+    part_dc[(size_t)cta * D + d] = acc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pass 2 (summary path):  a = softmax_pixels(y),  dy = a (t - delta),  t = x^T ds^T
+//   d_x (+)= dy K + a ds ,   d_K_2 += dy^T x
+// TMEM: [0,QP) y -> dy   [QP,2QP) t -> a   [2QP,2QP+32) d_x tile   [2QP+32,2QP+64) d_K accumulator
+// ------------------------------------------------------------------------------------------------
+template <int QP>
+struct BwdSumSmem {
+  static constexpr size_t x_raw = 0, x_hi = kXTile, x_lo = 2 * kXTile, x_k = 3 * kXTile, k_hi = 4 * kXTile,
+                          k_lo = k_hi + QP * 128, ds = k_lo + QP * 128, kT = ds + QP * 128,
+                          dsT = kT + (QP / 32) * 32 * 128, dyT = dsT + (QP / 32) * 32 * 128, tail = dyT + 4 * 128 * 128;
+  static constexpr size_t bytes = 1024 + tail + 3 * QP * 4 + 64;
+};
+
+template <int QP>
+__global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
+    const __grid_constant__ CUtensorMap map_mn, const __grid_constant__ CUtensorMap map_k,
+    const float* __restrict__ queries, const float* __restrict__ summary, const float* __restrict__ row_max,
+    const float* __restrict__ row_sum, const float* __restrict__ d_summary, int Q, int n, int tiles_per_chunk,
+    int accumulate, float* __restrict__ d_x, float* __restrict__ part_dK /*[cta][Q][32]*/) {
+  using L = BwdSumSmem<QP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Smem s;
+  s.x_raw = base + L::x_raw; s.x_hi = base + L::x_hi; s.x_lo = base + L::x_lo;
+  s.k_hi = base + L::k_hi; s.k_lo = base + L::k_lo;
+  uint8_t* x_k = base + L::x_k;
+  uint8_t* ds = base + L::ds;
+  uint8_t* kT = base + L::kT;
+  uint8_t* dsT = base + L::dsT;
+  uint8_t* dyT = base + L::dyT;
+  float* mq = reinterpret_cast<float*>(base + L::tail);
+  float* il = mq + QP;
+  float* dl = il + QP;
+  s.bar_tma = reinterpret_cast<uint64_t*>(dl + QP);
+  s.bar_mma = s.bar_tma + 1;
+  uint64_t* bar_xk = s.bar_tma + 2;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar_tma + 3);
+  const int b = blockIdx.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kCols = 512;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_mn);
+    tma_prefetch_desc(&map_k);
+    mbar_init(s.bar_tma, 1);
+    mbar_init(s.bar_mma, 1);
+    mbar_init(bar_xk, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(s.tmem_slot, kCols);
+    tmem_relinquish();
+  }
+  const int t_begin = blockIdx.x * tiles_per_chunk;
+  const int t_end = min((n + kTile - 1) / kTile, t_begin + tiles_per_chunk);
+  __syncthreads();
+  if (threadIdx.x == 0 && t_begin < t_end) issue_x_tma(s, &map_mn, t_begin * kTile, b * kE);
+  stage_queries(s, queries + (size_t)b * Q * kE, Q, QP);
+  {
+    const float* qb = queries + (size_t)b * Q * kE;
+    const float* dsb = d_summary + (size_t)b * Q * kE;
+    for (int idx = threadIdx.x; idx < QP * kE; idx += kThreads) {
+      const int q = idx >> 5, e = idx & 31;
+      const float kv = q < Q ? __ldg(qb + idx) : 0.f;
+      const float dv = q < Q ? __ldg(dsb + idx) : 0.f;
+      *reinterpret_cast<float*>(ds + sw128_offset(q, e)) = dv;
+      const uint32_t offT = (uint32_t)(q >> 5) * 32u * 128u + sw128_offset(e, q & 31);
+      *reinterpret_cast<float*>(kT + offT) = kv;
+      *reinterpret_cast<float*>(dsT + offT) = dv;
+    }
+    for (int idx = threadIdx.x; idx < 4 * 128 * 32; idx += kThreads) reinterpret_cast<float*>(dyT)[idx] = 0.f;
+    for (int q = threadIdx.x; q < QP; q += kThreads) {
+      float m = 0.f, inv = 0.f, delta = 0.f;
+      if (q < Q) {
+        m = __ldg(row_max + b * Q + q);
+        inv = 1.f / __ldg(row_sum + b * Q + q);
+        for (int e = 0; e < kE; ++e)
+          delta = fmaf(__ldg(dsb + q * kE + e), __ldg(summary + ((size_t)b * Q + q) * kE + e), delta);
+      }
+      mq[q] = m; il[q] = inv; dl[q] = delta;
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s.tmem_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  constexpr uint32_t tm_y = 0, tm_t = QP, tm_dx = 2 * QP, tm_dk = 2 * QP + 32;
+  const uint32_t id_t = make_idesc_tf32(128, QP, 1, 0);
+  const uint32_t id_32 = make_idesc_tf32(128, 32, 0, 0);
+  uint32_t ph_tma = 0, ph_mma = 0, ph_xk = 0, acc_dk = 0;
+  float* dxb = d_x + (size_t)b * kE * n;
+  for (int t = t_begin; t < t_end; ++t) {
+    const int p0 = t * kTile;
+    const int p = p0 + warp * 32 + lane;
+    mbar_wait(s.bar_tma, ph_tma); ph_tma ^= 1;
+    split_x_tile(s);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (t + 1 < t_end) issue_x_tma(s, &map_mn, p0 + kTile, b * kE);
+      mbar_arrive_expect_tx(bar_xk, kXTile);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tma_load_2d(x_k + j * kXBlock, &map_k, p0 + 32 * j, b * kE, bar_xk);
+      tc_fence_after();
+      issue_y(s, tmem + tm_y, QP);
+      const uint32_t xh = smem_u32(s.x_hi), dsa = smem_u32(ds);
+#pragma unroll
+      for (int k = 0; k < kE / 8; ++k)
+        umma_tf32_ss(tmem + tm_t, make_desc_mn32(xh + k * 1024, kXBlock), make_desc_sw128(dsa + k * 32, 16, 1024), id_t,
+                     k > 0);
+      umma_commit(s.bar_mma);
+    }
+    mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < QP; c += 16) {
+      float yv[16], tt[16];
+      tmem_ld16(lane_base + tm_y + c, yv);
+      tmem_ld16(lane_base + tm_t + c, tt);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int q = c + i;
+        const float a = (q < Q && p < n) ? __expf(yv[i] - mq[q]) * il[q] : 0.f;
+        yv[i] = a * (tt[i] - dl[q]);
+        tt[i] = a;
+        *reinterpret_cast<float*>(dyT + warp * 128 * 128 + sw128_offset(q, lane)) = yv[i];
+      }
+      tmem_st16(lane_base + tm_y + c, yv);
+      tmem_st16(lane_base + tm_t + c, tt);
+    }
+    tmem_wait_st();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      mbar_wait(bar_xk, ph_xk);
+      const uint32_t a0 = smem_u32(dyT), xk = smem_u32(x_k), kt = smem_u32(kT), dst = smem_u32(dsT);
+#pragma unroll
+      for (int k = 0; k < kTile / 8; ++k) {
+        umma_tf32_ss(tmem + tm_dk, make_desc_sw128(a0 + (k >> 2) * 128 * 128 + (k & 3) * 32, 16, 1024),
+                     make_desc_sw128(xk + (k >> 2) * kXBlock + (k & 3) * 32, 16, 1024), id_32, acc_dk);
+        acc_dk = 1;
+      }
+#pragma unroll
+      for (int k = 0; k < QP / 8; ++k)
+        umma_tf32_ts(tmem + tm_dx, tmem + tm_y + k * 8,
+                     make_desc_sw128(kt + (k >> 2) * 32 * 128 + (k & 3) * 32, 16, 1024), id_32, k > 0);
+#pragma unroll
+      for (int k = 0; k < QP / 8; ++k)
+        umma_tf32_ts(tmem + tm_dx, tmem + tm_t + k * 8,
+                     make_desc_sw128(dst + (k >> 2) * 32 * 128 + (k & 3) * 32, 16, 1024), id_32, 1);
+      umma_commit(s.bar_mma);
+    }
+    ph_xk ^= 1;
+    mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < kE; c += 16) {
+      float v[16];
+      tmem_ld16(lane_base + tm_dx + c, v);
+      tmem_wait_ld();
+      if (p < n) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float* o = dxb + (size_t)(c + i) * n + p;
+          *o = accumulate ? *o + v[i] : v[i];
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  {
+    const int q = threadIdx.x;
+    float* out = part_dK + ((size_t)cta * Q + q) * kE;
+    const bool have = t_begin < t_end;
+#pragma unroll
+    for (int c = 0; c < kE; c += 16) {
+      float v[16];
+      if (have) {
+        tmem_ld16(lane_base + tm_dk + c, v);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      }
+      if (q < Q) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) out[c + i] = v[i];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kCols);
+}
+
 // ------------------------------------------------------------------------------------------------
 // energy maps  y[b,q,p]   (module-level FullQueryLayer output; also the bring-up kernel of this file)
 // ------------------------------------------------------------------------------------------------
@@ -1183,6 +1715,89 @@ int tc_bwd_dx_partials(const float* x, const float* queries, const float* Wp, co
   tcsql::sql_tc_bwd_dx_kernel<<<dim3(chunks, B), tcsql::kThreads, tcsql::kSmemDxBytes, st>>>(
       map_mn, map_k, queries, Wp, bp, centers, g_pred, summary, row_max, row_sum, d_summary, Q, D, n, tpc, d_x, part_dK);
   return check_launch("sql_tc_bwd_dx_kernel");
+}
+
+// ---- mixed-weight decomposition launchers
+int tc_pred_mix_fwd(const float* x, const float* Mx, const float* bp, const float* centers, int B, int D, int n,
+                    float* pred, cudaStream_t st) {
+  SQLX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
+  const int DP = (D + 15) / 16 * 16;
+  const size_t smem = tcsql::smem_p2_bytes(DP);
+  const uint32_t cols = pow2_cols(DP);
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  per_sm = per_sm > (int)(512 / cols) ? (int)(512 / cols) : per_sm;
+  per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);
+  const int tiles = ceil_div(n, tcsql::kTile);
+  int chunks = (per_sm * kNumSMs) / B;
+  chunks = chunks < 1 ? 1 : (chunks > tiles ? tiles : chunks);
+  const int tpc = ceil_div(tiles, chunks);
+  chunks = ceil_div(tiles, tpc);
+  CUtensorMap xmap;
+  if (int e = make_tensor_map_2d(&xmap, x, (uint64_t)B * tcsql::kE, (uint64_t)n, 32, 32, 1)) return e;
+  static bool configured = false;
+  if (!configured) {
+    if (int e = raise_smem(tcsql::sql_tc_pred2_kernel)) return e;
+    configured = true;
+  }
+  ProfScope prof("sql_tc_pred_kernel", st);
+  tcsql::sql_tc_pred2_kernel<<<dim3(chunks, B), tcsql::kThreads, smem, st>>>(xmap, Mx, bp, centers, D, DP, n, tpc, cols, pred);
+  return check_launch("sql_tc_pred2_kernel");
+}
+
+template <int DP>
+int launch_bwd_pred(const CUtensorMap& map_mn, const CUtensorMap& map_k, const float* Mx, const float* bp,
+                    const float* centers, const float* g_pred, int B, int D, int n, int chunks, int tpc, float* d_x,
+                    float* part_dM, float* part_db, float* part_dc, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    if (int e = raise_smem(tcsql::sql_tc_bwd_pred_kernel<DP>)) return e;
+    configured = true;
+  }
+  ProfScope prof("sql_tc_bwd_pred_kernel", st);
+  tcsql::sql_tc_bwd_pred_kernel<DP><<<dim3(chunks, B), tcsql::kThreads, tcsql::BwdPredSmem<DP>::bytes, st>>>(
+      map_mn, map_k, Mx, bp, centers, g_pred, D, n, tpc, d_x, part_dM, part_db, part_dc);
+  return check_launch("sql_tc_bwd_pred_kernel");
+}
+
+int tc_bwd_pred_mix(const float* x, const float* Mx, const float* bp, const float* centers, const float* g_pred, int B,
+                    int D, int n, float* d_x, float* part_dM, float* part_db, float* part_dc, int chunks, int tpc,
+                    cudaStream_t st) {
+  SQLX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
+  CUtensorMap map_mn, map_k;
+  if (int e = make_tensor_map_2d(&map_mn, x, (uint64_t)B * tcsql::kE, (uint64_t)n, 32, 32, 1)) return e;
+  if (int e = make_tensor_map_2d(&map_k, x, (uint64_t)B * tcsql::kE, (uint64_t)n, 32, 32, 0)) return e;
+  if (D <= 64)
+    return launch_bwd_pred<64>(map_mn, map_k, Mx, bp, centers, g_pred, B, D, n, chunks, tpc, d_x, part_dM, part_db, part_dc, st);
+  return launch_bwd_pred<128>(map_mn, map_k, Mx, bp, centers, g_pred, B, D, n, chunks, tpc, d_x, part_dM, part_db, part_dc, st);
+}
+
+template <int QP>
+int launch_bwd_sum(const CUtensorMap& map_mn, const CUtensorMap& map_k, const float* queries, const float* summary,
+                   const float* row_max, const float* row_sum, const float* d_summary, int B, int Q, int n, int chunks,
+                   int tpc, int accumulate, float* d_x, float* part_dK, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    if (int e = raise_smem(tcsql::sql_tc_bwd_sum_kernel<QP>)) return e;
+    configured = true;
+  }
+  ProfScope prof("sql_tc_bwd_sum_kernel", st);
+  tcsql::sql_tc_bwd_sum_kernel<QP><<<dim3(chunks, B), tcsql::kThreads, tcsql::BwdSumSmem<QP>::bytes, st>>>(
+      map_mn, map_k, queries, summary, row_max, row_sum, d_summary, Q, n, tpc, accumulate, d_x, part_dK);
+  return check_launch("sql_tc_bwd_sum_kernel");
+}
+
+int tc_bwd_sum(const float* x, const float* queries, const float* summary, const float* row_max, const float* row_sum,
+               const float* d_summary, int B, int Q, int n, int accumulate, float* d_x, float* part_dK, int chunks, int tpc,
+               cudaStream_t st) {
+  SQLX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
+  CUtensorMap map_mn, map_k;
+  if (int e = make_tensor_map_2d(&map_mn, x, (uint64_t)B * tcsql::kE, (uint64_t)n, 32, 32, 1)) return e;
+  if (int e = make_tensor_map_2d(&map_k, x, (uint64_t)B * tcsql::kE, (uint64_t)n, 32, 32, 0)) return e;
+  if (Q <= 64)
+    return launch_bwd_sum<64>(map_mn, map_k, queries, summary, row_max, row_sum, d_summary, B, Q, n, chunks, tpc, accumulate,
+                              d_x, part_dK, st);
+  return launch_bwd_sum<128>(map_mn, map_k, queries, summary, row_max, row_sum, d_summary, B, Q, n, chunks, tpc, accumulate,
+                             d_x, part_dK, st);
 }
 }  // namespace sqlx
 

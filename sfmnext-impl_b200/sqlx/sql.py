@@ -80,6 +80,60 @@ def bwd_dx(x, queries, Wp=None, bp=None, centers=None, g_pred=None, summary=None
     return d_x, d_q
 
 
+# ----------------------------------------------------------------------------- mixed-weight decomposition (tensor cores)
+def use_mix(E, Q, D, n):
+    """True when the tensor-core kernels take the shape: the decoder tail then runs as
+    logits = (Wp K) x + b (regression contracts over E = 32, no Wp tiles on chip; csrc/sql_tc.cu)."""
+    L = lib()
+    on = L.sqlx_sql_set_tensor_cores(1)
+    L.sqlx_sql_set_tensor_cores(on)
+    return bool(on) and bool(L.sqlx_sql_tc_supported(E, Q, D, n))
+
+
+def _mix_workspace(B, Q, D, n, device):
+    nbytes = lib().sqlx_sql_mix_workspace_bytes(B, Q, D, n)
+    return torch.empty(nbytes, device=device, dtype=torch.uint8), nbytes
+
+
+def pred_mix_fwd(x, Mx, bp, centers):
+    B, E, h, w = x.shape
+    D = Mx.shape[1]
+    pred = torch.empty(B, 1, h, w, device=x.device, dtype=torch.float32)
+    check(lib().sqlx_sql_pred_mix_fwd(ptr(x), ptr(Mx), ptr(bp), ptr(centers), B, E, D, h * w, ptr(pred), stream_ptr()),
+          "sqlx_sql_pred_mix_fwd")
+    return pred
+
+
+def bwd_pred_mix(x, Mx, bp, centers, g_pred):
+    B, E, h, w = x.shape
+    D = Mx.shape[1]
+    dev = x.device
+    d_M = torch.empty_like(Mx)
+    d_bp = torch.empty(D, device=dev, dtype=torch.float32)
+    d_centers = torch.empty(B, D, device=dev, dtype=torch.float32)
+    d_x = torch.empty_like(x)
+    ws, nbytes = _mix_workspace(B, 1, D, h * w, dev)
+    check(lib().sqlx_sql_bwd_pred_mix(ptr(x), ptr(Mx), ptr(bp), ptr(centers), ptr(g_pred), B, E, D, h * w, ptr(d_M),
+                                      ptr(d_bp), ptr(d_centers), ptr(d_x), ptr(ws), nbytes, stream_ptr()),
+          "sqlx_sql_bwd_pred_mix")
+    return d_M, d_bp, d_centers, d_x
+
+
+def bwd_summary(x, queries, summary, row_max, row_sum, d_summary, d_x=None):
+    """Summary-path backward; accumulates into d_x when given (else writes a fresh tensor)."""
+    B, E, h, w = x.shape
+    Q = queries.shape[1]
+    accumulate = d_x is not None
+    if d_x is None:
+        d_x = torch.empty_like(x)
+    d_q = torch.empty_like(queries)
+    ws, nbytes = _mix_workspace(B, Q, 0, h * w, x.device)
+    check(lib().sqlx_sql_bwd_summary(ptr(x), ptr(queries), ptr(summary), ptr(row_max), ptr(row_sum), ptr(d_summary), B, E,
+                                     Q, h * w, int(accumulate), ptr(d_x), ptr(d_q), ptr(ws), nbytes, stream_ptr()),
+          "sqlx_sql_bwd_summary")
+    return d_x, d_q
+
+
 # ----------------------------------------------------------------------------- module-level FullQueryLayer
 class _FullQuery(torch.autograd.Function):
     @staticmethod
@@ -135,24 +189,40 @@ class _SqlTail(torch.autograd.Function):
             s_leaf = summary.detach().requires_grad_(True)
             centers = centers_fn(s_leaf)
         cc = _f32c(centers)
-        pred = pred_fwd(xc, qc, Wc, bc, cc)
-        ctx.save_for_backward(xc, qc, Wc, bc, cc, summary, row_max, row_sum)
+        B, E, h, w = xc.shape
+        ctx.mix = use_mix(E, qc.shape[1], Wc.shape[0], h * w)
+        if ctx.mix:
+            Mx = torch.matmul(Wc, qc)                    # [B,D,E] = Wp . K   (tiny; cuBLAS fp32)
+            pred = pred_mix_fwd(xc, Mx, bc, cc)
+            ctx.save_for_backward(xc, qc, Wc, bc, cc, summary, row_max, row_sum, Mx)
+        else:
+            pred = pred_fwd(xc, qc, Wc, bc, cc)
+            ctx.save_for_backward(xc, qc, Wc, bc, cc, summary, row_max, row_sum)
         ctx.graph = (s_leaf, centers)
         ctx.params = params
         return pred
 
     @staticmethod
     def backward(ctx, g_pred):
-        xc, qc, Wc, bc, cc, summary, row_max, row_sum = ctx.saved_tensors
         s_leaf, centers = ctx.graph
         g = _f32c(g_pred)
-        d_centers, d_Wp, d_bp = bwd_reduce(xc, qc, Wc, bc, cc, g)
         need = [p for p in ctx.params if p.requires_grad]
-        grads = torch.autograd.grad(centers, [s_leaf] + need, d_centers, allow_unused=True)
-        d_summary = grads[0]
-        if d_summary is None:
-            d_summary = torch.zeros_like(summary)
-        d_x, d_q = bwd_dx(xc, qc, Wc, bc, cc, g, summary, row_max, row_sum, _f32c(d_summary))
+        if ctx.mix:
+            xc, qc, Wc, bc, cc, summary, row_max, row_sum, Mx = ctx.saved_tensors
+            d_M, d_bp, d_centers, d_x = bwd_pred_mix(xc, Mx, bc, cc, g)
+            d_Wp = torch.einsum("bde,bqe->dq", d_M, qc)
+            grads = torch.autograd.grad(centers, [s_leaf] + need, d_centers, allow_unused=True)
+            d_summary = grads[0] if grads[0] is not None else torch.zeros_like(summary)
+            d_x, d_q = bwd_summary(xc, qc, summary, row_max, row_sum, _f32c(d_summary), d_x=d_x)
+            d_q = d_q + torch.matmul(Wc.t(), d_M)        # regression-path part of d_K:  Wp^T dM
+        else:
+            xc, qc, Wc, bc, cc, summary, row_max, row_sum = ctx.saved_tensors
+            d_centers, d_Wp, d_bp = bwd_reduce(xc, qc, Wc, bc, cc, g)
+            grads = torch.autograd.grad(centers, [s_leaf] + need, d_centers, allow_unused=True)
+            d_summary = grads[0]
+            if d_summary is None:
+                d_summary = torch.zeros_like(summary)
+            d_x, d_q = bwd_dx(xc, qc, Wc, bc, cc, g, summary, row_max, row_sum, _f32c(d_summary))
         it = iter(grads[1:])
         d_params = tuple((next(it) if p.requires_grad else None) for p in ctx.params)
         ctx.graph = None

@@ -96,3 +96,39 @@ def test_summary_tc(cfg):
     if B * h * w <= 100000:
         _, ref = O.full_query(x.double(), q.double())
         assert float((s_tc.cpu().double() - ref).abs().max()) < 2e-5 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, h=24, w=40, Q=64, D=64),
+    dict(B=1, h=17, w=20, Q=120, D=128),
+    dict(B=2, h=16, w=24, Q=128, D=128),
+    dict(B=3, h=8, w=12, Q=12, D=16),
+])
+def test_tail_paths_agree(cfg):
+    """sql_tail through the mixed-weight tensor-core decomposition vs the exact-fp32 CUDA-core kernels:
+    forward depth and every gradient (x, queries, Wp, bp, MLP weights)."""
+    import sqlx
+    B, h, w, Q, D = (cfg[k] for k in ("B", "h", "w", "Q", "D"))
+    g = torch.Generator().manual_seed(5 + Q)
+    x = torch.randn(B, 32, h, w, generator=g)
+    q = 0.4 * torch.randn(B, Q, 32, generator=g)
+    Wp = 0.3 * torch.randn(D, Q, generator=g)
+    bp = 0.1 * torch.randn(D, generator=g)
+    W1 = torch.randn(D, Q * 32, generator=g) / (Q * 32) ** 0.5
+    gout = torch.randn(B, 1, h, w, generator=g)
+    F = torch.nn.functional
+    res = {}
+    for on in (1, 0):
+        prev = _set_tc(on)
+        try:
+            leaves = [t.clone().cuda().requires_grad_(True) for t in (x, q, Wp, bp, W1)]
+            xc, qc, Wc, bc, W1c = leaves
+            pred = sqlx.sql_tail(xc, qc, Wc, bc, lambda s: sqlx.bin_centers(F.linear(s.reshape(B, -1), W1c), 0.01, 80.0), (W1c,))
+            grads = torch.autograd.grad((pred * gout.cuda()).sum(), leaves)
+            res[on] = (pred.detach(), grads)
+        finally:
+            _set_tc(prev)
+    assert float(((res[1][0] - res[0][0]) / res[0][0]).abs().max()) < 5e-5
+    for a, b, nm in zip(res[1][1], res[0][1], ("x", "queries", "Wp", "bp", "W1")):
+        rel = float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+        assert rel < 2e-3, (nm, rel)

@@ -1412,7 +1412,7 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
     }
     mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < QP; c += 16) {
       float yv[16], tt[16];
       tmem_ld16(lane_base + tm_y + c, yv);
@@ -1462,11 +1462,15 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
       tmem_ld16(lane_base + tm_dx + c, v);
       tmem_wait_ld();
       if (p < n) {
+        if (accumulate) {   // all loads first: one round trip instead of 16 dependent ones
+          float prev[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float* o = dxb + (size_t)(c + i) * n + p;
-          *o = accumulate ? *o + v[i] : v[i];
+          for (int i = 0; i < 16; ++i) prev[i] = __ldcg(dxb + (size_t)(c + i) * n + p);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += prev[i];
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dxb[(size_t)(c + i) * n + p] = v[i];
       }
     }
     tc_fence_before();

@@ -47,7 +47,7 @@ def test_argument_validation_without_gpu():
     assert b"query_nums" in L.sqlx_last_error()
     assert L.sqlx_sql_workspace_bytes(12, 32, 64, 64, 30720) > 0
     desc = sqlx._lib.PhotoDesc(2, 192, 640, 96, 320, 7, 3, 1, 0.85, 0.15, 1e-5, 1e-7)
-    assert L.sqlx_photo_fwd(ctypes.byref(desc), None, None, None, None, None, None, None, None, None, None, None, 0,
+    assert L.sqlx_photo_fwd(ctypes.byref(desc), None, None, None, None, None, None, None, None, None, None, None, None, 0,
                             None) == -1
     assert b"S=7" in L.sqlx_last_error()
 

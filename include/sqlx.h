@@ -91,7 +91,9 @@ int sqlx_ssim_bwd(const float* x, const float* y, const float* g_out, int B, int
  * replaces layers.py:210-215,247-258,31-46 + trainer.py:395-396,423-435,444-451,474-532.
  *   depth_lr  [B,1,h,w]       network output at this scale (this IS depth: trainer.py:399-402)
  *   target    [B,3,H,W]       inputs[("color",0,0)]
- *   sources   host array of S device pointers, each [B,3,H,W]   inputs[("color",f,0)]
+ *   sources_rgba  host array of S device pointers, each a [B,H,W,4] pixel-interleaved copy of inputs[("color",f,0)]
+ *             made by sqlx_pack_rgba (16-byte aligned): one 128-bit load per bilinear tap.  The frames are packed
+ *             once per step and shared by every loss scale, forward and backward.
  *   K, inv_K  [B,4,4]
  *   T         [B,S,4,4]       camera transforms (already rescaled by mean inverse depth when posecnn)
  *   identity  [B,S,H,W] or NULL (no automask): sqlx_reprojection_loss_fwd(source_f, target), WITHOUT noise
@@ -99,13 +101,16 @@ int sqlx_ssim_bwd(const float* x, const float* y, const float* g_out, int B, int
  * outputs
  *   loss_sum  [1]  double?  no: float, = sum over b,v,u of the per-pixel minimum (caller divides by B*H*W)
  *   argmin    [B,H,W] uint8: index into cat(identity, reprojection) exactly as torch.min(combined,dim=1)
- *   ssim_coef [B,S,3,3,H,W] or NULL: d SSIM/d(mean_x, E[x^2], E[xy]) per source / channel / pixel.  When given to
- *             sqlx_photo_bwd as well, the backward is a cheap adjoint box filter of these planes instead of a
- *             recomputation of the warp and the box sums on a doubled halo (36*S bytes per pixel of extra traffic).
+ *   ssim_coef [B,S,3,3,H,W] (sqlx_photo_coef_bytes) or NULL for a forward-only call: d SSIM/d(mean_x, E[x^2], E[xy])
+ *             per source / channel / pixel.  sqlx_photo_bwd is an arg-min masked adjoint box filter of these planes
+ *             (no recomputation of the warp and the box sums on a doubled halo).
  */
 size_t sqlx_photo_workspace_bytes(const sqlx_photo_desc* desc);
+size_t sqlx_photo_coef_bytes(const sqlx_photo_desc* desc);
+/* [B,3,H,W] planar frame -> [B,H,W,4] pixel-interleaved (r,g,b,0) frame; `out` 16-byte aligned. */
+int sqlx_pack_rgba(const float* image, int B, int H, int W, float* out, void* stream);
 int sqlx_photo_fwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
-                   const float* const* sources, const float* K, const float* inv_K, const float* T,
+                   const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
                    const float* identity, const float* noise,
                    float* loss_sum, uint8_t* argmin, float* ssim_coef, void* workspace, size_t workspace_bytes,
                    void* stream);
@@ -116,7 +121,7 @@ int sqlx_photo_fwd(const sqlx_photo_desc* desc, const float* depth_lr, const flo
  *   d_T        [B,S,4,4] overwritten     (gradient wrt T; rows 3 are zero)
  */
 int sqlx_photo_bwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
-                   const float* const* sources, const float* K, const float* inv_K, const float* T,
+                   const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
                    const uint8_t* argmin, const float* ssim_coef, const float* g_loss, float scale,
                    float* d_depth_lr, float* d_T, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -151,19 +156,20 @@ typedef struct sqlx_pose_inputs {
   uint32_t invert_mask;                        /* bit s set: invert=True for source s (frame_id < 0, trainer.py:336) */
 } sqlx_pose_inputs;
 
-/* `saved` (sqlx_scale_saved_bytes) carries T, depth statistics and smoothness sums from forward to backward;
+/* `sources_rgba`: as for sqlx_photo_fwd (sqlx_pack_rgba copies).
+ * `saved` (sqlx_scale_saved_bytes) carries T, depth statistics and smoothness sums from forward to backward;
  * `workspace` (sqlx_scale_workspace_bytes) is scratch.  loss: device scalar [1].  argmin [B,H,W] u8. */
 size_t sqlx_scale_saved_bytes(const sqlx_scale_desc* desc);
 size_t sqlx_scale_workspace_bytes(const sqlx_scale_desc* desc);
 int sqlx_scale_loss_fwd(const sqlx_scale_desc* desc, const float* depth_lr, const float* target,
-                        const float* const* sources, const float* color_s, const float* K, const float* inv_K,
+                        const float* const* sources_rgba, const float* color_s, const float* K, const float* inv_K,
                         const sqlx_pose_inputs* poses, const float* identity, const float* noise, float* loss,
                         uint8_t* argmin, void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes,
                         void* stream);
 /* g_loss: device scalar, upstream gradient of loss.  d_depth_lr [B,h,w] overwritten; d_axisangle[s], d_translation[s]
  * [B,3] overwritten for pose-net sources (entries may be NULL). */
 int sqlx_scale_loss_bwd(const sqlx_scale_desc* desc, const float* depth_lr, const float* target,
-                        const float* const* sources, const float* color_s, const float* K, const float* inv_K,
+                        const float* const* sources_rgba, const float* color_s, const float* K, const float* inv_K,
                         const sqlx_pose_inputs* poses, const uint8_t* argmin, const float* g_loss, const void* saved,
                         float* d_depth_lr, float* const* d_axisangle, float* const* d_translation, void* workspace,
                         size_t workspace_bytes, void* stream);

@@ -1,5 +1,5 @@
 // Photometric forward kernels:
-//   photo_fwd_kernel        fused upsample -> backproject -> project -> warp -> SSIM+L1 -> min(identity) -> sum
+//   (the fused forward / backward kernels live in photo_v3.cu)
 //   reproj_loss_kernel      reprojection loss of two given images (identity losses, compute_reprojection_loss)
 //   ssim_map_kernel         full SSIM map (module-level layers.SSIM drop-in)
 //   warp_kernel             materialise depth_up / sample grid / warped colour (what Trainer.log reads)
@@ -9,24 +9,6 @@
 
 namespace sqlx {
 
-// ------------------------------------------------------------------------------------------------
-// fused forward
-// ------------------------------------------------------------------------------------------------
-struct PhotoFwdParams {
-  sqlx_photo_desc d;
-  const float* depth_lr;
-  const float* target;
-  const float* src[SQLX_MAX_SOURCES];
-  const float* K;
-  const float* invK;
-  const float* T;
-  const float* identity;
-  const float* noise;
-  float* partial;      // [gridDim.z*gridDim.y*gridDim.x]
-  uint8_t* argmin;
-  float* coef;         // optional [B][S][3 ch][3][H][W]: d SSIM / d(mean_x, E[x^2], E[xy]) for the backward kernel
-};
-
 template <int R, int TH, int TW, int NT>
 struct FwdCfg {
   static constexpr int PH = TH + 2 * R, PW = TW + 2 * R;
@@ -34,159 +16,8 @@ struct FwdCfg {
   static constexpr int PLANE = PH * LD;
   static constexpr int HB = PH * TW;
   static constexpr int PPT = (TH * TW) / NT;
-  static constexpr size_t smem_bytes = sizeof(float) * (7 * PLANE + 5 * HB + 32) + sizeof(Camera) * SQLX_MAX_SOURCES;
   static_assert((TH * TW) % NT == 0, "tile must be a multiple of the block size");
 };
-
-template <int R, int TH, int TW, int NT>
-__global__ void __launch_bounds__(NT) photo_fwd_kernel(const PhotoFwdParams p) {
-  using C = FwdCfg<R, TH, TW, NT>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* dpl = reinterpret_cast<float*>(smem_raw);
-  float* tg = dpl + C::PLANE;           // 3 planes
-  float* wp = tg + 3 * C::PLANE;        // 3 planes
-  float* hb = wp + 3 * C::PLANE;        // 5 planes of HB
-  float* red = hb + 5 * C::HB;
-  Camera* cams = reinterpret_cast<Camera*>(red + 32);
-
-  const int H = p.d.H, W = p.d.W, S = p.d.S;
-  const int b = blockIdx.z;
-  const int v0 = blockIdx.y * TH, u0 = blockIdx.x * TW;
-  const size_t plane = (size_t)H * W;
-  const bool automask = p.d.flags & SQLX_AUTOMASK;
-  const bool avg = p.d.flags & SQLX_AVG_REPROJ;
-
-  if (threadIdx.x < S) {
-    load_camera(p.K + b * 16, p.invK + b * 16, p.T + ((size_t)b * S + threadIdx.x) * 16, cams[threadIdx.x]);
-  }
-  stage_depth<C::PH, C::PW, C::LD>(p.depth_lr + (size_t)b * p.d.h * p.d.w, p.d.h, p.d.w, H, W, v0 - R, u0 - R, dpl);
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
-    stage_plane<C::PH, C::PW, C::LD>(p.target + ((size_t)b * 3 + c) * plane, H, W, v0 - R, u0 - R, tg + c * C::PLANE);
-  __syncthreads();
-
-  // owned pixels: PPT vertically adjacent rows of one column (the vertical box sums share 2R of their rows)
-  int prow[C::PPT], pcol[C::PPT];
-  bool pin[C::PPT];
-#pragma unroll
-  for (int k = 0; k < C::PPT; ++k) {
-    prow[k] = (threadIdx.x / TW) * C::PPT + k;
-    pcol[k] = threadIdx.x % TW;
-    pin[k] = (v0 + prow[k] < H) && (u0 + pcol[k] < W);
-  }
-
-  // target box sums per channel, kept in registers
-  float Sy[3][C::PPT], Syy[3][C::PPT];
-  if (R > 0) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float* Y = tg + c * C::PLANE;
-      hpass_blocked<(R > 0 ? R : 1), C::PH, TW, C::LD, TW, false>(nullptr, Y, hb, hb + C::HB, nullptr);
-      __syncthreads();
-      vsum_multi<R, TW, C::PPT>(hb, prow[0], pcol[0], Sy[c]);
-      vsum_multi<R, TW, C::PPT>(hb + C::HB, prow[0], pcol[0], Syy[c]);
-      __syncthreads();
-    }
-  }
-
-  float best[C::PPT];
-  int arg[C::PPT];
-#pragma unroll
-  for (int k = 0; k < C::PPT; ++k) { best[k] = INFINITY; arg[k] = 0; }
-  int n_ident = 0;
-  if (automask) {
-    n_ident = avg ? 1 : S;
-#pragma unroll
-    for (int k = 0; k < C::PPT; ++k) {
-      if (!pin[k]) continue;
-      const size_t off = (size_t)(v0 + prow[k]) * W + (u0 + pcol[k]);
-      if (avg) {
-        float m = 0.f;
-        for (int s = 0; s < S; ++s) m += __ldg(p.identity + ((size_t)b * S + s) * plane + off);
-        m = m / (float)S + __ldg(p.noise + (size_t)b * plane + off) * p.d.noise_scale;
-        best[k] = m; arg[k] = 0;
-      } else {
-        for (int s = 0; s < S; ++s) {
-          const float v = __ldg(p.identity + ((size_t)b * S + s) * plane + off) +
-                          __ldg(p.noise + ((size_t)b * S + s) * plane + off) * p.d.noise_scale;
-          if (v < best[k]) { best[k] = v; arg[k] = s; }
-        }
-      }
-    }
-  }
-
-  float avg_acc[C::PPT];
-#pragma unroll
-  for (int k = 0; k < C::PPT; ++k) avg_acc[k] = 0.f;
-
-  for (int s = 0; s < S; ++s) {
-    stage_warped<C::PH, C::PW, C::LD>(p.src[s] + (size_t)b * 3 * plane, cams[s], dpl, H, W, v0 - R, u0 - R,
-                                      p.d.eps, wp, wp + C::PLANE, wp + 2 * C::PLANE);
-    __syncthreads();
-    float ssim_acc[C::PPT], l1_acc[C::PPT];
-#pragma unroll
-    for (int k = 0; k < C::PPT; ++k) { ssim_acc[k] = 0.f; l1_acc[k] = 0.f; }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float* X = wp + c * C::PLANE;
-      const float* Y = tg + c * C::PLANE;
-#pragma unroll
-      for (int k = 0; k < C::PPT; ++k) {
-        const int o = (prow[k] + R) * C::LD + pcol[k] + R;
-        l1_acc[k] += fabsf(Y[o] - X[o]);
-      }
-      if (R > 0) {
-        hpass_blocked<(R > 0 ? R : 1), C::PH, TW, C::LD, TW, true>(X, Y, hb, hb + C::HB, hb + 2 * C::HB);
-        __syncthreads();
-        float Sx[C::PPT], Sxx[C::PPT], Sxy[C::PPT];
-        vsum_multi<R, TW, C::PPT>(hb, prow[0], pcol[0], Sx);
-        vsum_multi<R, TW, C::PPT>(hb + C::HB, prow[0], pcol[0], Sxx);
-        vsum_multi<R, TW, C::PPT>(hb + 2 * C::HB, prow[0], pcol[0], Sxy);
-#pragma unroll
-        for (int k = 0; k < C::PPT; ++k) {
-          const SsimStats st = make_stats<R>(Sx[k], Sy[c][k], Sxx[k], Syy[c][k], Sxy[k]);
-          ssim_acc[k] += ssim_value(st);
-          if (p.coef && pin[k]) {   // saved so that the backward never recomputes the box sums (plane-major: coalesced)
-            const SsimGrad g = ssim_grad(st);
-            float* cp = p.coef + ((((size_t)b * S + s) * 3 + c) * 3) * plane + (size_t)(v0 + prow[k]) * W + (u0 + pcol[k]);
-            cp[0] = g.dmx; cp[plane] = g.dexx; cp[2 * plane] = g.dexy;
-          }
-        }
-        __syncthreads();
-      }
-    }
-    if (R == 0) __syncthreads();  // wp is overwritten by the next source
-#pragma unroll
-    for (int k = 0; k < C::PPT; ++k) {
-      float rho;
-      if (R > 0) rho = p.d.w_ssim * (ssim_acc[k] / 3.f) + p.d.w_l1 * (l1_acc[k] / 3.f);
-      else rho = l1_acc[k] / 3.f;
-      if (avg) {
-        avg_acc[k] += rho;
-      } else if (rho < best[k]) {
-        best[k] = rho; arg[k] = n_ident + s;
-      }
-    }
-  }
-  if (avg) {
-#pragma unroll
-    for (int k = 0; k < C::PPT; ++k) {
-      const float rho = avg_acc[k] / (float)S;
-      if (rho < best[k]) { best[k] = rho; arg[k] = n_ident; }
-    }
-  }
-
-  float local = 0.f;
-#pragma unroll
-  for (int k = 0; k < C::PPT; ++k) {
-    if (pin[k]) {
-      local += best[k];
-      p.argmin[(size_t)b * plane + (size_t)(v0 + prow[k]) * W + (u0 + pcol[k])] = (uint8_t)arg[k];
-    }
-  }
-  const float tot = block_sum(local, red);
-  if (threadIdx.x == 0) p.partial[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
-}
 
 // Deterministic final reduction of per-CTA partial sums (one block; double accumulation).
 __global__ void finalize_sum_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
@@ -378,21 +209,6 @@ using namespace sqlx;
 namespace {
 constexpr int kTH = 16, kTW = 32, kNT = 256;
 
-template <int R>
-int launch_photo_fwd(const PhotoFwdParams& p, cudaStream_t st) {
-  using C = FwdCfg<R, kTH, kTW, kNT>;
-  auto kern = photo_fwd_kernel<R, kTH, kTW, kNT>;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
-    configured = true;
-  }
-  dim3 grid(ceil_div(p.d.W, kTW), ceil_div(p.d.H, kTH), p.d.B);
-  ProfScope prof("photo_fwd_kernel", st);
-  kern<<<grid, kNT, C::smem_bytes, st>>>(p);
-  return check_launch("photo_fwd_kernel");
-}
-
 template <int R, bool MAP>
 int launch_reproj(const float* pred, const float* target, int B, int C_, int H, int W, float w_ssim, float w_l1,
                   float* out, cudaStream_t st, size_t out_bstride = 0) {
@@ -411,52 +227,6 @@ int launch_reproj(const float* pred, const float* target, int B, int C_, int H, 
   return check_launch("reproj_loss_kernel");
 }
 }  // namespace
-
-static int check_desc(const sqlx_photo_desc* d) {
-  SQLX_REQUIRE(d != nullptr, "desc is NULL");
-  SQLX_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->h > 0 && d->w > 0, "non-positive shape");
-  SQLX_REQUIRE(d->S >= 1 && d->S <= SQLX_MAX_SOURCES, "S=%d outside 1..%d", d->S, SQLX_MAX_SOURCES);
-  SQLX_REQUIRE(d->h <= d->H && d->w <= d->W, "depth map larger than the image is not supported");
-  SQLX_REQUIRE((d->flags & SQLX_NO_SSIM) || d->ssim_radius == 1 || d->ssim_radius == 3,
-               "ssim_radius must be 1 or 3 (got %d)", d->ssim_radius);
-  const int r = (d->flags & SQLX_NO_SSIM) ? 0 : d->ssim_radius;
-  SQLX_REQUIRE(d->H > 2 * r && d->W > 2 * r, "image smaller than the SSIM window");
-  return SQLX_OK;
-}
-
-extern "C" size_t sqlx_photo_workspace_bytes(const sqlx_photo_desc* d) {
-  if (!d) return 0;
-  const size_t ctas = (size_t)ceil_div(d->W, kTW) * ceil_div(d->H, kTH) * d->B;
-  // forward: per-CTA partial sums; backward: dP accumulators [B,S,12] (+ scratch)
-  return sizeof(float) * (ctas + (size_t)d->B * SQLX_MAX_SOURCES * 16 + 64);
-}
-
-extern "C" int sqlx_photo_fwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
-                              const float* const* sources, const float* K, const float* inv_K, const float* T,
-                              const float* identity, const float* noise, float* loss_sum, uint8_t* argmin,
-                              float* ssim_coef, void* workspace, size_t workspace_bytes, void* stream) {
-  if (int e = check_desc(desc)) return e;
-  SQLX_REQUIRE(depth_lr && target && sources && K && inv_K && T && loss_sum && argmin, "NULL pointer argument");
-  SQLX_REQUIRE(workspace && workspace_bytes >= sqlx_photo_workspace_bytes(desc), "workspace too small");
-  const bool automask = desc->flags & SQLX_AUTOMASK;
-  SQLX_REQUIRE(!automask || (identity && noise), "automask needs identity and noise");
-  PhotoFwdParams p;
-  p.d = *desc;
-  p.depth_lr = depth_lr; p.target = target;
-  for (int s = 0; s < SQLX_MAX_SOURCES; ++s) p.src[s] = s < desc->S ? sources[s] : nullptr;
-  for (int s = 0; s < desc->S; ++s) SQLX_REQUIRE(p.src[s], "source %d is NULL", s);
-  p.K = K; p.invK = inv_K; p.T = T; p.identity = identity; p.noise = noise;
-  p.partial = reinterpret_cast<float*>(workspace);
-  p.argmin = argmin;
-  p.coef = (desc->flags & SQLX_NO_SSIM) ? nullptr : ssim_coef;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int r = (desc->flags & SQLX_NO_SSIM) ? 0 : desc->ssim_radius;
-  int e = r == 3 ? launch_photo_fwd<3>(p, st) : (r == 1 ? launch_photo_fwd<1>(p, st) : launch_photo_fwd<0>(p, st));
-  if (e) return e;
-  const int ctas = ceil_div(desc->W, kTW) * ceil_div(desc->H, kTH) * desc->B;
-  finalize_sum_kernel<<<1, 256, 0, st>>>(p.partial, ctas, loss_sum);
-  return check_launch("finalize_sum_kernel");
-}
 
 extern "C" int sqlx_reprojection_loss_fwd(const float* pred, const float* target, int B, int H, int W,
                                           int ssim_radius, float w_ssim, float w_l1, int no_ssim, float* out,

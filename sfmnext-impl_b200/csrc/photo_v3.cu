@@ -1,0 +1,921 @@
+// Fused photometric kernels (forward and saved-coefficient backward), third generation.
+//
+//   photo_fwd3_kernel   upsample -> backproject -> project -> border-clamped bilinear warp of S sources ->
+//                       7x7 SSIM + L1 vs target -> running min with the identity (+noise) losses -> partial sums,
+//                       arg-min and the SSIM derivative coefficients of every (source, channel)
+//   photo_bwd3_kernel   arg-min masked adjoint box filter of the saved coefficients -> bilinear-sample adjoint ->
+//                       projection / back-projection adjoint -> bilinear-upsample adjoint (d depth_lr) and d P
+//   pack_rgba_kernel    [B,3,H,W] planar frame -> [B,H,W,4] pixel-interleaved frame: one 16-byte load per bilinear
+//                       tap instead of three 4-byte loads from three planes
+//
+// Reference lines: layers.py:31-46 (SSIM), 210-215 (backproject), 247-258 (project); trainer.py:395-396 (upsample),
+// 431-435 (grid_sample border / align_corners), 444-451 (0.85 SSIM + 0.15 L1), 516-532 (noise, min, mean).
+//
+// Instruction-count driven design (the previous generation issued 2430 thread instructions per pixel and launch and
+// was issue-bound at 7 % of the HBM roofline):
+//   * 32-wide tiles with the R halo staged once; region loops carry (row, col) incrementally (no div/mod) and
+//     take the reflect path only on tiles that touch the frame border
+//   * projection with one reciprocal (MUFU.RCP) instead of six IEEE divisions; the normalise / un-normalise round
+//     trip of Project3D + grid_sample is the identity and is skipped (the module-level Project3D drop-in and
+//     sqlx_warp_fwd keep the literal arithmetic)
+//   * bilinear taps clamped to (W-2, H-2) so the four taps always sit at offsets {0, 1, W, W+1}: identical values
+//     (the weight of the clamped-away tap is exactly 0 in ATen), 4 x LDG.128 per warped pixel
+//   * separable box sums: register-blocked horizontal pass (4 outputs / item), PPT vertically adjacent outputs per
+//     thread in the vertical pass, ping-pong horizontal buffers -> 4 block barriers per source
+//   * one reciprocal per SSIM value, shared with the derivative coefficients
+#include "photo_tile.cuh"
+
+#include <stdlib.h>
+
+namespace sqlx {
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_rgba_kernel(const float* __restrict__ img, int B, int plane, float4* __restrict__ out) {
+  const size_t total = (size_t)B * plane;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / plane, o = i - b * plane;
+    const float* p = img + b * 3 * plane + o;
+    out[i] = make_float4(__ldg(p), __ldg(p + plane), __ldg(p + 2 * (size_t)plane), 0.f);
+  }
+}
+
+// region loop: f(lr, lc) for every element of an RH x RW region, thread-strided, (lr, lc) carried incrementally
+template <int RH, int RW, int NT, class F>
+__device__ __forceinline__ void for_region(F&& f) {
+  int lr = threadIdx.x / RW, lc = threadIdx.x - lr * RW;
+#pragma unroll 2
+  for (int idx = threadIdx.x; idx < RH * RW; idx += NT) {
+    f(lr, lc, idx);
+    lc += NT % RW;
+    lr += NT / RW;
+    if (lc >= RW) { lc -= RW; ++lr; }
+  }
+}
+
+// advance (lr, lc) by NT flattened positions of an RW-wide region
+template <int RW, int NT>
+__device__ __forceinline__ void region_advance(int& lr, int& lc) {
+  lc += NT % RW;
+  lr += NT / RW;
+  if (lc >= RW) { lc -= RW; ++lr; }
+}
+
+// Two region elements per trip so that the global loads of both are in flight together:
+//   pre(j, lr, lc, live) issues the loads of element j into caller-owned registers, post(j, lr, lc) consumes them.
+template <int RH, int RW, int NT, class Pre, class Post>
+__device__ __forceinline__ void for_region2(Pre&& pre, Post&& post) {
+  int lr0 = threadIdx.x / RW, lc0 = threadIdx.x - lr0 * RW;
+  for (int idx = threadIdx.x; idx < RH * RW; idx += 2 * NT) {
+    int lr1 = lr0, lc1 = lc0;
+    region_advance<RW, NT>(lr1, lc1);
+    const bool has1 = idx + NT < RH * RW;
+    pre(0, lr0, lc0, true);
+    pre(1, has1 ? lr1 : lr0, has1 ? lc1 : lc0, has1);
+    post(0, lr0, lc0);
+    if (has1) post(1, lr1, lc1);
+    lr0 = lr1; lc0 = lc1;
+    region_advance<RW, NT>(lr0, lc0);
+  }
+}
+
+// Per-CTA tables of the region's rows / columns: reflected frame coordinate and the bilinear-upsample taps of the
+// low-resolution depth map (align_corners=False).  x = first tap offset, y = second tap offset, z = bits of the
+// second tap's weight, w = frame coordinate.
+template <int N>
+__device__ __forceinline__ void fill_axis_table(int4* tab, int first, int size, int lr_size, float scale, int lr_stride,
+                                                int tid0) {
+  const int i = (int)threadIdx.x - tid0;
+  if (i >= 0 && i < N) {
+    const int c = clamp_reflect(first + i, size);
+    const UpTap t = up_tap(c, scale, lr_size);
+    tab[i] = make_int4(t.i0 * lr_stride, t.i1 * lr_stride, __float_as_int(t.l1), c);
+  }
+}
+
+struct Proj {
+  float pu, pv;      // projected pixel coordinates (= the un-normalised grid_sample coordinates)
+  float rz;          // 1 / (z + eps)
+  float X0, X1, X2;  // camera point
+};
+__device__ __forceinline__ Proj project_fast(const Camera& cam, float u, float v, float d, float eps) {
+  Proj s;
+  const float r0 = fmaf(cam.iK[0], u, fmaf(cam.iK[1], v, cam.iK[2]));
+  const float r1 = fmaf(cam.iK[3], u, fmaf(cam.iK[4], v, cam.iK[5]));
+  const float r2 = fmaf(cam.iK[6], u, fmaf(cam.iK[7], v, cam.iK[8]));
+  s.X0 = d * r0; s.X1 = d * r1; s.X2 = d * r2;
+  const float c0 = fmaf(cam.P[0], s.X0, fmaf(cam.P[1], s.X1, fmaf(cam.P[2], s.X2, cam.P[3])));
+  const float c1 = fmaf(cam.P[4], s.X0, fmaf(cam.P[5], s.X1, fmaf(cam.P[6], s.X2, cam.P[7])));
+  const float c2 = fmaf(cam.P[8], s.X0, fmaf(cam.P[9], s.X1, fmaf(cam.P[10], s.X2, cam.P[11])));
+  s.rz = __fdividef(1.f, c2 + eps);
+  s.pu = c0 * s.rz;
+  s.pv = c1 * s.rz;
+  return s;
+}
+
+struct Taps4 {
+  int o;         // y0 * W + x0 with x0 <= W-2, y0 <= H-2
+  float fx, fy;  // may equal 1 on the last column / row
+};
+__device__ __forceinline__ Taps4 make_taps4(float pu, float pv, int H, int W) {
+  const float ix = fminf((float)(W - 1), fmaxf(pu, 0.f));   // padding_mode="border" (NaN -> 0 as fmaxf does)
+  const float iy = fminf((float)(H - 1), fmaxf(pv, 0.f));
+  const int x0 = min((int)ix, W - 2), y0 = min((int)iy, H - 2);
+  Taps4 t;
+  t.fx = ix - (float)x0;
+  t.fy = iy - (float)y0;
+  t.o = y0 * W + x0;
+  return t;
+}
+
+// Horizontal (2R+1)-tap sums of ONE plane, 4 outputs per item (adjoint pass of the backward kernel).
+template <int R, int ROWS, int OUTW, int LD, int OLD>
+__device__ __forceinline__ void hsum_blocked(const float* __restrict__ X, float* __restrict__ out) {
+  static_assert(OUTW % 4 == 0 && LD % 2 == 0 && OLD % 4 == 0, "blocked horizontal pass alignment");
+  constexpr int NIN = 4 + 2 * R;
+  constexpr int ITEMS = ROWS * (OUTW / 4);
+  for (int idx = threadIdx.x; idx < ITEMS; idx += blockDim.x) {
+    const int r = idx / (OUTW / 4), c = (idx - r * (OUTW / 4)) * 4;
+    float x[NIN];
+    const float2* xp = reinterpret_cast<const float2*>(X + r * LD + c);
+#pragma unroll
+    for (int k = 0; k < NIN / 2; ++k) { const float2 v = xp[k]; x[2 * k] = v.x; x[2 * k + 1] = v.y; }
+    float o[4];
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k <= 2 * R; ++k) a += x[k];
+    o[0] = a;
+#pragma unroll
+    for (int j = 1; j < 4; ++j) { a += x[j + 2 * R] - x[j - 1]; o[j] = a; }
+    *reinterpret_cast<float4*>(out + r * OLD + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles (instead of 5 per value): after the call
+// lanes 2i and 2i+1 both hold the warp total of v[i] in v[0].
+__device__ __forceinline__ void warp_reduce16(float (&v)[16]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int w = 16, n = 8; n >= 1; w >>= 1, n >>= 1) {
+    const bool upper = lane & w;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = upper ? v[i] : v[i + n];
+      const float keep = upper ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+struct PhotoFwdParams {
+  sqlx_photo_desc d;
+  const float* depth_lr;
+  const float* target;
+  const float4* src[SQLX_MAX_SOURCES];   // pixel-interleaved [B,H,W,4]
+  const float* K;
+  const float* invK;
+  const float* T;
+  const float* identity;
+  const float* noise;
+  float* partial;      // [gridDim.z*gridDim.y*gridDim.x]
+  uint8_t* argmin;
+  float* coef;         // optional [B][S][3 ch][3][H][W]: d SSIM / d(mean_x, E[x^2], E[xy])
+};
+
+template <int R, int TH, int TW, int NT>
+struct Fwd3Cfg {
+  static constexpr int PH = TH + 2 * R, PW = TW + 2 * R;
+  static constexpr int LD = ((PW + 3) & ~3) + 2;   // even, = 10 mod 32 for a 32-wide tile: conflict-free 8-byte rows
+  static constexpr int PLANE = PH * LD;
+  static constexpr int HB = PH * TW;
+  static constexpr int PPT = (TH * TW) / NT;
+  static constexpr size_t smem_bytes = sizeof(float) * (7 * PLANE + 6 * HB + 32) + sizeof(Camera) * SQLX_MAX_SOURCES +
+                                       sizeof(int4) * (PH + PW);
+  static_assert((TH * TW) % NT == 0 && NT % TW == 0 && NT >= PH + PW, "tile / block shape");
+};
+
+template <int R, int TH, int TW, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdParams p) {
+  using C = Fwd3Cfg<R, TH, TW, NT>;
+  constexpr int PPT = C::PPT;
+  constexpr int RR = R > 0 ? R : 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* dpl = reinterpret_cast<float*>(smem_raw);
+  float* tg = dpl + C::PLANE;           // 3 planes
+  float* wp = tg + 3 * C::PLANE;        // 3 planes
+  float* hbA = wp + 3 * C::PLANE;       // 3 planes of HB
+  float* hbB = hbA + 3 * C::HB;         // 3 planes of HB
+  float* red = hbB + 3 * C::HB;
+  int4* rowt = reinterpret_cast<int4*>(red + 32);     // [PH]
+  int4* colt = rowt + C::PH;                           // [PW]
+  Camera* cams = reinterpret_cast<Camera*>(colt + C::PW);
+
+  const int H = p.d.H, W = p.d.W, S = p.d.S;
+  const int b = blockIdx.z;
+  const int v0 = blockIdx.y * TH, u0 = blockIdx.x * TW;
+  const size_t plane = (size_t)H * W;
+  const bool automask = p.d.flags & SQLX_AUTOMASK;
+  const bool avg = p.d.flags & SQLX_AVG_REPROJ;
+  constexpr float ia = 1.f / (float)((2 * R + 1) * (2 * R + 1));
+
+  if (threadIdx.x < S)
+    load_camera(p.K + b * 16, p.invK + b * 16, p.T + ((size_t)b * S + threadIdx.x) * 16, cams[threadIdx.x]);
+
+  fill_axis_table<C::PH>(rowt, v0 - R, H, p.d.h, (float)p.d.h / (float)H, p.d.w, 0);
+  fill_axis_table<C::PW>(colt, u0 - R, W, p.d.w, (float)p.d.w / (float)W, 1, C::PH);
+  __syncthreads();
+
+  {   // upsampled depth and the three target planes on the R halo, two elements per trip
+    const float* lr_map = p.depth_lr + (size_t)b * p.d.h * p.d.w;
+    const float* tgb = p.target + (size_t)b * 3 * plane;
+    float dv[2][4], tv[2][3], wy[2], wx[2];
+    for_region2<C::PH, C::PW, NT>(
+        [&](int j, int lr, int lc, bool live) {
+          const int4 rt = rowt[lr], ct = colt[lc];
+          wy[j] = __int_as_float(rt.z); wx[j] = __int_as_float(ct.z);
+          if (live) {
+            const float* r0 = lr_map + rt.x;
+            const float* r1 = lr_map + rt.y;
+            dv[j][0] = __ldg(r0 + ct.x); dv[j][1] = __ldg(r0 + ct.y);
+            dv[j][2] = __ldg(r1 + ct.x); dv[j][3] = __ldg(r1 + ct.y);
+            const float* tp = tgb + (size_t)(rt.w * W + ct.w);
+            tv[j][0] = __ldg(tp); tv[j][1] = __ldg(tp + plane); tv[j][2] = __ldg(tp + 2 * plane);
+          }
+        },
+        [&](int j, int lr, int lc) {
+          const int o = lr * C::LD + lc;
+          // same expression as upsample_at (common.cuh): bit-identical depth in every kernel
+          dpl[o] = (1.f - wy[j]) * ((1.f - wx[j]) * dv[j][0] + wx[j] * dv[j][1]) +
+                   wy[j] * ((1.f - wx[j]) * dv[j][2] + wx[j] * dv[j][3]);
+          tg[o] = tv[j][0]; tg[C::PLANE + o] = tv[j][1]; tg[2 * C::PLANE + o] = tv[j][2];
+        });
+  }
+
+  // owned pixels: PPT vertically adjacent rows of one column
+  const int pcol = threadIdx.x % TW;
+  const int prow0 = (threadIdx.x / TW) * PPT;
+  const bool col_in = u0 + pcol < W;
+  const size_t pix0 = (size_t)(v0 + prow0) * W + (u0 + pcol);   // offset of the first owned pixel in a plane
+
+  // identity (+noise) candidates: independent global loads issued before the staging barrier, consumed after it
+  float best[PPT];
+  int arg[PPT];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) { best[k] = INFINITY; arg[k] = 0; }
+  const int n_ident = automask ? (avg ? 1 : S) : 0;
+  float idv[SQLX_MAX_SOURCES][PPT], nzv[SQLX_MAX_SOURCES][PPT];
+  if (automask) {
+    const float* idp = p.identity + (size_t)b * S * plane + pix0;
+    const float* nzp = p.noise + (size_t)b * (avg ? 1 : S) * plane + pix0;
+#pragma unroll
+    for (int s = 0; s < SQLX_MAX_SOURCES; ++s) {
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const bool live = s < S && col_in && (v0 + prow0 + k < H);
+        idv[s][k] = live ? __ldg(idp + (size_t)s * plane + k * W) : 0.f;
+        nzv[s][k] = (live && (!avg || s == 0)) ? __ldg(nzp + (size_t)s * plane + k * W) : 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  if (automask) {
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      if (avg) {
+        float m = 0.f;
+#pragma unroll
+        for (int s = 0; s < SQLX_MAX_SOURCES; ++s) m += idv[s][k];
+        best[k] = m / (float)S + nzv[0][k] * p.d.noise_scale;
+      } else {
+#pragma unroll
+        for (int s = 0; s < SQLX_MAX_SOURCES; ++s) {
+          const float v = idv[s][k] + nzv[s][k] * p.d.noise_scale;
+          if (s < S && v < best[k]) { best[k] = v; arg[k] = s; }
+        }
+      }
+    }
+  }
+
+  // target statistics per channel, kept in registers: mean and variance + C2
+  float my[3][PPT], syy2[3][PPT];
+  if (R > 0) {
+    hpass_blocked<RR, C::PH, TW, C::LD, TW, false>(nullptr, tg, hbA, hbA + C::HB, nullptr);
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float* cur = (c & 1) ? hbB : hbA;
+      float* nxt = (c & 1) ? hbA : hbB;
+      if (c < 2) hpass_blocked<RR, C::PH, TW, C::LD, TW, false>(nullptr, tg + (c + 1) * C::PLANE, nxt, nxt + C::HB, nullptr);
+      float Sy[PPT], Syy[PPT];
+      vsum_multi<R, TW, PPT>(cur, prow0, pcol, Sy);
+      vsum_multi<R, TW, PPT>(cur + C::HB, prow0, pcol, Syy);
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        my[c][k] = Sy[k] * ia;
+        syy2[c][k] = fmaf(-my[c][k], my[c][k], Syy[k] * ia) + kC2;
+      }
+      if (c < 2) __syncthreads();
+    }
+  }
+
+  float avg_acc[PPT];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) avg_acc[k] = 0.f;
+
+  for (int s = 0; s < S; ++s) {
+    {   // warp source s into the three shared planes (R halo included), two elements per trip
+      const float4* src = p.src[s] + (size_t)b * plane;
+      const Camera cam = cams[s];
+      const float eps = p.d.eps;
+      float4 ta[2], tb[2], tc[2], td[2];
+      float fx[2], fy[2];
+      for_region2<C::PH, C::PW, NT>(
+          [&](int j, int lr, int lc, bool live) {
+            const Proj pr = project_fast(cam, (float)colt[lc].w, (float)rowt[lr].w, dpl[lr * C::LD + lc], eps);
+            const Taps4 t = make_taps4(pr.pu, pr.pv, H, W);
+            fx[j] = t.fx; fy[j] = t.fy;
+            if (live) {
+              const float4* q = src + t.o;
+              ta[j] = __ldg(q); tb[j] = __ldg(q + 1); tc[j] = __ldg(q + W); td[j] = __ldg(q + W + 1);
+            }
+          },
+          [&](int j, int lr, int lc) {
+            const int o = lr * C::LD + lc;
+            const float w00 = (1.f - fx[j]) * (1.f - fy[j]), w01 = fx[j] * (1.f - fy[j]);
+            const float w10 = (1.f - fx[j]) * fy[j], w11 = fx[j] * fy[j];
+            wp[o] = ta[j].x * w00 + tb[j].x * w01 + tc[j].x * w10 + td[j].x * w11;
+            wp[C::PLANE + o] = ta[j].y * w00 + tb[j].y * w01 + tc[j].y * w10 + td[j].y * w11;
+            wp[2 * C::PLANE + o] = ta[j].z * w00 + tb[j].z * w01 + tc[j].z * w10 + td[j].z * w11;
+          });
+    }
+    __syncthreads();
+
+    float ssim_acc[PPT], l1_acc[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const int o = (prow0 + k + R) * C::LD + pcol + R;
+      l1_acc[k] = fabsf(tg[o] - wp[o]) + fabsf(tg[C::PLANE + o] - wp[C::PLANE + o]) +
+                  fabsf(tg[2 * C::PLANE + o] - wp[2 * C::PLANE + o]);
+      ssim_acc[k] = 0.f;
+    }
+    if (R > 0) {
+      hpass_blocked<RR, C::PH, TW, C::LD, TW, true>(wp, tg, hbA, hbA + C::HB, hbA + 2 * C::HB);
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float* cur = (c & 1) ? hbB : hbA;
+        float* nxt = (c & 1) ? hbA : hbB;
+        if (c < 2)
+          hpass_blocked<RR, C::PH, TW, C::LD, TW, true>(wp + (c + 1) * C::PLANE, tg + (c + 1) * C::PLANE, nxt,
+                                                        nxt + C::HB, nxt + 2 * C::HB);
+        float Sx[PPT], Sxx[PPT], Sxy[PPT];
+        vsum_multi<R, TW, PPT>(cur, prow0, pcol, Sx);
+        vsum_multi<R, TW, PPT>(cur + C::HB, prow0, pcol, Sxx);
+        vsum_multi<R, TW, PPT>(cur + 2 * C::HB, prow0, pcol, Sxy);
+        float* cbase = p.coef ? p.coef + ((((size_t)b * S + s) * 3 + c) * 3) * plane + pix0 : nullptr;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          // layers.py:37-46 with one reciprocal, shared by the value and its derivative coefficients
+          const float mx = Sx[k] * ia, myk = my[c][k];
+          const float sxx = fmaf(-mx, mx, Sxx[k] * ia);
+          const float sxy = fmaf(-mx, myk, Sxy[k] * ia);
+          const float n1 = fmaf(2.f * mx, myk, kC1), n2 = fmaf(2.f, sxy, kC2);
+          const float d1 = fmaf(mx, mx, fmaf(myk, myk, kC1)), d2 = sxx + syy2[c][k];
+          const float inv_d = __fdividef(1.f, d1 * d2);
+          const float q = n1 * n2 * inv_d;
+          const float val = 0.5f - 0.5f * q;
+          ssim_acc[k] += fminf(fmaxf(val, 0.f), 1.f);
+          if (cbase && col_in && v0 + prow0 + k < H) {
+            float gmx = 0.f, gxx = 0.f, gxy = 0.f;
+            if (val >= 0.f && val <= 1.f) {   // torch.clamp backward; NaN -> 0
+              const float dS_dn = -0.5f * inv_d, dS_dd = 0.5f * q * inv_d;
+              gmx = dS_dn * (2.f * myk * (n2 - n1)) + dS_dd * (2.f * mx * (d2 - d1));
+              gxx = dS_dd * d1;
+              gxy = dS_dn * 2.f * n1;
+            }
+            float* cp = cbase + (size_t)k * W;
+            __stcs(cp, gmx); __stcs(cp + plane, gxx); __stcs(cp + 2 * plane, gxy);
+          }
+        }
+        if (c < 2) __syncthreads();
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      float rho;
+      if (R > 0) rho = p.d.w_ssim * (ssim_acc[k] * (1.f / 3.f)) + p.d.w_l1 * (l1_acc[k] * (1.f / 3.f));
+      else rho = l1_acc[k] * (1.f / 3.f);
+      if (avg) {
+        avg_acc[k] += rho;
+      } else if (rho < best[k]) {
+        best[k] = rho; arg[k] = n_ident + s;
+      }
+    }
+    // the next source's warp may overwrite wp now: every read of wp happened before the last barrier above
+    // (R > 0) or happens before the barrier below (R == 0)
+    if (R == 0) __syncthreads();
+  }
+  if (avg) {
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const float rho = avg_acc[k] / (float)S;
+      if (rho < best[k]) { best[k] = rho; arg[k] = n_ident; }
+    }
+  }
+
+  float local = 0.f;
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    if (col_in && v0 + prow0 + k < H) {
+      local += best[k];
+      p.argmin[(size_t)b * plane + pix0 + (size_t)k * W] = (uint8_t)arg[k];
+    }
+  }
+  const float tot = block_sum(local, red);
+  if (threadIdx.x == 0) p.partial[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+}
+
+// Deterministic final reduction of per-CTA partial sums (one block; double accumulation).
+__global__ void finalize_sum3_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)partial[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)sh[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward from the saved SSIM coefficients
+// ------------------------------------------------------------------------------------------------
+struct PhotoBwdParams {
+  sqlx_photo_desc d;
+  const float* depth_lr;
+  const float* target;
+  const float4* src[SQLX_MAX_SOURCES];
+  const float* K;
+  const float* invK;
+  const float* T;
+  const uint8_t* argmin;
+  const float* coef;
+  const float* g_loss;
+  float scale;
+  float* d_depth_lr;
+  float* dP;  // [B,S,12] accumulators (zeroed by the host wrapper)
+};
+
+// multiplicity with which the window of output q (coordinate qi) covers pixel i under reflection padding
+template <int R>
+__device__ __forceinline__ float reflect_mult3(int i, int qi, int n) {
+  float m = 1.f;  // |qi - i| <= R is guaranteed by the caller's loop bounds
+  if (i >= 1 && i <= R && qi + i <= R) m += 1.f;
+  if (i <= n - 2 && i >= n - 1 - R && 2 * (n - 1) - i - qi <= R) m += 1.f;
+  return m;
+}
+
+template <int R, int TH, int TW, int NT>
+struct Bwd3Cfg {
+  static constexpr int PH1 = TH + 2 * R, PW1 = TW + 2 * R;
+  static constexpr int LD = ((PW1 + 3) & ~3) + 2;
+  static constexpr int CF = PH1 * LD;             // one coefficient plane on the R halo
+  static constexpr int H2 = PH1 * TW;             // one horizontally filtered plane
+  static constexpr int PPT = (TH * TW) / NT;
+  static constexpr int LRH = TH + 2, LRW = TW + 2;
+  static constexpr int SCR = (3 * H2 > LRH * LRW) ? 3 * H2 : LRH * LRW;
+  static constexpr size_t smem_bytes = sizeof(float) * (3 * CF + SCR + 32 + 16 * SQLX_MAX_SOURCES) +
+                                       sizeof(Camera) * SQLX_MAX_SOURCES + PH1 * PW1 + 16;
+  static_assert((TH * TW) % NT == 0 && NT % TW == 0, "tile / block shape");
+};
+
+template <int R, int TH, int TW, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdParams p) {
+  using C = Bwd3Cfg<R, TH, TW, NT>;
+  constexpr int PPT = C::PPT;
+  constexpr int RR = R > 0 ? R : 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* cf = reinterpret_cast<float*>(smem_raw);   // 3 planes on the R halo
+  float* h2 = cf + 3 * C::CF;                        // 3 planes PH1 x TW ; later the low-res accumulation scratch
+  float* red = h2 + C::SCR;
+  float* dPs = red + 32;                             // [S][16]
+  Camera* cams = reinterpret_cast<Camera*>(dPs + 16 * SQLX_MAX_SOURCES);
+  uint8_t* amin = reinterpret_cast<uint8_t*>(cams + SQLX_MAX_SOURCES);
+
+  const int H = p.d.H, W = p.d.W, S = p.d.S;
+  const int b = blockIdx.z;
+  const int v0 = blockIdx.y * TH, u0 = blockIdx.x * TW;
+  const size_t plane = (size_t)H * W;
+  const bool automask = p.d.flags & SQLX_AUTOMASK;
+  const bool avg = p.d.flags & SQLX_AVG_REPROJ;
+  const int n_ident = automask ? (avg ? 1 : S) : 0;
+  const float gscale = __ldg(p.g_loss) * p.scale;
+  constexpr float ia = 1.f / (float)((2 * R + 1) * (2 * R + 1));
+  const int h = p.d.h, w = p.d.w;
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  // every own pixel lies more than R from the frame border: all reflect-pad multiplicities are 1
+  const bool interior = (v0 > R) && (u0 > R) && (v0 + TH + R < H) && (u0 + TW + R < W);
+
+  if (threadIdx.x < S)
+    load_camera(p.K + b * 16, p.invK + b * 16, p.T + ((size_t)b * S + threadIdx.x) * 16, cams[threadIdx.x]);
+  if (threadIdx.x < 16 * SQLX_MAX_SOURCES) dPs[threadIdx.x] = 0.f;
+  for_region<C::PH1, C::PW1, NT>([&](int lr, int lc, int idx) {
+    const int v = v0 - R + lr, u = u0 - R + lc;
+    amin[idx] = (v >= 0 && v < H && u >= 0 && u < W) ? p.argmin[(size_t)b * plane + (size_t)v * W + u] : (uint8_t)255;
+  });
+
+  const int pcol = threadIdx.x % TW;
+  const int prow0 = (threadIdx.x / TW) * PPT;
+  const bool col_in = u0 + pcol < W;
+  const size_t pix0 = (size_t)(v0 + prow0) * W + (u0 + pcol);
+  bool pin[PPT];
+  float gd[PPT], dep[PPT], Yv[3][PPT];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    pin[k] = col_in && (v0 + prow0 + k < H);
+    gd[k] = 0.f;
+    dep[k] = 1.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Yv[c][k] = 0.f;
+    if (pin[k]) {
+      dep[k] = upsample_at(p.depth_lr + (size_t)b * h * w, h, w, v0 + prow0 + k, u0 + pcol, sy, sx);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Yv[c][k] = __ldg(p.target + ((size_t)b * 3 + c) * plane + pix0 + (size_t)k * W);
+    }
+  }
+  __syncthreads();
+
+  for (int s = 0; s < S; ++s) {
+    const float sel_w = avg ? 1.f / (float)S : 1.f;
+    const int sel_idx = avg ? n_ident : n_ident + s;
+    {   // nothing on this tile's halo selects source s (auto-masked or won by another source): no gradient at all
+      int any = 0;
+      for (int idx = threadIdx.x; idx < C::PH1 * C::PW1; idx += NT) any |= (amin[idx] == sel_idx);
+      if (!__syncthreads_or(any)) continue;
+    }
+    const Camera cam = cams[s];
+    const float4* srcb = p.src[s] + (size_t)b * plane;
+    // own pixels: warped value and its spatial derivatives per channel
+    float Xv[3][PPT], dXx[3][PPT], dXy[3][PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const Proj pr = project_fast(cam, (float)(u0 + pcol), (float)(v0 + prow0 + k), dep[k], p.d.eps);
+      const Taps4 t = make_taps4(pr.pu, pr.pv, H, W);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bq = a, cq = a, dq = a;
+      if (pin[k]) {
+        const float4* q = srcb + t.o;
+        a = __ldg(q); bq = __ldg(q + 1); cq = __ldg(q + W); dq = __ldg(q + W + 1);
+      }
+      const float w00 = (1.f - t.fx) * (1.f - t.fy), w01 = t.fx * (1.f - t.fy);
+      const float w10 = (1.f - t.fx) * t.fy, w11 = t.fx * t.fy;
+      Xv[0][k] = a.x * w00 + bq.x * w01 + cq.x * w10 + dq.x * w11;
+      Xv[1][k] = a.y * w00 + bq.y * w01 + cq.y * w10 + dq.y * w11;
+      Xv[2][k] = a.z * w00 + bq.z * w01 + cq.z * w10 + dq.z * w11;
+      dXx[0][k] = (bq.x - a.x) * (1.f - t.fy) + (dq.x - cq.x) * t.fy;
+      dXx[1][k] = (bq.y - a.y) * (1.f - t.fy) + (dq.y - cq.y) * t.fy;
+      dXx[2][k] = (bq.z - a.z) * (1.f - t.fy) + (dq.z - cq.z) * t.fy;
+      dXy[0][k] = (cq.x - a.x) * (1.f - t.fx) + (dq.x - bq.x) * t.fx;
+      dXy[1][k] = (cq.y - a.y) * (1.f - t.fx) + (dq.y - bq.y) * t.fx;
+      dXy[2][k] = (cq.z - a.z) * (1.f - t.fx) + (dq.z - bq.z) * t.fx;
+    }
+    float gix[PPT], giy[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) { gix[k] = 0.f; giy[k] = 0.f; }
+    const float alpha = (p.d.w_ssim / 3.f) * sel_w * gscale;
+    const float wl1 = ((R > 0) ? p.d.w_l1 : 1.f) / 3.f * sel_w * gscale;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float gx[PPT];
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const float diff = Yv[c][k] - Xv[c][k];
+        const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+        const bool sel = amin[(prow0 + k + R) * C::PW1 + pcol + R] == sel_idx;
+        gx[k] = sel ? -wl1 * sgn : 0.f;
+      }
+      if (R > 0) {
+        const float* cbase = p.coef + ((((size_t)b * S + s) * 3 + c) * 3) * plane;
+        for_region<C::PH1, C::PW1, NT>([&](int lr, int lc, int idx) {
+          float a = 0.f, bb = 0.f, cc = 0.f;
+          if (amin[idx] == sel_idx) {
+            const float* q = cbase + (size_t)(v0 - R + lr) * W + (u0 - R + lc);
+            a = __ldg(q); bb = __ldg(q + plane); cc = __ldg(q + 2 * plane);
+          }
+          const int o = lr * C::LD + lc;
+          cf[o] = a; cf[C::CF + o] = bb; cf[2 * C::CF + o] = cc;
+        });
+        __syncthreads();
+        float sa[PPT], sb[PPT], sc[PPT];
+        if (interior) {
+          hsum_blocked<RR, C::PH1, TW, C::LD, TW>(cf, h2);
+          hsum_blocked<RR, C::PH1, TW, C::LD, TW>(cf + C::CF, h2 + C::H2);
+          hsum_blocked<RR, C::PH1, TW, C::LD, TW>(cf + 2 * C::CF, h2 + 2 * C::H2);
+          __syncthreads();
+          vsum_multi<R, TW, PPT>(h2, prow0, pcol, sa);
+          vsum_multi<R, TW, PPT>(h2 + C::H2, prow0, pcol, sb);
+          vsum_multi<R, TW, PPT>(h2 + 2 * C::H2, prow0, pcol, sc);
+        } else {
+          // frame-border tiles: adjoint of the reflection padding = per-tap multiplicities
+          for (int idx = threadIdx.x; idx < C::PH1 * TW; idx += NT) {
+            const int lr = idx / TW, pc = idx - lr * TW;
+            const int u = u0 + pc;
+            const float* ca = cf + lr * C::LD + pc;
+            float ta = 0.f, tb = 0.f, tc = 0.f;
+            if (u < W) {
+#pragma unroll
+              for (int k = 0; k <= 2 * R; ++k) {
+                const int qu = u - R + k;
+                if (qu < 0 || qu >= W) continue;
+                const float m = reflect_mult3<R>(u, qu, W);
+                ta += m * ca[k]; tb += m * ca[C::CF + k]; tc += m * ca[2 * C::CF + k];
+              }
+            }
+            h2[idx] = ta; h2[C::H2 + idx] = tb; h2[2 * C::H2 + idx] = tc;
+          }
+          __syncthreads();
+#pragma unroll
+          for (int k = 0; k < PPT; ++k) {
+            const int v = v0 + prow0 + k;
+            const float* ha = h2 + (prow0 + k) * TW + pcol;
+            float ta = 0.f, tb = 0.f, tc = 0.f;
+            if (v < H) {
+#pragma unroll
+              for (int j = 0; j <= 2 * R; ++j) {
+                const int qv = v - R + j;
+                if (qv < 0 || qv >= H) continue;
+                const float m = reflect_mult3<R>(v, qv, H);
+                ta += m * ha[j * TW]; tb += m * ha[C::H2 + j * TW]; tc += m * ha[2 * C::H2 + j * TW];
+              }
+            }
+            sa[k] = ta; sb[k] = tb; sc[k] = tc;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < PPT; ++k)
+          gx[k] += alpha * ia * (sa[k] + 2.f * Xv[c][k] * sb[k] + Yv[c][k] * sc[k]);
+        // cf is rewritten by the next channel's staging: its readers finished before the barrier above; h2 is
+        // rewritten only after the next staging barrier
+      }
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        gix[k] = fmaf(gx[k], dXx[c][k], gix[k]);
+        giy[k] = fmaf(gx[k], dXy[c][k], giy[k]);
+      }
+    }
+    float dPacc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dPacc[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      if (!pin[k]) continue;
+      if (gix[k] == 0.f && giy[k] == 0.f) continue;
+      const float uf = (float)(u0 + pcol), vf = (float)(v0 + prow0 + k);
+      const Proj pr = project_fast(cam, uf, vf, dep[k], p.d.eps);
+      // grid_sample clips the coordinate: no gradient through a clipped axis (ATen clip_coordinates_set_grad)
+      const float gx_ = (pr.pu > 0.f && pr.pu < (float)(W - 1)) ? gix[k] : 0.f;
+      const float gy_ = (pr.pv > 0.f && pr.pv < (float)(H - 1)) ? giy[k] : 0.f;
+      const float g0 = gx_ * pr.rz, g1 = gy_ * pr.rz, g2 = -(gx_ * pr.pu + gy_ * pr.pv) * pr.rz;
+      const float r0 = fmaf(cam.iK[0], uf, fmaf(cam.iK[1], vf, cam.iK[2]));
+      const float r1 = fmaf(cam.iK[3], uf, fmaf(cam.iK[4], vf, cam.iK[5]));
+      const float r2 = fmaf(cam.iK[6], uf, fmaf(cam.iK[7], vf, cam.iK[8]));
+      gd[k] += g0 * (cam.P[0] * r0 + cam.P[1] * r1 + cam.P[2] * r2) + g1 * (cam.P[4] * r0 + cam.P[5] * r1 + cam.P[6] * r2) +
+               g2 * (cam.P[8] * r0 + cam.P[9] * r1 + cam.P[10] * r2);
+      dPacc[0] += g0 * pr.X0; dPacc[1] += g0 * pr.X1; dPacc[2] += g0 * pr.X2; dPacc[3] += g0;
+      dPacc[4] += g1 * pr.X0; dPacc[5] += g1 * pr.X1; dPacc[6] += g1 * pr.X2; dPacc[7] += g1;
+      dPacc[8] += g2 * pr.X0; dPacc[9] += g2 * pr.X1; dPacc[10] += g2 * pr.X2; dPacc[11] += g2;
+    }
+    warp_reduce16(dPacc);
+    {
+      const int lane = threadIdx.x & 31;
+      if (!(lane & 1) && (lane >> 1) < 12 && dPacc[0] != 0.f) atomicAdd(&dPs[s * 16 + (lane >> 1)], dPacc[0]);
+    }
+  }
+
+  // adjoint of the bilinear upsampling: per-tile accumulation in shared memory, one global atomic per touched cell
+  const int vend = min(v0 + TH, H) - 1, uend = min(u0 + TW, W) - 1;
+  const int i_lo = up_tap(v0, sy, h).i0, i_hi = up_tap(vend, sy, h).i1;
+  const int j_lo = up_tap(u0, sx, w).i0, j_hi = up_tap(uend, sx, w).i1;
+  const int nh = i_hi - i_lo + 1, nw = j_hi - j_lo + 1;
+  float* acc = h2;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < nh * nw; idx += NT) acc[idx] = 0.f;
+  if (threadIdx.x < 12 * S) {
+    const int s = threadIdx.x / 12, i = threadIdx.x - s * 12;
+    const float t = dPs[s * 16 + i];
+    if (t != 0.f) atomicAdd(p.dP + ((size_t)b * S + s) * 12 + i, t);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    if (!pin[k] || gd[k] == 0.f) continue;
+    const UpTap ty = up_tap(v0 + prow0 + k, sy, h), tx = up_tap(u0 + pcol, sx, w);
+    const int a0 = (ty.i0 - i_lo) * nw, a1 = (ty.i1 - i_lo) * nw, c0 = tx.i0 - j_lo, c1 = tx.i1 - j_lo;
+    atomicAdd(acc + a0 + c0, gd[k] * ty.l0 * tx.l0);
+    atomicAdd(acc + a0 + c1, gd[k] * ty.l0 * tx.l1);
+    atomicAdd(acc + a1 + c0, gd[k] * ty.l1 * tx.l0);
+    atomicAdd(acc + a1 + c1, gd[k] * ty.l1 * tx.l1);
+  }
+  __syncthreads();
+  float* out = p.d_depth_lr + (size_t)b * h * w;
+  for (int idx = threadIdx.x; idx < nh * nw; idx += NT) {
+    const float g = acc[idx];
+    if (g != 0.f) {
+      const int i = idx / nw, j = idx - i * nw;
+      atomicAdd(out + (size_t)(i_lo + i) * w + (j_lo + j), g);
+    }
+  }
+}
+
+// dT[b,s] = K[b][:3,:]^T * dP[b,s]   (P = (K T)[:3,:]  =>  dL/dT = K[:3,:]^T dL/dP)
+__global__ void dT_from_dP3_kernel(const float* __restrict__ K, const float* __restrict__ dP, int B, int S,
+                                   float* __restrict__ dT) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * S * 16) return;
+  const int e = idx & 15, bs = idx >> 4, b = bs / S;
+  const int i = e >> 2, j = e & 3;  // dT[i][j] = sum_k K[k][i] dP[k][j], k<3
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) acc += K[b * 16 + k * 4 + i] * dP[(size_t)bs * 12 + k * 4 + j];
+  dT[idx] = acc;
+}
+
+}  // namespace sqlx
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using namespace sqlx;
+
+namespace {
+// Tile configurations.  The default was picked on a B200 (tools/time_photo.py); SQLX_FWD_CFG / SQLX_BWD_CFG select
+// the others for tuning.
+//   forward : 0 = 32x32 tile, 256 threads (4 px/thread), 2 CTAs/SM     1 = 16x32, 256 (2 px/thread), 3 CTAs/SM
+//             2 = 16x32, 256, 4 CTAs/SM                                3 = 32x32, 512 (2 px/thread), 2 CTAs/SM
+//   backward: 0 = 16x32, 256, 3 CTAs/SM    1 = 16x32, 256, 4 CTAs/SM    2 = 32x32, 256 (4 px/thread), 2 CTAs/SM
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+constexpr int kMinTH = 16, kMinTW = 32;   // smallest tile of any configuration: sizes the per-CTA partial buffer
+
+template <int R, int TH, int TW, int NT, int MINB>
+int launch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
+  using C = Fwd3Cfg<R, TH, TW, NT>;
+  auto kern = photo_fwd3_kernel<R, TH, TW, NT, MINB>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
+    configured = true;
+  }
+  dim3 grid(ceil_div(p.d.W, TW), ceil_div(p.d.H, TH), p.d.B);
+  *ctas = (int)(grid.x * grid.y * grid.z);
+  ProfScope prof("photo_fwd_kernel", st);
+  kern<<<grid, NT, C::smem_bytes, st>>>(p);
+  return check_launch("photo_fwd3_kernel");
+}
+
+template <int R>
+int dispatch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
+  static const int cfg = env_int("SQLX_FWD_CFG", 0);
+  switch (cfg) {
+    case 1: return launch_photo_fwd3<R, 16, 32, 256, 3>(p, ctas, st);
+    case 2: return launch_photo_fwd3<R, 16, 32, 256, 4>(p, ctas, st);
+    case 3: return launch_photo_fwd3<R, 32, 32, 512, 2>(p, ctas, st);
+    default: return launch_photo_fwd3<R, 32, 32, 256, 2>(p, ctas, st);
+  }
+}
+
+template <int R, int TH, int TW, int NT, int MINB>
+int launch_photo_bwd3(const PhotoBwdParams& p, cudaStream_t st) {
+  using C = Bwd3Cfg<R, TH, TW, NT>;
+  auto kern = photo_bwd3_kernel<R, TH, TW, NT, MINB>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
+    configured = true;
+  }
+  dim3 grid(ceil_div(p.d.W, TW), ceil_div(p.d.H, TH), p.d.B);
+  ProfScope prof("photo_bwd_kernel", st);
+  kern<<<grid, NT, C::smem_bytes, st>>>(p);
+  return check_launch("photo_bwd3_kernel");
+}
+
+template <int R>
+int dispatch_photo_bwd3(const PhotoBwdParams& p, cudaStream_t st) {
+  static const int cfg = env_int("SQLX_BWD_CFG", 0);
+  switch (cfg) {
+    case 1: return launch_photo_bwd3<R, 16, 32, 256, 4>(p, st);
+    case 2: return launch_photo_bwd3<R, 32, 32, 256, 2>(p, st);
+    default: return launch_photo_bwd3<R, 16, 32, 256, 3>(p, st);
+  }
+}
+
+int check_desc(const sqlx_photo_desc* d) {
+  SQLX_REQUIRE(d != nullptr, "desc is NULL");
+  SQLX_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->h > 0 && d->w > 0, "non-positive shape");
+  SQLX_REQUIRE(d->S >= 1 && d->S <= SQLX_MAX_SOURCES, "S=%d outside 1..%d", d->S, SQLX_MAX_SOURCES);
+  SQLX_REQUIRE(d->h <= d->H && d->w <= d->W, "depth map larger than the image is not supported");
+  SQLX_REQUIRE((d->flags & SQLX_NO_SSIM) || d->ssim_radius == 1 || d->ssim_radius == 3,
+               "ssim_radius must be 1 or 3 (got %d)", d->ssim_radius);
+  const int r = (d->flags & SQLX_NO_SSIM) ? 0 : d->ssim_radius;
+  SQLX_REQUIRE(d->H > 2 * r && d->W > 2 * r && d->H >= 2 && d->W >= 2, "image smaller than the SSIM window");
+  SQLX_REQUIRE((long long)d->H * d->W < (1ll << 30), "frame too large for 32-bit pixel offsets");
+  return SQLX_OK;
+}
+
+size_t fwd_ctas(const sqlx_photo_desc* d) { return (size_t)ceil_div(d->W, kMinTW) * ceil_div(d->H, kMinTH) * d->B; }
+}  // namespace
+
+extern "C" int sqlx_pack_rgba(const float* image, int B, int H, int W, float* out, void* stream) {
+  SQLX_REQUIRE(image && out, "NULL pointer argument");
+  SQLX_REQUIRE(B > 0 && H > 0 && W > 0 && (long long)H * W < (1ll << 30), "bad shape");
+  SQLX_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "output must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = (long long)B * H * W;
+  const int blocks = (int)((total + 255) / 256 < 8 * kNumSMs ? (total + 255) / 256 : 8 * kNumSMs);
+  pack_rgba_kernel<<<blocks, 256, 0, st>>>(image, B, H * W, reinterpret_cast<float4*>(out));
+  return check_launch("pack_rgba_kernel");
+}
+
+extern "C" size_t sqlx_photo_workspace_bytes(const sqlx_photo_desc* d) {
+  if (!d) return 0;
+  // forward: per-CTA partial sums; backward: dP accumulators [B,S,12] (+ scratch)
+  return sizeof(float) * (fwd_ctas(d) + (size_t)d->B * SQLX_MAX_SOURCES * 16 + 64);
+}
+
+extern "C" size_t sqlx_photo_coef_bytes(const sqlx_photo_desc* d) {
+  if (!d || (d->flags & SQLX_NO_SSIM)) return 0;
+  return sizeof(float) * 9 * (size_t)d->B * d->S * d->H * d->W;
+}
+
+extern "C" int sqlx_photo_fwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
+                              const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
+                              const float* identity, const float* noise, float* loss_sum, uint8_t* argmin,
+                              float* ssim_coef, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_desc(desc)) return e;
+  SQLX_REQUIRE(depth_lr && target && sources_rgba && K && inv_K && T && loss_sum && argmin, "NULL pointer argument");
+  SQLX_REQUIRE(workspace && workspace_bytes >= sqlx_photo_workspace_bytes(desc), "workspace too small");
+  const bool automask = desc->flags & SQLX_AUTOMASK;
+  SQLX_REQUIRE(!automask || (identity && noise), "automask needs identity and noise");
+  PhotoFwdParams p;
+  p.d = *desc;
+  p.depth_lr = depth_lr; p.target = target;
+  for (int s = 0; s < SQLX_MAX_SOURCES; ++s)
+    p.src[s] = s < desc->S ? reinterpret_cast<const float4*>(sources_rgba[s]) : nullptr;
+  for (int s = 0; s < desc->S; ++s) {
+    SQLX_REQUIRE(p.src[s], "source %d is NULL", s);
+    SQLX_REQUIRE((reinterpret_cast<uintptr_t>(p.src[s]) & 15) == 0, "source %d is not 16-byte aligned", s);
+  }
+  p.K = K; p.invK = inv_K; p.T = T; p.identity = identity; p.noise = noise;
+  p.partial = reinterpret_cast<float*>(workspace);
+  p.argmin = argmin;
+  p.coef = (desc->flags & SQLX_NO_SSIM) ? nullptr : ssim_coef;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int r = (desc->flags & SQLX_NO_SSIM) ? 0 : desc->ssim_radius;
+  int ctas = 0;
+  int e = r == 3 ? dispatch_photo_fwd3<3>(p, &ctas, st)
+                 : (r == 1 ? dispatch_photo_fwd3<1>(p, &ctas, st) : dispatch_photo_fwd3<0>(p, &ctas, st));
+  if (e) return e;
+  finalize_sum3_kernel<<<1, 256, 0, st>>>(p.partial, ctas, loss_sum);
+  return check_launch("finalize_sum_kernel");
+}
+
+extern "C" int sqlx_photo_bwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
+                              const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
+                              const uint8_t* argmin, const float* ssim_coef, const float* g_loss, float scale,
+                              float* d_depth_lr, float* d_T, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_desc(desc)) return e;
+  SQLX_REQUIRE(depth_lr && target && sources_rgba && K && inv_K && T && argmin && g_loss && d_depth_lr && d_T,
+               "NULL pointer argument");
+  SQLX_REQUIRE(workspace && workspace_bytes >= sqlx_photo_workspace_bytes(desc), "workspace too small");
+  const int r = (desc->flags & SQLX_NO_SSIM) ? 0 : desc->ssim_radius;
+  SQLX_REQUIRE(r == 0 || ssim_coef, "the backward needs the SSIM coefficients exported by sqlx_photo_fwd");
+  PhotoBwdParams p;
+  p.d = *desc;
+  p.depth_lr = depth_lr; p.target = target;
+  for (int s = 0; s < SQLX_MAX_SOURCES; ++s)
+    p.src[s] = s < desc->S ? reinterpret_cast<const float4*>(sources_rgba[s]) : nullptr;
+  for (int s = 0; s < desc->S; ++s) {
+    SQLX_REQUIRE(p.src[s], "source %d is NULL", s);
+    SQLX_REQUIRE((reinterpret_cast<uintptr_t>(p.src[s]) & 15) == 0, "source %d is not 16-byte aligned", s);
+  }
+  p.K = K; p.invK = inv_K; p.T = T; p.argmin = argmin; p.coef = ssim_coef; p.g_loss = g_loss; p.scale = scale;
+  p.d_depth_lr = d_depth_lr;
+  // dP accumulators live after the forward partial sums in the workspace
+  p.dP = reinterpret_cast<float*>(workspace) + fwd_ctas(desc);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(p.dP, 0, sizeof(float) * (size_t)desc->B * desc->S * 12, st) != cudaSuccess)
+    return check_launch("cudaMemsetAsync(dP)");
+  int e = r == 3 ? dispatch_photo_bwd3<3>(p, st) : (r == 1 ? dispatch_photo_bwd3<1>(p, st) : dispatch_photo_bwd3<0>(p, st));
+  if (e) return e;
+  const int n = desc->B * desc->S * 16;
+  dT_from_dP3_kernel<<<ceil_div(n, 128), 128, 0, st>>>(K, p.dP, desc->B, desc->S, d_T);
+  return check_launch("dT_from_dP_kernel");
+}

@@ -52,6 +52,8 @@ _PROTOS = {
     "sqlx_ssim_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sqlx_ssim_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "sqlx_photo_workspace_bytes": (c_size_t, [ctypes.POINTER(PhotoDesc)]),
+    "sqlx_photo_coef_bytes": (c_size_t, [ctypes.POINTER(PhotoDesc)]),
+    "sqlx_pack_rgba": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sqlx_photo_fwd": (c_int, [ctypes.POINTER(PhotoDesc), c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sqlx_photo_bwd": (c_int, [ctypes.POINTER(PhotoDesc), c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_void_p,

@@ -31,6 +31,18 @@ def _src_array(sources):
     return arr
 
 
+def pack_rgba(image):
+    """[B,3,H,W] planar frame -> [B,H,W,4] pixel-interleaved frame (r,g,b,0): the layout the fused kernels gather
+    source frames from (one 128-bit load per bilinear tap).  Packed once per step, shared by all loss scales."""
+    require_cuda(image)
+    img = _f32c(image)
+    B, C, H, W = img.shape
+    assert C == 3
+    out = torch.empty(B, H, W, 4, device=img.device, dtype=torch.float32)
+    check(lib().sqlx_pack_rgba(ptr(img), B, H, W, ptr(out), stream_ptr()), "sqlx_pack_rgba")
+    return out
+
+
 # ----------------------------------------------------------------------------- small ops
 class _DepthStats(torch.autograd.Function):
     """[B,1,h,w] -> [B,2] = (mean, mean of reciprocal) of the map bilinearly upsampled to HxW."""
@@ -162,24 +174,25 @@ class _PhotoLoss(torch.autograd.Function):
         H, W = target.shape[-2:]
         S = len(sources)
         desc = make_desc(B, H, W, h, w, S, **cfg)
-        srcs = [_f32c(s) for s in sources]
+        srcs = [pack_rgba(s) for s in sources]
         tgt, Kc, iKc = _f32c(target), _f32c(K), _f32c(inv_K)
         ident, nz = _f32c(identity), _f32c(noise)
         nbytes = lib().sqlx_photo_workspace_bytes(ctypes.byref(desc))
         ws = torch.empty(nbytes, device=d.device, dtype=torch.uint8)
+        coef = torch.empty(max(1, lib().sqlx_photo_coef_bytes(ctypes.byref(desc))), device=d.device, dtype=torch.uint8)
         loss_sum = torch.empty(1, device=d.device, dtype=torch.float32)
         argmin = torch.empty(B, H, W, device=d.device, dtype=torch.uint8)
         check(lib().sqlx_photo_fwd(ctypes.byref(desc), ptr(d), ptr(tgt), _src_array(srcs), ptr(Kc), ptr(iKc), ptr(Tm),
-                                   ptr(ident), ptr(nz), ptr(loss_sum), ptr(argmin), None, ptr(ws), nbytes, stream_ptr()),
-              "sqlx_photo_fwd")
-        ctx.save_for_backward(d, Tm, tgt, Kc, iKc, argmin, *srcs)
+                                   ptr(ident), ptr(nz), ptr(loss_sum), ptr(argmin), ptr(coef), ptr(ws), nbytes,
+                                   stream_ptr()), "sqlx_photo_fwd")
+        ctx.save_for_backward(d, Tm, tgt, Kc, iKc, argmin, coef, *srcs)
         ctx.desc = desc
         ctx.mark_non_differentiable(argmin)
         return loss_sum, argmin
 
     @staticmethod
     def backward(ctx, g_loss, _g_argmin):
-        d, Tm, tgt, Kc, iKc, argmin, *srcs = ctx.saved_tensors
+        d, Tm, tgt, Kc, iKc, argmin, coef, *srcs = ctx.saved_tensors
         desc = ctx.desc
         nbytes = lib().sqlx_photo_workspace_bytes(ctypes.byref(desc))
         ws = torch.empty(nbytes, device=d.device, dtype=torch.uint8)
@@ -187,7 +200,7 @@ class _PhotoLoss(torch.autograd.Function):
         d_T = torch.empty_like(Tm)
         g = g_loss.contiguous().float()
         check(lib().sqlx_photo_bwd(ctypes.byref(desc), ptr(d), ptr(tgt), _src_array(srcs), ptr(Kc), ptr(iKc), ptr(Tm),
-                                   ptr(argmin), None, ptr(g), 1.0, ptr(d_depth), ptr(d_T), ptr(ws), nbytes, stream_ptr()),
+                                   ptr(argmin), ptr(coef), ptr(g), 1.0, ptr(d_depth), ptr(d_T), ptr(ws), nbytes, stream_ptr()),
               "sqlx_photo_bwd")
         return (d_depth, d_T, None, None, None, None, None, None) + (None,) * len(srcs)
 
@@ -239,7 +252,7 @@ class _ScaleLoss(torch.autograd.Function):
         ws = torch.empty(nws, device=dev, dtype=torch.uint8)
         loss = torch.empty(1, device=dev, dtype=torch.float32)
         argmin = torch.empty(B, H, W, device=dev, dtype=torch.uint8)
-        srcs = [_f32c(x) for x in sources]
+        srcs = list(sources)                       # [B,H,W,4] pixel-interleaved copies (pack_rgba)
         tgt, col, Kc, iKc, ident, nz = (_f32c(t) for t in (target, color_s, K, inv_K, identity, noise))
         check(lib().sqlx_scale_loss_fwd(ctypes.byref(desc), ptr(d), ptr(tgt), _src_array(srcs), ptr(col), ptr(Kc), ptr(iKc),
                                         ctypes.byref(pin), ptr(ident), ptr(nz), ptr(loss), ptr(argmin), ptr(saved),
@@ -326,6 +339,7 @@ def photometric_losses(disps, target_pyr, sources, K, inv_K, poses, noises, *, h
             pose_tensors += [pose["axisangle"], pose["translation"]]
     rescale = bool(rescale_translation) and any(sp[0] == "net" for sp in pose_spec)
     n_ident = 0 if not automask else (1 if avg_reprojection else S)
+    packed = [pack_rgba(src) for src in sources]    # once per step: every scale, forward and backward, gathers from these
     total = 0
     for s in scales:
         disp = disps[s]
@@ -334,7 +348,7 @@ def photometric_losses(disps, target_pyr, sources, K, inv_K, poses, noises, *, h
             noise = noises.get(s) if noises is not None else None
             if noise is None:
                 noise = torch.randn(B, 1 if avg_reprojection else S, H, W, device=target.device)
-        meta = (target, target_pyr[s], K, inv_K, identity, noise, list(sources), pose_spec, cfg,
+        meta = (target, target_pyr[s], K, inv_K, identity, noise, packed, pose_spec, cfg,
                 disparity_smoothness / (2 ** s), rescale)
         loss, argmin = _ScaleLoss.apply(disp, meta, *pose_tensors)
         out["loss/%d" % s] = loss

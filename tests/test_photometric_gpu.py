@@ -43,6 +43,20 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
 
 
+def _mask_flips(gr, ref, flips):
+    """An arg-min tie decided the other way (identity + 1e-5 * noise vs a reprojection loss equal to 1e-5: < 0.2 % of
+    the pixels, asserted separately) moves the gradient of every low-res depth cell whose upsample footprint touches
+    the flipped pixel's 7x7 SSIM window by O(max |grad|); both arg-mins are valid.  Those cells are excluded from the
+    element-wise comparison.  gr, ref: [B,1,h,w]; flips: [B,H,W] bool."""
+    if flips is None or not bool(flips.any()):
+        return gr, ref
+    import torch.nn.functional as F
+    m = F.max_pool2d(flips[:, None].float(), 9, 1, 4)                       # SSIM window + bilinear tap
+    m = F.adaptive_max_pool2d(m, ref.shape[-2:])
+    m = F.max_pool2d(m, 3, 1, 1) > 0                                        # upsample taps of neighbouring cells
+    return gr.masked_fill(m, 0.0), ref.masked_fill(m, 0.0)
+
+
 def _cos(a, b):
     a, b = a.double().flatten(), b.double().flatten()     # (F.cosine_similarity clamps tiny norms to 1e-8)
     if float(b.norm()) == 0.0:                             # e.g. a source frame the minimum never selects
@@ -57,11 +71,13 @@ def test_golden(name):
     g = _to_dev(kw)
     out = sqlx.photometric_losses(**g, materialize=True)
     assert abs(float(out["loss"]) - float(z["out_loss"])) < 1e-5
+    flips = {}
     for s in kw["scales"]:
         assert abs(float(out["loss/%d" % s]) - float(z["out_loss_s%d" % s])) < 1e-5
         if not kw["disable_automasking"]:
             sel = out["identity_selection/%d" % s].cpu().numpy().astype(np.uint8)
             assert (sel != z["out_idsel_s%d" % s]).mean() < 2e-3
+            flips[s] = torch.from_numpy(sel != z["out_idsel_s%d" % s])
         np.testing.assert_allclose(out[("depth", 0, s)].cpu().numpy(), z["out_depth_s%d" % s], rtol=1e-5, atol=1e-5)
     s0 = kw["scales"][0]
     for i, f in enumerate(fids[1:]):
@@ -76,6 +92,8 @@ def test_golden(name):
     for n, gr in zip(names, grads):
         ref = torch.from_numpy(z["grad_" + n])
         gr = torch.zeros_like(ref) if gr is None else gr.cpu()
+        if n.startswith("disp"):
+            gr, ref = _mask_flips(gr, ref, flips.get(int(n[4:])))
         assert _rel(gr, ref) < 2e-2, n
         cos = _cos(gr, ref)
         assert cos > 0.9995, n
@@ -111,16 +129,21 @@ def test_oracle_fp64(cfg):
     kd["noises"] = {s: dbl(v) for s, v in kw["noises"].items()}
     ref = O.photometric_losses(**kd)
     assert abs(float(out["loss"]) - float(ref["loss"])) < 1e-5
+    flips = []
     for s in kw["scales"]:
         a = out["identity_selection/%d" % s].cpu()
         b = ref["identity_selection/%d" % s].float()
         assert float((a != b).float().mean()) < 2e-3
+        flips.append(a != b)
     gl, rl = _grad_leaves(g), _grad_leaves(kd)
     gg = torch.autograd.grad(out["loss"], gl)
     rg = torch.autograd.grad(ref["loss"], rl)
-    for a, b in zip(gg, rg):
+    for i, (a, b) in enumerate(zip(gg, rg)):
         tol = 0.1 if cfg.get("white_noise") else 3e-2
-        assert _rel(a.cpu().double(), b) < tol
+        a, b = a.cpu().double(), b
+        if i < len(flips):                       # the first len(scales) leaves are the depth maps
+            a, b = _mask_flips(a, b, flips[i])
+        assert _rel(a, b) < tol
         cos = _cos(a.cpu(), b)
         assert cos > (0.99 if cfg.get("white_noise") else 0.999)
 
@@ -153,8 +176,8 @@ def test_full_size_properties():
 
 
 def test_backward_variants_agree():
-    """The saved-coefficient backward (photo_bwd2_kernel, used by the fused per-scale call) and the recompute
-    backward (photo_bwd_kernel, taken when no coefficient buffer is passed) give the same gradients."""
+    """The fused per-scale library call (sqlx_scale_loss_fwd/bwd) and the explicit chain of the un-fused autograd
+    functions (depth_stats -> pose_matrix -> sqlx_photo_fwd/bwd -> smoothness) give the same loss and gradients."""
     import sqlx
     from sqlx import photometric as P
     kw = synth_photo_case(seed=21, B=2, H=80, W=112, S=2)

@@ -114,6 +114,34 @@ __device__ __forceinline__ Proj project_fast(const Camera& cam, float u, float v
   return s;
 }
 
+// Forward-only form of the same projection with back-projection and projection composed:
+//   (K T)[:3,:] (d * inv_K (u,v,1), 1) = d * (M (u,v,1)) + t,  M = P[:, :3] inv_K[:3,:3],  t = P[:, 3]
+// 12 constants and 9 FMAs per pixel instead of 21 and 18 (the backward needs the camera point and keeps project_fast).
+struct CamM {
+  float M[9], t[3];
+};
+__device__ __forceinline__ CamM compose_camera(const Camera& cam) {
+  CamM c;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      c.M[i * 3 + j] = cam.P[i * 4 + 0] * cam.iK[0 * 3 + j] + cam.P[i * 4 + 1] * cam.iK[1 * 3 + j] +
+                       cam.P[i * 4 + 2] * cam.iK[2 * 3 + j];
+    c.t[i] = cam.P[i * 4 + 3];
+  }
+  return c;
+}
+__device__ __forceinline__ void project_composed(const CamM& c, float u, float v, float d, float eps, float& pu,
+                                                 float& pv) {
+  const float m0 = fmaf(c.M[0], u, fmaf(c.M[1], v, c.M[2]));
+  const float m1 = fmaf(c.M[3], u, fmaf(c.M[4], v, c.M[5]));
+  const float m2 = fmaf(c.M[6], u, fmaf(c.M[7], v, c.M[8]));
+  const float rz = __fdividef(1.f, fmaf(d, m2, c.t[2]) + eps);
+  pu = fmaf(d, m0, c.t[0]) * rz;
+  pv = fmaf(d, m1, c.t[1]) * rz;
+}
+
 struct Taps4 {
   int o;         // y0 * W + x0 with x0 <= W-2, y0 <= H-2
   float fx, fy;  // may equal 1 on the last column / row
@@ -194,8 +222,9 @@ struct Fwd3Cfg {
   static constexpr int PLANE = PH * LD;
   static constexpr int HB = PH * TW;
   static constexpr int PPT = (TH * TW) / NT;
-  static constexpr size_t smem_bytes = sizeof(float) * (7 * PLANE + 6 * HB + 32) + sizeof(Camera) * SQLX_MAX_SOURCES +
-                                       sizeof(int4) * (PH + PW);
+  static constexpr int TS = TH * TW;              // one plane of per-pixel target statistics
+  static constexpr size_t smem_bytes = sizeof(float) * (7 * PLANE + 6 * HB + 6 * TS + 32) +
+                                       sizeof(Camera) * SQLX_MAX_SOURCES + sizeof(int4) * (PH + PW);
   static_assert((TH * TW) % NT == 0 && NT % TW == 0 && NT >= PH + PW, "tile / block shape");
 };
 
@@ -210,7 +239,8 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
   float* wp = tg + 3 * C::PLANE;        // 3 planes
   float* hbA = wp + 3 * C::PLANE;       // 3 planes of HB
   float* hbB = hbA + 3 * C::HB;         // 3 planes of HB
-  float* red = hbB + 3 * C::HB;
+  float* tstat = hbB + 3 * C::HB;      // [3 ch][mean, variance + C2][TH*TW]: target statistics of the owned pixels
+  float* red = tstat + 6 * C::TS;
   int4* rowt = reinterpret_cast<int4*>(red + 32);     // [PH]
   int4* colt = rowt + C::PH;                           // [PW]
   Camera* cams = reinterpret_cast<Camera*>(colt + C::PW);
@@ -301,8 +331,9 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
     }
   }
 
-  // target statistics per channel, kept in registers: mean and variance + C2
-  float my[3][PPT], syy2[3][PPT];
+  // target statistics per channel (mean and variance + C2): written and read back by the owning thread only
+  // (shared memory rather than 6*PPT registers that would stay live across the whole source loop)
+  float* tsp = tstat + prow0 * TW + pcol;
   if (R > 0) {
     hpass_blocked<RR, C::PH, TW, C::LD, TW, false>(nullptr, tg, hbA, hbA + C::HB, nullptr);
     __syncthreads();
@@ -316,8 +347,9 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
       vsum_multi<R, TW, PPT>(cur + C::HB, prow0, pcol, Syy);
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
-        my[c][k] = Sy[k] * ia;
-        syy2[c][k] = fmaf(-my[c][k], my[c][k], Syy[k] * ia) + kC2;
+        const float m = Sy[k] * ia;
+        tsp[(2 * c) * C::TS + k * TW] = m;
+        tsp[(2 * c + 1) * C::TS + k * TW] = fmaf(-m, m, Syy[k] * ia) + kC2;
       }
       if (c < 2) __syncthreads();
     }
@@ -330,14 +362,15 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
   for (int s = 0; s < S; ++s) {
     {   // warp source s into the three shared planes (R halo included), two elements per trip
       const float4* src = p.src[s] + (size_t)b * plane;
-      const Camera cam = cams[s];
+      const CamM cam = compose_camera(cams[s]);
       const float eps = p.d.eps;
       float4 ta[2], tb[2], tc[2], td[2];
       float fx[2], fy[2];
       for_region2<C::PH, C::PW, NT>(
           [&](int j, int lr, int lc, bool live) {
-            const Proj pr = project_fast(cam, (float)colt[lc].w, (float)rowt[lr].w, dpl[lr * C::LD + lc], eps);
-            const Taps4 t = make_taps4(pr.pu, pr.pv, H, W);
+            float pu, pv;
+            project_composed(cam, (float)colt[lc].w, (float)rowt[lr].w, dpl[lr * C::LD + lc], eps, pu, pv);
+            const Taps4 t = make_taps4(pu, pv, H, W);
             fx[j] = t.fx; fy[j] = t.fy;
             if (live) {
               const float4* q = src + t.o;
@@ -381,11 +414,11 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
           // layers.py:37-46 with one reciprocal, shared by the value and its derivative coefficients
-          const float mx = Sx[k] * ia, myk = my[c][k];
+          const float mx = Sx[k] * ia, myk = tsp[(2 * c) * C::TS + k * TW];
           const float sxx = fmaf(-mx, mx, Sxx[k] * ia);
           const float sxy = fmaf(-mx, myk, Sxy[k] * ia);
           const float n1 = fmaf(2.f * mx, myk, kC1), n2 = fmaf(2.f, sxy, kC2);
-          const float d1 = fmaf(mx, mx, fmaf(myk, myk, kC1)), d2 = sxx + syy2[c][k];
+          const float d1 = fmaf(mx, mx, fmaf(myk, myk, kC1)), d2 = sxx + tsp[(2 * c + 1) * C::TS + k * TW];
           const float inv_d = __fdividef(1.f, d1 * d2);
           const float q = n1 * n2 * inv_d;
           const float val = 0.5f - 0.5f * q;

@@ -174,6 +174,40 @@ int sqlx_scale_loss_bwd(const sqlx_scale_desc* desc, const float* depth_lr, cons
                         float* d_depth_lr, float* const* d_axisangle, float* const* d_translation, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* ---- ALL loss scales as one forward and one backward call (the whole of generate_images_pred + compute_losses,
+ * trainer.py:386-439 and 455-549).  What is not the fused photometric kernel is batched across scales: 13 kernel
+ * launches per step for 4 scales; every reduction has a fixed order and the upsample adjoint is a gather, so the
+ * gradients are bit-reproducible run to run.
+ *   depth_lr[s] [B,1,h[s],w[s]]   outputs[("disp", s)] (these ARE depth, trainer.py:399-402)
+ *   color[s]    [B,3,Hc[s],Wc[s]] inputs[("color",0,s)]: either the depth map's own shape (used as is) or HxW
+ *                                 (the map is upsampled first, trainer.py:533-534)
+ *   noise[s]    [B,Sn,H,W]        tie-break noise of scale s
+ *   loss        [1 + num_scales]  device: {losses["loss"], losses["loss/0"], losses["loss/1"], ...}
+ *   argmin[s]   [B,H,W] u8 */
+#define SQLX_MAX_SCALES 8
+typedef struct sqlx_ms_desc {
+  sqlx_photo_desc photo;                 /* B, H, W, S, flags, weights; photo.h / photo.w are ignored */
+  int32_t num_scales;
+  int32_t h[SQLX_MAX_SCALES], w[SQLX_MAX_SCALES];
+  int32_t Hc[SQLX_MAX_SCALES], Wc[SQLX_MAX_SCALES];
+  float smooth_weight[SQLX_MAX_SCALES];  /* disparity_smoothness / 2^s (trainer.py:542) */
+  int32_t rescale_translation;           /* 1: translation *= mean inverse depth (posecnn and not use_stereo) */
+} sqlx_ms_desc;
+size_t sqlx_ms_saved_bytes(const sqlx_ms_desc* desc);
+size_t sqlx_ms_workspace_bytes(const sqlx_ms_desc* desc);
+int sqlx_ms_loss_fwd(const sqlx_ms_desc* desc, const float* const* depth_lr, const float* target,
+                     const float* const* sources_rgba, const float* const* color, const float* K, const float* inv_K,
+                     const sqlx_pose_inputs* poses, const float* identity, const float* const* noise, float* loss,
+                     uint8_t* const* argmin, void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* g_loss: device scalar, upstream gradient of loss[0].  d_depth_lr[s] [B,h[s],w[s]] overwritten; d_axisangle[f],
+ * d_translation[f] [B,3] overwritten with the sum over scales (entries may be NULL). */
+int sqlx_ms_loss_bwd(const sqlx_ms_desc* desc, const float* const* depth_lr, const float* target,
+                     const float* const* sources_rgba, const float* const* color, const float* K, const float* inv_K,
+                     const sqlx_pose_inputs* poses, const uint8_t* const* argmin, const float* g_loss, const void* saved,
+                     float* const* d_depth_lr, float* const* d_axisangle, float* const* d_translation, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /* Module-level geometry drop-ins (the fused path above never materialises these tensors).
  * BackprojectDepth.forward (layers.py:210-215): depth [B,1,H,W], inv_K [B,4,4] -> points [B,4,H*W] (row 3 = 1). */
 int sqlx_backproject_fwd(const float* depth, const float* inv_K, int B, int H, int W, float* points, void* stream);

@@ -202,6 +202,7 @@ __device__ __forceinline__ void warp_reduce16(float (&v)[16]) {
 // ------------------------------------------------------------------------------------------------
 struct PhotoFwdParams {
   sqlx_photo_desc d;
+  const float* depth_up;   // optional [B,H,W]: upsampled depth (multiscale.cu materialises it once per scale)
   const float* depth_lr;
   const float* target;
   const float4* src[SQLX_MAX_SOURCES];   // pixel-interleaved [B,H,W,4]
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
 
   {   // upsampled depth and the three target planes on the R halo, two elements per trip
     const float* lr_map = p.depth_lr + (size_t)b * p.d.h * p.d.w;
+    const float* up_map = p.depth_up ? p.depth_up + (size_t)b * plane : nullptr;
     const float* tgb = p.target + (size_t)b * 3 * plane;
     float dv[2][4], tv[2][3], wy[2], wx[2];
     for_region2<C::PH, C::PW, NT>(
@@ -269,10 +271,14 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
           const int4 rt = rowt[lr], ct = colt[lc];
           wy[j] = __int_as_float(rt.z); wx[j] = __int_as_float(ct.z);
           if (live) {
-            const float* r0 = lr_map + rt.x;
-            const float* r1 = lr_map + rt.y;
-            dv[j][0] = __ldg(r0 + ct.x); dv[j][1] = __ldg(r0 + ct.y);
-            dv[j][2] = __ldg(r1 + ct.x); dv[j][3] = __ldg(r1 + ct.y);
+            if (up_map) {
+              dv[j][0] = __ldg(up_map + rt.w * W + ct.w);
+            } else {
+              const float* r0 = lr_map + rt.x;
+              const float* r1 = lr_map + rt.y;
+              dv[j][0] = __ldg(r0 + ct.x); dv[j][1] = __ldg(r0 + ct.y);
+              dv[j][2] = __ldg(r1 + ct.x); dv[j][3] = __ldg(r1 + ct.y);
+            }
             const float* tp = tgb + (size_t)(rt.w * W + ct.w);
             tv[j][0] = __ldg(tp); tv[j][1] = __ldg(tp + plane); tv[j][2] = __ldg(tp + 2 * plane);
           }
@@ -280,8 +286,9 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
         [&](int j, int lr, int lc) {
           const int o = lr * C::LD + lc;
           // same expression as upsample_at (common.cuh): bit-identical depth in every kernel
-          dpl[o] = (1.f - wy[j]) * ((1.f - wx[j]) * dv[j][0] + wx[j] * dv[j][1]) +
-                   wy[j] * ((1.f - wx[j]) * dv[j][2] + wx[j] * dv[j][3]);
+          dpl[o] = up_map ? dv[j][0]
+                          : (1.f - wy[j]) * ((1.f - wx[j]) * dv[j][0] + wx[j] * dv[j][1]) +
+                                wy[j] * ((1.f - wx[j]) * dv[j][2] + wx[j] * dv[j][3]);
           tg[o] = tv[j][0]; tg[C::PLANE + o] = tv[j][1]; tg[2 * C::PLANE + o] = tv[j][2];
         });
   }
@@ -492,6 +499,7 @@ __global__ void finalize_sum3_kernel(const float* __restrict__ partial, int n, f
 // ------------------------------------------------------------------------------------------------
 struct PhotoBwdParams {
   sqlx_photo_desc d;
+  const float* depth_up;   // optional [B,H,W]
   const float* depth_lr;
   const float* target;
   const float4* src[SQLX_MAX_SOURCES];
@@ -502,7 +510,11 @@ struct PhotoBwdParams {
   const float* coef;
   const float* g_loss;
   float scale;
-  float* d_depth_lr;
+  float* d_depth_lr;   // [B,h,w] accumulated through the bilinear-upsample adjoint (atomics), or NULL when g_up is used
+  float* g_up;         // [B,H,W] gradient wrt the UPSAMPLED depth, one plain store per pixel (no atomics); the caller
+                       // applies the upsample adjoint as a gather (multiscale.cu).  NULL -> d_depth_lr path
+  float* q_up;         // optional [B,H,W]: 1 / d_up^2 (the upsample-adjoint kernel needs it for the mean-inverse-depth term)
+  int g_up_accumulate; // 1: g_up += (the smoothness backward already wrote the plane), 0: g_up =
   float* dP;  // [B,S,12] accumulators (zeroed by the host wrapper)
 };
 
@@ -578,7 +590,8 @@ __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdPara
 #pragma unroll
     for (int c = 0; c < 3; ++c) Yv[c][k] = 0.f;
     if (pin[k]) {
-      dep[k] = upsample_at(p.depth_lr + (size_t)b * h * w, h, w, v0 + prow0 + k, u0 + pcol, sy, sx);
+      dep[k] = p.depth_up ? __ldg(p.depth_up + (size_t)b * plane + pix0 + (size_t)k * W)
+                          : upsample_at(p.depth_lr + (size_t)b * h * w, h, w, v0 + prow0 + k, u0 + pcol, sy, sx);
 #pragma unroll
       for (int c = 0; c < 3; ++c) Yv[c][k] = __ldg(p.target + ((size_t)b * 3 + c) * plane + pix0 + (size_t)k * W);
     }
@@ -731,19 +744,30 @@ __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdPara
     }
   }
 
+  __syncthreads();
+  if (threadIdx.x < 12 * S) {
+    const int s = threadIdx.x / 12, i = threadIdx.x - s * 12;
+    const float t = dPs[s * 16 + i];
+    if (t != 0.f) atomicAdd(p.dP + ((size_t)b * S + s) * 12 + i, t);
+  }
+  if (p.g_up) {   // hand the per-pixel gradient to the gather-style upsample adjoint
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      if (!pin[k]) continue;
+      const size_t o = (size_t)b * plane + pix0 + (size_t)k * W;
+      float* q = p.g_up + o;
+      *q = p.g_up_accumulate ? *q + gd[k] : gd[k];
+      if (p.q_up) p.q_up[o] = __fdividef(1.f, dep[k] * dep[k]);
+    }
+    return;
+  }
   // adjoint of the bilinear upsampling: per-tile accumulation in shared memory, one global atomic per touched cell
   const int vend = min(v0 + TH, H) - 1, uend = min(u0 + TW, W) - 1;
   const int i_lo = up_tap(v0, sy, h).i0, i_hi = up_tap(vend, sy, h).i1;
   const int j_lo = up_tap(u0, sx, w).i0, j_hi = up_tap(uend, sx, w).i1;
   const int nh = i_hi - i_lo + 1, nw = j_hi - j_lo + 1;
   float* acc = h2;
-  __syncthreads();
   for (int idx = threadIdx.x; idx < nh * nw; idx += NT) acc[idx] = 0.f;
-  if (threadIdx.x < 12 * S) {
-    const int s = threadIdx.x / 12, i = threadIdx.x - s * 12;
-    const float t = dPs[s * 16 + i];
-    if (t != 0.f) atomicAdd(p.dP + ((size_t)b * S + s) * 12 + i, t);
-  }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < PPT; ++k) {
@@ -888,18 +912,19 @@ extern "C" size_t sqlx_photo_coef_bytes(const sqlx_photo_desc* d) {
   return sizeof(float) * 9 * (size_t)d->B * d->S * d->H * d->W;
 }
 
-extern "C" int sqlx_photo_fwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
-                              const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
-                              const float* identity, const float* noise, float* loss_sum, uint8_t* argmin,
-                              float* ssim_coef, void* workspace, size_t workspace_bytes, void* stream) {
+// internal entry points shared with multiscale.cu (declared in photo_v3.h)
+namespace sqlx {
+int photo_fwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const float* depth_up, const float* target,
+                      const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
+                      const float* identity, const float* noise, float* partial, int* ctas, uint8_t* argmin,
+                      float* ssim_coef, cudaStream_t st) {
   if (int e = check_desc(desc)) return e;
-  SQLX_REQUIRE(depth_lr && target && sources_rgba && K && inv_K && T && loss_sum && argmin, "NULL pointer argument");
-  SQLX_REQUIRE(workspace && workspace_bytes >= sqlx_photo_workspace_bytes(desc), "workspace too small");
+  SQLX_REQUIRE(depth_lr && target && sources_rgba && K && inv_K && T && partial && ctas && argmin, "NULL pointer argument");
   const bool automask = desc->flags & SQLX_AUTOMASK;
   SQLX_REQUIRE(!automask || (identity && noise), "automask needs identity and noise");
   PhotoFwdParams p;
   p.d = *desc;
-  p.depth_lr = depth_lr; p.target = target;
+  p.depth_lr = depth_lr; p.depth_up = depth_up; p.target = target;
   for (int s = 0; s < SQLX_MAX_SOURCES; ++s)
     p.src[s] = s < desc->S ? reinterpret_cast<const float4*>(sources_rgba[s]) : nullptr;
   for (int s = 0; s < desc->S; ++s) {
@@ -907,16 +932,55 @@ extern "C" int sqlx_photo_fwd(const sqlx_photo_desc* desc, const float* depth_lr
     SQLX_REQUIRE((reinterpret_cast<uintptr_t>(p.src[s]) & 15) == 0, "source %d is not 16-byte aligned", s);
   }
   p.K = K; p.invK = inv_K; p.T = T; p.identity = identity; p.noise = noise;
-  p.partial = reinterpret_cast<float*>(workspace);
+  p.partial = partial;
   p.argmin = argmin;
   p.coef = (desc->flags & SQLX_NO_SSIM) ? nullptr : ssim_coef;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int r = (desc->flags & SQLX_NO_SSIM) ? 0 : desc->ssim_radius;
+  return r == 3 ? dispatch_photo_fwd3<3>(p, ctas, st)
+                : (r == 1 ? dispatch_photo_fwd3<1>(p, ctas, st) : dispatch_photo_fwd3<0>(p, ctas, st));
+}
+
+int photo_bwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const float* depth_up, const float* target,
+                      const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
+                      const uint8_t* argmin, const float* ssim_coef, const float* g_loss, float scale,
+                      float* d_depth_lr, float* g_up, float* q_up, int g_up_accumulate, float* dP, cudaStream_t st) {
+  if (int e = check_desc(desc)) return e;
+  SQLX_REQUIRE(depth_lr && target && sources_rgba && K && inv_K && T && argmin && g_loss && (d_depth_lr || g_up) && dP,
+               "NULL pointer argument");
+  const int r = (desc->flags & SQLX_NO_SSIM) ? 0 : desc->ssim_radius;
+  SQLX_REQUIRE(r == 0 || ssim_coef, "the backward needs the SSIM coefficients exported by sqlx_photo_fwd");
+  PhotoBwdParams p;
+  p.d = *desc;
+  p.depth_lr = depth_lr; p.depth_up = depth_up; p.target = target;
+  for (int s = 0; s < SQLX_MAX_SOURCES; ++s)
+    p.src[s] = s < desc->S ? reinterpret_cast<const float4*>(sources_rgba[s]) : nullptr;
+  for (int s = 0; s < desc->S; ++s) {
+    SQLX_REQUIRE(p.src[s], "source %d is NULL", s);
+    SQLX_REQUIRE((reinterpret_cast<uintptr_t>(p.src[s]) & 15) == 0, "source %d is not 16-byte aligned", s);
+  }
+  p.K = K; p.invK = inv_K; p.T = T; p.argmin = argmin; p.coef = ssim_coef; p.g_loss = g_loss; p.scale = scale;
+  p.d_depth_lr = d_depth_lr; p.g_up = g_up; p.q_up = q_up; p.g_up_accumulate = g_up_accumulate;
+  p.dP = dP;
+  return r == 3 ? dispatch_photo_bwd3<3>(p, st) : (r == 1 ? dispatch_photo_bwd3<1>(p, st) : dispatch_photo_bwd3<0>(p, st));
+}
+
+size_t photo_max_ctas(const sqlx_photo_desc* d) { return fwd_ctas(d); }
+}  // namespace sqlx
+
+extern "C" int sqlx_photo_fwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
+                              const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
+                              const float* identity, const float* noise, float* loss_sum, uint8_t* argmin,
+                              float* ssim_coef, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_desc(desc)) return e;
+  SQLX_REQUIRE(loss_sum, "NULL pointer argument");
+  SQLX_REQUIRE(workspace && workspace_bytes >= sqlx_photo_workspace_bytes(desc), "workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* partial = reinterpret_cast<float*>(workspace);
   int ctas = 0;
-  int e = r == 3 ? dispatch_photo_fwd3<3>(p, &ctas, st)
-                 : (r == 1 ? dispatch_photo_fwd3<1>(p, &ctas, st) : dispatch_photo_fwd3<0>(p, &ctas, st));
-  if (e) return e;
-  finalize_sum3_kernel<<<1, 256, 0, st>>>(p.partial, ctas, loss_sum);
+  if (int e = photo_fwd3_launch(desc, depth_lr, nullptr, target, sources_rgba, K, inv_K, T, identity, noise, partial, &ctas, argmin,
+                                ssim_coef, st))
+    return e;
+  finalize_sum3_kernel<<<1, 256, 0, st>>>(partial, ctas, loss_sum);
   return check_launch("finalize_sum_kernel");
 }
 
@@ -925,30 +989,17 @@ extern "C" int sqlx_photo_bwd(const sqlx_photo_desc* desc, const float* depth_lr
                               const uint8_t* argmin, const float* ssim_coef, const float* g_loss, float scale,
                               float* d_depth_lr, float* d_T, void* workspace, size_t workspace_bytes, void* stream) {
   if (int e = check_desc(desc)) return e;
-  SQLX_REQUIRE(depth_lr && target && sources_rgba && K && inv_K && T && argmin && g_loss && d_depth_lr && d_T,
-               "NULL pointer argument");
+  SQLX_REQUIRE(d_depth_lr && d_T, "NULL pointer argument");
   SQLX_REQUIRE(workspace && workspace_bytes >= sqlx_photo_workspace_bytes(desc), "workspace too small");
-  const int r = (desc->flags & SQLX_NO_SSIM) ? 0 : desc->ssim_radius;
-  SQLX_REQUIRE(r == 0 || ssim_coef, "the backward needs the SSIM coefficients exported by sqlx_photo_fwd");
-  PhotoBwdParams p;
-  p.d = *desc;
-  p.depth_lr = depth_lr; p.target = target;
-  for (int s = 0; s < SQLX_MAX_SOURCES; ++s)
-    p.src[s] = s < desc->S ? reinterpret_cast<const float4*>(sources_rgba[s]) : nullptr;
-  for (int s = 0; s < desc->S; ++s) {
-    SQLX_REQUIRE(p.src[s], "source %d is NULL", s);
-    SQLX_REQUIRE((reinterpret_cast<uintptr_t>(p.src[s]) & 15) == 0, "source %d is not 16-byte aligned", s);
-  }
-  p.K = K; p.invK = inv_K; p.T = T; p.argmin = argmin; p.coef = ssim_coef; p.g_loss = g_loss; p.scale = scale;
-  p.d_depth_lr = d_depth_lr;
   // dP accumulators live after the forward partial sums in the workspace
-  p.dP = reinterpret_cast<float*>(workspace) + fwd_ctas(desc);
+  float* dP = reinterpret_cast<float*>(workspace) + fwd_ctas(desc);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (cudaMemsetAsync(p.dP, 0, sizeof(float) * (size_t)desc->B * desc->S * 12, st) != cudaSuccess)
+  if (cudaMemsetAsync(dP, 0, sizeof(float) * (size_t)desc->B * desc->S * 12, st) != cudaSuccess)
     return check_launch("cudaMemsetAsync(dP)");
-  int e = r == 3 ? dispatch_photo_bwd3<3>(p, st) : (r == 1 ? dispatch_photo_bwd3<1>(p, st) : dispatch_photo_bwd3<0>(p, st));
-  if (e) return e;
+  if (int e = photo_bwd3_launch(desc, depth_lr, nullptr, target, sources_rgba, K, inv_K, T, argmin, ssim_coef, g_loss, scale,
+                                d_depth_lr, nullptr, nullptr, 0, dP, st))
+    return e;
   const int n = desc->B * desc->S * 16;
-  dT_from_dP3_kernel<<<ceil_div(n, 128), 128, 0, st>>>(K, p.dP, desc->B, desc->S, d_T);
+  dT_from_dP3_kernel<<<ceil_div(n, 128), 128, 0, st>>>(K, dP, desc->B, desc->S, d_T);
   return check_launch("dT_from_dP_kernel");
 }

@@ -1,0 +1,19 @@
+// Internal (non-ABI) entry points of photo_v3.cu used by multiscale.cu.
+#pragma once
+#include "common.cuh"
+
+namespace sqlx {
+// launches photo_fwd3_kernel; per-CTA partial sums of the per-pixel minimum land in partial[0 .. *ctas)
+// depth_up: optional [B,H,W] already-upsampled depth (read instead of upsampling depth_lr per pixel)
+int photo_fwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const float* depth_up, const float* target,
+                      const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
+                      const float* identity, const float* noise, float* partial, int* ctas, uint8_t* argmin,
+                      float* ssim_coef, cudaStream_t st);
+// launches photo_bwd3_kernel; exactly one of d_depth_lr (atomic upsample adjoint) / g_up (per-pixel plane) is given
+int photo_bwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const float* depth_up, const float* target,
+                      const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
+                      const uint8_t* argmin, const float* ssim_coef, const float* g_loss, float scale,
+                      float* d_depth_lr, float* g_up, float* q_up /*optional 1/d_up^2 plane*/, int g_up_accumulate, float* dP,
+                      cudaStream_t st);
+size_t photo_max_ctas(const sqlx_photo_desc* d);   // upper bound of *ctas for any tile configuration
+}  // namespace sqlx

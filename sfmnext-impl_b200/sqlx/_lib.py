@@ -33,6 +33,16 @@ class ScaleDesc(ctypes.Structure):
                 ("smooth_weight", ctypes.c_float), ("rescale_translation", ctypes.c_int32)]
 
 
+MAX_SCALES = 8
+
+
+class MsDesc(ctypes.Structure):
+    _fields_ = [("photo", PhotoDesc), ("num_scales", ctypes.c_int32),
+                ("h", ctypes.c_int32 * MAX_SCALES), ("w", ctypes.c_int32 * MAX_SCALES),
+                ("Hc", ctypes.c_int32 * MAX_SCALES), ("Wc", ctypes.c_int32 * MAX_SCALES),
+                ("smooth_weight", ctypes.c_float * MAX_SCALES), ("rescale_translation", ctypes.c_int32)]
+
+
 class PoseInputs(ctypes.Structure):
     _fields_ = [("axisangle", ctypes.c_void_p * MAX_SOURCES), ("translation", ctypes.c_void_p * MAX_SOURCES),
                 ("fixed_T", ctypes.c_void_p * MAX_SOURCES), ("invert_mask", ctypes.c_uint32)]
@@ -71,6 +81,16 @@ _PROTOS = {
     "sqlx_scale_loss_bwd": (c_int, [ctypes.POINTER(ScaleDesc), c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_void_p,
                                     c_void_p, c_void_p, ctypes.POINTER(PoseInputs), c_void_p, c_void_p, c_void_p, c_void_p,
                                     ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_void_p, c_size_t, c_void_p]),
+    "sqlx_ms_saved_bytes": (c_size_t, [ctypes.POINTER(MsDesc)]),
+    "sqlx_ms_workspace_bytes": (c_size_t, [ctypes.POINTER(MsDesc)]),
+    "sqlx_ms_loss_fwd": (c_int, [ctypes.POINTER(MsDesc), ctypes.POINTER(c_void_p), c_void_p, ctypes.POINTER(c_void_p),
+                                 ctypes.POINTER(c_void_p), c_void_p, c_void_p, ctypes.POINTER(PoseInputs), c_void_p,
+                                 ctypes.POINTER(c_void_p), c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_size_t,
+                                 c_void_p, c_size_t, c_void_p]),
+    "sqlx_ms_loss_bwd": (c_int, [ctypes.POINTER(MsDesc), ctypes.POINTER(c_void_p), c_void_p, ctypes.POINTER(c_void_p),
+                                 ctypes.POINTER(c_void_p), c_void_p, c_void_p, ctypes.POINTER(PoseInputs),
+                                 ctypes.POINTER(c_void_p), c_void_p, c_void_p, ctypes.POINTER(c_void_p),
+                                 ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_void_p, c_size_t, c_void_p]),
     "sqlx_backproject_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sqlx_backproject_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sqlx_project_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),

@@ -295,6 +295,107 @@ class _ScaleLoss(torch.autograd.Function):
         return (d_depth, None) + tuple(gr.reshape(sh) for gr, sh in zip(grads, shapes))
 
 
+def _ptr_array(tensors, n):
+    arr = (ctypes.c_void_p * n)()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
+class _MultiScaleLoss(torch.autograd.Function):
+    """Every loss scale in one library call forward and one backward (csrc/multiscale.cu): 13 kernel launches per
+    step for 4 scales, one autograd node, pose gradients summed over scales inside the library."""
+
+    @staticmethod
+    def forward(ctx, meta, *tensors):
+        (target, colors, K, inv_K, identity, noises, sources, pose_spec, cfg, smooth_weights, rescale) = meta
+        ns = len(colors)
+        disps = [_f32c(t) for t in tensors[:ns]]
+        pose_tensors = tensors[ns:]
+        B = disps[0].shape[0]
+        H, W = target.shape[-2:]
+        S = len(sources)
+        desc = _lib.MsDesc()
+        desc.photo = make_desc(B, H, W, disps[0].shape[-2], disps[0].shape[-1], S, **cfg)
+        desc.num_scales = ns
+        cols = [_f32c(c) for c in colors]
+        for i in range(ns):
+            desc.h[i], desc.w[i] = disps[i].shape[-2:]
+            desc.Hc[i], desc.Wc[i] = cols[i].shape[-2:]
+            desc.smooth_weight[i] = float(smooth_weights[i])
+        desc.rescale_translation = int(bool(rescale))
+        keep = []                                  # contiguous fp32 views that must outlive the call
+        pin = _lib.PoseInputs()
+        mask = 0
+        it = iter(pose_tensors)
+        for i, spec in enumerate(pose_spec):
+            if spec[0] == "fixed":
+                Tm = _f32c(spec[1]); keep.append(Tm)
+                pin.fixed_T[i] = Tm.data_ptr()
+            else:
+                aa = _f32c(next(it)).reshape(B, 3); tr = _f32c(next(it)).reshape(B, 3)
+                keep += [aa, tr]
+                pin.axisangle[i] = aa.data_ptr(); pin.translation[i] = tr.data_ptr()
+                if spec[1]:
+                    mask |= 1 << i
+        pin.invert_mask = mask
+        dev = disps[0].device
+        saved = torch.empty(lib().sqlx_ms_saved_bytes(ctypes.byref(desc)), device=dev, dtype=torch.uint8)
+        nws = lib().sqlx_ms_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(nws, device=dev, dtype=torch.uint8)
+        losses = torch.empty(1 + ns, device=dev, dtype=torch.float32)
+        argmins = [torch.empty(B, H, W, device=dev, dtype=torch.uint8) for _ in range(ns)]
+        srcs = list(sources)                       # [B,H,W,4] pixel-interleaved copies (pack_rgba)
+        tgt, Kc, iKc, ident = (_f32c(t) for t in (target, K, inv_K, identity))
+        nzs = [_f32c(n) for n in noises]
+        M = _lib.MAX_SCALES
+        check(lib().sqlx_ms_loss_fwd(ctypes.byref(desc), _ptr_array(disps, M), ptr(tgt), _src_array(srcs),
+                                     _ptr_array(cols, M), ptr(Kc), ptr(iKc), ctypes.byref(pin), ptr(ident),
+                                     _ptr_array(nzs, M), ptr(losses), _ptr_array(argmins, M), ptr(saved), saved.numel(),
+                                     ptr(ws), nws, stream_ptr()), "sqlx_ms_loss_fwd")
+        ctx.save_for_backward(tgt, Kc, iKc, saved, *disps, *cols, *argmins, *srcs, *keep)
+        ctx.state = (desc, pose_spec, mask, S, ns, [t.shape for t in pose_tensors], [t.shape for t in tensors[:ns]])
+        per_scale = losses[1:].detach()
+        ctx.mark_non_differentiable(per_scale, *argmins)
+        return (losses[0], per_scale) + tuple(argmins)
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_per_scale, *_g_argmins):
+        desc, pose_spec, mask, S, ns, pose_shapes, disp_shapes = ctx.state
+        tgt, Kc, iKc, saved, *rest = ctx.saved_tensors
+        disps, cols, argmins = rest[:ns], rest[ns:2 * ns], rest[2 * ns:3 * ns]
+        srcs, keep = rest[3 * ns:3 * ns + S], rest[3 * ns + S:]
+        B = disps[0].shape[0]
+        dev = disps[0].device
+        pin = _lib.PoseInputs()
+        pin.invert_mask = mask
+        d_aa = (ctypes.c_void_p * _lib.MAX_SOURCES)()
+        d_tr = (ctypes.c_void_p * _lib.MAX_SOURCES)()
+        grads = []
+        it = iter(keep)
+        for i, spec in enumerate(pose_spec):
+            if spec[0] == "fixed":
+                pin.fixed_T[i] = next(it).data_ptr()
+            else:
+                aa, tr = next(it), next(it)
+                pin.axisangle[i] = aa.data_ptr(); pin.translation[i] = tr.data_ptr()
+                ga = torch.empty(B, 3, device=dev, dtype=torch.float32)
+                gt = torch.empty(B, 3, device=dev, dtype=torch.float32)
+                d_aa[i] = ga.data_ptr(); d_tr[i] = gt.data_ptr()
+                grads += [ga, gt]
+        nws = lib().sqlx_ms_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(nws, device=dev, dtype=torch.uint8)
+        d_disps = [torch.empty_like(d) for d in disps]
+        g = g_loss.contiguous().float().reshape(1)
+        M = _lib.MAX_SCALES
+        check(lib().sqlx_ms_loss_bwd(ctypes.byref(desc), _ptr_array(disps, M), ptr(tgt), _src_array(srcs),
+                                     _ptr_array(cols, M), ptr(Kc), ptr(iKc), ctypes.byref(pin), _ptr_array(argmins, M),
+                                     ptr(g), ptr(saved), _ptr_array(d_disps, M), d_aa, d_tr, ptr(ws), nws, stream_ptr()),
+              "sqlx_ms_loss_bwd")
+        return (None,) + tuple(dd.reshape(sh) for dd, sh in zip(d_disps, disp_shapes)) + \
+            tuple(gr.reshape(sh) for gr, sh in zip(grads, pose_shapes))
+
+
 def identity_losses(target, sources, *, no_ssim=False, ssim_radius=3, w_ssim=0.85, w_l1=0.15):
     """[B,S,H,W]: compute_reprojection_loss(source_f, target) for every source (trainer.py:480-493), no torch.cat."""
     require_cuda(target, *sources)
@@ -310,8 +411,10 @@ def identity_losses(target, sources, *, no_ssim=False, ssim_radius=3, w_ssim=0.8
 
 def photometric_losses(disps, target_pyr, sources, K, inv_K, poses, noises, *, height, width, scales=(0,),
                        disparity_smoothness=1e-3, rescale_translation=True, no_ssim=False, avg_reprojection=False,
-                       disable_automasking=False, ssim_radius=3, materialize=False, identity=None):
-    """generate_images_pred + compute_losses (trainer.py:386-549): one fused library call per loss scale.
+                       disable_automasking=False, ssim_radius=3, materialize=False, identity=None,
+                       per_scale_calls=False):
+    """generate_images_pred + compute_losses (trainer.py:386-549): ONE fused library call for all loss scales
+    (`per_scale_calls=True`: one call per scale through sqlx_scale_loss_fwd/bwd instead, same results).
 
     disps {s: [B,1,h_s,w_s]} network outputs (these ARE depth, trainer.py:399-402); target_pyr {s: [B,3,H_s,W_s]};
     sources: list of S [B,3,H,W]; poses: per source {"T": [B,4,4]} or {"axisangle", "translation" [B,1,1,3], "invert"};
@@ -340,22 +443,40 @@ def photometric_losses(disps, target_pyr, sources, K, inv_K, poses, noises, *, h
     rescale = bool(rescale_translation) and any(sp[0] == "net" for sp in pose_spec)
     n_ident = 0 if not automask else (1 if avg_reprojection else S)
     packed = [pack_rgba(src) for src in sources]    # once per step: every scale, forward and backward, gathers from these
-    total = 0
+    scales = tuple(scales)
+    if len(scales) > _lib.MAX_SCALES:
+        raise ValueError("at most %d loss scales" % _lib.MAX_SCALES)
+    noise_list = []
     for s in scales:
-        disp = disps[s]
         noise = None
         if automask:
             noise = noises.get(s) if noises is not None else None
             if noise is None:
                 noise = torch.randn(B, 1 if avg_reprojection else S, H, W, device=target.device)
-        meta = (target, target_pyr[s], K, inv_K, identity, noise, packed, pose_spec, cfg,
-                disparity_smoothness / (2 ** s), rescale)
-        loss, argmin = _ScaleLoss.apply(disp, meta, *pose_tensors)
-        out["loss/%d" % s] = loss
-        out[("argmin", s)] = argmin
+        noise_list.append(noise)
+    if per_scale_calls:
+        total = 0
+        for s, noise in zip(scales, noise_list):
+            meta = (target, target_pyr[s], K, inv_K, identity, noise, packed, pose_spec, cfg,
+                    disparity_smoothness / (2 ** s), rescale)
+            loss, argmin = _ScaleLoss.apply(disps[s], meta, *pose_tensors)
+            out["loss/%d" % s] = loss
+            out[("argmin", s)] = argmin
+            total = total + loss
+        out["loss"] = total / len(scales)
+    else:
+        meta = (target, [target_pyr[s] for s in scales], K, inv_K, identity, noise_list, packed, pose_spec, cfg,
+                [disparity_smoothness / (2 ** s) for s in scales], rescale)
+        res = _MultiScaleLoss.apply(meta, *[disps[s] for s in scales], *pose_tensors)
+        out["loss"] = res[0]
+        for i, s in enumerate(scales):
+            out["loss/%d" % s] = res[1][i]
+            out[("argmin", s)] = res[2 + i]
+    for s in scales:
+        disp = disps[s]
+        argmin = out[("argmin", s)]
         if automask:
             out["identity_selection/%d" % s] = _LazyMask(argmin, n_ident)
-        total = total + loss
         if materialize:
             stats = depth_stats(disp.detach(), H, W) if rescale else None
             for i, src in enumerate(sources):
@@ -373,7 +494,6 @@ def photometric_losses(disps, target_pyr, sources, K, inv_K, poses, noises, *, h
     if materialize and automask:
         for s in scales:
             out["identity_selection/%d" % s] = out["identity_selection/%d" % s].float()
-    out["loss"] = total / len(scales)
     return out
 
 

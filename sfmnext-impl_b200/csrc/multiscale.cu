@@ -75,19 +75,60 @@ __global__ void ms_stats_pose_kernel(MsShapes sh, MsPose ps, int rescale, float*
     const float* lr = sh.depth[sc] + (size_t)b * h * w;
     float* dup = sh.d_up[sc] + (size_t)b * H * W;
     float s1 = 0.f;
-    for (int u0 = 0; u0 < W; u0 += kKC * blockDim.x) {
-      UpTap tx[kKC];
-#pragma unroll
-      for (int k = 0; k < kKC; ++k) tx[k] = up_tap(min(u0 + k * (int)blockDim.x + (int)threadIdx.x, W - 1), sx, w);
-      for (int v = blockIdx.x; v < H; v += gridDim.x) {
-        const UpTap ty = up_tap(v, sy, h);
-#pragma unroll
-        for (int k = 0; k < kKC; ++k) {
-          const int u = u0 + k * (int)blockDim.x + (int)threadIdx.x;
-          if (u < W) {
-            const float d = blend4(lr, w, ty, tx[k]);
-            dup[v * W + u] = d;
+    const int f = H / h;
+    if (H == f * h && W == f * w && (f == 1 || (f & 1) == 0)) {
+      // Integer upsampling factor (1, 2, 4, ...): one thread per low-resolution cell (i, j) produces the f x f block of
+      // pixels whose first bilinear tap is that cell -- four loads per BLOCK, three FMAs per pixel.  The tap weights
+      // (r + .5) / f are exactly the ones up_tap() derives from src = (v + .5) / f - .5 for these factors.
+      const float rf = 1.f / (float)f;
+      const int half = f >> 1;
+      // work item = (cell, group of rows): whole block for f <= 2, one row of the block for larger factors (so a
+      // thread never walks more than f pixels... 3f/2 on the frame border)
+      const int rows_per_item = f <= 2 ? f : 1;
+      const int groups = f / rows_per_item;
+      const int items = h * w * groups;
+      for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+        const int cell = it / groups, grp = it - cell * groups;
+        const int i = cell / w, j = cell - i * w;
+        const int i1 = min(i + 1, h - 1), j1 = min(j + 1, w - 1);
+        const float a = __ldg(lr + i * w + j), bq = __ldg(lr + i * w + j1);
+        const float c = __ldg(lr + i1 * w + j), dq = __ldg(lr + i1 * w + j1);
+        // rows f*i + half + r, r = 0..f-1; the first cell row / column also owns the clamped pixels before it
+        int r_lo = grp * rows_per_item, r_hi = r_lo + rows_per_item;
+        if (i == 0 && grp == 0) r_lo = -half;
+        const int c_lo = (j == 0) ? -half : 0;
+        for (int r = r_lo; r < r_hi; ++r) {
+          const int v = f * i + half + r;
+          if (v >= H) break;
+          const float wy = f == 1 ? 0.f : fmaxf(((float)r + 0.5f) * rf, 0.f);
+          const float top = (1.f - wy), bot = wy;
+          float* row = dup + (size_t)v * W;
+#pragma unroll 4
+          for (int q = c_lo; q < f; ++q) {
+            const int u = f * j + half + q;
+            if (u >= W) break;
+            const float wx = f == 1 ? 0.f : fmaxf(((float)q + 0.5f) * rf, 0.f);
+            const float d = top * ((1.f - wx) * a + wx * bq) + bot * ((1.f - wx) * c + wx * dq);
+            row[u] = d;
             s1 += __fdividef(1.f, d);
+          }
+        }
+      }
+    } else {
+      for (int u0 = 0; u0 < W; u0 += kKC * blockDim.x) {
+        UpTap tx[kKC];
+#pragma unroll
+        for (int k = 0; k < kKC; ++k) tx[k] = up_tap(min(u0 + k * (int)blockDim.x + (int)threadIdx.x, W - 1), sx, w);
+        for (int v = blockIdx.x; v < H; v += gridDim.x) {
+          const UpTap ty = up_tap(v, sy, h);
+#pragma unroll
+          for (int k = 0; k < kKC; ++k) {
+            const int u = u0 + k * (int)blockDim.x + (int)threadIdx.x;
+            if (u < W) {
+              const float d = blend4(lr, w, ty, tx[k]);
+              dup[v * W + u] = d;
+              s1 += __fdividef(1.f, d);
+            }
           }
         }
       }
@@ -149,6 +190,8 @@ __global__ void ms_smooth_loss_kernel(MsShapes sh, float* __restrict__ spartial,
                                       unsigned int* __restrict__ counter, float* __restrict__ loss) {
   __shared__ float red[32];
   __shared__ double dred[256];
+  __shared__ float lsum[SQLX_MAX_SCALES];
+  extern __shared__ float sterm[];        // [ns * B]
   __shared__ int is_last;
   const int sc = blockIdx.z, b = blockIdx.y, B = sh.B;
   {
@@ -188,42 +231,67 @@ __global__ void ms_smooth_loss_kernel(MsShapes sh, float* __restrict__ spartial,
     if (!is_last) return;
     __threadfence();
   }
-  // ---- last block of the launch: every reduction in a fixed order
+  // ---- last block of the launch: every reduction in a fixed order, spread over the block's threads
   const int ns = sh.ns;
-  const volatile float* vsp = spartial;
   for (int i = threadIdx.x; i < ns * B * 3; i += blockDim.x) {
     const int k = i % 3, sb = i / 3;
+    const float* q = spartial + (size_t)sb * kMsBlocks * 3 + k;
     float v = 0.f;
-    for (int j = 0; j < kMsBlocks; ++j) v += vsp[((size_t)sb * kMsBlocks + j) * 3 + k];
+#pragma unroll 8
+    for (int j = 0; j < kMsBlocks; ++j) v += __ldcg(q + j * 3);
     sums[i] = v;
   }
-  __syncthreads();
-  float total = 0.f;
-  for (int s = 0; s < ns; ++s) {
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < ctas; i += blockDim.x) acc += (double)photo_partial[(size_t)s * max_ctas + i];
-    dred[threadIdx.x] = acc;
+  // photometric per-CTA partials of every scale: strided double sums, one tree for all scales
+  double acc[SQLX_MAX_SCALES];
+#pragma unroll
+  for (int s = 0; s < SQLX_MAX_SCALES; ++s) {
+    acc[s] = 0.0;
+    if (s < ns) {
+      const float* pp = photo_partial + (size_t)s * max_ctas;
+      for (int base = 0; base < ctas; base += 8 * (int)blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int i = base + k * (int)blockDim.x + (int)threadIdx.x;
+          v[k] = i < ctas ? pp[i] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[s] += (double)v[k];
+      }
+    }
+  }
+  __syncthreads();   // sums[] visible to the block
+#pragma unroll
+  for (int s = 0; s < SQLX_MAX_SCALES; ++s) {
+    if (s >= ns) break;
+    dred[threadIdx.x] = acc[s];
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
       if ((int)threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
       __syncthreads();
     }
-    if (threadIdx.x == 0) {
-      const float Hc = (float)sh.Hc[s], Wc = (float)sh.Wc[s];
-      const float rN = 1.f / (Hc * Wc), rNx = 1.f / ((float)B * Hc * (Wc - 1.f)), rNy = 1.f / ((float)B * (Hc - 1.f) * Wc);
+    if (threadIdx.x == 0) lsum[s] = (float)dred[0];
+    __syncthreads();
+  }
+  // smoothness term of every (scale, sample) in parallel, then a fixed-order sum per scale
+  for (int i = threadIdx.x; i < ns * B; i += blockDim.x) {
+    const int s = i / B;
+    const float Hc = (float)sh.Hc[s], Wc = (float)sh.Wc[s];
+    const float rN = 1.f / (Hc * Wc), rNx = 1.f / ((float)B * Hc * (Wc - 1.f)), rNy = 1.f / ((float)B * (Hc - 1.f) * Wc);
+    const float* q = sums + (size_t)i * 3;
+    const float inv = 1.f / (q[2] * rN + 1e-7f);
+    sterm[i] = (q[0] * inv) * rNx + (q[1] * inv) * rNy;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float total = 0.f;
+    for (int s = 0; s < ns; ++s) {
       double sm = 0.0;
-      for (int bb = 0; bb < B; ++bb) {
-        const float* q = sums + ((size_t)s * B + bb) * 3;
-        const float inv = 1.f / (q[2] * rN + 1e-7f);
-        sm += (double)((q[0] * inv) * rNx + (q[1] * inv) * rNy);
-      }
-      const float ls = (float)dred[0] * (1.f / ((float)B * (float)sh.H * (float)sh.W)) + sh.smooth_weight[s] * (float)sm;
+      for (int bb = 0; bb < B; ++bb) sm += (double)sterm[s * B + bb];
+      const float ls = lsum[s] * (1.f / ((float)B * (float)sh.H * (float)sh.W)) + sh.smooth_weight[s] * (float)sm;
       loss[1 + s] = ls;
       total += ls;
     }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
     loss[0] = total / (float)ns;
     *counter = 0u;
   }
@@ -345,47 +413,86 @@ __global__ void ms_pose_bwd_kernel(MsShapes sh, MsPose ps, int rescale, const fl
 // q_up[px] = 1 / d_up(px)^2 is stored by photo_bwd3_kernel; g_stat = d loss / d mean(1/d_up) / (H W).
 struct MsAdjoint {
   const float* q_up[SQLX_MAX_SCALES];
-  int tpc[SQLX_MAX_SCALES];
+  int log2_tpc[SQLX_MAX_SCALES];
+  int factor[SQLX_MAX_SCALES];   // integer upsampling factor (1 or even) or 0: generic path
+  float sy[SQLX_MAX_SCALES], sx[SQLX_MAX_SCALES], ry[SQLX_MAX_SCALES], rx[SQLX_MAX_SCALES];
+  float rHW;
 };
 
 __global__ void ms_upsample_adjoint_kernel(MsShapes sh, MsGrads g, MsAdjoint ad, int rescale,
                                            const float* __restrict__ g_stats) {
   const int sc = blockIdx.y;
   const int B = sh.B, H = sh.H, W = sh.W, h = sh.h[sc], w = sh.w[sc];
-  const int tpc = ad.tpc[sc];
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long cell = gid / tpc;
-  const int sub = (int)(gid - cell * tpc);
-  if ((long long)blockIdx.x * blockDim.x / tpc >= (long long)B * h * w) return;   // whole block beyond this scale
-  const bool live = cell < (long long)B * h * w;
+  const int lt = ad.log2_tpc[sc], tpc = 1 << lt;
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;      // < 2^31 (checked on the host)
+  const unsigned ncell = (unsigned)B * h * w;
+  if ((blockIdx.x * blockDim.x) >> lt >= ncell) return;            // whole block beyond this scale
+  const unsigned cell = gid >> lt;
+  const int sub = (int)(gid & (tpc - 1));
+  const bool live = cell < ncell;
   float acc = 0.f;
   if (live) {
-    const int b = (int)(cell / (h * w)), rem = (int)(cell - (long long)b * h * w);
+    const unsigned hw = (unsigned)h * w;
+    const int b = (int)(cell / hw), rem = (int)(cell - (unsigned)b * hw);
     const int i = rem / w, j = rem - i * w;
-    const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+    const float sy = ad.sy[sc], sx = ad.sx[sc], ry = ad.ry[sc], rx = ad.rx[sc];   // h/H, w/W, H/h, W/w
     // rows whose source coordinate sy*(v+.5)-.5 lies in [i-1, i+1): a margin keeps the bounds conservative, the
     // weights themselves are exact (rows outside the true footprint evaluate to weight 0)
-    const int v_lo = max(0, (int)ceilf(((float)i - 0.5f) / sy - 0.5f - 1e-3f));
-    const int v_hi = min(H - 1, (int)ceilf(((float)i + 1.5f) / sy - 0.5f + 1e-3f));
-    const int u_lo = max(0, (int)ceilf(((float)j - 0.5f) / sx - 0.5f - 1e-3f));
-    const int u_hi = min(W - 1, (int)ceilf(((float)j + 1.5f) / sx - 0.5f + 1e-3f));
+    const int v_lo = max(0, (int)ceilf(((float)i - 0.5f) * ry - 0.5f - 1e-3f));
+    const int v_hi = min(H - 1, (int)ceilf(((float)i + 1.5f) * ry - 0.5f + 1e-3f));
+    const int u_lo = max(0, (int)ceilf(((float)j - 0.5f) * rx - 0.5f - 1e-3f));
+    const int u_hi = min(W - 1, (int)ceilf(((float)j + 1.5f) * rx - 0.5f + 1e-3f));
     const float* gp = g.g_up[sc] + (size_t)b * H * W;
     const float* qp = ad.q_up[sc] + (size_t)b * H * W;
-    const float gs = rescale ? g_stats[sc * B + b] / ((float)H * (float)W) : 0.f;
-    for (int u = u_lo + sub; u <= u_hi; u += tpc) {
-      const UpTap tx = up_tap(u, sx, w);
-      const float wx = (tx.i0 == j ? tx.l0 : 0.f) + (tx.i1 == j ? tx.l1 : 0.f);
-      if (wx == 0.f) continue;
-      float col = 0.f;
-      for (int v = v_lo; v <= v_hi; ++v) {
-        const UpTap ty = up_tap(v, sy, h);
-        const float wy = (ty.i0 == i ? ty.l0 : 0.f) + (ty.i1 == i ? ty.l1 : 0.f);
-        const size_t o = (size_t)v * W + u;
-        float gg = gp[o];
-        if (rescale) gg = fmaf(-gs, qp[o], gg);
-        col = fmaf(wy, gg, col);
+    const float gs = rescale ? g_stats[sc * B + b] * ad.rHW : 0.f;
+    const int f = ad.factor[sc];
+    if (f == 1) {                      // identity "upsampling": the footprint is the cell itself
+      if (sub == 0) acc = fmaf(-gs, rescale ? qp[i * W + j] : 0.f, gp[i * W + j]);
+    } else if (f > 1) {
+      // Even integer factor: the footprint is rows f*i - f/2 .. f*i + 3f/2 - 1 (same for columns) with the tent weights
+      // (t + .5)/f, t < f, and (2f - t - .5)/f above; pixels clamped onto the first / last map row carry weight 1.
+      // One footprint column per lane, rows in a loop (4 independent loads per trip).
+      const int half = f >> 1;
+      const float rf = 1.f / (float)f;
+      const int vb = f * i - half, ub = f * j - half;
+      for (int tu = sub; tu < 2 * f; tu += tpc) {
+        const int u = ub + tu;
+        if (u < 0 || u >= W) continue;
+        float wx = tu < f ? ((float)tu + 0.5f) * rf : ((float)(2 * f - tu) - 0.5f) * rf;
+        if ((j == 0 && u < half) || (j == w - 1 && tu >= f)) wx = 1.f;
+        float col = 0.f;
+        const float* gcol = gp + u;
+        const float* qcol = qp + u;
+#pragma unroll 4
+        for (int tv = 0; tv < 2 * f; ++tv) {
+          const int v = vb + tv;
+          if (v < 0 || v >= H) continue;
+          float wy = tv < f ? ((float)tv + 0.5f) * rf : ((float)(2 * f - tv) - 0.5f) * rf;
+          if ((i == 0 && v < half) || (i == h - 1 && tv >= f)) wy = 1.f;
+          float gg = gcol[v * W];
+          if (rescale) gg = fmaf(-gs, qcol[v * W], gg);
+          col = fmaf(wy, gg, col);
+        }
+        acc = fmaf(wx, col, acc);
       }
-      acc = fmaf(wx, col, acc);
+    } else {
+      // generic scale: conservative footprint bounds, exact weights from up_tap
+      for (int u = u_lo + sub; u <= u_hi; u += tpc) {
+        const UpTap tx = up_tap(u, sx, w);
+        const float wx = (tx.i0 == j ? tx.l0 : 0.f) + (tx.i1 == j ? tx.l1 : 0.f);
+        if (wx == 0.f) continue;
+        float col = 0.f;
+        const float* gcol = gp + u;
+        const float* qcol = qp + u;
+        for (int v = v_lo; v <= v_hi; ++v) {
+          const UpTap ty = up_tap(v, sy, h);
+          const float wy = (ty.i0 == i ? ty.l0 : 0.f) + (ty.i1 == i ? ty.l1 : 0.f);
+          float gg = gcol[v * W];
+          if (rescale) gg = fmaf(-gs, qcol[v * W], gg);
+          col = fmaf(wy, gg, col);
+        }
+        acc = fmaf(wx, col, acc);
+      }
     }
   }
   for (int o = tpc >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -563,7 +670,7 @@ extern "C" int sqlx_ms_loss_fwd(const sqlx_ms_desc* d, const float* const* depth
   }
   {
     ProfScope prof("ms_smooth_loss_kernel", st);
-    ms_smooth_loss_kernel<<<dim3(kMsBlocks, B, ns), 256, 0, st>>>(sh, reinterpret_cast<float*>(ws + L.spartial), sums,
+    ms_smooth_loss_kernel<<<dim3(kMsBlocks, B, ns), 256, sizeof(float) * (size_t)ns * B, st>>>(sh, reinterpret_cast<float*>(ws + L.spartial), sums,
                                                                   reinterpret_cast<float*>(ws + L.photo_partial),
                                                                   L.max_ctas, ctas, counters, loss);
     if (int e = check_launch("ms_smooth_loss_kernel")) return e;
@@ -631,17 +738,25 @@ extern "C" int sqlx_ms_loss_bwd(const sqlx_ms_desc* d, const float* const* depth
   {
     MsAdjoint ad;
     long long max_threads = 0;
+    ad.rHW = 1.f / ((float)H * (float)W);
     for (int s = 0; s < SQLX_MAX_SCALES; ++s) {
       ad.q_up[s] = s < ns ? reinterpret_cast<const float*>(ws + L.q_up + L.g_up_stride * s) : nullptr;
-      ad.tpc[s] = 1;
+      ad.log2_tpc[s] = 0;
+      ad.factor[s] = 0;
+      ad.sy[s] = ad.sx[s] = ad.ry[s] = ad.rx[s] = 1.f;
       if (s >= ns) continue;
+      ad.sy[s] = (float)d->h[s] / (float)H; ad.sx[s] = (float)d->w[s] / (float)W;
+      ad.ry[s] = (float)H / (float)d->h[s]; ad.rx[s] = (float)W / (float)d->w[s];
       const int fw = ceil_div(W, d->w[s]);      // footprint columns of a cell ~ 2 * fw (+1)
-      int tpc = 4;
-      while (tpc < 32 && tpc < 2 * fw) tpc <<= 1;
-      ad.tpc[s] = tpc;
-      const long long t = (long long)B * d->h[s] * d->w[s] * tpc;
+      const int fi = H / d->h[s];
+      if (H == fi * d->h[s] && W == fi * d->w[s] && (fi == 1 || (fi & 1) == 0)) ad.factor[s] = fi;
+      int lt = 2;
+      while (lt < 5 && (1 << lt) < 2 * fw) ++lt;
+      ad.log2_tpc[s] = lt;
+      const long long t = ((long long)B * d->h[s] * d->w[s]) << lt;
       if (t > max_threads) max_threads = t;
     }
+    SQLX_REQUIRE(max_threads < (1ll << 31), "depth maps too large for the upsample-adjoint launch");
     ProfScope prof("ms_upsample_adjoint_kernel", st);
     ms_upsample_adjoint_kernel<<<dim3((unsigned)((max_threads + 255) / 256), ns), 256, 0, st>>>(sh, g, ad, rescale, g_stats);
     if (int e = check_launch("ms_upsample_adjoint_kernel")) return e;

@@ -216,7 +216,7 @@ struct PhotoFwdParams {
   float* coef;         // optional [B][S][3 ch][3][H][W]: d SSIM / d(mean_x, E[x^2], E[xy])
 };
 
-template <int R, int TH, int TW, int NT>
+template <int R, int TH, int TW, int NT, bool MERGED = false>
 struct Fwd3Cfg {
   static constexpr int PH = TH + 2 * R, PW = TW + 2 * R;
   static constexpr int LD = ((PW + 3) & ~3) + 2;   // even, = 10 mod 32 for a 32-wide tile: conflict-free 8-byte rows
@@ -224,14 +224,15 @@ struct Fwd3Cfg {
   static constexpr int HB = PH * TW;
   static constexpr int PPT = (TH * TW) / NT;
   static constexpr int TS = TH * TW;              // one plane of per-pixel target statistics
-  static constexpr size_t smem_bytes = sizeof(float) * (7 * PLANE + 6 * HB + 6 * TS + 32) +
+  static constexpr int NHB = MERGED ? 9 : 6;       // horizontal-sum planes: all channels at once, or ping-pong
+  static constexpr size_t smem_bytes = sizeof(float) * (7 * PLANE + NHB * HB + 6 * TS + 32) +
                                        sizeof(Camera) * SQLX_MAX_SOURCES + sizeof(int4) * (PH + PW);
   static_assert((TH * TW) % NT == 0 && NT % TW == 0 && NT >= PH + PW, "tile / block shape");
 };
 
-template <int R, int TH, int TW, int NT, int MINB>
+template <int R, int TH, int TW, int NT, int MINB, bool MERGED>
 __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdParams p) {
-  using C = Fwd3Cfg<R, TH, TW, NT>;
+  using C = Fwd3Cfg<R, TH, TW, NT, MERGED>;
   constexpr int PPT = C::PPT;
   constexpr int RR = R > 0 ? R : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
   float* wp = tg + 3 * C::PLANE;        // 3 planes
   float* hbA = wp + 3 * C::PLANE;       // 3 planes of HB
   float* hbB = hbA + 3 * C::HB;         // 3 planes of HB
-  float* tstat = hbB + 3 * C::HB;      // [3 ch][mean, variance + C2][TH*TW]: target statistics of the owned pixels
+  float* tstat = hbA + C::NHB * C::HB; // [3 ch][mean, variance + C2][TH*TW]: target statistics of the owned pixels
   float* red = tstat + 6 * C::TS;
   int4* rowt = reinterpret_cast<int4*>(red + 32);     // [PH]
   int4* colt = rowt + C::PH;                           // [PW]
@@ -341,7 +342,26 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
   // target statistics per channel (mean and variance + C2): written and read back by the owning thread only
   // (shared memory rather than 6*PPT registers that would stay live across the whole source loop)
   float* tsp = tstat + prow0 * TW + pcol;
-  if (R > 0) {
+  if (R > 0 && MERGED) {
+    // all channels in one pass: 6 horizontal planes, one barrier
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      hpass_blocked<RR, C::PH, TW, C::LD, TW, false>(nullptr, tg + c * C::PLANE, hbA + (2 * c) * C::HB,
+                                                     hbA + (2 * c + 1) * C::HB, nullptr);
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float Sy[PPT], Syy[PPT];
+      vsum_multi<R, TW, PPT>(hbA + (2 * c) * C::HB, prow0, pcol, Sy);
+      vsum_multi<R, TW, PPT>(hbA + (2 * c + 1) * C::HB, prow0, pcol, Syy);
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const float m = Sy[k] * ia;
+        tsp[(2 * c) * C::TS + k * TW] = m;
+        tsp[(2 * c + 1) * C::TS + k * TW] = fmaf(-m, m, Syy[k] * ia) + kC2;
+      }
+    }
+  } else if (R > 0) {
     hpass_blocked<RR, C::PH, TW, C::LD, TW, false>(nullptr, tg, hbA, hbA + C::HB, nullptr);
     __syncthreads();
 #pragma unroll
@@ -404,13 +424,20 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
       ssim_acc[k] = 0.f;
     }
     if (R > 0) {
-      hpass_blocked<RR, C::PH, TW, C::LD, TW, true>(wp, tg, hbA, hbA + C::HB, hbA + 2 * C::HB);
+      if (MERGED) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          hpass_blocked<RR, C::PH, TW, C::LD, TW, true>(wp + c * C::PLANE, tg + c * C::PLANE, hbA + (3 * c) * C::HB,
+                                                        hbA + (3 * c + 1) * C::HB, hbA + (3 * c + 2) * C::HB);
+      } else {
+        hpass_blocked<RR, C::PH, TW, C::LD, TW, true>(wp, tg, hbA, hbA + C::HB, hbA + 2 * C::HB);
+      }
       __syncthreads();
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float* cur = (c & 1) ? hbB : hbA;
+        float* cur = MERGED ? hbA + (3 * c) * C::HB : ((c & 1) ? hbB : hbA);
         float* nxt = (c & 1) ? hbA : hbB;
-        if (c < 2)
+        if (!MERGED && c < 2)
           hpass_blocked<RR, C::PH, TW, C::LD, TW, true>(wp + (c + 1) * C::PLANE, tg + (c + 1) * C::PLANE, nxt,
                                                         nxt + C::HB, nxt + 2 * C::HB);
         float Sx[PPT], Sxx[PPT], Sxy[PPT];
@@ -442,7 +469,7 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
             __stcs(cp, gmx); __stcs(cp + plane, gxx); __stcs(cp + 2 * plane, gxy);
           }
         }
-        if (c < 2) __syncthreads();
+        if (!MERGED && c < 2) __syncthreads();
       }
     }
 #pragma unroll
@@ -535,8 +562,8 @@ struct Bwd3Cfg {
   static constexpr int H2 = PH1 * TW;             // one horizontally filtered plane
   static constexpr int PPT = (TH * TW) / NT;
   static constexpr int LRH = TH + 2, LRW = TW + 2;
-  static constexpr int SCR = (3 * H2 > LRH * LRW) ? 3 * H2 : LRH * LRW;
-  static constexpr size_t smem_bytes = sizeof(float) * (3 * CF + SCR + 32 + 16 * SQLX_MAX_SOURCES) +
+  static constexpr int SCR = (9 * H2 > LRH * LRW) ? 9 * H2 : LRH * LRW;
+  static constexpr size_t smem_bytes = sizeof(float) * (9 * CF + SCR + 32 + 16 * SQLX_MAX_SOURCES) +
                                        sizeof(Camera) * SQLX_MAX_SOURCES + PH1 * PW1 + 16;
   static_assert((TH * TW) % NT == 0 && NT % TW == 0, "tile / block shape");
 };
@@ -547,8 +574,8 @@ __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdPara
   constexpr int PPT = C::PPT;
   constexpr int RR = R > 0 ? R : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* cf = reinterpret_cast<float*>(smem_raw);   // 3 planes on the R halo
-  float* h2 = cf + 3 * C::CF;                        // 3 planes PH1 x TW ; later the low-res accumulation scratch
+  float* cf = reinterpret_cast<float*>(smem_raw);   // 9 planes on the R halo (3 channels x 3 coefficients)
+  float* h2 = cf + 9 * C::CF;                        // 9 planes PH1 x TW ; later the low-res accumulation scratch
   float* red = h2 + C::SCR;
   float* dPs = red + 32;                             // [S][16]
   Camera* cams = reinterpret_cast<Camera*>(dPs + 16 * SQLX_MAX_SOURCES);
@@ -636,83 +663,104 @@ __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdPara
     for (int k = 0; k < PPT; ++k) { gix[k] = 0.f; giy[k] = 0.f; }
     const float alpha = (p.d.w_ssim / 3.f) * sel_w * gscale;
     const float wl1 = ((R > 0) ? p.d.w_l1 : 1.f) / 3.f * sel_w * gscale;
+    float gx[3][PPT];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float gx[PPT];
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
         const float diff = Yv[c][k] - Xv[c][k];
         const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
         const bool sel = amin[(prow0 + k + R) * C::PW1 + pcol + R] == sel_idx;
-        gx[k] = sel ? -wl1 * sgn : 0.f;
+        gx[c][k] = sel ? -wl1 * sgn : 0.f;
       }
-      if (R > 0) {
-        const float* cbase = p.coef + ((((size_t)b * S + s) * 3 + c) * 3) * plane;
-        for_region<C::PH1, C::PW1, NT>([&](int lr, int lc, int idx) {
-          float a = 0.f, bb = 0.f, cc = 0.f;
-          if (amin[idx] == sel_idx) {
-            const float* q = cbase + (size_t)(v0 - R + lr) * W + (u0 - R + lc);
-            a = __ldg(q); bb = __ldg(q + plane); cc = __ldg(q + 2 * plane);
-          }
-          const int o = lr * C::LD + lc;
-          cf[o] = a; cf[C::CF + o] = bb; cf[2 * C::CF + o] = cc;
-        });
-        __syncthreads();
-        float sa[PPT], sb[PPT], sc[PPT];
-        if (interior) {
-          hsum_blocked<RR, C::PH1, TW, C::LD, TW>(cf, h2);
-          hsum_blocked<RR, C::PH1, TW, C::LD, TW>(cf + C::CF, h2 + C::H2);
-          hsum_blocked<RR, C::PH1, TW, C::LD, TW>(cf + 2 * C::CF, h2 + 2 * C::H2);
-          __syncthreads();
-          vsum_multi<R, TW, PPT>(h2, prow0, pcol, sa);
-          vsum_multi<R, TW, PPT>(h2 + C::H2, prow0, pcol, sb);
-          vsum_multi<R, TW, PPT>(h2 + 2 * C::H2, prow0, pcol, sc);
+    }
+    if (R > 0) {
+      // all nine coefficient planes (3 channels x {d/d mean, d/d E[x^2], d/d E[xy]}) of this source in ONE staging
+      // pass: nine independent masked loads per halo pixel in flight, two block barriers per source
+      const float* cb9 = p.coef + ((size_t)b * S + s) * 9 * plane;
+      for_region<C::PH1, C::PW1, NT>([&](int lr, int lc, int idx) {
+        float cv[9];
+        if (amin[idx] == sel_idx) {
+          const float* q = cb9 + (size_t)(v0 - R + lr) * W + (u0 - R + lc);
+#pragma unroll
+          for (int m = 0; m < 9; ++m) cv[m] = __ldg(q + (size_t)m * plane);
         } else {
-          // frame-border tiles: adjoint of the reflection padding = per-tap multiplicities
-          for (int idx = threadIdx.x; idx < C::PH1 * TW; idx += NT) {
-            const int lr = idx / TW, pc = idx - lr * TW;
-            const int u = u0 + pc;
-            const float* ca = cf + lr * C::LD + pc;
-            float ta = 0.f, tb = 0.f, tc = 0.f;
-            if (u < W) {
 #pragma unroll
-              for (int k = 0; k <= 2 * R; ++k) {
-                const int qu = u - R + k;
-                if (qu < 0 || qu >= W) continue;
-                const float m = reflect_mult3<R>(u, qu, W);
-                ta += m * ca[k]; tb += m * ca[C::CF + k]; tc += m * ca[2 * C::CF + k];
-              }
-            }
-            h2[idx] = ta; h2[C::H2 + idx] = tb; h2[2 * C::H2 + idx] = tc;
-          }
-          __syncthreads();
-#pragma unroll
-          for (int k = 0; k < PPT; ++k) {
-            const int v = v0 + prow0 + k;
-            const float* ha = h2 + (prow0 + k) * TW + pcol;
-            float ta = 0.f, tb = 0.f, tc = 0.f;
-            if (v < H) {
-#pragma unroll
-              for (int j = 0; j <= 2 * R; ++j) {
-                const int qv = v - R + j;
-                if (qv < 0 || qv >= H) continue;
-                const float m = reflect_mult3<R>(v, qv, H);
-                ta += m * ha[j * TW]; tb += m * ha[C::H2 + j * TW]; tc += m * ha[2 * C::H2 + j * TW];
-              }
-            }
-            sa[k] = ta; sb[k] = tb; sc[k] = tc;
-          }
+          for (int m = 0; m < 9; ++m) cv[m] = 0.f;
         }
+        const int o = lr * C::LD + lc;
 #pragma unroll
-        for (int k = 0; k < PPT; ++k)
-          gx[k] += alpha * ia * (sa[k] + 2.f * Xv[c][k] * sb[k] + Yv[c][k] * sc[k]);
-        // cf is rewritten by the next channel's staging: its readers finished before the barrier above; h2 is
-        // rewritten only after the next staging barrier
+        for (int m = 0; m < 9; ++m) cf[m * C::CF + o] = cv[m];
+      });
+      __syncthreads();
+      if (interior) {
+#pragma unroll
+        for (int m = 0; m < 9; ++m) hsum_blocked<RR, C::PH1, TW, C::LD, TW>(cf + m * C::CF, h2 + m * C::H2);
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float sa[PPT], sb[PPT], sc[PPT];
+          vsum_multi<R, TW, PPT>(h2 + (3 * c) * C::H2, prow0, pcol, sa);
+          vsum_multi<R, TW, PPT>(h2 + (3 * c + 1) * C::H2, prow0, pcol, sb);
+          vsum_multi<R, TW, PPT>(h2 + (3 * c + 2) * C::H2, prow0, pcol, sc);
+#pragma unroll
+          for (int k = 0; k < PPT; ++k)
+            gx[c][k] += alpha * ia * (sa[k] + 2.f * Xv[c][k] * sb[k] + Yv[c][k] * sc[k]);
+        }
+      } else {
+        // frame-border tiles: adjoint of the reflection padding = per-tap multiplicities
+        for (int idx = threadIdx.x; idx < C::PH1 * TW; idx += NT) {
+          const int lr = idx / TW, pc = idx - lr * TW;
+          const int u = u0 + pc;
+          const float* ca = cf + lr * C::LD + pc;
+          float t9[9];
+#pragma unroll
+          for (int m = 0; m < 9; ++m) t9[m] = 0.f;
+          if (u < W) {
+#pragma unroll
+            for (int k = 0; k <= 2 * R; ++k) {
+              const int qu = u - R + k;
+              if (qu < 0 || qu >= W) continue;
+              const float mult = reflect_mult3<R>(u, qu, W);
+#pragma unroll
+              for (int m = 0; m < 9; ++m) t9[m] += mult * ca[m * C::CF + k];
+            }
+          }
+#pragma unroll
+          for (int m = 0; m < 9; ++m) h2[m * C::H2 + idx] = t9[m];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          const int v = v0 + prow0 + k;
+          const float* ha = h2 + (prow0 + k) * TW + pcol;
+          float t9[9];
+#pragma unroll
+          for (int m = 0; m < 9; ++m) t9[m] = 0.f;
+          if (v < H) {
+#pragma unroll
+            for (int j = 0; j <= 2 * R; ++j) {
+              const int qv = v - R + j;
+              if (qv < 0 || qv >= H) continue;
+              const float mult = reflect_mult3<R>(v, qv, H);
+#pragma unroll
+              for (int m = 0; m < 9; ++m) t9[m] += mult * ha[m * C::H2 + j * TW];
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            gx[c][k] += alpha * ia * (t9[3 * c] + 2.f * Xv[c][k] * t9[3 * c + 1] + Yv[c][k] * t9[3 * c + 2]);
+        }
       }
+      // cf is rewritten by the next source's staging: its readers finished before the second barrier; h2 is rewritten
+      // only after the next staging barrier
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
-        gix[k] = fmaf(gx[k], dXx[c][k], gix[k]);
-        giy[k] = fmaf(gx[k], dXy[c][k], giy[k]);
+        gix[k] = fmaf(gx[c][k], dXx[c][k], gix[k]);
+        giy[k] = fmaf(gx[c][k], dXy[c][k], giy[k]);
       }
     }
     float dPacc[16];
@@ -815,17 +863,19 @@ namespace {
 // the others for tuning.
 //   forward : 0 = 32x32 tile, 256 threads (4 px/thread), 2 CTAs/SM     1 = 16x32, 256 (2 px/thread), 3 CTAs/SM
 //             2 = 16x32, 256, 4 CTAs/SM                                3 = 32x32, 512 (2 px/thread), 2 CTAs/SM
+//             4 = configuration 0 with the three channels' horizontal sums in one pass (2 barriers per source)
 //   backward: 0 = 16x32, 256, 3 CTAs/SM    1 = 16x32, 256, 4 CTAs/SM    2 = 32x32, 256 (4 px/thread), 2 CTAs/SM
+//             3 = 16x32, 256, 2 CTAs/SM (no register cap)
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
 constexpr int kMinTH = 16, kMinTW = 32;   // smallest tile of any configuration: sizes the per-CTA partial buffer
 
-template <int R, int TH, int TW, int NT, int MINB>
+template <int R, int TH, int TW, int NT, int MINB, bool MERGED = false>
 int launch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
-  using C = Fwd3Cfg<R, TH, TW, NT>;
-  auto kern = photo_fwd3_kernel<R, TH, TW, NT, MINB>;
+  using C = Fwd3Cfg<R, TH, TW, NT, MERGED>;
+  auto kern = photo_fwd3_kernel<R, TH, TW, NT, MINB, MERGED>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
@@ -845,6 +895,7 @@ int dispatch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
     case 1: return launch_photo_fwd3<R, 16, 32, 256, 3>(p, ctas, st);
     case 2: return launch_photo_fwd3<R, 16, 32, 256, 4>(p, ctas, st);
     case 3: return launch_photo_fwd3<R, 32, 32, 512, 2>(p, ctas, st);
+    case 4: return launch_photo_fwd3<R, 32, 32, 256, 2, true>(p, ctas, st);
     default: return launch_photo_fwd3<R, 32, 32, 256, 2>(p, ctas, st);
   }
 }
@@ -870,6 +921,7 @@ int dispatch_photo_bwd3(const PhotoBwdParams& p, cudaStream_t st) {
   switch (cfg) {
     case 1: return launch_photo_bwd3<R, 16, 32, 256, 4>(p, st);
     case 2: return launch_photo_bwd3<R, 32, 32, 256, 2>(p, st);
+    case 3: return launch_photo_bwd3<R, 16, 32, 256, 2>(p, st);
     default: return launch_photo_bwd3<R, 16, 32, 256, 3>(p, st);
   }
 }

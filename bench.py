@@ -32,7 +32,7 @@ UNIT = "frames/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="sqlx", choices=["sqlx", "reference"])
     ap.add_argument("--batch", type=int, default=12, help="batch per GPU (BASELINE config 2: 12)")
@@ -46,15 +46,18 @@ def parse():
                     help="2 = BASELINE config 2 (default, the bench line); 3 = config 3 shapes: 320x1024, batch 8/GPU, "
                          "3 sources, Q = D = 128, single loss scale (informational)")
     ap.add_argument("--no-graph", action="store_true", help="submit the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--f32-frames", action="store_true",
+                    help="ship the frames as float32 in the end-to-end loop (default: uint8, converted on the device)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     return ap.parse_args()
 
 
 # --------------------------------------------------------------------------------------------- synthetic data
-def make_host_batch(cfg, seed, pin):
+def make_host_batch(cfg, seed, pin, u8_frames=False):
     """Seeded KITTI-shape synthetic batch on the host (SURVEY 8d recipe): smooth frames, KITTI intrinsics,
-    PoseCNN-scale poses, decoder-feature-like x and queries."""
+    PoseCNN-scale poses, decoder-feature-like x and queries.  Frames are quantised to 8 bits (as decoded images
+    are); with u8_frames they stay uint8 on the host and are scaled to [0,1] on the device by HotPath.load."""
     from _cases import smooth_images, kitti_K, depth_like
     g = torch.Generator().manual_seed(seed)
     c = cfg
@@ -77,6 +80,10 @@ def make_host_batch(cfg, seed, pin):
             hb["target%d" % s] = F.interpolate(hb["target"], [c.H // 2 ** s, c.W // 2 ** s], mode="bilinear",
                                                align_corners=False)
     hb = {k: v.contiguous().float() for k, v in hb.items()}
+    for k in list(hb):
+        if k.startswith("target") or k.startswith("source"):
+            q = (hb[k].clamp(0, 1) * 255.0).round()
+            hb[k] = q.to(torch.uint8) if u8_frames else q / 255.0
     if pin:
         hb = {k: v.pin_memory() for k, v in hb.items()}
     return hb
@@ -96,7 +103,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -216,6 +223,10 @@ def algorithmic_bytes(c):
         "sql_tc_pred_kernel": B * (4 * n0 * E + 4 * n0),
         "sql_tc_bwd_reduce_kernel": B * (4 * n0 * E + 4 * n0),
         "sql_tc_bwd_dx_kernel": B * (4 * n0 * E + 4 * n0 + 4 * n0 * E),
+        # mixed-weight decomposition (sql_tc.cu): regression backward reads x + g_pred and writes d_x; the summary-path
+        # backward reads x and accumulates into d_x (read + write)
+        "sql_tc_bwd_pred_kernel": B * (4 * n0 * E + 4 * n0 + 4 * n0 * E),
+        "sql_tc_bwd_sum_kernel": B * (4 * n0 * E + 2 * 4 * n0 * E),
     }
 
 
@@ -268,7 +279,7 @@ def main():
     if world > 1:   # identical initial weights on every rank
         for p in hp.parameters():
             dist.broadcast(p.data, 0)
-    hb = make_host_batch(cfg, seed=1234 + rank, pin=True)
+    hb = make_host_batch(cfg, seed=1234 + rank, pin=True, u8_frames=not args.f32_frames)
     h2d_bytes = hp.load(hb, non_blocking=False, slot=0)
     hp.load(hb, non_blocking=False, slot=1)
     torch.cuda.synchronize()
@@ -371,7 +382,8 @@ def main():
 
     # per-kernel device times: the same steps submitted eagerly with CUDA events around each main kernel
     _lib.profile_enable(True)
-    for _ in range(min(args.steps, 20)):
+    nprof = min(args.steps, 20)
+    for _ in range(nprof):
         hp.step_eager()
     torch.cuda.synchronize()
     prof = _lib.profile_report()
@@ -393,7 +405,11 @@ def main():
     traffic = {}
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
-        traffic = {k: v["dram_bytes_per_launch"] for k, v in tj["kernels"].items()}
+        for k, v in tj["kernels"].items():     # ncu names -> the names of the library's profile hooks
+            k = k.replace("void ", "").split("<")[0].split("::")[-1]
+            k = {"photo_fwd3_kernel": "photo_fwd_kernel", "photo_bwd3_kernel": "photo_bwd_kernel",
+                 "sql_tc_pred2_kernel": "sql_tc_pred_kernel"}.get(k, k)
+            traffic[k] = v["dram_bytes_per_launch"]
     except Exception:
         pass
     cand = {k: v for k, v in prof.items() if k in ab}
@@ -409,9 +425,9 @@ def main():
                     "timing": "CUDA events around each launch on the launching stream (eager submission of the same "
                               "steps after the timed region); traffic = dram bytes/launch from the committed ncu "
                               "capture profiles/traffic_latest.json"}
-    step_ms_kernels = sum(v[1] for v in prof.values()) / max(1, min(args.steps, 20))
-    kernels = {k: {"launches_per_step": v[0] / max(1, min(args.steps, 20)),
-                   "ms_per_step": v[1] / max(1, min(args.steps, 20)),
+    step_ms_kernels = sum(v[1] for v in prof.values()) / max(1, nprof)
+    kernels = {k: {"launches_per_step": v[0] / max(1, nprof),
+                   "ms_per_step": v[1] / max(1, nprof),
                    "hbm_frac": (ab[k] / (v[1] / v[0] * 1e-3) / 1e9 / peak) if k in ab else None}
                for k, v in sorted(prof.items())}
 
@@ -420,12 +436,13 @@ def main():
         cpu = time_cpu(cfg, args, steps=3, warmup=1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
-    total_bytes = sum(v.numel() * 4 for v in hb.values())
+    total_bytes = sum(v.numel() * 4 for v in hb.values())   # device-resident footprint (frames are fp32 on the device)
     config["l2"] = ("no explicit flush: every step streams %.0f MB of inputs plus %.0f MB of gradients through a 126 MB L2"
                     % (total_bytes / 1e6, (hb["x"].numel() * 4) / 1e6))
     config["submission"] = "eager" if args.no_graph else "cuda_graph"
     config["e2e_pipeline"] = ("H2D of batch i+1 on a copy stream overlaps the step on batch i (2 device input sets); "
-                              "tie-break noise drawn on the device instead of copied from the host")
+                              "tie-break noise drawn on the device instead of copied from the host; frames shipped as %s"
+                              % ("float32" if args.f32_frames else "uint8 and scaled to [0,1] on the device"))
     line = {"metric": METRIC, "value": cfg.B * world / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,

@@ -208,6 +208,17 @@ int sqlx_ms_loss_bwd(const sqlx_ms_desc* desc, const float* const* depth_lr, con
                      float* const* d_depth_lr, float* const* d_axisangle, float* const* d_translation, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* ---- Supervised fine-tuning loss: finetune/loss.py:29-42 SILogLoss.forward with the
+ * align_corners=True bilinear resize (train_ft_SQLdepth.py:235) and the boolean-mask gather fused into one pass.
+ *   pred [B,1,h,w]; gt [B,1,H,W]; mask [B,1,H,W] u8 (torch.bool storage) or NULL; loss [1]; saved [4] floats
+ *   (mean, count, Dg, loss) carried to the backward; d_pred [B,1,h,w] overwritten. */
+size_t sqlx_silog_workspace_bytes(void);
+int sqlx_silog_fwd(const float* pred, const float* gt, const uint8_t* mask, int B, int h, int w, int H, int W,
+                   float variance_focus, float* loss, float* saved, void* workspace, size_t workspace_bytes,
+                   void* stream);
+int sqlx_silog_bwd(const float* pred, const float* gt, const uint8_t* mask, int B, int h, int w, int H, int W,
+                   float variance_focus, const float* saved, const float* g_loss, float* d_pred, void* stream);
+
 /* Module-level geometry drop-ins (the fused path above never materialises these tensors).
  * BackprojectDepth.forward (layers.py:210-215): depth [B,1,H,W], inv_K [B,4,4] -> points [B,4,H*W] (row 3 = 1). */
 int sqlx_backproject_fwd(const float* depth, const float* inv_K, int B, int H, int W, float* points, void* stream);

@@ -91,6 +91,11 @@ _PROTOS = {
                                  ctypes.POINTER(c_void_p), c_void_p, c_void_p, ctypes.POINTER(PoseInputs),
                                  ctypes.POINTER(c_void_p), c_void_p, c_void_p, ctypes.POINTER(c_void_p),
                                  ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_void_p, c_size_t, c_void_p]),
+    "sqlx_silog_workspace_bytes": (c_size_t, []),
+    "sqlx_silog_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                               c_void_p, c_size_t, c_void_p]),
+    "sqlx_silog_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
     "sqlx_backproject_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sqlx_backproject_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sqlx_project_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),

@@ -77,12 +77,16 @@ class HotPath(torch.nn.Module):
     # ------------------------------------------------------------------ data
     def load(self, host_batch, non_blocking=True, slot=0):
         """host_batch: {name: CPU tensor (pinned for async copies)} -> device input set `slot` on the current
-        stream; returns the bytes copied."""
+        stream; returns the bytes copied.  Frames may be shipped as uint8 (what the dataset decodes to): they cross
+        PCIe at one byte per channel and are scaled to [0,1] floats on the device -- the reference does the same
+        conversion (transforms.ToTensor) on the host and ships four bytes per channel."""
         n = 0
         inp = self.slots[slot]
         with torch.no_grad():
             for k, v in host_batch.items():
                 inp[k].copy_(v, non_blocking=non_blocking)
+                if v.dtype == torch.uint8:
+                    inp[k].mul_(1.0 / 255.0)
                 n += v.numel() * v.element_size()
         return n
 

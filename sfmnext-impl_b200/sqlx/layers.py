@@ -142,3 +142,57 @@ def get_smooth_loss(disp, img):
     B = disp.shape[0]
     H, W = img.shape[-2:]
     return sums[:, 0].sum() / float(B * H * (W - 1)) + sums[:, 1].sum() / float(B * (H - 1) * W)
+
+
+class _SILogFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, mask, variance_focus):
+        require_cuda(pred, target)
+        p, t = _f32c(pred), _f32c(target)
+        if p.dim() != 4 or t.dim() != 4 or p.shape[:2] != t.shape[:2]:
+            raise RuntimeError("SILogLoss expects input [B,C,h,w] and target [B,C,H,W]")
+        B, C, h, w = p.shape
+        H, W = t.shape[-2:]
+        m = None
+        if mask is not None:
+            if mask.shape != t.shape:
+                raise RuntimeError("SILogLoss mask must have the target's shape")
+            m = mask.contiguous()
+            m = m.view(torch.uint8) if m.dtype == torch.bool else (m != 0).view(torch.uint8)
+        loss = torch.empty(1, device=p.device, dtype=torch.float32)
+        saved = torch.empty(4, device=p.device, dtype=torch.float32)
+        nws = lib().sqlx_silog_workspace_bytes()
+        ws = torch.empty(nws, device=p.device, dtype=torch.uint8)
+        check(lib().sqlx_silog_fwd(ptr(p), ptr(t), ptr(m), B * C, h, w, H, W, float(variance_focus), ptr(loss), ptr(saved),
+                                   ptr(ws), nws, stream_ptr()), "sqlx_silog_fwd")
+        ctx.save_for_backward(p, t, saved, *([m] if m is not None else []))
+        ctx.vf = float(variance_focus)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        p, t, saved, *rest = ctx.saved_tensors
+        m = rest[0] if rest else None
+        B, C, h, w = p.shape
+        H, W = t.shape[-2:]
+        d = torch.empty_like(p)
+        gl = g.contiguous().float().reshape(1)
+        check(lib().sqlx_silog_bwd(ptr(p), ptr(t), ptr(m), B * C, h, w, H, W, ctx.vf, ptr(saved), ptr(gl), ptr(d),
+                                   stream_ptr()), "sqlx_silog_bwd")
+        return d, None, None, None
+
+
+class SILogLoss(torch.nn.Module):
+    """Drop-in for finetune/loss.py:24-42 (the cfg-5 metric-depth fine-tuning loss): same constructor, attribute
+    `name` and forward(input, target, mask=None, interpolate=True) -> scalar.  The align_corners=True resize, the
+    mask gather and both reductions run in one kernel."""
+
+    def __init__(self, variance_focus=0.15):
+        super().__init__()
+        self.name = "SILog"
+        self.variance_focus = variance_focus
+
+    def forward(self, input, target, mask=None, interpolate=True):
+        if not interpolate and input.shape[-2:] != target.shape[-2:]:
+            raise RuntimeError("The size of tensor a must match the size of tensor b")   # what the reference raises
+        return _SILogFn.apply(input, target, mask, self.variance_focus)

@@ -84,3 +84,35 @@ def test_ssim_3x3_variant():
     out = sqlx.SSIM(radius=1)(x.cuda(), y.cuda())
     ref = O.ssim(x.double(), y.double(), radius=1)
     assert float((out.cpu().double() - ref).abs().max()) < 1e-4
+
+
+def test_silog_golden_and_oracle():
+    """finetune/loss.py:SILogLoss: forward value and gradient against the reference-generated fixture, and against the
+    float64 oracle on fresh inputs (all-valid mask, no mask, interpolate=False)."""
+    import sqlx
+    from oracle import sqldepth_oracle as O
+    z = load_npz("modules")
+    pred = torch.from_numpy(z["silog_pred"]).cuda().requires_grad_(True)
+    gt = torch.from_numpy(z["silog_gt"]).cuda()
+    mask = gt > 1e-3
+    crit = sqlx.SILogLoss()
+    loss = crit(pred, gt, mask=mask, interpolate=True)
+    assert abs(float(loss) - float(z["out_silog"])) < 1e-4 * max(1.0, abs(float(z["out_silog"])))
+    (g,) = torch.autograd.grad(loss, pred)
+    ref = torch.from_numpy(z["grad_silog"])
+    assert float((g.cpu() - ref).abs().max() / ref.abs().max()) < 1e-3
+    # fresh inputs vs the float64 oracle
+    gen = torch.Generator().manual_seed(7)
+    for shape_lr, shape_hr, use_mask in [((2, 1, 24, 40), (2, 1, 48, 80), True), ((1, 1, 30, 50), (1, 1, 30, 50), False),
+                                         ((2, 1, 17, 23), (2, 1, 50, 70), True)]:
+        p = (0.5 + 5 * torch.rand(shape_lr, generator=gen))
+        t = (0.5 + 5 * torch.rand(shape_hr, generator=gen))
+        m = (torch.rand(shape_hr, generator=gen) > 0.3) if use_mask else None
+        pd = p.double().requires_grad_(True)
+        lo = O.silog_loss(pd, t.double(), mask=m, interpolate=True)
+        (go,) = torch.autograd.grad(lo, pd)
+        pc = p.cuda().requires_grad_(True)
+        lc = crit(pc, t.cuda(), mask=None if m is None else m.cuda(), interpolate=True)
+        (gc,) = torch.autograd.grad(lc, pc)
+        assert abs(float(lc) - float(lo)) < 1e-4 * max(1.0, abs(float(lo)))
+        assert float((gc.cpu().double() - go).abs().max() / go.abs().max()) < 1e-3

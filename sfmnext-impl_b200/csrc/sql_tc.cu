@@ -216,29 +216,39 @@ __device__ __forceinline__ void issue_z(const Smem& s, uint32_t tm_z, uint32_t t
 
 // softmax over the Dp logits of this thread's pixel (TMEM lane) and expected bin centre, one pass (online max)
 __device__ __forceinline__ float softmax_expect(const Smem& s, uint32_t lane_base, uint32_t tm_z, int Dp) {
-  float m = -INFINITY, se = 0.f, sc = 0.f;
+  // four independent accumulation chains (the kernels run 4-12 warps per SM: a single dependent add / fma chain per
+  // thread leaves the issue slots idle), bias and centres fetched as 128-bit shared loads
+  float m = -INFINITY, se[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float4* bias4 = reinterpret_cast<const float4*>(s.bias);
+  const float4* cen4 = reinterpret_cast<const float4*>(s.cen);
   for (int c = 0; c < Dp; c += 16) {
     float v[16];
     tmem_ld16(lane_base + tm_z + c, v);
     tmem_wait_ld();
-    float cm = -INFINITY;
+    float cmx[4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      v[i] += s.bias[c + i];
-      cm = fmaxf(cm, v[i]);
+    for (int j = 0; j < 4; ++j) {
+      const float4 bq = bias4[(c >> 2) + j];
+      v[4 * j] += bq.x; v[4 * j + 1] += bq.y; v[4 * j + 2] += bq.z; v[4 * j + 3] += bq.w;
+      cmx[j] = fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), fmaxf(v[4 * j + 2], v[4 * j + 3]));
     }
+    const float cm = fmaxf(fmaxf(cmx[0], cmx[1]), fmaxf(cmx[2], cmx[3]));
     if (cm > m) {
       const float r = __expf(m - cm);
-      se *= r; sc *= r; m = cm;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { se[j] *= r; sc[j] *= r; }
+      m = cm;
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float e = __expf(v[i] - m);
-      se += e;
-      sc = fmaf(e, s.cen[c + i], sc);
+    for (int j = 0; j < 4; ++j) {
+      const float4 cq = cen4[(c >> 2) + j];
+      const float e0 = __expf(v[4 * j] - m), e1 = __expf(v[4 * j + 1] - m);
+      const float e2 = __expf(v[4 * j + 2] - m), e3 = __expf(v[4 * j + 3] - m);
+      se[j] += (e0 + e1) + (e2 + e3);
+      sc[j] += fmaf(e0, cq.x, e1 * cq.y) + fmaf(e2, cq.z, e3 * cq.w);
     }
   }
-  return sc / se;
+  return ((sc[0] + sc[1]) + (sc[2] + sc[3])) / ((se[0] + se[1]) + (se[2] + se[3]));
 }
 
 // ------------------------------------------------------------------------------------------------

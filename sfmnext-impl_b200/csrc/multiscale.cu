@@ -20,7 +20,7 @@
 
 namespace sqlx {
 
-constexpr int kMsBlocks = 32;   // blocks per (scale, sample) of the batched reduction kernels
+constexpr int kMsBlocks = 96;   // blocks per (scale, sample) of the batched reduction kernels
 
 struct MsShapes {
   int ns, B, S, H, W;
@@ -188,7 +188,7 @@ __device__ __forceinline__ float absdiff_mean3(const float* __restrict__ col, si
 __global__ void ms_smooth_loss_kernel(MsShapes sh, float* __restrict__ spartial, float* __restrict__ sums,
                                       const float* __restrict__ photo_partial, int max_ctas, int ctas,
                                       unsigned int* __restrict__ counter, float* __restrict__ loss) {
-  __shared__ float red[32];
+  __shared__ float red3[3][32];
   __shared__ double dred[256];
   __shared__ float lsum[SQLX_MAX_SCALES];
   extern __shared__ float sterm[];        // [ns * B]
@@ -218,9 +218,16 @@ __global__ void ms_smooth_loss_kernel(MsShapes sh, float* __restrict__ spartial,
         }
       }
     }
-    const float t0 = block_sum(s0, red);
-    const float t1 = block_sum(s1, red);
-    const float t2 = block_sum(s2, red);
+    // one shared stage for the three sums (two barriers instead of six)
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if ((threadIdx.x & 31) == 0) {
+      red3[0][threadIdx.x >> 5] = s0; red3[1][threadIdx.x >> 5] = s1; red3[2][threadIdx.x >> 5] = s2;
+    }
+    __syncthreads();
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { t0 += red3[0][i]; t1 += red3[1][i]; t2 += red3[2][i]; }
+    }
     if (threadIdx.x == 0) {
       float* o = spartial + (((size_t)sc * B + b) * kMsBlocks + blockIdx.x) * 3;
       o[0] = t0; o[1] = t1; o[2] = t2;
@@ -419,6 +426,45 @@ struct MsAdjoint {
   float rHW;
 };
 
+// Even integer factor F, TPC lanes per cell: lane `sub` takes footprint columns sub, sub + TPC, ...; all trip counts
+// are compile-time so the loads of a column are issued together.
+template <int F, int TPC>
+__device__ __forceinline__ float adjoint_even(const float* __restrict__ gp, const float* __restrict__ qp, int i, int j,
+                                              int h, int w, int H, int W, int sub, float gs, bool rescale) {
+  constexpr int half = F / 2;
+  constexpr float rf = 1.f / (float)F;
+  const int vb = F * i - half, ub = F * j - half;
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 2 * F / TPC; ++c) {
+    const int tu = sub + c * TPC;
+    const int u = ub + tu;
+    if (u < 0 || u >= W) continue;
+    float wx = tu < F ? ((float)tu + 0.5f) * rf : ((float)(2 * F - tu) - 0.5f) * rf;
+    if ((j == 0 && u < half) || (j == w - 1 && tu >= F)) wx = 1.f;
+    const float* gcol = gp + u;
+    const float* qcol = qp + u;
+    float gv[2 * F], qv[2 * F];
+#pragma unroll
+    for (int tv = 0; tv < 2 * F; ++tv) {
+      const int v = vb + tv;
+      const bool in = v >= 0 && v < H;
+      gv[tv] = in ? gcol[v * W] : 0.f;
+      qv[tv] = (in && rescale) ? qcol[v * W] : 0.f;
+    }
+    float col = 0.f;
+#pragma unroll
+    for (int tv = 0; tv < 2 * F; ++tv) {
+      const int v = vb + tv;
+      float wy = tv < F ? ((float)tv + 0.5f) * rf : ((float)(2 * F - tv) - 0.5f) * rf;
+      if ((i == 0 && v < half) || (i == h - 1 && tv >= F)) wy = 1.f;
+      col = fmaf(wy, fmaf(-gs, qv[tv], gv[tv]), col);
+    }
+    acc = fmaf(wx, col, acc);
+  }
+  return acc;
+}
+
 __global__ void ms_upsample_adjoint_kernel(MsShapes sh, MsGrads g, MsAdjoint ad, int rescale,
                                            const float* __restrict__ g_stats) {
   const int sc = blockIdx.y;
@@ -435,23 +481,24 @@ __global__ void ms_upsample_adjoint_kernel(MsShapes sh, MsGrads g, MsAdjoint ad,
     const unsigned hw = (unsigned)h * w;
     const int b = (int)(cell / hw), rem = (int)(cell - (unsigned)b * hw);
     const int i = rem / w, j = rem - i * w;
-    const float sy = ad.sy[sc], sx = ad.sx[sc], ry = ad.ry[sc], rx = ad.rx[sc];   // h/H, w/W, H/h, W/w
-    // rows whose source coordinate sy*(v+.5)-.5 lies in [i-1, i+1): a margin keeps the bounds conservative, the
-    // weights themselves are exact (rows outside the true footprint evaluate to weight 0)
-    const int v_lo = max(0, (int)ceilf(((float)i - 0.5f) * ry - 0.5f - 1e-3f));
-    const int v_hi = min(H - 1, (int)ceilf(((float)i + 1.5f) * ry - 0.5f + 1e-3f));
-    const int u_lo = max(0, (int)ceilf(((float)j - 0.5f) * rx - 0.5f - 1e-3f));
-    const int u_hi = min(W - 1, (int)ceilf(((float)j + 1.5f) * rx - 0.5f + 1e-3f));
     const float* gp = g.g_up[sc] + (size_t)b * H * W;
     const float* qp = ad.q_up[sc] + (size_t)b * H * W;
     const float gs = rescale ? g_stats[sc * B + b] * ad.rHW : 0.f;
     const int f = ad.factor[sc];
     if (f == 1) {                      // identity "upsampling": the footprint is the cell itself
       if (sub == 0) acc = fmaf(-gs, rescale ? qp[i * W + j] : 0.f, gp[i * W + j]);
+    } else if (f == 2) {       // lanes per cell fixed by the host: 1, 2, 8, 32 for factors 2, 4, 8, 16
+      acc = adjoint_even<2, 1>(gp, qp, i, j, h, w, H, W, sub, gs, rescale);
+    } else if (f == 4) {
+      acc = adjoint_even<4, 2>(gp, qp, i, j, h, w, H, W, sub, gs, rescale);
+    } else if (f == 8) {
+      acc = adjoint_even<8, 8>(gp, qp, i, j, h, w, H, W, sub, gs, rescale);
+    } else if (f == 16) {
+      acc = adjoint_even<16, 32>(gp, qp, i, j, h, w, H, W, sub, gs, rescale);
     } else if (f > 1) {
       // Even integer factor: the footprint is rows f*i - f/2 .. f*i + 3f/2 - 1 (same for columns) with the tent weights
       // (t + .5)/f, t < f, and (2f - t - .5)/f above; pixels clamped onto the first / last map row carry weight 1.
-      // One footprint column per lane, rows in a loop (4 independent loads per trip).
+      // One footprint column per lane, rows in a loop.
       const int half = f >> 1;
       const float rf = 1.f / (float)f;
       const int vb = f * i - half, ub = f * j - half;
@@ -476,7 +523,13 @@ __global__ void ms_upsample_adjoint_kernel(MsShapes sh, MsGrads g, MsAdjoint ad,
         acc = fmaf(wx, col, acc);
       }
     } else {
-      // generic scale: conservative footprint bounds, exact weights from up_tap
+      // generic scale: conservative footprint bounds (rows whose source coordinate sy*(v+.5)-.5 lies in [i-1, i+1),
+      // with a margin), exact weights from up_tap (rows outside the true footprint evaluate to weight 0)
+      const float sy = ad.sy[sc], sx = ad.sx[sc], ry = ad.ry[sc], rx = ad.rx[sc];   // h/H, w/W, H/h, W/w
+      const int v_lo = max(0, (int)ceilf(((float)i - 0.5f) * ry - 0.5f - 1e-3f));
+      const int v_hi = min(H - 1, (int)ceilf(((float)i + 1.5f) * ry - 0.5f + 1e-3f));
+      const int u_lo = max(0, (int)ceilf(((float)j - 0.5f) * rx - 0.5f - 1e-3f));
+      const int u_hi = min(W - 1, (int)ceilf(((float)j + 1.5f) * rx - 0.5f + 1e-3f));
       for (int u = u_lo + sub; u <= u_hi; u += tpc) {
         const UpTap tx = up_tap(u, sx, w);
         const float wx = (tx.i0 == j ? tx.l0 : 0.f) + (tx.i1 == j ? tx.l1 : 0.f);
@@ -752,6 +805,10 @@ extern "C" int sqlx_ms_loss_bwd(const sqlx_ms_desc* d, const float* const* depth
       if (H == fi * d->h[s] && W == fi * d->w[s] && (fi == 1 || (fi & 1) == 0)) ad.factor[s] = fi;
       int lt = 2;
       while (lt < 5 && (1 << lt) < 2 * fw) ++lt;
+      if (ad.factor[s] == 1 || ad.factor[s] == 2) lt = 0;      // must match the adjoint_even<F, TPC> instantiations
+      else if (ad.factor[s] == 4) lt = 1;
+      else if (ad.factor[s] == 8) lt = 3;
+      else if (ad.factor[s] == 16) lt = 5;
       ad.log2_tpc[s] = lt;
       const long long t = ((long long)B * d->h[s] * d->w[s]) << lt;
       if (t > max_threads) max_threads = t;

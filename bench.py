@@ -214,6 +214,8 @@ def algorithmic_bytes(c):
         # depth_lr + target + S sources + argmin (reads); d_depth_lr (write)
         "photo_bwd_kernel": B * (4 * n_avg + 12 * N + 12 * N * S + N + 4 * n_avg),
         "reproj_loss_kernel": B * (24 * N + 4 * N),
+        # identity losses of all S sources in one launch: target once, every source once, S loss maps out
+        "identity_loss_kernel": B * (12 * N + 12 * N * S + 4 * N * S),
         "sql_summary_kernel": B * 4 * n0 * E,
         "sql_pred_kernel": B * (4 * n0 * E + 4 * n0),
         "sql_bwd_reduce_kernel": B * (4 * n0 * E + 4 * n0),

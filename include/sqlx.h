@@ -219,6 +219,12 @@ int sqlx_silog_fwd(const float* pred, const float* gt, const uint8_t* mask, int 
 int sqlx_silog_bwd(const float* pred, const float* gt, const uint8_t* mask, int B, int h, int w, int H, int W,
                    float variance_focus, const float* saved, const float* g_loss, float* d_pred, void* stream);
 
+/* ---- Evaluation: flip test-time-augmentation blend, evaluate_depth_config.py:51-59
+ * (batch_post_process_disparity) fused with the un-flip of the second pass (:157).  l_disp, r_disp, out [N,h,w];
+ * r_is_flipped = 1 when r_disp still is in the mirrored frame (as the network returned it). */
+int sqlx_postprocess_disparity(const float* l_disp, const float* r_disp, int N, int h, int w, int r_is_flipped,
+                               float* out, void* stream);
+
 /* Module-level geometry drop-ins (the fused path above never materialises these tensors).
  * BackprojectDepth.forward (layers.py:210-215): depth [B,1,H,W], inv_K [B,4,4] -> points [B,4,H*W] (row 3 = 1). */
 int sqlx_backproject_fwd(const float* depth, const float* inv_K, int B, int H, int W, float* points, void* stream);

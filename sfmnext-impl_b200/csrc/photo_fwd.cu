@@ -242,27 +242,6 @@ extern "C" int sqlx_reprojection_loss_fwd(const float* pred, const float* target
   return launch_reproj<0, false>(pred, target, B, 3, H, W, w_ssim, w_l1, out, st);
 }
 
-extern "C" int sqlx_identity_losses_fwd(const float* target, const float* const* sources, int S, int B, int H, int W,
-                                        int ssim_radius, float w_ssim, float w_l1, int no_ssim, float* identity,
-                                        void* stream) {
-  SQLX_REQUIRE(target && sources && identity, "NULL pointer argument");
-  SQLX_REQUIRE(S >= 1 && S <= SQLX_MAX_SOURCES && B > 0 && H > 0 && W > 0, "bad shape");
-  const int r = no_ssim ? 0 : ssim_radius;
-  SQLX_REQUIRE(r == 0 || r == 1 || r == 3, "ssim_radius must be 1 or 3");
-  SQLX_REQUIRE(H > 2 * r && W > 2 * r, "image smaller than the SSIM window");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const size_t plane = (size_t)H * W;
-  for (int s = 0; s < S; ++s) {
-    SQLX_REQUIRE(sources[s], "source %d is NULL", s);
-    float* out = identity + (size_t)s * plane;
-    int e = r == 3 ? launch_reproj<3, false>(sources[s], target, B, 3, H, W, w_ssim, w_l1, out, st, (size_t)S * plane)
-          : r == 1 ? launch_reproj<1, false>(sources[s], target, B, 3, H, W, w_ssim, w_l1, out, st, (size_t)S * plane)
-                   : launch_reproj<0, false>(sources[s], target, B, 3, H, W, w_ssim, w_l1, out, st, (size_t)S * plane);
-    if (e) return e;
-  }
-  return SQLX_OK;
-}
-
 extern "C" int sqlx_ssim_fwd(const float* x, const float* y, int B, int C, int H, int W, int ssim_radius, float* out,
                              void* stream) {
   SQLX_REQUIRE(x && y && out, "NULL pointer argument");

@@ -507,6 +507,137 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
   if (threadIdx.x == 0) p.partial[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
 }
 
+// ------------------------------------------------------------------------------------------------
+// identity (auto-mask) losses of every source in one launch: compute_reprojection_loss(source_f, target) for all f
+// (trainer.py:480-493).  Same tile machinery as the fused forward without the warp: the target tile and its box
+// statistics are staged / computed once per CTA and shared by the S sources.
+// ------------------------------------------------------------------------------------------------
+struct IdentParams {
+  int B, H, W, S;
+  float w_ssim, w_l1;
+  const float* target;                    // [B,3,H,W]
+  const float* src[SQLX_MAX_SOURCES];     // planar [B,3,H,W]
+  float* out;                             // [B,S,H,W]
+};
+
+template <int R, int TH, int TW, int NT>
+struct Ident3Cfg {
+  static constexpr int PH = TH + 2 * R, PW = TW + 2 * R;
+  static constexpr int LD = ((PW + 3) & ~3) + 2;
+  static constexpr int PLANE = PH * LD;
+  static constexpr int HB = PH * TW;
+  static constexpr int PPT = (TH * TW) / NT;
+  static constexpr int TS = TH * TW;
+  static constexpr size_t smem_bytes = sizeof(float) * (6 * PLANE + 9 * HB + 6 * TS) + sizeof(int4) * (PH + PW);
+  static_assert((TH * TW) % NT == 0 && NT % TW == 0 && NT >= PH + PW, "tile / block shape");
+};
+
+template <int R, int TH, int TW, int NT>
+__global__ void __launch_bounds__(NT, 2) identity3_kernel(const IdentParams p) {
+  using C = Ident3Cfg<R, TH, TW, NT>;
+  constexpr int PPT = C::PPT;
+  constexpr int RR = R > 0 ? R : 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* tg = reinterpret_cast<float*>(smem_raw);   // 3 planes
+  float* wp = tg + 3 * C::PLANE;                    // 3 planes
+  float* hb = wp + 3 * C::PLANE;                    // 9 planes of HB
+  float* tstat = hb + 9 * C::HB;                    // [3 ch][mean, variance + C2][TH*TW]
+  int4* rowt = reinterpret_cast<int4*>(tstat + 6 * C::TS);
+  int4* colt = rowt + C::PH;
+  const int H = p.H, W = p.W, S = p.S;
+  const int b = blockIdx.z;
+  const int v0 = blockIdx.y * TH, u0 = blockIdx.x * TW;
+  const size_t plane = (size_t)H * W;
+  constexpr float ia = 1.f / (float)((2 * R + 1) * (2 * R + 1));
+  fill_axis_table<C::PH>(rowt, v0 - R, H, H, 1.f, 0, 0);
+  fill_axis_table<C::PW>(colt, u0 - R, W, W, 1.f, 0, C::PH);
+  __syncthreads();
+  auto stage3 = [&](const float* __restrict__ img, float* __restrict__ dst) {
+    float tv[2][3];
+    for_region2<C::PH, C::PW, NT>(
+        [&](int j, int lr, int lc, bool live) {
+          if (live) {
+            const float* tp = img + (size_t)(rowt[lr].w * W + colt[lc].w);
+            tv[j][0] = __ldg(tp); tv[j][1] = __ldg(tp + plane); tv[j][2] = __ldg(tp + 2 * plane);
+          }
+        },
+        [&](int j, int lr, int lc) {
+          const int o = lr * C::LD + lc;
+          dst[o] = tv[j][0]; dst[C::PLANE + o] = tv[j][1]; dst[2 * C::PLANE + o] = tv[j][2];
+        });
+  };
+  stage3(p.target + (size_t)b * 3 * plane, tg);
+  __syncthreads();
+  const int pcol = threadIdx.x % TW;
+  const int prow0 = (threadIdx.x / TW) * PPT;
+  const bool col_in = u0 + pcol < W;
+  const size_t pix0 = (size_t)(v0 + prow0) * W + (u0 + pcol);
+  float* tsp = tstat + prow0 * TW + pcol;
+  if (R > 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      hpass_blocked<RR, C::PH, TW, C::LD, TW, false>(nullptr, tg + c * C::PLANE, hb + (2 * c) * C::HB,
+                                                     hb + (2 * c + 1) * C::HB, nullptr);
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float Sy[PPT], Syy[PPT];
+      vsum_multi<R, TW, PPT>(hb + (2 * c) * C::HB, prow0, pcol, Sy);
+      vsum_multi<R, TW, PPT>(hb + (2 * c + 1) * C::HB, prow0, pcol, Syy);
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const float m = Sy[k] * ia;
+        tsp[(2 * c) * C::TS + k * TW] = m;
+        tsp[(2 * c + 1) * C::TS + k * TW] = fmaf(-m, m, Syy[k] * ia) + kC2;
+      }
+    }
+  }
+  for (int s = 0; s < S; ++s) {
+    stage3(p.src[s] + (size_t)b * 3 * plane, wp);     // (wp / hb readers of the previous source are past its barriers)
+    __syncthreads();
+    float ssim_acc[PPT], l1_acc[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const int o = (prow0 + k + R) * C::LD + pcol + R;
+      l1_acc[k] = fabsf(tg[o] - wp[o]) + fabsf(tg[C::PLANE + o] - wp[C::PLANE + o]) +
+                  fabsf(tg[2 * C::PLANE + o] - wp[2 * C::PLANE + o]);
+      ssim_acc[k] = 0.f;
+    }
+    if (R > 0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        hpass_blocked<RR, C::PH, TW, C::LD, TW, true>(wp + c * C::PLANE, tg + c * C::PLANE, hb + (3 * c) * C::HB,
+                                                      hb + (3 * c + 1) * C::HB, hb + (3 * c + 2) * C::HB);
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float Sx[PPT], Sxx[PPT], Sxy[PPT];
+        vsum_multi<R, TW, PPT>(hb + (3 * c) * C::HB, prow0, pcol, Sx);
+        vsum_multi<R, TW, PPT>(hb + (3 * c + 1) * C::HB, prow0, pcol, Sxx);
+        vsum_multi<R, TW, PPT>(hb + (3 * c + 2) * C::HB, prow0, pcol, Sxy);
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          const float mx = Sx[k] * ia, myk = tsp[(2 * c) * C::TS + k * TW];
+          const float sxx = fmaf(-mx, mx, Sxx[k] * ia);
+          const float sxy = fmaf(-mx, myk, Sxy[k] * ia);
+          const float n1 = fmaf(2.f * mx, myk, kC1), n2 = fmaf(2.f, sxy, kC2);
+          const float d1 = fmaf(mx, mx, fmaf(myk, myk, kC1)), d2 = sxx + tsp[(2 * c + 1) * C::TS + k * TW];
+          const float val = 0.5f - 0.5f * (n1 * n2 * __fdividef(1.f, d1 * d2));
+          ssim_acc[k] += fminf(fmaxf(val, 0.f), 1.f);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      if (!(col_in && v0 + prow0 + k < H)) continue;
+      const float rho = R > 0 ? p.w_ssim * (ssim_acc[k] * (1.f / 3.f)) + p.w_l1 * (l1_acc[k] * (1.f / 3.f))
+                              : l1_acc[k] * (1.f / 3.f);
+      p.out[((size_t)b * S + s) * plane + pix0 + (size_t)k * W] = rho;
+    }
+    __syncthreads();   // wp and hb are rewritten by the next source
+  }
+}
+
 // Deterministic final reduction of per-CTA partial sums (one block; double accumulation).
 __global__ void finalize_sum3_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
   __shared__ double sh[256];
@@ -1054,4 +1185,38 @@ extern "C" int sqlx_photo_bwd(const sqlx_photo_desc* desc, const float* depth_lr
   const int n = desc->B * desc->S * 16;
   dT_from_dP3_kernel<<<ceil_div(n, 128), 128, 0, st>>>(K, dP, desc->B, desc->S, d_T);
   return check_launch("dT_from_dP_kernel");
+}
+
+namespace {
+template <int R>
+int launch_identity3(const IdentParams& p, cudaStream_t st) {
+  using C = Ident3Cfg<R, 32, 32, 256>;
+  auto kern = identity3_kernel<R, 32, 32, 256>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
+    configured = true;
+  }
+  dim3 grid(ceil_div(p.W, 32), ceil_div(p.H, 32), p.B);
+  ProfScope prof("identity_loss_kernel", st);
+  kern<<<grid, 256, C::smem_bytes, st>>>(p);
+  return check_launch("identity3_kernel");
+}
+}  // namespace
+
+extern "C" int sqlx_identity_losses_fwd(const float* target, const float* const* sources, int S, int B, int H, int W,
+                                        int ssim_radius, float w_ssim, float w_l1, int no_ssim, float* identity,
+                                        void* stream) {
+  SQLX_REQUIRE(target && sources && identity, "NULL pointer argument");
+  SQLX_REQUIRE(S >= 1 && S <= SQLX_MAX_SOURCES && B > 0 && H > 0 && W > 0, "bad shape");
+  const int r = no_ssim ? 0 : ssim_radius;
+  SQLX_REQUIRE(r == 0 || r == 1 || r == 3, "ssim_radius must be 1 or 3");
+  SQLX_REQUIRE(H > 2 * r && W > 2 * r, "image smaller than the SSIM window");
+  SQLX_REQUIRE((long long)H * W < (1ll << 30), "frame too large for 32-bit pixel offsets");
+  IdentParams p;
+  p.B = B; p.H = H; p.W = W; p.S = S; p.w_ssim = w_ssim; p.w_l1 = w_l1; p.target = target; p.out = identity;
+  for (int s = 0; s < SQLX_MAX_SOURCES; ++s) p.src[s] = s < S ? sources[s] : nullptr;
+  for (int s = 0; s < S; ++s) SQLX_REQUIRE(p.src[s], "source %d is NULL", s);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return r == 3 ? launch_identity3<3>(p, st) : (r == 1 ? launch_identity3<1>(p, st) : launch_identity3<0>(p, st));
 }

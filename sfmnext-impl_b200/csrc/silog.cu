@@ -163,3 +163,36 @@ extern "C" int sqlx_silog_bwd(const float* pred, const float* gt, const uint8_t*
   silog_bwd_kernel<<<blocks, 256, 0, st>>>(pred, gt, mask, B, h, w, H, W, variance_focus, saved, g_loss, d_pred);
   return check_launch("silog_bwd_kernel");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Flip test-time augmentation blend: evaluate_depth_config.py:51-59 batch_post_process_disparity
+// fused with the flip of the second pass (evaluate_depth_config.py:131,157): one kernel, no host round trip.
+//   l [N,h,w] prediction of the frames, r [N,h,w] prediction of the horizontally flipped frames
+//   r_is_flipped = 1: r still is in the flipped frame (as the network returned it) and is read mirrored
+//   out = r_mask * l + l_mask * r' + (1 - l_mask - r_mask) * (l + r') / 2,  l_mask(u) = 1 - clip(20 (u/(w-1) - .05), 0, 1)
+// ------------------------------------------------------------------------------------------------
+namespace sqlx {
+__global__ void postprocess_disp_kernel(const float* __restrict__ l, const float* __restrict__ r, int rows, int w,
+                                        int r_is_flipped, float* __restrict__ out) {
+  const float inv = w > 1 ? 1.f / (float)(w - 1) : 0.f;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const size_t o = (size_t)row * w;
+    for (int u = threadIdx.x; u < w; u += blockDim.x) {
+      const float lm = 1.f - fminf(fmaxf(20.f * ((float)u * inv - 0.05f), 0.f), 1.f);
+      const float rm = 1.f - fminf(fmaxf(20.f * ((float)(w - 1 - u) * inv - 0.05f), 0.f), 1.f);
+      const float a = l[o + u], b = r[o + (r_is_flipped ? w - 1 - u : u)];
+      out[o + u] = rm * a + lm * b + (1.f - lm - rm) * (0.5f * (a + b));
+    }
+  }
+}
+}  // namespace sqlx
+
+extern "C" int sqlx_postprocess_disparity(const float* l_disp, const float* r_disp, int N, int h, int w, int r_is_flipped,
+                                          float* out, void* stream) {
+  SQLX_REQUIRE(l_disp && r_disp && out, "NULL pointer argument");
+  SQLX_REQUIRE(N > 0 && h > 0 && w > 0, "non-positive shape");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rows = N * h;
+  postprocess_disp_kernel<<<rows < 8 * kNumSMs ? rows : 8 * kNumSMs, 128, 0, st>>>(l_disp, r_disp, rows, w, r_is_flipped, out);
+  return check_launch("postprocess_disp_kernel");
+}

@@ -196,3 +196,33 @@ class SILogLoss(torch.nn.Module):
         if not interpolate and input.shape[-2:] != target.shape[-2:]:
             raise RuntimeError("The size of tensor a must match the size of tensor b")   # what the reference raises
         return _SILogFn.apply(input, target, mask, self.variance_focus)
+
+
+def batch_post_process_disparity(l_disp, r_disp, r_is_flipped=False):
+    """Drop-in for evaluate_depth_config.batch_post_process_disparity (evaluate_depth_config.py:51-59) on CUDA tensors:
+    l_disp, r_disp [N,h,w] -> [N,h,w].  With r_is_flipped=True `r_disp` is the raw prediction for the mirrored frames
+    (the reference un-flips it on the host first, :157); the kernel reads it mirrored instead."""
+    require_cuda(l_disp, r_disp)
+    l, r = _f32c(l_disp), _f32c(r_disp)
+    if l.dim() != 3 or l.shape != r.shape:
+        raise RuntimeError("batch_post_process_disparity expects two [N,h,w] tensors of the same shape")
+    N, h, w = l.shape
+    out = torch.empty_like(l)
+    check(lib().sqlx_postprocess_disparity(ptr(l), ptr(r), N, h, w, int(bool(r_is_flipped)), ptr(out), stream_ptr()),
+          "sqlx_postprocess_disparity")
+    return out
+
+
+def predict_disparity(encoder, depth_decoder, input_color, post_process=False):
+    """The evaluation forward of evaluate_depth_config.py:126-158 kept on the device: optional flip test-time
+    augmentation (one batched pass over [frames; mirrored frames]) and the Monodepth-v1 blend.  `encoder` is the
+    reference's backbone, `depth_decoder` a sqlx.Depth_Decoder_QueryTr / Lite_Depth_Decoder_QueryTr.
+    Returns pred_disp [N,h,w]."""
+    with torch.no_grad():
+        if post_process:
+            input_color = torch.cat((input_color, torch.flip(input_color, [3])), 0)
+        pred = depth_decoder(encoder(input_color))[("disp", 0)][:, 0]
+        if post_process:
+            N = pred.shape[0] // 2
+            pred = batch_post_process_disparity(pred[:N], pred[N:], r_is_flipped=True)
+    return pred

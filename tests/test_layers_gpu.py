@@ -116,3 +116,17 @@ def test_silog_golden_and_oracle():
         (gc,) = torch.autograd.grad(lc, pc)
         assert abs(float(lc) - float(lo)) < 1e-4 * max(1.0, abs(float(lo)))
         assert float((gc.cpu().double() - go).abs().max() / go.abs().max()) < 1e-3
+
+
+def test_postprocess_disparity_golden():
+    """Flip-TTA blend against the reference's own numpy output (evaluate_depth_config.py:51-59), both with the second
+    prediction already un-flipped (the reference's call) and with the fused un-flip."""
+    import sqlx
+    z = load_npz("eval_postprocess")
+    for i in range(3):
+        l, r = _t(z["l%d" % i]), _t(z["r%d" % i])
+        ref = torch.from_numpy(z["out%d" % i])
+        out = sqlx.batch_post_process_disparity(l, r).cpu().double()
+        assert float((out - ref).abs().max()) < 1e-6
+        out2 = sqlx.batch_post_process_disparity(l, torch.flip(r, [2]).contiguous(), r_is_flipped=True).cpu().double()
+        assert float((out2 - ref).abs().max()) < 1e-6

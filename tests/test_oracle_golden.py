@@ -78,3 +78,11 @@ def test_modules_match_reference():
     assert abs(float(sm) - float(z["out_smooth"])) < 1e-7
     sil = O.silog_loss(_t(z["silog_pred"]), _t(z["silog_gt"]), mask=_t(z["silog_gt"]) > 1e-3)
     assert abs(float(sil) - float(z["out_silog"])) < 1e-5
+
+
+def test_postprocess_disparity_golden():
+    """Flip-TTA blend (evaluate_depth_config.py:51-59): oracle vs the reference's own numpy output."""
+    z = load_npz("eval_postprocess")
+    for i in range(3):
+        out = O.batch_post_process_disparity(_t(z["l%d" % i]), _t(z["r%d" % i]))
+        assert float((out - torch.from_numpy(z["out%d" % i])).abs().max()) < 1e-12

@@ -208,6 +208,19 @@ int sqlx_ms_loss_bwd(const sqlx_ms_desc* desc, const float* const* depth_lr, con
                      float* const* d_depth_lr, float* const* d_axisangle, float* const* d_translation, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* ---- Bins head: the nn.Linear layers of bins_regressor and the bin-centre arithmetic
+ * (networks/depth_decoder_QTR.py:48-66) as weight-streaming kernels for batch <= 16 per GPU.
+ *   linear_fwd : y [B,N] = act(x [B,K] W^T [N,K] + bias), act = LeakyReLU(0.01) when leaky
+ *   linear_bwd : dy is the gradient wrt y; dz [B,N] scratch; dW [N,K], db [N] and (unless NULL) dx [B,K] overwritten
+ *   centers    : raw [B,D] -> centers [B,D] for norm == 'linear' (relu + 0.1, normalise, widths, cumsum, mid-points) */
+int sqlx_head_linear_fwd(const float* W, const float* bias, const float* x, int B, int N, int K, int leaky, float* y,
+                         void* stream);
+int sqlx_head_linear_bwd(const float* W, const float* x, const float* y, const float* dy, int B, int N, int K, int leaky,
+                         float* dz, float* dW, float* db, float* dx, void* stream);
+int sqlx_head_centers_fwd(const float* raw, int B, int D, float min_val, float max_val, float* centers, void* stream);
+int sqlx_head_centers_bwd(const float* raw, const float* centers, const float* g_centers, int B, int D, float min_val,
+                          float max_val, float* d_raw, void* stream);
+
 /* ---- Supervised fine-tuning loss: finetune/loss.py:29-42 SILogLoss.forward with the
  * align_corners=True bilinear resize (train_ft_SQLdepth.py:235) and the boolean-mask gather fused into one pass.
  *   pred [B,1,h,w]; gt [B,1,H,W]; mask [B,1,H,W] u8 (torch.bool storage) or NULL; loss [1]; saved [4] floats

@@ -1,0 +1,244 @@
+// Bins head of the SQLdepth decoder: the three nn.Linear of `bins_regressor` and the bin-centre
+// arithmetic (networks/depth_decoder_QTR.py:48-66) as weight-streaming kernels for a handful of samples per GPU.
+//   y_b     = bins_regressor(summary.view(B, Q*E))            Linear(QE -> 16Q) LeakyReLU Linear(16Q -> 256) LeakyReLU Linear(256 -> D)
+//   y       = relu(y_b) + 0.1 ; y /= sum_d y                  (norm == 'linear')
+//   widths  = (max - min) * y ; edges = cumsum(pad(widths, min)) ; centers = (edges[:-1] + edges[1:]) / 2
+// With M = batch <= 16 these layers are bound by reading (forward, d_input) and writing (d_weight) the weight
+// matrices once -- 8.4 MB for the first layer at Q = 64 -- which cuBLAS does through ~12 small-M GEMM / split-K /
+// elementwise launches per direction.  Here: one CTA per output row streams the row with 128-bit loads against all
+// samples at once; 4 launches forward, 10 backward, exact fp32.
+#include "common.cuh"
+
+namespace sqlx {
+
+constexpr int kHeadMaxB = 16;
+constexpr float kLeakySlope = 0.01f;   // nn.LeakyReLU() default negative_slope
+
+// Sum 16 per-lane values over the warp (16 shuffles): lanes 2i and 2i+1 end with the total of v[i] in v[0].
+__device__ __forceinline__ void head_reduce16(float (&v)[16]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int w = 16, n = 8; n >= 1; w >>= 1, n >>= 1) {
+    const bool upper = lane & w;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = upper ? v[i] : v[i + n];
+      const float keep = upper ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// y[b,n] = act(sum_k W[n,k] x[b,k] + bias[n]); one 4-warp CTA per output row n, K split across the 128 threads
+__global__ void __launch_bounds__(128) head_linear_fwd_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                              const float* __restrict__ x, int B, int N, int K, int leaky,
+                                                              float* __restrict__ y) {
+  __shared__ float part[4][kHeadMaxB];
+  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[kHeadMaxB];
+#pragma unroll
+  for (int b = 0; b < kHeadMaxB; ++b) acc[b] = 0.f;
+  const float4* wr = reinterpret_cast<const float4*>(W + (size_t)n * K);
+  for (int k4 = threadIdx.x; k4 < K / 4; k4 += 128) {
+    const float4 wv = __ldg(wr + k4);
+#pragma unroll
+    for (int b = 0; b < kHeadMaxB; ++b) {
+      if (b < B) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)b * K) + k4);
+        acc[b] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[b]))));
+      }
+    }
+  }
+  head_reduce16(acc);
+  if (!(lane & 1)) part[warp][lane >> 1] = acc[0];
+  __syncthreads();
+  const int b = threadIdx.x;
+  if (b < B) {
+    float v = ((part[0][b] + part[1][b]) + (part[2][b] + part[3][b])) + __ldg(bias + n);
+    if (leaky) v = v > 0.f ? v : kLeakySlope * v;
+    y[(size_t)b * N + n] = v;
+  }
+}
+
+// dz[b,n] = dy[b,n] * act'(y[b,n]);  dW[n,k] = sum_b dz[b,n] x[b,k];  db[n] = sum_b dz[b,n].  One 4-warp CTA per row n.
+__global__ void __launch_bounds__(128) head_linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                                const float* __restrict__ x, int B, int N, int K,
+                                                                int leaky, float* __restrict__ dz, float* __restrict__ dW,
+                                                                float* __restrict__ db) {
+  const int n = blockIdx.x;
+  float g[kHeadMaxB];
+  float bsum = 0.f;
+#pragma unroll
+  for (int b = 0; b < kHeadMaxB; ++b) {
+    g[b] = 0.f;
+    if (b < B) {
+      float v = __ldg(dy + (size_t)b * N + n);
+      if (leaky && !(__ldg(y + (size_t)b * N + n) > 0.f)) v *= kLeakySlope;
+      g[b] = v;
+      bsum += v;
+    }
+  }
+  if ((int)threadIdx.x < B) {
+    float mine = 0.f;
+#pragma unroll
+    for (int b = 0; b < kHeadMaxB; ++b) mine = (b == (int)threadIdx.x) ? g[b] : mine;
+    dz[(size_t)threadIdx.x * N + n] = mine;
+  }
+  if (threadIdx.x == 0) db[n] = bsum;
+  float4* out = reinterpret_cast<float4*>(dW + (size_t)n * K);
+  for (int k4 = threadIdx.x; k4 < K / 4; k4 += 128) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int b = 0; b < kHeadMaxB; ++b) {
+      if (b < B) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)b * K) + k4);
+        a.x = fmaf(g[b], xv.x, a.x); a.y = fmaf(g[b], xv.y, a.y); a.z = fmaf(g[b], xv.z, a.z); a.w = fmaf(g[b], xv.w, a.w);
+      }
+    }
+    out[k4] = a;
+  }
+}
+
+// dx[b,k] += sum_{n in chunk} dz[b,n] W[n,k]; grid (ceil(K/128), chunks); dx zeroed by the caller
+constexpr int kHeadChunk = 32;
+__global__ void __launch_bounds__(128) head_linear_bwd_x_kernel(const float* __restrict__ dz, const float* __restrict__ W,
+                                                                int B, int N, int K, float* __restrict__ dx) {
+  __shared__ float sdz[kHeadMaxB][kHeadChunk];
+  const int k = blockIdx.x * 128 + threadIdx.x;
+  const int n0 = blockIdx.y * kHeadChunk, n1 = min(N, n0 + kHeadChunk);
+  for (int i = threadIdx.x; i < kHeadMaxB * kHeadChunk; i += 128) {
+    const int b = i / kHeadChunk, j = i - b * kHeadChunk;
+    sdz[b][j] = (b < B && n0 + j < n1) ? __ldg(dz + (size_t)b * N + n0 + j) : 0.f;
+  }
+  __syncthreads();
+  if (k >= K) return;
+  float acc[kHeadMaxB];
+#pragma unroll
+  for (int b = 0; b < kHeadMaxB; ++b) acc[b] = 0.f;
+#pragma unroll 8
+  for (int n = n0; n < n1; ++n) {
+    const float wv = __ldg(W + (size_t)n * K + k);
+#pragma unroll
+    for (int b = 0; b < kHeadMaxB; ++b) acc[b] = fmaf(sdz[b][n - n0], wv, acc[b]);
+  }
+#pragma unroll
+  for (int b = 0; b < kHeadMaxB; ++b)
+    if (b < B) atomicAdd(dx + (size_t)b * K + k, acc[b]);
+}
+
+// ---- bin centres (depth_decoder_QTR.py:51-66, norm == 'linear'); one block of 256 threads per sample, D <= 256
+__global__ void __launch_bounds__(256) head_centers_fwd_kernel(const float* __restrict__ raw, int D, float min_val,
+                                                               float max_val, float* __restrict__ centers) {
+  __shared__ float sh[256];
+  const int b = blockIdx.x, d = threadIdx.x;
+  const float y = d < D ? fmaxf(__ldg(raw + (size_t)b * D + d), 0.f) + 0.1f : 0.f;
+  sh[d] = y;
+  __syncthreads();
+  // inclusive scan (Hillis-Steele, D <= 256)
+  for (int o = 1; o < 256; o <<= 1) {
+    const float t = d >= o ? sh[d - o] : 0.f;
+    __syncthreads();
+    sh[d] += t;
+    __syncthreads();
+  }
+  const float total = sh[255];
+  const float c = (max_val - min_val) / total;
+  if (d < D) {
+    const float incl = sh[d], excl = incl - y;                  // cumulative y up to and excluding / including bin d
+    centers[(size_t)b * D + d] = min_val + c * (excl + 0.5f * y);   // 0.5 (edge_d + edge_{d+1})
+  }
+}
+
+// centers_d = min + c/s (sum_{j<d} y_j + y_d / 2), s = sum y, c = max - min
+//   d centers_d / d y_j = c/s ([j<d] + [j==d]/2) - (centers_d - min) / s
+__global__ void __launch_bounds__(256) head_centers_bwd_kernel(const float* __restrict__ raw,
+                                                               const float* __restrict__ centers,
+                                                               const float* __restrict__ g_centers, int D, float min_val,
+                                                               float max_val, float* __restrict__ d_raw) {
+  __shared__ float sy[256], sg[256], sgc[256];
+  const int b = blockIdx.x, d = threadIdx.x;
+  const float r = d < D ? __ldg(raw + (size_t)b * D + d) : 0.f;
+  const float y = d < D ? fmaxf(r, 0.f) + 0.1f : 0.f;
+  const float g = d < D ? __ldg(g_centers + (size_t)b * D + d) : 0.f;
+  const float cen = d < D ? __ldg(centers + (size_t)b * D + d) : min_val;
+  sy[d] = y;
+  sg[d] = g;                        // suffix sums of g
+  sgc[d] = g * (cen - min_val);     // sum_d g_d (centers_d - min)
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {            // totals of y and g (centers - min)
+    if (d < o) { sy[d] += sy[d + o]; sgc[d] += sgc[d + o]; }
+    __syncthreads();
+  }
+  const float s = sy[0], dot = sgc[0];
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {            // inclusive suffix scan of g
+    const float t = d + o < 256 ? sg[d + o] : 0.f;
+    __syncthreads();
+    sg[d] += t;
+    __syncthreads();
+  }
+  if (d < D) {
+    const float c = (max_val - min_val) / s;
+    const float suffix_excl = sg[d] - g;          // sum_{d' > d} g_d'
+    const float dy = c * (suffix_excl + 0.5f * g) - dot / s;
+    d_raw[(size_t)b * D + d] = r > 0.f ? dy : 0.f;
+  }
+}
+
+}  // namespace sqlx
+
+using namespace sqlx;
+
+extern "C" int sqlx_head_linear_fwd(const float* W, const float* bias, const float* x, int B, int N, int K, int leaky,
+                                    float* y, void* stream) {
+  SQLX_REQUIRE(W && bias && x && y, "NULL pointer argument");
+  SQLX_REQUIRE(B >= 1 && B <= kHeadMaxB, "batch %d outside 1..%d", B, kHeadMaxB);
+  SQLX_REQUIRE(N >= 1 && K >= 4 && K % 4 == 0, "in_features must be a positive multiple of 4 (got %d)", K);
+  SQLX_REQUIRE(((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(x)) & 15) == 0, "W and x must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ProfScope prof("head_linear_fwd_kernel", st);
+  head_linear_fwd_kernel<<<N, 128, 0, st>>>(W, bias, x, B, N, K, leaky, y);
+  return check_launch("head_linear_fwd_kernel");
+}
+
+/* dy: gradient wrt the layer output y (after the activation when leaky); dz [B,N] scratch; dW [N,K], db [N] overwritten;
+ * dx [B,K] overwritten (may be NULL: first layer input without gradient). */
+extern "C" int sqlx_head_linear_bwd(const float* W, const float* x, const float* y, const float* dy, int B, int N, int K,
+                                    int leaky, float* dz, float* dW, float* db, float* dx, void* stream) {
+  SQLX_REQUIRE(W && x && dy && dz && dW && db && (!leaky || y), "NULL pointer argument");
+  SQLX_REQUIRE(B >= 1 && B <= kHeadMaxB, "batch %d outside 1..%d", B, kHeadMaxB);
+  SQLX_REQUIRE(N >= 1 && K >= 4 && K % 4 == 0, "in_features must be a positive multiple of 4 (got %d)", K);
+  SQLX_REQUIRE(((reinterpret_cast<uintptr_t>(dW) | reinterpret_cast<uintptr_t>(x)) & 15) == 0, "dW and x must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {
+    ProfScope prof("head_linear_bwd_kernel", st);
+    head_linear_bwd_w_kernel<<<N, 128, 0, st>>>(dy, y, x, B, N, K, leaky, dz, dW, db);
+    if (int e = check_launch("head_linear_bwd_w_kernel")) return e;
+  }
+  if (dx) {
+    if (cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * K, st) != cudaSuccess) return check_launch("cudaMemsetAsync(dx)");
+    ProfScope prof("head_linear_bwd_kernel", st);
+    head_linear_bwd_x_kernel<<<dim3(ceil_div(K, 128), ceil_div(N, kHeadChunk)), 128, 0, st>>>(dz, W, B, N, K, dx);
+    if (int e = check_launch("head_linear_bwd_x_kernel")) return e;
+  }
+  return SQLX_OK;
+}
+
+extern "C" int sqlx_head_centers_fwd(const float* raw, int B, int D, float min_val, float max_val, float* centers,
+                                     void* stream) {
+  SQLX_REQUIRE(raw && centers, "NULL pointer argument");
+  SQLX_REQUIRE(B >= 1 && D >= 1 && D <= 256, "dim_out %d outside 1..256", D);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  head_centers_fwd_kernel<<<B, 256, 0, st>>>(raw, D, min_val, max_val, centers);
+  return check_launch("head_centers_fwd_kernel");
+}
+
+extern "C" int sqlx_head_centers_bwd(const float* raw, const float* centers, const float* g_centers, int B, int D,
+                                     float min_val, float max_val, float* d_raw, void* stream) {
+  SQLX_REQUIRE(raw && centers && g_centers && d_raw, "NULL pointer argument");
+  SQLX_REQUIRE(B >= 1 && D >= 1 && D <= 256, "dim_out %d outside 1..256", D);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  head_centers_bwd_kernel<<<B, 256, 0, st>>>(raw, centers, g_centers, D, min_val, max_val, d_raw);
+  return check_launch("head_centers_bwd_kernel");
+}

@@ -93,7 +93,7 @@ class HotPath(torch.nn.Module):
     # ------------------------------------------------------------------ one eager step
     def _centers(self, summary):
         c = self.cfg
-        return S.bin_centers(self.bins_regressor(summary.reshape(c.B, c.Q * c.E)), c.min_depth, c.max_depth)
+        return S.bins_head(summary.reshape(c.B, c.Q * c.E), self.bins_regressor, c.min_depth, c.max_depth)
 
     def forward_loss(self, slot=0):
         c, I = self.cfg, self.slots[slot]

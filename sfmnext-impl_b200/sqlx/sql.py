@@ -173,6 +173,74 @@ def bin_centers(raw, min_val, max_val, norm="linear"):
     return 0.5 * (edges[:, :-1] + edges[:, 1:])
 
 
+class _BinsHead(torch.autograd.Function):
+    """summary [B, Q*E] -> bin centres [B, D] through the three Linear layers of bins_regressor and the centre
+    arithmetic, on the weight-streaming kernels of csrc/bins_head.cu (4 launches forward, 10 backward)."""
+
+    @staticmethod
+    def forward(ctx, s, W1, b1, W2, b2, W3, b3, min_val, max_val):
+        L = lib()
+        sc = _f32c(s)
+        Ws = [_f32c(W1), _f32c(W2), _f32c(W3)]
+        bs = [_f32c(b1), _f32c(b2), _f32c(b3)]
+        B = sc.shape[0]
+        acts = [sc]
+        for i in range(3):
+            N, K = Ws[i].shape
+            y = torch.empty(B, N, device=sc.device, dtype=torch.float32)
+            check(L.sqlx_head_linear_fwd(ptr(Ws[i]), ptr(bs[i]), ptr(acts[-1]), B, N, K, int(i < 2), ptr(y), stream_ptr()),
+                  "sqlx_head_linear_fwd")
+            acts.append(y)
+        raw = acts[3]
+        D = raw.shape[1]
+        centers = torch.empty_like(raw)
+        check(L.sqlx_head_centers_fwd(ptr(raw), B, D, float(min_val), float(max_val), ptr(centers), stream_ptr()),
+              "sqlx_head_centers_fwd")
+        ctx.save_for_backward(*acts, centers, *Ws)
+        ctx.lims = (float(min_val), float(max_val))
+        return centers
+
+    @staticmethod
+    def backward(ctx, g_centers):
+        L = lib()
+        s, h1, h2, raw, centers, W1, W2, W3 = ctx.saved_tensors
+        B, D = raw.shape
+        g = _f32c(g_centers)
+        d_raw = torch.empty_like(raw)
+        check(L.sqlx_head_centers_bwd(ptr(raw), ptr(centers), ptr(g), B, D, ctx.lims[0], ctx.lims[1], ptr(d_raw),
+                                      stream_ptr()), "sqlx_head_centers_bwd")
+        acts, Ws = [s, h1, h2, raw], [W1, W2, W3]
+        dy = d_raw
+        dWs, dbs = [None] * 3, [None] * 3
+        for i in (2, 1, 0):
+            N, K = Ws[i].shape
+            dz = torch.empty(B, N, device=g.device, dtype=torch.float32)
+            dWs[i] = torch.empty_like(Ws[i])
+            dbs[i] = torch.empty(N, device=g.device, dtype=torch.float32)
+            need_dx = i > 0 or ctx.needs_input_grad[0]
+            dx = torch.empty(B, K, device=g.device, dtype=torch.float32) if need_dx else None
+            check(L.sqlx_head_linear_bwd(ptr(Ws[i]), ptr(acts[i]), ptr(acts[i + 1]), ptr(dy), B, N, K, int(i < 2), ptr(dz),
+                                         ptr(dWs[i]), ptr(dbs[i]), ptr(dx), stream_ptr()), "sqlx_head_linear_bwd")
+            dy = dx
+        return dy, dWs[0], dbs[0], dWs[1], dbs[1], dWs[2], dbs[2], None, None
+
+
+def bins_head(summary_flat, regressor, min_val, max_val, norm="linear"):
+    """bin centres [B,D] = centres(bins_regressor(summary)) (depth_decoder_QTR.py:48-66).  `regressor` is the
+    nn.Sequential(Linear, LeakyReLU, Linear, LeakyReLU, Linear) of the reference decoder.  The weight-streaming
+    kernels take batch <= 16, norm == 'linear', in_features % 4 == 0 and dim_out <= 256 (every reference config);
+    other cases run the same arithmetic through cuBLAS + elementwise PyTorch ops on the GPU."""
+    lins = [m for m in regressor if isinstance(m, torch.nn.Linear)]
+    acts = [m for m in regressor if isinstance(m, torch.nn.LeakyReLU)]
+    ok = (norm == "linear" and len(lins) == 3 and len(acts) == 2 and all(a.negative_slope == 0.01 for a in acts) and
+          summary_flat.is_cuda and summary_flat.shape[0] <= 16 and lins[2].out_features <= 256 and
+          all(l.in_features % 4 == 0 and l.bias is not None for l in lins))
+    if not ok:
+        return bin_centers(regressor(summary_flat), min_val, max_val, norm)
+    return _BinsHead.apply(summary_flat, lins[0].weight, lins[0].bias, lins[1].weight, lins[1].bias, lins[2].weight,
+                           lins[2].bias, min_val, max_val)
+
+
 class _SqlTail(torch.autograd.Function):
     """x, queries, Wp, bp -> pred, with the bins MLP evaluated by a caller-supplied closure.
 
@@ -283,7 +351,7 @@ class Depth_Decoder_QueryTr(torch.nn.Module):
 
         def centers_fn(summary):
             B, Q, E = summary.shape
-            return bin_centers(self.bins_regressor(summary.view(B, Q * E)), self.min_val, self.max_val, self.norm)
+            return bins_head(summary.view(B, Q * E), self.bins_regressor, self.min_val, self.max_val, self.norm)
 
         pred = sql_tail(x, queries.contiguous(), Wp, conv.bias, centers_fn, tuple(self.bins_regressor.parameters()))
         return {("disp", 0): pred}

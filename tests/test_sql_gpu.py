@@ -161,3 +161,28 @@ def test_full_size_properties():
     s1 = S.summary_fwd(x, q)[0]
     s2 = S.summary_fwd(xp, q)[0]
     assert float((s1 - s2).abs().max()) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,Q,E,D", [(12, 64, 32, 64), (2, 120, 32, 128), (16, 16, 32, 24)])
+def test_bins_head_matches_torch(B, Q, E, D):
+    """csrc/bins_head.cu (three Linear layers + centre arithmetic, depth_decoder_QTR.py:48-66) against the same
+    arithmetic in float64 PyTorch: values and every gradient."""
+    from sqlx import sql as S
+    torch.manual_seed(B + Q)
+    nn = torch.nn
+    reg = nn.Sequential(nn.Linear(Q * E, 16 * Q), nn.LeakyReLU(), nn.Linear(16 * Q, 256), nn.LeakyReLU(),
+                        nn.Linear(256, D)).cuda()
+    s = torch.randn(B, Q * E, device="cuda", requires_grad=True)
+    g = torch.randn(B, D, device="cuda")
+    c = S.bins_head(s, reg, 0.001, 80.0)
+    grads = torch.autograd.grad(c, [s] + list(reg.parameters()), g)
+    reg64 = nn.Sequential(nn.Linear(Q * E, 16 * Q), nn.LeakyReLU(), nn.Linear(16 * Q, 256), nn.LeakyReLU(),
+                          nn.Linear(256, D)).double().cuda()
+    reg64.load_state_dict({k: v.double() for k, v in reg.state_dict().items()})
+    s64 = s.detach().double().requires_grad_(True)
+    c64 = S.bin_centers(reg64(s64), 0.001, 80.0)
+    grads64 = torch.autograd.grad(c64, [s64] + list(reg64.parameters()), g.double())
+    assert float((c.double() - c64).abs().max() / c64.abs().max()) < 1e-5
+    for a, b in zip(grads, grads64):
+        assert float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30)) < 1e-4

@@ -71,8 +71,9 @@ class HotPath(torch.nn.Module):
         self.losses = [None] * num_slots
         self.loss = None
         self.pred = None
-        for p in self.parameters():          # static gradient buffers shared by every captured graph
-            p.grad = torch.zeros_like(p)
+        # parameter gradients of each captured graph live in that graph's memory pool (autograd ASSIGNS them: no
+        # zero-fill + accumulate kernels per parameter); step(slot) points p.grad at the replayed graph's tensors
+        self.slot_grads = [None] * num_slots
 
     # ------------------------------------------------------------------ data
     def load(self, host_batch, non_blocking=True, slot=0):
@@ -112,7 +113,7 @@ class HotPath(torch.nn.Module):
 
     def _zero_grads(self, slot=0):
         for p in self.parameters():
-            p.grad.zero_()                    # in place: the buffers are shared with the captured graphs
+            p.grad = None
         for k in self.grad_inputs:
             self.slots[slot][k].grad = None
 
@@ -126,8 +127,8 @@ class HotPath(torch.nn.Module):
 
     # ------------------------------------------------------------------ graph
     def capture(self, warmup=3, slot=0):
-        """Capture zero-grads + forward + backward on input set `slot` into one CUDA graph (parameter gradients
-        land in the shared static .grad buffers, input gradients in the slot's own .grad tensors)."""
+        """Capture forward + backward on input set `slot` into one CUDA graph (parameter and input gradients are the
+        tensors autograd creates during capture: static addresses in the graph's pool)."""
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -138,13 +139,14 @@ class HotPath(torch.nn.Module):
         for k in self.grad_inputs:
             self.slots[slot][k].grad = None
         g = torch.cuda.CUDAGraph()
+        for p in self.parameters():
+            p.grad = None
         with torch.cuda.graph(g):
-            for p in self.parameters():
-                p.grad.zero_()
             loss, pred = self.forward_loss(slot)
             loss.backward()
             self.losses[slot] = loss.detach()
             self.pred = pred.detach()
+        self.slot_grads[slot] = [p.grad for p in self.parameters()]
         self.graphs[slot] = g
         return g
 
@@ -154,6 +156,8 @@ class HotPath(torch.nn.Module):
             if self.graphs[slot] is None:
                 self.capture(slot=slot)
             self.graphs[slot].replay()
+            for p, gr in zip(self.parameters(), self.slot_grads[slot]):
+                p.grad = gr
             self.loss = self.losses[slot]
             return self.loss
         return self.step_eager(slot)

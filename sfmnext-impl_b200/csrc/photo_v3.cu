@@ -41,6 +41,14 @@ __global__ void pack_rgba_kernel(const float* __restrict__ img, int B, int plane
   }
 }
 
+// 1/x as a single MUFU.RCP (rcp.approx.ftz): every caller's argument is far from the denormal range
+// (SSIM denominators >= C1*C2 = 9e-8; camera depths), so the range fix-up of __fdividef is dead weight
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // region loop: f(lr, lc) for every element of an RH x RW region, thread-strided, (lr, lc) carried incrementally
 template <int RH, int RW, int NT, class F>
 __device__ __forceinline__ void for_region(F&& f) {
@@ -108,7 +116,7 @@ __device__ __forceinline__ Proj project_fast(const Camera& cam, float u, float v
   const float c0 = fmaf(cam.P[0], s.X0, fmaf(cam.P[1], s.X1, fmaf(cam.P[2], s.X2, cam.P[3])));
   const float c1 = fmaf(cam.P[4], s.X0, fmaf(cam.P[5], s.X1, fmaf(cam.P[6], s.X2, cam.P[7])));
   const float c2 = fmaf(cam.P[8], s.X0, fmaf(cam.P[9], s.X1, fmaf(cam.P[10], s.X2, cam.P[11])));
-  s.rz = __fdividef(1.f, c2 + eps);
+  s.rz = rcp_fast(c2 + eps);
   s.pu = c0 * s.rz;
   s.pv = c1 * s.rz;
   return s;
@@ -137,7 +145,7 @@ __device__ __forceinline__ void project_composed(const CamM& c, float u, float v
   const float m0 = fmaf(c.M[0], u, fmaf(c.M[1], v, c.M[2]));
   const float m1 = fmaf(c.M[3], u, fmaf(c.M[4], v, c.M[5]));
   const float m2 = fmaf(c.M[6], u, fmaf(c.M[7], v, c.M[8]));
-  const float rz = __fdividef(1.f, fmaf(d, m2, c.t[2]) + eps);
+  const float rz = rcp_fast(fmaf(d, m2, c.t[2]) + eps);
   pu = fmaf(d, m0, c.t[0]) * rz;
   pv = fmaf(d, m1, c.t[1]) * rz;
 }
@@ -453,18 +461,17 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
           const float sxy = fmaf(-mx, myk, Sxy[k] * ia);
           const float n1 = fmaf(2.f * mx, myk, kC1), n2 = fmaf(2.f, sxy, kC2);
           const float d1 = fmaf(mx, mx, fmaf(myk, myk, kC1)), d2 = sxx + tsp[(2 * c + 1) * C::TS + k * TW];
-          const float inv_d = __fdividef(1.f, d1 * d2);
+          const float inv_d = rcp_fast(d1 * d2);
           const float q = n1 * n2 * inv_d;
           const float val = 0.5f - 0.5f * q;
           ssim_acc[k] += fminf(fmaxf(val, 0.f), 1.f);
           if (cbase && col_in && v0 + prow0 + k < H) {
-            float gmx = 0.f, gxx = 0.f, gxy = 0.f;
-            if (val >= 0.f && val <= 1.f) {   // torch.clamp backward; NaN -> 0
-              const float dS_dn = -0.5f * inv_d, dS_dd = 0.5f * q * inv_d;
-              gmx = dS_dn * (2.f * myk * (n2 - n1)) + dS_dd * (2.f * mx * (d2 - d1));
-              gxx = dS_dd * d1;
-              gxy = dS_dn * 2.f * n1;
-            }
+            // torch.clamp backward: zero outside [0,1] (NaN -> 0); branch-free
+            const bool ok = val >= 0.f && val <= 1.f;
+            const float dS_dn = -0.5f * inv_d, dS_dd = 0.5f * q * inv_d;
+            const float gmx = ok ? dS_dn * (2.f * myk * (n2 - n1)) + dS_dd * (2.f * mx * (d2 - d1)) : 0.f;
+            const float gxx = ok ? dS_dd * d1 : 0.f;
+            const float gxy = ok ? dS_dn * 2.f * n1 : 0.f;
             float* cp = cbase + (size_t)k * W;
             __stcs(cp, gmx); __stcs(cp + plane, gxx); __stcs(cp + 2 * plane, gxy);
           }
@@ -622,7 +629,7 @@ __global__ void __launch_bounds__(NT, 2) identity3_kernel(const IdentParams p) {
           const float sxy = fmaf(-mx, myk, Sxy[k] * ia);
           const float n1 = fmaf(2.f * mx, myk, kC1), n2 = fmaf(2.f, sxy, kC2);
           const float d1 = fmaf(mx, mx, fmaf(myk, myk, kC1)), d2 = sxx + tsp[(2 * c + 1) * C::TS + k * TW];
-          const float val = 0.5f - 0.5f * (n1 * n2 * __fdividef(1.f, d1 * d2));
+          const float val = 0.5f - 0.5f * (n1 * n2 * rcp_fast(d1 * d2));
           ssim_acc[k] += fminf(fmaxf(val, 0.f), 1.f);
         }
       }

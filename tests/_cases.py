@@ -76,7 +76,7 @@ def depth_like(g, B, h, w, lo=2.0, hi=30.0):
     return (lo + (hi - lo) * d).contiguous()
 
 
-def synth_photo_case(seed, B, H, W, S=2, scales=(0,), stereo=False, white_noise=False):
+def synth_photo_case(seed, B, H, W, S=2, scales=(0,), stereo=False, white_noise=False, full_res_disp=False):
     """Seeded synthetic photometric case (same recipe as oracle/make_golden.py) for oracle-vs-CUDA tests."""
     g = torch.Generator().manual_seed(seed)
     n_frames = S + 1
@@ -93,7 +93,7 @@ def synth_photo_case(seed, B, H, W, S=2, scales=(0,), stereo=False, white_noise=
     for s in scales:
         if s > 0:
             target_pyr[s] = F.interpolate(target, [H // 2 ** s, W // 2 ** s], mode="bilinear", align_corners=False)
-        hs, ws = (H // 2, W // 2) if s == 0 else (H // 2 ** s, W // 2 ** s)
+        hs, ws = ((H, W) if full_res_disp else (H // 2, W // 2)) if s == 0 else (H // 2 ** s, W // 2 ** s)
         disps[s] = depth_like(g, B, hs, ws)
     poses = []
     for i in range(S):

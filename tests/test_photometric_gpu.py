@@ -106,6 +106,8 @@ def test_golden(name):
     dict(seed=4, B=1, H=64, W=96, S=1, scales=(0,)),
     dict(seed=5, B=1, H=96, W=160, S=2, scales=(0, 1, 2, 3)),
     dict(seed=6, B=2, H=48, W=64, S=2, scales=(0,), white_noise=True),
+    dict(seed=7, B=1, H=64, W=96, S=3, scales=(0,), full_res_disp=True),   # config 4 (EffB5): decoder output at HxW
+    dict(seed=8, B=1, H=65, W=97, S=2, scales=(0,)),                       # 32x48 map under a 65x97 frame: non-integer factor
 ])
 def test_oracle_fp64(cfg):
     """CUDA fp32 vs the oracle evaluated in float64 on the same seeded inputs."""

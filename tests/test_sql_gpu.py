@@ -163,6 +163,50 @@ def test_full_size_properties():
     assert float((s1 - s2).abs().max()) < 1e-5
 
 
+def test_config4_size_properties():
+    """BASELINE config-4 size (EffB5: x0 32x320x1024 = 327,680 pixels per sample, Q = D = 128), through the public
+    sql_tail (tensor-core mixed-weight path), forward and backward: (1) pred inside the centre range; (2) a constant
+    shift of the logits leaves pred and the gradient wrt x unchanged; (3) permuting the pixels permutes pred and
+    d_x and leaves d_queries / d_Wp unchanged (every reduction over pixels is order-independent up to rounding)."""
+    import sqlx
+    torch.manual_seed(6)
+    B, E, h, w, Q, D = 2, 32, 320, 1024, 128, 128
+    x = torch.randn(B, E, h, w, device="cuda")
+    q = 0.4 * torch.randn(B, Q, E, device="cuda")
+    Wp = 0.3 * torch.randn(D, Q, device="cuda")
+    bp = 0.1 * torch.randn(D, device="cuda")
+    lin = torch.nn.Linear(Q * E, D).cuda()
+    gout = torch.randn(B, 1, h, w, device="cuda")
+
+    def run(xin, bias, g):
+        xl, ql, Wl = xin.clone().requires_grad_(True), q.clone().requires_grad_(True), Wp.clone().requires_grad_(True)
+        cen = []
+
+        def centers_fn(s):
+            c = sqlx.bin_centers(lin(s.reshape(B, -1)), 0.01, 80.0)
+            cen.append(c.detach())
+            return c
+        pred = sqlx.sql_tail(xl, ql, Wl, bias, centers_fn, tuple(lin.parameters()))
+        gx, gq, gW = torch.autograd.grad((pred * g).sum(), [xl, ql, Wl])
+        return pred.detach(), gx, gq, gW, cen[0]
+
+    pred, gx, gq, gW, cen = run(x, bp, gout)
+    pv = pred.view(B, -1)
+    assert bool(torch.isfinite(pv).all()) and bool(torch.isfinite(gx).all())
+    assert bool((pv >= cen[:, :1] * (1 - 1e-5)).all()) and bool((pv <= cen[:, -1:] * (1 + 1e-5)).all())
+    pred2, gx2, _, _, _ = run(x, bp + 3.0, gout)
+    assert float(((pred - pred2) / pred).abs().max()) < 1e-4
+    assert float((gx - gx2).abs().max() / gx.abs().max()) < 2e-3
+    perm = torch.randperm(h * w, device="cuda")
+    xp = x.view(B, E, -1)[:, :, perm].view(B, E, h, w).contiguous()
+    gp = gout.view(B, 1, -1)[:, :, perm].view(B, 1, h, w).contiguous()
+    predp, gxp, gqp, gWp, _ = run(xp, bp, gp)
+    assert float(((predp.view(B, -1) - pv[:, perm]) / pv[:, perm]).abs().max()) < 1e-4
+    assert float((gxp.view(B, E, -1) - gx.view(B, E, -1)[:, :, perm]).abs().max() / gx.abs().max()) < 2e-3
+    assert float((gqp - gq).abs().max() / gq.abs().max()) < 2e-3
+    assert float((gWp - gW).abs().max() / gW.abs().max()) < 2e-3
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,Q,E,D", [(12, 64, 32, 64), (2, 120, 32, 128), (16, 16, 32, 24)])
 def test_bins_head_matches_torch(B, Q, E, D):

@@ -244,3 +244,54 @@ def test_multiscale_gradients_are_reproducible():
     n = len(kw["scales"])
     for i, (a, b) in enumerate(zip(runs[0][1], runs[1][1])):
         assert _rel(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["photo_mono_ms4", "photo_stereo_s0"])
+def test_trainer_mixin_dict_contract(name):
+    """sqlx.FusedLossMixin: Trainer.generate_images_pred / compute_losses / compute_reprojection_loss with the
+    reference's signatures and inputs / outputs dict keys (trainer.py:386-549), against the reference's own results."""
+    import types
+    import sqlx
+    kw, leaves, z, fids = photo_case(name)
+    g = _to_dev(kw)
+
+    class T(sqlx.FusedLossMixin):
+        pass
+    tr = T()
+    tr.opt = types.SimpleNamespace(scales=list(kw["scales"]), frame_ids=list(fids), height=kw["height"], width=kw["width"],
+                                   pose_model_type="posecnn", use_stereo="s" in fids, no_ssim=kw["no_ssim"],
+                                   avg_reprojection=kw["avg_reprojection"], disable_automasking=kw["disable_automasking"],
+                                   disparity_smoothness=1e-3, v1_multiscale=False, predictive_mask=False)
+    tr.sqlx_noises = g["noises"]
+    inputs = {("K", 0): g["K"], ("inv_K", 0): g["inv_K"]}
+    outputs = {}
+    for s in kw["scales"]:
+        inputs[("color", 0, s)] = g["target_pyr"][s]
+        outputs[("disp", s)] = g["disps"][s]
+    for f, src, pose in zip(fids[1:], g["sources"], g["poses"]):
+        inputs[("color", f, 0)] = src
+        if f == "s":
+            inputs["stereo_T"] = pose["T"]
+        else:
+            outputs[("axisangle", 0, f)], outputs[("translation", 0, f)] = pose["axisangle"], pose["translation"]
+    tr.generate_images_pred(inputs, outputs)
+    losses = tr.compute_losses(inputs, outputs)
+    assert abs(float(losses["loss"]) - float(z["out_loss"])) < 1e-5
+    s0 = kw["scales"][0]
+    for s in kw["scales"]:
+        assert abs(float(losses["loss/%d" % s]) - float(z["out_loss_s%d" % s])) < 1e-5
+        np.testing.assert_allclose(outputs[("depth", 0, s)].cpu().numpy(), z["out_depth_s%d" % s], rtol=1e-5, atol=1e-5)
+    for f in fids[1:]:
+        np.testing.assert_allclose(outputs[("color", f, s0)].cpu().numpy(), z["out_color_%s_s%d" % (f, s0)], atol=1e-4)
+        assert outputs[("color_identity", f, s0)] is inputs[("color", f, 0)]
+    sel = outputs["identity_selection/%d" % s0].cpu().numpy().astype(np.uint8)
+    assert (sel != z["out_idsel_s%d" % s0]).mean() < 2e-3
+    losses["loss"].backward()
+    assert g["disps"][s0].grad is not None and bool(torch.isfinite(g["disps"][s0].grad).all())
+    # compute_reprojection_loss: same values as the fused identity losses, and differentiable
+    p = g["sources"][0].clone().requires_grad_(True)
+    r = tr.compute_reprojection_loss(p, g["target_pyr"][0])
+    ident = sqlx.photometric.identity_losses(g["target_pyr"][0], g["sources"])
+    assert float((r[:, 0] - ident[:, 0]).abs().max()) < 2e-4
+    r.mean().backward()
+    assert bool(torch.isfinite(p.grad).all())

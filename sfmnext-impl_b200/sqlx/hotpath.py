@@ -74,6 +74,7 @@ class HotPath(torch.nn.Module):
         # parameter gradients of each captured graph live in that graph's memory pool (autograd ASSIGNS them: no
         # zero-fill + accumulate kernels per parameter); step(slot) points p.grad at the replayed graph's tensors
         self.slot_grads = [None] * num_slots
+        self.side_stream = None
 
     # ------------------------------------------------------------------ data
     def load(self, host_batch, non_blocking=True, slot=0):
@@ -99,16 +100,28 @@ class HotPath(torch.nn.Module):
     def forward_loss(self, slot=0):
         c, I = self.cfg, self.slots[slot]
         conv = self.convert_to_prob[0]
+        sources = [I["source%d" % i] for i in range(c.S)]
+        # what depends on the input frames only (identity losses, pixel-interleaved source copies) runs on a side
+        # stream while the decoder tail -- a few 4-warp CTAs per SM -- occupies the main one
+        main = torch.cuda.current_stream()
+        if self.side_stream is None:
+            self.side_stream = torch.cuda.Stream()
+        side = self.side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            identity = P.identity_losses(I["target"], sources)
+            packed = [P.pack_rgba(src) for src in sources]
         pred = S.sql_tail(I["x"], I["queries"], conv.weight.view(c.D, c.Q), conv.bias, self._centers,
                           tuple(self.bins_regressor.parameters()))
+        main.wait_stream(side)
         disps = {s: (pred if s == 0 else I["disp%d" % s]) for s in c.scales}
         target_pyr = {s: (I["target"] if s == 0 else I["target%d" % s]) for s in c.scales}
-        sources = [I["source%d" % i] for i in range(c.S)]
         poses = [{"axisangle": I["axisangle%d" % i], "translation": I["translation%d" % i], "invert": i == 0}
                  for i in range(c.S)]
         noises = {s: I["noise%d" % s] for s in c.scales}
         out = P.photometric_losses(disps, target_pyr, sources, I["K"], I["inv_K"], poses, noises, height=c.H,
-                                   width=c.W, scales=c.scales, disparity_smoothness=c.disparity_smoothness)
+                                   width=c.W, scales=c.scales, disparity_smoothness=c.disparity_smoothness,
+                                   identity=identity, packed_sources=packed)
         return out["loss"], pred
 
     def _zero_grads(self, slot=0):

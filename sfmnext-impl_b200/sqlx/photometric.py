@@ -412,7 +412,7 @@ def identity_losses(target, sources, *, no_ssim=False, ssim_radius=3, w_ssim=0.8
 def photometric_losses(disps, target_pyr, sources, K, inv_K, poses, noises, *, height, width, scales=(0,),
                        disparity_smoothness=1e-3, rescale_translation=True, no_ssim=False, avg_reprojection=False,
                        disable_automasking=False, ssim_radius=3, materialize=False, identity=None,
-                       per_scale_calls=False):
+                       packed_sources=None, per_scale_calls=False):
     """generate_images_pred + compute_losses (trainer.py:386-549): ONE fused library call for all loss scales
     (`per_scale_calls=True`: one call per scale through sqlx_scale_loss_fwd/bwd instead, same results).
 
@@ -442,7 +442,9 @@ def photometric_losses(disps, target_pyr, sources, K, inv_K, poses, noises, *, h
             pose_tensors += [pose["axisangle"], pose["translation"]]
     rescale = bool(rescale_translation) and any(sp[0] == "net" for sp in pose_spec)
     n_ident = 0 if not automask else (1 if avg_reprojection else S)
-    packed = [pack_rgba(src) for src in sources]    # once per step: every scale, forward and backward, gathers from these
+    # once per step: every scale, forward and backward, gathers from these (`identity` and `packed_sources` depend on
+    # the input frames only: a caller may compute them early, e.g. on a side stream while the decoder runs)
+    packed = list(packed_sources) if packed_sources is not None else [pack_rgba(src) for src in sources]
     scales = tuple(scales)
     if len(scales) > _lib.MAX_SCALES:
         raise ValueError("at most %d loss scales" % _lib.MAX_SCALES)

@@ -975,6 +975,21 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_dx_kernel(
   if (warp == 0) tmem_dealloc(tmem, kCols);
 }
 
+// 2^x as one MUFU.EX2 (callers fold log2(e) and the softmax reference point into x with one FFMA)
+__device__ __forceinline__ float ex2_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
+// Per-thread part of sw128_offset(row, lane) for the eight values of row & 7: with a compile-time row the transposed
+// store address becomes base + row * 128 + sw[row & 7] (no per-element address arithmetic).
+__device__ __forceinline__ void sw128_lane_offsets(int lane, uint32_t (&sw)[8]) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) sw[r] = ((((uint32_t)lane >> 2) ^ (uint32_t)r) << 4) + (((uint32_t)lane & 3u) << 2);
+}
+
 // ================================================================================================
 // "Mixed-weight" decomposition (all Q, D <= 128):   logits = Wp (K x) + b = (Wp K) x + b = M x + b,  M [D x 32].
 // The depth regression and its backward then contract over E = 32 instead of Q, need no Wp tiles on chip and no
@@ -1165,7 +1180,7 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_pred_kernel(
   }
   for (int i = threadIdx.x; i < 4 * 128 * 32; i += kThreads) reinterpret_cast<float*>(adz)[i] = 0.f;
   for (int d = threadIdx.x; d < DP; d += kThreads) {
-    s.bias[d] = d < D ? __ldg(bp + d) : -INFINITY;
+    s.bias[d] = d < D ? __ldg(bp + d) * kLog2e : -INFINITY;   // logits are handled in base 2: t = z log2e + bias log2e
     s.cen[d] = d < D ? __ldg(centers + (size_t)b * D + d) : 0.f;
   }
   fence_proxy_async();
@@ -1174,6 +1189,8 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_pred_kernel(
   tc_fence_after();
   const uint32_t tmem = *s.tmem_slot;
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  uint32_t swl[8];
+  sw128_lane_offsets(lane, swl);
   constexpr uint32_t tm_z = 0, tm_dx = DP, tm_acc = DP + 32;
   const uint32_t id_acc = make_idesc_tf32(128, kAccN, 0, 0);
   const uint32_t id_dx = make_idesc_tf32(128, 32, 0, 0);
@@ -1201,8 +1218,10 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_pred_kernel(
     }
     mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
-    // pass A: online max / sum / expectation over the logits
+    // pass A: online max / sum / expectation over the base-2 logits t = (z + bias) log2e
     float m = -INFINITY, se = 0.f, sc = 0.f;
+    const float4* bias4 = reinterpret_cast<const float4*>(s.bias);
+    const float4* cen4 = reinterpret_cast<const float4*>(s.cen);
 #pragma unroll
     for (int c = 0; c < DP; c += 16) {
       float v[16];
@@ -1210,25 +1229,43 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_pred_kernel(
       tmem_wait_ld();
       float cm = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { v[i] += s.bias[c + i]; cm = fmaxf(cm, v[i]); }
-      if (cm > m) { const float r = __expf(m - cm); se *= r; sc *= r; m = cm; }
+      for (int j = 0; j < 4; ++j) {
+        const float4 bq = bias4[(c >> 2) + j];
+        v[4 * j] = fmaf(v[4 * j], kLog2e, bq.x); v[4 * j + 1] = fmaf(v[4 * j + 1], kLog2e, bq.y);
+        v[4 * j + 2] = fmaf(v[4 * j + 2], kLog2e, bq.z); v[4 * j + 3] = fmaf(v[4 * j + 3], kLog2e, bq.w);
+        cm = fmaxf(cm, fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), fmaxf(v[4 * j + 2], v[4 * j + 3])));
+      }
+      if (cm > m) { const float r = ex2_fast(m - cm); se *= r; sc *= r; m = cm; }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { const float e = __expf(v[i] - m); se += e; sc = fmaf(e, s.cen[c + i], sc); }
+      for (int j = 0; j < 4; ++j) {
+        const float4 cq = cen4[(c >> 2) + j];
+        const float e0 = ex2_fast(v[4 * j] - m), e1 = ex2_fast(v[4 * j + 1] - m);
+        const float e2 = ex2_fast(v[4 * j + 2] - m), e3 = ex2_fast(v[4 * j + 3] - m);
+        se += (e0 + e1) + (e2 + e3);
+        sc += fmaf(e0, cq.x, e1 * cq.y) + fmaf(e2, cq.z, e3 * cq.w);
+      }
     }
     const float inv = 1.f / se, pr = sc * inv;
     const float g = p < n ? __ldg(g_pred + (size_t)b * n + p) * inv : 0.f;   // g / sum folded together
     // pass B: pi g, dz -> registers (d_centers), TMEM (A operand of d_x) and transposed shared memory (A operand of dM)
+    uint8_t* adw = adz + warp * 128 * 128;
 #pragma unroll
     for (int c = 0; c < DP; c += 16) {
       float v[16];
       tmem_ld16(lane_base + tm_z + c, v);
       tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float pg = __expf(v[i] + s.bias[c + i] - m) * g;
-        dc[c + i] += pg;
-        v[i] = pg * (s.cen[c + i] - pr);
-        *reinterpret_cast<float*>(adz + warp * 128 * 128 + sw128_offset(c + i, lane)) = v[i];
+      for (int j = 0; j < 4; ++j) {
+        const float4 bq = bias4[(c >> 2) + j], cq = cen4[(c >> 2) + j];
+        const float bv[4] = {bq.x, bq.y, bq.z, bq.w}, cv[4] = {cq.x, cq.y, cq.z, cq.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = 4 * j + k, d = c + i;
+          const float pg = ex2_fast(fmaf(v[i], kLog2e, bv[k]) - m) * g;
+          dc[d] += pg;
+          v[i] = pg * (cv[k] - pr);
+          *reinterpret_cast<float*>(adw + d * 128 + swl[d & 7]) = v[i];
+        }
       }
       tmem_st16(lane_base + tm_z + c, v);
     }
@@ -1384,7 +1421,10 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
         for (int e = 0; e < kE; ++e)
           delta = fmaf(__ldg(dsb + q * kE + e), __ldg(summary + ((size_t)b * Q + q) * kE + e), delta);
       }
-      mq[q] = m; il[q] = inv; dl[q] = delta;
+      // a[p,q] = exp(y - m) / l = 2^(y log2e + cq),  cq = -m log2e - log2(l)  (-inf for the padded queries: a = 0)
+      mq[q] = q < Q ? fmaf(-m, kLog2e, log2f(inv)) : -INFINITY;
+      il[q] = delta;
+      dl[q] = 0.f;
     }
   }
   fence_proxy_async();
@@ -1393,6 +1433,8 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
   tc_fence_after();
   const uint32_t tmem = *s.tmem_slot;
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  uint32_t swl[8];
+  sw128_lane_offsets(lane, swl);
   constexpr uint32_t tm_y = 0, tm_t = QP, tm_dx = 2 * QP, tm_dk = 2 * QP + 32;
   const uint32_t id_t = make_idesc_tf32(128, QP, 1, 0);
   const uint32_t id_32 = make_idesc_tf32(128, 32, 0, 0);
@@ -1401,6 +1443,7 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
   for (int t = t_begin; t < t_end; ++t) {
     const int p0 = t * kTile;
     const int p = p0 + warp * 32 + lane;
+    const bool pin = p < n;
     mbar_wait(s.bar_tma, ph_tma); ph_tma ^= 1;
     split_x_tile(s);
     fence_proxy_async();
@@ -1428,13 +1471,20 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
       tmem_ld16(lane_base + tm_y + c, yv);
       tmem_ld16(lane_base + tm_t + c, tt);
       tmem_wait_ld();
+      uint8_t* dyw = dyT + warp * 128 * 128;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int q = c + i;
-        const float a = (q < Q && p < n) ? __expf(yv[i] - mq[q]) * il[q] : 0.f;
-        yv[i] = a * (tt[i] - dl[q]);
-        tt[i] = a;
-        *reinterpret_cast<float*>(dyT + warp * 128 * 128 + sw128_offset(q, lane)) = yv[i];
+      for (int i4 = 0; i4 < 16; i4 += 4) {
+        const float4 cq4 = *reinterpret_cast<const float4*>(mq + c + i4);    // folded exponent offsets
+        const float4 dl4 = *reinterpret_cast<const float4*>(il + c + i4);    // delta_q = ds_q . summary_q
+        const float cqv[4] = {cq4.x, cq4.y, cq4.z, cq4.w}, dlv[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i4 + j, q = c + i;
+          const float a = pin ? ex2_fast(fmaf(yv[i], kLog2e, cqv[j])) : 0.f;
+          yv[i] = a * (tt[i] - dlv[j]);
+          tt[i] = a;
+          *reinterpret_cast<float*>(dyw + q * 128 + swl[q & 7]) = yv[i];
+        }
       }
       tmem_st16(lane_base + tm_y + c, yv);
       tmem_st16(lane_base + tm_t + c, tt);

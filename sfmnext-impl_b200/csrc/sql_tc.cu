@@ -60,6 +60,7 @@ constexpr int kTile = 128;       // pixels per tile = UMMA M
 constexpr int kThreads = 128;    // 4 warps: warp w owns TMEM lanes [32w, 32w+32)
 constexpr int kXBlock = 32 * kE * 4;         // one [32 e][32 px] SWIZZLE_128B block: 4096 B
 constexpr int kXTile = 4 * kXBlock;          // 128 pixels: 16 KB
+constexpr float kLog2eS = 1.4426950408889634f;   // softmax arithmetic runs in base 2: exp(a - m) = 2^(a log2e - m log2e)
 
 // shared-memory carve-up (all operand regions 1024-B aligned for SWIZZLE_128B)
 struct Smem {
@@ -128,7 +129,7 @@ __device__ __forceinline__ void stage_wp(const Smem& s, const float* __restrict_
     *reinterpret_cast<float*>(s.w_lo + off) = v - hi;
   }
   for (int d = threadIdx.x; d < Dp; d += kThreads) {
-    s.bias[d] = d < D ? __ldg(bp + d) : -INFINITY;   // padded bins never win the softmax
+    s.bias[d] = d < D ? __ldg(bp + d) * kLog2eS : -INFINITY;   // base-2 logits; padded bins never win the softmax
     s.cen[d] = d < D ? __ldg(centers_b + d) : 0.f;
   }
 }
@@ -215,6 +216,13 @@ __device__ __forceinline__ void issue_z(const Smem& s, uint32_t tm_z, uint32_t t
 }
 
 // softmax over the Dp logits of this thread's pixel (TMEM lane) and expected bin centre, one pass (online max)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// s.bias holds bias * log2e: the logits are handled in base 2 (one FFMA + one MUFU.EX2 per element)
 __device__ __forceinline__ float softmax_expect(const Smem& s, uint32_t lane_base, uint32_t tm_z, int Dp) {
   // four independent accumulation chains (the kernels run 4-12 warps per SM: a single dependent add / fma chain per
   // thread leaves the issue slots idle), bias and centres fetched as 128-bit shared loads
@@ -229,12 +237,13 @@ __device__ __forceinline__ float softmax_expect(const Smem& s, uint32_t lane_bas
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float4 bq = bias4[(c >> 2) + j];
-      v[4 * j] += bq.x; v[4 * j + 1] += bq.y; v[4 * j + 2] += bq.z; v[4 * j + 3] += bq.w;
+      v[4 * j] = fmaf(v[4 * j], kLog2eS, bq.x); v[4 * j + 1] = fmaf(v[4 * j + 1], kLog2eS, bq.y);
+      v[4 * j + 2] = fmaf(v[4 * j + 2], kLog2eS, bq.z); v[4 * j + 3] = fmaf(v[4 * j + 3], kLog2eS, bq.w);
       cmx[j] = fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), fmaxf(v[4 * j + 2], v[4 * j + 3]));
     }
     const float cm = fmaxf(fmaxf(cmx[0], cmx[1]), fmaxf(cmx[2], cmx[3]));
     if (cm > m) {
-      const float r = __expf(m - cm);
+      const float r = ex2_approx(m - cm);
 #pragma unroll
       for (int j = 0; j < 4; ++j) { se[j] *= r; sc[j] *= r; }
       m = cm;
@@ -242,8 +251,8 @@ __device__ __forceinline__ float softmax_expect(const Smem& s, uint32_t lane_bas
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float4 cq = cen4[(c >> 2) + j];
-      const float e0 = __expf(v[4 * j] - m), e1 = __expf(v[4 * j + 1] - m);
-      const float e2 = __expf(v[4 * j + 2] - m), e3 = __expf(v[4 * j + 3] - m);
+      const float e0 = ex2_approx(v[4 * j] - m), e1 = ex2_approx(v[4 * j + 1] - m);
+      const float e2 = ex2_approx(v[4 * j + 2] - m), e3 = ex2_approx(v[4 * j + 3] - m);
       se[j] += (e0 + e1) + (e2 + e3);
       sc[j] += fmaf(e0, cq.x, e1 * cq.y) + fmaf(e2, cq.z, e3 * cq.w);
     }
@@ -462,29 +471,40 @@ __global__ void __launch_bounds__(kThreads) sql_tc_summary_kernel(const __grid_c
     tc_fence_after();
     // ---- this thread's query row: tile max, lazy rescale, P = exp(y - m) -> TMEM (hi in place, lo beside it)
     const int valid = min(kTileS, n - p0);   // pixels >= n were zero-filled by TMA: exclude them
+    const bool full = valid == kTileS;        // every tile but (possibly) the last: no per-element range checks
     float tmax = -INFINITY;
     for (int c = 0; c < kTileS; c += 16) {
       float v[16];
       tmem_ld16(lane_base + c, v);
       tmem_wait_ld();
+      if (full) {
+        float t4[4];
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (c + i < valid) tmax = fmaxf(tmax, v[i]);
+        for (int j = 0; j < 4; ++j) t4[j] = fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), fmaxf(v[4 * j + 2], v[4 * j + 3]));
+        tmax = fmaxf(tmax, fmaxf(fmaxf(t4[0], t4[1]), fmaxf(t4[2], t4[3])));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c + i < valid) tmax = fmaxf(tmax, v[i]);
+      }
     }
     float rs = 1.f;
     if (tmax > m + 8.f) {          // lazy: the reference point only moves when exceeded by > 8 (exp args <= 8)
       rs = __expf(m - tmax);       // m = -inf at first: 0
       m = tmax;
     }
-    float lsum = 0.f;
+    const float nm2 = -m * kLog2eS;   // exp(y - m) = 2^(y log2e - m log2e): one FFMA + one MUFU.EX2 per element
+    float ls4[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = 0; c < kTileS; c += 16) {
       float v[16], lo[16];
       tmem_ld16(lane_base + c, v);
       tmem_wait_ld();
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float pe = (c + i < valid) ? __expf(v[i] - m) : 0.f;
-        lsum += pe;
+        float pe;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(fmaf(v[i], kLog2eS, nm2)));
+        if (!full && c + i >= valid) pe = 0.f;
+        ls4[i & 3] += pe;
         const float h = tf32_hi(pe);
         v[i] = h;
         lo[i] = pe - h;
@@ -492,6 +512,7 @@ __global__ void __launch_bounds__(kThreads) sql_tc_summary_kernel(const __grid_c
       tmem_st16(lane_base + c, v);
       tmem_st16(lane_base + kTileS + c, lo);
     }
+    const float lsum = (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
     tmem_wait_st();
     l = l * rs + lsum;
     tc_fence_before();
@@ -556,7 +577,7 @@ __device__ __forceinline__ float softmax64(const float* __restrict__ bias, const
     tmem_ld16(lane_base + tm_z + c, v);
     tmem_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) z[c + i] = v[i] + bias[c + i];
+    for (int i = 0; i < 16; ++i) z[c + i] = fmaf(v[i], kLog2eS, bias[c + i]);   // bias is staged as bias * log2e
   }
   float m = z[0];
 #pragma unroll
@@ -564,7 +585,7 @@ __device__ __forceinline__ float softmax64(const float* __restrict__ bias, const
   float se = 0.f, sc = 0.f;
 #pragma unroll
   for (int d = 0; d < kDB; ++d) {
-    z[d] = __expf(z[d] - m);
+    z[d] = ex2_approx(z[d] - m);
     se += z[d];
     sc = fmaf(z[d], cen[d], sc);
   }
@@ -1075,7 +1096,7 @@ __global__ void __launch_bounds__(kThreads) sql_tc_pred2_kernel(const __grid_con
   if (threadIdx.x == 0 && t_begin < t_end) issue_x_tma(s, &xmap, t_begin * kTile, b * kE);
   stage_mix(s.k_hi, s.k_lo, Mx + (size_t)b * D * kE, D, DP);
   for (int d = threadIdx.x; d < DP; d += kThreads) {
-    s.bias[d] = d < D ? __ldg(bp + d) : -INFINITY;
+    s.bias[d] = d < D ? __ldg(bp + d) * kLog2eS : -INFINITY;
     s.cen[d] = d < D ? __ldg(centers + (size_t)b * D + d) : 0.f;
   }
   fence_proxy_async();

@@ -1223,6 +1223,7 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_pred_kernel(
   for (int t = t_begin; t < t_end; ++t) {
     const int p0 = t * kTile;
     const int p = p0 + warp * 32 + lane;
+    const float gp = p < n ? __ldg(g_pred + (size_t)b * n + p) : 0.f;   // upstream gradient: in flight during the tile
     mbar_wait(s.bar_tma, ph_tma); ph_tma ^= 1;
     split_x_tile(s);
     fence_proxy_async();
@@ -1267,7 +1268,7 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_pred_kernel(
       }
     }
     const float inv = 1.f / se, pr = sc * inv;
-    const float g = p < n ? __ldg(g_pred + (size_t)b * n + p) * inv : 0.f;   // g / sum folded together
+    const float g = gp * inv;   // g / sum folded together
     // pass B: pi g, dz -> registers (d_centers), TMEM (A operand of d_x) and transposed shared memory (A operand of dM)
     uint8_t* adw = adz + warp * 128 * 128;
 #pragma unroll
@@ -1465,6 +1466,11 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
     const int p0 = t * kTile;
     const int p = p0 + warp * 32 + lane;
     const bool pin = p < n;
+    // accumulate mode: the regression-path d_x written by sql_tc_bwd_pred_kernel is fetched now (32 independent L2
+    // loads in flight for the whole tile) and added at the end -- the kernel runs one CTA per SM, registers are free
+    float prev[kE];
+#pragma unroll
+    for (int e = 0; e < kE; ++e) prev[e] = (accumulate && pin) ? __ldcg(dxb + (size_t)e * n + p) : 0.f;
     mbar_wait(s.bar_tma, ph_tma); ph_tma ^= 1;
     split_x_tile(s);
     fence_proxy_async();
@@ -1543,15 +1549,8 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
       tmem_ld16(lane_base + tm_dx + c, v);
       tmem_wait_ld();
       if (p < n) {
-        if (accumulate) {   // all loads first: one round trip instead of 16 dependent ones
-          float prev[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) prev[i] = __ldcg(dxb + (size_t)(c + i) * n + p);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += prev[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) dxb[(size_t)(c + i) * n + p] = v[i];
+        for (int i = 0; i < 16; ++i) dxb[(size_t)(c + i) * n + p] = v[i] + prev[c + i];
       }
     }
     tc_fence_before();

@@ -1,3 +1,9 @@
-timeout 600 python -m pytest tests/test_sql_gpu.py tests/test_sql_tc_gpu.py -m gpu -x -q 2>&1 | tail -3
-timeout 120 python tools/time_sql.py 2>&1 | head -9
-timeout 120 python tools/time_sql.py 8 160 512 128 128 2>&1 | head -6
+mkdir -p gpurun_out
+timeout 300 python bench.py --no-cpu-baseline --steps 200 2> gpurun_out/b1.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('c2', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'], 'loss', d['loss'])
+for k,v in d['kernels'].items(): print('   %-28s %5.1f x %8.1f us'%(k, v['launches_per_step'], v['ms_per_step']/v['launches_per_step']*1e3))"
+timeout 300 python bench.py --no-cpu-baseline --steps 200 --config 3 2> gpurun_out/b3.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('c3', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'], 'loss', d['loss'])
+for k,v in d['kernels'].items(): print('   %-28s %5.1f x %8.1f us'%(k, v['launches_per_step'], v['ms_per_step']/v['launches_per_step']*1e3))"

@@ -134,24 +134,46 @@ template <int E>
 __global__ void sql_summary_combine_kernel(const float* __restrict__ partial, int Q, int chunks,
                                            float* __restrict__ summary, float* __restrict__ row_max,
                                            float* __restrict__ row_sum) {
+  // one warp per (sample, query): lanes own the embedding channels, chunk records are read as coalesced rows,
+  // eight chunks in flight per trip (the first version ran one THREAD per query: 12 x 64 threads walking 800
+  // dependent loads each)
   constexpr int REC = E + 2;
-  const int b = blockIdx.x;
-  for (int q = threadIdx.x; q < Q; q += blockDim.x) {
-    float M = -INFINITY;
-    for (int c = 0; c < chunks; ++c) M = fmaxf(M, partial[(((size_t)b * chunks + c) * Q + q) * REC]);
-    float L = 0.f, acc[E];
+  constexpr int EPL = (E + 31) / 32;   // channels per lane
+  const int b = blockIdx.x, lane = threadIdx.x & 31;
+  const int q = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const float* base = partial + ((size_t)b * chunks * Q + q) * REC;
+  const size_t cstride = (size_t)Q * REC;
+  float M = -INFINITY;
+  for (int c = lane; c < chunks; c += 32) M = fmaxf(M, base[c * cstride]);
+  M = warp_max(M);
+  float L = 0.f, acc[EPL];
 #pragma unroll
-    for (int e = 0; e < E; ++e) acc[e] = 0.f;
-    for (int c = 0; c < chunks; ++c) {
-      const float* rec = partial + (((size_t)b * chunks + c) * Q + q) * REC;
-      const float wgt = rec[0] == -INFINITY ? 0.f : expf(rec[0] - M);
-      L = fmaf(rec[1], wgt, L);
+  for (int k = 0; k < EPL; ++k) acc[k] = 0.f;
+  for (int c0 = 0; c0 < chunks; c0 += 8) {
+    float m8[8], l8[8], a8[8][EPL];
 #pragma unroll
-      for (int e = 0; e < E; ++e) acc[e] = fmaf(rec[2 + e], wgt, acc[e]);
+    for (int j = 0; j < 8; ++j) {
+      const bool on = c0 + j < chunks;
+      const float* rec = base + (size_t)(on ? c0 + j : 0) * cstride;
+      m8[j] = on ? rec[0] : -INFINITY;
+      l8[j] = on ? rec[1] : 0.f;
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) a8[j][k] = (on && lane + 32 * k < E) ? rec[2 + lane + 32 * k] : 0.f;
     }
-    const float inv = 1.f / L;
 #pragma unroll
-    for (int e = 0; e < E; ++e) summary[((size_t)b * Q + q) * E + e] = acc[e] * inv;
+    for (int j = 0; j < 8; ++j) {
+      const float wgt = m8[j] == -INFINITY ? 0.f : expf(m8[j] - M);
+      L = fmaf(l8[j], wgt, L);
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) acc[k] = fmaf(a8[j][k], wgt, acc[k]);
+    }
+  }
+  const float inv = 1.f / L;
+#pragma unroll
+  for (int k = 0; k < EPL; ++k)
+    if (lane + 32 * k < E) summary[((size_t)b * Q + q) * E + lane + 32 * k] = acc[k] * inv;
+  if (lane == 0) {
     if (row_max) row_max[b * Q + q] = M;
     if (row_sum) row_sum[b * Q + q] = L;
   }
@@ -412,7 +434,15 @@ __global__ void sum_partials_kernel(const float* __restrict__ part, int count, i
   if (i >= stride) return;
   const float* src = part + (size_t)blockIdx.y * count * stride + i;
   float acc = 0.f;
-  for (int c = 0; c < count; ++c) acc += src[(size_t)c * stride];
+  int c = 0;
+  for (; c + 8 <= count; c += 8) {      // eight independent loads per trip, summed in index order
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = src[(size_t)(c + j) * stride];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += v[j];
+  }
+  for (; c < count; ++c) acc += src[(size_t)c * stride];
   out[(size_t)blockIdx.y * stride + i] = acc;
 }
 
@@ -695,7 +725,7 @@ int run_summary(const float* x, const float* queries, int B, int Q, int n, float
     sql_summary_kernel<E><<<dim3(c.chunks, B), kNT, smem, st>>>(x, queries, Q, n, c.tiles_per_chunk, ws);
   }
   if (int e = check_launch("sql_summary_kernel")) return e;
-  sql_summary_combine_kernel<E><<<B, 128, 0, st>>>(ws, Q, c.chunks, summary, row_max, row_sum);
+  sql_summary_combine_kernel<E><<<dim3(B, (Q + 3) / 4), 128, 0, st>>>(ws, Q, c.chunks, summary, row_max, row_sum);
   if (int e = check_launch("sql_summary_combine_kernel")) return e;
   if (energy) {
     const ChunkPlan t = plan_chunks(B, n, 2 * kTileTarget);
@@ -800,7 +830,7 @@ extern "C" int sqlx_sql_summary_fwd(const float* x, const float* queries, int B,
   if (use_tensor_cores(E, Q, 0, n)) {
     int chunks = 0;
     if (int e = tc_summary_partials(x, queries, B, Q, n, ws, &chunks, st)) return e;
-    sql_summary_combine_kernel<32><<<B, 128, 0, st>>>(ws, Q, chunks, summary, row_max, row_sum);
+    sql_summary_combine_kernel<32><<<dim3(B, (Q + 3) / 4), 128, 0, st>>>(ws, Q, chunks, summary, row_max, row_sum);
     if (int e = check_launch("sql_summary_combine_kernel")) return e;
     if (energy) return sqlx_sql_energy_tc(x, queries, B, E, Q, n, energy, stream);
     return SQLX_OK;

@@ -105,13 +105,23 @@ __device__ __forceinline__ Smem carve(uint8_t* raw, int Qp, int Dp) {
 
 // queries [Q][32] -> K-major SW128 hi / lo blocks with Qp rows (rows >= Q zero)
 __device__ __forceinline__ void stage_queries(const Smem& s, const float* __restrict__ qb, int Q, int Qp) {
-  for (int idx = threadIdx.x; idx < Qp * kE; idx += kThreads) {
-    const int q = idx >> 5, e = idx & 31;
-    const float v = q < Q ? __ldg(qb + idx) : 0.f;
-    const float hi = tf32_hi(v);
-    const uint32_t off = sw128_offset(q, e);
-    *reinterpret_cast<float*>(s.k_hi + off) = hi;
-    *reinterpret_cast<float*>(s.k_lo + off) = v - hi;
+  // eight independent loads in flight per trip (an in-order warp otherwise pays the global latency once per element)
+  for (int base = threadIdx.x; base < Qp * kE; base += 8 * kThreads) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = base + j * kThreads;
+      v[j] = (idx < Qp * kE && (idx >> 5) < Q) ? __ldg(qb + idx) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = base + j * kThreads;
+      if (idx >= Qp * kE) break;
+      const float hi = tf32_hi(v[j]);
+      const uint32_t off = sw128_offset(idx >> 5, idx & 31);
+      *reinterpret_cast<float*>(s.k_hi + off) = hi;
+      *reinterpret_cast<float*>(s.k_lo + off) = v[j] - hi;
+    }
   }
 }
 
@@ -422,13 +432,21 @@ __global__ void __launch_bounds__(kThreads) sql_tc_summary_kernel(const __grid_c
   // queries -> [128 rows][32] K-major SW128 hi / lo, rows >= Q zero
   {
     const float* qb = queries + (size_t)b * Q * kE;
-    for (int idx = threadIdx.x; idx < 128 * kE; idx += kThreads) {
-      const int q = idx >> 5, e = idx & 31;
-      const float v = q < Q ? __ldg(qb + idx) : 0.f;
-      const float hi = tf32_hi(v);
-      const uint32_t off = sw128_offset(q, e);
-      *reinterpret_cast<float*>(s.q_hi + off) = hi;
-      *reinterpret_cast<float*>(s.q_lo + off) = v - hi;
+    for (int base = threadIdx.x; base < 128 * kE; base += 8 * kThreads) {   // eight loads in flight per trip
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = base + j * kThreads;
+        v[j] = (idx >> 5) < Q ? __ldg(qb + idx) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = base + j * kThreads;
+        const float hi = tf32_hi(v[j]);
+        const uint32_t off = sw128_offset(idx >> 5, idx & 31);
+        *reinterpret_cast<float*>(s.q_hi + off) = hi;
+        *reinterpret_cast<float*>(s.q_lo + off) = v[j] - hi;
+      }
     }
   }
   tc_fence_before();
@@ -1023,13 +1041,22 @@ __device__ __forceinline__ void sw128_lane_offsets(int lane, uint32_t (&sw)[8]) 
 
 // M tiles: [DP rows][32 e] K-major SW128, hi / lo
 __device__ __forceinline__ void stage_mix(uint8_t* m_hi, uint8_t* m_lo, const float* __restrict__ Mb, int D, int DP) {
-  for (int idx = threadIdx.x; idx < DP * kE; idx += kThreads) {
-    const int d = idx >> 5, e = idx & 31;
-    const float v = d < D ? __ldg(Mb + idx) : 0.f;
-    const float hi = tf32_hi(v);
-    const uint32_t off = sw128_offset(d, e);
-    *reinterpret_cast<float*>(m_hi + off) = hi;
-    if (m_lo) *reinterpret_cast<float*>(m_lo + off) = v - hi;
+  for (int base = threadIdx.x; base < DP * kE; base += 8 * kThreads) {   // eight loads in flight per trip
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = base + j * kThreads;
+      v[j] = (idx < DP * kE && (idx >> 5) < D) ? __ldg(Mb + idx) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = base + j * kThreads;
+      if (idx >= DP * kE) break;
+      const float hi = tf32_hi(v[j]);
+      const uint32_t off = sw128_offset(idx >> 5, idx & 31);
+      *reinterpret_cast<float*>(m_hi + off) = hi;
+      if (m_lo) *reinterpret_cast<float*>(m_lo + off) = v[j] - hi;
+    }
   }
 }
 
@@ -1190,16 +1217,26 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_pred_kernel(
   if (threadIdx.x == 0 && t_begin < t_end) issue_x_tma(s, &map_mn, t_begin * kTile, b * kE);
   const float* Mb = Mx + (size_t)b * D * kE;
   stage_mix(s.k_hi, s.k_lo, Mb, D, DP);
-  for (int idx = threadIdx.x; idx < DP * kE; idx += kThreads) {   // mT[e][d] = M[d][e]
-    const int d = idx >> 5, e = idx & 31;
-    const float v = d < D ? __ldg(Mb + idx) : 0.f;
-    *reinterpret_cast<float*>(mT + (uint32_t)(d >> 5) * 32u * 128u + sw128_offset(e, d & 31)) = v;
+  for (int base = threadIdx.x; base < DP * kE; base += 8 * kThreads) {   // mT[e][d] = M[d][e]; eight loads per trip
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = base + j * kThreads;
+      v[j] = (idx < DP * kE && (idx >> 5) < D) ? __ldg(Mb + idx) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = base + j * kThreads;
+      if (idx >= DP * kE) break;
+      const int d = idx >> 5, e = idx & 31;
+      *reinterpret_cast<float*>(mT + (uint32_t)(d >> 5) * 32u * 128u + sw128_offset(e, d & 31)) = v[j];
+    }
   }
   for (int i = threadIdx.x; i < 4 * 16 * 32; i += kThreads) {      // rows 32..47 of every pixel atom: ones | zeros
     const int atom = i / (16 * 32), rem = i - atom * 16 * 32, row = kE + (rem >> 5), col = rem & 31;
     *reinterpret_cast<float*>(bx + atom * kAccN * 128 + sw128_offset(row, col)) = row == kE ? 1.f : 0.f;
   }
-  for (int i = threadIdx.x; i < 4 * 128 * 32; i += kThreads) reinterpret_cast<float*>(adz)[i] = 0.f;
+  for (int i = threadIdx.x; i < 4 * 128 * 32 / 4; i += kThreads) reinterpret_cast<float4*>(adz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int d = threadIdx.x; d < DP; d += kThreads) {
     s.bias[d] = d < D ? __ldg(bp + d) * kLog2e : -INFINITY;   // logits are handled in base 2: t = z log2e + bias log2e
     s.cen[d] = d < D ? __ldg(centers + (size_t)b * D + d) : 0.f;
@@ -1425,23 +1462,38 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
   {
     const float* qb = queries + (size_t)b * Q * kE;
     const float* dsb = d_summary + (size_t)b * Q * kE;
-    for (int idx = threadIdx.x; idx < QP * kE; idx += kThreads) {
-      const int q = idx >> 5, e = idx & 31;
-      const float kv = q < Q ? __ldg(qb + idx) : 0.f;
-      const float dv = q < Q ? __ldg(dsb + idx) : 0.f;
-      *reinterpret_cast<float*>(ds + sw128_offset(q, e)) = dv;
-      const uint32_t offT = (uint32_t)(q >> 5) * 32u * 128u + sw128_offset(e, q & 31);
-      *reinterpret_cast<float*>(kT + offT) = kv;
-      *reinterpret_cast<float*>(dsT + offT) = dv;
+    for (int base = threadIdx.x; base < QP * kE; base += 4 * kThreads) {   // eight loads in flight per trip
+      float kv[4], dv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = base + j * kThreads;
+        const bool on = idx < QP * kE && (idx >> 5) < Q;
+        kv[j] = on ? __ldg(qb + idx) : 0.f;
+        dv[j] = on ? __ldg(dsb + idx) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = base + j * kThreads;
+        if (idx >= QP * kE) break;
+        const int q = idx >> 5, e = idx & 31;
+        *reinterpret_cast<float*>(ds + sw128_offset(q, e)) = dv[j];
+        const uint32_t offT = (uint32_t)(q >> 5) * 32u * 128u + sw128_offset(e, q & 31);
+        *reinterpret_cast<float*>(kT + offT) = kv[j];
+        *reinterpret_cast<float*>(dsT + offT) = dv[j];
+      }
     }
-    for (int idx = threadIdx.x; idx < 4 * 128 * 32; idx += kThreads) reinterpret_cast<float*>(dyT)[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < 4 * 128 * 32 / 4; idx += kThreads)
+      reinterpret_cast<float4*>(dyT)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int q = threadIdx.x; q < QP; q += kThreads) {
       float m = 0.f, inv = 0.f, delta = 0.f;
       if (q < Q) {
         m = __ldg(row_max + b * Q + q);
         inv = 1.f / __ldg(row_sum + b * Q + q);
-        for (int e = 0; e < kE; ++e)
-          delta = fmaf(__ldg(dsb + q * kE + e), __ldg(summary + ((size_t)b * Q + q) * kE + e), delta);
+        float dsv[kE], smv[kE];
+#pragma unroll
+        for (int e = 0; e < kE; ++e) { dsv[e] = __ldg(dsb + q * kE + e); smv[e] = __ldg(summary + ((size_t)b * Q + q) * kE + e); }
+#pragma unroll
+        for (int e = 0; e < kE; ++e) delta = fmaf(dsv[e], smv[e], delta);
       }
       // a[p,q] = exp(y - m) / l = 2^(y log2e + cq),  cq = -m log2e - log2(l)  (-inf for the padded queries: a = 0)
       mq[q] = q < Q ? fmaf(-m, kLog2e, log2f(inv)) : -INFINITY;

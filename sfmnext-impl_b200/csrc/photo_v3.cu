@@ -736,10 +736,16 @@ __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdPara
   if (threadIdx.x < S)
     load_camera(p.K + b * 16, p.invK + b * 16, p.T + ((size_t)b * S + threadIdx.x) * 16, cams[threadIdx.x]);
   if (threadIdx.x < 16 * SQLX_MAX_SOURCES) dPs[threadIdx.x] = 0.f;
-  for_region<C::PH1, C::PW1, NT>([&](int lr, int lc, int idx) {
-    const int v = v0 - R + lr, u = u0 - R + lc;
-    amin[idx] = (v >= 0 && v < H && u >= 0 && u < W) ? p.argmin[(size_t)b * plane + (size_t)v * W + u] : (uint8_t)255;
-  });
+  {   // arg-min of the tile's R halo, two elements per trip (loads of both in flight)
+    uint8_t av[2];
+    for_region2<C::PH1, C::PW1, NT>(
+        [&](int j, int lr, int lc, bool live) {
+          const int v = v0 - R + lr, u = u0 - R + lc;
+          av[j] = (live && v >= 0 && v < H && u >= 0 && u < W) ? p.argmin[(size_t)b * plane + (size_t)v * W + u]
+                                                               : (uint8_t)255;
+        },
+        [&](int j, int lr, int lc) { amin[lr * C::PW1 + lc] = av[j]; });
+  }
 
   const int pcol = threadIdx.x % TW;
   const int prow0 = (threadIdx.x / TW) * PPT;
@@ -816,20 +822,23 @@ __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdPara
       // all nine coefficient planes (3 channels x {d/d mean, d/d E[x^2], d/d E[xy]}) of this source in ONE staging
       // pass: nine independent masked loads per halo pixel in flight, two block barriers per source
       const float* cb9 = p.coef + ((size_t)b * S + s) * 9 * plane;
-      for_region<C::PH1, C::PW1, NT>([&](int lr, int lc, int idx) {
-        float cv[9];
-        if (amin[idx] == sel_idx) {
-          const float* q = cb9 + (size_t)(v0 - R + lr) * W + (u0 - R + lc);
+      float cv[2][9];
+      for_region2<C::PH1, C::PW1, NT>(
+          [&](int j, int lr, int lc, bool live) {
+            if (live && amin[lr * C::PW1 + lc] == sel_idx) {
+              const float* q = cb9 + (size_t)(v0 - R + lr) * W + (u0 - R + lc);
 #pragma unroll
-          for (int m = 0; m < 9; ++m) cv[m] = __ldg(q + (size_t)m * plane);
-        } else {
+              for (int m = 0; m < 9; ++m) cv[j][m] = __ldg(q + (size_t)m * plane);
+            } else {
 #pragma unroll
-          for (int m = 0; m < 9; ++m) cv[m] = 0.f;
-        }
-        const int o = lr * C::LD + lc;
+              for (int m = 0; m < 9; ++m) cv[j][m] = 0.f;
+            }
+          },
+          [&](int j, int lr, int lc) {
+            const int o = lr * C::LD + lc;
 #pragma unroll
-        for (int m = 0; m < 9; ++m) cf[m * C::CF + o] = cv[m];
-      });
+            for (int m = 0; m < 9; ++m) cf[m * C::CF + o] = cv[j][m];
+          });
       __syncthreads();
       if (interior) {
 #pragma unroll

@@ -1,3 +1,4 @@
-timeout 600 python -m pytest tests/test_sql_gpu.py tests/test_sql_tc_gpu.py -m gpu -x -q 2>&1 | tail -2
-timeout 120 python tools/time_sql.py 2>&1 | head -6
-timeout 120 python tools/time_sql.py 8 160 512 128 128 2>&1 | head -6
+timeout 600 python -m pytest tests/test_photometric_gpu.py -m gpu -x -q 2>&1 | tail -2
+for f in 0 3; do echo "bwd cfg $f"; SQLX_BWD_CFG=$f timeout 200 python tools/time_photo.py 2>&1 | grep -E "photometric|photo_bwd" ; done
+SQLX_BWD_CFG=0 timeout 200 python tools/time_photo.py 8 320 1024 3 1 2>&1 | grep -E "photo_bwd"
+SQLX_BWD_CFG=3 timeout 200 python tools/time_photo.py 8 320 1024 3 1 2>&1 | grep -E "photo_bwd"

@@ -200,21 +200,41 @@ __global__ void ms_smooth_loss_kernel(MsShapes sh, float* __restrict__ spartial,
     const float* dm = sh.dmap[sc] + (size_t)b * plane;
     const float* col = sh.color[sc] + (size_t)b * 3 * plane;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    // three pixels of a row per thread and trip: their 36 loads are issued together
+    constexpr int KU = 3;
     for (int v = blockIdx.x; v < Hc; v += gridDim.x) {
-      for (int u = threadIdx.x; u < Wc; u += blockDim.x) {
-        const int idx = v * Wc + u;
-        const float d = dm[idx];
-        const float c0 = __ldg(col + idx), c1 = __ldg(col + plane + idx), c2 = __ldg(col + 2 * plane + idx);
-        s2 += d;
-        if (u + 1 < Wc) {
-          const float e = (fabsf(c0 - __ldg(col + idx + 1)) + fabsf(c1 - __ldg(col + plane + idx + 1)) +
-                           fabsf(c2 - __ldg(col + 2 * plane + idx + 1))) * (1.f / 3.f);
-          s0 += fabsf(d - dm[idx + 1]) * __expf(-e);
+      const bool down = v + 1 < Hc;
+      for (int u0 = threadIdx.x; u0 < Wc; u0 += KU * blockDim.x) {
+        float d[KU], dr[KU], dd[KU], c[KU][3], cr[KU][3], cd[KU][3];
+        bool on[KU], right[KU];
+#pragma unroll
+        for (int k = 0; k < KU; ++k) {
+          const int u = u0 + k * blockDim.x;
+          on[k] = u < Wc;
+          right[k] = u + 1 < Wc;
+          const int idx = v * Wc + (on[k] ? u : 0);
+          d[k] = on[k] ? dm[idx] : 0.f;
+          dr[k] = right[k] ? dm[idx + 1] : 0.f;
+          dd[k] = (on[k] && down) ? dm[idx + Wc] : 0.f;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            c[k][ch] = on[k] ? __ldg(col + ch * plane + idx) : 0.f;
+            cr[k][ch] = right[k] ? __ldg(col + ch * plane + idx + 1) : 0.f;
+            cd[k][ch] = (on[k] && down) ? __ldg(col + ch * plane + idx + Wc) : 0.f;
+          }
         }
-        if (v + 1 < Hc) {
-          const float e = (fabsf(c0 - __ldg(col + idx + Wc)) + fabsf(c1 - __ldg(col + plane + idx + Wc)) +
-                           fabsf(c2 - __ldg(col + 2 * plane + idx + Wc))) * (1.f / 3.f);
-          s1 += fabsf(d - dm[idx + Wc]) * __expf(-e);
+#pragma unroll
+        for (int k = 0; k < KU; ++k) {
+          if (!on[k]) continue;
+          s2 += d[k];
+          if (right[k]) {
+            const float e = (fabsf(c[k][0] - cr[k][0]) + fabsf(c[k][1] - cr[k][1]) + fabsf(c[k][2] - cr[k][2])) * (1.f / 3.f);
+            s0 += fabsf(d[k] - dr[k]) * __expf(-e);
+          }
+          if (down) {
+            const float e = (fabsf(c[k][0] - cd[k][0]) + fabsf(c[k][1] - cd[k][1]) + fabsf(c[k][2] - cd[k][2])) * (1.f / 3.f);
+            s1 += fabsf(d[k] - dd[k]) * __expf(-e);
+          }
         }
       }
     }

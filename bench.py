@@ -340,16 +340,19 @@ def main():
     # the CPU generator and copies it every step (trainer.py:516-517), our API draws it on the device when no noise
     # tensor is supplied.  Everything else the step consumes (frames, decoder features, queries, intrinsics, poses,
     # coarser-scale depth maps) crosses PCIe every step.
-    hb_e2e = {k: v for k, v in hb.items() if not k.startswith("noise")}
-    e2e_bytes = sum(v.numel() * v.element_size() for v in hb_e2e.values())
+    hb_e2e = {k: (torch.zeros_like(v) if k.startswith("noise") else v) for k, v in hb.items()}
+    host_frames, host_other = hp.pack_host(hb_e2e, pin=True)     # what a collate_fn would fill: two pinned buffers
+    noise_floats = sum(hb[k].numel() for k in hb if k.startswith("noise"))
+    # the noise region is part of the flat buffer but is NOT shipped: only the leading part (everything else) is
+    other_ship = hp.other_numel_without(("noise",))
+    e2e_bytes = host_frames.numel() * host_frames.element_size() + other_ship * 4
 
     def enqueue_load(slot):
         """host -> device copy of one batch into input set `slot` on the copy stream (+ fresh device noise)"""
         copy_stream.wait_event(ev_done[slot])          # the previous step on this set has finished reading it
         with torch.cuda.stream(copy_stream):
-            hp.load(hb_e2e, non_blocking=True, slot=slot)
-            for s_ in cfg.scales:
-                hp.slots[slot]["noise%d" % s_].normal_()
+            hp.load_flat(host_frames, host_other[:other_ship], non_blocking=True, slot=slot)
+            hp.noise_region(slot).normal_()             # all scales' noise: one contiguous region, one kernel
             ev_loaded[slot].record(copy_stream)
 
     loss_ring = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]

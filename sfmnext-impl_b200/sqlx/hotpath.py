@@ -59,12 +59,41 @@ class HotPath(torch.nn.Module):
                            ["axisangle%d" % i for i in range(c.S)] + ["translation%d" % i for i in range(c.S)]
         # `num_slots` independent device input sets: with 2, the host->device copy of batch i+1 (on a copy stream)
         # overlaps the step on batch i, as a pinned-memory DataLoader does for the reference (trainer.py:164-171)
-        self.slots = []
+        # Every input of a set is a view into ONE flat device buffer (frames in a second one), so a host batch that
+        # is packed the same way crosses PCIe as two large copies instead of a dozen small ones (load_flat()).
+        shapes = cfg.input_shapes()
+        self.frame_keys = [k for k in shapes if k.startswith("target") or k.startswith("source")]
+        # the tie-break noise planes go last: a caller that draws them on the device ships only the leading part
+        self.other_keys = [k for k in shapes if k not in self.frame_keys and not k.startswith("noise")] + \
+                          [k for k in shapes if k.startswith("noise")]
+
+        def layout(keys):
+            off, table = 0, {}
+            for k in keys:
+                n = 1
+                for d in shapes[k]:
+                    n *= d
+                table[k] = (off, n)
+                off += (n + 63) // 64 * 64          # 256-byte aligned views
+            return table, off
+        self.frame_layout, self.frame_numel = layout(self.frame_keys)
+        self.other_layout, self.other_numel = layout(self.other_keys)
+        self.slots, self.flat = [], []
         for _ in range(num_slots):
-            inp = {k: torch.zeros(v, device=device, dtype=torch.float32) for k, v in cfg.input_shapes().items()}
+            fl = {"frames": torch.zeros(self.frame_numel, device=device, dtype=torch.float32),
+                  "frames_u8": torch.zeros(self.frame_numel, device=device, dtype=torch.uint8),
+                  "other": torch.zeros(self.other_numel, device=device, dtype=torch.float32)}
+            inp = {}
+            for k in self.frame_keys:
+                o, n = self.frame_layout[k]
+                inp[k] = fl["frames"].narrow(0, o, n).view(shapes[k])
+            for k in self.other_keys:
+                o, n = self.other_layout[k]
+                inp[k] = fl["other"].narrow(0, o, n).view(shapes[k])
             for k in self.grad_inputs:
                 inp[k].requires_grad_(True)
             self.slots.append(inp)
+            self.flat.append(fl)
         self.inp = self.slots[0]
         self.use_graph = use_graph
         self.graphs = [None] * num_slots
@@ -91,6 +120,45 @@ class HotPath(torch.nn.Module):
                     inp[k].mul_(1.0 / 255.0)
                 n += v.numel() * v.element_size()
         return n
+
+    def pack_host(self, host_batch, pin=True):
+        """Pack a host batch dict into the flat layout of the device input sets: (frames, other) where `frames` is
+        uint8 when the batch carries uint8 frames (else float32) and `other` is float32.  A data loader would
+        collate straight into these buffers."""
+        u8 = all(host_batch[k].dtype == torch.uint8 for k in self.frame_keys)
+        frames = torch.zeros(self.frame_numel, dtype=torch.uint8 if u8 else torch.float32)
+        other = torch.zeros(self.other_numel, dtype=torch.float32)
+        for k in self.frame_keys:
+            o, n = self.frame_layout[k]
+            frames[o:o + n] = host_batch[k].reshape(-1)
+        for k in self.other_keys:
+            o, n = self.other_layout[k]
+            other[o:o + n] = host_batch[k].reshape(-1).float()
+        if pin:
+            frames, other = frames.pin_memory(), other.pin_memory()
+        return frames, other
+
+    def other_numel_without(self, prefixes=("noise",)):
+        """Length of the leading part of the flat `other` buffer that excludes the trailing keys with these prefixes."""
+        first = [self.other_layout[k][0] for k in self.other_keys if k.startswith(tuple(prefixes))]
+        return min(first) if first else self.other_numel
+
+    def noise_region(self, slot=0):
+        """The contiguous tail of the flat buffer holding every scale's tie-break noise (one normal_() fills it)."""
+        return self.flat[slot]["other"][self.other_numel_without(("noise",)):]
+
+    def load_flat(self, frames, other, non_blocking=True, slot=0):
+        """Two host->device copies for a whole batch (pack_host layout) plus, for uint8 frames, ONE scaling kernel;
+        returns the bytes copied."""
+        fl = self.flat[slot]
+        with torch.no_grad():
+            fl["other"][:other.numel()].copy_(other, non_blocking=non_blocking)
+            if frames.dtype == torch.uint8:
+                fl["frames_u8"].copy_(frames, non_blocking=non_blocking)
+                torch.mul(fl["frames_u8"], 1.0 / 255.0, out=fl["frames"])
+            else:
+                fl["frames"].copy_(frames, non_blocking=non_blocking)
+        return frames.numel() * frames.element_size() + other.numel() * other.element_size()
 
     # ------------------------------------------------------------------ one eager step
     def _centers(self, summary):

@@ -6,7 +6,7 @@
 // With M = batch <= 16 these layers are bound by reading (forward, d_input) and writing (d_weight) the weight
 // matrices once -- 8.4 MB for the first layer at Q = 64 -- which cuBLAS does through ~12 small-M GEMM / split-K /
 // elementwise launches per direction.  Here: one CTA per output row streams the row with 128-bit loads against all
-// samples at once; 4 launches forward, 10 backward, exact fp32.
+// samples at once; 4 launches forward, 7 backward, exact fp32, no atomics.
 #include "common.cuh"
 
 namespace sqlx {
@@ -100,31 +100,63 @@ __global__ void __launch_bounds__(128) head_linear_bwd_w_kernel(const float* __r
   }
 }
 
-// dx[b,k] += sum_{n in chunk} dz[b,n] W[n,k]; grid (ceil(K/128), chunks); dx zeroed by the caller
-constexpr int kHeadChunk = 32;
-__global__ void __launch_bounds__(128) head_linear_bwd_x_kernel(const float* __restrict__ dz, const float* __restrict__ W,
-                                                                int B, int N, int K, float* __restrict__ dx) {
-  __shared__ float sdz[kHeadMaxB][kHeadChunk];
-  const int k = blockIdx.x * 128 + threadIdx.x;
-  const int n0 = blockIdx.y * kHeadChunk, n1 = min(N, n0 + kHeadChunk);
-  for (int i = threadIdx.x; i < kHeadMaxB * kHeadChunk; i += 128) {
-    const int b = i / kHeadChunk, j = i - b * kHeadChunk;
-    sdz[b][j] = (b < B && n0 + j < n1) ? __ldg(dz + (size_t)b * N + n0 + j) : 0.f;
+// dx[b,k] = sum_n dz[b,n] W[n,k].  One CTA per 32 input features k (lane = k: W rows are read as coalesced 128-byte
+// segments); the 8 warps split the output rows n, dz is staged once per CTA as [n][16 samples] (128-bit broadcast
+// loads), partial sums meet in shared memory: no atomics, fixed summation order.
+constexpr int kHeadXWarps = 8;
+__global__ void __launch_bounds__(32 * kHeadXWarps) head_linear_bwd_x_kernel(const float* __restrict__ dz,
+                                                                             const float* __restrict__ W, int B, int N,
+                                                                             int K, float* __restrict__ dx) {
+  extern __shared__ __align__(16) float sdz[];             // [N][16]
+  __shared__ float part[kHeadXWarps][kHeadMaxB][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane;
+  for (int base = threadIdx.x; base < N * kHeadMaxB; base += 8 * blockDim.x) {    // eight loads in flight per trip
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = base + j * blockDim.x, n = i >> 4, b = i & 15;
+      v[j] = (i < N * kHeadMaxB && b < B) ? __ldg(dz + (size_t)b * N + n) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = base + j * blockDim.x;
+      if (i < N * kHeadMaxB) sdz[i] = v[j];
+    }
   }
   __syncthreads();
-  if (k >= K) return;
   float acc[kHeadMaxB];
 #pragma unroll
   for (int b = 0; b < kHeadMaxB; ++b) acc[b] = 0.f;
-#pragma unroll 8
-  for (int n = n0; n < n1; ++n) {
-    const float wv = __ldg(W + (size_t)n * K + k);
+  const int per = (N + kHeadXWarps - 1) / kHeadXWarps;
+  const int n0 = warp * per, n1 = min(N, n0 + per);
+  const bool kin = k < K;
+  for (int nb = n0; nb < n1; nb += 8) {
+    float wv[8];
 #pragma unroll
-    for (int b = 0; b < kHeadMaxB; ++b) acc[b] = fmaf(sdz[b][n - n0], wv, acc[b]);
+    for (int j = 0; j < 8; ++j) wv[j] = (kin && nb + j < n1) ? __ldg(W + (size_t)(nb + j) * K + k) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (nb + j >= n1) break;
+      const float4* zr = reinterpret_cast<const float4*>(sdz + (size_t)(nb + j) * kHeadMaxB);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 z = zr[q];
+        acc[4 * q] = fmaf(z.x, wv[j], acc[4 * q]); acc[4 * q + 1] = fmaf(z.y, wv[j], acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(z.z, wv[j], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(z.w, wv[j], acc[4 * q + 3]);
+      }
+    }
   }
 #pragma unroll
-  for (int b = 0; b < kHeadMaxB; ++b)
-    if (b < B) atomicAdd(dx + (size_t)b * K + k, acc[b]);
+  for (int b = 0; b < kHeadMaxB; ++b) part[warp][b][lane] = acc[b];
+  __syncthreads();
+  for (int i = threadIdx.x; i < B * 32; i += blockDim.x) {
+    const int b = i >> 5, l = i & 31;
+    float t = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < kHeadXWarps; ++w2) t += part[w2][b][l];
+    if (blockIdx.x * 32 + l < K) dx[(size_t)b * K + blockIdx.x * 32 + l] = t;
+  }
 }
 
 // ---- bin centres (depth_decoder_QTR.py:51-66, norm == 'linear'); one block of 256 threads per sample, D <= 256
@@ -217,9 +249,15 @@ extern "C" int sqlx_head_linear_bwd(const float* W, const float* x, const float*
     if (int e = check_launch("head_linear_bwd_w_kernel")) return e;
   }
   if (dx) {
-    if (cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * K, st) != cudaSuccess) return check_launch("cudaMemsetAsync(dx)");
+    const size_t smem = sizeof(float) * (size_t)N * kHeadMaxB;
+    SQLX_REQUIRE(smem <= 160 * 1024, "out_features %d too large for the d_input kernel", N);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      cudaFuncSetAttribute(head_linear_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured = smem;
+    }
     ProfScope prof("head_linear_bwd_kernel", st);
-    head_linear_bwd_x_kernel<<<dim3(ceil_div(K, 128), ceil_div(N, kHeadChunk)), 128, 0, st>>>(dz, W, B, N, K, dx);
+    head_linear_bwd_x_kernel<<<ceil_div(K, 32), 32 * kHeadXWarps, smem, st>>>(dz, W, B, N, K, dx);
     if (int e = check_launch("head_linear_bwd_x_kernel")) return e;
   }
   return SQLX_OK;

@@ -55,6 +55,65 @@ __device__ __forceinline__ float blend4(const float* __restrict__ lr, int w, con
          ty.l1 * (tx.l0 * __ldg(r1 + tx.i0) + tx.l1 * __ldg(r1 + tx.i1));   // same expression as upsample_at
 }
 
+// Integer upsampling factor (1 or even): one work item = (low-resolution cell (i, j), one row of the F x F block of
+// pixels whose first bilinear tap is that cell; the whole block for F <= 2) -- four loads per item, the tap weights
+// (r + .5) / F are exactly the ones up_tap() derives from src = (v + .5) / F - .5 for these factors.  Writes d_up and
+// returns this thread's sum of 1 / d_up.  F = 0: runtime factor `fr` (same arithmetic, loops not unrolled).
+template <int F>
+__device__ __forceinline__ float upsample_blocks(const float* __restrict__ lr, float* __restrict__ dup, int h, int w,
+                                                 int H, int W, int fr = 0) {
+  const int f = F > 0 ? F : fr;
+  const float rf = 1.f / (float)f;
+  const int half = f >> 1;
+  const int rows_per_item = f <= 2 ? f : 1;
+  const int groups = f / rows_per_item;
+  const int items = h * w * groups;
+  float s1 = 0.f;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+    const int cell = it / groups, grp = it - cell * groups;
+    const int i = cell / w, j = cell - i * w;
+    const int i1 = min(i + 1, h - 1), j1 = min(j + 1, w - 1);
+    const float a = __ldg(lr + i * w + j), bq = __ldg(lr + i * w + j1);
+    const float c = __ldg(lr + i1 * w + j), dq = __ldg(lr + i1 * w + j1);
+    if (F > 1 && i > 0 && j > 0 && i < h - 1 && j < w - 1) {
+      // interior cell: compile-time weights, no range checks
+#pragma unroll
+      for (int rr = 0; rr < (F <= 2 ? F : 1); ++rr) {
+        const int r = grp * rows_per_item + rr;
+        const float wy = ((float)r + 0.5f) * rf;
+        float* row = dup + (size_t)(F * i + half + r) * W + (F * j + half);
+#pragma unroll
+        for (int q = 0; q < F; ++q) {
+          const float wx = ((float)q + 0.5f) * rf;
+          const float d = (1.f - wy) * ((1.f - wx) * a + wx * bq) + wy * ((1.f - wx) * c + wx * dq);   // as upsample_at
+          row[q] = d;
+          s1 += __fdividef(1.f, d);
+        }
+      }
+      continue;
+    }
+    // border cells (and the runtime-factor path): the first cell row / column also owns the clamped pixels before it
+    int r_lo = grp * rows_per_item, r_hi = r_lo + rows_per_item;
+    if (i == 0 && grp == 0) r_lo = -half;
+    const int c_lo = (j == 0) ? -half : 0;
+    for (int r = r_lo; r < r_hi; ++r) {
+      const int v = f * i + half + r;
+      if (v >= H) break;
+      const float wy = f == 1 ? 0.f : fmaxf(((float)r + 0.5f) * rf, 0.f);
+      float* row = dup + (size_t)v * W;
+      for (int q = c_lo; q < f; ++q) {
+        const int u = f * j + half + q;
+        if (u >= W) break;
+        const float wx = f == 1 ? 0.f : fmaxf(((float)q + 0.5f) * rf, 0.f);
+        const float d = (1.f - wy) * ((1.f - wx) * a + wx * bq) + wy * ((1.f - wx) * c + wx * dq);
+        row[u] = d;
+        s1 += __fdividef(1.f, d);
+      }
+    }
+  }
+  return s1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward: depth statistics + pose matrices
 // ------------------------------------------------------------------------------------------------
@@ -80,40 +139,12 @@ __global__ void ms_stats_pose_kernel(MsShapes sh, MsPose ps, int rescale, float*
       // Integer upsampling factor (1, 2, 4, ...): one thread per low-resolution cell (i, j) produces the f x f block of
       // pixels whose first bilinear tap is that cell -- four loads per BLOCK, three FMAs per pixel.  The tap weights
       // (r + .5) / f are exactly the ones up_tap() derives from src = (v + .5) / f - .5 for these factors.
-      const float rf = 1.f / (float)f;
-      const int half = f >> 1;
-      // work item = (cell, group of rows): whole block for f <= 2, one row of the block for larger factors (so a
-      // thread never walks more than f pixels... 3f/2 on the frame border)
-      const int rows_per_item = f <= 2 ? f : 1;
-      const int groups = f / rows_per_item;
-      const int items = h * w * groups;
-      for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
-        const int cell = it / groups, grp = it - cell * groups;
-        const int i = cell / w, j = cell - i * w;
-        const int i1 = min(i + 1, h - 1), j1 = min(j + 1, w - 1);
-        const float a = __ldg(lr + i * w + j), bq = __ldg(lr + i * w + j1);
-        const float c = __ldg(lr + i1 * w + j), dq = __ldg(lr + i1 * w + j1);
-        // rows f*i + half + r, r = 0..f-1; the first cell row / column also owns the clamped pixels before it
-        int r_lo = grp * rows_per_item, r_hi = r_lo + rows_per_item;
-        if (i == 0 && grp == 0) r_lo = -half;
-        const int c_lo = (j == 0) ? -half : 0;
-        for (int r = r_lo; r < r_hi; ++r) {
-          const int v = f * i + half + r;
-          if (v >= H) break;
-          const float wy = f == 1 ? 0.f : fmaxf(((float)r + 0.5f) * rf, 0.f);
-          const float top = (1.f - wy), bot = wy;
-          float* row = dup + (size_t)v * W;
-#pragma unroll 4
-          for (int q = c_lo; q < f; ++q) {
-            const int u = f * j + half + q;
-            if (u >= W) break;
-            const float wx = f == 1 ? 0.f : fmaxf(((float)q + 0.5f) * rf, 0.f);
-            const float d = top * ((1.f - wx) * a + wx * bq) + bot * ((1.f - wx) * c + wx * dq);
-            row[u] = d;
-            s1 += __fdividef(1.f, d);
-          }
-        }
-      }
+      if (f == 2) s1 = upsample_blocks<2>(lr, dup, h, w, H, W);
+      else if (f == 4) s1 = upsample_blocks<4>(lr, dup, h, w, H, W);
+      else if (f == 8) s1 = upsample_blocks<8>(lr, dup, h, w, H, W);
+      else if (f == 16) s1 = upsample_blocks<16>(lr, dup, h, w, H, W);
+      else if (f == 1) s1 = upsample_blocks<1>(lr, dup, h, w, H, W);
+      else s1 = upsample_blocks<0>(lr, dup, h, w, H, W, f);
     } else {
       for (int u0 = 0; u0 < W; u0 += kKC * blockDim.x) {
         UpTap tx[kKC];
@@ -455,6 +486,38 @@ __device__ __forceinline__ float adjoint_even(const float* __restrict__ gp, cons
   constexpr float rf = 1.f / (float)F;
   const int vb = F * i - half, ub = F * j - half;
   float acc = 0.f;
+  if (i > 0 && i < h - 1 && j > 0 && j < w - 1) {
+    // interior cell (all but the map's border ring): the whole footprint is inside the frame and every weight is the
+    // compile-time tent value -- two loads and two FMAs per pixel, addresses are base + constant offsets
+#pragma unroll
+    for (int c = 0; c < 2 * F / TPC; ++c) {
+      const int tu = sub + c * TPC;
+      const float wx = tu < F ? ((float)tu + 0.5f) * rf : ((float)(2 * F - tu) - 0.5f) * rf;
+      const float* gcol = gp + (size_t)vb * W + (ub + tu);
+      const float* qcol = qp + (size_t)vb * W + (ub + tu);
+      // rows in batches of (at most) 8: 16 loads in flight per thread keeps the kernel at 64 registers / 4 CTAs per SM
+      // (with the whole 2F-row column in registers the launch ran 19 latency-bound waves at 2 CTAs per SM)
+      constexpr int RB = 2 * F < 8 ? 2 * F : 8;
+      float col = 0.f;
+#pragma unroll
+      for (int t0 = 0; t0 < 2 * F; t0 += RB) {
+        float gv[RB], qv[RB];
+#pragma unroll
+        for (int t = 0; t < RB; ++t) {
+          gv[t] = gcol[(t0 + t) * W];
+          qv[t] = rescale ? qcol[(t0 + t) * W] : 0.f;
+        }
+#pragma unroll
+        for (int t = 0; t < RB; ++t) {
+          const int tv = t0 + t;
+          const float wy = tv < F ? ((float)tv + 0.5f) * rf : ((float)(2 * F - tv) - 0.5f) * rf;
+          col = fmaf(wy, fmaf(-gs, qv[t], gv[t]), col);
+        }
+      }
+      acc = fmaf(wx, col, acc);
+    }
+    return acc;
+  }
 #pragma unroll
   for (int c = 0; c < 2 * F / TPC; ++c) {
     const int tu = sub + c * TPC;
@@ -464,28 +527,22 @@ __device__ __forceinline__ float adjoint_even(const float* __restrict__ gp, cons
     if ((j == 0 && u < half) || (j == w - 1 && tu >= F)) wx = 1.f;
     const float* gcol = gp + u;
     const float* qcol = qp + u;
-    float gv[2 * F], qv[2 * F];
-#pragma unroll
-    for (int tv = 0; tv < 2 * F; ++tv) {
-      const int v = vb + tv;
-      const bool in = v >= 0 && v < H;
-      gv[tv] = in ? gcol[v * W] : 0.f;
-      qv[tv] = (in && rescale) ? qcol[v * W] : 0.f;
-    }
     float col = 0.f;
-#pragma unroll
-    for (int tv = 0; tv < 2 * F; ++tv) {
+#pragma unroll 4
+    for (int tv = 0; tv < 2 * F; ++tv) {      // border ring of the map only: not batched
       const int v = vb + tv;
+      if (v < 0 || v >= H) continue;
       float wy = tv < F ? ((float)tv + 0.5f) * rf : ((float)(2 * F - tv) - 0.5f) * rf;
       if ((i == 0 && v < half) || (i == h - 1 && tv >= F)) wy = 1.f;
-      col = fmaf(wy, fmaf(-gs, qv[tv], gv[tv]), col);
+      const float gq = rescale ? qcol[v * W] : 0.f;
+      col = fmaf(wy, fmaf(-gs, gq, gcol[v * W]), col);
     }
     acc = fmaf(wx, col, acc);
   }
   return acc;
 }
 
-__global__ void ms_upsample_adjoint_kernel(MsShapes sh, MsGrads g, MsAdjoint ad, int rescale,
+__global__ void __launch_bounds__(256, 4) ms_upsample_adjoint_kernel(MsShapes sh, MsGrads g, MsAdjoint ad, int rescale,
                                            const float* __restrict__ g_stats) {
   const int sc = blockIdx.y;
   const int B = sh.B, H = sh.H, W = sh.W, h = sh.h[sc], w = sh.w[sc];

@@ -7,6 +7,7 @@ The fixtures are small seeded synthetic cases fed through
   - networks.Depth_Decoder_QueryTr / Lite_Depth_Decoder_QueryTr forward (depth_decoder_QTR.py:36-74)
   - layers.SSIM, BackprojectDepth, Project3D, get_smooth_loss, transformation_from_parameters
   - finetune/loss.py SILogLoss
+  - trainer_indoor.Trainer.generate_images_pred + compute_losses_with_occ  (trainer_indoor.py:512-719)
 and store inputs, outputs and autograd gradients.
 """
 import os
@@ -224,9 +225,74 @@ def module_case(name, seed, B, H, W):
     print(name, "ssim mean", float(ss.mean()), "silog", float(sil))
 
 
+def indoor_case(name, seed, B, H, W, extra_args=()):
+    """trainer_indoor.Trainer.generate_images_pred + compute_losses_with_occ (trainer_indoor.py:512-599, 615-719)
+    with --use_improved_mini_reproj_loss, scales = [0]."""
+    ref = ref_shim.load()
+    import trainer_indoor
+    g = torch.Generator().manual_seed(seed)
+    base = ref_shim.make_trainer(B, H, W, scales=[0], frame_ids=[0, -1, 1],
+                                 extra_args=["--use_improved_mini_reproj_loss"] + list(extra_args))
+    T = trainer_indoor.Trainer.__new__(trainer_indoor.Trainer)
+    T.__dict__.update(base.__dict__)
+    fids = T.opt.frame_ids
+    frames = smooth_images(g, B, H, W, 3)
+    # a dark band in one source so that valid_mask (mean |pred| > 1e-3) is exercised
+    frames[0][:, :, H // 3:H // 3 + 5, W // 4:W // 4 + 12] = 0.0
+    K, inv_K = kitti_K(B, H, W)
+    inputs = {("K", 0): K, ("inv_K", 0): inv_K, ("color", 0, 0): frames[1], ("color", -1, 0): frames[0],
+              ("color", 1, 0): frames[2]}
+    outputs, leaves = {}, {}
+    d = depth_like(g, B, H // 2, W // 2).requires_grad_(True)
+    outputs[("disp", 0)] = d
+    leaves["disp0"] = d
+    for f in fids[1:]:
+        # depth of the reference frames: close to the target depth (the consistency term compares them)
+        dr = (F.interpolate(d.detach(), [H, W], mode="bilinear", align_corners=False) *
+              (1.0 + 0.2 * (torch.rand(B, 1, H, W, generator=g) - 0.5))).requires_grad_(True)
+        outputs[("depth_ref", f, 0)] = dr
+        leaves["depth_ref_%d" % f] = dr
+        aa = (0.01 * torch.randn(B, 1, 1, 3, generator=g)).requires_grad_(True)
+        tr = (0.3 * torch.randn(B, 1, 1, 3, generator=g)).requires_grad_(True)
+        outputs[("axisangle", 0, f)] = aa
+        outputs[("translation", 0, f)] = tr
+        outputs[("cam_T_cam", 0, f)] = ref.layers.transformation_from_parameters(aa[:, 0], tr[:, 0], invert=(f < 0))
+        leaves["axisangle_%d" % f] = aa
+        leaves["translation_%d" % f] = tr
+    S = 2
+    noise_seed = seed + 1000
+    torch.manual_seed(noise_seed)
+    noise = torch.randn(B, 1 if T.opt.avg_reprojection else S, H, W)
+    T.generate_images_pred(inputs, outputs)
+    torch.manual_seed(noise_seed)
+    total, losses = T.compute_losses_with_occ(inputs, outputs)
+    total = total / T.num_scales                                   # trainer_indoor.py:413
+    names = list(leaves.keys())
+    grads = torch.autograd.grad(total, [leaves[n] for n in names], allow_unused=True)
+    rec = {"B": B, "H": H, "W": W, "K": K.numpy(), "inv_K": inv_K.numpy(), "noise": noise.numpy(),
+           "reg_wt": np.float32(T.opt.reg_wt), "avg_reprojection": int(T.opt.avg_reprojection),
+           "disable_automasking": int(T.opt.disable_automasking), "no_ssim": int(T.opt.no_ssim),
+           "out_loss": total.detach().numpy(), "out_loss_s0": losses["loss/0"].detach().numpy(),
+           "out_depth_s0": outputs[("depth", 0, 0)].detach().numpy()}
+    for f in fids:
+        rec["color_%s" % f] = inputs[("color", f, 0)].numpy()
+    for f in fids[1:]:
+        rec["out_color_%s" % f] = outputs[("color", f, 0)].detach().numpy()
+        rec["out_pred_dep_%s" % f] = outputs[("pred_dep", f, 0)].detach().numpy()
+    for n, gr in zip(names, grads):
+        rec["in_" + n] = leaves[n].detach().numpy()
+        rec["grad_" + n] = (gr if gr is not None else torch.zeros_like(leaves[n])).numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
+    print(name, "loss", float(total))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "indoor":      # only the fixtures added for SURVEY 8f row N4
+        indoor_case("indoor_occ", 41, B=2, H=48, W=80)
+        indoor_case("indoor_occ_avg", 42, B=1, H=48, W=80, extra_args=["--avg_reprojection"])
+        return
     photometric_case("photo_mono_s0", 11, B=2, H=48, W=80, scales=[0])
     photometric_case("photo_mono_ms4", 12, B=1, H=64, W=96, scales=[0, 1, 2, 3])
     photometric_case("photo_stereo_s0", 13, B=2, H=48, W=80, scales=[0], use_stereo=True)
@@ -237,6 +303,8 @@ def main():
     decoder_case("decoder_full", 21, lite=False, B=2, E=32, h=24, w=40, P=8, Q=12, D=16, min_val=0.001, max_val=80.0)
     decoder_case("decoder_lite", 22, lite=True, B=2, E=32, h=32, w=32, P=8, Q=16, D=24, min_val=0.01, max_val=80.0)
     module_case("modules", 31, B=2, H=40, W=72)
+    indoor_case("indoor_occ", 41, B=2, H=48, W=80)
+    indoor_case("indoor_occ_avg", 42, B=1, H=48, W=80, extra_args=["--avg_reprojection"])
 
 
 if __name__ == "__main__":

@@ -50,6 +50,33 @@ def photo_case(name, dtype=torch.float32, device="cpu"):
     return kw, leaves, z, fids
 
 
+INDOOR_CASES = ["indoor_occ", "indoor_occ_avg"]
+
+
+def indoor_case(name, dtype=torch.float32, device="cpu"):
+    """Golden indoor case (trainer_indoor.py compute_losses_with_occ) -> kwargs for oracle.indoor_losses /
+    sqlx.indoor_losses + the leaves whose gradients the fixture holds."""
+    z = load_npz(name)
+    t = lambda a: torch.from_numpy(np.asarray(a)).to(device=device, dtype=dtype)  # noqa: E731
+    leaves = {"disp0": t(z["in_disp0"]).requires_grad_(True)}
+    sources, ref_depths, poses = [], [], []
+    for f in (-1, 1):
+        sources.append(t(z["color_%d" % f]))
+        dr = t(z["in_depth_ref_%d" % f]).requires_grad_(True)
+        aa = t(z["in_axisangle_%d" % f]).requires_grad_(True)
+        tr = t(z["in_translation_%d" % f]).requires_grad_(True)
+        leaves["depth_ref_%d" % f] = dr
+        leaves["axisangle_%d" % f] = aa
+        leaves["translation_%d" % f] = tr
+        ref_depths.append(dr)
+        poses.append({"axisangle": aa, "translation": tr, "invert": f < 0})
+    kw = dict(disp=leaves["disp0"], target=t(z["color_0"]), sources=sources, ref_depths=ref_depths, K=t(z["K"]),
+              inv_K=t(z["inv_K"]), poses=poses, noise=t(z["noise"]), height=int(z["H"]), width=int(z["W"]),
+              reg_wt=float(z["reg_wt"]), no_ssim=bool(z["no_ssim"]), avg_reprojection=bool(z["avg_reprojection"]),
+              disable_automasking=bool(z["disable_automasking"]))
+    return kw, leaves, z
+
+
 def smooth_images(g, B, H, W, n_frames, shift=2.5, noise=0.02):
     base = torch.rand(B, 3, H // 8 + 2, W // 8 + 2, generator=g)
     big = F.interpolate(base, size=(H + 16, W + 16), mode="bicubic", align_corners=False).clamp(0, 1)

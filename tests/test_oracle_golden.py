@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import sqldepth_oracle as O
-from _cases import PHOTO_CASES, load_npz, photo_case
+from _cases import INDOOR_CASES, PHOTO_CASES, indoor_case, load_npz, photo_case
 
 
 def _t(a):
@@ -30,6 +30,26 @@ def test_photometric_matches_reference(name):
     for i, f in enumerate(fids[1:]):
         np.testing.assert_allclose(out[("sample", i, s0)].detach().numpy(), z["out_sample_%s_s%d" % (f, s0)], atol=2e-6)
         np.testing.assert_allclose(out[("color", i, s0)].detach().numpy(), z["out_color_%s_s%d" % (f, s0)], atol=2e-5)
+    names = list(leaves)
+    grads = torch.autograd.grad(out["loss"], [leaves[n] for n in names], allow_unused=True)
+    for n, g in zip(names, grads):
+        ref = z["grad_" + n]
+        g = np.zeros_like(ref) if g is None else g.numpy()
+        scale = max(np.abs(ref).max(), 1e-12)
+        assert np.abs(g - ref).max() / scale < 2e-3, n
+
+
+@pytest.mark.parametrize("name", INDOOR_CASES)
+def test_indoor_losses_match_reference(name):
+    """oracle.indoor_losses vs trainer_indoor.py generate_images_pred + compute_losses_with_occ."""
+    kw, leaves, z = indoor_case(name)
+    out = O.indoor_losses(**kw)
+    assert abs(float(out["loss"]) - float(z["out_loss"])) < 2e-7
+    assert abs(float(out["loss/0"]) - float(z["out_loss_s0"])) < 2e-7
+    np.testing.assert_allclose(out[("depth", 0, 0)].detach().numpy(), z["out_depth_s0"], rtol=1e-6, atol=1e-6)
+    for i, f in enumerate((-1, 1)):
+        np.testing.assert_allclose(out[("color", i, 0)].detach().numpy(), z["out_color_%d" % f], atol=2e-5)
+        np.testing.assert_allclose(out[("pred_dep", i, 0)].detach().numpy(), z["out_pred_dep_%d" % f], rtol=2e-5, atol=2e-4)
     names = list(leaves)
     grads = torch.autograd.grad(out["loss"], [leaves[n] for n in names], allow_unused=True)
     for n, g in zip(names, grads):

@@ -125,6 +125,32 @@ int sqlx_photo_bwd(const sqlx_photo_desc* desc, const float* depth_lr, const flo
                    const uint8_t* argmin, const float* ssim_coef, const float* g_loss, float scale,
                    float* d_depth_lr, float* d_T, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Indoor variant: generate_images_pred + the photometric part of compute_losses_with_occ,
+ * trainer_indoor.py:512-599 and 615-699 (--use_improved_mini_reproj_loss), for one loss scale.  On top of
+ * sqlx_photo_fwd, per source f and pixel:
+ *   pd     = grid_sample(depth_ref_f, pix_coords, border, align_corners=True)         trainer_indoor.py:583-587
+ *   valid  = mean_c |warped_f| > 1e-3                                                 :636
+ *   diff   = |d - pd| / (d + pd),  d = the upsampled depth                            :642-643
+ *   weight = 1 - sqrt(1 - (diff - 1)^2)   (detached)                                  :647-648
+ *   reprojection_f *= weight * valid  before the mean / minimum over candidates       :650-651, 690
+ *   ref_depths  host array of S device pointers, each [B,1,H,W]: outputs[("depth_ref",f,0)]
+ *   sums [2]    sums[0] = sum over pixels of the per-pixel minimum, sums[1] = sum over sources and pixels of
+ *               diff * valid  (the caller forms mean(min) + reg_wt * sums[1] / (S*B*H*W), :698-699)
+ * The exported SSIM coefficients already carry the per-pixel weight.  Backward: g_sums [2] device (upstream
+ * gradients of sums[0], sums[1]); d_depth_lr accumulated (caller zeroes), d_T overwritten, d_ref_depths[f] [B,1,H,W]
+ * accumulated with atomics (caller zeroes): the source depths are network outputs too (:374-377). */
+size_t sqlx_photo_occ_workspace_bytes(const sqlx_photo_desc* desc);
+int sqlx_photo_occ_fwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
+                       const float* const* sources_rgba, const float* const* ref_depths, const float* K,
+                       const float* inv_K, const float* T, const float* identity, const float* noise,
+                       float* sums, uint8_t* argmin, float* ssim_coef, void* workspace, size_t workspace_bytes,
+                       void* stream);
+int sqlx_photo_occ_bwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
+                       const float* const* sources_rgba, const float* const* ref_depths, const float* K,
+                       const float* inv_K, const float* T, const uint8_t* argmin, const float* ssim_coef,
+                       const float* g_sums, float scale, float* d_depth_lr, float* d_T, float* const* d_ref_depths,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* Warp only (materialises what Trainer.log reads): sample [B,H,W,2] normalised grid (layers.py:255-257),
  * color [B,3,H,W] warped source (trainer.py:431-435), depth_up [B,1,H,W] (trainer.py:402). Any output may be NULL. */
 int sqlx_warp_fwd(const float* depth_lr, const float* source, const float* K, const float* inv_K,

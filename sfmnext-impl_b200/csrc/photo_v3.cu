@@ -222,7 +222,26 @@ struct PhotoFwdParams {
   float* partial;      // [gridDim.z*gridDim.y*gridDim.x]
   uint8_t* argmin;
   float* coef;         // optional [B][S][3 ch][3][H][W]: d SSIM / d(mean_x, E[x^2], E[xy])
+  // indoor variant (OCC kernels only; trainer_indoor.py:583-587, 636-651)
+  const float* ref[SQLX_MAX_SOURCES];    // depth of each source frame, planar [B,H,W]
+  float* partial_reg;                    // per-CTA partial sums of diff_depth * valid_mask
 };
+
+// Depth-consistency terms of the indoor loss at one pixel (trainer_indoor.py:636-648): pd = the source frame's depth
+// sampled at the projected position, diff = |d - pd| / (d + pd), weight = (1 - sqrt(1 - (diff - 1)^2)) * valid.
+struct OccTerm {
+  float pd, diff, weight;
+  bool valid;
+};
+__device__ __forceinline__ OccTerm occ_term(float d, float pd, float r, float g, float b) {
+  OccTerm o;
+  o.pd = pd;
+  o.valid = (fabsf(r) + fabsf(g) + fabsf(b)) / 3.f > 1e-3f;
+  o.diff = fabsf(d - pd) / (d + pd);
+  const float e = o.diff - 1.f;
+  o.weight = o.valid ? 1.f - sqrtf(1.f - e * e) : 0.f;
+  return o;
+}
 
 template <int R, int TH, int TW, int NT, bool MERGED = false>
 struct Fwd3Cfg {
@@ -238,7 +257,7 @@ struct Fwd3Cfg {
   static_assert((TH * TW) % NT == 0 && NT % TW == 0 && NT >= PH + PW, "tile / block shape");
 };
 
-template <int R, int TH, int TW, int NT, int MINB, bool MERGED>
+template <int R, int TH, int TW, int NT, int MINB, bool MERGED, bool OCC = false>
 __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdParams p) {
   using C = Fwd3Cfg<R, TH, TW, NT, MERGED>;
   constexpr int PPT = C::PPT;
@@ -390,14 +409,14 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
     }
   }
 
-  float avg_acc[PPT];
+  float avg_acc[PPT], reg_acc[PPT];
 #pragma unroll
-  for (int k = 0; k < PPT; ++k) avg_acc[k] = 0.f;
+  for (int k = 0; k < PPT; ++k) { avg_acc[k] = 0.f; reg_acc[k] = 0.f; }
 
   for (int s = 0; s < S; ++s) {
+    const CamM cam = compose_camera(cams[s]);
     {   // warp source s into the three shared planes (R halo included), two elements per trip
       const float4* src = p.src[s] + (size_t)b * plane;
-      const CamM cam = compose_camera(cams[s]);
       const float eps = p.d.eps;
       float4 ta[2], tb[2], tc[2], td[2];
       float fx[2], fy[2];
@@ -422,6 +441,29 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
           });
     }
     __syncthreads();
+
+    float occ_w[PPT];
+    if (OCC) {   // own pixels: sample the source frame's depth at the projected position (4 scalar taps)
+      const float* rd = p.ref[s] + (size_t)b * plane;
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const int o = (prow0 + k + R) * C::LD + pcol + R;
+        const float d = dpl[o];
+        float pu, pv;
+        project_composed(cam, (float)(u0 + pcol), (float)(v0 + prow0 + k), d, p.d.eps, pu, pv);
+        const Taps4 t = make_taps4(pu, pv, H, W);
+        const bool live = col_in && (v0 + prow0 + k < H);
+        float pd = d;
+        if (live) {
+          const float* q = rd + t.o;
+          pd = (__ldg(q) * (1.f - t.fx) + __ldg(q + 1) * t.fx) * (1.f - t.fy) +
+               (__ldg(q + W) * (1.f - t.fx) + __ldg(q + W + 1) * t.fx) * t.fy;
+        }
+        const OccTerm oc = occ_term(d, pd, wp[o], wp[C::PLANE + o], wp[2 * C::PLANE + o]);
+        occ_w[k] = oc.weight;
+        if (live && oc.valid) reg_acc[k] += oc.diff;
+      }
+    }
 
     float ssim_acc[PPT], l1_acc[PPT];
 #pragma unroll
@@ -469,9 +511,10 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
             // torch.clamp backward: zero outside [0,1] (NaN -> 0); branch-free
             const bool ok = val >= 0.f && val <= 1.f;
             const float dS_dn = -0.5f * inv_d, dS_dd = 0.5f * q * inv_d;
-            const float gmx = ok ? dS_dn * (2.f * myk * (n2 - n1)) + dS_dd * (2.f * mx * (d2 - d1)) : 0.f;
-            const float gxx = ok ? dS_dd * d1 : 0.f;
-            const float gxy = ok ? dS_dn * 2.f * n1 : 0.f;
+            float gmx = ok ? dS_dn * (2.f * myk * (n2 - n1)) + dS_dd * (2.f * mx * (d2 - d1)) : 0.f;
+            float gxx = ok ? dS_dd * d1 : 0.f;
+            float gxy = ok ? dS_dn * 2.f * n1 : 0.f;
+            if (OCC) { gmx *= occ_w[k]; gxx *= occ_w[k]; gxy *= occ_w[k]; }   // the (detached) per-pixel loss weight
             float* cp = cbase + (size_t)k * W;
             __stcs(cp, gmx); __stcs(cp + plane, gxx); __stcs(cp + 2 * plane, gxy);
           }
@@ -484,6 +527,7 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
       float rho;
       if (R > 0) rho = p.d.w_ssim * (ssim_acc[k] * (1.f / 3.f)) + p.d.w_l1 * (l1_acc[k] * (1.f / 3.f));
       else rho = l1_acc[k] * (1.f / 3.f);
+      if (OCC) rho *= occ_w[k];
       if (avg) {
         avg_acc[k] += rho;
       } else if (rho < best[k]) {
@@ -512,6 +556,14 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
   }
   const float tot = block_sum(local, red);
   if (threadIdx.x == 0) p.partial[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+  if (OCC) {
+    float lr = 0.f;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) lr += reg_acc[k];
+    __syncthreads();
+    const float treg = block_sum(lr, red);
+    if (threadIdx.x == 0) p.partial_reg[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = treg;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -681,6 +733,10 @@ struct PhotoBwdParams {
   float* q_up;         // optional [B,H,W]: 1 / d_up^2 (the upsample-adjoint kernel needs it for the mean-inverse-depth term)
   int g_up_accumulate; // 1: g_up += (the smoothness backward already wrote the plane), 0: g_up =
   float* dP;  // [B,S,12] accumulators (zeroed by the host wrapper)
+  // indoor variant (OCC kernels only)
+  const float* ref[SQLX_MAX_SOURCES];    // depth of each source frame, planar [B,H,W]
+  float* d_ref[SQLX_MAX_SOURCES];        // its gradient, accumulated with atomics (caller zeroes)
+  const float* g_reg;                    // device scalar: upstream gradient of the regularisation sum
 };
 
 // multiplicity with which the window of output q (coordinate qi) covers pixel i under reflection padding
@@ -706,7 +762,7 @@ struct Bwd3Cfg {
   static_assert((TH * TW) % NT == 0 && NT % TW == 0, "tile / block shape");
 };
 
-template <int R, int TH, int TW, int NT, int MINB>
+template <int R, int TH, int TW, int NT, int MINB, bool OCC = false>
 __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdParams p) {
   using C = Bwd3Cfg<R, TH, TW, NT>;
   constexpr int PPT = C::PPT;
@@ -772,7 +828,8 @@ __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdPara
   for (int s = 0; s < S; ++s) {
     const float sel_w = avg ? 1.f / (float)S : 1.f;
     const int sel_idx = avg ? n_ident : n_ident + s;
-    {   // nothing on this tile's halo selects source s (auto-masked or won by another source): no gradient at all
+    if (!OCC) {   // nothing on this tile's halo selects source s (auto-masked or won by another source): no gradient
+                  // at all (the indoor regularisation term has a gradient at every valid pixel: never skipped)
       int any = 0;
       for (int idx = threadIdx.x; idx < C::PH1 * C::PW1; idx += NT) any |= (amin[idx] == sel_idx);
       if (!__syncthreads_or(any)) continue;
@@ -781,14 +838,22 @@ __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdPara
     const float4* srcb = p.src[s] + (size_t)b * plane;
     // own pixels: warped value and its spatial derivatives per channel
     float Xv[3][PPT], dXx[3][PPT], dXy[3][PPT];
+    float gix[PPT], giy[PPT], occ_w[PPT];
+    const float greg = OCC ? __ldg(p.g_reg) * p.scale : 0.f;
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
+      gix[k] = 0.f; giy[k] = 0.f; occ_w[k] = 1.f;
       const Proj pr = project_fast(cam, (float)(u0 + pcol), (float)(v0 + prow0 + k), dep[k], p.d.eps);
       const Taps4 t = make_taps4(pr.pu, pr.pv, H, W);
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bq = a, cq = a, dq = a;
+      float ra = 0.f, rb = 0.f, rc = 0.f, rd = 0.f;
       if (pin[k]) {
         const float4* q = srcb + t.o;
         a = __ldg(q); bq = __ldg(q + 1); cq = __ldg(q + W); dq = __ldg(q + W + 1);
+        if (OCC) {
+          const float* r = p.ref[s] + (size_t)b * plane + t.o;
+          ra = __ldg(r); rb = __ldg(r + 1); rc = __ldg(r + W); rd = __ldg(r + W + 1);
+        }
       }
       const float w00 = (1.f - t.fx) * (1.f - t.fy), w01 = t.fx * (1.f - t.fy);
       const float w10 = (1.f - t.fx) * t.fy, w11 = t.fx * t.fy;
@@ -801,10 +866,25 @@ __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdPara
       dXy[0][k] = (cq.x - a.x) * (1.f - t.fx) + (dq.x - bq.x) * t.fx;
       dXy[1][k] = (cq.y - a.y) * (1.f - t.fx) + (dq.y - bq.y) * t.fx;
       dXy[2][k] = (cq.z - a.z) * (1.f - t.fx) + (dq.z - bq.z) * t.fx;
+      if (OCC && pin[k]) {
+        // depth-consistency terms (trainer_indoor.py:636-651, 699): the loss weight is detached; the regularisation
+        // sum diff * valid has a gradient wrt the depth, the sampled source depth and (through it) the position
+        const float d = dep[k];
+        const float pd = (ra * (1.f - t.fx) + rb * t.fx) * (1.f - t.fy) + (rc * (1.f - t.fx) + rd * t.fx) * t.fy;
+        const OccTerm oc = occ_term(d, pd, Xv[0][k], Xv[1][k], Xv[2][k]);
+        occ_w[k] = oc.weight;
+        if (oc.valid && greg != 0.f) {
+          const float inv = 1.f / (d + pd);
+          const float sg = d > pd ? 1.f : (d < pd ? -1.f : 0.f);
+          gd[k] += greg * (sg - oc.diff) * inv;
+          const float gpd = greg * (-sg - oc.diff) * inv;
+          gix[k] = gpd * ((rb - ra) * (1.f - t.fy) + (rd - rc) * t.fy);
+          giy[k] = gpd * ((rc - ra) * (1.f - t.fx) + (rd - rb) * t.fx);
+          float* q = p.d_ref[s] + (size_t)b * plane + t.o;
+          atomicAdd(q, gpd * w00); atomicAdd(q + 1, gpd * w01); atomicAdd(q + W, gpd * w10); atomicAdd(q + W + 1, gpd * w11);
+        }
+      }
     }
-    float gix[PPT], giy[PPT];
-#pragma unroll
-    for (int k = 0; k < PPT; ++k) { gix[k] = 0.f; giy[k] = 0.f; }
     const float alpha = (p.d.w_ssim / 3.f) * sel_w * gscale;
     const float wl1 = ((R > 0) ? p.d.w_l1 : 1.f) / 3.f * sel_w * gscale;
     float gx[3][PPT];
@@ -815,7 +895,7 @@ __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdPara
         const float diff = Yv[c][k] - Xv[c][k];
         const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
         const bool sel = amin[(prow0 + k + R) * C::PW1 + pcol + R] == sel_idx;
-        gx[c][k] = sel ? -wl1 * sgn : 0.f;
+        gx[c][k] = sel ? -wl1 * sgn * (OCC ? occ_w[k] : 1.f) : 0.f;
       }
     }
     if (R > 0) {
@@ -1020,10 +1100,10 @@ int env_int(const char* name, int dflt) {
 }
 constexpr int kMinTH = 16, kMinTW = 32;   // smallest tile of any configuration: sizes the per-CTA partial buffer
 
-template <int R, int TH, int TW, int NT, int MINB, bool MERGED = false>
+template <int R, int TH, int TW, int NT, int MINB, bool MERGED = false, bool OCC = false>
 int launch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
   using C = Fwd3Cfg<R, TH, TW, NT, MERGED>;
-  auto kern = photo_fwd3_kernel<R, TH, TW, NT, MINB, MERGED>;
+  auto kern = photo_fwd3_kernel<R, TH, TW, NT, MINB, MERGED, OCC>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
@@ -1031,13 +1111,14 @@ int launch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
   }
   dim3 grid(ceil_div(p.d.W, TW), ceil_div(p.d.H, TH), p.d.B);
   *ctas = (int)(grid.x * grid.y * grid.z);
-  ProfScope prof("photo_fwd_kernel", st);
+  ProfScope prof(OCC ? "photo_occ_fwd_kernel" : "photo_fwd_kernel", st);
   kern<<<grid, NT, C::smem_bytes, st>>>(p);
   return check_launch("photo_fwd3_kernel");
 }
 
 template <int R>
 int dispatch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
+  if (p.partial_reg) return launch_photo_fwd3<R, 32, 32, 256, 2, false, true>(p, ctas, st);   // indoor variant
   static const int cfg = env_int("SQLX_FWD_CFG", 0);
   switch (cfg) {
     case 1: return launch_photo_fwd3<R, 16, 32, 256, 3>(p, ctas, st);
@@ -1049,23 +1130,24 @@ int dispatch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
   }
 }
 
-template <int R, int TH, int TW, int NT, int MINB>
+template <int R, int TH, int TW, int NT, int MINB, bool OCC = false>
 int launch_photo_bwd3(const PhotoBwdParams& p, cudaStream_t st) {
   using C = Bwd3Cfg<R, TH, TW, NT>;
-  auto kern = photo_bwd3_kernel<R, TH, TW, NT, MINB>;
+  auto kern = photo_bwd3_kernel<R, TH, TW, NT, MINB, OCC>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
     configured = true;
   }
   dim3 grid(ceil_div(p.d.W, TW), ceil_div(p.d.H, TH), p.d.B);
-  ProfScope prof("photo_bwd_kernel", st);
+  ProfScope prof(OCC ? "photo_occ_bwd_kernel" : "photo_bwd_kernel", st);
   kern<<<grid, NT, C::smem_bytes, st>>>(p);
   return check_launch("photo_bwd3_kernel");
 }
 
 template <int R>
 int dispatch_photo_bwd3(const PhotoBwdParams& p, cudaStream_t st) {
+  if (p.g_reg) return launch_photo_bwd3<R, 16, 32, 256, 2, true>(p, st);   // indoor variant
   static const int cfg = env_int("SQLX_BWD_CFG", 0);
   switch (cfg) {
     case 1: return launch_photo_bwd3<R, 16, 32, 256, 4>(p, st);
@@ -1108,6 +1190,12 @@ extern "C" size_t sqlx_photo_workspace_bytes(const sqlx_photo_desc* d) {
   return sizeof(float) * (fwd_ctas(d) + (size_t)d->B * SQLX_MAX_SOURCES * 16 + 64);
 }
 
+extern "C" size_t sqlx_photo_occ_workspace_bytes(const sqlx_photo_desc* d) {
+  if (!d) return 0;
+  // two per-CTA partial-sum arrays (photometric, regularisation), then the dP accumulators
+  return sizeof(float) * (2 * fwd_ctas(d) + (size_t)d->B * SQLX_MAX_SOURCES * 16 + 64);
+}
+
 extern "C" size_t sqlx_photo_coef_bytes(const sqlx_photo_desc* d) {
   if (!d || (d->flags & SQLX_NO_SSIM)) return 0;
   return sizeof(float) * 9 * (size_t)d->B * d->S * d->H * d->W;
@@ -1118,7 +1206,7 @@ namespace sqlx {
 int photo_fwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const float* depth_up, const float* target,
                       const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
                       const float* identity, const float* noise, float* partial, int* ctas, uint8_t* argmin,
-                      float* ssim_coef, cudaStream_t st) {
+                      float* ssim_coef, cudaStream_t st, const float* const* ref_depths, float* partial_reg) {
   if (int e = check_desc(desc)) return e;
   SQLX_REQUIRE(depth_lr && target && sources_rgba && K && inv_K && T && partial && ctas && argmin, "NULL pointer argument");
   const bool automask = desc->flags & SQLX_AUTOMASK;
@@ -1136,6 +1224,12 @@ int photo_fwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const 
   p.partial = partial;
   p.argmin = argmin;
   p.coef = (desc->flags & SQLX_NO_SSIM) ? nullptr : ssim_coef;
+  p.partial_reg = partial_reg;
+  for (int s = 0; s < SQLX_MAX_SOURCES; ++s) p.ref[s] = (ref_depths && s < desc->S) ? ref_depths[s] : nullptr;
+  if (partial_reg) {
+    SQLX_REQUIRE(ref_depths, "the indoor variant needs the source frames' depth maps");
+    for (int s = 0; s < desc->S; ++s) SQLX_REQUIRE(p.ref[s], "ref_depths[%d] is NULL", s);
+  }
   const int r = (desc->flags & SQLX_NO_SSIM) ? 0 : desc->ssim_radius;
   return r == 3 ? dispatch_photo_fwd3<3>(p, ctas, st)
                 : (r == 1 ? dispatch_photo_fwd3<1>(p, ctas, st) : dispatch_photo_fwd3<0>(p, ctas, st));
@@ -1144,7 +1238,8 @@ int photo_fwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const 
 int photo_bwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const float* depth_up, const float* target,
                       const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
                       const uint8_t* argmin, const float* ssim_coef, const float* g_loss, float scale,
-                      float* d_depth_lr, float* g_up, float* q_up, int g_up_accumulate, float* dP, cudaStream_t st) {
+                      float* d_depth_lr, float* g_up, float* q_up, int g_up_accumulate, float* dP, cudaStream_t st,
+                      const float* const* ref_depths, float* const* d_ref_depths, const float* g_reg) {
   if (int e = check_desc(desc)) return e;
   SQLX_REQUIRE(depth_lr && target && sources_rgba && K && inv_K && T && argmin && g_loss && (d_depth_lr || g_up) && dP,
                "NULL pointer argument");
@@ -1162,6 +1257,15 @@ int photo_bwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const 
   p.K = K; p.invK = inv_K; p.T = T; p.argmin = argmin; p.coef = ssim_coef; p.g_loss = g_loss; p.scale = scale;
   p.d_depth_lr = d_depth_lr; p.g_up = g_up; p.q_up = q_up; p.g_up_accumulate = g_up_accumulate;
   p.dP = dP;
+  p.g_reg = g_reg;
+  for (int s = 0; s < SQLX_MAX_SOURCES; ++s) {
+    p.ref[s] = (g_reg && ref_depths && s < desc->S) ? ref_depths[s] : nullptr;
+    p.d_ref[s] = (g_reg && d_ref_depths && s < desc->S) ? d_ref_depths[s] : nullptr;
+  }
+  if (g_reg) {
+    SQLX_REQUIRE(ref_depths && d_ref_depths, "the indoor variant needs the source frames' depth maps and their gradients");
+    for (int s = 0; s < desc->S; ++s) SQLX_REQUIRE(p.ref[s] && p.d_ref[s], "ref_depths[%d] / d_ref_depths[%d] is NULL", s, s);
+  }
   return r == 3 ? dispatch_photo_bwd3<3>(p, st) : (r == 1 ? dispatch_photo_bwd3<1>(p, st) : dispatch_photo_bwd3<0>(p, st));
 }
 
@@ -1179,7 +1283,7 @@ extern "C" int sqlx_photo_fwd(const sqlx_photo_desc* desc, const float* depth_lr
   float* partial = reinterpret_cast<float*>(workspace);
   int ctas = 0;
   if (int e = photo_fwd3_launch(desc, depth_lr, nullptr, target, sources_rgba, K, inv_K, T, identity, noise, partial, &ctas, argmin,
-                                ssim_coef, st))
+                                ssim_coef, st, nullptr, nullptr))
     return e;
   finalize_sum3_kernel<<<1, 256, 0, st>>>(partial, ctas, loss_sum);
   return check_launch("finalize_sum_kernel");
@@ -1198,7 +1302,48 @@ extern "C" int sqlx_photo_bwd(const sqlx_photo_desc* desc, const float* depth_lr
   if (cudaMemsetAsync(dP, 0, sizeof(float) * (size_t)desc->B * desc->S * 12, st) != cudaSuccess)
     return check_launch("cudaMemsetAsync(dP)");
   if (int e = photo_bwd3_launch(desc, depth_lr, nullptr, target, sources_rgba, K, inv_K, T, argmin, ssim_coef, g_loss, scale,
-                                d_depth_lr, nullptr, nullptr, 0, dP, st))
+                                d_depth_lr, nullptr, nullptr, 0, dP, st, nullptr, nullptr, nullptr))
+    return e;
+  const int n = desc->B * desc->S * 16;
+  dT_from_dP3_kernel<<<ceil_div(n, 128), 128, 0, st>>>(K, dP, desc->B, desc->S, d_T);
+  return check_launch("dT_from_dP_kernel");
+}
+
+/* Indoor variant: see include/sqlx.h */
+extern "C" int sqlx_photo_occ_fwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
+                                  const float* const* sources_rgba, const float* const* ref_depths, const float* K,
+                                  const float* inv_K, const float* T, const float* identity, const float* noise,
+                                  float* sums, uint8_t* argmin, float* ssim_coef, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  if (int e = check_desc(desc)) return e;
+  SQLX_REQUIRE(sums && ref_depths, "NULL pointer argument");
+  SQLX_REQUIRE(workspace && workspace_bytes >= sqlx_photo_occ_workspace_bytes(desc), "workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* partial = reinterpret_cast<float*>(workspace);
+  float* partial_reg = partial + fwd_ctas(desc);
+  int ctas = 0;
+  if (int e = photo_fwd3_launch(desc, depth_lr, nullptr, target, sources_rgba, K, inv_K, T, identity, noise, partial, &ctas,
+                                argmin, ssim_coef, st, ref_depths, partial_reg))
+    return e;
+  finalize_sum3_kernel<<<1, 256, 0, st>>>(partial, ctas, sums);
+  finalize_sum3_kernel<<<1, 256, 0, st>>>(partial_reg, ctas, sums + 1);
+  return check_launch("finalize_sum_kernel");
+}
+
+extern "C" int sqlx_photo_occ_bwd(const sqlx_photo_desc* desc, const float* depth_lr, const float* target,
+                                  const float* const* sources_rgba, const float* const* ref_depths, const float* K,
+                                  const float* inv_K, const float* T, const uint8_t* argmin, const float* ssim_coef,
+                                  const float* g_sums, float scale, float* d_depth_lr, float* d_T,
+                                  float* const* d_ref_depths, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_desc(desc)) return e;
+  SQLX_REQUIRE(d_depth_lr && d_T && g_sums, "NULL pointer argument");
+  SQLX_REQUIRE(workspace && workspace_bytes >= sqlx_photo_occ_workspace_bytes(desc), "workspace too small");
+  float* dP = reinterpret_cast<float*>(workspace) + 2 * fwd_ctas(desc);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(dP, 0, sizeof(float) * (size_t)desc->B * desc->S * 12, st) != cudaSuccess)
+    return check_launch("cudaMemsetAsync(dP)");
+  if (int e = photo_bwd3_launch(desc, depth_lr, nullptr, target, sources_rgba, K, inv_K, T, argmin, ssim_coef, g_sums, scale,
+                                d_depth_lr, nullptr, nullptr, 0, dP, st, ref_depths, d_ref_depths, g_sums + 1))
     return e;
   const int n = desc->B * desc->S * 16;
   dT_from_dP3_kernel<<<ceil_div(n, 128), 128, 0, st>>>(K, dP, desc->B, desc->S, d_T);

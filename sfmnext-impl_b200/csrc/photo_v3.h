@@ -8,12 +8,17 @@ namespace sqlx {
 int photo_fwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const float* depth_up, const float* target,
                       const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
                       const float* identity, const float* noise, float* partial, int* ctas, uint8_t* argmin,
-                      float* ssim_coef, cudaStream_t st);
+                      float* ssim_coef, cudaStream_t st,
+                      // indoor variant: depth of every source frame [B,H,W] + per-CTA sums of the regularisation term
+                      const float* const* ref_depths = nullptr, float* partial_reg = nullptr);
 // launches photo_bwd3_kernel; exactly one of d_depth_lr (atomic upsample adjoint) / g_up (per-pixel plane) is given
 int photo_bwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const float* depth_up, const float* target,
                       const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
                       const uint8_t* argmin, const float* ssim_coef, const float* g_loss, float scale,
                       float* d_depth_lr, float* g_up, float* q_up /*optional 1/d_up^2 plane*/, int g_up_accumulate, float* dP,
-                      cudaStream_t st);
+                      cudaStream_t st,
+                      // indoor variant: source depths, their gradients (atomically accumulated), d loss / d reg-sum
+                      const float* const* ref_depths = nullptr, float* const* d_ref_depths = nullptr,
+                      const float* g_reg = nullptr);
 size_t photo_max_ctas(const sqlx_photo_desc* d);   // upper bound of *ctas for any tile configuration
 }  // namespace sqlx

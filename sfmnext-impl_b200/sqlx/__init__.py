@@ -5,7 +5,7 @@ Python mirrors of the reference's nn.Module / Trainer signatures on top of libsq
 """
 from ._lib import SqlxError, lib, LIB_PATH, exported_symbols  # noqa: F401
 from .photometric import (photometric_losses, reprojection_loss, depth_stats, pose_matrix,  # noqa: F401
-                          smooth_loss_normalised, warp, pack_rgba)
+                          smooth_loss_normalised, warp, pack_rgba, indoor_losses)
 from .layers import (SSIM, BackprojectDepth, Project3D, get_smooth_loss, SILogLoss,  # noqa: F401
                      batch_post_process_disparity, predict_disparity,
                      transformation_from_parameters)

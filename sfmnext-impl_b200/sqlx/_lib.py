@@ -69,6 +69,13 @@ _PROTOS = {
     "sqlx_photo_bwd": (c_int, [ctypes.POINTER(PhotoDesc), c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
                                c_void_p]),
+    "sqlx_photo_occ_workspace_bytes": (c_size_t, [ctypes.POINTER(PhotoDesc)]),
+    "sqlx_photo_occ_fwd": (c_int, [ctypes.POINTER(PhotoDesc), c_void_p, c_void_p, ctypes.POINTER(c_void_p),
+                                   ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sqlx_photo_occ_bwd": (c_int, [ctypes.POINTER(PhotoDesc), c_void_p, c_void_p, ctypes.POINTER(c_void_p),
+                                   ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_float, c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_size_t, c_void_p]),
     "sqlx_warp_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sqlx_identity_losses_fwd": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_float,

@@ -205,6 +205,99 @@ class _PhotoLoss(torch.autograd.Function):
         return (d_depth, d_T, None, None, None, None, None, None) + (None,) * len(srcs)
 
 
+class _PhotoOccLoss(torch.autograd.Function):
+    """Indoor variant of _PhotoLoss (sqlx_photo_occ_fwd/bwd): depth-consistency weighted reprojection losses and
+    the regularisation sum; differentiable wrt the depth map, the camera transforms and the source frames' depths."""
+
+    @staticmethod
+    def forward(ctx, depth_lr, T, target, K, inv_K, identity, noise, cfg, sources, *ref_depths):
+        require_cuda(depth_lr, T, target, K, inv_K, identity, noise, *sources, *ref_depths)
+        d = _f32c(depth_lr)
+        Tm = _f32c(T)
+        B, _, h, w = d.shape
+        H, W = target.shape[-2:]
+        S = len(sources)
+        assert len(ref_depths) == S
+        desc = make_desc(B, H, W, h, w, S, **cfg)
+        srcs = [pack_rgba(s) for s in sources]
+        refs = [_f32c(r) for r in ref_depths]
+        for r in refs:
+            assert tuple(r.shape) == (B, 1, H, W), "depth_ref must be [B,1,H,W] (trainer_indoor.py:377)"
+        tgt, Kc, iKc = _f32c(target), _f32c(K), _f32c(inv_K)
+        ident, nz = _f32c(identity), _f32c(noise)
+        nbytes = lib().sqlx_photo_occ_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(nbytes, device=d.device, dtype=torch.uint8)
+        coef = torch.empty(max(1, lib().sqlx_photo_coef_bytes(ctypes.byref(desc))), device=d.device, dtype=torch.uint8)
+        sums = torch.empty(2, device=d.device, dtype=torch.float32)
+        argmin = torch.empty(B, H, W, device=d.device, dtype=torch.uint8)
+        check(lib().sqlx_photo_occ_fwd(ctypes.byref(desc), ptr(d), ptr(tgt), _src_array(srcs), _src_array(refs), ptr(Kc),
+                                       ptr(iKc), ptr(Tm), ptr(ident), ptr(nz), ptr(sums), ptr(argmin), ptr(coef), ptr(ws),
+                                       nbytes, stream_ptr()), "sqlx_photo_occ_fwd")
+        ctx.save_for_backward(d, Tm, tgt, Kc, iKc, argmin, coef, *srcs, *refs)
+        ctx.desc = desc
+        ctx.S = S
+        ctx.ref_shapes = [r.shape for r in ref_depths]
+        ctx.mark_non_differentiable(argmin)
+        return sums, argmin
+
+    @staticmethod
+    def backward(ctx, g_sums, _g_argmin):
+        d, Tm, tgt, Kc, iKc, argmin, coef, *rest = ctx.saved_tensors
+        S = ctx.S
+        srcs, refs = rest[:S], rest[S:]
+        desc = ctx.desc
+        nbytes = lib().sqlx_photo_occ_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(nbytes, device=d.device, dtype=torch.uint8)
+        d_depth = torch.zeros_like(d)
+        d_T = torch.empty_like(Tm)
+        d_refs = [torch.zeros_like(r) for r in refs]
+        g = g_sums.contiguous().float()
+        check(lib().sqlx_photo_occ_bwd(ctypes.byref(desc), ptr(d), ptr(tgt), _src_array(srcs), _src_array(refs), ptr(Kc),
+                                       ptr(iKc), ptr(Tm), ptr(argmin), ptr(coef), ptr(g), 1.0, ptr(d_depth), ptr(d_T),
+                                       _src_array(d_refs), ptr(ws), nbytes, stream_ptr()), "sqlx_photo_occ_bwd")
+        return (d_depth, d_T, None, None, None, None, None, None, None) + \
+            tuple(g.reshape(sh) for g, sh in zip(d_refs, ctx.ref_shapes))
+
+
+def indoor_losses(disp, target, sources, ref_depths, K, inv_K, poses, noise=None, *, height, width,
+                  disparity_smoothness=1e-3, reg_wt=0.01, rescale_translation=True, no_ssim=False,
+                  avg_reprojection=False, disable_automasking=False, ssim_radius=3):
+    """Indoor loss variant: trainer_indoor.py generate_images_pred (:512-599) +
+    compute_losses_with_occ (:615-719) for --use_improved_mini_reproj_loss at the single loss scale the SQL decoder
+    emits (scales = [0]; every indoor arg file of the reference uses it).
+
+    disp [B,1,h,w] = outputs[("disp",0)]; ref_depths: list of S [B,1,H,W] = outputs[("depth_ref",f,0)] (network
+    depth of every source frame, differentiable); the other arguments as for photometric_losses.  Returns
+    {"loss", "loss/0", ("argmin",0)}; gradients reach disp, the pose parameters and ref_depths."""
+    H, W = height, width
+    S = len(sources)
+    B = target.shape[0]
+    require_cuda(disp, target, K, inv_K, *sources, *ref_depths)
+    automask = not disable_automasking
+    cfg = dict(ssim_radius=ssim_radius, automask=automask, avg=avg_reprojection, no_ssim=no_ssim)
+    identity = identity_losses(target, sources, no_ssim=no_ssim, ssim_radius=ssim_radius) if automask else None
+    if automask and noise is None:
+        noise = torch.randn(B, 1 if avg_reprojection else S, H, W, device=target.device)
+    rescale = bool(rescale_translation) and any("T" not in p for p in poses)
+    stats = depth_stats(disp, H, W) if rescale else None          # mean(1/depth) of the upsampled map (:543-544)
+    Ts = []
+    for pose in poses:
+        if "T" in pose:
+            Ts.append(pose["T"].float())
+        else:
+            Ts.append(pose_matrix(pose["axisangle"][:, 0], pose["translation"][:, 0],
+                                  stats[:, 1] if rescale else None, pose["invert"]))
+    T = torch.stack(Ts, 1)                                        # [B,S,4,4]
+    sums, argmin = _PhotoOccLoss.apply(disp, T, target, K, inv_K, identity, noise, cfg, tuple(sources), *ref_depths)
+    n = float(B * H * W)
+    loss = sums[0] / n + reg_wt * sums[1] / (n * S)               # :698-699 (mean over sources, then over pixels)
+    h, w = disp.shape[-2:]
+    # the colour is always resized to the depth map's shape (`shape[-2:] != [H, W]` is always True, :704-707)
+    color = torch.nn.functional.interpolate(target, [h, w], mode="bilinear", align_corners=False)
+    loss = loss + disparity_smoothness * smooth_loss_normalised(disp, color)     # :701-711
+    return {"loss": loss, "loss/0": loss, ("argmin", 0): argmin}
+
+
 def warp(depth_lr, source, K, inv_K, T, H, W, *, want_depth=True, want_sample=True, want_color=True, eps=1e-7):
     """Materialise outputs[("depth",0,s)], ("sample",f,s), ("color",f,s) for logging (no autograd)."""
     require_cuda(depth_lr, source, K, inv_K, T)

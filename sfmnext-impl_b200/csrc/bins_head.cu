@@ -6,7 +6,7 @@
 // With M = batch <= 16 these layers are bound by reading (forward, d_input) and writing (d_weight) the weight
 // matrices once -- 8.4 MB for the first layer at Q = 64 -- which cuBLAS does through ~12 small-M GEMM / split-K /
 // elementwise launches per direction.  Here: one CTA per output row streams the row with 128-bit loads against all
-// samples at once; 4 launches forward, 7 backward, exact fp32, no atomics.
+// samples at once; 4 launches forward, 4 backward, exact fp32, no atomics.
 #include "common.cuh"
 
 namespace sqlx {
@@ -61,67 +61,74 @@ __global__ void __launch_bounds__(128) head_linear_fwd_kernel(const float* __res
   }
 }
 
-// dz[b,n] = dy[b,n] * act'(y[b,n]);  dW[n,k] = sum_b dz[b,n] x[b,k];  db[n] = sum_b dz[b,n].  One 4-warp CTA per row n.
-__global__ void __launch_bounds__(128) head_linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ y,
-                                                                const float* __restrict__ x, int B, int N, int K,
-                                                                int leaky, float* __restrict__ dz, float* __restrict__ dW,
-                                                                float* __restrict__ db) {
-  const int n = blockIdx.x;
-  float g[kHeadMaxB];
-  float bsum = 0.f;
-#pragma unroll
-  for (int b = 0; b < kHeadMaxB; ++b) {
-    g[b] = 0.f;
-    if (b < B) {
-      float v = __ldg(dy + (size_t)b * N + n);
-      if (leaky && !(__ldg(y + (size_t)b * N + n) > 0.f)) v *= kLeakySlope;
-      g[b] = v;
-      bsum += v;
-    }
-  }
-  if ((int)threadIdx.x < B) {
-    float mine = 0.f;
-#pragma unroll
-    for (int b = 0; b < kHeadMaxB; ++b) mine = (b == (int)threadIdx.x) ? g[b] : mine;
-    dz[(size_t)threadIdx.x * N + n] = mine;
-  }
-  if (threadIdx.x == 0) db[n] = bsum;
-  float4* out = reinterpret_cast<float4*>(dW + (size_t)n * K);
-  for (int k4 = threadIdx.x; k4 < K / 4; k4 += 128) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+// Backward of one Linear layer in ONE launch (both halves only need dy, y, x, W):
+//   dz[b,n] = dy[b,n] * act'(y[b,n]);  dW[n,k] = sum_b dz[b,n] x[b,k];  db[n] = sum_b dz[b,n];  dx[b,k] = sum_n dz[b,n] W[n,k]
+// The first `nx` CTAs compute dx (the critical path of the backward chain: the next layer waits for it), the
+// following N CTAs one row of dW each; the two halves overlap on the machine instead of running back to back.
+//   dx CTA: 32 input features k (lane = k: W rows are read as coalesced 128-byte segments); the 8 warps split the
+//           output rows n, dz is derived from (dy, y) and staged once per CTA as [n][16 samples] (128-bit broadcast
+//           loads), partial sums meet in shared memory: no atomics, fixed summation order.
+//   dW CTA: streams the row with 128-bit stores against all samples at once.
+constexpr int kHeadXWarps = 8;
+constexpr int kHeadBwdThreads = 32 * kHeadXWarps;
+__global__ void __launch_bounds__(kHeadBwdThreads) head_linear_bwd_kernel(
+    const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, const float* __restrict__ W,
+    int B, int N, int K, int leaky, int nx, float* __restrict__ dz, float* __restrict__ dW, float* __restrict__ db,
+    float* __restrict__ dx) {
+  extern __shared__ __align__(16) float sdz[];             // dx CTAs: [N][16]
+  __shared__ float part[kHeadXWarps][kHeadMaxB][33];
+  if ((int)blockIdx.x >= nx) {
+    // ---- one row of dW (and db, dz)
+    const int n = blockIdx.x - nx;
+    float g[kHeadMaxB];
+    float bsum = 0.f;
 #pragma unroll
     for (int b = 0; b < kHeadMaxB; ++b) {
+      g[b] = 0.f;
       if (b < B) {
-        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)b * K) + k4);
-        a.x = fmaf(g[b], xv.x, a.x); a.y = fmaf(g[b], xv.y, a.y); a.z = fmaf(g[b], xv.z, a.z); a.w = fmaf(g[b], xv.w, a.w);
+        float v = __ldg(dy + (size_t)b * N + n);
+        if (leaky && !(__ldg(y + (size_t)b * N + n) > 0.f)) v *= kLeakySlope;
+        g[b] = v;
+        bsum += v;
       }
     }
-    out[k4] = a;
+    if ((int)threadIdx.x < B) {
+      float mine = 0.f;
+#pragma unroll
+      for (int b = 0; b < kHeadMaxB; ++b) mine = (b == (int)threadIdx.x) ? g[b] : mine;
+      dz[(size_t)threadIdx.x * N + n] = mine;
+    }
+    if (threadIdx.x == 0) db[n] = bsum;
+    float4* out = reinterpret_cast<float4*>(dW + (size_t)n * K);
+    for (int k4 = threadIdx.x; k4 < K / 4; k4 += kHeadBwdThreads) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int b = 0; b < kHeadMaxB; ++b) {
+        if (b < B) {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)b * K) + k4);
+          a.x = fmaf(g[b], xv.x, a.x); a.y = fmaf(g[b], xv.y, a.y); a.z = fmaf(g[b], xv.z, a.z); a.w = fmaf(g[b], xv.w, a.w);
+        }
+      }
+      out[k4] = a;
+    }
+    return;
   }
-}
-
-// dx[b,k] = sum_n dz[b,n] W[n,k].  One CTA per 32 input features k (lane = k: W rows are read as coalesced 128-byte
-// segments); the 8 warps split the output rows n, dz is staged once per CTA as [n][16 samples] (128-bit broadcast
-// loads), partial sums meet in shared memory: no atomics, fixed summation order.
-constexpr int kHeadXWarps = 8;
-__global__ void __launch_bounds__(32 * kHeadXWarps) head_linear_bwd_x_kernel(const float* __restrict__ dz,
-                                                                             const float* __restrict__ W, int B, int N,
-                                                                             int K, float* __restrict__ dx) {
-  extern __shared__ __align__(16) float sdz[];             // [N][16]
-  __shared__ float part[kHeadXWarps][kHeadMaxB][33];
+  // ---- 32 columns of dx
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + lane;
-  for (int base = threadIdx.x; base < N * kHeadMaxB; base += 8 * blockDim.x) {    // eight loads in flight per trip
-    float v[8];
+  for (int base = threadIdx.x; base < N * kHeadMaxB; base += 4 * kHeadBwdThreads) {    // loads of four elements in flight
+    float v[4], a[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = base + j * blockDim.x, n = i >> 4, b = i & 15;
-      v[j] = (i < N * kHeadMaxB && b < B) ? __ldg(dz + (size_t)b * N + n) : 0.f;
+    for (int j = 0; j < 4; ++j) {
+      const int i = base + j * kHeadBwdThreads, n = i >> 4, b = i & 15;
+      const bool live = i < N * kHeadMaxB && b < B;
+      v[j] = live ? __ldg(dy + (size_t)b * N + n) : 0.f;
+      a[j] = (live && leaky) ? __ldg(y + (size_t)b * N + n) : 1.f;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = base + j * blockDim.x;
-      if (i < N * kHeadMaxB) sdz[i] = v[j];
+    for (int j = 0; j < 4; ++j) {
+      const int i = base + j * kHeadBwdThreads;
+      if (i < N * kHeadMaxB) sdz[i] = (a[j] > 0.f) ? v[j] : v[j] * kLeakySlope;
     }
   }
   __syncthreads();
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(32 * kHeadXWarps) head_linear_bwd_x_kernel(con
 #pragma unroll
   for (int b = 0; b < kHeadMaxB; ++b) part[warp][b][lane] = acc[b];
   __syncthreads();
-  for (int i = threadIdx.x; i < B * 32; i += blockDim.x) {
+  for (int i = threadIdx.x; i < B * 32; i += kHeadBwdThreads) {
     const int b = i >> 5, l = i & 31;
     float t = 0.f;
 #pragma unroll
@@ -243,24 +250,17 @@ extern "C" int sqlx_head_linear_bwd(const float* W, const float* x, const float*
   SQLX_REQUIRE(N >= 1 && K >= 4 && K % 4 == 0, "in_features must be a positive multiple of 4 (got %d)", K);
   SQLX_REQUIRE(((reinterpret_cast<uintptr_t>(dW) | reinterpret_cast<uintptr_t>(x)) & 15) == 0, "dW and x must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  {
-    ProfScope prof("head_linear_bwd_kernel", st);
-    head_linear_bwd_w_kernel<<<N, 128, 0, st>>>(dy, y, x, B, N, K, leaky, dz, dW, db);
-    if (int e = check_launch("head_linear_bwd_w_kernel")) return e;
+  const int nx = dx ? ceil_div(K, 32) : 0;
+  const size_t smem = dx ? sizeof(float) * (size_t)N * kHeadMaxB : 0;
+  SQLX_REQUIRE(smem <= 160 * 1024, "out_features %d too large for the d_input half", N);
+  static size_t configured = 0;
+  if (smem >= 24 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(head_linear_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
   }
-  if (dx) {
-    const size_t smem = sizeof(float) * (size_t)N * kHeadMaxB;
-    SQLX_REQUIRE(smem <= 160 * 1024, "out_features %d too large for the d_input kernel", N);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      cudaFuncSetAttribute(head_linear_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      configured = smem;
-    }
-    ProfScope prof("head_linear_bwd_kernel", st);
-    head_linear_bwd_x_kernel<<<ceil_div(K, 32), 32 * kHeadXWarps, smem, st>>>(dz, W, B, N, K, dx);
-    if (int e = check_launch("head_linear_bwd_x_kernel")) return e;
-  }
-  return SQLX_OK;
+  ProfScope prof("head_linear_bwd_kernel", st);
+  head_linear_bwd_kernel<<<nx + N, kHeadBwdThreads, smem, st>>>(dy, y, x, W, B, N, K, leaky, nx, dz, dW, db, dx);
+  return check_launch("head_linear_bwd_kernel");
 }
 
 extern "C" int sqlx_head_centers_fwd(const float* raw, int B, int D, float min_val, float max_val, float* centers,

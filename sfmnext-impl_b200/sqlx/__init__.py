@@ -9,6 +9,6 @@ from .photometric import (photometric_losses, reprojection_loss, depth_stats, po
 from .layers import (SSIM, BackprojectDepth, Project3D, get_smooth_loss, SILogLoss,  # noqa: F401
                      batch_post_process_disparity, predict_disparity,
                      transformation_from_parameters)
-from .trainer import FusedLossMixin  # noqa: F401
+from .trainer import FusedLossMixin, IndoorFusedLossMixin  # noqa: F401
 from .sql import (FullQueryLayer, Depth_Decoder_QueryTr, Lite_Depth_Decoder_QueryTr, sql_tail,  # noqa: F401
                   bin_centers)

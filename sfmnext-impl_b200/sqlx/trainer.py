@@ -21,7 +21,7 @@ Unsupported exactly where the reference is: --predictive_mask (model never built
 import torch
 
 from .layers import SSIM
-from .photometric import photometric_losses
+from .photometric import indoor_losses, photometric_losses, warp
 
 
 class FusedLossMixin:
@@ -83,3 +83,64 @@ class FusedLossMixin:
             raise RuntimeError("compute_losses called before generate_images_pred (trainer.py:296-297 order)")
         self._sqlx_losses = None
         return losses
+
+
+class IndoorFusedLossMixin(FusedLossMixin):
+    """Indoor trainer (trainer_indoor.py, --use_improved_mini_reproj_loss):
+
+        class FusedIndoorTrainer(sqlx.IndoorFusedLossMixin, trainer_indoor.Trainer): ...
+
+    Replaces generate_images_pred (trainer_indoor.py:512-599) and compute_losses_with_occ (:615-719, returns
+    `(total_loss, losses)` as the reference does).  The single loss scale of the SQL decoder (opt.scales == [0]) and the
+    un-rectified frames (not --use_rectify_net) are supported; `outputs[("depth_ref", f, 0)]` must hold the network
+    depth of every source frame (:370-377).  `outputs[("depth",0,0)]` and `("color",f,0)` (read by log()) are
+    materialised when `self.sqlx_materialize` is true."""
+
+    def generate_images_pred(self, inputs, outputs):
+        opt = self.opt
+        if not getattr(opt, "use_improved_mini_reproj_loss", False):
+            return FusedLossMixin.generate_images_pred(self, inputs, outputs)
+        if list(opt.scales) != [0] or getattr(opt, "v1_multiscale", False) or getattr(opt, "use_rectify_net", False):
+            raise NotImplementedError("the fused indoor loss supports scales == [0] without --v1_multiscale / "
+                                      "--use_rectify_net")
+        fids = list(opt.frame_ids[1:])
+        rescale = opt.pose_model_type == "posecnn" and not opt.use_stereo               # trainer_indoor.py:537
+        poses = []
+        for f in fids:
+            if f == "s":
+                poses.append({"T": inputs["stereo_T"]})
+            else:
+                poses.append({"axisangle": outputs[("axisangle", 0, f)][:, 0:1],
+                              "translation": outputs[("translation", 0, f)][:, 0:1], "invert": f < 0})
+        if not rescale:                         # the camera transforms predict_poses produced (:533-535)
+            poses = [{"T": inputs["stereo_T"]} if f == "s" else {"T": outputs[("cam_T_cam", 0, f)]} for f in fids]
+        noise = self.sqlx_noises.get(0) if self.sqlx_noises else None
+        out = indoor_losses(outputs[("disp", 0)], inputs[("color", 0, 0)], [inputs[("color", f, 0)] for f in fids],
+                            [outputs[("depth_ref", f, 0)] for f in fids], inputs[("K", 0)], inputs[("inv_K", 0)], poses,
+                            noise, height=opt.height, width=opt.width, disparity_smoothness=opt.disparity_smoothness,
+                            reg_wt=opt.reg_wt, rescale_translation=rescale, no_ssim=opt.no_ssim,
+                            avg_reprojection=opt.avg_reprojection, disable_automasking=opt.disable_automasking)
+        if self.sqlx_materialize:
+            from .photometric import depth_stats, pose_matrix
+            disp = outputs[("disp", 0)].detach()
+            stats = depth_stats(disp, opt.height, opt.width) if rescale else None
+            for f, pose in zip(fids, poses):
+                T = pose["T"].detach().float() if "T" in pose else pose_matrix(
+                    pose["axisangle"].detach()[:, 0], pose["translation"].detach()[:, 0], stats[:, 1], pose["invert"])
+                depth_up, _, color = warp(disp, inputs[("color", f, 0)], inputs[("K", 0)], inputs[("inv_K", 0)], T,
+                                          opt.height, opt.width, want_sample=False)
+                outputs[("depth", 0, 0)] = depth_up
+                outputs[("color", f, 0)] = color
+                if not opt.disable_automasking:
+                    outputs[("color_identity", f, 0)] = inputs[("color", f, 0)]          # :596-598
+        self._sqlx_losses = {"loss/0": out["loss/0"]}
+        self._sqlx_total = out["loss"]
+
+    def compute_losses_with_occ(self, inputs, outputs):
+        losses = getattr(self, "_sqlx_losses", None)
+        if losses is None:
+            raise RuntimeError("compute_losses_with_occ called before generate_images_pred (trainer_indoor.py:378-407)")
+        self._sqlx_losses = None
+        total = self._sqlx_total / self.num_scales                                        # :714-715
+        losses["loss"] = total
+        return total, losses

@@ -129,3 +129,41 @@ def test_indoor_abi_validation():
     kw["ref_depths"] = [r[:, :, ::2, ::2].contiguous() for r in kw["ref_depths"]]    # wrong shape
     with pytest.raises((AssertionError, sqlx.SqlxError)):
         sqlx.indoor_losses(**kw)
+
+
+def test_indoor_trainer_mixin_dict_contract():
+    """sqlx.IndoorFusedLossMixin: generate_images_pred / compute_losses_with_occ with trainer_indoor.py's signatures,
+    dict keys and (total, losses) return value, against the reference's own results."""
+    import types
+    import sqlx
+    kw, leaves, z = indoor_case("indoor_occ")
+    g = _to_dev(kw)
+
+    class T(sqlx.IndoorFusedLossMixin):
+        pass
+    tr = T()
+    fids = [0, -1, 1]
+    tr.num_scales = 1
+    tr.opt = types.SimpleNamespace(scales=[0], frame_ids=fids, height=kw["height"], width=kw["width"],
+                                   pose_model_type="posecnn", use_stereo=False, no_ssim=False, avg_reprojection=False,
+                                   disable_automasking=False, disparity_smoothness=1e-3, v1_multiscale=False,
+                                   predictive_mask=False, use_improved_mini_reproj_loss=True, use_rectify_net=False,
+                                   reg_wt=kw["reg_wt"])
+    tr.sqlx_noises = {0: g["noise"]}
+    inputs = {("K", 0): g["K"], ("inv_K", 0): g["inv_K"], ("color", 0, 0): g["target"]}
+    outputs = {("disp", 0): g["disp"]}
+    for f, src, ref, pose in zip(fids[1:], g["sources"], g["ref_depths"], g["poses"]):
+        inputs[("color", f, 0)] = src
+        outputs[("depth_ref", f, 0)] = ref
+        outputs[("axisangle", 0, f)], outputs[("translation", 0, f)] = pose["axisangle"], pose["translation"]
+    tr.generate_images_pred(inputs, outputs)
+    total, losses = tr.compute_losses_with_occ(inputs, outputs)
+    assert abs(float(total) - float(z["out_loss"])) < 1e-5
+    assert abs(float(losses["loss/0"]) - float(z["out_loss_s0"])) < 1e-5
+    np.testing.assert_allclose(outputs[("depth", 0, 0)].cpu().numpy(), z["out_depth_s0"], rtol=1e-5, atol=1e-5)
+    for f in fids[1:]:
+        np.testing.assert_allclose(outputs[("color", f, 0)].cpu().numpy(), z["out_color_%d" % f], atol=1e-4)
+        assert outputs[("color_identity", f, 0)] is inputs[("color", f, 0)]
+    total.backward()
+    for t in [g["disp"]] + g["ref_depths"]:
+        assert t.grad is not None and bool(torch.isfinite(t.grad).all())

@@ -211,6 +211,8 @@ def algorithmic_bytes(c):
     return {
         # depth_lr + target + S sources + S identity + S noise (reads); argmin u8 (write)
         "photo_fwd_kernel": B * (4 * n_avg + 12 * N + 12 * N * S + 4 * N * S + 4 * N * S + N),
+        # all loss scales in one launch: the per-scale figure (SURVEY 8d's unit) times the scales one launch processes
+        "photo_fwd_ms_kernel": B * sum(4 * n + 12 * N + 12 * N * S + 4 * N * S + 4 * N * S + N for n in ns),
         # depth_lr + target + S sources + argmin (reads); d_depth_lr (write)
         "photo_bwd_kernel": B * (4 * n_avg + 12 * N + 12 * N * S + N + 4 * n_avg),
         "reproj_loss_kernel": B * (24 * N + 4 * N),

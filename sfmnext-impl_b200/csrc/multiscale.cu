@@ -16,6 +16,8 @@
 //
 // 12 launches (+2 memsets) per step for 4 scales instead of 64.  Every reduction has a fixed summation order.
 #include "photo_v3.h"
+
+#include <stdlib.h>
 #include "pose.cuh"
 
 namespace sqlx {
@@ -790,6 +792,18 @@ extern "C" int sqlx_ms_loss_fwd(const sqlx_ms_desc* d, const float* const* depth
     if (int e = check_launch("ms_stats_pose_kernel")) return e;
   }
   int ctas = 0;
+  static const int fused = []() { const char* v = getenv("SQLX_MS_FUSED_FWD"); return v ? atoi(v) : 1; }();
+  if (fused && ns > 1) {
+    // every scale in one launch: the target tile, its statistics and the identity losses are shared by the scales
+    const sqlx_photo_desc pd = scale_photo_desc(d, 0);
+    const float* dups[SQLX_MAX_SCALES];
+    for (int s = 0; s < ns; ++s) dups[s] = sh.d_up[s];
+    if (int e = photo_fwd3_ms_launch(&pd, ns, dups, target, sources_rgba, K, inv_K, T, (size_t)B * S * 16, identity,
+                                     automask ? noise : nullptr, reinterpret_cast<float*>(ws + L.photo_partial), L.max_ctas,
+                                     &ctas, argmin, L.coef_stride ? reinterpret_cast<float*>(sv + L.coef) : nullptr,
+                                     L.coef_stride / sizeof(float), st))
+      return e;
+  } else
   for (int s = 0; s < ns; ++s) {
     const sqlx_photo_desc pd = scale_photo_desc(d, s);
     if (int e = photo_fwd3_launch(&pd, depth_lr[s], sh.d_up[s], target, sources_rgba, K, inv_K, T + (size_t)s * B * S * 16, identity,

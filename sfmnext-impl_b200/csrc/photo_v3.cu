@@ -26,6 +26,7 @@
 #include "photo_tile.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace sqlx {
 
@@ -225,6 +226,14 @@ struct PhotoFwdParams {
   // indoor variant (OCC kernels only; trainer_indoor.py:583-587, 636-651)
   const float* ref[SQLX_MAX_SOURCES];    // depth of each source frame, planar [B,H,W]
   float* partial_reg;                    // per-CTA partial sums of diff_depth * valid_mask
+  // all loss scales in one CTA pass (MS kernels only): the target tile, its box statistics and the identity losses are
+  // staged once and shared by the scales; scale i reads ms_depth_up[i] / ms_noise[i] / T + i * ms_T_stride and writes
+  // ms_argmin[i] / partial + i * ms_partial_stride / coef + i * ms_coef_stride
+  int ns;
+  const float* ms_depth_up[SQLX_MAX_SCALES];
+  const float* ms_noise[SQLX_MAX_SCALES];
+  uint8_t* ms_argmin[SQLX_MAX_SCALES];
+  size_t ms_T_stride, ms_partial_stride, ms_coef_stride;   // in floats
 };
 
 // Depth-consistency terms of the indoor loss at one pixel (trainer_indoor.py:636-648): pd = the source frame's depth
@@ -257,8 +266,8 @@ struct Fwd3Cfg {
   static_assert((TH * TW) % NT == 0 && NT % TW == 0 && NT >= PH + PW, "tile / block shape");
 };
 
-template <int R, int TH, int TW, int NT, int MINB, bool MERGED, bool OCC = false>
-__global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdParams p) {
+template <int R, int TH, int TW, int NT, int MINB, bool MERGED, bool OCC = false, bool MS = false>
+__global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const __grid_constant__ PhotoFwdParams p) {
   using C = Fwd3Cfg<R, TH, TW, NT, MERGED>;
   constexpr int PPT = C::PPT;
   constexpr int RR = R > 0 ? R : 1;
@@ -282,16 +291,33 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
   const bool avg = p.d.flags & SQLX_AVG_REPROJ;
   constexpr float ia = 1.f / (float)((2 * R + 1) * (2 * R + 1));
 
-  if (threadIdx.x < S)
-    load_camera(p.K + b * 16, p.invK + b * 16, p.T + ((size_t)b * S + threadIdx.x) * 16, cams[threadIdx.x]);
-
   fill_axis_table<C::PH>(rowt, v0 - R, H, p.d.h, (float)p.d.h / (float)H, p.d.w, 0);
   fill_axis_table<C::PW>(colt, u0 - R, W, p.d.w, (float)p.d.w / (float)W, 1, C::PH);
+
+  // owned pixels: PPT vertically adjacent rows of one column
+  const int pcol = threadIdx.x % TW;
+  const int prow0 = (threadIdx.x / TW) * PPT;
+  const bool col_in = u0 + pcol < W;
+  const size_t pix0 = (size_t)(v0 + prow0) * W + (u0 + pcol);   // offset of the first owned pixel in a plane
+  const int n_ident = automask ? (avg ? 1 : S) : 0;
+  float* tsp = tstat + prow0 * TW + pcol;
+  const size_t cta_index = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+
+  const int nsc = MS ? p.ns : 1;
+  for (int sc = 0; sc < nsc; ++sc) {
+  const bool first = !MS || sc == 0;
+  const float* T_sc = MS ? p.T + (size_t)sc * p.ms_T_stride : p.T;
+  const float* noise_sc = MS ? p.ms_noise[sc] : p.noise;
+  uint8_t* argmin_sc = MS ? p.ms_argmin[sc] : p.argmin;
+  float* coef_sc = (MS && p.coef) ? p.coef + (size_t)sc * p.ms_coef_stride : p.coef;
+  if (threadIdx.x < S)
+    load_camera(p.K + b * 16, p.invK + b * 16, T_sc + ((size_t)b * S + threadIdx.x) * 16, cams[threadIdx.x]);
   __syncthreads();
 
-  {   // upsampled depth and the three target planes on the R halo, two elements per trip
+  {   // upsampled depth and (first scale only) the three target planes on the R halo, two elements per trip
     const float* lr_map = p.depth_lr + (size_t)b * p.d.h * p.d.w;
-    const float* up_map = p.depth_up ? p.depth_up + (size_t)b * plane : nullptr;
+    const float* dup = MS ? p.ms_depth_up[sc] : p.depth_up;
+    const float* up_map = dup ? dup + (size_t)b * plane : nullptr;
     const float* tgb = p.target + (size_t)b * 3 * plane;
     float dv[2][4], tv[2][3], wy[2], wx[2];
     for_region2<C::PH, C::PW, NT>(
@@ -307,8 +333,10 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
               dv[j][0] = __ldg(r0 + ct.x); dv[j][1] = __ldg(r0 + ct.y);
               dv[j][2] = __ldg(r1 + ct.x); dv[j][3] = __ldg(r1 + ct.y);
             }
-            const float* tp = tgb + (size_t)(rt.w * W + ct.w);
-            tv[j][0] = __ldg(tp); tv[j][1] = __ldg(tp + plane); tv[j][2] = __ldg(tp + 2 * plane);
+            if (first) {
+              const float* tp = tgb + (size_t)(rt.w * W + ct.w);
+              tv[j][0] = __ldg(tp); tv[j][1] = __ldg(tp + plane); tv[j][2] = __ldg(tp + 2 * plane);
+            }
           }
         },
         [&](int j, int lr, int lc) {
@@ -317,26 +345,19 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
           dpl[o] = up_map ? dv[j][0]
                           : (1.f - wy[j]) * ((1.f - wx[j]) * dv[j][0] + wx[j] * dv[j][1]) +
                                 wy[j] * ((1.f - wx[j]) * dv[j][2] + wx[j] * dv[j][3]);
-          tg[o] = tv[j][0]; tg[C::PLANE + o] = tv[j][1]; tg[2 * C::PLANE + o] = tv[j][2];
+          if (first) { tg[o] = tv[j][0]; tg[C::PLANE + o] = tv[j][1]; tg[2 * C::PLANE + o] = tv[j][2]; }
         });
   }
-
-  // owned pixels: PPT vertically adjacent rows of one column
-  const int pcol = threadIdx.x % TW;
-  const int prow0 = (threadIdx.x / TW) * PPT;
-  const bool col_in = u0 + pcol < W;
-  const size_t pix0 = (size_t)(v0 + prow0) * W + (u0 + pcol);   // offset of the first owned pixel in a plane
 
   // identity (+noise) candidates: independent global loads issued before the staging barrier, consumed after it
   float best[PPT];
   int arg[PPT];
 #pragma unroll
   for (int k = 0; k < PPT; ++k) { best[k] = INFINITY; arg[k] = 0; }
-  const int n_ident = automask ? (avg ? 1 : S) : 0;
   float idv[SQLX_MAX_SOURCES][PPT], nzv[SQLX_MAX_SOURCES][PPT];
   if (automask) {
     const float* idp = p.identity + (size_t)b * S * plane + pix0;
-    const float* nzp = p.noise + (size_t)b * (avg ? 1 : S) * plane + pix0;
+    const float* nzp = noise_sc + (size_t)b * (avg ? 1 : S) * plane + pix0;
 #pragma unroll
     for (int s = 0; s < SQLX_MAX_SOURCES; ++s) {
 #pragma unroll
@@ -368,8 +389,9 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
 
   // target statistics per channel (mean and variance + C2): written and read back by the owning thread only
   // (shared memory rather than 6*PPT registers that would stay live across the whole source loop)
-  float* tsp = tstat + prow0 * TW + pcol;
-  if (R > 0 && MERGED) {
+  if (!first) {
+    // the target statistics of the tile are already in shared memory
+  } else if (R > 0 && MERGED) {
     // all channels in one pass: 6 horizontal planes, one barrier
 #pragma unroll
     for (int c = 0; c < 3; ++c)
@@ -494,7 +516,7 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
         vsum_multi<R, TW, PPT>(cur, prow0, pcol, Sx);
         vsum_multi<R, TW, PPT>(cur + C::HB, prow0, pcol, Sxx);
         vsum_multi<R, TW, PPT>(cur + 2 * C::HB, prow0, pcol, Sxy);
-        float* cbase = p.coef ? p.coef + ((((size_t)b * S + s) * 3 + c) * 3) * plane + pix0 : nullptr;
+        float* cbase = coef_sc ? coef_sc + ((((size_t)b * S + s) * 3 + c) * 3) * plane + pix0 : nullptr;
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
           // layers.py:37-46 with one reciprocal, shared by the value and its derivative coefficients
@@ -551,19 +573,21 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const PhotoFwdPara
   for (int k = 0; k < PPT; ++k) {
     if (col_in && v0 + prow0 + k < H) {
       local += best[k];
-      p.argmin[(size_t)b * plane + pix0 + (size_t)k * W] = (uint8_t)arg[k];
+      argmin_sc[(size_t)b * plane + pix0 + (size_t)k * W] = (uint8_t)arg[k];
     }
   }
   const float tot = block_sum(local, red);
-  if (threadIdx.x == 0) p.partial[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+  if (threadIdx.x == 0) p.partial[(MS ? (size_t)sc * p.ms_partial_stride : 0) + cta_index] = tot;
   if (OCC) {
     float lr = 0.f;
 #pragma unroll
     for (int k = 0; k < PPT; ++k) lr += reg_acc[k];
     __syncthreads();
     const float treg = block_sum(lr, red);
-    if (threadIdx.x == 0) p.partial_reg[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = treg;
+    if (threadIdx.x == 0) p.partial_reg[cta_index] = treg;
   }
+  if (MS) __syncthreads();   // the next scale rewrites the camera slots, the depth plane and `red`
+  }  // scales
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1100,10 +1124,10 @@ int env_int(const char* name, int dflt) {
 }
 constexpr int kMinTH = 16, kMinTW = 32;   // smallest tile of any configuration: sizes the per-CTA partial buffer
 
-template <int R, int TH, int TW, int NT, int MINB, bool MERGED = false, bool OCC = false>
+template <int R, int TH, int TW, int NT, int MINB, bool MERGED = false, bool OCC = false, bool MS = false>
 int launch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
   using C = Fwd3Cfg<R, TH, TW, NT, MERGED>;
-  auto kern = photo_fwd3_kernel<R, TH, TW, NT, MINB, MERGED, OCC>;
+  auto kern = photo_fwd3_kernel<R, TH, TW, NT, MINB, MERGED, OCC, MS>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
@@ -1111,7 +1135,7 @@ int launch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
   }
   dim3 grid(ceil_div(p.d.W, TW), ceil_div(p.d.H, TH), p.d.B);
   *ctas = (int)(grid.x * grid.y * grid.z);
-  ProfScope prof(OCC ? "photo_occ_fwd_kernel" : "photo_fwd_kernel", st);
+  ProfScope prof(OCC ? "photo_occ_fwd_kernel" : (MS ? "photo_fwd_ms_kernel" : "photo_fwd_kernel"), st);
   kern<<<grid, NT, C::smem_bytes, st>>>(p);
   return check_launch("photo_fwd3_kernel");
 }
@@ -1119,6 +1143,7 @@ int launch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
 template <int R>
 int dispatch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
   if (p.partial_reg) return launch_photo_fwd3<R, 32, 32, 256, 2, false, true>(p, ctas, st);   // indoor variant
+  if (p.ns > 0) return launch_photo_fwd3<R, 32, 32, 256, 2, false, false, true>(p, ctas, st);  // all scales per CTA
   static const int cfg = env_int("SQLX_FWD_CFG", 0);
   switch (cfg) {
     case 1: return launch_photo_fwd3<R, 16, 32, 256, 3>(p, ctas, st);
@@ -1225,11 +1250,48 @@ int photo_fwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const 
   p.argmin = argmin;
   p.coef = (desc->flags & SQLX_NO_SSIM) ? nullptr : ssim_coef;
   p.partial_reg = partial_reg;
+  p.ns = 0;
   for (int s = 0; s < SQLX_MAX_SOURCES; ++s) p.ref[s] = (ref_depths && s < desc->S) ? ref_depths[s] : nullptr;
   if (partial_reg) {
     SQLX_REQUIRE(ref_depths, "the indoor variant needs the source frames' depth maps");
     for (int s = 0; s < desc->S; ++s) SQLX_REQUIRE(p.ref[s], "ref_depths[%d] is NULL", s);
   }
+  const int r = (desc->flags & SQLX_NO_SSIM) ? 0 : desc->ssim_radius;
+  return r == 3 ? dispatch_photo_fwd3<3>(p, ctas, st)
+                : (r == 1 ? dispatch_photo_fwd3<1>(p, ctas, st) : dispatch_photo_fwd3<0>(p, ctas, st));
+}
+
+int photo_fwd3_ms_launch(const sqlx_photo_desc* desc, int ns, const float* const* depth_up, const float* target,
+                         const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
+                         size_t T_stride, const float* identity, const float* const* noise, float* partial,
+                         size_t partial_stride, int* ctas, uint8_t* const* argmin, float* ssim_coef, size_t coef_stride,
+                         cudaStream_t st) {
+  if (int e = check_desc(desc)) return e;
+  SQLX_REQUIRE(ns >= 1 && ns <= SQLX_MAX_SCALES, "num_scales %d outside 1..%d", ns, SQLX_MAX_SCALES);
+  SQLX_REQUIRE(depth_up && target && sources_rgba && K && inv_K && T && partial && ctas && argmin, "NULL pointer argument");
+  const bool automask = desc->flags & SQLX_AUTOMASK;
+  SQLX_REQUIRE(!automask || (identity && noise), "automask needs identity and noise");
+  PhotoFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.d = *desc;
+  p.target = target;
+  for (int s = 0; s < desc->S; ++s) {
+    p.src[s] = reinterpret_cast<const float4*>(sources_rgba[s]);
+    SQLX_REQUIRE(p.src[s], "source %d is NULL", s);
+    SQLX_REQUIRE((reinterpret_cast<uintptr_t>(p.src[s]) & 15) == 0, "source %d is not 16-byte aligned", s);
+  }
+  p.K = K; p.invK = inv_K; p.T = T; p.identity = identity;
+  p.partial = partial;
+  p.coef = (desc->flags & SQLX_NO_SSIM) ? nullptr : ssim_coef;
+  p.ns = ns;
+  p.ms_T_stride = T_stride; p.ms_partial_stride = partial_stride; p.ms_coef_stride = coef_stride;
+  for (int i = 0; i < ns; ++i) {
+    SQLX_REQUIRE(depth_up[i] && argmin[i] && (!automask || noise[i]), "scale %d: NULL pointer", i);
+    p.ms_depth_up[i] = depth_up[i];
+    p.ms_noise[i] = automask ? noise[i] : nullptr;
+    p.ms_argmin[i] = argmin[i];
+  }
+  p.depth_lr = depth_up[0];   // never read: every scale has its upsampled plane
   const int r = (desc->flags & SQLX_NO_SSIM) ? 0 : desc->ssim_radius;
   return r == 3 ? dispatch_photo_fwd3<3>(p, ctas, st)
                 : (r == 1 ? dispatch_photo_fwd3<1>(p, ctas, st) : dispatch_photo_fwd3<0>(p, ctas, st));

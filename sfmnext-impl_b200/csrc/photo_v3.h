@@ -11,6 +11,14 @@ int photo_fwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const 
                       float* ssim_coef, cudaStream_t st,
                       // indoor variant: depth of every source frame [B,H,W] + per-CTA sums of the regularisation term
                       const float* const* ref_depths = nullptr, float* partial_reg = nullptr);
+// All loss scales in ONE launch: every CTA stages its target tile, the tile's box statistics and the identity losses
+// once and runs the scales back to back.  depth_up[i] [B,H,W] (upsampled depth of scale i), noise[i], argmin[i];
+// T + i * T_stride, partial + i * partial_stride, ssim_coef + i * coef_stride (strides in floats).
+int photo_fwd3_ms_launch(const sqlx_photo_desc* desc, int ns, const float* const* depth_up, const float* target,
+                         const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
+                         size_t T_stride, const float* identity, const float* const* noise, float* partial,
+                         size_t partial_stride, int* ctas, uint8_t* const* argmin, float* ssim_coef, size_t coef_stride,
+                         cudaStream_t st);
 // launches photo_bwd3_kernel; exactly one of d_depth_lr (atomic upsample adjoint) / g_up (per-pixel plane) is given
 int photo_bwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const float* depth_up, const float* target,
                       const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,

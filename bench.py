@@ -215,6 +215,7 @@ def algorithmic_bytes(c):
         "photo_fwd_ms_kernel": B * sum(4 * n + 12 * N + 12 * N * S + 4 * N * S + 4 * N * S + N for n in ns),
         # depth_lr + target + S sources + argmin (reads); d_depth_lr (write)
         "photo_bwd_kernel": B * (4 * n_avg + 12 * N + 12 * N * S + N + 4 * n_avg),
+        "photo_bwd_ms_kernel": B * sum(4 * n + 12 * N + 12 * N * S + N + 4 * n for n in ns),
         "reproj_loss_kernel": B * (24 * N + 4 * N),
         # identity losses of all S sources in one launch: target once, every source once, S loss maps out
         "identity_loss_kernel": B * (12 * N + 12 * N * S + 4 * N * S),
@@ -421,8 +422,11 @@ def main():
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
         for k, v in tj["kernels"].items():     # ncu names -> the names of the library's profile hooks
-            k = k.replace("void ", "").split("<")[0].split("::")[-1]
-            k = {"photo_fwd3_kernel": "photo_fwd_kernel", "photo_bwd3_kernel": "photo_bwd_kernel",
+            full = k.replace("void ", "")
+            k = full.split("<")[0].split("::")[-1]
+            ms = full.rstrip().endswith(", 1>")       # last template argument of the photometric kernels: all scales per launch
+            k = {"photo_fwd3_kernel": "photo_fwd_ms_kernel" if ms else "photo_fwd_kernel",
+                 "photo_bwd3_kernel": "photo_bwd_ms_kernel" if ms else "photo_bwd_kernel",
                  "sql_tc_pred2_kernel": "sql_tc_pred_kernel"}.get(k, k)
             traffic[k] = v["dram_bytes_per_launch"]
     except Exception:

@@ -862,6 +862,23 @@ extern "C" int sqlx_ms_loss_bwd(const sqlx_ms_desc* d, const float* const* depth
   }
   if (cudaMemsetAsync(dP, 0, sizeof(float) * (size_t)ns * B * S * 12, st) != cudaSuccess)
     return check_launch("cudaMemsetAsync(dP)");
+  static const int fused = []() { const char* v = getenv("SQLX_MS_FUSED_BWD"); return v ? atoi(v) : 1; }();
+  if (fused && ns > 1) {
+    const sqlx_photo_desc pd = scale_photo_desc(d, 0);
+    const float* dups[SQLX_MAX_SCALES];
+    float* qups[SQLX_MAX_SCALES];
+    unsigned acc = 0;
+    for (int s = 0; s < ns; ++s) {
+      dups[s] = sh.d_up[s];
+      qups[s] = rescale ? reinterpret_cast<float*>(ws + L.q_up + L.g_up_stride * s) : nullptr;
+      if (!g.g_direct[s]) acc |= 1u << s;
+    }
+    if (int e = photo_bwd3_ms_launch(&pd, ns, dups, target, sources_rgba, K, inv_K, T, (size_t)B * S * 16, argmin,
+                                     L.coef_stride ? reinterpret_cast<const float*>(sv + L.coef) : nullptr,
+                                     L.coef_stride / sizeof(float), g_loss, 1.f / ((float)ns * (float)B * H * W), g.g_up,
+                                     qups, acc, dP, (size_t)B * S * 12, st))
+      return e;
+  } else
   for (int s = 0; s < ns; ++s) {
     const sqlx_photo_desc pd = scale_photo_desc(d, s);
     if (int e = photo_bwd3_launch(&pd, depth_lr[s], sh.d_up[s], target, sources_rgba, K, inv_K, T + (size_t)s * B * S * 16, argmin[s],

@@ -761,6 +761,14 @@ struct PhotoBwdParams {
   const float* ref[SQLX_MAX_SOURCES];    // depth of each source frame, planar [B,H,W]
   float* d_ref[SQLX_MAX_SOURCES];        // its gradient, accumulated with atomics (caller zeroes)
   const float* g_reg;                    // device scalar: upstream gradient of the regularisation sum
+  // all loss scales in one launch (MS kernels only): blockIdx.z = scale * B + sample
+  int ns;
+  const float* ms_depth_up[SQLX_MAX_SCALES];
+  const uint8_t* ms_argmin[SQLX_MAX_SCALES];
+  float* ms_g_up[SQLX_MAX_SCALES];
+  float* ms_q_up[SQLX_MAX_SCALES];       // entries may be NULL
+  unsigned ms_accumulate;                // bit i: g_up of scale i is accumulated into
+  size_t ms_T_stride, ms_coef_stride, ms_dP_stride;   // in floats
 };
 
 // multiplicity with which the window of output q (coordinate qi) covers pixel i under reflection padding
@@ -786,8 +794,8 @@ struct Bwd3Cfg {
   static_assert((TH * TW) % NT == 0 && NT % TW == 0, "tile / block shape");
 };
 
-template <int R, int TH, int TW, int NT, int MINB, bool OCC = false>
-__global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdParams p) {
+template <int R, int TH, int TW, int NT, int MINB, bool OCC = false, bool MS = false>
+__global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const __grid_constant__ PhotoBwdParams p) {
   using C = Bwd3Cfg<R, TH, TW, NT>;
   constexpr int PPT = C::PPT;
   constexpr int RR = R > 0 ? R : 1;
@@ -800,7 +808,16 @@ __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdPara
   uint8_t* amin = reinterpret_cast<uint8_t*>(cams + SQLX_MAX_SOURCES);
 
   const int H = p.d.H, W = p.d.W, S = p.d.S;
-  const int b = blockIdx.z;
+  const int sc = MS ? (int)blockIdx.z / p.d.B : 0;
+  const int b = MS ? (int)blockIdx.z - sc * p.d.B : (int)blockIdx.z;
+  const float* depth_up = MS ? p.ms_depth_up[sc] : p.depth_up;
+  const uint8_t* argmin_p = MS ? p.ms_argmin[sc] : p.argmin;
+  const float* T_p = MS ? p.T + (size_t)sc * p.ms_T_stride : p.T;
+  const float* coef_p = (MS && p.coef) ? p.coef + (size_t)sc * p.ms_coef_stride : p.coef;
+  float* dP_p = MS ? p.dP + (size_t)sc * p.ms_dP_stride : p.dP;
+  float* g_up_p = MS ? p.ms_g_up[sc] : p.g_up;
+  float* q_up_p = MS ? p.ms_q_up[sc] : p.q_up;
+  const int g_up_acc = MS ? (int)((p.ms_accumulate >> sc) & 1u) : p.g_up_accumulate;
   const int v0 = blockIdx.y * TH, u0 = blockIdx.x * TW;
   const size_t plane = (size_t)H * W;
   const bool automask = p.d.flags & SQLX_AUTOMASK;
@@ -814,14 +831,14 @@ __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdPara
   const bool interior = (v0 > R) && (u0 > R) && (v0 + TH + R < H) && (u0 + TW + R < W);
 
   if (threadIdx.x < S)
-    load_camera(p.K + b * 16, p.invK + b * 16, p.T + ((size_t)b * S + threadIdx.x) * 16, cams[threadIdx.x]);
+    load_camera(p.K + b * 16, p.invK + b * 16, T_p + ((size_t)b * S + threadIdx.x) * 16, cams[threadIdx.x]);
   if (threadIdx.x < 16 * SQLX_MAX_SOURCES) dPs[threadIdx.x] = 0.f;
   {   // arg-min of the tile's R halo, two elements per trip (loads of both in flight)
     uint8_t av[2];
     for_region2<C::PH1, C::PW1, NT>(
         [&](int j, int lr, int lc, bool live) {
           const int v = v0 - R + lr, u = u0 - R + lc;
-          av[j] = (live && v >= 0 && v < H && u >= 0 && u < W) ? p.argmin[(size_t)b * plane + (size_t)v * W + u]
+          av[j] = (live && v >= 0 && v < H && u >= 0 && u < W) ? argmin_p[(size_t)b * plane + (size_t)v * W + u]
                                                                : (uint8_t)255;
         },
         [&](int j, int lr, int lc) { amin[lr * C::PW1 + lc] = av[j]; });
@@ -841,7 +858,7 @@ __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdPara
 #pragma unroll
     for (int c = 0; c < 3; ++c) Yv[c][k] = 0.f;
     if (pin[k]) {
-      dep[k] = p.depth_up ? __ldg(p.depth_up + (size_t)b * plane + pix0 + (size_t)k * W)
+      dep[k] = depth_up ? __ldg(depth_up + (size_t)b * plane + pix0 + (size_t)k * W)
                           : upsample_at(p.depth_lr + (size_t)b * h * w, h, w, v0 + prow0 + k, u0 + pcol, sy, sx);
 #pragma unroll
       for (int c = 0; c < 3; ++c) Yv[c][k] = __ldg(p.target + ((size_t)b * 3 + c) * plane + pix0 + (size_t)k * W);
@@ -925,7 +942,7 @@ __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdPara
     if (R > 0) {
       // all nine coefficient planes (3 channels x {d/d mean, d/d E[x^2], d/d E[xy]}) of this source in ONE staging
       // pass: nine independent masked loads per halo pixel in flight, two block barriers per source
-      const float* cb9 = p.coef + ((size_t)b * S + s) * 9 * plane;
+      const float* cb9 = coef_p + ((size_t)b * S + s) * 9 * plane;
       float cv[2][9];
       for_region2<C::PH1, C::PW1, NT>(
           [&](int j, int lr, int lc, bool live) {
@@ -1047,16 +1064,16 @@ __global__ void __launch_bounds__(NT, MINB) photo_bwd3_kernel(const PhotoBwdPara
   if (threadIdx.x < 12 * S) {
     const int s = threadIdx.x / 12, i = threadIdx.x - s * 12;
     const float t = dPs[s * 16 + i];
-    if (t != 0.f) atomicAdd(p.dP + ((size_t)b * S + s) * 12 + i, t);
+    if (t != 0.f) atomicAdd(dP_p + ((size_t)b * S + s) * 12 + i, t);
   }
-  if (p.g_up) {   // hand the per-pixel gradient to the gather-style upsample adjoint
+  if (g_up_p) {   // hand the per-pixel gradient to the gather-style upsample adjoint
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
       if (!pin[k]) continue;
       const size_t o = (size_t)b * plane + pix0 + (size_t)k * W;
-      float* q = p.g_up + o;
-      *q = p.g_up_accumulate ? *q + gd[k] : gd[k];
-      if (p.q_up) p.q_up[o] = __fdividef(1.f, dep[k] * dep[k]);
+      float* q = g_up_p + o;
+      *q = g_up_acc ? *q + gd[k] : gd[k];
+      if (q_up_p) q_up_p[o] = __fdividef(1.f, dep[k] * dep[k]);
     }
     return;
   }
@@ -1155,17 +1172,17 @@ int dispatch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
   }
 }
 
-template <int R, int TH, int TW, int NT, int MINB, bool OCC = false>
+template <int R, int TH, int TW, int NT, int MINB, bool OCC = false, bool MS = false>
 int launch_photo_bwd3(const PhotoBwdParams& p, cudaStream_t st) {
   using C = Bwd3Cfg<R, TH, TW, NT>;
-  auto kern = photo_bwd3_kernel<R, TH, TW, NT, MINB, OCC>;
+  auto kern = photo_bwd3_kernel<R, TH, TW, NT, MINB, OCC, MS>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
     configured = true;
   }
-  dim3 grid(ceil_div(p.d.W, TW), ceil_div(p.d.H, TH), p.d.B);
-  ProfScope prof(OCC ? "photo_occ_bwd_kernel" : "photo_bwd_kernel", st);
+  dim3 grid(ceil_div(p.d.W, TW), ceil_div(p.d.H, TH), p.d.B * (MS ? p.ns : 1));
+  ProfScope prof(OCC ? "photo_occ_bwd_kernel" : (MS ? "photo_bwd_ms_kernel" : "photo_bwd_kernel"), st);
   kern<<<grid, NT, C::smem_bytes, st>>>(p);
   return check_launch("photo_bwd3_kernel");
 }
@@ -1173,6 +1190,7 @@ int launch_photo_bwd3(const PhotoBwdParams& p, cudaStream_t st) {
 template <int R>
 int dispatch_photo_bwd3(const PhotoBwdParams& p, cudaStream_t st) {
   if (p.g_reg) return launch_photo_bwd3<R, 16, 32, 256, 2, true>(p, st);   // indoor variant
+  if (p.ns > 0) return launch_photo_bwd3<R, 16, 32, 256, 3, false, true>(p, st);   // all scales in one launch
   static const int cfg = env_int("SQLX_BWD_CFG", 0);
   switch (cfg) {
     case 1: return launch_photo_bwd3<R, 16, 32, 256, 4>(p, st);
@@ -1319,6 +1337,7 @@ int photo_bwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const 
   p.K = K; p.invK = inv_K; p.T = T; p.argmin = argmin; p.coef = ssim_coef; p.g_loss = g_loss; p.scale = scale;
   p.d_depth_lr = d_depth_lr; p.g_up = g_up; p.q_up = q_up; p.g_up_accumulate = g_up_accumulate;
   p.dP = dP;
+  p.ns = 0;
   p.g_reg = g_reg;
   for (int s = 0; s < SQLX_MAX_SOURCES; ++s) {
     p.ref[s] = (g_reg && ref_depths && s < desc->S) ? ref_depths[s] : nullptr;
@@ -1328,6 +1347,42 @@ int photo_bwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const 
     SQLX_REQUIRE(ref_depths && d_ref_depths, "the indoor variant needs the source frames' depth maps and their gradients");
     for (int s = 0; s < desc->S; ++s) SQLX_REQUIRE(p.ref[s] && p.d_ref[s], "ref_depths[%d] / d_ref_depths[%d] is NULL", s, s);
   }
+  return r == 3 ? dispatch_photo_bwd3<3>(p, st) : (r == 1 ? dispatch_photo_bwd3<1>(p, st) : dispatch_photo_bwd3<0>(p, st));
+}
+
+int photo_bwd3_ms_launch(const sqlx_photo_desc* desc, int ns, const float* const* depth_up, const float* target,
+                         const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
+                         size_t T_stride, const uint8_t* const* argmin, const float* ssim_coef, size_t coef_stride,
+                         const float* g_loss, float scale, float* const* g_up, float* const* q_up, unsigned accumulate_mask,
+                         float* dP, size_t dP_stride, cudaStream_t st) {
+  if (int e = check_desc(desc)) return e;
+  SQLX_REQUIRE(ns >= 1 && ns <= SQLX_MAX_SCALES, "num_scales %d outside 1..%d", ns, SQLX_MAX_SCALES);
+  SQLX_REQUIRE(depth_up && target && sources_rgba && K && inv_K && T && argmin && g_loss && g_up && dP, "NULL pointer argument");
+  const int r = (desc->flags & SQLX_NO_SSIM) ? 0 : desc->ssim_radius;
+  SQLX_REQUIRE(r == 0 || ssim_coef, "the backward needs the SSIM coefficients exported by the forward");
+  SQLX_REQUIRE((long long)desc->B * ns <= 65535, "batch x scales exceeds the grid's z extent");
+  PhotoBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.d = *desc;
+  p.target = target;
+  for (int s = 0; s < desc->S; ++s) {
+    p.src[s] = reinterpret_cast<const float4*>(sources_rgba[s]);
+    SQLX_REQUIRE(p.src[s], "source %d is NULL", s);
+    SQLX_REQUIRE((reinterpret_cast<uintptr_t>(p.src[s]) & 15) == 0, "source %d is not 16-byte aligned", s);
+  }
+  p.K = K; p.invK = inv_K; p.T = T; p.coef = ssim_coef; p.g_loss = g_loss; p.scale = scale; p.dP = dP;
+  p.ns = ns;
+  p.ms_accumulate = accumulate_mask;
+  p.ms_T_stride = T_stride; p.ms_coef_stride = coef_stride; p.ms_dP_stride = dP_stride;
+  for (int i = 0; i < ns; ++i) {
+    SQLX_REQUIRE(depth_up[i] && argmin[i] && g_up[i], "scale %d: NULL pointer", i);
+    p.ms_depth_up[i] = depth_up[i];
+    p.ms_argmin[i] = argmin[i];
+    p.ms_g_up[i] = g_up[i];
+    p.ms_q_up[i] = q_up ? q_up[i] : nullptr;
+  }
+  p.depth_lr = depth_up[0];   // never read: every scale has its upsampled plane
+  p.g_up = g_up[0];
   return r == 3 ? dispatch_photo_bwd3<3>(p, st) : (r == 1 ? dispatch_photo_bwd3<1>(p, st) : dispatch_photo_bwd3<0>(p, st));
 }
 

@@ -28,5 +28,13 @@ int photo_bwd3_launch(const sqlx_photo_desc* desc, const float* depth_lr, const 
                       // indoor variant: source depths, their gradients (atomically accumulated), d loss / d reg-sum
                       const float* const* ref_depths = nullptr, float* const* d_ref_depths = nullptr,
                       const float* g_reg = nullptr);
+// All loss scales in ONE backward launch (blockIdx.z = scale * B + sample): g_up[i] / q_up[i] [B,H,W] per scale (q_up
+// entries may be NULL), bit i of accumulate_mask: g_up[i] += instead of =; T, ssim_coef and dP advance by their strides
+// (in floats) per scale.
+int photo_bwd3_ms_launch(const sqlx_photo_desc* desc, int ns, const float* const* depth_up, const float* target,
+                         const float* const* sources_rgba, const float* K, const float* inv_K, const float* T,
+                         size_t T_stride, const uint8_t* const* argmin, const float* ssim_coef, size_t coef_stride,
+                         const float* g_loss, float scale, float* const* g_up, float* const* q_up, unsigned accumulate_mask,
+                         float* dP, size_t dP_stride, cudaStream_t st);
 size_t photo_max_ctas(const sqlx_photo_desc* d);   // upper bound of *ctas for any tile configuration
 }  // namespace sqlx

@@ -116,20 +116,20 @@ __global__ void __launch_bounds__(kHeadBwdThreads) head_linear_bwd_kernel(
   // ---- 32 columns of dx
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + lane;
-  for (int base = threadIdx.x; base < N * kHeadMaxB; base += 4 * kHeadBwdThreads) {    // loads of four elements in flight
-    float v[4], a[4];
+  // dz staging: one output row n per thread and trip, all samples' dy (and y) loads in flight together; every load is
+  // coalesced across the threads (consecutive n), the 16 values of a row leave as four 128-bit shared stores
+  for (int n = threadIdx.x; n < N; n += kHeadBwdThreads) {
+    float v[kHeadMaxB], a[kHeadMaxB];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = base + j * kHeadBwdThreads, n = i >> 4, b = i & 15;
-      const bool live = i < N * kHeadMaxB && b < B;
-      v[j] = live ? __ldg(dy + (size_t)b * N + n) : 0.f;
-      a[j] = (live && leaky) ? __ldg(y + (size_t)b * N + n) : 1.f;
+    for (int b = 0; b < kHeadMaxB; ++b) {
+      v[b] = b < B ? __ldg(dy + (size_t)b * N + n) : 0.f;
+      a[b] = (b < B && leaky) ? __ldg(y + (size_t)b * N + n) : 1.f;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = base + j * kHeadBwdThreads;
-      if (i < N * kHeadMaxB) sdz[i] = (a[j] > 0.f) ? v[j] : v[j] * kLeakySlope;
-    }
+    for (int b = 0; b < kHeadMaxB; ++b) v[b] = (a[b] > 0.f) ? v[b] : v[b] * kLeakySlope;
+    float4* dst = reinterpret_cast<float4*>(sdz + (size_t)n * kHeadMaxB);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
   __syncthreads();
   float acc[kHeadMaxB];
@@ -138,12 +138,13 @@ __global__ void __launch_bounds__(kHeadBwdThreads) head_linear_bwd_kernel(
   const int per = (N + kHeadXWarps - 1) / kHeadXWarps;
   const int n0 = warp * per, n1 = min(N, n0 + per);
   const bool kin = k < K;
-  for (int nb = n0; nb < n1; nb += 8) {
-    float wv[8];
+  constexpr int kRows = 16;                     // weight rows in flight per warp and trip
+  for (int nb = n0; nb < n1; nb += kRows) {
+    float wv[kRows];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) wv[j] = (kin && nb + j < n1) ? __ldg(W + (size_t)(nb + j) * K + k) : 0.f;
+    for (int j = 0; j < kRows; ++j) wv[j] = (kin && nb + j < n1) ? __ldg(W + (size_t)(nb + j) * K + k) : 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < kRows; ++j) {
       if (nb + j >= n1) break;
       const float4* zr = reinterpret_cast<const float4*>(sdz + (size_t)(nb + j) * kHeadMaxB);
 #pragma unroll

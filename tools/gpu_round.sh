@@ -11,5 +11,5 @@ timeout 300 python bench.py --config 3 --no-cpu-baseline > gpurun_out/bench_c3.j
 timeout 120 python tools/time_sql.py > gpurun_out/time_sql_c2.log 2>&1
 timeout 120 python tools/time_sql.py 8 160 512 128 128 > gpurun_out/time_sql_c3.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python profiles/run_step.py 2 > gpurun_out/ncu_launch.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'photo_fwd3|photo_bwd3|identity3|sql_tc|ms_|head_' -c 34 -o gpurun_out/full_round python profiles/run_step.py 1 > gpurun_out/ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'photo_fwd3|photo_bwd3|identity3|sql_tc|ms_|head_' -c 28 -o gpurun_out/full_round python profiles/run_step.py 1 > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out

@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--f32-frames", action="store_true",
                     help="ship the frames as float32 in the end-to-end loop (default: uint8, converted on the device)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--allreduce-after-step", action="store_true",
+                    help="N > 1: issue the gradient all-reduce after the step instead of inside it (overlapping the last "
+                         "backward kernel); A/B switch")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     return ap.parse_args()
 
@@ -280,7 +283,20 @@ def main():
     assert sqlx.lib().sqlx_device_ok(local_rank) == 1, "libsqlx targets sm_100a (B200) only"
 
     torch.manual_seed(0)
-    hp = HotPath(cfg, device=dev, use_graph=not args.no_graph, num_slots=2)
+    # N > 1: the path's one exchange step -- a single bucketed NCCL all-reduce (average) of the parameter gradients --
+    # is issued inside the step on a communication stream as soon as the last parameter gradient exists, so it
+    # overlaps the summary-path backward kernel (captured into the step's CUDA graph with everything else)
+    exchange_in_step = world > 1 and not args.allreduce_after_step
+    bucket_box = [None]
+
+    def exchange(grads):
+        if bucket_box[0] is None:
+            from sqlx.dist import GradBucket
+            bucket_box[0] = GradBucket(grads)
+        bucket_box[0].allreduce_(grads)
+
+    hp = HotPath(cfg, device=dev, use_graph=not args.no_graph, num_slots=2,
+                 grad_exchange=exchange if exchange_in_step else None)
     if world > 1:   # identical initial weights on every rank
         for p in hp.parameters():
             dist.broadcast(p.data, 0)
@@ -298,12 +314,29 @@ def main():
         hp.capture(slot=0)
         hp.capture(slot=1)
 
+    exchange_check = None
+    if exchange_in_step:
+        # pre-flight: the gradients of a step with the in-step (overlapped, graph-captured) exchange equal those of an
+        # eager step followed by a plain bucketed all-reduce
+        hp.step(0)
+        torch.cuda.synchronize()
+        fused = [g.clone() for g in hp.param_grads()]
+        hp.grad_exchange = None
+        hp.step_eager(0)
+        from sqlx.dist import GradBucket
+        ref = hp.param_grads()
+        GradBucket(ref).allreduce_(ref)
+        torch.cuda.synchronize()
+        exchange_check = max(float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)) for a, b in zip(fused, ref))
+        hp.grad_exchange = exchange
+        assert exchange_check < 1e-4, "in-step gradient exchange disagrees with the plain all-reduce: %g" % exchange_check
+
     bucket = None
 
     def allreduce_grads():
         """the path's one exchange step: a single bucketed NCCL all-reduce (average) of the parameter gradients"""
         nonlocal bucket
-        if world == 1:
+        if world == 1 or exchange_in_step:
             return
         grads = hp.param_grads()
         if bucket is None:
@@ -405,9 +438,22 @@ def main():
     prof = _lib.profile_report()
     _lib.profile_enable(False)
 
+    def finish():
+        """N > 1 teardown.  With the all-reduce captured inside the step's CUDA graphs, destroying the NCCL communicator
+        while those graphs are alive blocks forever (observed on 2 x B200, torch 2.11 / NCCL 2.28): drop the graphs, drain
+        the device, and leave without the communicator teardown (the process is exiting anyway)."""
+        if world == 1:
+            return
+        torch.cuda.synchronize()
+        if exchange_in_step:
+            hp.graphs = [None] * len(hp.graphs)
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+        dist.destroy_process_group()
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish()
         return
 
     peaks = {}
@@ -459,6 +505,12 @@ def main():
     config["l2"] = ("no explicit flush: every step streams %.0f MB of inputs plus %.0f MB of gradients through a 126 MB L2"
                     % (total_bytes / 1e6, (hb["x"].numel() * 4) / 1e6))
     config["submission"] = "eager" if args.no_graph else "cuda_graph"
+    if world > 1:
+        config["grad_exchange"] = ("one bucketed NCCL all-reduce (average) of the parameter gradients per step, issued inside "
+                                   "the step on a communication stream when the last parameter gradient exists (overlaps the "
+                                   "summary-path backward kernel; part of the CUDA graph); max rel. difference to a plain "
+                                   "all-reduce after the step: %.2g" % exchange_check) if exchange_in_step else \
+            "one bucketed NCCL all-reduce (average) of the parameter gradients after the step"
     config["e2e_pipeline"] = ("H2D of batch i+1 on a copy stream overlaps the step on batch i (2 device input sets); "
                               "tie-break noise drawn on the device instead of copied from the host; the loss of every step is "
                               "copied to pinned host memory and read by the host one step later; frames shipped as %s"
@@ -472,8 +524,7 @@ def main():
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "kernels": kernels, "kernel_ms_per_step": step_ms_kernels, "loss": float(hp.loss)}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

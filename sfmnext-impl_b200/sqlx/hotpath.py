@@ -45,7 +45,7 @@ class HotPath(torch.nn.Module):
     """Parameters: the decoder's 1x1 conv (convert_to_prob.0) and bins_regressor.  Inputs live in static
     device buffers `self.inp[name]` (see HotPathConfig.input_shapes); `load()` copies a host batch into them."""
 
-    def __init__(self, cfg, device="cuda", use_graph=True, num_slots=1):
+    def __init__(self, cfg, device="cuda", use_graph=True, num_slots=1, grad_exchange=None):
         super().__init__()
         nn = torch.nn
         self.cfg = cfg
@@ -104,6 +104,12 @@ class HotPath(torch.nn.Module):
         # zero-fill + accumulate kernels per parameter); step(slot) points p.grad at the replayed graph's tensors
         self.slot_grads = [None] * num_slots
         self.side_stream = None
+        # grad_exchange(list of gradient tensors): in-place data-parallel exchange (e.g. GradBucket.allreduce_) of the
+        # parameter gradients.  It is issued INSIDE the step, on a side stream, as soon as the last parameter gradient
+        # exists, so that it overlaps the summary-path backward kernel; the step (eager or captured graph, NCCL
+        # collectives are capturable) ends with the main stream waiting for it.
+        self.grad_exchange = grad_exchange
+        self.comm_stream = None
 
     # ------------------------------------------------------------------ data
     def load(self, host_batch, non_blocking=True, slot=0):
@@ -180,7 +186,8 @@ class HotPath(torch.nn.Module):
             identity = P.identity_losses(I["target"], sources)
             packed = [P.pack_rgba(src) for src in sources]
         pred = S.sql_tail(I["x"], I["queries"], conv.weight.view(c.D, c.Q), conv.bias, self._centers,
-                          tuple(self.bins_regressor.parameters()))
+                          tuple(self.bins_regressor.parameters()),
+                          on_param_grads=self._start_grad_exchange if self.grad_exchange is not None else None)
         main.wait_stream(side)
         disps = {s: (pred if s == 0 else I["disp%d" % s]) for s in c.scales}
         target_pyr = {s: (I["target"] if s == 0 else I["target%d" % s]) for s in c.scales}
@@ -191,6 +198,17 @@ class HotPath(torch.nn.Module):
                                    width=c.W, scales=c.scales, disparity_smoothness=c.disparity_smoothness,
                                    identity=identity, packed_sources=packed)
         return out["loss"], pred
+
+    def _start_grad_exchange(self, grads):
+        """fork: the exchange runs on the communication stream after everything enqueued so far; returns the join"""
+        main = torch.cuda.current_stream()
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream()
+        comm = self.comm_stream
+        comm.wait_stream(main)
+        with torch.cuda.stream(comm):
+            self.grad_exchange(grads)
+        return lambda: torch.cuda.current_stream().wait_stream(comm)
 
     def _zero_grads(self, slot=0):
         for p in self.parameters():

@@ -250,7 +250,7 @@ class _SqlTail(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, queries, Wp, bp, centers_fn, n_params, *params):
+    def forward(ctx, x, queries, Wp, bp, centers_fn, n_params, on_param_grads, *params):
         xc, qc, Wc, bc = _f32c(x), _f32c(queries), _f32c(Wp), _f32c(bp)
         summary, row_max, row_sum, _ = summary_fwd(xc, qc)
         with torch.enable_grad():
@@ -268,6 +268,7 @@ class _SqlTail(torch.autograd.Function):
             ctx.save_for_backward(xc, qc, Wc, bc, cc, summary, row_max, row_sum)
         ctx.graph = (s_leaf, centers)
         ctx.params = params
+        ctx.on_param_grads = on_param_grads
         return pred
 
     @staticmethod
@@ -281,8 +282,15 @@ class _SqlTail(torch.autograd.Function):
             d_Wp = torch.einsum("bde,bqe->dq", d_M, qc)
             grads = torch.autograd.grad(centers, [s_leaf] + need, d_centers, allow_unused=True)
             d_summary = grads[0] if grads[0] is not None else torch.zeros_like(summary)
+            join = None
+            if ctx.on_param_grads is not None:
+                # every parameter gradient of the tail exists now; the summary-path backward (the longest kernel of the
+                # tail) is still to run: the caller's gradient exchange overlaps it
+                join = ctx.on_param_grads([d_Wp, d_bp] + [g_ for g_ in grads[1:] if g_ is not None])
             d_x, d_q = bwd_summary(xc, qc, summary, row_max, row_sum, _f32c(d_summary), d_x=d_x)
             d_q = d_q + torch.matmul(Wc.t(), d_M)        # regression-path part of d_K:  Wp^T dM
+            if join is not None:
+                join()
         else:
             xc, qc, Wc, bc, cc, summary, row_max, row_sum = ctx.saved_tensors
             d_centers, d_Wp, d_bp = bwd_reduce(xc, qc, Wc, bc, cc, g)
@@ -294,13 +302,17 @@ class _SqlTail(torch.autograd.Function):
         it = iter(grads[1:])
         d_params = tuple((next(it) if p.requires_grad else None) for p in ctx.params)
         ctx.graph = None
-        return (d_x, d_q, d_Wp.view_as(Wc), d_bp, None, None) + d_params
+        return (d_x, d_q, d_Wp.view_as(Wc), d_bp, None, None, None) + d_params
 
 
-def sql_tail(x, queries, Wp, bp, centers_fn, params=()):
-    """pred [B,1,h,w] = sum_d softmax_d(Wp (x^T K) + bp) * centers_fn(summary(x, K))."""
+def sql_tail(x, queries, Wp, bp, centers_fn, params=(), on_param_grads=None):
+    """pred [B,1,h,w] = sum_d softmax_d(Wp (x^T K) + bp) * centers_fn(summary(x, K)).
+
+    on_param_grads(list of gradient tensors) -> join callable or None: called in the backward as soon as the gradients
+    of Wp, bp and `params` exist (before the summary-path kernel runs), e.g. to start their all-reduce on a side
+    stream; the returned callable is invoked once the remaining backward kernels are enqueued (tensor-core path)."""
     params = tuple(params)
-    return _SqlTail.apply(x, queries, Wp, bp, centers_fn, len(params), *params)
+    return _SqlTail.apply(x, queries, Wp, bp, centers_fn, len(params), on_param_grads, *params)
 
 
 class Depth_Decoder_QueryTr(torch.nn.Module):

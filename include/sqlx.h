@@ -65,7 +65,7 @@ int sqlx_profile_report(char* buf, size_t buf_bytes);
 /* Per-sample statistics of the bilinearly upsampled (align_corners=False) depth:
  *   stats[b][0] = mean_{HxW} d_up,  stats[b][1] = mean_{HxW} 1/d_up
  * replaces F.interpolate + (1/depth).mean  (trainer.py:395-396, 417-418) and disp.mean (trainer.py:535).
- * stats must be zeroed by the caller?  No: the kernel overwrites.  workspace: sqlx_depth_stats_workspace_bytes. */
+ * stats is overwritten (no zeroing needed).  workspace: sqlx_depth_stats_workspace_bytes. */
 size_t sqlx_depth_stats_workspace_bytes(int B, int H, int W);
 int sqlx_depth_stats_fwd(const float* depth_lr, int B, int h, int w, int H, int W,
                          float* stats /*[B,2]*/, void* workspace, size_t workspace_bytes, void* stream);
@@ -99,7 +99,7 @@ int sqlx_ssim_bwd(const float* x, const float* y, const float* g_out, int B, int
  *   identity  [B,S,H,W] or NULL (no automask): sqlx_reprojection_loss_fwd(source_f, target), WITHOUT noise
  *   noise     [B,Sn,H,W] or NULL: standard-normal tie-break noise, Sn = 1 if AVG_REPROJ else S (trainer.py:516)
  * outputs
- *   loss_sum  [1]  double?  no: float, = sum over b,v,u of the per-pixel minimum (caller divides by B*H*W)
+ *   loss_sum  [1]  float: sum over b,v,u of the per-pixel minimum (caller divides by B*H*W)
  *   argmin    [B,H,W] uint8: index into cat(identity, reprojection) exactly as torch.min(combined,dim=1)
  *   ssim_coef [B,S,3,3,H,W] (sqlx_photo_coef_bytes) or NULL for a forward-only call: d SSIM/d(mean_x, E[x^2], E[xy])
  *             per source / channel / pixel.  sqlx_photo_bwd is an arg-min masked adjoint box filter of these planes

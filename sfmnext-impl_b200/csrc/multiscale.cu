@@ -298,7 +298,7 @@ __global__ void ms_smooth_loss_kernel(MsShapes sh, float* __restrict__ spartial,
     const float* q = spartial + (size_t)sb * kMsBlocks * 3 + k;
     float v = 0.f;
 #pragma unroll 8
-    for (int j = 0; j < kMsBlocks; ++j) v += __ldcg(q + j * 3);
+    for (int j = 0; j < (int)gridDim.x; ++j) v += __ldcg(q + j * 3);
     sums[i] = v;
   }
   // photometric per-CTA partials of every scale: strided double sums, one tree for all scales
@@ -739,6 +739,16 @@ MsPose make_pose(const sqlx_pose_inputs* poses, int S, float* const* d_aa, float
   return ps;
 }
 
+// Blocks per (scale, sample) actually launched (<= kMsBlocks, which sizes the partial arrays): about 15 frame pixels
+// per thread -- measured on a B200 at 192x640 x 4 scales x 12 samples: 96 blocks 36 + 40 us (statistics + smoothness
+// kernels), 48: 32 + 34, 32: 30 + 31, 24: 29 + 33.  SQLX_MS_BLOCKS overrides.
+int ms_blocks(int H, int W) {
+  static const int forced = []() { const char* v = getenv("SQLX_MS_BLOCKS"); return v ? atoi(v) : 0; }();
+  int k = forced > 0 ? forced : (int)(((long long)H * W + 256 * 15 - 1) / (256 * 15));
+  if (forced <= 0 && k < 24) k = 24;
+  return k < 1 ? 1 : (k > kMsBlocks ? kMsBlocks : k);
+}
+
 sqlx_photo_desc scale_photo_desc(const sqlx_ms_desc* d, int s) {
   sqlx_photo_desc pd = d->photo;
   pd.h = d->h[s]; pd.w = d->w[s];
@@ -786,7 +796,7 @@ extern "C" int sqlx_ms_loss_fwd(const sqlx_ms_desc* d, const float* const* depth
     return check_launch("cudaMemsetAsync(counters)");
   {
     ProfScope prof("ms_stats_pose_kernel", st);
-    ms_stats_pose_kernel<<<dim3(kMsBlocks, B, ns), 256, 0, st>>>(
+    ms_stats_pose_kernel<<<dim3(ms_blocks(d->photo.H, d->photo.W), B, ns), 256, 0, st>>>(
         sh, make_pose(poses, S, nullptr, nullptr), rescale, reinterpret_cast<float*>(ws + L.partial), counters + 64,
         stats, T);
     if (int e = check_launch("ms_stats_pose_kernel")) return e;
@@ -814,7 +824,7 @@ extern "C" int sqlx_ms_loss_fwd(const sqlx_ms_desc* d, const float* const* depth
   }
   {
     ProfScope prof("ms_smooth_loss_kernel", st);
-    ms_smooth_loss_kernel<<<dim3(kMsBlocks, B, ns), 256, sizeof(float) * (size_t)ns * B, st>>>(sh, reinterpret_cast<float*>(ws + L.spartial), sums,
+    ms_smooth_loss_kernel<<<dim3(ms_blocks(d->photo.H, d->photo.W), B, ns), 256, sizeof(float) * (size_t)ns * B, st>>>(sh, reinterpret_cast<float*>(ws + L.spartial), sums,
                                                                   reinterpret_cast<float*>(ws + L.photo_partial),
                                                                   L.max_ctas, ctas, counters, loss);
     if (int e = check_launch("ms_smooth_loss_kernel")) return e;

@@ -230,3 +230,48 @@ def test_bins_head_matches_torch(B, Q, E, D):
     assert float((c.double() - c64).abs().max() / c64.abs().max()) < 1e-5
     for a, b in zip(grads, grads64):
         assert float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30)) < 1e-4
+
+
+def test_param_grad_hook_overlap_semantics():
+    """sql_tail(on_param_grads=...): the hook sees every parameter gradient of the tail before the summary-path kernel
+    runs; an in-place exchange it starts on a side stream (here: halving, standing in for the all-reduce average of two
+    identical ranks' doubled gradients) is what ends up in .grad, and the gradients of x / queries are untouched."""
+    import sqlx
+    torch.manual_seed(3)
+    B, E, h, w, Q, D = 4, 32, 48, 64, 64, 64
+    x = torch.randn(B, E, h, w, device="cuda")
+    q = 0.4 * torch.randn(B, Q, E, device="cuda")
+    conv = torch.nn.Conv2d(Q, D, 1).cuda()
+    mlp = torch.nn.Sequential(torch.nn.Linear(Q * E, 16 * Q), torch.nn.LeakyReLU(), torch.nn.Linear(16 * Q, 256),
+                              torch.nn.LeakyReLU(), torch.nn.Linear(256, D)).cuda()
+    params = [conv.weight, conv.bias] + list(mlp.parameters())
+    gout = torch.randn(B, 1, h, w, device="cuda")
+    side = torch.cuda.Stream()
+    seen = []
+
+    def hook(grads):
+        seen.append(len(grads))
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for g in grads:
+                g.mul_(0.5)
+        return lambda: torch.cuda.current_stream().wait_stream(side)
+
+    def run(cb):
+        xs, qs = x.clone().requires_grad_(True), q.clone().requires_grad_(True)
+        for p in params:
+            p.grad = None
+        pred = sqlx.sql_tail(xs, qs, conv.weight.view(D, Q), conv.bias,
+                             lambda s: sqlx.sql.bins_head(s.reshape(B, Q * E), mlp, 0.001, 80.0), tuple(mlp.parameters()),
+                             on_param_grads=cb)
+        (pred * gout).sum().backward()
+        torch.cuda.synchronize()
+        return [xs.grad.clone(), qs.grad.clone()] + [p.grad.clone() for p in params]
+
+    ref = run(None)
+    got = run(hook)
+    assert seen == [len(params)]
+    assert _rel(got[0], ref[0]) < 1e-6 and _rel(got[1], ref[1]) < 1e-6
+    for a, b in zip(got[2:], ref[2:]):
+        assert _rel(a, 0.5 * b) < 1e-6

@@ -428,6 +428,59 @@ __global__ void __launch_bounds__(kNT) sql_bwd_reduce_kernel(
   }
 }
 
+// The three partial-sum reductions after the regression backward in ONE launch (grid (ceil(D*32/256), B, 3)):
+//   z = 0: d_M[b][i]  = sum_{c < chunks} part_dM[(b*chunks + c) * D*32 + i]
+//   z = 1: d_c[b][d]  = sum_{c < chunks} part_dc[(b*chunks + c) * D + d]
+//   z = 2: d_b[d]     = sum_{c < B*chunks} part_db[c * D + d]   (one block; two halves of the CTAs, then a fixed-order add)
+__global__ void __launch_bounds__(256) sum_partials3_kernel(const float* __restrict__ part_dM, const float* __restrict__ part_dc,
+                                                            const float* __restrict__ part_db, int chunks, int B, int D,
+                                                            float* __restrict__ d_M, float* __restrict__ d_c,
+                                                            float* __restrict__ d_b) {
+  __shared__ float half[256];
+  const int b = blockIdx.y, t = threadIdx.x;
+  if (blockIdx.z == 0) {
+    const int stride = D * 32, i = blockIdx.x * 256 + t;
+    if (i >= stride) return;
+    const float* src = part_dM + (size_t)b * chunks * stride + i;
+    float acc = 0.f;
+    int c = 0;
+    for (; c + 8 <= chunks; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = src[(size_t)(c + j) * stride];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += v[j];
+    }
+    for (; c < chunks; ++c) acc += src[(size_t)c * stride];
+    d_M[(size_t)b * stride + i] = acc;
+  } else if (blockIdx.z == 1) {
+    if (blockIdx.x != 0 || t >= D) return;
+    const float* src = part_dc + (size_t)b * chunks * D + t;
+    float acc = 0.f;
+    for (int c = 0; c < chunks; ++c) acc += src[(size_t)c * D];
+    d_c[(size_t)b * D + t] = acc;
+  } else {
+    if (blockIdx.x != 0 || b != 0) return;
+    const int d = t & 127, g = t >> 7, ctas = B * chunks;      // D <= 128: two groups of 128 threads
+    const int c0 = g * (ctas / 2), c1 = g ? ctas : ctas / 2;
+    float acc = 0.f;
+    if (d < D) {
+      int c = c0;
+      for (; c + 8 <= c1; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = part_db[(size_t)(c + j) * D + d];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += v[j];
+      }
+      for (; c < c1; ++c) acc += part_db[(size_t)c * D + d];
+    }
+    half[t] = acc;
+    __syncthreads();
+    if (g == 0 && d < D) d_b[d] = half[d] + half[128 + d];
+  }
+}
+
 // out[i] = sum_{c < count} part[(c0 + c) * stride + i]     grid.y selects the group (c0 = group * count)
 __global__ void sum_partials_kernel(const float* __restrict__ part, int count, int stride, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -935,17 +988,15 @@ extern "C" int sqlx_sql_bwd_pred_mix(const float* x, const float* Mx, const floa
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int chunks = 0, tpc = 0;
   tc_bwd_plan(B, n, &chunks, &tpc);
-  const int ctas = B * chunks;
+  const int ctas = B * chunks;   // partial arrays are [ctas][...]
   float* part_dM = reinterpret_cast<float*>(workspace);
   float* part_db = part_dM + (size_t)ctas * D * 32;
   float* part_dc = part_db + (size_t)ctas * D;
   if (int e = tc_bwd_pred_mix(x, Mx, bp, centers, g_pred, B, D, n, d_x, part_dM, part_db, part_dc, chunks, tpc, st)) return e;
-  sum_partials_kernel<<<dim3(ceil_div(D * 32, 256), B), 256, 0, st>>>(part_dM, chunks, D * 32, d_M);
-  if (int e = check_launch("sum_partials_kernel")) return e;
-  sum_partials_kernel<<<dim3(ceil_div(D, 256), 1), 256, 0, st>>>(part_db, ctas, D, d_bp);
-  if (int e = check_launch("sum_partials_kernel")) return e;
-  sum_partials_kernel<<<dim3(ceil_div(D, 256), B), 256, 0, st>>>(part_dc, chunks, D, d_centers);
-  return check_launch("sum_partials_kernel");
+  SQLX_REQUIRE(D <= 128, "dim_out %d exceeds the tensor-core path's limit", D);
+  sum_partials3_kernel<<<dim3(ceil_div(D * 32, 256), B, 3), 256, 0, st>>>(part_dM, part_dc, part_db, chunks, B, D, d_M, d_centers,
+                                                                         d_bp);
+  return check_launch("sum_partials3_kernel");
 }
 
 extern "C" int sqlx_sql_bwd_summary(const float* x, const float* queries, const float* summary, const float* row_max,

@@ -739,6 +739,10 @@ MsPose make_pose(const sqlx_pose_inputs* poses, int S, float* const* d_aa, float
   return ps;
 }
 
+// The one-launch multi-scale photometric kernels are instantiated and GPU-tested for the live 7x7 SSIM; the 3x3 and
+// --no_ssim variants go through the per-scale launches.
+bool ms_fusable(const sqlx_ms_desc* d) { return !(d->photo.flags & SQLX_NO_SSIM) && d->photo.ssim_radius == 3; }
+
 // Blocks per (scale, sample) actually launched (<= kMsBlocks, which sizes the partial arrays): about 15 frame pixels
 // per thread -- measured on a B200 at 192x640 x 4 scales x 12 samples: 96 blocks 36 + 40 us (statistics + smoothness
 // kernels), 48: 32 + 34, 32: 30 + 31, 24: 29 + 33.  SQLX_MS_BLOCKS overrides.
@@ -803,7 +807,7 @@ extern "C" int sqlx_ms_loss_fwd(const sqlx_ms_desc* d, const float* const* depth
   }
   int ctas = 0;
   static const int fused = []() { const char* v = getenv("SQLX_MS_FUSED_FWD"); return v ? atoi(v) : 1; }();
-  if (fused && ns > 1) {
+  if (fused && ns > 1 && ms_fusable(d)) {
     // every scale in one launch: the target tile, its statistics and the identity losses are shared by the scales
     const sqlx_photo_desc pd = scale_photo_desc(d, 0);
     const float* dups[SQLX_MAX_SCALES];
@@ -873,7 +877,7 @@ extern "C" int sqlx_ms_loss_bwd(const sqlx_ms_desc* d, const float* const* depth
   if (cudaMemsetAsync(dP, 0, sizeof(float) * (size_t)ns * B * S * 12, st) != cudaSuccess)
     return check_launch("cudaMemsetAsync(dP)");
   static const int fused = []() { const char* v = getenv("SQLX_MS_FUSED_BWD"); return v ? atoi(v) : 1; }();
-  if (fused && ns > 1) {
+  if (fused && ns > 1 && ms_fusable(d)) {
     const sqlx_photo_desc pd = scale_photo_desc(d, 0);
     const float* dups[SQLX_MAX_SCALES];
     float* qups[SQLX_MAX_SCALES];

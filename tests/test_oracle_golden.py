@@ -106,3 +106,44 @@ def test_postprocess_disparity_golden():
     for i in range(3):
         out = O.batch_post_process_disparity(_t(z["l%d" % i]), _t(z["r%d" % i]))
         assert float((out - torch.from_numpy(z["out%d" % i])).abs().max()) < 1e-12
+
+
+def test_indoor_reduces_to_outdoor_when_depths_agree():
+    """Property of compute_losses_with_occ (trainer_indoor.py:636-651): with a fixed identity camera transform the source
+    depth is sampled at the pixel itself; if it equals the target depth, diff = 0, the weight is exactly 1, the
+    regularisation term vanishes and the photometric part equals compute_losses' (trainer.py:474-532)."""
+    import torch.nn.functional as F
+    from _cases import synth_photo_case
+    kw = synth_photo_case(seed=9, B=1, H=48, W=80, S=2)
+    for k in ("K", "inv_K"):
+        kw[k] = kw[k].double()
+    kw["disps"] = {0: kw["disps"][0].double()}
+    kw["target_pyr"] = {0: kw["target_pyr"][0].double()}
+    kw["sources"] = [t.double() for t in kw["sources"]]
+    kw["noises"] = {0: kw["noises"][0].double()}
+    B, H, W = 1, 48, 80
+    eye = torch.eye(4, dtype=torch.float64).unsqueeze(0).repeat(B, 1, 1)
+    poses = [{"T": eye}, {"T": eye}]
+    disp = kw["disps"][0]
+    up = F.interpolate(disp, [H, W], mode="bilinear", align_corners=False)
+    out = O.indoor_losses(disp, kw["target_pyr"][0], kw["sources"], [up, up], kw["K"], kw["inv_K"], poses,
+                          kw["noises"][0], height=H, width=W)
+    ref = O.photometric_losses({0: disp}, kw["target_pyr"], kw["sources"], kw["K"], kw["inv_K"], poses, kw["noises"],
+                               height=H, width=W, scales=(0,), rescale_translation=False, disparity_smoothness=0.0)
+    # (not exactly 0: inv_K is a float32 pseudo-inverse and Project3D adds eps = 1e-7 to z, layers.py:252)
+    assert float(out["reg"]) < 1e-6
+    assert abs(float(out["photo"]) - float(ref["loss"])) < 1e-6
+    assert float((out[("argmin", 0)] != ref[("argmin", 0)]).double().mean()) < 1e-3
+
+
+@pytest.mark.parametrize("variant", [{"no_ssim": True}, {"disable_automasking": True}, {"avg_reprojection": True}])
+def test_indoor_variants_are_finite_and_differentiable(variant):
+    kw, leaves, z = indoor_case("indoor_occ")
+    kw.update(variant)
+    if variant.get("avg_reprojection"):
+        kw["noise"] = kw["noise"][:, :1]
+    out = O.indoor_losses(**kw)
+    grads = torch.autograd.grad(out["loss"], list(leaves.values()), allow_unused=True)
+    assert bool(torch.isfinite(out["loss"]))
+    assert all(g is None or bool(torch.isfinite(g).all()) for g in grads)
+    assert grads[0] is not None and float(grads[0].abs().max()) > 0

@@ -132,7 +132,8 @@ def test_indoor_reduces_to_outdoor_when_depths_agree():
                                height=H, width=W, scales=(0,), rescale_translation=False, disparity_smoothness=0.0)
     # (not exactly 0: inv_K is a float32 pseudo-inverse and Project3D adds eps = 1e-7 to z, layers.py:252)
     assert float(out["reg"]) < 1e-6
-    assert abs(float(out["photo"]) - float(ref["loss"])) < 1e-6
+    # weight = 1 - sqrt(1 - (diff - 1)^2) = 1 - sqrt(2 diff - diff^2): a residual diff of 1e-7 leaves 1 - 4.5e-4
+    assert abs(float(out["photo"]) - float(ref["loss"])) < 1e-3 * float(ref["loss"])
     assert float((out[("argmin", 0)] != ref[("argmin", 0)]).double().mean()) < 1e-3
 
 

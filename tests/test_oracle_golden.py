@@ -134,7 +134,8 @@ def test_indoor_reduces_to_outdoor_when_depths_agree():
     assert float(out["reg"]) < 1e-6
     # weight = 1 - sqrt(1 - (diff - 1)^2) = 1 - sqrt(2 diff - diff^2): a residual diff of 1e-7 leaves 1 - 4.5e-4
     assert abs(float(out["photo"]) - float(ref["loss"])) < 1e-3 * float(ref["loss"])
-    assert float((out[("argmin", 0)] != ref[("argmin", 0)]).double().mean()) < 1e-3
+    # (the arg-min itself is not comparable here: with an identity transform every reprojection loss ties with its
+    # identity loss up to the 1e-5 noise)
 
 
 @pytest.mark.parametrize("variant", [{"no_ssim": True}, {"disable_automasking": True}, {"avg_reprojection": True}])

@@ -201,8 +201,8 @@ int sqlx_scale_loss_bwd(const sqlx_scale_desc* desc, const float* depth_lr, cons
                         size_t workspace_bytes, void* stream);
 
 /* ---- ALL loss scales as one forward and one backward call (the whole of generate_images_pred + compute_losses,
- * trainer.py:386-439 and 455-549).  What is not the fused photometric kernel is batched across scales: 13 kernel
- * launches per step for 4 scales; every reduction has a fixed order and the upsample adjoint is a gather, so the
+ * trainer.py:386-439 and 455-549).  Every kernel is batched across scales (the fused photometric forward / backward
+ * kernels take all scales in one launch): 3 + 4 kernel launches per step; every reduction has a fixed order and the upsample adjoint is a gather, so the
  * gradients are bit-reproducible run to run.
  *   depth_lr[s] [B,1,h[s],w[s]]   outputs[("disp", s)] (these ARE depth, trainer.py:399-402)
  *   color[s]    [B,3,Hc[s],Wc[s]] inputs[("color",0,s)]: either the depth map's own shape (used as is) or HxW

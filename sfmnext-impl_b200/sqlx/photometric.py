@@ -396,8 +396,9 @@ def _ptr_array(tensors, n):
 
 
 class _MultiScaleLoss(torch.autograd.Function):
-    """Every loss scale in one library call forward and one backward (csrc/multiscale.cu): 13 kernel launches per
-    step for 4 scales, one autograd node, pose gradients summed over scales inside the library."""
+    """Every loss scale in one library call forward and one backward (csrc/multiscale.cu): 3 + 4 kernel launches per
+    step whatever the number of scales (the fused photometric forward / backward kernels take all scales in one launch),
+    one autograd node, pose gradients summed over scales inside the library."""
 
     @staticmethod
     def forward(ctx, meta, *tensors):

@@ -175,7 +175,7 @@ def bin_centers(raw, min_val, max_val, norm="linear"):
 
 class _BinsHead(torch.autograd.Function):
     """summary [B, Q*E] -> bin centres [B, D] through the three Linear layers of bins_regressor and the centre
-    arithmetic, on the weight-streaming kernels of csrc/bins_head.cu (4 launches forward, 10 backward)."""
+    arithmetic, on the weight-streaming kernels of csrc/bins_head.cu (4 launches forward, 4 backward)."""
 
     @staticmethod
     def forward(ctx, s, W1, b1, W2, b2, W3, b3, min_val, max_val):

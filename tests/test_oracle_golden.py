@@ -149,3 +149,40 @@ def test_indoor_variants_are_finite_and_differentiable(variant):
     assert bool(torch.isfinite(out["loss"]))
     assert all(g is None or bool(torch.isfinite(g).all()) for g in grads)
     assert grads[0] is not None and float(grads[0].abs().max()) > 0
+
+
+# ---- the explicit-index rules (oracle/explicit.py) against the library primitives the reference calls
+def test_explicit_upsample_and_grid_sample_rules():
+    import torch.nn.functional as F
+    from oracle import explicit as X
+    g = torch.Generator().manual_seed(0)
+    for (h, w, H, W) in ((6, 10, 12, 20), (5, 7, 13, 17), (8, 8, 8, 8)):
+        x = torch.rand(1, 1, h, w, generator=g, dtype=torch.float64)
+        ref = F.interpolate(x, [H, W], mode="bilinear", align_corners=False)[0, 0].numpy()
+        assert np.abs(X.upsample_bilinear(x[0, 0].numpy(), H, W) - ref).max() < 1e-13
+    src = torch.rand(1, 3, 9, 11, generator=g, dtype=torch.float64)
+    grid = torch.rand(1, 6, 7, 2, generator=g, dtype=torch.float64) * 2.6 - 1.3      # some coordinates outside the frame
+    grid[0, 0, 0] = torch.tensor([1.0, 1.0])                                          # exactly the last pixel
+    grid[0, 0, 1] = torch.tensor([-1.0, -1.0])
+    ref = F.grid_sample(src, grid, padding_mode="border", align_corners=True)[0].numpy()
+    assert np.abs(X.grid_sample_border(src[0].numpy(), grid[0].numpy()) - ref).max() < 1e-13
+
+
+def test_explicit_ssim_softmax_centers_rules():
+    from oracle import explicit as X
+    g = torch.Generator().manual_seed(1)
+    a = torch.rand(1, 1, 12, 15, generator=g, dtype=torch.float64)
+    b = (a + 0.1 * torch.rand(1, 1, 12, 15, generator=g, dtype=torch.float64)).clamp(0, 1)
+    for radius in (3, 1):
+        ref = O.ssim(a, b, radius)[0, 0].numpy()
+        assert np.abs(X.ssim_reflect(a[0, 0].numpy(), b[0, 0].numpy(), radius) - ref).max() < 1e-12
+    x = torch.randn(1, 8, 5, 6, generator=g, dtype=torch.float64)
+    K = torch.randn(1, 4, 8, generator=g, dtype=torch.float64)
+    energy, summary = O.full_query(x, K)
+    e2, s2 = X.pixel_softmax_summary(x[0].reshape(8, 30).numpy(), K[0].numpy())
+    assert np.abs(e2 - energy[0].reshape(4, 30).numpy()).max() < 1e-12
+    assert np.abs(s2 - summary[0].numpy()).max() < 1e-12
+    r = torch.randn(2, 10, generator=g, dtype=torch.float64)
+    ref = O.bin_centers(r, 0.001, 80.0).numpy()
+    for i in range(2):
+        assert np.abs(X.bin_centers(r[i].numpy(), 0.001, 80.0) - ref[i]).max() < 1e-12

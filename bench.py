@@ -497,7 +497,7 @@ def main():
                for k, v in sorted(prof.items())}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # reported beside the N = 1 line only
         cpu = time_cpu(cfg, args, steps=3, warmup=1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 

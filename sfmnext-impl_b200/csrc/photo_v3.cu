@@ -266,7 +266,10 @@ struct Fwd3Cfg {
   static_assert((TH * TW) % NT == 0 && NT % TW == 0 && NT >= PH + PW, "tile / block shape");
 };
 
-template <int R, int TH, int TW, int NT, int MINB, bool MERGED, bool OCC = false, bool MS = false>
+// STG = 1 (candidate, selected with SQLX_FWD_MS_STAGE=1, not the default): the depth / target staging issues ALL of a
+// thread's region elements in one trip (6 elements: 6 depth loads, + 18 target loads on the first scale) instead of
+// two elements per trip -- one exposed global-load latency per scale instead of three.
+template <int R, int TH, int TW, int NT, int MINB, bool MERGED, bool OCC = false, bool MS = false, int STG = 0>
 __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const __grid_constant__ PhotoFwdParams p) {
   using C = Fwd3Cfg<R, TH, TW, NT, MERGED>;
   constexpr int PPT = C::PPT;
@@ -314,7 +317,34 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const __grid_const
     load_camera(p.K + b * 16, p.invK + b * 16, T_sc + ((size_t)b * S + threadIdx.x) * 16, cams[threadIdx.x]);
   __syncthreads();
 
-  {   // upsampled depth and (first scale only) the three target planes on the R halo, two elements per trip
+  if (STG == 1 && MS) {   // (MS: every scale has its upsampled plane) all elements of the thread in one trip
+    const float* up_map = p.ms_depth_up[sc] + (size_t)b * plane;
+    const float* tgb = p.target + (size_t)b * 3 * plane;
+    constexpr int NEL = (C::PH * C::PW + NT - 1) / NT;
+    float dv1[NEL], tv1[NEL][3];
+    int lr = threadIdx.x / C::PW, lc = threadIdx.x - lr * C::PW;
+#pragma unroll
+    for (int e = 0; e < NEL; ++e) {
+      if ((int)threadIdx.x + e * NT < C::PH * C::PW) {
+        const int off = rowt[lr].w * W + colt[lc].w;
+        dv1[e] = __ldg(up_map + off);
+        if (first) {
+          tv1[e][0] = __ldg(tgb + off); tv1[e][1] = __ldg(tgb + plane + off); tv1[e][2] = __ldg(tgb + 2 * plane + off);
+        }
+      }
+      region_advance<C::PW, NT>(lr, lc);
+    }
+    lr = threadIdx.x / C::PW; lc = threadIdx.x - lr * C::PW;
+#pragma unroll
+    for (int e = 0; e < NEL; ++e) {
+      if ((int)threadIdx.x + e * NT < C::PH * C::PW) {
+        const int o = lr * C::LD + lc;
+        dpl[o] = dv1[e];
+        if (first) { tg[o] = tv1[e][0]; tg[C::PLANE + o] = tv1[e][1]; tg[2 * C::PLANE + o] = tv1[e][2]; }
+      }
+      region_advance<C::PW, NT>(lr, lc);
+    }
+  } else {   // upsampled depth and (first scale only) the three target planes on the R halo, two elements per trip
     const float* lr_map = p.depth_lr + (size_t)b * p.d.h * p.d.w;
     const float* dup = MS ? p.ms_depth_up[sc] : p.depth_up;
     const float* up_map = dup ? dup + (size_t)b * plane : nullptr;
@@ -1141,10 +1171,10 @@ int env_int(const char* name, int dflt) {
 }
 constexpr int kMinTH = 16, kMinTW = 32;   // smallest tile of any configuration: sizes the per-CTA partial buffer
 
-template <int R, int TH, int TW, int NT, int MINB, bool MERGED = false, bool OCC = false, bool MS = false>
+template <int R, int TH, int TW, int NT, int MINB, bool MERGED = false, bool OCC = false, bool MS = false, int STG = 0>
 int launch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
   using C = Fwd3Cfg<R, TH, TW, NT, MERGED>;
-  auto kern = photo_fwd3_kernel<R, TH, TW, NT, MINB, MERGED, OCC, MS>;
+  auto kern = photo_fwd3_kernel<R, TH, TW, NT, MINB, MERGED, OCC, MS, STG>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
@@ -1160,7 +1190,11 @@ int launch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
 template <int R>
 int dispatch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
   if (p.partial_reg) return launch_photo_fwd3<R, 32, 32, 256, 2, false, true>(p, ctas, st);   // indoor variant
-  if (p.ns > 0) return launch_photo_fwd3<R, 32, 32, 256, 2, false, false, true>(p, ctas, st);  // all scales per CTA
+  if (p.ns > 0) {   // all scales per CTA
+    static const int stage = env_int("SQLX_FWD_MS_STAGE", 0);
+    if (stage == 1) return launch_photo_fwd3<R, 32, 32, 256, 2, false, false, true, 1>(p, ctas, st);
+    return launch_photo_fwd3<R, 32, 32, 256, 2, false, false, true>(p, ctas, st);
+  }
   static const int cfg = env_int("SQLX_FWD_CFG", 0);
   switch (cfg) {
     case 1: return launch_photo_fwd3<R, 16, 32, 256, 3>(p, ctas, st);

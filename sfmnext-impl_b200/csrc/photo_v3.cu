@@ -1191,8 +1191,14 @@ template <int R>
 int dispatch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
   if (p.partial_reg) return launch_photo_fwd3<R, 32, 32, 256, 2, false, true>(p, ctas, st);   // indoor variant
   if (p.ns > 0) {   // all scales per CTA
+    // candidates (not the default; tools/check_candidates.py runs the A/B): staging variant, other tile shapes
     static const int stage = env_int("SQLX_FWD_MS_STAGE", 0);
-    if (stage == 1) return launch_photo_fwd3<R, 32, 32, 256, 2, false, false, true, 1>(p, ctas, st);
+    static const int mscfg = env_int("SQLX_FWD_MS_CFG", 0);
+    if constexpr (R == 3) {
+      if (stage == 1) return launch_photo_fwd3<R, 32, 32, 256, 2, false, false, true, 1>(p, ctas, st);
+      if (mscfg == 1) return launch_photo_fwd3<R, 16, 32, 256, 3, false, false, true>(p, ctas, st);
+      if (mscfg == 5) return launch_photo_fwd3<R, 16, 32, 128, 4, false, false, true>(p, ctas, st);
+    }
     return launch_photo_fwd3<R, 32, 32, 256, 2, false, false, true>(p, ctas, st);
   }
   static const int cfg = env_int("SQLX_FWD_CFG", 0);
@@ -1224,7 +1230,14 @@ int launch_photo_bwd3(const PhotoBwdParams& p, cudaStream_t st) {
 template <int R>
 int dispatch_photo_bwd3(const PhotoBwdParams& p, cudaStream_t st) {
   if (p.g_reg) return launch_photo_bwd3<R, 16, 32, 256, 2, true>(p, st);   // indoor variant
-  if (p.ns > 0) return launch_photo_bwd3<R, 16, 32, 256, 3, false, true>(p, st);   // all scales in one launch
+  if (p.ns > 0) {   // all scales in one launch
+    static const int mscfg = env_int("SQLX_BWD_MS_CFG", 0);      // candidates, see tools/check_candidates.py
+    if constexpr (R == 3) {
+      if (mscfg == 2) return launch_photo_bwd3<R, 32, 32, 256, 2, false, true>(p, st);
+      if (mscfg == 3) return launch_photo_bwd3<R, 16, 32, 256, 2, false, true>(p, st);
+    }
+    return launch_photo_bwd3<R, 16, 32, 256, 3, false, true>(p, st);
+  }
   static const int cfg = env_int("SQLX_BWD_CFG", 0);
   switch (cfg) {
     case 1: return launch_photo_bwd3<R, 16, 32, 256, 4>(p, st);

@@ -5,6 +5,8 @@ compares loss, gradients and per-kernel times against the default.
   python tools/check_candidates.py                       # on a B200 (gpurun)
 
 Candidates:  SQLX_FWD_MS_STAGE=1   photo_fwd3_kernel<MS, STG=1>: depth/target staging in one trip per thread
+             SQLX_FWD_MS_CFG=1|5   multi-scale forward on 16x32 tiles (256 threads, 3 CTAs/SM | 128 threads, 4 CTAs/SM)
+             SQLX_BWD_MS_CFG=2|3   multi-scale backward on 32x32 tiles, 2 CTAs/SM | 16x32 tiles, 2 CTAs/SM (no register cap)
 """
 import json
 import os
@@ -63,7 +65,9 @@ if __name__ == "__main__":
     base = run({})
     print("default               loss %.9f  fwd %.1f us  bwd %.1f us" % (base["loss"], base["us"].get("photo_fwd_ms_kernel", 0),
                                                                        base["us"].get("photo_bwd_ms_kernel", 0)))
-    for name, env in (("SQLX_FWD_MS_STAGE=1", {"SQLX_FWD_MS_STAGE": "1"}),):
+    for name, env in (("SQLX_FWD_MS_STAGE=1", {"SQLX_FWD_MS_STAGE": "1"}), ("SQLX_FWD_MS_CFG=1", {"SQLX_FWD_MS_CFG": "1"}),
+                      ("SQLX_FWD_MS_CFG=5", {"SQLX_FWD_MS_CFG": "5"}), ("SQLX_BWD_MS_CFG=2", {"SQLX_BWD_MS_CFG": "2"}),
+                      ("SQLX_BWD_MS_CFG=3", {"SQLX_BWD_MS_CFG": "3"})):
         r = run(env)
         same = (r["loss"] == base["loss"] and r["argmin"] == base["argmin"] and
                 all(abs(a - b) <= 1e-6 * abs(b) for a, b in zip(r["grads"], base["grads"])))

@@ -1175,7 +1175,10 @@ struct BwdPredSmem {
   static constexpr size_t bytes = 1024 + tail + 2 * DP * 4 + 64;
 };
 
-template <int DP>
+// PIPE = true (candidate, SQLX_SQL_PIPE=1, not the default): the d_x / accumulator MMAs of tile t are committed to a
+// second mbarrier and NOT waited for; tile t+1's TMA wait, hi/lo split and logits MMA are issued first, and the d_x rows
+// of tile t leave TMEM while that logits MMA runs.  Same arithmetic, same order of every accumulation.
+template <int DP, bool PIPE = false>
 __global__ void __launch_bounds__(kThreads) sql_tc_bwd_pred_kernel(
     const __grid_constant__ CUtensorMap map_mn, const __grid_constant__ CUtensorMap map_k, const float* __restrict__ Mx,
     const float* __restrict__ bp, const float* __restrict__ centers, const float* __restrict__ g_pred, int D, int n,
@@ -1196,6 +1199,7 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_pred_kernel(
   s.bar_mma = s.bar_tma + 1;
   uint64_t* bar_bx = s.bar_tma + 2;
   s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar_tma + 3);
+  uint64_t* bar_mma2 = s.bar_tma + 4;     // PIPE: completion of a tile's d_x / accumulator MMAs
   const int b = blockIdx.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kCols = 256;
@@ -1205,6 +1209,7 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_pred_kernel(
     mbar_init(s.bar_tma, 1);
     mbar_init(s.bar_mma, 1);
     mbar_init(bar_bx, 1);
+    if (PIPE) mbar_init(bar_mma2, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -1256,7 +1261,22 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_pred_kernel(
 #pragma unroll
   for (int d = 0; d < DP; ++d) dc[d] = 0.f;
   uint32_t ph_tma = 0, ph_mma = 0, ph_bx = 0, acc_on = 0;
+  uint32_t ph_mma2 = 0;
+  bool pending = false;     // PIPE: the previous tile's d_x rows still sit in TMEM (its MMAs possibly in flight)
+  int p_prev = 0;
   float* dxb = d_x + (size_t)b * kE * n;
+  auto store_dx = [&](int pp) {
+#pragma unroll
+    for (int c = 0; c < kE; c += 16) {
+      float v[16];
+      tmem_ld16(lane_base + tm_dx + c, v);
+      tmem_wait_ld();
+      if (pp < n) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dxb[(size_t)(c + i) * n + pp] = v[i];
+      }
+    }
+  };
   for (int t = t_begin; t < t_end; ++t) {
     const int p0 = t * kTile;
     const int p = p0 + warp * 32 + lane;
@@ -1267,6 +1287,8 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_pred_kernel(
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) {
+      // PIPE: the previous tile's MMAs read bx and the dz columns of TMEM: they must be done before both are reused
+      if (PIPE && pending) mbar_wait(bar_mma2, ph_mma2);
       if (t + 1 < t_end) issue_x_tma(s, &map_mn, p0 + kTile, b * kE);
       mbar_arrive_expect_tx(bar_bx, kXTile);   // the K-major x rows of the accumulator's B tile (free: previous MMAs waited)
 #pragma unroll
@@ -1274,6 +1296,12 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_pred_kernel(
       tc_fence_after();
       issue_xm(smem_u32(s.x_hi), smem_u32(s.x_lo), smem_u32(s.k_hi), smem_u32(s.k_lo), tmem + tm_z, DP);
       umma_commit(s.bar_mma);
+    }
+    if (PIPE && pending) {     // the previous tile's d_x rows leave TMEM while this tile's logits MMA runs
+      mbar_wait(bar_mma2, ph_mma2); ph_mma2 ^= 1;
+      tc_fence_after();
+      store_dx(p_prev);
+      pending = false;       // (the d_x columns are rewritten only after this tile's epilogue and its block barrier)
     }
     mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
@@ -1346,21 +1374,24 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_pred_kernel(
       for (int k = 0; k < DP / 8; ++k)          // d_x tile = dz M               (K = DP bins, A from TMEM)
         umma_tf32_ts(tmem + tm_dx, tmem + tm_z + k * 8,
                      make_desc_sw128(mt + (uint32_t)(k >> 2) * 32u * 128u + (uint32_t)(k & 3) * 32u, 16, 1024), id_dx, k > 0);
-      umma_commit(s.bar_mma);
+      umma_commit(PIPE ? bar_mma2 : s.bar_mma);
     }
     ph_bx ^= 1;
+    if (PIPE) {
+      pending = true;
+      p_prev = p;
+      continue;
+    }
     mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < kE; c += 16) {
-      float v[16];
-      tmem_ld16(lane_base + tm_dx + c, v);
-      tmem_wait_ld();
-      if (p < n) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) dxb[(size_t)(c + i) * n + p] = v[i];
-      }
-    }
+    store_dx(p);
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (PIPE && pending) {       // drain: the last tile's d_x rows (the commit also covers every accumulator MMA)
+    mbar_wait(bar_mma2, ph_mma2);
+    tc_fence_after();
+    store_dx(p_prev);
     tc_fence_before();
     __syncthreads();
   }
@@ -1880,19 +1911,32 @@ int tc_pred_mix_fwd(const float* x, const float* Mx, const float* bp, const floa
   return check_launch("sql_tc_pred2_kernel");
 }
 
+template <int DP, bool PIPE>
+int launch_bwd_pred_impl(const CUtensorMap& map_mn, const CUtensorMap& map_k, const float* Mx, const float* bp,
+                         const float* centers, const float* g_pred, int B, int D, int n, int chunks, int tpc, float* d_x,
+                         float* part_dM, float* part_db, float* part_dc, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    if (int e = raise_smem(tcsql::sql_tc_bwd_pred_kernel<DP, PIPE>)) return e;
+    configured = true;
+  }
+  ProfScope prof("sql_tc_bwd_pred_kernel", st);
+  tcsql::sql_tc_bwd_pred_kernel<DP, PIPE><<<dim3(chunks, B), tcsql::kThreads, tcsql::BwdPredSmem<DP>::bytes, st>>>(
+      map_mn, map_k, Mx, bp, centers, g_pred, D, n, tpc, d_x, part_dM, part_db, part_dc);
+  return check_launch("sql_tc_bwd_pred_kernel");
+}
+
 template <int DP>
 int launch_bwd_pred(const CUtensorMap& map_mn, const CUtensorMap& map_k, const float* Mx, const float* bp,
                     const float* centers, const float* g_pred, int B, int D, int n, int chunks, int tpc, float* d_x,
                     float* part_dM, float* part_db, float* part_dc, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    if (int e = raise_smem(tcsql::sql_tc_bwd_pred_kernel<DP>)) return e;
-    configured = true;
-  }
-  ProfScope prof("sql_tc_bwd_pred_kernel", st);
-  tcsql::sql_tc_bwd_pred_kernel<DP><<<dim3(chunks, B), tcsql::kThreads, tcsql::BwdPredSmem<DP>::bytes, st>>>(
-      map_mn, map_k, Mx, bp, centers, g_pred, D, n, tpc, d_x, part_dM, part_db, part_dc);
-  return check_launch("sql_tc_bwd_pred_kernel");
+  // candidate (tools/check_candidates.py): software-pipelined tile loop, see the kernel's PIPE parameter
+  static const bool pipe = []() { const char* v = getenv("SQLX_SQL_PIPE"); return v && atoi(v) == 1; }();
+  if (pipe)
+    return launch_bwd_pred_impl<DP, true>(map_mn, map_k, Mx, bp, centers, g_pred, B, D, n, chunks, tpc, d_x, part_dM, part_db,
+                                          part_dc, st);
+  return launch_bwd_pred_impl<DP, false>(map_mn, map_k, Mx, bp, centers, g_pred, B, D, n, chunks, tpc, d_x, part_dM, part_db,
+                                         part_dc, st);
 }
 
 int tc_bwd_pred_mix(const float* x, const float* Mx, const float* bp, const float* centers, const float* g_pred, int B,

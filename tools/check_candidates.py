@@ -7,6 +7,8 @@ compares loss, gradients and per-kernel times against the default.
 Candidates:  SQLX_FWD_MS_STAGE=1   photo_fwd3_kernel<MS, STG=1>: depth/target staging in one trip per thread
              SQLX_FWD_MS_CFG=1|5   multi-scale forward on 16x32 tiles (256 threads, 3 CTAs/SM | 128 threads, 4 CTAs/SM)
              SQLX_BWD_MS_CFG=2|3   multi-scale backward on 32x32 tiles, 2 CTAs/SM | 16x32 tiles, 2 CTAs/SM (no register cap)
+             SQLX_SQL_PIPE=1       sql_tc_bwd_pred_kernel<DP, PIPE>: software-pipelined tile loop (run under `timeout`:
+                                   a wrong mbarrier phase would hang)
 """
 import json
 import os
@@ -52,9 +54,38 @@ print("RESULT " + json.dumps(res))
 ''' % ROOT
 
 
-def run(env_extra):
+SQL_CHILD = r'''
+import json, os, sys
+ROOT = %r
+for p in (ROOT, os.path.join(ROOT, "sfmnext-impl_b200")):
+    sys.path.insert(0, p)
+import torch
+from sqlx import sql as S
+res = {}
+for (B, h, w, Q, D) in ((12, 96, 320, 64, 64), (8, 160, 512, 128, 128), (2, 24, 40, 16, 24)):
+    torch.manual_seed(0)
+    x = torch.randn(B, 32, h, w, device="cuda"); q = 0.4 * torch.randn(B, Q, 32, device="cuda")
+    Wp = 0.3 * torch.randn(D, Q, device="cuda"); bp = 0.1 * torch.randn(D, device="cuda")
+    cen = torch.sort(torch.rand(B, D, device="cuda") * 80, dim=1).values.contiguous()
+    g = torch.randn(B, 1, h, w, device="cuda")
+    Mx = torch.matmul(Wp, q)
+    outs = S.bwd_pred_mix(x, Mx, bp, cen, g)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        S.bwd_pred_mix(x, Mx, bp, cen, g)
+    b.record(); torch.cuda.synchronize()
+    res["%%dx%%dx%%d Q%%d D%%d" %% (B, h, w, Q, D)] = {"sums": [float(t.double().sum()) for t in outs],
+                                                   "abs": [float(t.double().abs().sum()) for t in outs],
+                                                   "us": a.elapsed_time(b) / 20 * 1e3}
+print("RESULT " + json.dumps(res))
+''' % ROOT
+
+
+def run(env_extra, child=None):
     env = dict(os.environ, **env_extra)
-    out = subprocess.run([sys.executable, "-c", CHILD], capture_output=True, text=True, env=env, timeout=300)
+    out = subprocess.run([sys.executable, "-c", child or CHILD], capture_output=True, text=True, env=env, timeout=300)
     for line in out.stdout.splitlines():
         if line.startswith("RESULT "):
             return json.loads(line[7:])
@@ -74,3 +105,9 @@ if __name__ == "__main__":
         print("%-21s loss %.9f  fwd %.1f us  bwd %.1f us  %s" % (name, r["loss"], r["us"].get("photo_fwd_ms_kernel", 0),
                                                                  r["us"].get("photo_bwd_ms_kernel", 0),
                                                                  "bit-identical results" if same else "RESULTS DIFFER"))
+    base = run({}, SQL_CHILD)
+    pipe = run({"SQLX_SQL_PIPE": "1"}, SQL_CHILD)
+    for k in base:
+        same = base[k]["sums"] == pipe[k]["sums"] and base[k]["abs"] == pipe[k]["abs"]
+        print("bwd_pred_mix %-22s default %.1f us  SQLX_SQL_PIPE=1 %.1f us  %s" %
+              (k, base[k]["us"], pipe[k]["us"], "bit-identical results" if same else "RESULTS DIFFER"))

@@ -1446,7 +1446,8 @@ struct BwdSumSmem {
   static constexpr size_t bytes = 1024 + tail + 3 * QP * 4 + 64;
 };
 
-template <int QP>
+// PIPE = true: the same software pipelining as sql_tc_bwd_pred_kernel<DP, PIPE> (candidate, SQLX_SQL_PIPE=1).
+template <int QP, bool PIPE = false>
 __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
     const __grid_constant__ CUtensorMap map_mn, const __grid_constant__ CUtensorMap map_k,
     const float* __restrict__ queries, const float* __restrict__ summary, const float* __restrict__ row_max,
@@ -1470,6 +1471,7 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
   s.bar_mma = s.bar_tma + 1;
   uint64_t* bar_xk = s.bar_tma + 2;
   s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar_tma + 3);
+  uint64_t* bar_mma2 = s.bar_tma + 4;     // PIPE: completion of a tile's d_x / d_K MMAs
   const int b = blockIdx.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kCols = 512;
@@ -1479,6 +1481,7 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
     mbar_init(s.bar_tma, 1);
     mbar_init(s.bar_mma, 1);
     mbar_init(bar_xk, 1);
+    if (PIPE) mbar_init(bar_mma2, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -1544,7 +1547,25 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
   const uint32_t id_t = make_idesc_tf32(128, QP, 1, 0);
   const uint32_t id_32 = make_idesc_tf32(128, 32, 0, 0);
   uint32_t ph_tma = 0, ph_mma = 0, ph_xk = 0, acc_dk = 0;
+  uint32_t ph_mma2 = 0;
+  bool pending = false;     // PIPE: the previous tile's d_x rows still sit in TMEM
+  int p_prev = 0;
+  float prev_old[kE];       // PIPE: the previous tile's accumulate operands
+#pragma unroll
+  for (int e = 0; e < kE; ++e) prev_old[e] = 0.f;
   float* dxb = d_x + (size_t)b * kE * n;
+  auto store_dx = [&](int pp, const float (&add)[kE]) {
+#pragma unroll
+    for (int c = 0; c < kE; c += 16) {
+      float v[16];
+      tmem_ld16(lane_base + tm_dx + c, v);
+      tmem_wait_ld();
+      if (pp < n) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dxb[(size_t)(c + i) * n + pp] = v[i] + add[c + i];
+      }
+    }
+  };
   for (int t = t_begin; t < t_end; ++t) {
     const int p0 = t * kTile;
     const int p = p0 + warp * 32 + lane;
@@ -1560,6 +1581,8 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) {
+      // PIPE: the previous tile's MMAs read x_k and the dy / a columns of TMEM: done before both are reused
+      if (PIPE && pending) mbar_wait(bar_mma2, ph_mma2);
       if (t + 1 < t_end) issue_x_tma(s, &map_mn, p0 + kTile, b * kE);
       mbar_arrive_expect_tx(bar_xk, kXTile);
 #pragma unroll
@@ -1572,6 +1595,12 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
         umma_tf32_ss(tmem + tm_t, make_desc_mn32(xh + k * 1024, kXBlock), make_desc_sw128(dsa + k * 32, 16, 1024), id_t,
                      k > 0);
       umma_commit(s.bar_mma);
+    }
+    if (PIPE && pending) {     // the previous tile's d_x rows leave TMEM while this tile's y / t MMAs run
+      mbar_wait(bar_mma2, ph_mma2); ph_mma2 ^= 1;
+      tc_fence_after();
+      store_dx(p_prev, prev_old);
+      pending = false;
     }
     mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
@@ -1621,21 +1650,26 @@ __global__ void __launch_bounds__(kThreads) sql_tc_bwd_sum_kernel(
       for (int k = 0; k < QP / 8; ++k)
         umma_tf32_ts(tmem + tm_dx, tmem + tm_t + k * 8,
                      make_desc_sw128(dst + (k >> 2) * 32 * 128 + (k & 3) * 32, 16, 1024), id_32, 1);
-      umma_commit(s.bar_mma);
+      umma_commit(PIPE ? bar_mma2 : s.bar_mma);
     }
     ph_xk ^= 1;
+    if (PIPE) {
+      pending = true;
+      p_prev = p;
+#pragma unroll
+      for (int e = 0; e < kE; ++e) prev_old[e] = prev[e];
+      continue;
+    }
     mbar_wait(s.bar_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < kE; c += 16) {
-      float v[16];
-      tmem_ld16(lane_base + tm_dx + c, v);
-      tmem_wait_ld();
-      if (p < n) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) dxb[(size_t)(c + i) * n + p] = v[i] + prev[c + i];
-      }
-    }
+    store_dx(p, prev);
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (PIPE && pending) {       // drain: the last tile's d_x rows (the commit also covers every d_K MMA)
+    mbar_wait(bar_mma2, ph_mma2);
+    tc_fence_after();
+    store_dx(p_prev, prev_old);
     tc_fence_before();
     __syncthreads();
   }
@@ -1951,19 +1985,31 @@ int tc_bwd_pred_mix(const float* x, const float* Mx, const float* bp, const floa
   return launch_bwd_pred<128>(map_mn, map_k, Mx, bp, centers, g_pred, B, D, n, chunks, tpc, d_x, part_dM, part_db, part_dc, st);
 }
 
+template <int QP, bool PIPE>
+int launch_bwd_sum_impl(const CUtensorMap& map_mn, const CUtensorMap& map_k, const float* queries, const float* summary,
+                        const float* row_max, const float* row_sum, const float* d_summary, int B, int Q, int n, int chunks,
+                        int tpc, int accumulate, float* d_x, float* part_dK, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    if (int e = raise_smem(tcsql::sql_tc_bwd_sum_kernel<QP, PIPE>)) return e;
+    configured = true;
+  }
+  ProfScope prof("sql_tc_bwd_sum_kernel", st);
+  tcsql::sql_tc_bwd_sum_kernel<QP, PIPE><<<dim3(chunks, B), tcsql::kThreads, tcsql::BwdSumSmem<QP>::bytes, st>>>(
+      map_mn, map_k, queries, summary, row_max, row_sum, d_summary, Q, n, tpc, accumulate, d_x, part_dK);
+  return check_launch("sql_tc_bwd_sum_kernel");
+}
+
 template <int QP>
 int launch_bwd_sum(const CUtensorMap& map_mn, const CUtensorMap& map_k, const float* queries, const float* summary,
                    const float* row_max, const float* row_sum, const float* d_summary, int B, int Q, int n, int chunks,
                    int tpc, int accumulate, float* d_x, float* part_dK, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    if (int e = raise_smem(tcsql::sql_tc_bwd_sum_kernel<QP>)) return e;
-    configured = true;
-  }
-  ProfScope prof("sql_tc_bwd_sum_kernel", st);
-  tcsql::sql_tc_bwd_sum_kernel<QP><<<dim3(chunks, B), tcsql::kThreads, tcsql::BwdSumSmem<QP>::bytes, st>>>(
-      map_mn, map_k, queries, summary, row_max, row_sum, d_summary, Q, n, tpc, accumulate, d_x, part_dK);
-  return check_launch("sql_tc_bwd_sum_kernel");
+  static const bool pipe = []() { const char* v = getenv("SQLX_SQL_PIPE"); return v && atoi(v) == 1; }();   // candidate
+  if (pipe)
+    return launch_bwd_sum_impl<QP, true>(map_mn, map_k, queries, summary, row_max, row_sum, d_summary, B, Q, n, chunks, tpc,
+                                         accumulate, d_x, part_dK, st);
+  return launch_bwd_sum_impl<QP, false>(map_mn, map_k, queries, summary, row_max, row_sum, d_summary, B, Q, n, chunks, tpc,
+                                        accumulate, d_x, part_dK, st);
 }
 
 int tc_bwd_sum(const float* x, const float* queries, const float* summary, const float* row_max, const float* row_sum,

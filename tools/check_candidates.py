@@ -7,7 +7,7 @@ compares loss, gradients and per-kernel times against the default.
 Candidates:  SQLX_FWD_MS_STAGE=1   photo_fwd3_kernel<MS, STG=1>: depth/target staging in one trip per thread
              SQLX_FWD_MS_CFG=1|5   multi-scale forward on 16x32 tiles (256 threads, 3 CTAs/SM | 128 threads, 4 CTAs/SM)
              SQLX_BWD_MS_CFG=2|3   multi-scale backward on 32x32 tiles, 2 CTAs/SM | 16x32 tiles, 2 CTAs/SM (no register cap)
-             SQLX_SQL_PIPE=1       sql_tc_bwd_pred_kernel<DP, PIPE>: software-pipelined tile loop (run under `timeout`:
+             SQLX_SQL_PIPE=1       sql_tc_bwd_pred_kernel<DP, PIPE>, sql_tc_bwd_sum_kernel<QP, PIPE>: software-pipelined tile loop (run under `timeout`:
                                    a wrong mbarrier phase would hang)
 """
 import json
@@ -69,12 +69,18 @@ for (B, h, w, Q, D) in ((12, 96, 320, 64, 64), (8, 160, 512, 128, 128), (2, 24, 
     cen = torch.sort(torch.rand(B, D, device="cuda") * 80, dim=1).values.contiguous()
     g = torch.randn(B, 1, h, w, device="cuda")
     Mx = torch.matmul(Wp, q)
-    outs = S.bwd_pred_mix(x, Mx, bp, cen, g)
+    outs = list(S.bwd_pred_mix(x, Mx, bp, cen, g))
+    summ, m, l, _ = S.summary_fwd(x, q)
+    ds = torch.randn_like(summ)
+    outs += list(S.bwd_summary(x, q, summ, m, l, ds))                       # write mode
+    acc0 = torch.randn_like(x)
+    outs += list(S.bwd_summary(x, q, summ, m, l, ds, d_x=acc0.clone()))     # accumulate mode
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(20):
         S.bwd_pred_mix(x, Mx, bp, cen, g)
+        S.bwd_summary(x, q, summ, m, l, ds)
     b.record(); torch.cuda.synchronize()
     res["%%dx%%dx%%d Q%%d D%%d" %% (B, h, w, Q, D)] = {"sums": [float(t.double().sum()) for t in outs],
                                                    "abs": [float(t.double().abs().sum()) for t in outs],
@@ -109,5 +115,5 @@ if __name__ == "__main__":
     pipe = run({"SQLX_SQL_PIPE": "1"}, SQL_CHILD)
     for k in base:
         same = base[k]["sums"] == pipe[k]["sums"] and base[k]["abs"] == pipe[k]["abs"]
-        print("bwd_pred_mix %-22s default %.1f us  SQLX_SQL_PIPE=1 %.1f us  %s" %
+        print("bwd_pred_mix + bwd_summary %-22s default %.1f us  SQLX_SQL_PIPE=1 %.1f us  %s" %
               (k, base[k]["us"], pipe[k]["us"], "bit-identical results" if same else "RESULTS DIFFER"))

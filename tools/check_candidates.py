@@ -91,7 +91,7 @@ print("RESULT " + json.dumps(res))
 
 def run(env_extra, child=None):
     env = dict(os.environ, **env_extra)
-    out = subprocess.run([sys.executable, "-c", child or CHILD], capture_output=True, text=True, env=env, timeout=300)
+    out = subprocess.run([sys.executable, "-c", child or CHILD], capture_output=True, text=True, env=env, timeout=120)
     for line in out.stdout.splitlines():
         if line.startswith("RESULT "):
             return json.loads(line[7:])

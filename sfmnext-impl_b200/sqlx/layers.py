@@ -226,3 +226,63 @@ def predict_disparity(encoder, depth_decoder, input_color, post_process=False):
             N = pred.shape[0] // 2
             pred = batch_post_process_disparity(pred[:N], pred[N:], r_is_flipped=True)
     return pred
+
+
+# ----------------------------------------------------------------------------- fine-tuning: per-sample median scaling
+def _crop_mask(H, W, garg_crop, eigen_crop, dataset, device):
+    """eval_mask of finetune/train_ft_SQLdepth.py:240-253 as a bool [H, W] tensor."""
+    if not (garg_crop or eigen_crop):
+        # the reference's loop reads eval_mask unconditionally (:254): without a crop flag it raises NameError
+        raise ValueError("median scaling needs garg_crop or eigen_crop (finetune/train_ft_SQLdepth.py:240-254)")
+    m = torch.zeros(H, W, dtype=torch.bool, device=device)
+    if garg_crop:
+        m[int(0.40810811 * H):int(0.99189189 * H), int(0.03594771 * W):int(0.96405229 * W)] = True
+    elif dataset == "kitti":
+        m[int(0.3324324 * H):int(0.91351351 * H), int(0.0359477 * W):int(0.96405229 * W)] = True
+    else:
+        m[45:471, 41:601] = True
+    return m
+
+
+def _masked_median(v, mask):
+    """numpy.median of v[mask] per row (mean of the two middle order statistics; NaN when the selection is empty or
+    holds a NaN) for v, mask [R, n] -- one sort, no boolean indexing, no device->host synchronisation."""
+    k = mask.sum(dim=1)
+    key = torch.where(mask, v, torch.full_like(v, float("inf")))
+    key = torch.where(torch.isnan(key), torch.full_like(v, float("inf")), key)      # NaNs are flagged separately
+    srt = torch.sort(key, dim=1).values
+    lo = ((k - 1).clamp_min(0) // 2).unsqueeze(1)
+    hi = (k // 2).clamp_max(v.shape[1] - 1).unsqueeze(1)
+    med = (srt.gather(1, lo) + srt.gather(1, hi))[:, 0] * 0.5
+    bad = (k == 0) | (torch.isnan(v) & mask).any(dim=1)
+    return torch.where(bad, torch.full_like(med, float("nan")), med)
+
+
+def median_scale_ratios(pred, depth, min_depth_eval, max_depth_eval, garg_crop=False, eigen_crop=False,
+                        dataset="kitti", count=None):
+    """The per-sample factors of finetune/train_ft_SQLdepth.py:236-266, computed on the tensors' device:
+    ratio_i = median(depth_i[valid]) / median(pred_i[valid]) for the first `count` (default B // 2, :236) samples,
+    1 where either median is NaN (:261-264), 1 for the remaining samples.  pred, depth: [B,1,H,W] -> [B] (detached)."""
+    B, _, H, W = pred.shape
+    count = B // 2 if count is None else count
+    with torch.no_grad():
+        p = pred.detach().reshape(B, H * W).float()
+        d = depth.detach().reshape(B, H * W).float()
+        valid = (d > min_depth_eval) & (d < max_depth_eval)
+        valid = valid & _crop_mask(H, W, garg_crop, eigen_crop, dataset, pred.device).reshape(1, H * W)
+        md, mp = _masked_median(d, valid), _masked_median(p, valid)
+        ratio = md / mp
+        ratio = torch.where(torch.isnan(md) | torch.isnan(mp), torch.ones_like(ratio), ratio)
+        ratio = torch.where(torch.arange(B, device=pred.device) < count, ratio, torch.ones_like(ratio))
+    return ratio
+
+
+def median_scale(pred, depth, min_depth_eval, max_depth_eval, garg_crop=False, eigen_crop=False, dataset="kitti",
+                 count=None):
+    """Drop-in for the NumPy loop of finetune/train_ft_SQLdepth.py:236-266 (`pred[i] *= ratio`, one device->host->device
+    round trip per sample in the reference): returns pred scaled per sample, differentiable wrt pred (the ratios are
+    constants, as in the reference).  Sort-based torch ops on the device; the fused loss that follows is
+    sqlx.SILogLoss (sqlx_silog_fwd/bwd)."""
+    require_cuda(pred, depth)
+    ratio = median_scale_ratios(pred, depth, min_depth_eval, max_depth_eval, garg_crop, eigen_crop, dataset, count)
+    return pred * ratio.view(-1, 1, 1, 1)

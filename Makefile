@@ -9,7 +9,7 @@ LIB       := $(PKG)/lib/libsqlx.so
 
 all: $(LIB)
 
-$(PKG)/build/%.o: $(PKG)/csrc/%.cu $(wildcard $(PKG)/csrc/*.cuh) include/sqlx.h
+$(PKG)/build/%.o: $(PKG)/csrc/%.cu $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/sqlx.h
 	@mkdir -p $(PKG)/build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(PKG)/build/$*.ptxas.log || (cat $(PKG)/build/$*.ptxas.log; exit 1)
 

@@ -1,15 +1,17 @@
 #!/usr/bin/env python
-"""Benchmark of the SQLdepth training hot path (BASELINE.json metric: train frames/s).
+"""Benchmark of the SQLdepth training hot path (BASELINE.json metric: train frames/s at 192x640 and 320x1024).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path (libsqlx)
-  python bench.py --impl reference [...]                         the reference's CPU path (oracle port)
+  python bench.py --impl reference [...]                         the UNMODIFIED reference's CPU path (oracle/_ref)
 
-One "step" = SQL decoder tail forward -> photometric losses (4 loss scales) forward -> backward of both, on one
-batch of synthetic KITTI-shape 3-frame inputs (BASELINE config 2: batch 12 per GPU, 192x640, decoder features
-32x96x320, Q = D = 64).  frames/s = target frames processed per second = batch / step time (trainer.py:584).
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the byte accounting behind `roofline`.
+One "step" = SQL decoder tail forward -> photometric losses forward -> backward of both, on one batch of synthetic
+KITTI-shape inputs.  frames/s = target frames processed per second = batch / step time (trainer.py:584).
+The headline workload is BASELINE config 2 (batch 12 per GPU, 192x640, decoder features 32x96x320, Q = D = 64, 4 loss
+scales); the same JSON line carries configs 3 and 4 (320x1024, Q = D = 128) under "workloads".  Prints ONE JSON line
+(rank 0).  See DESIGN.md "Measurement" for the byte accounting behind `roofline`.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -23,7 +25,6 @@ for p in (ROOT, os.path.join(ROOT, "sfmnext-impl_b200"), os.path.join(ROOT, "tes
         sys.path.insert(0, p)
 
 import torch  # noqa: E402
-import torch.nn.functional as F  # noqa: E402
 
 METRIC = "train_frames_per_sec_hot_path"
 UNIT = "frames/s"
@@ -35,61 +36,33 @@ def parse():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="sqlx", choices=["sqlx", "reference"])
-    ap.add_argument("--batch", type=int, default=12, help="batch per GPU (BASELINE config 2: 12)")
-    ap.add_argument("--height", type=int, default=192)
-    ap.add_argument("--width", type=int, default=640)
-    ap.add_argument("--queries", type=int, default=64)
-    ap.add_argument("--bins", type=int, default=64)
-    ap.add_argument("--scales", type=int, default=4, help="number of loss scales (BASELINE config 2: 4)")
-    ap.add_argument("--sources", type=int, default=2, help="source frames (2 = [-1,+1]; 3 with --use_stereo)")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
-                    help="2 = BASELINE config 2 (default, the bench line); 3 = config 3 shapes: 320x1024, batch 8/GPU, "
-                         "3 sources, Q = D = 128, single loss scale (informational)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="headline workload = BASELINE config (default 2: the configuration the metric is quoted on "
+                         "that fits one GPU step for step with the reference's CPU-runnable case)")
+    ap.add_argument("--workloads", default="3,4",
+                    help="further BASELINE configs measured into the same JSON line under 'workloads' ('' = none)")
+    ap.add_argument("--batch", type=int, default=0, help="override the batch per GPU of the headline workload")
     ap.add_argument("--no-graph", action="store_true", help="submit the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--f32-frames", action="store_true",
                     help="ship the frames as float32 in the end-to-end loop (default: uint8, converted on the device)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the fp64 oracle evaluation of the timed batch")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the informational legs (reprojection-dominant batch, h2d-only, stock-PyTorch-on-GPU)")
     ap.add_argument("--allreduce-after-step", action="store_true",
-                    help="N > 1: issue the gradient all-reduce after the step instead of inside it (overlapping the last "
-                         "backward kernel); A/B switch")
-    ap.add_argument("--cpu-sample-batch", type=int, default=2)
+                    help="N > 1: issue the gradient all-reduce after the step instead of inside it (A/B switch)")
+    ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: where the unmodified reference runs (cpu = the contract's arm)")
+    ap.add_argument("--prefetch", type=int, default=2, help="batches in flight ahead of the step in the e2e loop")
     return ap.parse_args()
 
 
-# --------------------------------------------------------------------------------------------- synthetic data
-def make_host_batch(cfg, seed, pin, u8_frames=False):
-    """Seeded KITTI-shape synthetic batch on the host (SURVEY 8d recipe): smooth frames, KITTI intrinsics,
-    PoseCNN-scale poses, decoder-feature-like x and queries.  Frames are quantised to 8 bits (as decoded images
-    are); with u8_frames they stay uint8 on the host and are scaled to [0,1] on the device by HotPath.load."""
-    from _cases import smooth_images, kitti_K, depth_like
-    g = torch.Generator().manual_seed(seed)
-    c = cfg
-    frames = smooth_images(g, c.B, c.H, c.W, c.S + 1)
-    mid = (c.S + 1) // 2
-    hb = {"target": frames[mid]}
-    for i, fr in enumerate([f for j, f in enumerate(frames) if j != mid]):
-        hb["source%d" % i] = fr
-    hb["K"], hb["inv_K"] = kitti_K(c.B, c.H, c.W)
-    hb["x"] = torch.randn(c.B, c.E, c.h, c.w, generator=g)
-    hb["queries"] = 0.4 * torch.randn(c.B, c.Q, c.E, generator=g)
-    for i in range(c.S):
-        hb["axisangle%d" % i] = 0.01 * torch.randn(c.B, 1, 1, 3, generator=g)
-        hb["translation%d" % i] = 0.01 * torch.randn(c.B, 1, 1, 3, generator=g)
-    for s in c.scales:
-        hb["noise%d" % s] = torch.randn(c.B, c.S, c.H, c.W, generator=g)
-        if s > 0:
-            hs, ws = c.scale_hw(s)
-            hb["disp%d" % s] = depth_like(g, c.B, hs, ws)
-            hb["target%d" % s] = F.interpolate(hb["target"], [c.H // 2 ** s, c.W // 2 ** s], mode="bilinear",
-                                               align_corners=False)
-    hb = {k: v.contiguous().float() for k, v in hb.items()}
-    for k in list(hb):
-        if k.startswith("target") or k.startswith("source"):
-            q = (hb[k].clamp(0, 1) * 255.0).round()
-            hb[k] = q.to(torch.uint8) if u8_frames else q / 255.0
-    if pin:
-        hb = {k: v.pin_memory() for k, v in hb.items()}
-    return hb
+def workload_text(n, cfg):
+    return ("BASELINE config %d hot path: SQL decoder tail (x0 32x%dx%d, Q=%d, D=%d) + photometric loss (%dx%d, %d source "
+            "frames%s, %d loss scale%s: scale 0 = decoder output, coarser scales synthetic since the reference decoder "
+            "emits scale 0 only), forward+backward"
+            % (n, cfg.h, cfg.w, cfg.Q, cfg.D, cfg.H, cfg.W, cfg.S, " incl. the stereo frame" if cfg.stereo else "",
+               len(cfg.scales), "s" if len(cfg.scales) > 1 else ""))
 
 
 # --------------------------------------------------------------------------------------------- clocks
@@ -138,171 +111,248 @@ class ClockSampler:
             for nm, val in zip(names, f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        # the median UNDER LOAD: samples taken while the SM clock was above idle (the sampler also sees setup phases)
+        busy = sorted(x for x in sm if x > 0.5 * max(mx or [0]))
+        allv = sorted(sm)
+        med = (busy or allv)
+        return {"sm_mhz": med[len(med) // 2] if med else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "samples_under_load": len(busy), "reasons": sorted(reasons)}
 
 
-# --------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_step_factory(cfg, hb, mlp_state):
-    """The reference's CPU path for the same step, restated by oracle/sqldepth_oracle.py (same ATen primitives as
-    the reference: matmul, softmax, F.interpolate, F.grid_sample, avg_pool2d), autograd backward included."""
-    from oracle import sqldepth_oracle as O
+# --------------------------------------------------------------------------------------------- reference arm
+def reference_step_factory(cfg, cfg_id, hb, device="cpu"):
+    """The UNMODIFIED reference on this workload, through its own public API (oracle/ref_shim.py imports it from
+    /root/reference, or from oracle/_ref -- the copy oracle/build_ref.py makes -- on the GPU box):
+        networks.{Lite_,}Depth_Decoder_QueryTr.forward   (networks/depth_decoder_QTR.py:36-74)
+        Trainer.generate_images_pred + compute_losses     (trainer.py:386-549), then loss.backward().
+    The decoder's forward includes its patch-embedding conv, 4-layer transformer and conv3x3 (lines 37-45), which are not
+    on our path: the reference arm does slightly MORE work than ours per step (reported as `front_ms`)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shim
+    ref = ref_shim.load(force_cpu=(device == "cpu"))
     c = cfg
-    leaves = {k: hb[k].clone().requires_grad_(True) for k in ["x", "queries"] +
-              ["disp%d" % s for s in c.scales if s > 0] +
-              ["axisangle%d" % i for i in range(c.S)] + ["translation%d" % i for i in range(c.S)]}
-    params = {k: v.clone().requires_grad_(True) for k, v in mlp_state.items()}
+    dev = torch.device(device)
+    T = ref_shim.make_trainer(c.B, c.H, c.W, scales=c.scales, use_stereo=c.stereo, device=device)
+    patch = {2: 16, 3: 20, 4: 32}[cfg_id]
+    cls = ref.networks.Depth_Decoder_QueryTr if cfg_id == 4 else ref.networks.Lite_Depth_Decoder_QueryTr
+    torch.manual_seed(0)
+    dec = cls(in_channels=c.E, patch_size=patch, dim_out=c.D, embedding_dim=c.E, query_nums=c.Q, num_heads=4,
+              min_val=c.min_depth, max_val=c.max_depth).to(dev)
+    dec.train()
+    t = {k: (v.float() / 255.0 if v.dtype == torch.uint8 else v).to(dev) for k, v in hb.items()}
+    fids = [-1, 1] + (["s"] if c.stereo else [])
+    inputs = {("K", 0): t["K"], ("inv_K", 0): t["inv_K"], ("color", 0, 0): t["target"]}
+    for i, f in enumerate(fids):
+        inputs[("color", f, 0)] = t["source%d" % i]
+    for s in c.scales:
+        if s > 0:
+            inputs[("color", 0, s)] = t["target%d" % s]
+    if c.stereo:
+        inputs["stereo_T"] = t["stereo_T"]
+    x0 = t["x"].clone().requires_grad_(True)
+    leaves = {("disp", s): t["disp%d" % s].clone().requires_grad_(True) for s in c.scales if s > 0}
+    poses = {}
+    for i in c.pose_sources:
+        poses[fids[i]] = (t["axisangle%d" % i].clone().requires_grad_(True),
+                          t["translation%d" % i].clone().requires_grad_(True))
+    params = list(dec.parameters())
 
     def step():
-        for t in list(leaves.values()) + list(params.values()):
-            t.grad = None
-        mlp = [params["bins_regressor.%d.%s" % (i, k)] for i in (0, 2, 4) for k in ("weight", "bias")]
-        Wp = params["convert_to_prob.0.weight"].view(c.D, c.Q)
-        tail = O.sql_tail(leaves["x"], leaves["queries"], mlp, Wp, params["convert_to_prob.0.bias"], c.min_depth,
-                          c.max_depth)
-        disps = {s: (tail["pred"] if s == 0 else leaves["disp%d" % s]) for s in c.scales}
-        target_pyr = {s: (hb["target"] if s == 0 else hb["target%d" % s]) for s in c.scales}
-        poses = [{"axisangle": leaves["axisangle%d" % i], "translation": leaves["translation%d" % i], "invert": i == 0}
-                 for i in range(c.S)]
-        out = O.photometric_losses(disps, target_pyr, [hb["source%d" % i] for i in range(c.S)], hb["K"], hb["inv_K"],
-                                   poses, {s: hb["noise%d" % s] for s in c.scales}, height=c.H, width=c.W,
-                                   scales=c.scales, disparity_smoothness=c.disparity_smoothness)
-        out["loss"].backward()
-        return float(out["loss"].detach())
-    return step
+        for p_ in params + [x0] + list(leaves.values()) + [q for pr in poses.values() for q in pr]:
+            p_.grad = None
+        outputs = dec(x0)
+        outputs.update(leaves)
+        for f, (aa, tr) in poses.items():           # what Trainer.predict_poses leaves in `outputs` (trainer.py:330-337)
+            outputs[("axisangle", 0, f)] = aa
+            outputs[("translation", 0, f)] = tr
+            outputs[("cam_T_cam", 0, f)] = ref.layers.transformation_from_parameters(aa[:, 0], tr[:, 0], invert=(f < 0))
+        T.generate_images_pred(inputs, outputs)
+        losses = T.compute_losses(inputs, outputs)
+        losses["loss"].backward()
+        return losses["loss"]
+
+    def front():
+        """forward + backward of depth_decoder_QTR.py:37-45 alone (the part of decoder.forward outside our path)"""
+        xx = x0.detach().clone().requires_grad_(True)
+        emb = dec.embedding_convPxP(xx).flatten(2)
+        emb = emb + dec.positional_encodings[:emb.shape[2], :].T.unsqueeze(0)
+        tok = dec.transformer_encoder(emb.permute(2, 0, 1))
+        y = dec.conv3x3(xx)
+        (tok.sum() + y.sum()).backward()
+    return step, front
 
 
-def time_cpu(cfg_full, args, steps, warmup):
-    from sqlx.hotpath import HotPathConfig
-    c = cfg_full
-    Bs = min(args.cpu_sample_batch, c.B)
-    cs = HotPathConfig(B=Bs, H=c.H, W=c.W, h=c.h, w=c.w, E=c.E, Q=c.Q, D=c.D, S=c.S, scales=c.scales,
-                       min_depth=c.min_depth, max_depth=c.max_depth)
+def port_step_factory(cfg, hb, state):
+    """Fallback when the reference tree is not available (oracle/_ref missing): the oracle port, same ATen primitives."""
+    from _workload import oracle_step
+    return lambda: oracle_step(cfg, hb, state, dtype=torch.float32)["loss"]
+
+
+def time_reference(cfg, cfg_id, steps, warmup, device="cpu"):
+    from _workload import make_host_batch, head_state
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shim
     cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
     torch.set_num_threads(cores)
-    hb = make_host_batch(cs, seed=1234, pin=False)
-    torch.manual_seed(0)
-    nn = torch.nn
-    conv = nn.Conv2d(c.Q, c.D, 1)
-    mlp = nn.Sequential(nn.Linear(c.E * c.Q, 16 * c.Q), nn.LeakyReLU(), nn.Linear(16 * c.Q, 256), nn.LeakyReLU(),
-                        nn.Linear(256, c.D))
-    state = {"convert_to_prob.0.weight": conv.weight.detach(), "convert_to_prob.0.bias": conv.bias.detach()}
-    for k, v in mlp.state_dict().items():
-        state["bins_regressor." + k] = v
-    step = cpu_reference_step_factory(cs, hb, state)
+    hb = make_host_batch(cfg, seed=1234, pin=False)
+    front_ms = None
+    if ref_shim.available():
+        kind = "reference"
+        step, front = reference_step_factory(cfg, cfg_id, hb, device)
+    else:
+        kind = "port"
+        step, front = port_step_factory(cfg, hb, head_state(cfg)), None
+    sync = torch.cuda.synchronize if device == "cuda" else (lambda: None)
     for _ in range(warmup):
         step()
+    sync()
     t0 = time.perf_counter()
     for _ in range(steps):
-        step()
+        loss = step()
+    sync()
     dt = (time.perf_counter() - t0) / steps
-    return {"value": Bs / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "batch %d of the same workload (%dx%d, %d loss scales, fwd+bwd), %d timed steps, torch CPU fp32 "
-                      "threads=%d" % (Bs, c.H, c.W, len(c.scales), steps, cores),
-            "ms_per_step": dt * 1e3}
+    if front is not None:
+        front(); sync()
+        t1 = time.perf_counter()
+        front(); sync()
+        front_ms = (time.perf_counter() - t1) * 1e3
+    what = ("unmodified reference (oracle/_ref): Lite_/Depth_Decoder_QueryTr.forward + Trainer.generate_images_pred + "
+            "compute_losses + backward" if kind == "reference" else "oracle port (reference tree not available)")
+    return {"value": cfg.B / dt, "unit": UNIT, "cores": cores, "kind": kind, "ms_per_step": dt * 1e3,
+            "front_ms": front_ms, "loss": float(loss),
+            "sample": "%s; the FULL batch of the workload (%d x %dx%d, %d loss scales), %d timed steps after %d warm-up, "
+                      "torch %s fp32 threads=%d%s"
+                      % (what, cfg.B, cfg.H, cfg.W, len(cfg.scales), steps, warmup, device, cores,
+                         ("; of which %.0f ms/step is the decoder front (patch embedding, transformer, conv3x3) that is "
+                          "not on our path" % front_ms) if front_ms is not None else "")}
 
 
 # --------------------------------------------------------------------------------------------- roofline
 def algorithmic_bytes(c):
-    """Compulsory fp32 bytes per launch of every main kernel ("Measurement"), averaged over the
-    loss scales for the per-scale kernels."""
+    """Compulsory fp32 bytes of ONE LAUNCH of every main kernel, counting each input ONCE per launch (DESIGN.md,
+    "Measurement"): frames, identity losses and intrinsics are scale-invariant; depth, noise and arg-min are per scale."""
     N, S, B, E = c.H * c.W, c.S, c.B, c.E
     n0 = c.h * c.w
     ns = [c.scale_hw(s)[0] * c.scale_hw(s)[1] for s in c.scales]
-    n_avg = sum(ns) / len(ns)
+    L = len(ns)
+    frames = 12 * N * (1 + S)                      # target + S sources, read once
+    fwd = B * (frames + 4 * N * S + sum(4 * n + 4 * N * S + N for n in ns))       # + identity; depth, noise, arg-min
+    bwd = B * (frames + sum(4 * n + N + 4 * n for n in ns))                       # depth + arg-min in, d_depth out
     return {
-        # depth_lr + target + S sources + S identity + S noise (reads); argmin u8 (write)
-        "photo_fwd_kernel": B * (4 * n_avg + 12 * N + 12 * N * S + 4 * N * S + 4 * N * S + N),
-        # all loss scales in one launch: the per-scale figure (SURVEY 8d's unit) times the scales one launch processes
-        "photo_fwd_ms_kernel": B * sum(4 * n + 12 * N + 12 * N * S + 4 * N * S + 4 * N * S + N for n in ns),
-        # depth_lr + target + S sources + argmin (reads); d_depth_lr (write)
-        "photo_bwd_kernel": B * (4 * n_avg + 12 * N + 12 * N * S + N + 4 * n_avg),
-        "photo_bwd_ms_kernel": B * sum(4 * n + 12 * N + 12 * N * S + N + 4 * n for n in ns),
-        "reproj_loss_kernel": B * (24 * N + 4 * N),
+        "photo_fwd_ms_kernel": fwd, "photo_fwd_kernel": fwd / L if L else fwd,
+        "photo_bwd_ms_kernel": bwd, "photo_bwd_kernel": bwd / L if L else bwd,
         # identity losses of all S sources in one launch: target once, every source once, S loss maps out
         "identity_loss_kernel": B * (12 * N + 12 * N * S + 4 * N * S),
-        "sql_summary_kernel": B * 4 * n0 * E,
-        "sql_pred_kernel": B * (4 * n0 * E + 4 * n0),
-        "sql_bwd_reduce_kernel": B * (4 * n0 * E + 4 * n0),
-        "sql_bwd_dx_kernel": B * (4 * n0 * E + 4 * n0 + 4 * n0 * E),
-        # tensor-core versions: same compulsory traffic
         "sql_tc_summary_kernel": B * 4 * n0 * E,
         "sql_tc_pred_kernel": B * (4 * n0 * E + 4 * n0),
-        "sql_tc_bwd_reduce_kernel": B * (4 * n0 * E + 4 * n0),
-        "sql_tc_bwd_dx_kernel": B * (4 * n0 * E + 4 * n0 + 4 * n0 * E),
-        # mixed-weight decomposition (sql_tc.cu): regression backward reads x + g_pred and writes d_x; the summary-path
-        # backward reads x and accumulates into d_x (read + write)
+        # regression backward reads x + g_pred and writes d_x; the summary-path backward reads x and accumulates into d_x
         "sql_tc_bwd_pred_kernel": B * (4 * n0 * E + 4 * n0 + 4 * n0 * E),
         "sql_tc_bwd_sum_kernel": B * (4 * n0 * E + 2 * 4 * n0 * E),
+        "sql_summary_kernel": B * 4 * n0 * E, "sql_pred_kernel": B * (4 * n0 * E + 4 * n0),
+        "sql_bwd_reduce_kernel": B * (4 * n0 * E + 4 * n0), "sql_bwd_dx_kernel": B * (8 * n0 * E + 4 * n0),
     }
 
 
-def main():
-    args = parse()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    from sqlx.hotpath import HotPath, HotPathConfig
-    if args.config == 3:
-        args.height, args.width, args.batch, args.queries, args.bins, args.sources, args.scales = 320, 1024, 8, 128, 128, 3, 1
-    H, W = args.height, args.width
-    cfg = HotPathConfig(B=args.batch, H=H, W=W, h=H // 2, w=W // 2, E=32, Q=args.queries, D=args.bins, S=args.sources,
-                        scales=tuple(range(args.scales)), min_depth=0.01 if args.config == 3 else 0.001)
-    config = {"workload": "BASELINE config %d hot path: SQL decoder tail (x0 32x%dx%d, Q=%d, D=%d) + photometric loss "
-                          "(%dx%d, %d loss scales: scale 0 = decoder output, coarser scales synthetic "
-                          "since the reference decoder emits scale 0 only), forward+backward"
-                          % (args.config, H // 2, W // 2, args.queries, args.bins, H, W, args.scales),
-              "batch_per_gpu": args.batch, "global_batch": args.batch * world, "height": H, "width": W,
-              "source_frames": args.sources, "loss_scales": args.scales, "parallelism": "dp%d" % world}
+def survey_8d_bytes(c):
+    """SURVEY 8d's per-scale unit (every scale re-reads the frames) x the scales one launch processes: what round 1
+    reported; kept beside the unique-byte figure for comparison."""
+    N, S, B = c.H * c.W, c.S, c.B
+    ns = [c.scale_hw(s)[0] * c.scale_hw(s)[1] for s in c.scales]
+    return {"photo_fwd_ms_kernel": B * sum(4 * n + 12 * N + 12 * N * S + 4 * N * S for n in ns),
+            "photo_bwd_ms_kernel": B * sum(4 * n + 12 * N + 12 * N * S + 4 * N * S + 4 * n for n in ns)}
 
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        cb = time_cpu(cfg, args, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
-        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 0,
-                "steps": max(1, args.steps), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": cb["ms_per_step"],
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config, "gpu_launches": 0,
-                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return
 
+def algorithmic_flops(c):
+    """Algorithmic (1x, not 3xTF32) tensor FLOPs per launch of the SQL kernels."""
+    n0, E, Q, D, B = c.h * c.w, c.E, c.Q, c.D, c.B
+    return {"sql_tc_summary_kernel": B * 4.0 * n0 * E * Q,          # y = x^T K and S = P x^T
+            "sql_tc_pred_kernel": B * 2.0 * n0 * E * D,             # z = M x (mixed weights: contraction over E)
+            "sql_tc_bwd_pred_kernel": B * 6.0 * n0 * E * D,         # z recompute, dM = dz^T x, d_x = dz M
+            "sql_tc_bwd_sum_kernel": B * 10.0 * n0 * E * Q}         # y, t = x^T ds^T, d_x = dy K + a ds, dK = dy^T x
+
+
+def selection_stats(hp, cfg):
+    """Arg-min histogram of the timed batch per scale (identity / per-source shares) and the share of (tile, source)
+    pairs the backward kernel skips because no pixel of the tile's halo selected that source (photo_v3.cu)."""
+    import torch.nn.functional as F
+    S = cfg.S
+    n_ident = S if cfg.automask else 0
+    out = {"per_scale": {}, "backward_tile_skip_rate": None}
+    skipped, total = 0, 0
+    ident_tot, n_tot = 0.0, 0
+    for s, am in hp.argmins.items():
+        hist = torch.bincount(am.flatten().long(), minlength=n_ident + S).float()
+        hist = (hist / hist.sum()).tolist()
+        out["per_scale"][str(s)] = {"identity": sum(hist[:n_ident]), "reprojection": hist[n_ident:n_ident + S]}
+        ident_tot += sum(hist[:n_ident]); n_tot += 1
+        for k in range(S):
+            sel = (am == n_ident + k).float()[:, None]
+            tiles = F.max_pool2d(sel, kernel_size=(22, 38), stride=(16, 32), padding=(3, 3), ceil_mode=True)
+            skipped += int((tiles == 0).sum()); total += tiles.numel()
+    out["identity_share"] = ident_tot / max(1, n_tot)
+    out["backward_tile_skip_rate"] = skipped / max(1, total)
+    return out
+
+
+def load_traffic():
+    """{configN: {profile-hook kernel name: DRAM bytes per launch}} from the committed ncu --set full summary
+    (profiles/traffic_latest.json, written by tools/ncu_summary.py)."""
+    out = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
+    except Exception:
+        return out
+    by_cfg = tj.get("by_config") or {"config2": tj.get("kernels", {})}
+    for ck, kern in by_cfg.items():
+        d = {}
+        for k, v in kern.items():              # ncu names -> the names of the library's profile hooks
+            full = k.replace("void ", "")
+            base = full.split("<")[0].split("::")[-1]
+            ms = full.rstrip().endswith(", 1>")      # last template argument of the photometric kernels: all scales per launch
+            base = {"photo_fwd3_kernel": "photo_fwd_ms_kernel" if ms else "photo_fwd_kernel",
+                    "photo_bwd3_kernel": "photo_bwd_ms_kernel" if ms else "photo_bwd_kernel",
+                    "identity3_kernel": "identity_loss_kernel",
+                    "sql_tc_pred2_kernel": "sql_tc_pred_kernel"}.get(base, base)
+            d[base] = v["dram_bytes_per_launch"]
+        out[ck] = d
+    return out
+
+
+# --------------------------------------------------------------------------------------------- one workload on the GPU
+class Ctx:
+    pass
+
+
+def run_workload(cx, cfg_id, cfg, steps, warmup, full):
+    """Times one workload on this rank's GPU.  full: the headline workload (CPU legs, extras, per-N exchange A/B);
+    otherwise a shorter measurement (value, e2e, per-kernel table, roofline, parity)."""
     import sqlx
     from sqlx import _lib
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (use --impl reference for the CPU arm)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        # keep stdout to the single JSON line: NCCL's version banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    assert sqlx.lib().sqlx_device_ok(local_rank) == 1, "libsqlx targets sm_100a (B200) only"
-
+    from sqlx.hotpath import HotPath
+    from _workload import make_host_batch, head_state, oracle_step
+    args, dev, world, rank, dist = cx.args, cx.dev, cx.world, cx.rank, cx.dist
+    res = {"config": {"workload": workload_text(cfg_id, cfg), "batch_per_gpu": cfg.B, "global_batch": cfg.B * world,
+                      "height": cfg.H, "width": cfg.W, "source_frames": cfg.S, "loss_scales": len(cfg.scales),
+                      "stereo": cfg.stereo, "parallelism": "dp%d" % world}}
     torch.manual_seed(0)
-    # N > 1: the path's one exchange step -- a single bucketed NCCL all-reduce (average) of the parameter gradients --
-    # is issued inside the step on a communication stream as soon as the last parameter gradient exists, so it
-    # overlaps the summary-path backward kernel (captured into the step's CUDA graph with everything else)
     exchange_in_step = world > 1 and not args.allreduce_after_step
-    bucket_box = [None]
 
-    def exchange(grads):
-        if bucket_box[0] is None:
-            from sqlx.dist import GradBucket
-            bucket_box[0] = GradBucket(grads)
-        bucket_box[0].allreduce_(grads)
+    def exchange(flat):
+        """the path's one exchange step: ONE NCCL all-reduce (average) of the flat gradient bucket, in place"""
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
 
-    hp = HotPath(cfg, device=dev, use_graph=not args.no_graph, num_slots=2,
+    nslots = max(2, args.prefetch + 1)
+    hp = HotPath(cfg, device=dev, use_graph=not args.no_graph, num_slots=nslots,
                  grad_exchange=exchange if exchange_in_step else None)
-    if world > 1:   # identical initial weights on every rank
-        for p in hp.parameters():
-            dist.broadcast(p.data, 0)
+    state = head_state(cfg)                       # identical initial weights on every rank (seeded)
+    hp.load_state_dict(state, strict=True)
     hb = make_host_batch(cfg, seed=1234 + rank, pin=True, u8_frames=not args.f32_frames)
-    h2d_bytes = hp.load(hb, non_blocking=False, slot=0)
-    hp.load(hb, non_blocking=False, slot=1)
+    for sl in range(nslots):
+        hp.load(hb, non_blocking=False, slot=sl)
     torch.cuda.synchronize()
 
     # launches of OUR kernels in one step (counted eagerly; a graph replay re-issues the same nodes)
@@ -311,75 +361,62 @@ def main():
     torch.cuda.synchronize()
     launches_per_step = int(sqlx.lib().sqlx_launch_count() - n0)
     if hp.use_graph:
-        hp.capture(slot=0)
-        hp.capture(slot=1)
+        for sl in range(nslots):
+            hp.capture(slot=sl)
 
     exchange_check = None
-    if exchange_in_step:
+    if exchange_in_step and full:
         # pre-flight: the gradients of a step with the in-step (overlapped, graph-captured) exchange equal those of an
-        # eager step followed by a plain bucketed all-reduce
+        # eager step followed by a plain all-reduce of the bucket
         hp.step(0)
         torch.cuda.synchronize()
-        fused = [g.clone() for g in hp.param_grads()]
+        fused = hp.grad_flat[0].clone()
         hp.grad_exchange = None
         hp.step_eager(0)
-        from sqlx.dist import GradBucket
-        ref = hp.param_grads()
-        GradBucket(ref).allreduce_(ref)
+        ref = hp.grad_flat[0].clone()
+        exchange(ref)
         torch.cuda.synchronize()
-        exchange_check = max(float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)) for a, b in zip(fused, ref))
+        exchange_check = float((fused - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
         hp.grad_exchange = exchange
         assert exchange_check < 1e-4, "in-step gradient exchange disagrees with the plain all-reduce: %g" % exchange_check
 
-    bucket = None
-
-    def allreduce_grads():
-        """the path's one exchange step: a single bucketed NCCL all-reduce (average) of the parameter gradients"""
-        nonlocal bucket
-        if world == 1 or exchange_in_step:
-            return
-        grads = hp.param_grads()
-        if bucket is None:
-            from sqlx.dist import GradBucket
-            bucket = GradBucket(grads)
-        bucket.allreduce_(grads)
+    def allreduce_after():
+        if world > 1 and not exchange_in_step:
+            exchange(hp.grad_flat[0])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, k):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(steps):
+        for _ in range(k):
             fn()
         b.record()
         barrier()
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms) / steps
+        return float(ms) / k
 
     def dev_step():
         hp.step()
-        allreduce_grads()
+        allreduce_after()
 
     copy_stream = torch.cuda.Stream()
     main = torch.cuda.current_stream()
-    ev_loaded = [torch.cuda.Event(), torch.cuda.Event()]
-    ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_loaded = [torch.cuda.Event() for _ in range(nslots)]
+    ev_done = [torch.cuda.Event() for _ in range(nslots)]
     e2e_i = [0]
-
     # The auto-mask tie-break noise is NOT shipped from the host in the end-to-end loop: the reference draws it with
     # the CPU generator and copies it every step (trainer.py:516-517), our API draws it on the device when no noise
     # tensor is supplied.  Everything else the step consumes (frames, decoder features, queries, intrinsics, poses,
     # coarser-scale depth maps) crosses PCIe every step.
     hb_e2e = {k: (torch.zeros_like(v) if k.startswith("noise") else v) for k, v in hb.items()}
     host_frames, host_other = hp.pack_host(hb_e2e, pin=True)     # what a collate_fn would fill: two pinned buffers
-    noise_floats = sum(hb[k].numel() for k in hb if k.startswith("noise"))
-    # the noise region is part of the flat buffer but is NOT shipped: only the leading part (everything else) is
     other_ship = hp.other_numel_without(("noise",))
     e2e_bytes = host_frames.numel() * host_frames.element_size() + other_ship * 4
 
@@ -391,138 +428,325 @@ def main():
             hp.noise_region(slot).normal_()             # all scales' noise: one contiguous region, one kernel
             ev_loaded[slot].record(copy_stream)
 
-    loss_ring = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
-    ev_loss = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_ring = [torch.zeros(1).pin_memory() for _ in range(nslots)]
+    ev_loss = [torch.cuda.Event() for _ in range(nslots)]
     loss_seen = [0.0]
+    ahead = nslots - 1
 
     def e2e_step():
-        """What a training loop with a pinned-memory prefetching loader does: the H2D copy of batch i+1 overlaps the
-        step on batch i (two device input sets).  The loss of EVERY step is copied to pinned host memory and read by
-        the host; the read of step i happens after step i+1 has been submitted, so the host never stalls the device
-        (the reference reads the loss only on logging steps, trainer.py:242-262)."""
+        """What a training loop with a pinned-memory prefetching loader does: the H2D copies of the next `ahead`
+        batches overlap the step on batch i.  The loss of EVERY step is copied to pinned host memory and read by the
+        host one step later, so the host never stalls the device (the reference reads the loss only on logging steps,
+        trainer.py:242-262)."""
         i = e2e_i[0]
-        slot = i & 1
+        slot = i % nslots
         main.wait_event(ev_loaded[slot])
         hp.step(slot)
-        allreduce_grads()
+        allreduce_after()
         ev_done[slot].record(main)
         loss_ring[slot].copy_(hp.loss.reshape(1), non_blocking=True)
         ev_loss[slot].record(main)
-        enqueue_load(slot ^ 1)                         # prefetch the next batch while this one computes
+        enqueue_load((i + ahead) % nslots)             # keep `ahead` batches in flight
         if i > 0:                                      # host-side read of the previous step's loss
-            ev_loss[slot ^ 1].synchronize()
-            loss_seen[0] = float(loss_ring[slot ^ 1])
+            pslot = (i - 1) % nslots
+            ev_loss[pslot].synchronize()
+            loss_seen[0] = float(loss_ring[pslot])
         e2e_i[0] = i + 1
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         dev_step()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = None
+    if rank == 0 and full:
+        sampler = ClockSampler(cx.local_rank)
         sampler.start()
-    ms_dev = timed(dev_step, args.steps)
+    ms_dev = timed(dev_step, steps)
     for ev in ev_done:
         ev.record(main)
-    enqueue_load(0)                                    # the very first batch; afterwards every step prefetches the next
+    for sl in range(ahead):                            # the first batches; afterwards every step prefetches one more
+        enqueue_load(sl)
     for _ in range(3):
         e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)               # (timed() ends with a device synchronize: the last loss is in)
+    ms_e2e = timed(e2e_step, steps)                    # (timed() ends with a device synchronize: the last loss is in)
     copy_stream.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
+    if sampler is not None:
+        res["clocks"] = sampler.stop()
+    res.update(value=cfg.B * world / (ms_dev * 1e-3), ms_per_step=ms_dev,
+               e2e={"value": cfg.B * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(e2e_bytes), "d2h_bytes_per_step": 4},
+               gpu_launches_per_step=launches_per_step, loss=float(hp.loss))
+
+    if not args.no_extras:
+        # the copy ceiling of the end-to-end loop: the same host -> device traffic with no compute behind it
+        h2d_i = [0]
+
+        def h2d_only():
+            with torch.cuda.stream(copy_stream):
+                hp.load_flat(host_frames, host_other[:other_ship], non_blocking=True, slot=h2d_i[0] % nslots)
+            main.wait_stream(copy_stream)
+            h2d_i[0] += 1
+        h2d_only(); torch.cuda.synchronize()
+        ms_h2d = timed(h2d_only, min(steps, 50))
+        res["e2e"]["h2d_only_ms_per_step"] = ms_h2d
+        res["e2e"]["h2d_only_GBps_per_gpu"] = e2e_bytes / (ms_h2d * 1e-3) / 1e9
+
+    if world > 1 and full:
+        # exposed communication: the same step replayed with and without the in-step exchange
+        if exchange_in_step:
+            hp.grad_exchange = None
+            hp.drop_graphs()
+            if hp.use_graph:
+                hp.capture(slot=0)
+            for _ in range(3):
+                hp.step(0)
+            ms_nocomm = timed(lambda: hp.step(0), steps)
+            res["exposed_comm_ms"] = ms_dev - ms_nocomm
+            res["ms_per_step_without_exchange"] = ms_nocomm
+            hp.grad_exchange = exchange
+            hp.drop_graphs()
 
     # per-kernel device times: the same steps submitted eagerly with CUDA events around each main kernel
+    ge, hp.grad_exchange = hp.grad_exchange, None
     _lib.profile_enable(True)
-    nprof = min(args.steps, 20)
+    nprof = min(steps, 20)
     for _ in range(nprof):
         hp.step_eager()
     torch.cuda.synchronize()
     prof = _lib.profile_report()
     _lib.profile_enable(False)
-
-    def finish():
-        """N > 1 teardown.  With the all-reduce captured inside the step's CUDA graphs, destroying the NCCL communicator
-        while those graphs are alive blocks forever (observed on 2 x B200, torch 2.11 / NCCL 2.28): drop the graphs, drain
-        the device, and leave without the communicator teardown (the process is exiting anyway)."""
-        if world == 1:
-            return
-        torch.cuda.synchronize()
-        if exchange_in_step:
-            hp.graphs = [None] * len(hp.graphs)
-            sys.stdout.flush()
-            sys.stderr.flush()
-            os._exit(0)
-        dist.destroy_process_group()
-
+    hp.grad_exchange = ge
     if rank != 0:
-        finish()
+        hp.drop_graphs()
+        del hp
+        gc.collect()
+        return None
+
+    ab, fl = algorithmic_bytes(cfg), algorithmic_flops(cfg)
+    s8d = survey_8d_bytes(cfg)
+    peak, peak_src, tpeak = cx.peak, cx.peak_src, cx.tf32_peak
+    ktot = sum(v[1] for v in prof.values())
+    kernels = {}
+    for k, v in sorted(prof.items()):
+        us = v[1] / v[0] * 1e3
+        row = {"launches_per_step": v[0] / max(1, nprof), "us_per_launch": us, "share_of_kernel_time": v[1] / ktot,
+               "hbm_frac": (ab[k] / (us * 1e-6) / 1e9 / peak) if k in ab else None}
+        if k in fl:
+            row["tensor_frac_1xtf32"] = fl[k] / (us * 1e-6) / 1e12 / tpeak
+        kernels[k] = row
+    res["kernels"] = kernels
+    res["kernel_ms_per_step"] = ktot / max(1, nprof)
+    cand = {k: v for k, v in prof.items() if k in ab}
+    dom = max(cand.items(), key=lambda kv: kv[1][1])[0] if cand else None
+    traffic = cx.traffic.get("config%d" % cfg_id, {})
+    if dom is not None:
+        cnt, tot_ms = prof[dom]
+        sec = tot_ms / cnt * 1e-3
+        achieved = ab[dom] / sec / 1e9
+        tr = traffic.get(dom)
+        res["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                           "frac": achieved / peak, "traffic": tr, "peak_source": peak_src,
+                           "avg_launch_us": sec * 1e6, "algorithmic_bytes_per_launch": ab[dom],
+                           "algorithmic_bytes": "unique bytes per launch: frames / identity losses once, depth / noise / "
+                                                "arg-min per scale (fp32)",
+                           "traffic_over_algorithmic": (tr / ab[dom]) if tr else None,
+                           "survey_8d_bytes_per_launch": s8d.get(dom),
+                           "survey_8d_frac": (s8d[dom] / sec / 1e9 / peak) if dom in s8d else None,
+                           "share_of_kernel_time": tot_ms / ktot,
+                           "timing": "CUDA events around each launch on the launching stream (eager submission of the "
+                                     "same steps after the timed region); traffic = dram bytes/launch from the "
+                                     "committed ncu capture profiles/traffic_latest.json"}
+    # step-level roofline: SURVEY 8d's compulsory bytes of the whole step over the device-timed step
+    N, n0 = cfg.H * cfg.W, cfg.h * cfg.w
+    step_bytes = cfg.B * (len(cfg.scales) * ((24 + 32 * cfg.S) * N + 12 * n0) + 4 * n0 * (3 * cfg.E + 2))
+    res["step_roofline"] = {"survey_8d_bytes_per_step": step_bytes, "frac": step_bytes / (ms_dev * 1e-3) / 1e9 / peak}
+    res["selection"] = selection_stats(hp, cfg)
+
+    if not args.no_parity and world == 1:
+        # the fp64 oracle on the timed batch (forward only, CPU, two samples at a time: every loss term is a per-sample
+        # mean followed by a batch mean, trainer.py:532,535,546, so the batch loss is the mean of the chunk losses)
+        t0 = time.perf_counter()
+        tot = 0.0
+        hb_cpu = {k: v for k, v in hb.items()}
+        for b0 in range(0, cfg.B, 2):
+            sub = {k: v[b0:b0 + 2] for k, v in hb_cpu.items()}
+            ccfg = type(cfg)(**{**cfg_kwargs(cfg), "B": sub["x"].shape[0]})
+            tot += float(oracle_step(ccfg, sub, state, backward=False)["loss"]) * sub["x"].shape[0]
+        loss_ref = tot / cfg.B
+        # the GPU loss on the SAME noise (the timed loops draw fresh device noise per step)
+        hp.load(hb, non_blocking=False, slot=0)
+        hp.step_eager(0)
+        torch.cuda.synchronize()
+        res["parity"] = {"loss_gpu": float(hp.loss), "loss_oracle_fp64": loss_ref,
+                         "abs_diff": abs(float(hp.loss) - loss_ref), "bar": 1e-5,
+                         "oracle": "oracle/sqldepth_oracle.py in float64 on the host CPU, forward only, %.1f s"
+                                   % (time.perf_counter() - t0)}
+
+    hp.drop_graphs()
+    del hp
+    gc.collect()
+    torch.cuda.empty_cache()
+    if full and not args.no_extras and world == 1:
+        # The backward's coefficient reads and tile skipping depend on which candidate wins the per-pixel minimum, and the
+        # synthetic batch is auto-masked on most pixels (see `selection`).  Upper bound of the selection-dependent cost:
+        # the same batch with --disable_automasking (trainer.py:480,514,520): EVERY pixel selects a reprojection, as a
+        # well-trained model on real driving data does on most pixels -- no tile is skipped, every coefficient is read.
+        cfg2 = type(cfg)(**{**cfg_kwargs(cfg), "automask": False})
+        hp2 = HotPath(cfg2, device=dev, use_graph=not args.no_graph, num_slots=1)
+        hp2.load_state_dict(state, strict=True)
+        hp2.load(hb, non_blocking=False)
+        for _ in range(3):
+            hp2.step()
+        ms2 = timed(lambda: hp2.step(), steps)
+        _lib.profile_enable(True)
+        for _ in range(10):
+            hp2.step_eager()
+        torch.cuda.synchronize()
+        prof2 = _lib.profile_report()
+        _lib.profile_enable(False)
+        res["reprojection_dominant"] = {
+            "value": cfg.B / (ms2 * 1e-3), "ms_per_step": ms2, "selection": selection_stats(hp2, cfg2),
+            "kernels_us": {k: v[1] / v[0] * 1e3 for k, v in prof2.items() if k.startswith("photo_")},
+            "batch": "the timed batch with --disable_automasking: 100 % of the pixels select a reprojection"}
+        hp2.drop_graphs()
+        del hp2
+        gc.collect()
+        torch.cuda.empty_cache()
+    return res
+
+
+def cfg_kwargs(c):
+    return dict(B=c.B, H=c.H, W=c.W, h=c.h, w=c.w, E=c.E, Q=c.Q, D=c.D, S=c.S, scales=c.scales, min_depth=c.min_depth,
+                max_depth=c.max_depth, disparity_smoothness=c.disparity_smoothness, stereo=c.stereo, automask=c.automask)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from _workload import baseline_config
+    cfg = baseline_config(args.config, B=args.batch or None)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warmup = max(1, args.steps), max(0, args.warmup)
+        cb = time_reference(cfg, args.config, steps=steps, warmup=warmup, device=args.device)
+        config = {"workload": workload_text(args.config, cfg), "batch_per_gpu": cfg.B, "global_batch": cfg.B,
+                  "height": cfg.H, "width": cfg.W, "source_frames": cfg.S, "loss_scales": len(cfg.scales),
+                  "stereo": cfg.stereo, "parallelism": "dp1"}
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+                "n_gpus": 1 if args.device == "cuda" else 0, "steps": steps, "warmup": warmup,
+                "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config, "gpu_launches": 0, "device": args.device,
+                "loss": cb["loss"],
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
         return
 
+    import sqlx
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (use --impl reference for the CPU arm)"
+    from sqlx.affinity import bind_to_gpu
+    binding = bind_to_gpu(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        # keep stdout to the single JSON line: NCCL's version banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    assert sqlx.lib().sqlx_device_ok(local_rank) == 1, "libsqlx targets sm_100a (B200) only"
+
+    cx = Ctx()
+    cx.args, cx.dev, cx.world, cx.rank, cx.local_rank, cx.dist = args, dev, world, rank, local_rank, dist
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    ab = algorithmic_bytes(cfg)
-    traffic = {}
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
-        for k, v in tj["kernels"].items():     # ncu names -> the names of the library's profile hooks
-            full = k.replace("void ", "")
-            k = full.split("<")[0].split("::")[-1]
-            ms = full.rstrip().endswith(", 1>")       # last template argument of the photometric kernels: all scales per launch
-            k = {"photo_fwd3_kernel": "photo_fwd_ms_kernel" if ms else "photo_fwd_kernel",
-                 "photo_bwd3_kernel": "photo_bwd_ms_kernel" if ms else "photo_bwd_kernel",
-                 "sql_tc_pred2_kernel": "sql_tc_pred_kernel"}.get(k, k)
-            traffic[k] = v["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    cand = {k: v for k, v in prof.items() if k in ab}
-    dom = max(cand.items(), key=lambda kv: kv[1][1])[0] if cand else None
-    roofline = None
-    if dom is not None:
-        cnt, tot_ms = prof[dom]
-        achieved = ab[dom] / (tot_ms / cnt * 1e-3) / 1e9
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic.get(dom), "peak_source": peak_src,
-                    "avg_launch_us": tot_ms / cnt * 1e3, "algorithmic_bytes_per_launch": ab[dom],
-                    "share_of_kernel_time": tot_ms / sum(v[1] for v in prof.values()),
-                    "timing": "CUDA events around each launch on the launching stream (eager submission of the same "
-                              "steps after the timed region); traffic = dram bytes/launch from the committed ncu "
-                              "capture profiles/traffic_latest.json"}
-    step_ms_kernels = sum(v[1] for v in prof.values()) / max(1, nprof)
-    kernels = {k: {"launches_per_step": v[0] / max(1, nprof),
-                   "ms_per_step": v[1] / max(1, nprof),
-                   "hbm_frac": (ab[k] / (v[1] / v[0] * 1e-3) / 1e9 / peak) if k in ab else None}
-               for k, v in sorted(prof.items())}
+    cx.peak = float(peaks.get("hbm_gbs", 6650.0))
+    cx.peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    # 1xTF32 tensor peak = half the measured sustained bf16 rate (SURVEY 8d)
+    cx.tf32_peak = 0.5 * float(peaks.get("bf16_tflops_sustained", 1422.0))
+    cx.traffic = load_traffic()
+
+    res = run_workload(cx, args.config, cfg, args.steps, args.warmup, full=True)
+    extra = {}
+    for tok in [t for t in args.workloads.split(",") if t.strip()]:
+        n = int(tok)
+        if n == args.config:
+            continue
+        r = run_workload(cx, n, baseline_config(n), max(20, min(args.steps, 100)), max(args.warmup, 3), full=False)
+        if r is not None:
+            extra["config%d" % n] = r
+
+    def finish():
+        """N > 1 teardown: the graphs holding captured collectives are gone (run_workload drops them), drain the device
+        and destroy the process group; a watchdog ends the process if the communicator teardown does not return."""
+        if world == 1:
+            return
+        torch.cuda.synchronize()
+        gc.collect()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        t = threading.Timer(20.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        dist.barrier()
+        dist.destroy_process_group()
+        t.cancel()
+
+    if rank != 0:
+        finish()
+        return
+
+    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    config = res.pop("config")
+    config["l2"] = ("no explicit flush: every step streams its inputs (frames, decoder features, noise: > 126 MB at every "
+                    "workload) plus the saved planes of the loss scales through the 126 MB L2")
+    config["submission"] = "eager" if args.no_graph else "cuda_graph"
+    if world > 1:
+        config["grad_exchange"] = (
+            "one NCCL all-reduce (average) of the flat gradient bucket per step (the kernels write the parameter gradients "
+            "into views of it: no pack / unpack), issued inside the step on a communication stream when the last parameter "
+            "gradient exists (overlaps the summary-path backward kernel; part of the CUDA graph)"
+            if not args.allreduce_after_step else
+            "one NCCL all-reduce (average) of the flat gradient bucket after the step")
+    config["e2e_pipeline"] = ("H2D of the next %d batches on a copy stream overlaps the step on batch i (%d device input "
+                              "sets); tie-break noise drawn on the device instead of copied from the host; the loss of "
+                              "every step is copied to pinned host memory and read by the host one step later; frames "
+                              "shipped as %s" % (max(1, args.prefetch), max(2, args.prefetch + 1),
+                                                 "float32" if args.f32_frames else "uint8 and scaled to [0,1] on the device"))
+    config["cpu_binding"] = binding
+    line["config"] = config
+    line["e2e"] = res.pop("e2e")
+    line["gpu_launches"] = res["gpu_launches_per_step"] * args.steps
+    for k in ("gpu_launches_per_step", "clocks", "roofline", "step_roofline", "kernels", "kernel_ms_per_step", "loss",
+              "parity", "selection", "reprojection_dominant", "exposed_comm_ms", "ms_per_step_without_exchange"):
+        if k in res:
+            line[k] = res[k]
+    line["workloads"] = extra
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:          # reported beside the N = 1 line only
-        cpu = time_cpu(cfg, args, steps=3, warmup=1)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-
-    total_bytes = sum(v.numel() * 4 for v in hb.values())   # device-resident footprint (frames are fp32 on the device)
-    config["l2"] = ("no explicit flush: every step streams %.0f MB of inputs plus %.0f MB of gradients through a 126 MB L2"
-                    % (total_bytes / 1e6, (hb["x"].numel() * 4) / 1e6))
-    config["submission"] = "eager" if args.no_graph else "cuda_graph"
-    if world > 1:
-        config["grad_exchange"] = ("one bucketed NCCL all-reduce (average) of the parameter gradients per step, issued inside "
-                                   "the step on a communication stream when the last parameter gradient exists (overlaps the "
-                                   "summary-path backward kernel; part of the CUDA graph); max rel. difference to a plain "
-                                   "all-reduce after the step: %.2g" % exchange_check) if exchange_in_step else \
-            "one bucketed NCCL all-reduce (average) of the parameter gradients after the step"
-    config["e2e_pipeline"] = ("H2D of batch i+1 on a copy stream overlaps the step on batch i (2 device input sets); "
-                              "tie-break noise drawn on the device instead of copied from the host; the loss of every step is "
-                              "copied to pinned host memory and read by the host one step later; frames shipped as %s"
-                              % ("float32" if args.f32_frames else "uint8 and scaled to [0,1] on the device"))
-    line = {"metric": METRIC, "value": cfg.B * world / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "e2e": {"value": cfg.B * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(e2e_bytes), "d2h_bytes_per_step": 4},
-            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "kernels": kernels, "kernel_ms_per_step": step_ms_kernels, "loss": float(hp.loss)}
+        cb = time_reference(cfg, args.config, steps=4, warmup=1, device="cpu")
+        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line["cpu_baseline"] = cpu
+    if not args.no_extras and world == 1:
+        # informational: the same unmodified reference code on THIS GPU (stock PyTorch / cuDNN / cuBLAS op chain)
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--device", "cuda",
+                                  "--config", str(args.config), "--steps", "20", "--warmup", "5"],
+                                 capture_output=True, text=True, timeout=300)
+            g = json.loads(out.stdout.strip().splitlines()[-1])
+            line["torch_gpu_baseline"] = {"value": g["value"], "unit": UNIT, "ms_per_step": g["ms_per_step"],
+                                          "what": "unmodified reference modules (oracle/_ref) on the same B200, fp32, "
+                                                  "eager PyTorch; includes the decoder front (see cpu_baseline.sample)"}
+        except Exception as e:       # never fail the bench line on the informational leg
+            line["torch_gpu_baseline"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line))
     finish()
 

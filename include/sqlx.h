@@ -319,16 +319,27 @@ int sqlx_sql_summary_fwd(const float* x, const float* queries, int B, int E, int
 int sqlx_sql_tc_supported(int E, int Q, int D, int n);
 /* on = 0 forces the exact-fp32 CUDA-core kernels for every shape (A/B tests); returns the previous setting */
 int sqlx_sql_set_tensor_cores(int on);
+int sqlx_sql_get_tensor_cores(void);   /* current setting (read-only) */
 int sqlx_sql_energy_tc(const float* x, const float* queries, int B, int E, int Q, int n, float* energy, void* stream);
 
 /* Mixed-weight decomposition (tensor cores only; sqlx_sql_tc_supported must hold):
- *   logits = Wp (K x) + b = (Wp K) x + b = M x + b with M [B,D,E] = Wp . queries computed by the caller (cuBLAS).
+ *   logits = Wp (K x) + b = (Wp K) x + b = M x + b with M [B,D,E] = Wp . queries (sqlx_sql_mix_weights).
  * The regression and its backward then contract over E = 32 instead of Q and need no Wp tiles on chip:
  *   sqlx_sql_pred_mix_fwd   pred [B,n]                                  (depth_decoder_QTR.py:61,70)
  *   sqlx_sql_bwd_pred_mix   d_M [B,D,E], d_bp [D], d_centers [B,D], d_x [B,E,n] (regression path; all overwritten)
  *   sqlx_sql_bwd_summary    d_x (+)= summary path, d_queries [B,Q,E] = summary-path part of d_K (overwritten)
- * The caller finishes with d_Wp = sum_b d_M queries^T and d_queries += Wp^T d_M. */
+ * The caller finishes with d_Wp = sum_b d_M queries^T and d_queries += Wp^T d_M (sqlx_sql_mix_weights_bwd).
+ *   sqlx_sql_mix_weights      Mx [B,D,E] = Wp [D,Q] . queries [B,Q,E]   (the 1x1 conv weight of depth_decoder_QTR.py:28
+ *                             folded into the queries of networks/layers.py:17)
+ *   sqlx_sql_mix_weights_bwd  d_Wp [D,Q] = sum_b d_Mx[b] queries[b]^T (overwritten);
+ *                             d_queries [B,Q,E] (+)= Wp^T d_Mx[b]  (accumulate_d_queries: add to what
+ *                             sqlx_sql_bwd_summary wrote); either output may be NULL (skipped), so the weight
+ *                             gradient can be produced before the gradient exchange starts and the query part later
+ * Fixed summation order; no workspace. */
 size_t sqlx_sql_mix_workspace_bytes(int B, int Q, int D, int n);
+int sqlx_sql_mix_weights(const float* Wp, const float* queries, int B, int Q, int D, int E, float* Mx, void* stream);
+int sqlx_sql_mix_weights_bwd(const float* d_Mx, const float* queries, const float* Wp, int B, int Q, int D, int E,
+                             int accumulate_d_queries, float* d_Wp, float* d_queries, void* stream);
 int sqlx_sql_pred_mix_fwd(const float* x, const float* Mx, const float* bp, const float* centers, int B, int E, int D,
                           int n, float* pred, void* stream);
 int sqlx_sql_bwd_pred_mix(const float* x, const float* Mx, const float* bp, const float* centers, const float* g_pred,

@@ -21,7 +21,11 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SQLX_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# /root/reference where it is mounted (the build container); otherwise oracle/_ref, the unmodified copy that
+# oracle/build_ref.py makes (git-ignored, shipped to the GPU box like the built .so files)
+REFERENCE_ROOT = os.environ.get("SQLX_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/trainer.py") else os.path.join(_HERE, "_ref"))
 
 
 def available():
@@ -29,15 +33,32 @@ def available():
 
 
 _loaded = {}
+_orig_cuda = {}
 
 
-def load():
-    """Returns a namespace with the reference modules: layers, networks, trainer, options."""
+def cuda_noop(on):
+    """Make Tensor.cuda / Module.cuda no-ops (on=True) or restore them: the reference calls .cuda() unconditionally
+    (trainer.py:517 on the tie-break noise), which must stay on the host for the CPU arm."""
+    import torch
+    if on and not _orig_cuda:
+        _orig_cuda.update(t=torch.Tensor.cuda, m=torch.nn.Module.cuda)
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+    elif not on and _orig_cuda:
+        torch.Tensor.cuda, torch.nn.Module.cuda = _orig_cuda.pop("t"), _orig_cuda.pop("m")
+
+
+def load(force_cpu=False):
+    """Returns a namespace with the reference modules: layers, networks, trainer, options.
+    force_cpu: make Tensor.cuda / Module.cuda no-ops even when a GPU is visible (the CPU arm of bench.py on the GPU
+    box: trainer.py:517 calls .cuda() on the tie-break noise)."""
+    import torch
+    cuda_noop(force_cpu or not torch.cuda.is_available())
     if _loaded:
         return types.SimpleNamespace(**_loaded)
     if not available():
-        raise RuntimeError("reference tree not mounted at %s" % REFERENCE_ROOT)
-    import torch
+        raise RuntimeError("reference tree not found at %s (run oracle/build_ref.py where /root/reference is mounted)"
+                           % REFERENCE_ROOT)
 
     def stub(name, **attrs):
         if name in sys.modules:
@@ -56,10 +77,6 @@ def load():
 
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
-    if not torch.cuda.is_available():
-        torch.Tensor.cuda = lambda self, *a, **k: self
-        torch.nn.Module.cuda = lambda self, *a, **k: self
-
     import torchvision.models as tvm
     import layers as ref_layers
     import networks as ref_networks
@@ -76,10 +93,10 @@ def load():
 
 
 def make_trainer(batch_size, height, width, scales=(0,), frame_ids=(0, -1, 1), use_stereo=False,
-                 extra_args=()):
+                 extra_args=(), device="cpu"):
     """A reference Trainer with only the attributes the loss path needs (no models, no data)."""
     import torch
-    ref = load()
+    ref = load(force_cpu=(str(device) == "cpu"))
     argv = ["--height", str(height), "--width", str(width), "--batch_size", str(batch_size),
             "--scales"] + [str(s) for s in scales] + ["--frame_ids"] + [str(f) for f in frame_ids if f != "s"]
     if use_stereo:
@@ -90,7 +107,7 @@ def make_trainer(batch_size, height, width, scales=(0,), frame_ids=(0, -1, 1), u
         opt.frame_ids.append("s")          # trainer.py:52-53
     T = ref.trainer.Trainer.__new__(ref.trainer.Trainer)
     T.opt = opt
-    T.device = torch.device("cpu")
+    T.device = torch.device(device)
     T.num_scales = len(opt.scales)
     T.num_input_frames = len(opt.frame_ids)
     T.num_pose_frames = 2
@@ -98,6 +115,6 @@ def make_trainer(batch_size, height, width, scales=(0,), frame_ids=(0, -1, 1), u
     T.models = {}
     if not opt.no_ssim:
         T.ssim = ref.layers.SSIM()
-    T.backproject_depth = {0: ref.layers.BackprojectDepth(batch_size, height, width)}
-    T.project_3d = {0: ref.layers.Project3D(batch_size, height, width)}
+    T.backproject_depth = {0: ref.layers.BackprojectDepth(batch_size, height, width).to(T.device)}
+    T.project_3d = {0: ref.layers.Project3D(batch_size, height, width).to(T.device)}
     return T

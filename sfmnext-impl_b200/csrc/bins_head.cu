@@ -254,11 +254,7 @@ extern "C" int sqlx_head_linear_bwd(const float* W, const float* x, const float*
   const int nx = dx ? ceil_div(K, 32) : 0;
   const size_t smem = dx ? sizeof(float) * (size_t)N * kHeadMaxB : 0;
   SQLX_REQUIRE(smem <= 160 * 1024, "out_features %d too large for the d_input half", N);
-  static size_t configured = 0;
-  if (smem >= 24 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(head_linear_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  if (int e = ensure_dyn_smem(head_linear_bwd_kernel, 160 * 1024)) return e;   // the cap checked above, once per device
   ProfScope prof("head_linear_bwd_kernel", st);
   head_linear_bwd_kernel<<<nx + N, kHeadBwdThreads, smem, st>>>(dy, y, x, W, B, N, K, leaky, nx, dz, dW, db, dx);
   return check_launch("head_linear_bwd_kernel");

@@ -22,6 +22,13 @@ int check_launch(const char* what);
 
 constexpr int kNumSMs = 148;  // B200
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device, per-function attribute: set it once per (kernel, current
+// device), thread-safe (core.cu).  The library is entered from the training thread and from autograd's per-device
+// backward threads, and one process may drive several GPUs (nn.DataParallel).  Returns SQLX_OK or SQLX_ECUDA.
+int ensure_dyn_smem(const void* kernel, size_t bytes);
+template <class K>
+inline int ensure_dyn_smem(K* kernel, size_t bytes) { return ensure_dyn_smem(reinterpret_cast<const void*>(kernel), bytes); }
+
 // Times the enclosed launches with CUDA events on `st` while sqlx_profile_enable(1) is in effect (core.cu).
 class ProfScope {
  public:

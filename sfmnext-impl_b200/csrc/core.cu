@@ -29,6 +29,29 @@ int check_launch(const char* what) {
 
 }  // namespace sqlx
 
+#include <mutex>
+#include <set>
+#include <utility>
+
+namespace sqlx {
+int ensure_dyn_smem(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;      // (kernel, device) pairs already configured
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return check_launch("cudaGetDevice");
+  std::lock_guard<std::mutex> lk(mu);
+  const auto key = std::make_pair(kernel, dev);
+  if (done.count(key)) return SQLX_OK;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize = %zu) failed on device %d: %s", bytes, dev,
+              cudaGetErrorString(cudaGetLastError()));
+    return SQLX_ECUDA;
+  }
+  done.insert(key);
+  return SQLX_OK;
+}
+}  // namespace sqlx
+
 extern "C" const char* sqlx_last_error(void) { return sqlx::g_err; }
 
 extern "C" int sqlx_version(void) { return 100; }

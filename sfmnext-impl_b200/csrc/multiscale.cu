@@ -745,12 +745,11 @@ bool ms_fusable(const sqlx_ms_desc* d) { return !(d->photo.flags & SQLX_NO_SSIM)
 
 // Blocks per (scale, sample) actually launched (<= kMsBlocks, which sizes the partial arrays): about 15 frame pixels
 // per thread -- measured on a B200 at 192x640 x 4 scales x 12 samples: 96 blocks 36 + 40 us (statistics + smoothness
-// kernels), 48: 32 + 34, 32: 30 + 31, 24: 29 + 33.  SQLX_MS_BLOCKS overrides.
+// kernels), 48: 32 + 34, 32: 30 + 31, 24: 29 + 33.
 int ms_blocks(int H, int W) {
-  static const int forced = []() { const char* v = getenv("SQLX_MS_BLOCKS"); return v ? atoi(v) : 0; }();
-  int k = forced > 0 ? forced : (int)(((long long)H * W + 256 * 15 - 1) / (256 * 15));
-  if (forced <= 0 && k < 24) k = 24;
-  return k < 1 ? 1 : (k > kMsBlocks ? kMsBlocks : k);
+  int k = (int)(((long long)H * W + 256 * 15 - 1) / (256 * 15));
+  if (k < 24) k = 24;
+  return k > kMsBlocks ? kMsBlocks : k;
 }
 
 sqlx_photo_desc scale_photo_desc(const sqlx_ms_desc* d, int s) {
@@ -806,8 +805,7 @@ extern "C" int sqlx_ms_loss_fwd(const sqlx_ms_desc* d, const float* const* depth
     if (int e = check_launch("ms_stats_pose_kernel")) return e;
   }
   int ctas = 0;
-  static const int fused = []() { const char* v = getenv("SQLX_MS_FUSED_FWD"); return v ? atoi(v) : 1; }();
-  if (fused && ns > 1 && ms_fusable(d)) {
+  if (ns > 1 && ms_fusable(d)) {
     // every scale in one launch: the target tile, its statistics and the identity losses are shared by the scales
     const sqlx_photo_desc pd = scale_photo_desc(d, 0);
     const float* dups[SQLX_MAX_SCALES];
@@ -876,8 +874,7 @@ extern "C" int sqlx_ms_loss_bwd(const sqlx_ms_desc* d, const float* const* depth
   }
   if (cudaMemsetAsync(dP, 0, sizeof(float) * (size_t)ns * B * S * 12, st) != cudaSuccess)
     return check_launch("cudaMemsetAsync(dP)");
-  static const int fused = []() { const char* v = getenv("SQLX_MS_FUSED_BWD"); return v ? atoi(v) : 1; }();
-  if (fused && ns > 1 && ms_fusable(d)) {
+  if (ns > 1 && ms_fusable(d)) {
     const sqlx_photo_desc pd = scale_photo_desc(d, 0);
     const float* dups[SQLX_MAX_SCALES];
     float* qups[SQLX_MAX_SCALES];

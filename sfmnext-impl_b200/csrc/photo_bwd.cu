@@ -260,11 +260,7 @@ int launch_ssim_bwd(const float* x, const float* y, const float* g, int planes, 
   using C = BwdCfg<R, kTH, kTW, kNT>;
   auto kern = ssim_bwd_kernel<R, kTH, kTW, kNT>;
   const size_t smem = sizeof(float) * (2 * C::PLANE2 + 5 * C::HB + 3 * C::CF);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  if (int e = ensure_dyn_smem(kern, smem)) return e;
   dim3 grid(ceil_div(W, kTW), ceil_div(H, kTH), planes);
   kern<<<grid, kNT, smem, st>>>(x, y, g, H, W, gx);
   return check_launch("ssim_bwd_kernel");

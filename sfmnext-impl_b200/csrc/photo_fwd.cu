@@ -216,11 +216,7 @@ int launch_reproj(const float* pred, const float* target, int B, int C_, int H, 
   using C = FwdCfg<R, kTH, kTW, kNT>;
   auto kern = reproj_loss_kernel<R, kTH, kTW, kNT, MAP>;
   const size_t smem = sizeof(float) * (2 * C::PLANE + 5 * C::HB);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  if (int e = ensure_dyn_smem(kern, smem)) return e;
   dim3 grid(ceil_div(W, kTW), ceil_div(H, kTH), B);
   ProfScope prof("reproj_loss_kernel", st);
   kern<<<grid, kNT, smem, st>>>(pred, target, C_, H, W, w_ssim, w_l1, out, out_bstride);

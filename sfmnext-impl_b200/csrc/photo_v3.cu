@@ -266,10 +266,7 @@ struct Fwd3Cfg {
   static_assert((TH * TW) % NT == 0 && NT % TW == 0 && NT >= PH + PW, "tile / block shape");
 };
 
-// STG = 1 (candidate, selected with SQLX_FWD_MS_STAGE=1, not the default): the depth / target staging issues ALL of a
-// thread's region elements in one trip (6 elements: 6 depth loads, + 18 target loads on the first scale) instead of
-// two elements per trip -- one exposed global-load latency per scale instead of three.
-template <int R, int TH, int TW, int NT, int MINB, bool MERGED, bool OCC = false, bool MS = false, int STG = 0>
+template <int R, int TH, int TW, int NT, int MINB, bool MERGED, bool OCC = false, bool MS = false>
 __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const __grid_constant__ PhotoFwdParams p) {
   using C = Fwd3Cfg<R, TH, TW, NT, MERGED>;
   constexpr int PPT = C::PPT;
@@ -317,34 +314,7 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const __grid_const
     load_camera(p.K + b * 16, p.invK + b * 16, T_sc + ((size_t)b * S + threadIdx.x) * 16, cams[threadIdx.x]);
   __syncthreads();
 
-  if (STG == 1 && MS) {   // (MS: every scale has its upsampled plane) all elements of the thread in one trip
-    const float* up_map = p.ms_depth_up[sc] + (size_t)b * plane;
-    const float* tgb = p.target + (size_t)b * 3 * plane;
-    constexpr int NEL = (C::PH * C::PW + NT - 1) / NT;
-    float dv1[NEL], tv1[NEL][3];
-    int lr = threadIdx.x / C::PW, lc = threadIdx.x - lr * C::PW;
-#pragma unroll
-    for (int e = 0; e < NEL; ++e) {
-      if ((int)threadIdx.x + e * NT < C::PH * C::PW) {
-        const int off = rowt[lr].w * W + colt[lc].w;
-        dv1[e] = __ldg(up_map + off);
-        if (first) {
-          tv1[e][0] = __ldg(tgb + off); tv1[e][1] = __ldg(tgb + plane + off); tv1[e][2] = __ldg(tgb + 2 * plane + off);
-        }
-      }
-      region_advance<C::PW, NT>(lr, lc);
-    }
-    lr = threadIdx.x / C::PW; lc = threadIdx.x - lr * C::PW;
-#pragma unroll
-    for (int e = 0; e < NEL; ++e) {
-      if ((int)threadIdx.x + e * NT < C::PH * C::PW) {
-        const int o = lr * C::LD + lc;
-        dpl[o] = dv1[e];
-        if (first) { tg[o] = tv1[e][0]; tg[C::PLANE + o] = tv1[e][1]; tg[2 * C::PLANE + o] = tv1[e][2]; }
-      }
-      region_advance<C::PW, NT>(lr, lc);
-    }
-  } else {   // upsampled depth and (first scale only) the three target planes on the R halo, two elements per trip
+  {   // upsampled depth and (first scale only) the three target planes on the R halo, two elements per trip
     const float* lr_map = p.depth_lr + (size_t)b * p.d.h * p.d.w;
     const float* dup = MS ? p.ms_depth_up[sc] : p.depth_up;
     const float* up_map = dup ? dup + (size_t)b * plane : nullptr;
@@ -1157,29 +1127,17 @@ __global__ void dT_from_dP3_kernel(const float* __restrict__ K, const float* __r
 using namespace sqlx;
 
 namespace {
-// Tile configurations.  The default was picked on a B200 (tools/time_photo.py); SQLX_FWD_CFG / SQLX_BWD_CFG select
-// the others for tuning.
-//   forward : 0 = 32x32 tile, 256 threads (4 px/thread), 2 CTAs/SM     1 = 16x32, 256 (2 px/thread), 3 CTAs/SM
-//             2 = 16x32, 256, 4 CTAs/SM                                3 = 32x32, 512 (2 px/thread), 2 CTAs/SM
-//             4 = configuration 0 with the three channels' horizontal sums in one pass (2 barriers per source)
-//             5 = 16x32, 128 threads (4 px/thread), 4 CTAs/SM (measured equal to 0: +16 % halo work, better overlap)
-//   backward: 0 = 16x32, 256, 3 CTAs/SM    1 = 16x32, 256, 4 CTAs/SM    2 = 32x32, 256 (4 px/thread), 2 CTAs/SM
-//             3 = 16x32, 256, 2 CTAs/SM (no register cap)
-int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
+// Tile configurations, picked on a B200 (A/B of round 1 and round 2, profiles/r02a_candidates.log: every alternative
+// -- 16x32 forward tiles at 3 or 4 CTAs/SM, one-trip staging, 32x32 or uncapped backward tiles -- measured slower or
+// equal and was removed):
+//   forward : 32x32 tile, 256 threads (4 px/thread), 2 CTAs/SM        backward: 16x32 tile, 256 threads, 3 CTAs/SM
 constexpr int kMinTH = 16, kMinTW = 32;   // smallest tile of any configuration: sizes the per-CTA partial buffer
 
-template <int R, int TH, int TW, int NT, int MINB, bool MERGED = false, bool OCC = false, bool MS = false, int STG = 0>
+template <int R, int TH, int TW, int NT, int MINB, bool MERGED = false, bool OCC = false, bool MS = false>
 int launch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
   using C = Fwd3Cfg<R, TH, TW, NT, MERGED>;
-  auto kern = photo_fwd3_kernel<R, TH, TW, NT, MINB, MERGED, OCC, MS, STG>;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
-    configured = true;
-  }
+  auto kern = photo_fwd3_kernel<R, TH, TW, NT, MINB, MERGED, OCC, MS>;
+  if (int e = ensure_dyn_smem(kern, C::smem_bytes)) return e;
   dim3 grid(ceil_div(p.d.W, TW), ceil_div(p.d.H, TH), p.d.B);
   *ctas = (int)(grid.x * grid.y * grid.z);
   ProfScope prof(OCC ? "photo_occ_fwd_kernel" : (MS ? "photo_fwd_ms_kernel" : "photo_fwd_kernel"), st);
@@ -1190,37 +1148,15 @@ int launch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
 template <int R>
 int dispatch_photo_fwd3(const PhotoFwdParams& p, int* ctas, cudaStream_t st) {
   if (p.partial_reg) return launch_photo_fwd3<R, 32, 32, 256, 2, false, true>(p, ctas, st);   // indoor variant
-  if (p.ns > 0) {   // all scales per CTA
-    // candidates (not the default; tools/check_candidates.py runs the A/B): staging variant, other tile shapes
-    static const int stage = env_int("SQLX_FWD_MS_STAGE", 0);
-    static const int mscfg = env_int("SQLX_FWD_MS_CFG", 0);
-    if constexpr (R == 3) {
-      if (stage == 1) return launch_photo_fwd3<R, 32, 32, 256, 2, false, false, true, 1>(p, ctas, st);
-      if (mscfg == 1) return launch_photo_fwd3<R, 16, 32, 256, 3, false, false, true>(p, ctas, st);
-      if (mscfg == 5) return launch_photo_fwd3<R, 16, 32, 128, 4, false, false, true>(p, ctas, st);
-    }
-    return launch_photo_fwd3<R, 32, 32, 256, 2, false, false, true>(p, ctas, st);
-  }
-  static const int cfg = env_int("SQLX_FWD_CFG", 0);
-  switch (cfg) {
-    case 1: return launch_photo_fwd3<R, 16, 32, 256, 3>(p, ctas, st);
-    case 2: return launch_photo_fwd3<R, 16, 32, 256, 4>(p, ctas, st);
-    case 3: return launch_photo_fwd3<R, 32, 32, 512, 2>(p, ctas, st);
-    case 4: return launch_photo_fwd3<R, 32, 32, 256, 2, true>(p, ctas, st);
-    case 5: return launch_photo_fwd3<R, 16, 32, 128, 4>(p, ctas, st);
-    default: return launch_photo_fwd3<R, 32, 32, 256, 2>(p, ctas, st);
-  }
+  if (p.ns > 0) return launch_photo_fwd3<R, 32, 32, 256, 2, false, false, true>(p, ctas, st);   // all scales per CTA
+  return launch_photo_fwd3<R, 32, 32, 256, 2>(p, ctas, st);
 }
 
 template <int R, int TH, int TW, int NT, int MINB, bool OCC = false, bool MS = false>
 int launch_photo_bwd3(const PhotoBwdParams& p, cudaStream_t st) {
   using C = Bwd3Cfg<R, TH, TW, NT>;
   auto kern = photo_bwd3_kernel<R, TH, TW, NT, MINB, OCC, MS>;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
-    configured = true;
-  }
+  if (int e = ensure_dyn_smem(kern, C::smem_bytes)) return e;
   dim3 grid(ceil_div(p.d.W, TW), ceil_div(p.d.H, TH), p.d.B * (MS ? p.ns : 1));
   ProfScope prof(OCC ? "photo_occ_bwd_kernel" : (MS ? "photo_bwd_ms_kernel" : "photo_bwd_kernel"), st);
   kern<<<grid, NT, C::smem_bytes, st>>>(p);
@@ -1230,21 +1166,8 @@ int launch_photo_bwd3(const PhotoBwdParams& p, cudaStream_t st) {
 template <int R>
 int dispatch_photo_bwd3(const PhotoBwdParams& p, cudaStream_t st) {
   if (p.g_reg) return launch_photo_bwd3<R, 16, 32, 256, 2, true>(p, st);   // indoor variant
-  if (p.ns > 0) {   // all scales in one launch
-    static const int mscfg = env_int("SQLX_BWD_MS_CFG", 0);      // candidates, see tools/check_candidates.py
-    if constexpr (R == 3) {
-      if (mscfg == 2) return launch_photo_bwd3<R, 32, 32, 256, 2, false, true>(p, st);
-      if (mscfg == 3) return launch_photo_bwd3<R, 16, 32, 256, 2, false, true>(p, st);
-    }
-    return launch_photo_bwd3<R, 16, 32, 256, 3, false, true>(p, st);
-  }
-  static const int cfg = env_int("SQLX_BWD_CFG", 0);
-  switch (cfg) {
-    case 1: return launch_photo_bwd3<R, 16, 32, 256, 4>(p, st);
-    case 2: return launch_photo_bwd3<R, 32, 32, 256, 2>(p, st);
-    case 3: return launch_photo_bwd3<R, 16, 32, 256, 2>(p, st);
-    default: return launch_photo_bwd3<R, 16, 32, 256, 3>(p, st);
-  }
+  if (p.ns > 0) return launch_photo_bwd3<R, 16, 32, 256, 3, false, true>(p, st);   // all scales in one launch
+  return launch_photo_bwd3<R, 16, 32, 256, 3>(p, st);
 }
 
 int check_desc(const sqlx_photo_desc* d) {
@@ -1519,11 +1442,7 @@ template <int R>
 int launch_identity3(const IdentParams& p, cudaStream_t st) {
   using C = Ident3Cfg<R, 32, 32, 256>;
   auto kern = identity3_kernel<R, 32, 32, 256>;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
-    configured = true;
-  }
+  if (int e = ensure_dyn_smem(kern, C::smem_bytes)) return e;
   dim3 grid(ceil_div(p.W, 32), ceil_div(p.H, 32), p.B);
   ProfScope prof("identity_loss_kernel", st);
   kern<<<grid, 256, C::smem_bytes, st>>>(p);

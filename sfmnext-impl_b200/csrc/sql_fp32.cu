@@ -11,6 +11,8 @@
 // Backward formulas: SURVEY.md Appendix A.1.
 #include "common.cuh"
 
+#include <atomic>
+
 #include <math.h>
 
 namespace sqlx {
@@ -698,9 +700,6 @@ namespace sqlx {
 void tc_summary_plan(int B, int n, int* chunks, int* tiles_per_chunk);
 int tc_summary_partials(const float* x, const float* queries, int B, int Q, int n, float* partial, int* chunks_out,
                         cudaStream_t st);
-int tc_pred_fwd(const float* x, const float* queries, const float* Wp, const float* bp, const float* centers, int B,
-                int Q, int D, int n, float* pred, cudaStream_t st);
-bool tc_bwd_supported(int Q, int D);
 int tc_pred_mix_fwd(const float* x, const float* Mx, const float* bp, const float* centers, int B, int D, int n,
                     float* pred, cudaStream_t st);
 int tc_bwd_pred_mix(const float* x, const float* Mx, const float* bp, const float* centers, const float* g_pred, int B,
@@ -710,13 +709,6 @@ int tc_bwd_sum(const float* x, const float* queries, const float* summary, const
                const float* d_summary, int B, int Q, int n, int accumulate, float* d_x, float* part_dK, int chunks, int tpc,
                cudaStream_t st);
 void tc_bwd_plan(int B, int n, int* chunks, int* tiles_per_chunk);
-int tc_bwd_dx_partials(const float* x, const float* queries, const float* Wp, const float* bp, const float* centers,
-                       const float* g_pred, const float* summary, const float* row_max, const float* row_sum,
-                       const float* d_summary, int B, int Q, int D, int n, float* d_x, float* part_dK, int chunks, int tpc,
-                       cudaStream_t st);
-int tc_bwd_reduce_partials(const float* x, const float* queries, const float* Wp, const float* bp, const float* centers,
-                           const float* g_pred, int B, int Q, int D, int n, float* part_dW, float* part_dc,
-                           float* part_db, int chunks, int tpc, cudaStream_t st);
 }
 extern "C" int sqlx_sql_tc_supported(int E, int Q, int D, int n);
 extern "C" int sqlx_sql_set_tensor_cores(int on);
@@ -725,7 +717,7 @@ extern "C" int sqlx_sql_energy_tc(const float* x, const float* queries, int B, i
 
 namespace {
 
-int g_use_tc = 1;   // sqlx_sql_set_tensor_cores(0) forces the exact-fp32 CUDA-core kernels (tests, A/B timing)
+std::atomic<int> g_use_tc{1};   // sqlx_sql_set_tensor_cores(0) forces the exact-fp32 CUDA-core kernels (tests, A/B timing)
 bool use_tensor_cores(int E, int Q, int D, int n) { return g_use_tc && sqlx_sql_tc_supported(E, Q, D, n); }
 
 int check_sql_shape(int B, int E, int Q, int D, int n, bool need_d) {
@@ -857,11 +849,8 @@ int run_bwd_dx(const float* x, const float* queries, const float* Wp, const floa
 
 }  // namespace
 
-extern "C" int sqlx_sql_set_tensor_cores(int on) {
-  const int prev = g_use_tc;
-  g_use_tc = on ? 1 : 0;
-  return prev;
-}
+extern "C" int sqlx_sql_set_tensor_cores(int on) { return g_use_tc.exchange(on ? 1 : 0); }
+extern "C" int sqlx_sql_get_tensor_cores(void) { return g_use_tc.load(); }
 
 extern "C" size_t sqlx_sql_workspace_bytes(int B, int E, int Q, int D, int n) {
   if (B <= 0 || E <= 0 || Q <= 0 || D < 0 || n <= 0) return 0;
@@ -896,7 +885,7 @@ extern "C" int sqlx_sql_pred_fwd(const float* x, const float* queries, const flo
   if (int e = check_sql_shape(B, E, Q, D, n, true)) return e;
   SQLX_REQUIRE(x && queries && Wp && bp && centers && pred, "NULL pointer argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (use_tensor_cores(E, Q, D, n)) return tc_pred_fwd(x, queries, Wp, bp, centers, B, Q, D, n, pred, st);
+  // (un-mixed formulation: exact-fp32 CUDA-core kernel for every shape; the tensor-core path is sqlx_sql_pred_mix_fwd)
   SQLX_DISPATCH_E(E, run_pred<kE>(x, queries, Wp, bp, centers, B, Q, D, n, pred, st));
 }
 
@@ -910,23 +899,6 @@ extern "C" int sqlx_sql_bwd_reduce(const float* x, const float* queries, const f
   SQLX_REQUIRE(workspace && workspace_bytes >= sizeof(float) * reduce_ws_floats(B, Q, D, n), "workspace too small");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* ws = reinterpret_cast<float*>(workspace);
-  if (use_tensor_cores(E, Q, D, n) && tc_bwd_supported(Q, D)) {
-    int chunks = 0, tpc = 0;
-    tc_bwd_plan(B, n, &chunks, &tpc);
-    const int ctas = B * chunks;
-    float* part_dW = ws;
-    float* part_dc = part_dW + (size_t)ctas * D * Q;
-    float* part_db = part_dc + (size_t)ctas * D;
-    if (int e = tc_bwd_reduce_partials(x, queries, Wp, bp, centers, g_pred, B, Q, D, n, part_dW, part_dc, part_db, chunks,
-                                       tpc, st))
-      return e;
-    sum_partials_kernel<<<dim3(ceil_div(D * Q, 256), 1), 256, 0, st>>>(part_dW, ctas, D * Q, d_Wp);
-    if (int e = check_launch("sum_partials_kernel")) return e;
-    sum_partials_kernel<<<dim3(ceil_div(D, 256), 1), 256, 0, st>>>(part_db, ctas, D, d_bp);
-    if (int e = check_launch("sum_partials_kernel")) return e;
-    sum_partials_kernel<<<dim3(ceil_div(D, 256), B), 256, 0, st>>>(part_dc, chunks, D, d_centers);
-    return check_launch("sum_partials_kernel");
-  }
   SQLX_DISPATCH_E(E, run_bwd_reduce<kE>(x, queries, Wp, bp, centers, g_pred, B, Q, D, n, d_centers, d_Wp, d_bp, ws, st));
 }
 
@@ -945,15 +917,6 @@ extern "C" int sqlx_sql_bwd_dx(const float* x, const float* queries, const float
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* ws = reinterpret_cast<float*>(workspace);
   if (!has_pred) { Wp = nullptr; bp = nullptr; centers = nullptr; }
-  if (has_pred && d_summary && !g_energy && use_tensor_cores(E, Q, D, n) && tc_bwd_supported(Q, D)) {
-    int chunks = 0, tpc = 0;
-    tc_bwd_plan(B, n, &chunks, &tpc);
-    if (int e = tc_bwd_dx_partials(x, queries, Wp, bp, centers, g_pred, summary, row_max, row_sum, d_summary, B, Q, D, n,
-                                   d_x, ws, chunks, tpc, st))
-      return e;
-    sum_partials_kernel<<<dim3(ceil_div(Q * E, 256), B), 256, 0, st>>>(ws, chunks, Q * E, d_queries);
-    return check_launch("sum_partials_kernel");
-  }
   SQLX_DISPATCH_E(E, run_bwd_dx<kE>(x, queries, Wp, bp, centers, g_pred, summary, row_max, row_sum, d_summary, g_energy,
                                     B, Q, D, n, d_x, d_queries, ws, st));
 }

@@ -124,8 +124,12 @@ _PROTOS = {
                                      c_void_p, c_size_t, c_void_p]),
     "sqlx_sql_tc_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "sqlx_sql_set_tensor_cores": (c_int, [c_int]),
+    "sqlx_sql_get_tensor_cores": (c_int, []),
     "sqlx_sql_energy_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sqlx_sql_mix_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "sqlx_sql_mix_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sqlx_sql_mix_weights_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                         c_void_p]),
     "sqlx_sql_pred_mix_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sqlx_sql_bwd_pred_mix": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -14,12 +14,21 @@ from . import sql as S
 
 class HotPathConfig:
     def __init__(self, B=12, H=192, W=640, h=96, w=320, E=32, Q=64, D=64, S=2, scales=(0, 1, 2, 3),
-                 min_depth=0.001, max_depth=80.0, disparity_smoothness=1e-3):
+                 min_depth=0.001, max_depth=80.0, disparity_smoothness=1e-3, stereo=False, automask=True):
         self.B, self.H, self.W, self.h, self.w = B, H, W, h, w
         self.E, self.Q, self.D, self.S = E, Q, D, S
         self.scales = tuple(scales)
         self.min_depth, self.max_depth = min_depth, max_depth
         self.disparity_smoothness = disparity_smoothness
+        # --use_stereo (trainer.py:52-53, 408-421): the LAST source is the stereo frame "s" with the fixed transform
+        # inputs["stereo_T"], and the PoseCNN translations are not rescaled by mean(1/depth)
+        self.stereo = bool(stereo)
+        self.automask = bool(automask)          # False: --disable_automasking (trainer.py:480,514,520)
+
+    @property
+    def pose_sources(self):
+        """indices of the sources whose pose comes from the pose network (all but the stereo frame)"""
+        return list(range(self.S - 1 if self.stereo else self.S))
 
     def scale_hw(self, s):
         """resolution of outputs[("disp", s)]: the decoder emits scale 0 at h x w; coarser scales are H/2^s."""
@@ -31,8 +40,11 @@ class HotPathConfig:
                "target": (c.B, 3, c.H, c.W)}
         for i in range(c.S):
             shp["source%d" % i] = (c.B, 3, c.H, c.W)
+        for i in c.pose_sources:
             shp["axisangle%d" % i] = (c.B, 1, 1, 3)
             shp["translation%d" % i] = (c.B, 1, 1, 3)
+        if c.stereo:
+            shp["stereo_T"] = (c.B, 4, 4)
         for s in c.scales:
             shp["noise%d" % s] = (c.B, c.S, c.H, c.W)
             if s > 0:
@@ -56,7 +68,7 @@ class HotPath(torch.nn.Module):
         self.to(device)
         self.device = torch.device(device)
         self.grad_inputs = ["x", "queries"] + ["disp%d" % s for s in c.scales if s > 0] + \
-                           ["axisangle%d" % i for i in range(c.S)] + ["translation%d" % i for i in range(c.S)]
+                           ["axisangle%d" % i for i in c.pose_sources] + ["translation%d" % i for i in c.pose_sources]
         # `num_slots` independent device input sets: with 2, the host->device copy of batch i+1 (on a copy stream)
         # overlaps the step on batch i, as a pinned-memory DataLoader does for the reference (trainer.py:164-171)
         # Every input of a set is a view into ONE flat device buffer (frames in a second one), so a host batch that
@@ -95,16 +107,26 @@ class HotPath(torch.nn.Module):
             self.slots.append(inp)
             self.flat.append(fl)
         self.inp = self.slots[0]
+        # ONE flat gradient bucket per input set: the backward kernels write every parameter gradient of the path
+        # (1x1 conv, bins MLP) straight into 256-byte aligned views of it, `p.grad` are those views, and the
+        # data-parallel exchange all-reduces the flat tensor in place -- no pack / unpack copies, no per-parameter
+        # zero-fill or accumulate kernels (the reference's nn.DataParallel reduce-adds replica gradients, trainer.py:74,93)
+        self.param_list = list(self.parameters())
+        offs, total = [], 0
+        for p_ in self.param_list:
+            offs.append(total)
+            total += (p_.numel() + 63) // 64 * 64
+        self.grad_flat = [torch.zeros(total, device=device, dtype=torch.float32) for _ in range(num_slots)]
+        self.grad_views = [[fl.narrow(0, o, p_.numel()).view_as(p_) for o, p_ in zip(offs, self.param_list)]
+                           for fl in self.grad_flat]
+        self._one = torch.ones((), device=device, dtype=torch.float32)
         self.use_graph = use_graph
         self.graphs = [None] * num_slots
         self.losses = [None] * num_slots
         self.loss = None
         self.pred = None
-        # parameter gradients of each captured graph live in that graph's memory pool (autograd ASSIGNS them: no
-        # zero-fill + accumulate kernels per parameter); step(slot) points p.grad at the replayed graph's tensors
-        self.slot_grads = [None] * num_slots
         self.side_stream = None
-        # grad_exchange(list of gradient tensors): in-place data-parallel exchange (e.g. GradBucket.allreduce_) of the
+        # grad_exchange(flat gradient bucket): in-place data-parallel exchange (e.g. an NCCL all-reduce, average) of the
         # parameter gradients.  It is issued INSIDE the step, on a side stream, as soon as the last parameter gradient
         # exists, so that it overlaps the summary-path backward kernel; the step (eager or captured graph, NCCL
         # collectives are capturable) ends with the main stream waiting for it.
@@ -167,9 +189,14 @@ class HotPath(torch.nn.Module):
         return frames.numel() * frames.element_size() + other.numel() * other.element_size()
 
     # ------------------------------------------------------------------ one eager step
-    def _centers(self, summary):
+    def _centers_fn(self, slot):
         c = self.cfg
-        return S.bins_head(summary.reshape(c.B, c.Q * c.E), self.bins_regressor, c.min_depth, c.max_depth)
+        bufs = self.grad_views[slot][2:]           # [dW1, db1, dW2, db2, dW3, db3]
+
+        def centers(summary):
+            return S.bins_head(summary.reshape(c.B, c.Q * c.E), self.bins_regressor, c.min_depth, c.max_depth,
+                               grad_buffers=bufs)
+        return centers
 
     def forward_loss(self, slot=0):
         c, I = self.cfg, self.slots[slot]
@@ -183,51 +210,60 @@ class HotPath(torch.nn.Module):
         side = self.side_stream
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            identity = P.identity_losses(I["target"], sources)
+            identity = P.identity_losses(I["target"], sources) if c.automask else None
             packed = [P.pack_rgba(src) for src in sources]
-        pred = S.sql_tail(I["x"], I["queries"], conv.weight.view(c.D, c.Q), conv.bias, self._centers,
-                          tuple(self.bins_regressor.parameters()),
-                          on_param_grads=self._start_grad_exchange if self.grad_exchange is not None else None)
+        gv = self.grad_views[slot]
+        hook = (lambda grads: self._start_grad_exchange(slot)) if self.grad_exchange is not None else None
+        pred = S.sql_tail(I["x"], I["queries"], conv.weight.view(c.D, c.Q), conv.bias, self._centers_fn(slot), (),
+                          on_param_grads=hook, head_grad_out=(gv[0].view(c.D, c.Q), gv[1]))
         main.wait_stream(side)
         disps = {s: (pred if s == 0 else I["disp%d" % s]) for s in c.scales}
         target_pyr = {s: (I["target"] if s == 0 else I["target%d" % s]) for s in c.scales}
         poses = [{"axisangle": I["axisangle%d" % i], "translation": I["translation%d" % i], "invert": i == 0}
-                 for i in range(c.S)]
+                 for i in c.pose_sources]
+        if c.stereo:
+            poses.append({"T": I["stereo_T"]})
         noises = {s: I["noise%d" % s] for s in c.scales}
         out = P.photometric_losses(disps, target_pyr, sources, I["K"], I["inv_K"], poses, noises, height=c.H,
                                    width=c.W, scales=c.scales, disparity_smoothness=c.disparity_smoothness,
+                                   rescale_translation=not c.stereo, disable_automasking=not c.automask,
                                    identity=identity, packed_sources=packed)
+        self.argmins = {s: out[("argmin", s)] for s in c.scales}       # [B,H,W] u8 per scale (what Trainer.log reads)
         return out["loss"], pred
 
-    def _start_grad_exchange(self, grads):
-        """fork: the exchange runs on the communication stream after everything enqueued so far; returns the join"""
+    def _start_grad_exchange(self, slot):
+        """fork: the exchange of the slot's flat gradient bucket runs on the communication stream after everything
+        enqueued so far; returns the join"""
         main = torch.cuda.current_stream()
         if self.comm_stream is None:
             self.comm_stream = torch.cuda.Stream()
         comm = self.comm_stream
         comm.wait_stream(main)
         with torch.cuda.stream(comm):
-            self.grad_exchange(grads)
+            self.grad_exchange(self.grad_flat[slot])
         return lambda: torch.cuda.current_stream().wait_stream(comm)
 
     def _zero_grads(self, slot=0):
-        for p in self.parameters():
-            p.grad = None
         for k in self.grad_inputs:
             self.slots[slot][k].grad = None
+
+    def _point_grads(self, slot):
+        for p, gv in zip(self.param_list, self.grad_views[slot]):
+            p.grad = gv
 
     def step_eager(self, slot=0):
         self._zero_grads(slot)
         loss, pred = self.forward_loss(slot)
-        loss.backward()
+        torch.autograd.backward(loss, grad_tensors=self._one)     # (a static one: no fill kernel per step)
+        self._point_grads(slot)
         self.loss, self.pred = loss.detach(), pred.detach()
         self.losses[slot] = self.loss
         return self.loss
 
     # ------------------------------------------------------------------ graph
     def capture(self, warmup=3, slot=0):
-        """Capture forward + backward on input set `slot` into one CUDA graph (parameter and input gradients are the
-        tensors autograd creates during capture: static addresses in the graph's pool)."""
+        """Capture forward + backward on input set `slot` into one CUDA graph (parameter gradients land in the slot's
+        flat bucket; input gradients are the tensors autograd creates during capture: static addresses in the pool)."""
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -238,16 +274,17 @@ class HotPath(torch.nn.Module):
         for k in self.grad_inputs:
             self.slots[slot][k].grad = None
         g = torch.cuda.CUDAGraph()
-        for p in self.parameters():
-            p.grad = None
         with torch.cuda.graph(g):
             loss, pred = self.forward_loss(slot)
-            loss.backward()
+            torch.autograd.backward(loss, grad_tensors=self._one)
             self.losses[slot] = loss.detach()
             self.pred = pred.detach()
-        self.slot_grads[slot] = [p.grad for p in self.parameters()]
         self.graphs[slot] = g
         return g
+
+    def drop_graphs(self):
+        """Release the captured graphs (before tearing down a process group whose collectives they hold)."""
+        self.graphs = [None] * len(self.graphs)
 
     def step(self, slot=0):
         """Run one step on whatever is in input set `slot`; returns the (device) loss scalar."""
@@ -255,11 +292,10 @@ class HotPath(torch.nn.Module):
             if self.graphs[slot] is None:
                 self.capture(slot=slot)
             self.graphs[slot].replay()
-            for p, gr in zip(self.parameters(), self.slot_grads[slot]):
-                p.grad = gr
+            self._point_grads(slot)
             self.loss = self.losses[slot]
             return self.loss
         return self.step_eager(slot)
 
     def param_grads(self):
-        return [p.grad for p in self.parameters() if p.grad is not None]
+        return [p.grad for p in self.param_list if p.grad is not None]

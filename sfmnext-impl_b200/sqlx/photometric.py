@@ -402,6 +402,7 @@ class _MultiScaleLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, meta, *tensors):
+        ctx.set_materialize_grads(False)       # no zero "gradients" for the per-scale losses / arg-min outputs
         (target, colors, K, inv_K, identity, noises, sources, pose_spec, cfg, smooth_weights, rescale) = meta
         ns = len(colors)
         disps = [_f32c(t) for t in tensors[:ns]]
@@ -456,6 +457,8 @@ class _MultiScaleLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, _g_per_scale, *_g_argmins):
         desc, pose_spec, mask, S, ns, pose_shapes, disp_shapes = ctx.state
+        if g_loss is None:
+            return (None,) * (1 + ns + len(pose_shapes))
         tgt, Kc, iKc, saved, *rest = ctx.saved_tensors
         disps, cols, argmins = rest[:ns], rest[ns:2 * ns], rest[2 * ns:3 * ns]
         srcs, keep = rest[3 * ns:3 * ns + S], rest[3 * ns + S:]
@@ -605,6 +608,16 @@ class _LazyMask:
 
     def cpu(self):
         return self.float().cpu()
+
+    @property
+    def shape(self):
+        return self.argmin.shape
+
+    def __len__(self):
+        return self.argmin.shape[0]
+
+    def __getitem__(self, idx):             # Trainer.log indexes outputs["identity_selection/s"][j] (trainer.py:620-623)
+        return (self.argmin[idx] >= self.n_ident).float()
 
     def __getattr__(self, name):            # behave like the float tensor for anything else
         return getattr(self.float(), name)

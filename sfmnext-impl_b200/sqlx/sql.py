@@ -85,9 +85,29 @@ def use_mix(E, Q, D, n):
     """True when the tensor-core kernels take the shape: the decoder tail then runs as
     logits = (Wp K) x + b (regression contracts over E = 32, no Wp tiles on chip; csrc/sql_tc.cu)."""
     L = lib()
-    on = L.sqlx_sql_set_tensor_cores(1)
-    L.sqlx_sql_set_tensor_cores(on)
-    return bool(on) and bool(L.sqlx_sql_tc_supported(E, Q, D, n))
+    return bool(L.sqlx_sql_get_tensor_cores()) and bool(L.sqlx_sql_tc_supported(E, Q, D, n))
+
+
+def mix_weights(Wp, queries):
+    """Mx [B,D,E] = Wp [D,Q] . queries [B,Q,E]: the 1x1 conv weight folded into the queries (one small kernel)."""
+    B, Q, E = queries.shape
+    D = Wp.shape[0]
+    Mx = torch.empty(B, D, E, device=queries.device, dtype=torch.float32)
+    check(lib().sqlx_sql_mix_weights(ptr(Wp), ptr(queries), B, Q, D, E, ptr(Mx), stream_ptr()), "sqlx_sql_mix_weights")
+    return Mx
+
+
+def mix_weights_bwd(d_M, queries, Wp, d_queries=None, d_Wp=None, want_d_Wp=True):
+    """d_Wp [D,Q] = sum_b d_M[b] queries[b]^T (written into `d_Wp` when given) and / or d_queries += Wp^T d_M, in one
+    launch; d_queries=None or want_d_Wp=False skips that half."""
+    B, Q, E = queries.shape
+    D = Wp.shape[0]
+    if want_d_Wp and d_Wp is None:
+        d_Wp = torch.empty(D, Q, device=queries.device, dtype=torch.float32)
+    check(lib().sqlx_sql_mix_weights_bwd(ptr(d_M), ptr(queries), ptr(Wp), B, Q, D, E, 1,
+                                         ptr(d_Wp) if want_d_Wp else None, ptr(d_queries), stream_ptr()),
+          "sqlx_sql_mix_weights_bwd")
+    return d_Wp
 
 
 def _mix_workspace(B, Q, D, n, device):
@@ -104,12 +124,13 @@ def pred_mix_fwd(x, Mx, bp, centers):
     return pred
 
 
-def bwd_pred_mix(x, Mx, bp, centers, g_pred):
+def bwd_pred_mix(x, Mx, bp, centers, g_pred, d_bp=None):
     B, E, h, w = x.shape
     D = Mx.shape[1]
     dev = x.device
     d_M = torch.empty_like(Mx)
-    d_bp = torch.empty(D, device=dev, dtype=torch.float32)
+    if d_bp is None:
+        d_bp = torch.empty(D, device=dev, dtype=torch.float32)
     d_centers = torch.empty(B, D, device=dev, dtype=torch.float32)
     d_x = torch.empty_like(x)
     ws, nbytes = _mix_workspace(B, 1, D, h * w, dev)
@@ -178,8 +199,9 @@ class _BinsHead(torch.autograd.Function):
     arithmetic, on the weight-streaming kernels of csrc/bins_head.cu (4 launches forward, 4 backward)."""
 
     @staticmethod
-    def forward(ctx, s, W1, b1, W2, b2, W3, b3, min_val, max_val):
+    def forward(ctx, s, W1, b1, W2, b2, W3, b3, min_val, max_val, grad_buffers=None):
         L = lib()
+        ctx.grad_buffers = grad_buffers
         sc = _f32c(s)
         Ws = [_f32c(W1), _f32c(W2), _f32c(W3)]
         bs = [_f32c(b1), _f32c(b2), _f32c(b3)]
@@ -212,33 +234,40 @@ class _BinsHead(torch.autograd.Function):
         acts, Ws = [s, h1, h2, raw], [W1, W2, W3]
         dy = d_raw
         dWs, dbs = [None] * 3, [None] * 3
+        gb = ctx.grad_buffers          # caller-owned [dW1, db1, dW2, db2, dW3, db3] (views of a flat gradient bucket)
         for i in (2, 1, 0):
             N, K = Ws[i].shape
             dz = torch.empty(B, N, device=g.device, dtype=torch.float32)
-            dWs[i] = torch.empty_like(Ws[i])
-            dbs[i] = torch.empty(N, device=g.device, dtype=torch.float32)
+            dWs[i] = gb[2 * i] if gb is not None else torch.empty_like(Ws[i])
+            dbs[i] = gb[2 * i + 1] if gb is not None else torch.empty(N, device=g.device, dtype=torch.float32)
             need_dx = i > 0 or ctx.needs_input_grad[0]
             dx = torch.empty(B, K, device=g.device, dtype=torch.float32) if need_dx else None
             check(L.sqlx_head_linear_bwd(ptr(Ws[i]), ptr(acts[i]), ptr(acts[i + 1]), ptr(dy), B, N, K, int(i < 2), ptr(dz),
                                          ptr(dWs[i]), ptr(dbs[i]), ptr(dx), stream_ptr()), "sqlx_head_linear_bwd")
             dy = dx
-        return dy, dWs[0], dbs[0], dWs[1], dbs[1], dWs[2], dbs[2], None, None
+        if gb is not None:              # the gradients live in the caller's buffers: nothing for autograd to accumulate
+            return dy, None, None, None, None, None, None, None, None, None
+        return dy, dWs[0], dbs[0], dWs[1], dbs[1], dWs[2], dbs[2], None, None, None
 
 
-def bins_head(summary_flat, regressor, min_val, max_val, norm="linear"):
+def bins_head(summary_flat, regressor, min_val, max_val, norm="linear", grad_buffers=None):
     """bin centres [B,D] = centres(bins_regressor(summary)) (depth_decoder_QTR.py:48-66).  `regressor` is the
     nn.Sequential(Linear, LeakyReLU, Linear, LeakyReLU, Linear) of the reference decoder.  The weight-streaming
     kernels take batch <= 16, norm == 'linear', in_features % 4 == 0 and dim_out <= 256 (every reference config);
-    other cases run the same arithmetic through cuBLAS + elementwise PyTorch ops on the GPU."""
+    other cases run the same arithmetic through cuBLAS + elementwise PyTorch ops on the GPU.
+    grad_buffers: optional [dW1, db1, dW2, db2, dW3, db3] the backward WRITES the parameter gradients into (e.g. views
+    of one flat all-reduce bucket) instead of handing them to autograd."""
     lins = [m for m in regressor if isinstance(m, torch.nn.Linear)]
     acts = [m for m in regressor if isinstance(m, torch.nn.LeakyReLU)]
     ok = (norm == "linear" and len(lins) == 3 and len(acts) == 2 and all(a.negative_slope == 0.01 for a in acts) and
           summary_flat.is_cuda and summary_flat.shape[0] <= 16 and lins[2].out_features <= 256 and
           all(l.in_features % 4 == 0 and l.bias is not None for l in lins))
     if not ok:
+        if grad_buffers is not None:
+            raise ValueError("grad_buffers needs the bins-head kernels (batch <= 16, norm='linear', dim_out <= 256)")
         return bin_centers(regressor(summary_flat), min_val, max_val, norm)
     return _BinsHead.apply(summary_flat, lins[0].weight, lins[0].bias, lins[1].weight, lins[1].bias, lins[2].weight,
-                           lins[2].bias, min_val, max_val)
+                           lins[2].bias, min_val, max_val, grad_buffers)
 
 
 class _SqlTail(torch.autograd.Function):
@@ -250,7 +279,9 @@ class _SqlTail(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, queries, Wp, bp, centers_fn, n_params, on_param_grads, *params):
+    def forward(ctx, x, queries, Wp, bp, centers_fn, n_params, on_param_grads, head_grad_out, *params):
+        ctx.set_materialize_grads(False)
+        ctx.head_grad_out = head_grad_out
         xc, qc, Wc, bc = _f32c(x), _f32c(queries), _f32c(Wp), _f32c(bp)
         summary, row_max, row_sum, _ = summary_fwd(xc, qc)
         with torch.enable_grad():
@@ -260,7 +291,7 @@ class _SqlTail(torch.autograd.Function):
         B, E, h, w = xc.shape
         ctx.mix = use_mix(E, qc.shape[1], Wc.shape[0], h * w)
         if ctx.mix:
-            Mx = torch.matmul(Wc, qc)                    # [B,D,E] = Wp . K   (tiny; cuBLAS fp32)
+            Mx = mix_weights(Wc, qc)                     # [B,D,E] = Wp . K
             pred = pred_mix_fwd(xc, Mx, bc, cc)
             ctx.save_for_backward(xc, qc, Wc, bc, cc, summary, row_max, row_sum, Mx)
         else:
@@ -274,45 +305,61 @@ class _SqlTail(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_pred):
         s_leaf, centers = ctx.graph
+        none = (None,) * (8 + len(ctx.params))
+        if g_pred is None:
+            return none
         g = _f32c(g_pred)
+        # head_grad_out = (d_Wp, d_bp) buffers: the 1x1 conv gradients are WRITTEN there (views of the caller's flat
+        # all-reduce bucket, like bins_head(grad_buffers=...)) and autograd gets nothing to accumulate for Wp / bp
+        out_Wp, out_bp = ctx.head_grad_out if ctx.head_grad_out is not None else (None, None)
         need = [p for p in ctx.params if p.requires_grad]
         if ctx.mix:
             xc, qc, Wc, bc, cc, summary, row_max, row_sum, Mx = ctx.saved_tensors
-            d_M, d_bp, d_centers, d_x = bwd_pred_mix(xc, Mx, bc, cc, g)
-            d_Wp = torch.einsum("bde,bqe->dq", d_M, qc)
-            grads = torch.autograd.grad(centers, [s_leaf] + need, d_centers, allow_unused=True)
-            d_summary = grads[0] if grads[0] is not None else torch.zeros_like(summary)
-            join = None
-            if ctx.on_param_grads is not None:
-                # every parameter gradient of the tail exists now; the summary-path backward (the longest kernel of the
-                # tail) is still to run: the caller's gradient exchange overlaps it
-                join = ctx.on_param_grads([d_Wp, d_bp] + [g_ for g_ in grads[1:] if g_ is not None])
-            d_x, d_q = bwd_summary(xc, qc, summary, row_max, row_sum, _f32c(d_summary), d_x=d_x)
-            d_q = d_q + torch.matmul(Wc.t(), d_M)        # regression-path part of d_K:  Wp^T dM
-            if join is not None:
-                join()
+            d_M, d_bp, d_centers, d_x = bwd_pred_mix(xc, Mx, bc, cc, g, d_bp=out_bp)
         else:
             xc, qc, Wc, bc, cc, summary, row_max, row_sum = ctx.saved_tensors
             d_centers, d_Wp, d_bp = bwd_reduce(xc, qc, Wc, bc, cc, g)
-            grads = torch.autograd.grad(centers, [s_leaf] + need, d_centers, allow_unused=True)
-            d_summary = grads[0]
-            if d_summary is None:
-                d_summary = torch.zeros_like(summary)
+            if out_Wp is not None:
+                out_Wp.copy_(d_Wp.view_as(out_Wp)); out_bp.copy_(d_bp)
+                d_Wp, d_bp = out_Wp, out_bp
+        grads = torch.autograd.grad(centers, [s_leaf] + need, d_centers, allow_unused=True)
+        d_summary = grads[0] if grads[0] is not None else torch.zeros_like(summary)
+        early = ctx.mix and ctx.on_param_grads is not None
+        if early:     # d_Wp = sum_b dM K^T now (the exchange needs it); the d_K half runs after the summary-path kernel
+            d_Wp = mix_weights_bwd(d_M, qc, Wc, None, d_Wp=out_Wp)
+        join = None
+        if ctx.on_param_grads is not None:
+            # every parameter gradient of the tail exists now; the summary-path backward (the longest kernel of the
+            # tail) is still to run: the caller's gradient exchange overlaps it
+            join = ctx.on_param_grads([d_Wp, d_bp] + [g_ for g_ in grads[1:] if g_ is not None])
+        if ctx.mix:
+            d_x, d_q = bwd_summary(xc, qc, summary, row_max, row_sum, _f32c(d_summary), d_x=d_x)
+            if early:
+                mix_weights_bwd(d_M, qc, Wc, d_q, want_d_Wp=False)         # d_q += Wp^T dM
+            else:
+                d_Wp = mix_weights_bwd(d_M, qc, Wc, d_q, d_Wp=out_Wp)      # d_Wp and d_q += Wp^T dM in one launch
+        else:
             d_x, d_q = bwd_dx(xc, qc, Wc, bc, cc, g, summary, row_max, row_sum, _f32c(d_summary))
+        if join is not None:
+            join()
         it = iter(grads[1:])
         d_params = tuple((next(it) if p.requires_grad else None) for p in ctx.params)
         ctx.graph = None
-        return (d_x, d_q, d_Wp.view_as(Wc), d_bp, None, None, None) + d_params
+        if out_Wp is not None:
+            return (d_x, d_q, None, None, None, None, None, None) + d_params
+        return (d_x, d_q, d_Wp.view_as(Wc), d_bp, None, None, None, None) + d_params
 
 
-def sql_tail(x, queries, Wp, bp, centers_fn, params=(), on_param_grads=None):
+def sql_tail(x, queries, Wp, bp, centers_fn, params=(), on_param_grads=None, head_grad_out=None):
     """pred [B,1,h,w] = sum_d softmax_d(Wp (x^T K) + bp) * centers_fn(summary(x, K)).
 
     on_param_grads(list of gradient tensors) -> join callable or None: called in the backward as soon as the gradients
     of Wp, bp and `params` exist (before the summary-path kernel runs), e.g. to start their all-reduce on a side
-    stream; the returned callable is invoked once the remaining backward kernels are enqueued (tensor-core path)."""
+    stream; the returned callable is invoked once the remaining backward kernels are enqueued.
+    head_grad_out = (d_Wp [D,Q], d_bp [D]) buffers: the gradients of Wp / bp are written there instead of being
+    returned to autograd (views of a flat gradient bucket: no pack / unpack around the all-reduce)."""
     params = tuple(params)
-    return _SqlTail.apply(x, queries, Wp, bp, centers_fn, len(params), on_param_grads, *params)
+    return _SqlTail.apply(x, queries, Wp, bp, centers_fn, len(params), on_param_grads, head_grad_out, *params)
 
 
 class Depth_Decoder_QueryTr(torch.nn.Module):

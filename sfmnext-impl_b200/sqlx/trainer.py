@@ -53,7 +53,10 @@ class FusedLossMixin:
             noises=self.sqlx_noises, height=opt.height, width=opt.width, scales=tuple(opt.scales),
             disparity_smoothness=opt.disparity_smoothness, rescale_translation=posecnn_rescale,
             no_ssim=opt.no_ssim, avg_reprojection=opt.avg_reprojection,
-            disable_automasking=opt.disable_automasking, materialize=bool(self.sqlx_materialize))
+            disable_automasking=opt.disable_automasking,
+            # Trainer.val() (trainer.py:363-384, under no_grad) always logs and reads outputs[("depth",0,0)] in
+            # compute_depth_losses (:557): materialise there whatever the per-step switch says
+            materialize=bool(self.sqlx_materialize) or not torch.is_grad_enabled())
         for s in opt.scales:
             if ("depth", 0, s) in out:
                 outputs[("depth", 0, s)] = out[("depth", 0, s)]

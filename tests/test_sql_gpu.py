@@ -275,3 +275,28 @@ def test_param_grad_hook_overlap_semantics():
     assert _rel(got[0], ref[0]) < 1e-6 and _rel(got[1], ref[1]) < 1e-6
     for a, b in zip(got[2:], ref[2:]):
         assert _rel(a, 0.5 * b) < 1e-6
+
+
+@pytest.mark.parametrize("B,Q,D,E", [(12, 64, 64, 32), (8, 128, 128, 32), (3, 12, 16, 32), (2, 120, 128, 32)])
+def test_mix_weight_glue_kernels(B, Q, D, E):
+    """csrc/sql_glue.cu: M = Wp K, dWp = sum_b dM K^T, dK += Wp^T dM against float64 matmuls (these replaced three cuBLAS
+    calls inside the step); both halves of the backward launch, together and separately."""
+    from sqlx import sql as S
+    g = torch.Generator().manual_seed(B + Q)
+    Wp = torch.randn(D, Q, generator=g).cuda()
+    K = torch.randn(B, Q, E, generator=g).cuda()
+    dM = torch.randn(B, D, E, generator=g).cuda()
+    dK0 = torch.randn(B, Q, E, generator=g).cuda()
+    M = S.mix_weights(Wp, K)
+    assert _rel(M.double(), torch.matmul(Wp.double(), K.double())) < 1e-6
+    dWp_ref = torch.einsum("bde,bqe->dq", dM.double(), K.double())
+    dK_ref = dK0.double() + torch.matmul(Wp.double().t(), dM.double())
+    dK = dK0.clone()
+    dWp = S.mix_weights_bwd(dM, K, Wp, dK)
+    assert _rel(dWp.double(), dWp_ref) < 1e-6 and _rel(dK.double(), dK_ref) < 1e-6
+    buf = torch.full((D, Q), float("nan"), device="cuda")
+    S.mix_weights_bwd(dM, K, Wp, None, d_Wp=buf)                  # weight half only, into a caller-owned buffer
+    assert torch.equal(buf, dWp)
+    dK2 = dK0.clone()
+    S.mix_weights_bwd(dM, K, Wp, dK2, want_d_Wp=False)            # query half only
+    assert torch.equal(dK2, dK)

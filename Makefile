@@ -17,7 +17,15 @@ $(LIB): $(OBJ)
 	@mkdir -p $(PKG)/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart -lcuda
 
-clean:
-	rm -rf $(PKG)/build $(PKG)/lib
+# A/B variants for kernel tuning (never loaded by the product unless SQLX_LIB_PATH points at one):
+#   make variant NAME=nw3 DEFS="-DSQLX_FWD_NW=3"   ->  $(PKG)/lib/libsqlx_nw3.so      (tools/ab.py times them side by side)
+variant:
+	@mkdir -p $(PKG)/build_$(NAME) $(PKG)/lib
+	for f in $(SRC); do o=$(PKG)/build_$(NAME)/$$(basename $$f .cu).o; \
+	  $(NVCC) $(NVCCFLAGS) $(DEFS) -c $$f -o $$o 2> $$o.log || (cat $$o.log; exit 1); done
+	$(NVCC) $(ARCH) -shared -o $(PKG)/lib/libsqlx_$(NAME).so $(PKG)/build_$(NAME)/*.o -lcudart -lcuda
 
-.PHONY: all clean
+clean:
+	rm -rf $(PKG)/build $(PKG)/build_* $(PKG)/lib
+
+.PHONY: all clean variant

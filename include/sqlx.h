@@ -340,11 +340,23 @@ size_t sqlx_sql_mix_workspace_bytes(int B, int Q, int D, int n);
 int sqlx_sql_mix_weights(const float* Wp, const float* queries, int B, int Q, int D, int E, float* Mx, void* stream);
 int sqlx_sql_mix_weights_bwd(const float* d_Mx, const float* queries, const float* Wp, int B, int Q, int D, int E,
                              int accumulate_d_queries, float* d_Wp, float* d_queries, void* stream);
+/* stats [2][B][n] (written by the forward, read by the backward): the per-pixel softmax statistics of the base-2 logits
+ * t = (M x + b) log2(e) -- plane 0: max_d t, plane 1: 1 / sum_d 2^(t - max).  With them the backward needs no max / sum pass. */
 int sqlx_sql_pred_mix_fwd(const float* x, const float* Mx, const float* bp, const float* centers, int B, int E, int D,
-                          int n, float* pred, void* stream);
+                          int n, float* pred, float* stats, void* stream);
 int sqlx_sql_bwd_pred_mix(const float* x, const float* Mx, const float* bp, const float* centers, const float* g_pred,
-                          int B, int E, int D, int n, float* d_M, float* d_bp, float* d_centers, float* d_x,
-                          void* workspace, size_t workspace_bytes, void* stream);
+                          const float* pred, const float* stats, int B, int E, int D, int n, float* d_M, float* d_bp,
+                          float* d_centers, float* d_x, void* workspace, size_t workspace_bytes, void* stream);
+/* round-1 generation of the two entry points above (one warpgroup, serial phases; no statistics): kept for one round as the
+ * A/B and cross-check of the warp-specialised kernels */
+int sqlx_sql_pred_mix_fwd_v1(const float* x, const float* Mx, const float* bp, const float* centers, int B, int E, int D,
+                             int n, float* pred, void* stream);
+int sqlx_sql_bwd_summary_v1(const float* x, const float* queries, const float* summary, const float* row_max,
+                            const float* row_sum, const float* d_summary, int B, int E, int Q, int n, int accumulate,
+                            float* d_x, float* d_queries, void* workspace, size_t workspace_bytes, void* stream);
+int sqlx_sql_bwd_pred_mix_v1(const float* x, const float* Mx, const float* bp, const float* centers, const float* g_pred,
+                             int B, int E, int D, int n, float* d_M, float* d_bp, float* d_centers, float* d_x,
+                             void* workspace, size_t workspace_bytes, void* stream);
 int sqlx_sql_bwd_summary(const float* x, const float* queries, const float* summary, const float* row_max,
                          const float* row_sum, const float* d_summary, int B, int E, int Q, int n, int accumulate,
                          float* d_x, float* d_queries, void* workspace, size_t workspace_bytes, void* stream);

@@ -315,38 +315,42 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const __grid_const
   __syncthreads();
 
   {   // upsampled depth and (first scale only) the three target planes on the R halo, two elements per trip
+    // (128-bit row-segment loads on interior tiles were measured SLOWER, 420 -> 440 us: the kernel sits at the 128-register
+    // cap of 2 CTAs/SM and any extra live state spills, profiles/r02d_ab.log)
     const float* lr_map = p.depth_lr + (size_t)b * p.d.h * p.d.w;
     const float* dup = MS ? p.ms_depth_up[sc] : p.depth_up;
     const float* up_map = dup ? dup + (size_t)b * plane : nullptr;
     const float* tgb = p.target + (size_t)b * 3 * plane;
-    float dv[2][4], tv[2][3], wy[2], wx[2];
-    for_region2<C::PH, C::PW, NT>(
-        [&](int j, int lr, int lc, bool live) {
-          const int4 rt = rowt[lr], ct = colt[lc];
-          wy[j] = __int_as_float(rt.z); wx[j] = __int_as_float(ct.z);
-          if (live) {
-            if (up_map) {
-              dv[j][0] = __ldg(up_map + rt.w * W + ct.w);
-            } else {
-              const float* r0 = lr_map + rt.x;
-              const float* r1 = lr_map + rt.y;
-              dv[j][0] = __ldg(r0 + ct.x); dv[j][1] = __ldg(r0 + ct.y);
-              dv[j][2] = __ldg(r1 + ct.x); dv[j][3] = __ldg(r1 + ct.y);
+    {
+      float dv[2][4], tv[2][3], wy[2], wx[2];
+      for_region2<C::PH, C::PW, NT>(
+          [&](int j, int lr, int lc, bool live) {
+            const int4 rt = rowt[lr], ct = colt[lc];
+            wy[j] = __int_as_float(rt.z); wx[j] = __int_as_float(ct.z);
+            if (live) {
+              if (up_map) {
+                dv[j][0] = __ldg(up_map + rt.w * W + ct.w);
+              } else {
+                const float* r0 = lr_map + rt.x;
+                const float* r1 = lr_map + rt.y;
+                dv[j][0] = __ldg(r0 + ct.x); dv[j][1] = __ldg(r0 + ct.y);
+                dv[j][2] = __ldg(r1 + ct.x); dv[j][3] = __ldg(r1 + ct.y);
+              }
+              if (first) {
+                const float* tp = tgb + (size_t)(rt.w * W + ct.w);
+                tv[j][0] = __ldg(tp); tv[j][1] = __ldg(tp + plane); tv[j][2] = __ldg(tp + 2 * plane);
+              }
             }
-            if (first) {
-              const float* tp = tgb + (size_t)(rt.w * W + ct.w);
-              tv[j][0] = __ldg(tp); tv[j][1] = __ldg(tp + plane); tv[j][2] = __ldg(tp + 2 * plane);
-            }
-          }
-        },
-        [&](int j, int lr, int lc) {
-          const int o = lr * C::LD + lc;
-          // same expression as upsample_at (common.cuh): bit-identical depth in every kernel
-          dpl[o] = up_map ? dv[j][0]
-                          : (1.f - wy[j]) * ((1.f - wx[j]) * dv[j][0] + wx[j] * dv[j][1]) +
-                                wy[j] * ((1.f - wx[j]) * dv[j][2] + wx[j] * dv[j][3]);
-          if (first) { tg[o] = tv[j][0]; tg[C::PLANE + o] = tv[j][1]; tg[2 * C::PLANE + o] = tv[j][2]; }
-        });
+          },
+          [&](int j, int lr, int lc) {
+            const int o = lr * C::LD + lc;
+            // same expression as upsample_at (common.cuh): bit-identical depth in every kernel
+            dpl[o] = up_map ? dv[j][0]
+                            : (1.f - wy[j]) * ((1.f - wx[j]) * dv[j][0] + wx[j] * dv[j][1]) +
+                                  wy[j] * ((1.f - wx[j]) * dv[j][2] + wx[j] * dv[j][3]);
+            if (first) { tg[o] = tv[j][0]; tg[C::PLANE + o] = tv[j][1]; tg[2 * C::PLANE + o] = tv[j][2]; }
+          });
+    }
   }
 
   // identity (+noise) candidates: independent global loads issued before the staging barrier, consumed after it
@@ -487,12 +491,13 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const __grid_const
       }
     }
 
-    float ssim_acc[PPT], l1_acc[PPT];
+    float ssim_acc[PPT], l1_acc[PPT], l1w[PPT];
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
       const int o = (prow0 + k + R) * C::LD + pcol + R;
       l1_acc[k] = fabsf(tg[o] - wp[o]) + fabsf(tg[C::PLANE + o] - wp[C::PLANE + o]) +
                   fabsf(tg[2 * C::PLANE + o] - wp[2 * C::PLANE + o]);
+      l1w[k] = p.d.w_l1 * (l1_acc[k] * (1.f / 3.f));
       ssim_acc[k] = 0.f;
     }
     if (R > 0) {
@@ -529,7 +534,13 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const __grid_const
           const float q = n1 * n2 * inv_d;
           const float val = 0.5f - 0.5f * q;
           ssim_acc[k] += fminf(fmaxf(val, 0.f), 1.f);
-          if (cbase && col_in && v0 + prow0 + k < H) {
+          // Lower bound of this source's loss from the channels seen so far (the SSIM terms still to come are >= 0, and
+          // the float sums / products below are monotone): once it reaches the running minimum the source cannot win this
+          // pixel any more, and its coefficients -- which the backward reads only where the arg-min selects the source --
+          // are neither computed nor stored.  (--avg_reprojection averages the sources: every coefficient is needed.)
+          float lb = fmaf(p.d.w_ssim, ssim_acc[k] * (1.f / 3.f), l1w[k]);
+          if (OCC) lb *= occ_w[k];
+          if (cbase && col_in && v0 + prow0 + k < H && (avg || lb < best[k])) {
             // torch.clamp backward: zero outside [0,1] (NaN -> 0); branch-free
             const bool ok = val >= 0.f && val <= 1.f;
             const float dS_dn = -0.5f * inv_d, dS_dd = 0.5f * q * inv_d;
@@ -547,7 +558,7 @@ __global__ void __launch_bounds__(NT, MINB) photo_fwd3_kernel(const __grid_const
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
       float rho;
-      if (R > 0) rho = p.d.w_ssim * (ssim_acc[k] * (1.f / 3.f)) + p.d.w_l1 * (l1_acc[k] * (1.f / 3.f));
+      if (R > 0) rho = fmaf(p.d.w_ssim, ssim_acc[k] * (1.f / 3.f), l1w[k]);   // (same expression as the pruning bound)
       else rho = l1_acc[k] * (1.f / 3.f);
       if (OCC) rho *= occ_w[k];
       if (avg) {

@@ -709,6 +709,16 @@ int tc_bwd_sum(const float* x, const float* queries, const float* summary, const
                const float* d_summary, int B, int Q, int n, int accumulate, float* d_x, float* part_dK, int chunks, int tpc,
                cudaStream_t st);
 void tc_bwd_plan(int B, int n, int* chunks, int* tiles_per_chunk);
+// warp-specialised generation (sql_ws.cu)
+void ws_plan(int B, int n, int* chunks, int* tiles_per_chunk);
+int ws_pred_fwd(const float* x, const float* Mx, const float* bp, const float* centers, int B, int D, int n, float* pred,
+                float* stat_m, float* stat_inv, cudaStream_t st);
+int ws_bwd_sum(const float* x, const float* queries, const float* summary, const float* row_max, const float* row_sum,
+               const float* d_summary, int B, int Q, int n, int accumulate, float* d_x, float* part_dK, int chunks, int tpc,
+               cudaStream_t st);
+int ws_bwd_pred(const float* x, const float* Mx, const float* bp, const float* centers, const float* g_pred,
+                const float* pred, const float* stat_m, const float* stat_inv, int B, int D, int n, float* d_x,
+                float* part_dM, float* part_db, float* part_dc, int chunks, int tpc, cudaStream_t st);
 }
 extern "C" int sqlx_sql_tc_supported(int E, int Q, int D, int n);
 extern "C" int sqlx_sql_set_tensor_cores(int on);
@@ -934,16 +944,50 @@ extern "C" size_t sqlx_sql_mix_workspace_bytes(int B, int Q, int D, int n) {
 }
 
 extern "C" int sqlx_sql_pred_mix_fwd(const float* x, const float* Mx, const float* bp, const float* centers, int B, int E,
-                                     int D, int n, float* pred, void* stream) {
+                                     int D, int n, float* pred, float* stats, void* stream) {
+  SQLX_REQUIRE(x && Mx && bp && centers && pred && stats, "NULL pointer argument");
+  SQLX_REQUIRE(B > 0 && B <= 65535 && n > 0, "bad shape B=%d n=%d", B, n);
+  SQLX_REQUIRE(sqlx_sql_tc_supported(E, 1, D, n), "shape E=%d D=%d n=%d is not supported by the tensor-core path", E, D, n);
+  return ws_pred_fwd(x, Mx, bp, centers, B, D, n, pred, stats, stats + (size_t)B * n, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sqlx_sql_bwd_pred_mix(const float* x, const float* Mx, const float* bp, const float* centers,
+                                     const float* g_pred, const float* pred, const float* stats, int B, int E, int D, int n,
+                                     float* d_M, float* d_bp, float* d_centers, float* d_x, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  SQLX_REQUIRE(x && Mx && bp && centers && g_pred && pred && stats && d_M && d_bp && d_centers && d_x && workspace,
+               "NULL pointer argument");
+  SQLX_REQUIRE(B > 0 && B <= 65535 && n > 0, "bad shape B=%d n=%d", B, n);
+  SQLX_REQUIRE(sqlx_sql_tc_supported(E, 1, D, n), "shape E=%d D=%d n=%d is not supported by the tensor-core path", E, D, n);
+  SQLX_REQUIRE(workspace_bytes >= sqlx_sql_mix_workspace_bytes(B, 1, D, n), "workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int chunks = 0, tpc = 0;
+  ws_plan(B, n, &chunks, &tpc);
+  const int ctas = B * chunks;   // partial arrays are [ctas][...]
+  float* part_dM = reinterpret_cast<float*>(workspace);
+  float* part_db = part_dM + (size_t)ctas * D * 32;
+  float* part_dc = part_db + (size_t)ctas * D;
+  if (int e = ws_bwd_pred(x, Mx, bp, centers, g_pred, pred, stats, stats + (size_t)B * n, B, D, n, d_x, part_dM, part_db, part_dc,
+                          chunks, tpc, st))
+    return e;
+  sum_partials3_kernel<<<dim3(ceil_div(D * 32, 256), B, 3), 256, 0, st>>>(part_dM, part_dc, part_db, chunks, B, D, d_M, d_centers,
+                                                                         d_bp);
+  return check_launch("sum_partials3_kernel");
+}
+
+/* round-1 generation of the two kernels above (single warpgroup, serial phases): kept for one round as the A/B and
+ * cross-check of the warp-specialised kernels (tests/test_sql_tc_gpu.py::test_ws_kernels_match_v1) */
+extern "C" int sqlx_sql_pred_mix_fwd_v1(const float* x, const float* Mx, const float* bp, const float* centers, int B, int E,
+                                        int D, int n, float* pred, void* stream) {
   SQLX_REQUIRE(x && Mx && bp && centers && pred, "NULL pointer argument");
   SQLX_REQUIRE(B > 0 && B <= 65535 && n > 0, "bad shape B=%d n=%d", B, n);
   SQLX_REQUIRE(sqlx_sql_tc_supported(E, 1, D, n), "shape E=%d D=%d n=%d is not supported by the tensor-core path", E, D, n);
   return tc_pred_mix_fwd(x, Mx, bp, centers, B, D, n, pred, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int sqlx_sql_bwd_pred_mix(const float* x, const float* Mx, const float* bp, const float* centers,
-                                     const float* g_pred, int B, int E, int D, int n, float* d_M, float* d_bp,
-                                     float* d_centers, float* d_x, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int sqlx_sql_bwd_pred_mix_v1(const float* x, const float* Mx, const float* bp, const float* centers,
+                                        const float* g_pred, int B, int E, int D, int n, float* d_M, float* d_bp,
+                                        float* d_centers, float* d_x, void* workspace, size_t workspace_bytes, void* stream) {
   SQLX_REQUIRE(x && Mx && bp && centers && g_pred && d_M && d_bp && d_centers && d_x && workspace, "NULL pointer argument");
   SQLX_REQUIRE(B > 0 && B <= 65535 && n > 0, "bad shape B=%d n=%d", B, n);
   SQLX_REQUIRE(sqlx_sql_tc_supported(E, 1, D, n), "shape E=%d D=%d n=%d is not supported by the tensor-core path", E, D, n);
@@ -963,6 +1007,26 @@ extern "C" int sqlx_sql_bwd_pred_mix(const float* x, const float* Mx, const floa
 }
 
 extern "C" int sqlx_sql_bwd_summary(const float* x, const float* queries, const float* summary, const float* row_max,
+                                    const float* row_sum, const float* d_summary, int B, int E, int Q, int n,
+                                    int accumulate, float* d_x, float* d_queries, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  SQLX_REQUIRE(x && queries && summary && row_max && row_sum && d_summary && d_x && d_queries && workspace,
+               "NULL pointer argument");
+  SQLX_REQUIRE(B > 0 && B <= 65535 && n > 0, "bad shape B=%d n=%d", B, n);
+  SQLX_REQUIRE(sqlx_sql_tc_supported(E, Q, 0, n), "shape E=%d Q=%d n=%d is not supported by the tensor-core path", E, Q, n);
+  SQLX_REQUIRE(workspace_bytes >= sqlx_sql_mix_workspace_bytes(B, Q, 0, n), "workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int chunks = 0, tpc = 0;
+  ws_plan(B, n, &chunks, &tpc);
+  float* part_dK = reinterpret_cast<float*>(workspace);
+  if (int e = ws_bwd_sum(x, queries, summary, row_max, row_sum, d_summary, B, Q, n, accumulate, d_x, part_dK, chunks, tpc, st))
+    return e;
+  sum_partials_kernel<<<dim3(ceil_div(Q * 32, 256), B), 256, 0, st>>>(part_dK, chunks, Q * 32, d_queries);
+  return check_launch("sum_partials_kernel");
+}
+
+/* round-1 generation of sqlx_sql_bwd_summary (A/B and cross-check, see sqlx_sql_bwd_pred_mix_v1) */
+extern "C" int sqlx_sql_bwd_summary_v1(const float* x, const float* queries, const float* summary, const float* row_max,
                                     const float* row_sum, const float* d_summary, int B, int E, int Q, int n,
                                     int accumulate, float* d_x, float* d_queries, void* workspace, size_t workspace_bytes,
                                     void* stream) {

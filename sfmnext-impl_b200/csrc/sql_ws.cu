@@ -1,0 +1,997 @@
+// SQL decoder tail on tcgen05 / TMEM / TMA, warp-specialised generation (round 2).
+//
+// Round 1's kernels ran every phase of a tile in series on ONE warpgroup: TMA wait -> hi/lo split -> tcgen05.mma -> wait ->
+// per-thread softmax epilogue out of TMEM -> tcgen05.mma -> wait.  With one warp per scheduler the epilogue paid the full
+// latency of every instruction and the tensor pipe idled under it (ncu, round 1: 6 % warps active, 11-25 % tensor pipe).
+// Here a CTA is 17 warps with fixed roles:
+//
+//   warp 16 (one elected lane)   issues every TMA load and every tcgen05.mma, commits them to mbarriers; never touches data
+//   warps 0..15                  TWO GROUPS of eight epilogue warps that ping-pong: group g owns the steps s = g (mod 2) and
+//                                the TMEM accumulator Z[g], so one group's TMEM loads / exponentials / stores overlap the
+//                                other group's barrier waits and the tensor pipe works on both.  tcgen05.ld / st reach the 32
+//                                TMEM lanes 32 * (warp % 4): warps q and q + 4 of a group own the same 32 pixels and split
+//                                the COLUMNS (bins / queries) in two
+//
+// i.e. the logits accumulator is DOUBLE-BUFFERED in TMEM and every wait of one step is covered by work of the other.  A step is (128-pixel tile, 64-column half): with the per-pixel softmax statistics saved
+// by the forward kernel (max and 1 / sum of the base-2 logits, 8 bytes per pixel) the backward needs no max / sum pass and
+// the halves of a 128-bin row are independent, so one kernel body serves D, Q <= 64 (one half) and <= 128 (two halves).
+//
+// Precision is unchanged from round 1: forward contractions 3xTF32 (hi/lo split of both operands), gradient contractions
+// single-pass TF32 with fp32 accumulation.
+//
+// Reference lines: networks/layers.py:17-20, networks/depth_decoder_QTR.py:61,70 and their autograd.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+#include <math.h>
+
+namespace sqlx {
+namespace wsql {
+
+using namespace tc;
+
+constexpr int kE = 32;                 // embedding channels
+constexpr int kTile = 128;             // pixels per tile = UMMA M
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kGrpWarps = 8;            // two ping-pong groups of epilogue warps
+constexpr int kGrpThreads = kGrpWarps * 32;
+constexpr int kThreads = kEpiThreads + 32;      // + the control warp.  17 warps: one scheduler hosts five, its 16 K registers
+                                                // cap every thread at 96 registers (what __launch_bounds__ enforces)
+constexpr int kXBlock = 32 * kE * 4;   // one [32 e][32 px] block: 4 KB
+constexpr int kXTile = 4 * kXBlock;    // 16 KB
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kAccN = kE + 16;         // [x | 1 | zero padding] columns of the pixel-contraction accumulator
+
+__device__ __forceinline__ float ex2f(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// named barrier over `count` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// all epilogue threads: [rows][32] fp32 global matrix -> K-major SW128 hi (and lo) tiles with `rows_pad` rows
+__device__ __forceinline__ void stage_kmajor(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int rows, int rows_pad,
+                                             int tid, int nthreads) {
+  for (int base = tid; base < rows_pad * kE; base += 4 * nthreads) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = base + j * nthreads;
+      v[j] = (idx < rows_pad * kE && (idx >> 5) < rows) ? __ldg(src + idx) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = base + j * nthreads;
+      if (idx >= rows_pad * kE) break;
+      const uint32_t off = sw128_offset(idx >> 5, idx & 31);
+      const float h = lo ? tf32_hi(v[j]) : v[j];
+      *reinterpret_cast<float*>(hi + off) = h;
+      if (lo) *reinterpret_cast<float*>(lo + off) = v[j] - h;
+    }
+  }
+}
+
+// all epilogue threads: transposed [32 e rows][rows_pad cols] in 32-column SW128 atoms (single precision value)
+__device__ __forceinline__ void stage_transposed(uint8_t* dst, const float* __restrict__ src, int rows, int rows_pad, int tid,
+                                                 int nthreads) {
+  for (int base = tid; base < rows_pad * kE; base += 4 * nthreads) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = base + j * nthreads;
+      v[j] = (idx < rows_pad * kE && (idx >> 5) < rows) ? __ldg(src + idx) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = base + j * nthreads;
+      if (idx >= rows_pad * kE) break;
+      const int r = idx >> 5, e = idx & 31;
+      *reinterpret_cast<float*>(dst + (uint32_t)(r >> 5) * 32u * 128u + sw128_offset(e, r & 31)) = v[j];
+    }
+  }
+}
+
+// One group of epilogue warps (NT threads): x_lo = x - tf32(x) of a freshly landed tile (same swizzled layout: elementwise).
+// The landing buffer itself is the "hi" operand: the tensor core reads only the tf32 part of a 32-bit operand (the 13 low
+// mantissa bits are ignored -- measured: forward depth identical to the explicitly truncated operand to 2e-6,
+// tests/test_sql_tc_gpu.py::test_ws_kernels_match_v1), so it needs no pass of its own.  SQLX_WS_TRUNC=1 truncates it in place.
+#ifndef SQLX_WS_TRUNC
+#define SQLX_WS_TRUNC 0
+#endif
+template <int NT>
+__device__ __forceinline__ void split_x(uint8_t* x_hi, uint8_t* x_lo, int tid) {
+  float4* hi = reinterpret_cast<float4*>(x_hi);
+  float4* lo = reinterpret_cast<float4*>(x_lo);
+  constexpr int PER = kXTile / 16 / NT;
+  float4 v[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) v[i] = hi[tid + i * NT];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    float4 h, l;
+    h.x = tf32_hi(v[i].x); h.y = tf32_hi(v[i].y); h.z = tf32_hi(v[i].z); h.w = tf32_hi(v[i].w);
+    l.x = v[i].x - h.x; l.y = v[i].y - h.y; l.z = v[i].z - h.z; l.w = v[i].w - h.w;
+    if (SQLX_WS_TRUNC) hi[tid + i * NT] = h;
+    lo[tid + i * NT] = l;
+  }
+}
+
+// control lane: one 128-pixel x tile = four [32 e][32 px] boxes (pixels >= n are zero-filled by TMA)
+__device__ __forceinline__ void tma_x_tile(uint8_t* dst, uint32_t atom_stride, const CUtensorMap* map, int p0, int row0,
+                                           uint64_t* bar) {
+  mbar_arrive_expect_tx(bar, kXTile);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tma_load_2d(dst + j * atom_stride, map, p0 + 32 * j, row0, bar);
+}
+
+// control lane: D[128 px, N] = x^T B^T as 3xTF32; x tiles MN-major (hi / lo), B tiles K-major rows (hi / lo).
+// The ONE issuing thread is on the critical path of every step, so it works from descriptors built once before the tile
+// loop: a UMMA shared-memory descriptor holds (address >> 4) in its low 14 bits, and every operand of a step sits at
+// base + a compile-time byte offset inside the CTA's < 256 KB window, so "descriptor + (offset >> 4)" is one 64-bit add
+// (ncu, first warp-specialised cut: 39 % of the epilogue warps' samples sat in mbarrier waits behind a control lane that
+// rebuilt 72 descriptors -- shifts, masks, ors -- per step).
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
+__device__ __forceinline__ void mma_x_b3(uint64_t dxh, uint64_t dxl, uint64_t dbh, uint64_t dbl, uint32_t tm_d, uint32_t idesc) {
+  uint32_t acc = 0;
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint64_t xa = pass == 1 ? dxl : dxh;
+    const uint64_t bb = pass == 2 ? dbl : dbh;
+#pragma unroll
+    for (int k = 0; k < kE / 8; ++k) {
+      // A: MN-major, 8 e-rows = 1024 B per k-step; B: K-major, 8 e = 32 B per k-step inside the 128-B row
+      umma_tf32_ss(tm_d, desc_add(xa, k * 1024), desc_add(bb, k * 32), idesc, acc);
+      acc = 1;
+    }
+  }
+}
+
+// Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles: afterwards lanes 2i and 2i+1 hold the total of v[i]
+// in v[0].
+__device__ __forceinline__ void warp_reduce16(float (&v)[16]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int w = 16, n = 8; n >= 1; w >>= 1, n >>= 1) {
+    const bool upper = lane & w;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = upper ? v[i] : v[i + n];
+      const float keep = upper ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// ================================================================================================================
+// forward: pred[b,p] = sum_d softmax_d(M x + b)[d] c_d, and the per-pixel softmax statistics for the backward
+//   TMEM: Z[0] = [0, DP), Z[1] = [DP, 2 DP)
+// ================================================================================================================
+constexpr int kPredStages = 6;     // TMA ring: a slot is refilled when its tile's MMA completes, 4 tile times before it is needed
+
+template <int DP>
+struct PredSmem {
+  static constexpr size_t x_ring = 0, x_lo = kPredStages * kXTile, m_hi = x_lo + 2 * kXTile, m_lo = m_hi + DP * 128,
+                          part = m_lo + DP * 128,                   // [4 column groups][128 px] float4 (m, se, sc, -)
+                          tail = part + 4 * 128 * 16;
+  static constexpr size_t bytes = 1024 + tail + 2 * DP * 4 + 256;
+};
+
+template <int DP>
+__global__ void __launch_bounds__(kThreads, 1) sql_ws_pred_kernel(const __grid_constant__ CUtensorMap map_mn,
+                                                                  const float* __restrict__ Mx, const float* __restrict__ bp,
+                                                                  const float* __restrict__ centers, int D, int n,
+                                                                  int tiles_per_chunk, float* __restrict__ pred,
+                                                                  float* __restrict__ stat_m, float* __restrict__ stat_inv) {
+  using L = PredSmem<DP>;
+  constexpr int NST = kPredStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* x_ring = base + L::x_ring;     // [NST] landing buffers = "hi" operands after the in-place truncation
+  uint8_t* x_lo = base + L::x_lo;         // [2]
+  uint8_t* m_hi = base + L::m_hi;
+  uint8_t* m_lo = base + L::m_lo;
+  float4* part = reinterpret_cast<float4*>(base + L::part);
+  float* bias2 = reinterpret_cast<float*>(base + L::tail);
+  float* cen = bias2 + DP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cen + DP);
+  uint64_t* bar_full = bars;                 // [NST] TMA: tile landed in ring slot
+  uint64_t* bar_split = bars + NST;          // [2]   16 warps: slot truncated in place, x_lo[i] written
+  uint64_t* bar_z = bars + NST + 2;          // [2]   MMA commit: Z[i] ready (ring slot and x_lo[i] free)
+  uint64_t* bar_zfree = bars + NST + 4;      // [2]   16 warps: Z[i] read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NST + 6);
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kCols = 2 * DP;
+  const int t_begin = blockIdx.x * tiles_per_chunk;
+  const int t_end = min((n + kTile - 1) / kTile, t_begin + tiles_per_chunk);
+  const int nsteps = max(t_end - t_begin, 0);
+  if (threadIdx.x == kEpiThreads) {
+    tma_prefetch_desc(&map_mn);
+    for (int i = 0; i < NST; ++i) mbar_init(bar_full + i, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_split + i, kGrpWarps); mbar_init(bar_z + i, 1); mbar_init(bar_zfree + i, kGrpWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarps) {
+    tmem_alloc(tmem_slot, kCols);
+    tmem_relinquish();
+  }
+  __syncthreads();
+  if (threadIdx.x == kEpiThreads)
+    for (int i = 0; i < NST && i < nsteps; ++i)
+      tma_x_tile(x_ring + i * kXTile, kXBlock, &map_mn, (t_begin + i) * kTile, b * kE, bar_full + i);
+  if (warp < kEpiWarps) {
+    stage_kmajor(m_hi, m_lo, Mx + (size_t)b * D * kE, D, DP, threadIdx.x, kEpiThreads);
+    for (int d = threadIdx.x; d < DP; d += kEpiThreads) {
+      bias2[d] = d < D ? __ldg(bp + d) * kLog2e : -INFINITY;   // base-2 logits; padded bins never win the softmax
+      cen[d] = d < D ? __ldg(centers + (size_t)b * D + d) : 0.f;
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == kEpiWarps) {
+    // ---------------------------------------------------------------- control lane
+    if (lane == 0) {
+      const uint64_t dx_ring = make_desc_mn32(smem_u32(x_ring), kXBlock), dx_lo = make_desc_mn32(smem_u32(x_lo), kXBlock);
+      const uint64_t dm_hi = make_desc_sw128(smem_u32(m_hi), 16, 1024), dm_lo = make_desc_sw128(smem_u32(m_lo), 16, 1024);
+      const uint32_t idesc = make_idesc_tf32(kTile, DP, 1, 0);
+      int slot = 0;
+      for (int s = 0; s < nsteps; ++s) {
+        mbar_wait(bar_split + (s & 1), (s >> 1) & 1);                     // operands of tile s are ready
+        if (s >= 2) mbar_wait(bar_zfree + (s & 1), ((s >> 1) - 1) & 1);   // the epilogue of step s-2 has read Z[s&1]
+        tc_fence_after();
+        mma_x_b3(desc_add(dx_ring, slot * kXTile), desc_add(dx_lo, (s & 1) * kXTile), dm_hi, dm_lo, tmem + (s & 1) * DP, idesc);
+        umma_commit(bar_z + (s & 1));
+        slot = slot + 1 == NST ? 0 : slot + 1;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps: group `grp` owns tiles s = grp (mod 2)
+    const int grp = warp >> 3, wl = warp & 7, q = wl & 3, cg = wl >> 2, gtid = threadIdx.x & (kGrpThreads - 1);
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    constexpr int CW = DP / 2;                     // columns per thread and tile
+    float4* gpart = part + grp * 2 * 128;          // [2 column halves][128 px] of this group
+    auto split_tile = [&](int i) {                 // tile i (same parity as the group): lo -> x_lo[i & 1]
+      mbar_wait(bar_full + i % NST, (i / NST) & 1);
+      split_x<kGrpThreads>(x_ring + (i % NST) * kXTile, x_lo + (i & 1) * kXTile, gtid);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_split + (i & 1));
+    };
+    if (grp < nsteps) split_tile(grp);
+    for (int s = grp; s < nsteps; s += 2) {
+      const int p = (t_begin + s) * kTile + q * 32 + lane;
+      mbar_wait(bar_z + grp, (s >> 1) & 1);              // logits of tile s are in Z[grp]; its ring slot and x_lo[grp] are free
+      tc_fence_after();
+      if (gtid == 0 && s + NST < nsteps)                 // refill the slot: NST - 2 tile times before that tile is split
+        tma_x_tile(x_ring + (s % NST) * kXTile, kXBlock, &map_mn, (t_begin + s + NST) * kTile, b * kE, bar_full + s % NST);
+      if (s + 2 < nsteps) split_tile(s + 2);             // operands of this group's next tile
+      // this thread's CW bins of its pixel: online max / sum / expectation in base 2
+      float m = -INFINITY, se = 0.f, sc = 0.f;
+#pragma unroll
+      for (int c = 0; c < CW; c += 32) {
+        float v[32];
+        tmem_ld16(lane_base + grp * DP + cg * CW + c, *reinterpret_cast<float(*)[16]>(v));
+        tmem_ld16(lane_base + grp * DP + cg * CW + c + 16, *reinterpret_cast<float(*)[16]>(v + 16));
+        tmem_wait_ld();
+        const float4* b4 = reinterpret_cast<const float4*>(bias2 + cg * CW + c);
+        const float4* c4 = reinterpret_cast<const float4*>(cen + cg * CW + c);
+        float cm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bq = b4[j];
+          v[4 * j] = fmaf(v[4 * j], kLog2e, bq.x); v[4 * j + 1] = fmaf(v[4 * j + 1], kLog2e, bq.y);
+          v[4 * j + 2] = fmaf(v[4 * j + 2], kLog2e, bq.z); v[4 * j + 3] = fmaf(v[4 * j + 3], kLog2e, bq.w);
+          cm = fmaxf(cm, fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), fmaxf(v[4 * j + 2], v[4 * j + 3])));
+        }
+        if (cm > m) { const float r = ex2f(m - cm); se *= r; sc *= r; m = cm; }
+        const float ms = fmaxf(m, -1e30f);     // every bin so far padding (-inf): keep the exponents -inf, not NaN
+        float se2 = 0.f, sc2 = 0.f;            // two accumulation chains
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 cq = c4[j];
+          const float e0 = ex2f(v[4 * j] - ms), e1 = ex2f(v[4 * j + 1] - ms);
+          const float e2 = ex2f(v[4 * j + 2] - ms), e3 = ex2f(v[4 * j + 3] - ms);
+          if (j & 1) { se2 += (e0 + e1) + (e2 + e3); sc2 += fmaf(e0, cq.x, e1 * cq.y) + fmaf(e2, cq.z, e3 * cq.w); }
+          else { se += (e0 + e1) + (e2 + e3); sc += fmaf(e0, cq.x, e1 * cq.y) + fmaf(e2, cq.z, e3 * cq.w); }
+        }
+        se += se2; sc += sc2;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_zfree + grp);       // Z[grp] may be overwritten by the MMA of tile s+2
+      // combine the two column halves of the pixel (warps q and q + 4 of the group) through shared memory
+      gpart[cg * 128 + q * 32 + lane] = make_float4(m, se, sc, 0.f);
+      named_sync(1 + grp * 4 + q, 64);
+      const float4 pa = gpart[q * 32 + lane], pb = gpart[128 + q * 32 + lane];
+      const float M = fmaxf(pa.x, pb.x);
+      const float ra = ex2f(pa.x - M), rb = ex2f(pb.x - M);   // (a half whose bins are all padding has m = -inf, se = 0)
+      const float SE = fmaf(pa.y, ra, pb.y * rb), SC = fmaf(pa.z, ra, pb.z * rb);
+      named_sync(1 + grp * 4 + q, 64);                   // `gpart` is rewritten by the group's next tile
+      if (p < n) {
+        const float inv = 1.f / SE;
+        if (cg == 0) { pred[(size_t)b * n + p] = SC * inv; stat_m[(size_t)b * n + p] = M; }
+        else stat_inv[(size_t)b * n + p] = inv;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps) tmem_dealloc(tmem, kCols);
+}
+
+// ================================================================================================================
+// backward pass 1 (regression path): d_x = dz M,  dM = dz^T x,  d_bp = sum_p dz,  d_centers = sum_p pi g
+//   dz[p,d] = pi[p,d] g[p] (c_d - pred[p]),  pi = 2^(t - m2) * inv  from the saved statistics (no max / sum pass)
+//   step = (tile, 64-bin half).  TMEM: Z[0] = [0,64)  Z[1] = [64,128)  dx[0..2] = [128 + 32 i, +32)
+//                                      acc[h] = [224 + 48 h, +48)   rows = bins of half h, cols = [e | ones]
+// ================================================================================================================
+template <int DP>
+struct BwdPredSmem {
+  static constexpr int NH = DP / 64;
+  static constexpr int NST = DP > 64 ? 2 : 3;      // TMA ring of x tiles (landing buffer = "hi" operand, truncated in place)
+  static constexpr size_t x_ring = 0, x_lo = NST * kXTile, m_hi = x_lo + kXTile, m_lo = m_hi + DP * 128,
+                          mT = m_lo + DP * 128,                     // [DP/32 atoms][32 e rows][32 d]
+                          bx = mT + (DP / 32) * 32 * 128,           // [2 buffers][4 px atoms][48 rows][32 px]: x (TMA) | ones
+                          adz = bx + 2 * 4 * kAccN * 128,           // [4 px atoms][128 rows][32 px]: dz^T, rows >= 64 zero
+                          tail = adz + 4 * 128 * 128;
+  static constexpr size_t bytes = 1024 + tail + 2 * DP * 4 + 128 + kEpiWarps * 32 * 4;
+  static_assert(bytes <= 227 * 1024, "shared-memory budget");
+};
+
+template <int DP>
+__global__ void __launch_bounds__(kThreads, 1) sql_ws_bwd_pred_kernel(
+    const __grid_constant__ CUtensorMap map_mn, const __grid_constant__ CUtensorMap map_k, const float* __restrict__ Mx,
+    const float* __restrict__ bp, const float* __restrict__ centers, const float* __restrict__ g_pred,
+    const float* __restrict__ pred, const float* __restrict__ stat_m, const float* __restrict__ stat_inv, int D, int n,
+    int tiles_per_chunk, float* __restrict__ d_x, float* __restrict__ part_dM /*[cta][D][32]*/,
+    float* __restrict__ part_db /*[cta][D]*/, float* __restrict__ part_dc /*[cta][D]*/) {
+  using L = BwdPredSmem<DP>;
+  constexpr int NH = L::NH, NST = L::NST;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* x_ring = base + L::x_ring;
+  uint8_t* x_lo = base + L::x_lo;
+  uint8_t* m_hi = base + L::m_hi;
+  uint8_t* m_lo = base + L::m_lo;
+  uint8_t* mT = base + L::mT;
+  uint8_t* bx = base + L::bx;
+  uint8_t* adz = base + L::adz;
+  float* bias2 = reinterpret_cast<float*>(base + L::tail);
+  float* cen = bias2 + DP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cen + DP);
+  uint64_t* bar_full = bars;            // [NST <= 3] TMA: x tile landed in its ring slot
+  uint64_t* bar_split = bars + 3;       // 16 warps: slot truncated in place, x_lo written
+  uint64_t* bar_bx = bars + 4;          // [2] TMA: K-major x rows of bx[i] landed
+  uint64_t* bar_z = bars + 6;           // [2] MMA commit: logits of a step in Z[i]
+  uint64_t* bar_epi = bars + 8;         // [2] 16 warps: dz of a step in Z[i] (TMEM) and adz (shared)
+  uint64_t* bar_m2 = bars + 10;         // [2] MMA commit: d_x / accumulator MMAs of a step done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* dc_part = reinterpret_cast<float*>(bars + 14);   // [16 warps][32]
+  const int b = blockIdx.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kCols = 512;
+  constexpr uint32_t tm_z = 0, tm_dx = 128, tm_acc = 224;
+  const int t_begin = blockIdx.x * tiles_per_chunk;
+  const int t_end = min((n + kTile - 1) / kTile, t_begin + tiles_per_chunk);
+  const int ntiles = max(t_end - t_begin, 0);
+  const int nsteps = ntiles * NH;
+  if (threadIdx.x == kEpiThreads) {
+    tma_prefetch_desc(&map_mn);
+    tma_prefetch_desc(&map_k);
+    for (int i = 0; i < NST; ++i) mbar_init(bar_full + i, 1);
+    mbar_init(bar_split, kGrpWarps);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_bx + i, 1); mbar_init(bar_z + i, 1); mbar_init(bar_epi + i, kGrpWarps); mbar_init(bar_m2 + i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarps) {
+    tmem_alloc(tmem_slot, kCols);
+    tmem_relinquish();
+  }
+  __syncthreads();
+  if (threadIdx.x == kEpiThreads && ntiles > 0) {
+    for (int i = 0; i < NST && i < ntiles; ++i)
+      tma_x_tile(x_ring + i * kXTile, kXBlock, &map_mn, (t_begin + i) * kTile, b * kE, bar_full + i);
+    tma_x_tile(bx, kAccN * 128, &map_k, t_begin * kTile, b * kE, bar_bx);
+  }
+  if (warp < kEpiWarps) {
+    const float* Mb = Mx + (size_t)b * D * kE;
+    stage_kmajor(m_hi, m_lo, Mb, D, DP, threadIdx.x, kEpiThreads);
+    stage_transposed(mT, Mb, D, DP, threadIdx.x, kEpiThreads);
+    for (int i = threadIdx.x; i < 2 * 4 * 16 * 32; i += kEpiThreads) {     // rows 32..47 of every pixel atom: ones | zeros
+      const int atom = i / (16 * 32), rem = i - atom * 16 * 32, row = kE + (rem >> 5), col = rem & 31;
+      *reinterpret_cast<float*>(bx + atom * kAccN * 128 + sw128_offset(row, col)) = row == kE ? 1.f : 0.f;
+    }
+    for (int i = threadIdx.x; i < 4 * 128 * 32 / 4; i += kEpiThreads)
+      reinterpret_cast<float4*>(adz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int d = threadIdx.x; d < DP; d += kEpiThreads) {
+      bias2[d] = d < D ? __ldg(bp + d) * kLog2e : -INFINITY;
+      cen[d] = d < D ? __ldg(centers + (size_t)b * D + d) : 0.f;
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  float* dxb = d_x + (size_t)b * kE * n;
+
+  if (warp == kEpiWarps) {
+    // ---------------------------------------------------------------- control lane
+    if (lane == 0) {
+      const uint32_t id_acc = make_idesc_tf32(128, kAccN, 0, 0);
+      const uint32_t id_dx = make_idesc_tf32(128, 32, 0, 0);
+      const uint32_t id_z = make_idesc_tf32(kTile, 64, 1, 0);
+      const uint64_t dx_ring = make_desc_mn32(smem_u32(x_ring), kXBlock), dx_lo = make_desc_mn32(smem_u32(x_lo), kXBlock);
+      const uint64_t dm_hi = make_desc_sw128(smem_u32(m_hi), 16, 1024), dm_lo = make_desc_sw128(smem_u32(m_lo), 16, 1024);
+      const uint64_t d_mT = make_desc_sw128(smem_u32(mT), 16, 1024), d_adz = make_desc_sw128(smem_u32(adz), 16, 1024);
+      const uint64_t d_bx = make_desc_sw128(smem_u32(bx), 16, 1024);
+      // d_x and accumulator MMAs of step sp = (tile ti, half h): its dz is in Z[sp&1] (TMEM) and adz (shared)
+      auto issue_mma2 = [&](int sp, int ti, int h) {
+        mbar_wait(bar_epi + (sp & 1), (sp >> 1) & 1);
+        if (h == 0) mbar_wait(bar_bx + (ti & 1), (ti >> 1) & 1);
+        tc_fence_after();
+        const uint64_t mt = desc_add(d_mT, h * 2 * 32 * 128), b0 = desc_add(d_bx, (ti & 1) * 4 * kAccN * 128);
+        const uint32_t t_dx = tmem + tm_dx + (ti % 3) * 32, t_z = tmem + tm_z + (sp & 1) * 64, t_acc = tmem + tm_acc + h * kAccN;
+#pragma unroll
+        for (int k = 0; k < 64 / 8; ++k)          // d_x tile (+)= dz_h M_h        (K = 64 bins, A from TMEM)
+          umma_tf32_ts(t_dx, t_z + k * 8, desc_add(mt, (k >> 2) * 32 * 128 + (k & 3) * 32), id_dx, (h > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kTile / 8; ++k)       // acc_h += dz_h^T [x | 1]       (K = 128 pixels)
+          umma_tf32_ss(t_acc, desc_add(d_adz, (k >> 2) * 128 * 128 + (k & 3) * 32),
+                       desc_add(b0, (k >> 2) * kAccN * 128 + (k & 3) * 32), id_acc, (ti > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bar_m2 + (sp & 1));
+      };
+      int ti = 0, h = 0, slot = 0, pti = 0, ph = 0;     // (tile, half, ring slot) of step s; (tile, half) of step s-1
+      for (int s = 0; s < nsteps; ++s) {
+        if (h == 0) mbar_wait(bar_split, ti & 1);   // ring slot ti % NST and x_lo hold the operands of tile ti
+        tc_fence_after();
+        // logits of (tile, half) -> Z[s&1].  Its previous contents (dz of step s-2) were last read by the d_x MMA of step
+        // s-2, issued before this one: tcgen05.mma of one thread execute in issue order.
+        mma_x_b3(desc_add(dx_ring, slot * kXTile), dx_lo, desc_add(dm_hi, h * 64 * 128), desc_add(dm_lo, h * 64 * 128),
+                 tmem + tm_z + (s & 1) * 64, id_z);
+        umma_commit(bar_z + (s & 1));
+        if (s > 0) issue_mma2(s - 1, pti, ph);
+        pti = ti; ph = h;
+        if (++h == NH) { h = 0; ++ti; slot = slot + 1 == NST ? 0 : slot + 1; }
+      }
+      if (nsteps > 0) issue_mma2(nsteps - 1, pti, ph);
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps: group `grp` owns steps s = grp (mod 2)
+    // (two halves per tile: group h owns half h of every tile; one half: the groups alternate tiles)
+    const int grp = warp >> 3, wl = warp & 7, q = wl & 3, cg = wl >> 2, gtid = threadIdx.x & (kGrpThreads - 1);
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t lane_hi = (uint32_t)lane >> 2, lane_lo4 = ((uint32_t)lane & 3u) << 2;   // swizzled column of this lane
+    float dc[32];                          // d_centers partials of this thread's 32 bins (the same bins at every step)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dc[i] = 0.f;
+    auto store_dx = [&](int ti) {          // this thread's 16 channels of its pixel of tile ti: TMEM -> global
+      const int pp = (t_begin + ti) * kTile + q * 32 + lane;
+      float v[16];
+      tmem_ld16(lane_base + tm_dx + (ti % 3) * 32 + cg * 16, v);
+      tmem_wait_ld();
+      if (pp < n) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dxb[(size_t)(cg * 16 + i) * n + pp] = v[i];
+      }
+    };
+    auto split_tile = [&](int i) {         // tile i: lo -> x_lo (the ring slot itself is the hi operand)
+      mbar_wait(bar_full + i % NST, (i / NST) & 1);
+      split_x<kGrpThreads>(x_ring + (i % NST) * kXTile, x_lo, gtid);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_split);
+    };
+    if (grp == 0 && ntiles > 0) split_tile(0);
+    for (int s = grp; s < nsteps; s += 2) {
+      const int ti = s / NH, h = s - ti * NH;
+      const int p = (t_begin + ti) * kTile + q * 32 + lane;
+      // per-pixel terms: in flight while waiting for the logits
+      const bool pin = p < n;
+      const size_t o = (size_t)b * n + p;
+      const float g = pin ? __ldg(g_pred + o) : 0.f;
+      const float inv = pin ? __ldg(stat_inv + o) : 0.f;
+      const float m2 = pin ? __ldg(stat_m + o) : 0.f;
+      const float pr = pin ? __ldg(pred + o) : 0.f;
+      const float gi = g * inv;
+      mbar_wait(bar_z + grp, (s >> 1) & 1);                // logits of step s in Z[grp]
+      tc_fence_after();
+      if (h == NH - 1) {                                   // the tile's last logits MMA is done: its ring slot and x_lo are free
+        if (gtid == 0 && ti + NST < ntiles)
+          tma_x_tile(x_ring + (ti % NST) * kXTile, kXBlock, &map_mn, (t_begin + ti + NST) * kTile, b * kE, bar_full + ti % NST);
+        if (ti + 1 < ntiles) split_tile(ti + 1);           // next tile's operands first: its MMA overlaps this epilogue
+      }
+      // ---- dz of this thread's 32 bins of its pixel: TMEM -> registers -> TMEM (the A operand of the d_x MMA)
+      float v[32];
+      {
+        const int c0 = h * 64 + cg * 32;
+        tmem_ld16(lane_base + tm_z + grp * 64 + cg * 32, *reinterpret_cast<float(*)[16]>(v));
+        tmem_ld16(lane_base + tm_z + grp * 64 + cg * 32 + 16, *reinterpret_cast<float(*)[16]>(v + 16));
+        tmem_wait_ld();
+        const float4* b4 = reinterpret_cast<const float4*>(bias2 + c0);
+        const float4* c4 = reinterpret_cast<const float4*>(cen + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bq = b4[j], cq = c4[j];
+          const float bv[4] = {bq.x, bq.y, bq.z, bq.w}, cv[4] = {cq.x, cq.y, cq.z, cq.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = 4 * j + k;
+            const float pg = ex2f(fmaf(v[i], kLog2e, bv[k]) - m2) * gi;
+            dc[i] += pg;
+            v[i] = pg * (cv[k] - pr);
+          }
+        }
+        tmem_st16(lane_base + tm_z + grp * 64 + cg * 32, *reinterpret_cast<float(*)[16]>(v));
+        tmem_st16(lane_base + tm_z + grp * 64 + cg * 32 + 16, *reinterpret_cast<float(*)[16]>(v + 16));
+      }
+      // ---- the transposed copy (A operand of the accumulator MMA) goes to the single adz tile: wait until the MMAs of
+      // the previous step -- the other group's -- have read it.  Everything above overlapped them.
+      if (s > 0) {
+        mbar_wait(bar_m2 + ((s - 1) & 1), ((s - 1) >> 1) & 1);
+        tc_fence_after();
+        if (h == 0 && gtid == 0 && ti + 1 < ntiles)        // all MMAs of tile ti-1 are done: bx[(ti+1)&1] is free, refill it
+          tma_x_tile(bx + (size_t)((ti + 1) & 1) * 4 * kAccN * 128, kAccN * 128, &map_k, (t_begin + ti + 1) * kTile, b * kE,
+                     bar_bx + ((ti + 1) & 1));
+      } else if (gtid == 0 && ntiles > 1) {
+        tma_x_tile(bx + (size_t)4 * kAccN * 128, kAccN * 128, &map_k, (t_begin + 1) * kTile, b * kE, bar_bx + 1);
+      }
+      {
+        uint8_t* adw = adz + q * 128 * 128;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int row = cg * 32 + i;
+          *reinterpret_cast<float*>(adw + row * 128 + ((lane_hi ^ (uint32_t)(row & 7)) << 4) + lane_lo4) = v[i];
+        }
+      }
+      tmem_wait_st();
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_epi + grp);
+      // the previous tile's d_x rows (complete: bar_m2 of its last step was waited for above) leave TMEM now
+      if (s > 0 && h == 0) store_dx(ti - 1);
+    }
+    if (nsteps > 0 && grp == ((nsteps - 1) & 1)) {         // the group of the last step drains the last tile
+      mbar_wait(bar_m2 + ((nsteps - 1) & 1), ((nsteps - 1) >> 1) & 1);
+      tc_fence_after();
+      store_dx(ntiles - 1);
+    }
+    // every MMA has completed before the accumulators are read: the last commit covers all earlier ones
+    named_sync(1, kEpiThreads);
+    tc_fence_after();
+    // ---- accumulators: rows = bins of half h (TMEM lanes 0..63: q < 2), cols [0,32) dM, col 32 d_bp.  Warps (q < 2, cg)
+    // of group 0 read half 0, of group 1 half 1 (one half: group 0 only); three 16-column chunks per warp pair
+    {
+      const int h = grp;
+      if (h < NH && q < 2) {
+        const int d = h * 64 + q * 32 + lane;
+        for (int ch = cg; ch < 3; ch += 2) {
+          float a[16];
+          if (ntiles > 0) {
+            tmem_ld16(lane_base + tm_acc + h * kAccN + ch * 16, a);
+            tmem_wait_ld();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = 0.f;
+          }
+          if (d < D) {
+            if (ch < 2) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) part_dM[((size_t)cta * D + d) * kE + ch * 16 + i] = a[i];
+            } else {
+              part_db[(size_t)cta * D + d] = a[0];
+            }
+          }
+        }
+      }
+    }
+    // ---- d_centers: warp totals of this thread's 32 bins, then the pixel quarters (and, with one half, the two groups)
+    {
+      float lo16[16], hi16[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { lo16[i] = dc[i]; hi16[i] = dc[16 + i]; }
+      warp_reduce16(lo16);
+      warp_reduce16(hi16);
+      if (!(lane & 1)) {
+        dc_part[warp * 32 + (lane >> 1)] = lo16[0];
+        dc_part[warp * 32 + 16 + (lane >> 1)] = hi16[0];
+      }
+    }
+    named_sync(1, kEpiThreads);
+    for (int i = threadIdx.x; i < NH * 64; i += kEpiThreads) {
+      const int h = i >> 6, c = i & 63, cgc = c >> 5, k = c & 31;
+      float acc = 0.f;
+      if (NH == 2) {
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) acc += dc_part[(h * 8 + cgc * 4 + qq) * 32 + k];
+      } else {
+#pragma unroll
+        for (int w8 = 0; w8 < 2; ++w8)
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) acc += dc_part[(w8 * 8 + cgc * 4 + qq) * 32 + k];
+      }
+      if (i < D) part_dc[(size_t)cta * D + i] = acc;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps) tmem_dealloc(tmem, kCols);
+}
+
+
+// ================================================================================================================
+// backward pass 2 (summary path):  a = softmax_pixels(y),  dy = a (t - delta),  t = x^T ds^T
+//   d_x (+)= dy K + a ds ,   d_K_2 += dy^T x
+//   step = (tile, 64-query half).  TMEM per step buffer i: y -> dy = [128 i, +64)   t -> a = [128 i + 64, +64)
+//                                  dx[0..2] = [256 + 32 j, +32)    dK[h] = [352 + 32 h, +32)  rows = queries of half h
+// ================================================================================================================
+template <int QP>
+struct BwdSumSmem {
+  static constexpr int NH = QP / 64;
+  static constexpr int NST = QP > 64 ? 2 : 3;
+  static constexpr size_t x_ring = 0, x_lo = NST * kXTile, x_k = x_lo + kXTile /* [2] */, k_hi = x_k + 2 * kXTile,
+                          k_lo = k_hi + QP * 128,
+                          ds = k_lo + QP * 128,                    // [QP rows][32 e]                 d_summary (K-major)
+                          kT = ds + QP * 128,                      // [QP/32 atoms][32 e rows][32 q]  queries transposed
+                          dsT = kT + (QP / 32) * 32 * 128,         // same shape                      d_summary transposed
+                          dyT = dsT + (QP / 32) * 32 * 128,        // [4 px atoms][128 rows][32 px]   dy^T, rows >= 64 zero
+                          tail = dyT + 4 * 128 * 128;
+  static constexpr size_t bytes = 1024 + tail + 2 * QP * 4 + 128;
+  static_assert(bytes <= 227 * 1024, "shared-memory budget");
+};
+
+template <int QP>
+__global__ void __launch_bounds__(kThreads, 1) sql_ws_bwd_sum_kernel(
+    const __grid_constant__ CUtensorMap map_mn, const __grid_constant__ CUtensorMap map_k,
+    const float* __restrict__ queries, const float* __restrict__ summary, const float* __restrict__ row_max,
+    const float* __restrict__ row_sum, const float* __restrict__ d_summary, int Q, int n, int tiles_per_chunk,
+    int accumulate, float* __restrict__ d_x, float* __restrict__ part_dK /*[cta][Q][32]*/) {
+  using L = BwdSumSmem<QP>;
+  constexpr int NH = L::NH, NST = L::NST;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* x_ring = base + L::x_ring;
+  uint8_t* x_lo = base + L::x_lo;
+  uint8_t* x_k = base + L::x_k;
+  uint8_t* k_hi = base + L::k_hi;
+  uint8_t* k_lo = base + L::k_lo;
+  uint8_t* dsm = base + L::ds;
+  uint8_t* kT = base + L::kT;
+  uint8_t* dsT = base + L::dsT;
+  uint8_t* dyT = base + L::dyT;
+  float* cqv = reinterpret_cast<float*>(base + L::tail);     // a[p,q] = 2^(y log2e + cq),  cq = -m log2e - log2(l)
+  float* dlv = cqv + QP;                                      // delta_q = ds_q . summary_q
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dlv + QP);
+  uint64_t* bar_full = bars;            // [NST <= 3] TMA: x tile landed in its ring slot
+  uint64_t* bar_split = bars + 3;       // 8 warps: x_lo written
+  uint64_t* bar_xk = bars + 4;          // [2] TMA: K-major x tile landed in x_k[i]
+  uint64_t* bar_z = bars + 6;           // [2] MMA commit: y, t of a step in buffer i
+  uint64_t* bar_epi = bars + 8;         // [2] 8 warps: dy, a of a step in buffer i (TMEM) and dyT (shared)
+  uint64_t* bar_m2 = bars + 10;         // [2] MMA commit: d_x / d_K MMAs of a step done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  const int b = blockIdx.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kCols = 512;
+  constexpr uint32_t tm_dx = 256, tm_dk = 352;
+  const int t_begin = blockIdx.x * tiles_per_chunk;
+  const int t_end = min((n + kTile - 1) / kTile, t_begin + tiles_per_chunk);
+  const int ntiles = max(t_end - t_begin, 0);
+  const int nsteps = ntiles * NH;
+  if (threadIdx.x == kEpiThreads) {
+    tma_prefetch_desc(&map_mn);
+    tma_prefetch_desc(&map_k);
+    for (int i = 0; i < NST; ++i) mbar_init(bar_full + i, 1);
+    mbar_init(bar_split, kGrpWarps);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_xk + i, 1); mbar_init(bar_z + i, 1); mbar_init(bar_epi + i, kGrpWarps); mbar_init(bar_m2 + i, 1); }
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarps) {
+    tmem_alloc(tmem_slot, kCols);
+    tmem_relinquish();
+  }
+  __syncthreads();
+  if (threadIdx.x == kEpiThreads && ntiles > 0) {
+    for (int i = 0; i < NST && i < ntiles; ++i)
+      tma_x_tile(x_ring + i * kXTile, kXBlock, &map_mn, (t_begin + i) * kTile, b * kE, bar_full + i);
+    tma_x_tile(x_k, kXBlock, &map_k, t_begin * kTile, b * kE, bar_xk);
+  }
+  if (warp < kEpiWarps) {
+    const float* qb = queries + (size_t)b * Q * kE;
+    const float* dsb = d_summary + (size_t)b * Q * kE;
+    stage_kmajor(k_hi, k_lo, qb, Q, QP, threadIdx.x, kEpiThreads);
+    stage_kmajor(dsm, nullptr, dsb, Q, QP, threadIdx.x, kEpiThreads);
+    stage_transposed(kT, qb, Q, QP, threadIdx.x, kEpiThreads);
+    stage_transposed(dsT, dsb, Q, QP, threadIdx.x, kEpiThreads);
+    for (int i = threadIdx.x; i < 4 * 128 * 32 / 4; i += kEpiThreads)
+      reinterpret_cast<float4*>(dyT)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = threadIdx.x; q < QP; q += kEpiThreads) {
+      float m = 0.f, inv = 0.f, delta = 0.f;
+      if (q < Q) {
+        m = __ldg(row_max + b * Q + q);
+        inv = 1.f / __ldg(row_sum + b * Q + q);
+        float dsv[kE], smv[kE];
+#pragma unroll
+        for (int e = 0; e < kE; ++e) { dsv[e] = __ldg(dsb + q * kE + e); smv[e] = __ldg(summary + ((size_t)b * Q + q) * kE + e); }
+#pragma unroll
+        for (int e = 0; e < kE; ++e) delta = fmaf(dsv[e], smv[e], delta);
+      }
+      cqv[q] = q < Q ? fmaf(-m, kLog2e, log2f(inv)) : -INFINITY;    // (-inf for the padded queries: a = 0)
+      dlv[q] = delta;
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  float* dxb = d_x + (size_t)b * kE * n;
+
+  if (warp == kEpiWarps) {
+    // ---------------------------------------------------------------- control lane
+    if (lane == 0) {
+      const uint32_t id_y = make_idesc_tf32(kTile, 64, 1, 0);       // y, t: A = x (MN-major), B = K / ds rows (K-major)
+      const uint32_t id_32 = make_idesc_tf32(128, 32, 0, 0);        // d_x, d_K
+      const uint64_t dx_ring = make_desc_mn32(smem_u32(x_ring), kXBlock), dx_lo = make_desc_mn32(smem_u32(x_lo), kXBlock);
+      const uint64_t dk_hi = make_desc_sw128(smem_u32(k_hi), 16, 1024), dk_lo = make_desc_sw128(smem_u32(k_lo), 16, 1024);
+      const uint64_t d_ds = make_desc_sw128(smem_u32(dsm), 16, 1024), d_kT = make_desc_sw128(smem_u32(kT), 16, 1024);
+      const uint64_t d_dsT = make_desc_sw128(smem_u32(dsT), 16, 1024), d_dyT = make_desc_sw128(smem_u32(dyT), 16, 1024);
+      const uint64_t d_xk = make_desc_sw128(smem_u32(x_k), 16, 1024);
+      auto issue_mma2 = [&](int sp, int ti, int h) {
+        mbar_wait(bar_epi + (sp & 1), (sp >> 1) & 1);
+        if (h == 0) mbar_wait(bar_xk + (ti & 1), (ti >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_dx = tmem + tm_dx + (ti % 3) * 32, t_dy = tmem + (sp & 1) * 128, t_a = t_dy + 64;
+        const uint32_t t_dk = tmem + tm_dk + h * 32;
+        const uint64_t kt = desc_add(d_kT, h * 2 * 32 * 128), dst = desc_add(d_dsT, h * 2 * 32 * 128);
+#pragma unroll
+        for (int k = 0; k < kTile / 8; ++k)       // d_K_h += dy_h^T x            (K = 128 pixels)
+          umma_tf32_ss(t_dk, desc_add(d_dyT, (k >> 2) * 128 * 128 + (k & 3) * 32),
+                       desc_add(d_xk, (ti & 1) * kXTile + (k >> 2) * kXBlock + (k & 3) * 32), id_32, (ti > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 64 / 8; ++k)          // d_x tile (+)= dy_h K_h        (K = 64 queries, A from TMEM)
+          umma_tf32_ts(t_dx, t_dy + k * 8, desc_add(kt, (k >> 2) * 32 * 128 + (k & 3) * 32), id_32, (h > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 64 / 8; ++k)          //              + a_h ds_h
+          umma_tf32_ts(t_dx, t_a + k * 8, desc_add(dst, (k >> 2) * 32 * 128 + (k & 3) * 32), id_32, 1u);
+        umma_commit(bar_m2 + (sp & 1));
+      };
+      int ti = 0, h = 0, slot = 0, pti = 0, ph = 0;
+      for (int s = 0; s < nsteps; ++s) {
+        if (h == 0) mbar_wait(bar_split, ti & 1);
+        tc_fence_after();
+        const uint64_t xa = desc_add(dx_ring, slot * kXTile);
+        mma_x_b3(xa, dx_lo, desc_add(dk_hi, h * 64 * 128), desc_add(dk_lo, h * 64 * 128), tmem + (s & 1) * 128, id_y);
+#pragma unroll
+        for (int k = 0; k < kE / 8; ++k)          // t_h = x^T ds_h^T (single pass: it only enters the gradient)
+          umma_tf32_ss(tmem + (s & 1) * 128 + 64, desc_add(xa, k * 1024), desc_add(d_ds, h * 64 * 128 + k * 32), id_y, k > 0);
+        umma_commit(bar_z + (s & 1));
+        if (s > 0) issue_mma2(s - 1, pti, ph);
+        pti = ti; ph = h;
+        if (++h == NH) { h = 0; ++ti; slot = slot + 1 == NST ? 0 : slot + 1; }
+      }
+      if (nsteps > 0) issue_mma2(nsteps - 1, pti, ph);
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps: group `grp` owns steps s = grp (mod 2)
+    const int grp = warp >> 3, wl = warp & 7, q = wl & 3, cg = wl >> 2, gtid = threadIdx.x & (kGrpThreads - 1);
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t lane_hi = (uint32_t)lane >> 2, lane_lo4 = ((uint32_t)lane & 3u) << 2;
+    auto store_dx = [&](int ti) {          // this thread's 16 channels of its pixel of tile ti: TMEM (+ old value) -> global
+      const int pp = (t_begin + ti) * kTile + q * 32 + lane;
+      float old[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) old[i] = (accumulate && pp < n) ? __ldcg(dxb + (size_t)(cg * 16 + i) * n + pp) : 0.f;
+      float v[16];
+      tmem_ld16(lane_base + tm_dx + (ti % 3) * 32 + cg * 16, v);
+      tmem_wait_ld();
+      if (pp < n) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dxb[(size_t)(cg * 16 + i) * n + pp] = v[i] + old[i];
+      }
+    };
+    auto split_tile = [&](int i) {
+      mbar_wait(bar_full + i % NST, (i / NST) & 1);
+      split_x<kGrpThreads>(x_ring + (i % NST) * kXTile, x_lo, gtid);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_split);
+    };
+    if (grp == 0 && ntiles > 0) split_tile(0);
+    for (int s = grp; s < nsteps; s += 2) {
+      const int ti = s / NH, h = s - ti * NH;
+      const int p = (t_begin + ti) * kTile + q * 32 + lane;
+      const bool pin = p < n;
+      mbar_wait(bar_z + grp, (s >> 1) & 1);                // y, t of step s in buffer grp
+      tc_fence_after();
+      if (h == NH - 1) {                                   // the tile's last y / t MMAs are done: its ring slot and x_lo are free
+        if (gtid == 0 && ti + NST < ntiles)
+          tma_x_tile(x_ring + (ti % NST) * kXTile, kXBlock, &map_mn, (t_begin + ti + NST) * kTile, b * kE, bar_full + ti % NST);
+        if (ti + 1 < ntiles) split_tile(ti + 1);
+      }
+      // ---- this thread's 32 queries of its pixel: a = softmax_pixels(y), dy = a (t - delta); both back to TMEM
+      float dy[32];
+      {
+        const int c0 = h * 64 + cg * 32;
+        const uint32_t ty = lane_base + grp * 128 + cg * 32, tt = ty + 64;
+#pragma unroll
+        for (int c = 0; c < 32; c += 16) {
+          float yv[16], tv[16];
+          tmem_ld16(ty + c, yv);
+          tmem_ld16(tt + c, tv);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i4 = 0; i4 < 16; i4 += 4) {
+            const float4 cq4 = *reinterpret_cast<const float4*>(cqv + c0 + c + i4);
+            const float4 dl4 = *reinterpret_cast<const float4*>(dlv + c0 + c + i4);
+            const float cq[4] = {cq4.x, cq4.y, cq4.z, cq4.w}, dl[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = i4 + j;
+              const float a = pin ? ex2f(fmaf(yv[i], kLog2e, cq[j])) : 0.f;
+              dy[c + i] = a * (tv[i] - dl[j]);
+              tv[i] = a;
+              yv[i] = dy[c + i];
+            }
+          }
+          tmem_st16(ty + c, yv);
+          tmem_st16(tt + c, tv);
+        }
+      }
+      // ---- dy^T (A operand of the d_K MMA) goes to the single dyT tile once the previous step's MMAs have read it
+      if (s > 0) {
+        mbar_wait(bar_m2 + ((s - 1) & 1), ((s - 1) >> 1) & 1);
+        tc_fence_after();
+        if (h == 0 && gtid == 0 && ti + 1 < ntiles)        // all MMAs of tile ti-1 are done: x_k[(ti+1)&1] is free, refill it
+          tma_x_tile(x_k + (size_t)((ti + 1) & 1) * kXTile, kXBlock, &map_k, (t_begin + ti + 1) * kTile, b * kE,
+                     bar_xk + ((ti + 1) & 1));
+      } else if (gtid == 0 && ntiles > 1) {
+        tma_x_tile(x_k + kXTile, kXBlock, &map_k, (t_begin + 1) * kTile, b * kE, bar_xk + 1);
+      }
+      {
+        uint8_t* dyw = dyT + q * 128 * 128;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int row = cg * 32 + i;
+          *reinterpret_cast<float*>(dyw + row * 128 + ((lane_hi ^ (uint32_t)(row & 7)) << 4) + lane_lo4) = dy[i];
+        }
+      }
+      tmem_wait_st();
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_epi + grp);
+      if (s > 0 && h == 0) store_dx(ti - 1);
+    }
+    if (nsteps > 0 && grp == ((nsteps - 1) & 1)) {
+      mbar_wait(bar_m2 + ((nsteps - 1) & 1), ((nsteps - 1) >> 1) & 1);
+      tc_fence_after();
+      store_dx(ntiles - 1);
+    }
+    named_sync(1, kEpiThreads);
+    tc_fence_after();
+    // ---- d_K accumulators: rows = queries of half h (TMEM lanes 0..63: q < 2); group h reads half h
+    {
+      const int h = grp;
+      if (h < NH && q < 2) {
+        const int qq = h * 64 + q * 32 + lane;
+        float a[16];
+        if (ntiles > 0) {
+          tmem_ld16(lane_base + tm_dk + h * 32 + cg * 16, a);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) a[i] = 0.f;
+        }
+        if (qq < Q) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) part_dK[((size_t)cta * Q + qq) * kE + cg * 16 + i] = a[i];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps) tmem_dealloc(tmem, kCols);
+}
+
+}  // namespace wsql
+
+// ------------------------------------------------------------------------------------------------
+// launchers (called from the C ABI in sql_fp32.cu)
+// ------------------------------------------------------------------------------------------------
+void ws_plan(int B, int n, int* chunks, int* tiles_per_chunk) {
+  const int tiles = ceil_div(n, wsql::kTile);
+  int c = kNumSMs / B;   // one CTA per SM
+  c = c < 1 ? 1 : (c > tiles ? tiles : c);
+  *tiles_per_chunk = ceil_div(tiles, c);
+  *chunks = ceil_div(tiles, *tiles_per_chunk);
+}
+
+template <int DP>
+static int launch_ws_pred(const CUtensorMap& map, const float* Mx, const float* bp, const float* centers, int B, int D, int n,
+                          float* pred, float* stat_m, float* stat_inv, cudaStream_t st) {
+  int chunks, tpc;
+  ws_plan(B, n, &chunks, &tpc);
+  if (int e = ensure_dyn_smem(wsql::sql_ws_pred_kernel<DP>, wsql::PredSmem<DP>::bytes)) return e;
+  ProfScope prof("sql_tc_pred_kernel", st);
+  wsql::sql_ws_pred_kernel<DP><<<dim3(chunks, B), wsql::kThreads, wsql::PredSmem<DP>::bytes, st>>>(
+      map, Mx, bp, centers, D, n, tpc, pred, stat_m, stat_inv);
+  return check_launch("sql_ws_pred_kernel");
+}
+
+int ws_pred_fwd(const float* x, const float* Mx, const float* bp, const float* centers, int B, int D, int n, float* pred,
+                float* stat_m, float* stat_inv, cudaStream_t st) {
+  SQLX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
+  CUtensorMap map;
+  if (int e = make_tensor_map_2d(&map, x, (uint64_t)B * wsql::kE, (uint64_t)n, 32, 32, 1)) return e;
+  if (D <= 64) return launch_ws_pred<64>(map, Mx, bp, centers, B, D, n, pred, stat_m, stat_inv, st);
+  return launch_ws_pred<128>(map, Mx, bp, centers, B, D, n, pred, stat_m, stat_inv, st);
+}
+
+template <int DP>
+static int launch_ws_bwd_pred(const CUtensorMap& map_mn, const CUtensorMap& map_k, const float* Mx, const float* bp,
+                              const float* centers, const float* g_pred, const float* pred, const float* stat_m,
+                              const float* stat_inv, int B, int D, int n, int chunks, int tpc, float* d_x, float* part_dM,
+                              float* part_db, float* part_dc, cudaStream_t st) {
+  if (int e = ensure_dyn_smem(wsql::sql_ws_bwd_pred_kernel<DP>, wsql::BwdPredSmem<DP>::bytes)) return e;
+  ProfScope prof("sql_tc_bwd_pred_kernel", st);
+  wsql::sql_ws_bwd_pred_kernel<DP><<<dim3(chunks, B), wsql::kThreads, wsql::BwdPredSmem<DP>::bytes, st>>>(
+      map_mn, map_k, Mx, bp, centers, g_pred, pred, stat_m, stat_inv, D, n, tpc, d_x, part_dM, part_db, part_dc);
+  return check_launch("sql_ws_bwd_pred_kernel");
+}
+
+int ws_bwd_pred(const float* x, const float* Mx, const float* bp, const float* centers, const float* g_pred,
+                const float* pred, const float* stat_m, const float* stat_inv, int B, int D, int n, float* d_x,
+                float* part_dM, float* part_db, float* part_dc, int chunks, int tpc, cudaStream_t st) {
+  SQLX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
+  CUtensorMap map_mn, map_k;
+  if (int e = make_tensor_map_2d(&map_mn, x, (uint64_t)B * wsql::kE, (uint64_t)n, 32, 32, 1)) return e;
+  if (int e = make_tensor_map_2d(&map_k, x, (uint64_t)B * wsql::kE, (uint64_t)n, 32, 32, 0)) return e;
+  if (D <= 64)
+    return launch_ws_bwd_pred<64>(map_mn, map_k, Mx, bp, centers, g_pred, pred, stat_m, stat_inv, B, D, n, chunks, tpc, d_x,
+                                  part_dM, part_db, part_dc, st);
+  return launch_ws_bwd_pred<128>(map_mn, map_k, Mx, bp, centers, g_pred, pred, stat_m, stat_inv, B, D, n, chunks, tpc, d_x,
+                                 part_dM, part_db, part_dc, st);
+}
+
+template <int QP>
+static int launch_ws_bwd_sum(const CUtensorMap& map_mn, const CUtensorMap& map_k, const float* queries, const float* summary,
+                             const float* row_max, const float* row_sum, const float* d_summary, int B, int Q, int n,
+                             int chunks, int tpc, int accumulate, float* d_x, float* part_dK, cudaStream_t st) {
+  if (int e = ensure_dyn_smem(wsql::sql_ws_bwd_sum_kernel<QP>, wsql::BwdSumSmem<QP>::bytes)) return e;
+  ProfScope prof("sql_tc_bwd_sum_kernel", st);
+  wsql::sql_ws_bwd_sum_kernel<QP><<<dim3(chunks, B), wsql::kThreads, wsql::BwdSumSmem<QP>::bytes, st>>>(
+      map_mn, map_k, queries, summary, row_max, row_sum, d_summary, Q, n, tpc, accumulate, d_x, part_dK);
+  return check_launch("sql_ws_bwd_sum_kernel");
+}
+
+int ws_bwd_sum(const float* x, const float* queries, const float* summary, const float* row_max, const float* row_sum,
+               const float* d_summary, int B, int Q, int n, int accumulate, float* d_x, float* part_dK, int chunks, int tpc,
+               cudaStream_t st) {
+  SQLX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
+  CUtensorMap map_mn, map_k;
+  if (int e = make_tensor_map_2d(&map_mn, x, (uint64_t)B * wsql::kE, (uint64_t)n, 32, 32, 1)) return e;
+  if (int e = make_tensor_map_2d(&map_k, x, (uint64_t)B * wsql::kE, (uint64_t)n, 32, 32, 0)) return e;
+  if (Q <= 64)
+    return launch_ws_bwd_sum<64>(map_mn, map_k, queries, summary, row_max, row_sum, d_summary, B, Q, n, chunks, tpc, accumulate,
+                                 d_x, part_dK, st);
+  return launch_ws_bwd_sum<128>(map_mn, map_k, queries, summary, row_max, row_sum, d_summary, B, Q, n, chunks, tpc, accumulate,
+                                d_x, part_dK, st);
+}
+
+}  // namespace sqlx

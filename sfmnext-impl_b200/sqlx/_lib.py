@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsqlx.so")
+# SQLX_LIB_PATH: development only -- load an A/B build of the same library (`make variant`, tools/ab.py)
+LIB_PATH = os.environ.get("SQLX_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libsqlx.so")
 
 c_float_p = ctypes.c_void_p   # device pointers are passed as raw addresses
 c_size_t = ctypes.c_size_t
@@ -130,11 +131,18 @@ _PROTOS = {
     "sqlx_sql_mix_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sqlx_sql_mix_weights_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                          c_void_p]),
-    "sqlx_sql_pred_mix_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "sqlx_sql_bwd_pred_mix": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sqlx_sql_pred_mix_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                      c_void_p]),
+    "sqlx_sql_bwd_pred_mix": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                      c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sqlx_sql_pred_mix_fwd_v1": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                         c_void_p]),
+    "sqlx_sql_bwd_pred_mix_v1": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sqlx_sql_bwd_summary": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sqlx_sql_bwd_summary_v1": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                        c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sqlx_sql_pred_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_void_p, c_void_p]),
     "sqlx_sql_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

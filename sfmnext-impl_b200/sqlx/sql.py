@@ -115,16 +115,24 @@ def _mix_workspace(B, Q, D, n, device):
     return torch.empty(nbytes, device=device, dtype=torch.uint8), nbytes
 
 
-def pred_mix_fwd(x, Mx, bp, centers):
+def pred_mix_fwd(x, Mx, bp, centers, version=2):
+    """pred [B,1,h,w] and the per-pixel softmax statistics [2,B,n] the backward reads (version=1: the round-1 kernel, no
+    statistics -- A/B and cross-check only)."""
     B, E, h, w = x.shape
     D = Mx.shape[1]
     pred = torch.empty(B, 1, h, w, device=x.device, dtype=torch.float32)
-    check(lib().sqlx_sql_pred_mix_fwd(ptr(x), ptr(Mx), ptr(bp), ptr(centers), B, E, D, h * w, ptr(pred), stream_ptr()),
-          "sqlx_sql_pred_mix_fwd")
-    return pred
+    if version == 1:
+        check(lib().sqlx_sql_pred_mix_fwd_v1(ptr(x), ptr(Mx), ptr(bp), ptr(centers), B, E, D, h * w, ptr(pred),
+                                             stream_ptr()), "sqlx_sql_pred_mix_fwd_v1")
+        return pred, None
+    stats = torch.empty(2, B, h * w, device=x.device, dtype=torch.float32)
+    check(lib().sqlx_sql_pred_mix_fwd(ptr(x), ptr(Mx), ptr(bp), ptr(centers), B, E, D, h * w, ptr(pred), ptr(stats),
+                                      stream_ptr()), "sqlx_sql_pred_mix_fwd")
+    return pred, stats
 
 
-def bwd_pred_mix(x, Mx, bp, centers, g_pred, d_bp=None):
+def bwd_pred_mix(x, Mx, bp, centers, g_pred, pred=None, stats=None, d_bp=None):
+    """Regression-path backward.  pred / stats from pred_mix_fwd; stats=None runs the round-1 kernel (cross-check)."""
     B, E, h, w = x.shape
     D = Mx.shape[1]
     dev = x.device
@@ -134,14 +142,19 @@ def bwd_pred_mix(x, Mx, bp, centers, g_pred, d_bp=None):
     d_centers = torch.empty(B, D, device=dev, dtype=torch.float32)
     d_x = torch.empty_like(x)
     ws, nbytes = _mix_workspace(B, 1, D, h * w, dev)
-    check(lib().sqlx_sql_bwd_pred_mix(ptr(x), ptr(Mx), ptr(bp), ptr(centers), ptr(g_pred), B, E, D, h * w, ptr(d_M),
-                                      ptr(d_bp), ptr(d_centers), ptr(d_x), ptr(ws), nbytes, stream_ptr()),
-          "sqlx_sql_bwd_pred_mix")
+    if stats is None:
+        check(lib().sqlx_sql_bwd_pred_mix_v1(ptr(x), ptr(Mx), ptr(bp), ptr(centers), ptr(g_pred), B, E, D, h * w, ptr(d_M),
+                                             ptr(d_bp), ptr(d_centers), ptr(d_x), ptr(ws), nbytes, stream_ptr()),
+              "sqlx_sql_bwd_pred_mix_v1")
+    else:
+        check(lib().sqlx_sql_bwd_pred_mix(ptr(x), ptr(Mx), ptr(bp), ptr(centers), ptr(g_pred), ptr(pred), ptr(stats), B, E,
+                                          D, h * w, ptr(d_M), ptr(d_bp), ptr(d_centers), ptr(d_x), ptr(ws), nbytes,
+                                          stream_ptr()), "sqlx_sql_bwd_pred_mix")
     return d_M, d_bp, d_centers, d_x
 
 
-def bwd_summary(x, queries, summary, row_max, row_sum, d_summary, d_x=None):
-    """Summary-path backward; accumulates into d_x when given (else writes a fresh tensor)."""
+def bwd_summary(x, queries, summary, row_max, row_sum, d_summary, d_x=None, version=2):
+    """Summary-path backward; accumulates into d_x when given (else writes a fresh tensor).  version=1: round-1 kernel."""
     B, E, h, w = x.shape
     Q = queries.shape[1]
     accumulate = d_x is not None
@@ -149,9 +162,9 @@ def bwd_summary(x, queries, summary, row_max, row_sum, d_summary, d_x=None):
         d_x = torch.empty_like(x)
     d_q = torch.empty_like(queries)
     ws, nbytes = _mix_workspace(B, Q, 0, h * w, x.device)
-    check(lib().sqlx_sql_bwd_summary(ptr(x), ptr(queries), ptr(summary), ptr(row_max), ptr(row_sum), ptr(d_summary), B, E,
-                                     Q, h * w, int(accumulate), ptr(d_x), ptr(d_q), ptr(ws), nbytes, stream_ptr()),
-          "sqlx_sql_bwd_summary")
+    fn = lib().sqlx_sql_bwd_summary if version == 2 else lib().sqlx_sql_bwd_summary_v1
+    check(fn(ptr(x), ptr(queries), ptr(summary), ptr(row_max), ptr(row_sum), ptr(d_summary), B, E, Q, h * w, int(accumulate),
+             ptr(d_x), ptr(d_q), ptr(ws), nbytes, stream_ptr()), "sqlx_sql_bwd_summary")
     return d_x, d_q
 
 
@@ -292,8 +305,8 @@ class _SqlTail(torch.autograd.Function):
         ctx.mix = use_mix(E, qc.shape[1], Wc.shape[0], h * w)
         if ctx.mix:
             Mx = mix_weights(Wc, qc)                     # [B,D,E] = Wp . K
-            pred = pred_mix_fwd(xc, Mx, bc, cc)
-            ctx.save_for_backward(xc, qc, Wc, bc, cc, summary, row_max, row_sum, Mx)
+            pred, stats = pred_mix_fwd(xc, Mx, bc, cc)
+            ctx.save_for_backward(xc, qc, Wc, bc, cc, summary, row_max, row_sum, Mx, pred, stats)
         else:
             pred = pred_fwd(xc, qc, Wc, bc, cc)
             ctx.save_for_backward(xc, qc, Wc, bc, cc, summary, row_max, row_sum)
@@ -314,8 +327,8 @@ class _SqlTail(torch.autograd.Function):
         out_Wp, out_bp = ctx.head_grad_out if ctx.head_grad_out is not None else (None, None)
         need = [p for p in ctx.params if p.requires_grad]
         if ctx.mix:
-            xc, qc, Wc, bc, cc, summary, row_max, row_sum, Mx = ctx.saved_tensors
-            d_M, d_bp, d_centers, d_x = bwd_pred_mix(xc, Mx, bc, cc, g, d_bp=out_bp)
+            xc, qc, Wc, bc, cc, summary, row_max, row_sum, Mx, pred, stats = ctx.saved_tensors
+            d_M, d_bp, d_centers, d_x = bwd_pred_mix(xc, Mx, bc, cc, g, pred, stats, d_bp=out_bp)
         else:
             xc, qc, Wc, bc, cc, summary, row_max, row_sum = ctx.saved_tensors
             d_centers, d_Wp, d_bp = bwd_reduce(xc, qc, Wc, bc, cc, g)

@@ -51,7 +51,8 @@ def test_pred_tc(cfg):
     centers = torch.sort(0.1 + 80 * torch.rand(B, D, generator=g), dim=1).values
     xc, qc, Wc, bc, cc = (t.cuda() for t in (x, q, Wp, bp, centers))
     assert S.tc_supported(32, Q, D, h * w)
-    pred_tc = S.pred_mix_fwd(xc, S.mix_weights(Wc, qc), bc, cc)
+    pred_tc, stats = S.pred_mix_fwd(xc, S.mix_weights(Wc, qc), bc, cc)
+    assert torch.isfinite(stats).all() and bool((stats[1] > 0).all()) and bool((stats[1] <= 1.0 + 1e-6).all())
     pred_fp = S.pred_fwd(xc, qc, Wc, bc, cc)
     assert float(((pred_tc - pred_fp) / pred_fp).abs().max()) < 5e-5
     ref = []
@@ -130,3 +131,48 @@ def test_tail_paths_agree(cfg):
     for a, b, nm in zip(res[1][1], res[0][1], ("x", "queries", "Wp", "bp", "W1")):
         rel = float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
         assert rel < 2e-3, (nm, rel)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, h=24, w=40, Q=64, D=64),
+    dict(B=1, h=17, w=20, Q=120, D=128),      # ragged last tile, two bin halves
+    dict(B=3, h=8, w=12, Q=12, D=16),         # fewer pixels than a tile, three column groups all padding
+    dict(B=5, h=3, w=4, Q=8, D=100),          # more CTAs than tiles: empty chunks
+    dict(B=12, h=96, w=320, Q=64, D=64),      # BASELINE config 2
+    dict(B=8, h=160, w=512, Q=128, D=128),    # BASELINE config 3
+    dict(B=2, h=320, w=1024, Q=128, D=128),   # BASELINE config 4 (two of its eight samples)
+])
+def test_ws_kernels_match_v1(cfg):
+    """Warp-specialised depth-regression forward / backward (csrc/sql_ws.cu: 16 epilogue warps, double-buffered TMEM, saved
+    softmax statistics) against the round-1 single-warpgroup kernels on the same inputs: same arithmetic up to summation
+    order (2e-6 of the depth; gradients 1e-4 of max |grad|)."""
+    from sqlx import sql as S
+    B, h, w, Q, D = (cfg[k] for k in ("B", "h", "w", "Q", "D"))
+    g = torch.Generator().manual_seed(3 + Q + D)
+    x = torch.randn(B, 32, h, w, generator=g).cuda()
+    q = (0.4 * torch.randn(B, Q, 32, generator=g)).cuda()
+    Wp = (0.3 * torch.randn(D, Q, generator=g)).cuda()
+    bp = (0.1 * torch.randn(D, generator=g)).cuda()
+    cen = torch.sort(0.1 + 80 * torch.rand(B, D, generator=g), dim=1).values.cuda()
+    gp = torch.randn(B, 1, h, w, generator=g).cuda()
+    Mx = S.mix_weights(Wp, q)
+    p1, _ = S.pred_mix_fwd(x, Mx, bp, cen, version=1)
+    p2, stats = S.pred_mix_fwd(x, Mx, bp, cen)
+    assert float(((p2 - p1) / p1).abs().max()) < 2e-6
+    r1 = S.bwd_pred_mix(x, Mx, bp, cen, gp)
+    r2 = S.bwd_pred_mix(x, Mx, bp, cen, gp, p2, stats)
+    for a, b, nm in zip(r2, r1, ("d_M", "d_bp", "d_centers", "d_x")):
+        assert torch.isfinite(a).all(), nm
+        rel = float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+        assert rel < 1e-3, (nm, rel)     # single-pass TF32 gradient contractions: operand-truncation noise ~2e-4
+    # summary-path backward, write and accumulate modes
+    summ, mx, sm, _ = S.summary_fwd(x, q)
+    ds = torch.randn(summ.shape, generator=g).cuda()
+    acc0 = torch.randn(x.shape, generator=g).cuda()
+    for mode in ("write", "accumulate"):
+        a1 = S.bwd_summary(x, q, summ, mx, sm, ds, d_x=acc0.clone() if mode == "accumulate" else None, version=1)
+        a2 = S.bwd_summary(x, q, summ, mx, sm, ds, d_x=acc0.clone() if mode == "accumulate" else None)
+        for a, b, nm in zip(a2, a1, ("d_x", "d_queries")):
+            assert torch.isfinite(a).all(), (mode, nm)
+            rel = float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+            assert rel < 1e-3, (mode, nm, rel)

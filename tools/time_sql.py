@@ -27,8 +27,12 @@ def t(name, fn, it=20):
 
 print("B=%d n=%d Q=%d D=%d" % (B, h * w, Q, D))
 t("summary_fwd", lambda: S.summary_fwd(x, q))
+t("pred_mix_fwd v1", lambda: S.pred_mix_fwd(x, Mx, bp, cen, version=1))
 t("pred_mix_fwd", lambda: S.pred_mix_fwd(x, Mx, bp, cen))
-t("bwd_pred_mix", lambda: S.bwd_pred_mix(x, Mx, bp, cen, g))
+pred, stats = S.pred_mix_fwd(x, Mx, bp, cen)
+t("bwd_pred_mix v1", lambda: S.bwd_pred_mix(x, Mx, bp, cen, g))
+t("bwd_pred_mix", lambda: S.bwd_pred_mix(x, Mx, bp, cen, g, pred, stats))
+t("bwd_summary v1 (write)", lambda: S.bwd_summary(x, q, summ, m, l, ds, version=1))
 t("bwd_summary (write)", lambda: S.bwd_summary(x, q, summ, m, l, ds))
 t("bwd_summary (accumulate)", lambda: S.bwd_summary(x, q, summ, m, l, ds, d_x=dx0))
 if Q <= 64 and D <= 64:

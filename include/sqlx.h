@@ -251,6 +251,26 @@ int sqlx_head_centers_bwd(const float* raw, const float* centers, const float* g
  * align_corners=True bilinear resize (train_ft_SQLdepth.py:235) and the boolean-mask gather fused into one pass.
  *   pred [B,1,h,w]; gt [B,1,H,W]; mask [B,1,H,W] u8 (torch.bool storage) or NULL; loss [1]; saved [4] floats
  *   (mean, count, Dg, loss) carried to the backward; d_pred [B,1,h,w] overwritten. */
+/* inverse_rotation_warp of the indoor trainer's rectification step (layers.py:460-479; N4):
+ *   out = grid_sample(img, pix, padding_mode="zeros", align_corners=True), pix = (P w).xy / ((P w).z + 1e-7),
+ *   w = depth_to_3d(ones, K)(u,v) = ((u - cx)/fx, (v - cy)/fy, 1), P [B,3,3] = K . euler2mat(rot) built by the caller.
+ * Backward: d_P [B,3,3] (autograd carries it to rot); workspace zero-initialised ONCE by the caller (left zero). */
+size_t sqlx_rotation_warp_workspace_bytes(int B);
+int sqlx_rotation_warp_fwd(const float* img, const float* P, const float* K3, int B, int H, int W, float* out, void* stream);
+int sqlx_rotation_warp_bwd(const float* img, const float* P, const float* K3, const float* g_out, int B, int H, int W,
+                           float* d_P, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Per-sample median scaling of the fine-tuning loop (finetune/train_ft_SQLdepth.py:236-266), on the device:
+ *   ratio[i] = median(depth_i[valid]) / median(pred_i[valid]) for i < count (1 when either median is NaN), 1 for i >= count
+ *   valid = min_depth_eval < depth < max_depth_eval inside the crop rows [r0,r1) x columns [c0,c1) (garg / eigen crop)
+ * pred, depth [B,H,W] fp32 (pred already resized to the ground truth, :235).  Exact radix select of the two middle order
+ * statistics (numpy.median); replaces one device->host->device round trip per sample.  workspace: zero-initialised ONCE by
+ * the caller (the kernel leaves it zero); B <= 64. */
+size_t sqlx_median_ratio_workspace_bytes(int B);
+int sqlx_median_ratio(const float* pred, const float* depth, int B, int H, int W, int count, float min_depth_eval,
+                      float max_depth_eval, int r0, int r1, int c0, int c1, float* ratio, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 size_t sqlx_silog_workspace_bytes(void);
 int sqlx_silog_fwd(const float* pred, const float* gt, const uint8_t* mask, int B, int h, int w, int H, int W,
                    float variance_focus, float* loss, float* saved, void* workspace, size_t workspace_bytes,

@@ -229,51 +229,39 @@ def predict_disparity(encoder, depth_decoder, input_color, post_process=False):
 
 
 # ----------------------------------------------------------------------------- fine-tuning: per-sample median scaling
-def _crop_mask(H, W, garg_crop, eigen_crop, dataset, device):
-    """eval_mask of finetune/train_ft_SQLdepth.py:240-253 as a bool [H, W] tensor."""
+def _crop_box(H, W, garg_crop, eigen_crop, dataset):
+    """eval_mask of finetune/train_ft_SQLdepth.py:240-253 as (r0, r1, c0, c1)."""
     if not (garg_crop or eigen_crop):
         # the reference's loop reads eval_mask unconditionally (:254): without a crop flag it raises NameError
         raise ValueError("median scaling needs garg_crop or eigen_crop (finetune/train_ft_SQLdepth.py:240-254)")
-    m = torch.zeros(H, W, dtype=torch.bool, device=device)
     if garg_crop:
-        m[int(0.40810811 * H):int(0.99189189 * H), int(0.03594771 * W):int(0.96405229 * W)] = True
-    elif dataset == "kitti":
-        m[int(0.3324324 * H):int(0.91351351 * H), int(0.0359477 * W):int(0.96405229 * W)] = True
-    else:
-        m[45:471, 41:601] = True
-    return m
+        return int(0.40810811 * H), int(0.99189189 * H), int(0.03594771 * W), int(0.96405229 * W)
+    if dataset == "kitti":
+        return int(0.3324324 * H), int(0.91351351 * H), int(0.0359477 * W), int(0.96405229 * W)
+    return 45, 471, 41, 601
 
 
-def _masked_median(v, mask):
-    """numpy.median of v[mask] per row (mean of the two middle order statistics; NaN when the selection is empty or
-    holds a NaN) for v, mask [R, n] -- one sort, no boolean indexing, no device->host synchronisation."""
-    k = mask.sum(dim=1)
-    key = torch.where(mask, v, torch.full_like(v, float("inf")))
-    key = torch.where(torch.isnan(key), torch.full_like(v, float("inf")), key)      # NaNs are flagged separately
-    srt = torch.sort(key, dim=1).values
-    lo = ((k - 1).clamp_min(0) // 2).unsqueeze(1)
-    hi = (k // 2).clamp_max(v.shape[1] - 1).unsqueeze(1)
-    med = (srt.gather(1, lo) + srt.gather(1, hi))[:, 0] * 0.5
-    bad = (k == 0) | (torch.isnan(v) & mask).any(dim=1)
-    return torch.where(bad, torch.full_like(med, float("nan")), med)
+_median_ws = {}
 
 
 def median_scale_ratios(pred, depth, min_depth_eval, max_depth_eval, garg_crop=False, eigen_crop=False,
                         dataset="kitti", count=None):
-    """The per-sample factors of finetune/train_ft_SQLdepth.py:236-266, computed on the tensors' device:
+    """The per-sample factors of finetune/train_ft_SQLdepth.py:236-266 in ONE kernel launch on the tensors' device
+    (csrc/median.cu: exact radix select of numpy.median's two middle order statistics over the valid pixels):
     ratio_i = median(depth_i[valid]) / median(pred_i[valid]) for the first `count` (default B // 2, :236) samples,
     1 where either median is NaN (:261-264), 1 for the remaining samples.  pred, depth: [B,1,H,W] -> [B] (detached)."""
+    require_cuda(pred, depth)
     B, _, H, W = pred.shape
     count = B // 2 if count is None else count
-    with torch.no_grad():
-        p = pred.detach().reshape(B, H * W).float()
-        d = depth.detach().reshape(B, H * W).float()
-        valid = (d > min_depth_eval) & (d < max_depth_eval)
-        valid = valid & _crop_mask(H, W, garg_crop, eigen_crop, dataset, pred.device).reshape(1, H * W)
-        md, mp = _masked_median(d, valid), _masked_median(p, valid)
-        ratio = md / mp
-        ratio = torch.where(torch.isnan(md) | torch.isnan(mp), torch.ones_like(ratio), ratio)
-        ratio = torch.where(torch.arange(B, device=pred.device) < count, ratio, torch.ones_like(ratio))
+    r0, r1, c0, c1 = _crop_box(H, W, garg_crop, eigen_crop, dataset)
+    p, d = _f32c(pred), _f32c(depth)
+    ratio = torch.empty(B, device=p.device, dtype=torch.float32)
+    key = (p.device, B)
+    ws = _median_ws.get(key)
+    if ws is None:                                  # arrival counters: zeroed once, the kernel leaves them zero
+        ws = _median_ws[key] = torch.zeros(lib().sqlx_median_ratio_workspace_bytes(B), device=p.device, dtype=torch.uint8)
+    check(lib().sqlx_median_ratio(ptr(p), ptr(d), B, H, W, int(count), float(min_depth_eval), float(max_depth_eval), r0, r1,
+                                  c0, c1, ptr(ratio), ptr(ws), ws.numel(), stream_ptr()), "sqlx_median_ratio")
     return ratio
 
 
@@ -281,8 +269,62 @@ def median_scale(pred, depth, min_depth_eval, max_depth_eval, garg_crop=False, e
                  count=None):
     """Drop-in for the NumPy loop of finetune/train_ft_SQLdepth.py:236-266 (`pred[i] *= ratio`, one device->host->device
     round trip per sample in the reference): returns pred scaled per sample, differentiable wrt pred (the ratios are
-    constants, as in the reference).  Sort-based torch ops on the device; the fused loss that follows is
-    sqlx.SILogLoss (sqlx_silog_fwd/bwd)."""
+    constants, as in the reference).  The loss that follows is sqlx.SILogLoss (sqlx_silog_fwd/bwd)."""
     require_cuda(pred, depth)
     ratio = median_scale_ratios(pred, depth, min_depth_eval, max_depth_eval, garg_crop, eigen_crop, dataset, count)
     return pred * ratio.view(-1, 1, 1, 1)
+
+
+# ----------------------------------------------------------------------------- indoor rectification warp (N4)
+def euler2mat(angle):
+    """layers.py:422-457: rotation matrix [B,3,3] = X(x) . Y(y) . Z(z) of Euler angles [B,3] (radians)."""
+    x, y, z = angle[:, 0], angle[:, 1], angle[:, 2]
+    zeros, ones = torch.zeros_like(z), torch.ones_like(z)
+    cz, sz, cy, sy, cx, sx = torch.cos(z), torch.sin(z), torch.cos(y), torch.sin(y), torch.cos(x), torch.sin(x)
+    B = angle.shape[0]
+    zmat = torch.stack([cz, -sz, zeros, sz, cz, zeros, zeros, zeros, ones], dim=1).reshape(B, 3, 3)
+    ymat = torch.stack([cy, zeros, sy, zeros, ones, zeros, -sy, zeros, cy], dim=1).reshape(B, 3, 3)
+    xmat = torch.stack([ones, zeros, zeros, zeros, cx, -sx, zeros, sx, cx], dim=1).reshape(B, 3, 3)
+    return xmat @ ymat @ zmat
+
+
+_rw_ws = {}
+
+
+class _RotationWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, P, K3):
+        require_cuda(img, P, K3)
+        im, Pc, Kc = _f32c(img), _f32c(P), _f32c(K3)
+        B, C, H, W = im.shape
+        if C != 3:
+            raise RuntimeError("inverse_rotation_warp expects [B,3,H,W] images")
+        out = torch.empty_like(im)
+        check(lib().sqlx_rotation_warp_fwd(ptr(im), ptr(Pc), ptr(Kc), B, H, W, ptr(out), stream_ptr()), "sqlx_rotation_warp_fwd")
+        ctx.save_for_backward(im, Pc, Kc)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        im, Pc, Kc = ctx.saved_tensors
+        B, _, H, W = im.shape
+        key = (im.device, B)
+        ws = _rw_ws.get(key)
+        if ws is None:
+            ws = _rw_ws[key] = torch.zeros(lib().sqlx_rotation_warp_workspace_bytes(B), device=im.device, dtype=torch.uint8)
+        dP = torch.empty(B, 3, 3, device=im.device, dtype=torch.float32)
+        check(lib().sqlx_rotation_warp_bwd(ptr(im), ptr(Pc), ptr(Kc), ptr(_f32c(g)), B, H, W, ptr(dP), ptr(ws), ws.numel(),
+                                           stream_ptr()), "sqlx_rotation_warp_bwd")
+        return None, dP, None
+
+
+def inverse_rotation_warp(img, rot, intrinsics, padding_mode="zeros"):
+    """Drop-in for layers.inverse_rotation_warp (layers.py:460-479): img [B,3,H,W], rot [B,3] Euler angles, intrinsics
+    [B,3,3] -> img resampled under the pure rotation, differentiable wrt `rot` (what trainer_indoor.rectify_imgs needs,
+    trainer_indoor.py:877-920; the frames themselves carry no gradient there).  The per-pixel work -- back-projection of
+    the unit-depth plane, projection, zero-padded bilinear gather, and the reduction of the gradient to dL/d(K R) -- is one
+    kernel each way; K . euler2mat(rot) is three tiny torch ops."""
+    if padding_mode != "zeros":
+        raise NotImplementedError("inverse_rotation_warp: the reference only ever passes padding_mode='zeros'")
+    P = torch.matmul(intrinsics.float(), euler2mat(rot.float()))
+    return _RotationWarp.apply(img, P, intrinsics)

@@ -434,6 +434,42 @@ class Lite_Depth_Decoder_QueryTr(Depth_Decoder_QueryTr):
     dim_feedforward = 512
 
 
+def convert_depth_decoder(ref_decoder):
+    """A sqlx decoder with the hyper-parameters and weights of a reference decoder instance -- networks.Depth_Decoder_QueryTr,
+    networks.Lite_Depth_Decoder_QueryTr (networks/{,lite_}depth_decoder_QTR.py) or the duplicate class inside SQLdepth.py
+    (:154-221): same parameter names, so its state_dict strict-loads."""
+    conv = ref_decoder.embedding_convPxP
+    layer = ref_decoder.transformer_encoder.layers[0]
+    ff = layer.linear1.out_features
+    cls = Lite_Depth_Decoder_QueryTr if ff == Lite_Depth_Decoder_QueryTr.dim_feedforward else Depth_Decoder_QueryTr
+    if ff not in (512, 1024):
+        raise ValueError("unexpected dim_feedforward %d" % ff)
+    out = cls(in_channels=conv.in_channels, embedding_dim=conv.out_channels, patch_size=conv.kernel_size[0],
+              num_heads=layer.self_attn.num_heads, query_nums=ref_decoder.query_nums,
+              dim_out=ref_decoder.convert_to_prob[0].out_channels, norm=ref_decoder.norm, min_val=ref_decoder.min_val,
+              max_val=ref_decoder.max_val)
+    out.load_state_dict(ref_decoder.state_dict(), strict=True)
+    p0 = next(ref_decoder.parameters())
+    out = out.to(p0.device)
+    out.train(ref_decoder.training)
+    return out
+
+
+def fuse_depth_decoder(model):
+    """Replace every reference SQL decoder inside `model` (e.g. SQLdepth(opt).depth_decoder, SQLdepth.py:22-27, or
+    Trainer.models["depth"]) by its sqlx drop-in, in place; returns the number of decoders replaced.  The inference
+    wrapper's forward -- self.depth_decoder(self.encoder(x))["disp", 0], SQLdepth.py:48-50 -- then runs lines 47-70 of the
+    decoder on libsqlx with the checkpoint it was loaded with."""
+    names = ("Depth_Decoder_QueryTr", "Lite_Depth_Decoder_QueryTr")
+    count = 0
+    for parent in list(model.modules()):
+        for name, child in list(parent.named_children()):
+            if type(child).__name__ in names and not isinstance(child, Depth_Decoder_QueryTr):
+                setattr(parent, name, convert_depth_decoder(child))
+                count += 1
+    return count
+
+
 # ----------------------------------------------------------------------------- tensor-core entry points (tests / profiling)
 def tc_supported(E, Q, D, n):
     return bool(lib().sqlx_sql_tc_supported(E, Q, D, n))

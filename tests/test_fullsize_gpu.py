@@ -153,10 +153,12 @@ def _leaves(kw):
 @pytest.mark.parametrize("n,B", [(2, 12), (3, 4)])
 def test_photometric_noauto_tight(n, B):
     """--disable_automasking at the BASELINE frame sizes: no identity candidates, no tie-break noise, so the only arg-min
-    is between the reprojections of different sources.  Loss 1e-5; gradients held to 5e-3 of max |grad| (+ cosine
-    0.99999): a 1 % systematic gradient error cannot pass.  The floor of an fp32 evaluation
-    against float64 is 1e-3 (smooth images) at B = 2; the maximum over the 1.5 M cells of a full
-    batch measured 2.7e-3 on the B200."""
+    is between the reprojections of different sources.  Loss 1e-5.  Gradients: a SYSTEMATIC error cannot pass -- the
+    norm of every gradient must agree with the float64 oracle's to 2e-3 and its direction to cosine 0.99999 (a 1 % scale
+    or a 0.5 % rotation fails) -- while single elements are held to 1e-2 of max |grad| at scale 0 and
+    2e-2 at the coarser scales: there one low-resolution cell sums 16-256 pixel gradients of both signs, and the fp32
+    evaluation's own distance from float64 (1e-3 per pixel on smooth images) reached 1.1e-2 of the
+    maximum on the B200 (6.4e-3 at scale 0 of the 320x1024 case)."""
     import sqlx
     from oracle import sqldepth_oracle as O
     cfg = baseline_config(n, B=B)
@@ -176,5 +178,8 @@ def test_photometric_noauto_tight(n, B):
             flips = out[("argmin", s)].cpu().long() != ref[("argmin", s)]
             assert float(flips.float().mean()) < 2e-3
             a, b = _mask_flips(a, b, flips)
-        assert _rel(a, b) < 5e-3, (i, _rel(a, b))
+        coarse = 0 < i < len(cfg.scales)
+        assert _rel(a, b) < (2e-2 if coarse else 1e-2), (i, _rel(a, b))
         assert _cos(a, b) > 0.99999, (i, _cos(a, b))
+        nr = float(a.norm() / b.norm().clamp_min(1e-300))
+        assert abs(nr - 1.0) < 2e-3, (i, nr)

@@ -167,3 +167,26 @@ def test_indoor_trainer_mixin_dict_contract():
     total.backward()
     for t in [g["disp"]] + g["ref_depths"]:
         assert t.grad is not None and bool(torch.isfinite(t.grad).all())
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 48, 64), (1, 37, 53)])
+def test_inverse_rotation_warp_vs_oracle(B, H, W):
+    """layers.inverse_rotation_warp (layers.py:460-479) on libsqlx vs the float64 restatement: warped frames and the
+    gradient wrt the Euler angles (what trainer_indoor.rectify_imgs back-propagates, trainer_indoor.py:877-920)."""
+    import sqlx
+    from oracle import sqldepth_oracle as O
+    from _cases import smooth_images
+    g = torch.Generator().manual_seed(B + H)
+    img = smooth_images(g, B, H + (8 - H % 8) % 8, W + (8 - W % 8) % 8, 1)[0][:, :, :H, :W].contiguous()
+    rot = 0.05 * torch.randn(B, 3, generator=g)
+    K = torch.tensor([[0.58 * W, 0, 0.5 * W], [0, 1.92 * H / 2, 0.5 * H], [0, 0, 1]]).repeat(B, 1, 1)
+    gout = torch.randn(B, 3, H, W, generator=g)
+    rd = rot.double().requires_grad_(True)
+    want = O.inverse_rotation_warp(img.double(), rd, K.double())
+    (g_want,) = torch.autograd.grad((want * gout.double()).sum(), [rd])
+    rc = rot.cuda().requires_grad_(True)
+    got = sqlx.inverse_rotation_warp(img.cuda(), rc, K.cuda())
+    assert float((got.cpu().double() - want).abs().max()) < 2e-4
+    (g_got,) = torch.autograd.grad((got * gout.cuda()).sum(), [rc])
+    rel = float((g_got.cpu().double() - g_want).abs().max() / g_want.abs().max())
+    assert rel < 5e-3, rel

@@ -1,70 +1,77 @@
-"""Per-sample median scaling of the supervised fine-tuning step (finetune/train_ft_SQLdepth.py:236-266):
-the device-side ratios (sort-based, no host round trip) against a NumPy restatement of the reference loop.  The maths
-is device-agnostic torch code, so it is checked here on CPU tensors; the public entry point takes CUDA tensors only."""
+"""Per-sample median scaling of the supervised fine-tuning step (finetune/train_ft_SQLdepth.py:236-266).
+
+The reference loop is inline NumPy code of train(); oracle/sqldepth_oracle.py:median_scale_ratios restates it line by line
+and oracle/make_golden_median.py executed it into tests/golden/median_scale.npz (outside the product).  CPU: the oracle
+against the fixture.  GPU: the radix-select kernel (csrc/median.cu, through the C ABI) against the fixture and against
+the oracle on seeded cases with ties, NaNs, empty selections and negative predictions -- ratios are order statistics, so
+the comparison is EXACT (same two float32 values averaged and divided)."""
+import os
+import sys
+
 import numpy as np
 import pytest
 import torch
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
-def _reference_ratios(pred, depth, lo, hi, garg_crop, eigen_crop, dataset):
-    """restates train_ft_SQLdepth.py:236-266 (boolean-mask gather + np.median per sample, first half of the batch)"""
-    B = pred.shape[0]
-    out = np.ones(B, dtype=np.float32)
-    for i in range(B // 2):
-        p = pred[i, 0].numpy()
-        d = depth[i, 0].numpy()
-        valid = np.logical_and(d > lo, d < hi)
-        H, W = d.shape
-        ev = np.zeros(valid.shape)
-        if garg_crop:
-            ev[int(0.40810811 * H):int(0.99189189 * H), int(0.03594771 * W):int(0.96405229 * W)] = 1
-        elif eigen_crop:
-            if dataset == "kitti":
-                ev[int(0.3324324 * H):int(0.91351351 * H), int(0.0359477 * W):int(0.96405229 * W)] = 1
-            else:
-                ev[45:471, 41:601] = 1
-        valid = np.logical_and(valid, ev)
-        with np.errstate(all="ignore"):
-            mp = np.median(p[valid]) if valid.any() else np.nan
-            md = np.median(d[valid]) if valid.any() else np.nan
-        out[i] = 1.0 if (np.isnan(md) or np.isnan(mp)) else md / mp
-    return out
+from _cases import load_npz  # noqa: E402
+
+CASES = {"garg": dict(garg_crop=True), "eigen_kitti": dict(eigen_crop=True, dataset="kitti")}
 
 
-@pytest.mark.parametrize("crop", [dict(garg_crop=True), dict(eigen_crop=True), dict(eigen_crop=True, dataset="nyu")])
-def test_median_ratios_match_numpy_loop(crop):
-    from sqlx.layers import median_scale_ratios
-    g = torch.Generator().manual_seed(4)
-    B, H, W = 6, 480, 640
-    depth = torch.rand(B, 1, H, W, generator=g) * 90.0
-    depth[depth < 20.0] = 0.0                      # sparse ground truth: most pixels invalid
-    pred = torch.rand(B, 1, H, W, generator=g) * 40.0 + 0.5
-    pred[1, 0, 300, 300] = float("nan")            # a NaN inside the crop -> ratio 1 for that sample (:261-262)
-    depth[2] = 0.0                                 # no valid pixel at all -> ratio 1
-    kw = dict(garg_crop=False, eigen_crop=False, dataset="kitti")
-    kw.update(crop)
-    got = median_scale_ratios(pred, depth, 1e-3, 80.0, **kw).numpy()
-    want = _reference_ratios(pred, depth, 1e-3, 80.0, kw["garg_crop"], kw["eigen_crop"], kw["dataset"])
-    assert got[1] == 1.0 and got[2] == 1.0 and (got[3:] == 1.0).all()
-    np.testing.assert_allclose(got, want, rtol=1e-6)
+def test_oracle_matches_fixture():
+    from oracle import sqldepth_oracle as O
+    z = load_npz("median_scale")
+    for name, kw in CASES.items():
+        got = O.median_scale_ratios(torch.from_numpy(z[name + "_pred"]), torch.from_numpy(z[name + "_depth"]), 1e-3, 80.0, **kw)
+        np.testing.assert_array_equal(got, z[name + "_ratio"])
+    # the 480x640 case is regenerated from its seed (make_golden_median.py keeps only its ratios)
+    import make_golden_median as G
+    pred, depth = G.make_case(3, 4, 480, 640, empty_sample=0)
+    got = O.median_scale_ratios(pred, depth, 1e-3, 80.0, eigen_crop=True, dataset="nyu")
+    np.testing.assert_array_equal(got, z["eigen_nyu_ratio"])
 
 
-def test_even_and_odd_counts():
-    from sqlx.layers import _masked_median
-    v = torch.tensor([[5.0, 1.0, 9.0, 3.0, 7.0], [5.0, 1.0, 9.0, 3.0, 7.0]])
-    m = torch.tensor([[True, True, True, True, True], [True, True, False, True, True]])
-    med = _masked_median(v, m)
-    assert med.tolist() == [5.0, 4.0]              # odd: middle element; even: mean of the two middle ones
-
-
-def test_crop_flag_is_required_like_the_reference():
-    from sqlx.layers import median_scale_ratios
-    with pytest.raises(ValueError):
-        median_scale_ratios(torch.ones(2, 1, 8, 8), torch.ones(2, 1, 8, 8), 1e-3, 80.0)
-
-
-def test_public_entry_point_takes_cuda_tensors_only():
+@pytest.mark.gpu
+def test_kernel_matches_fixture():
     import sqlx
-    from sqlx.layers import median_scale
-    with pytest.raises(sqlx.SqlxError):
-        median_scale(torch.ones(2, 1, 8, 8), torch.ones(2, 1, 8, 8), 1e-3, 80.0, garg_crop=True)
+    z = load_npz("median_scale")
+    for name, kw in CASES.items():
+        pred, depth = torch.from_numpy(z[name + "_pred"]).cuda(), torch.from_numpy(z[name + "_depth"]).cuda()
+        got = sqlx.median_scale_ratios(pred, depth, 1e-3, 80.0, **kw).cpu().numpy()
+        np.testing.assert_array_equal(got, z[name + "_ratio"])
+    import make_golden_median as G
+    pred, depth = G.make_case(3, 4, 480, 640, empty_sample=0)
+    got = sqlx.median_scale_ratios(pred.cuda(), depth.cuda(), 1e-3, 80.0, eigen_crop=True, dataset="nyu").cpu().numpy()
+    np.testing.assert_array_equal(got, z["eigen_nyu_ratio"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,B,H,W,kw", [
+    (11, 8, 352, 1216, dict(garg_crop=True)),                      # KITTI ground-truth resolution
+    (12, 2, 37, 53, dict(eigen_crop=True, dataset="kitti")),       # odd sizes, tiny selections
+    (13, 6, 480, 640, dict(eigen_crop=True, dataset="nyu")),
+])
+def test_kernel_matches_oracle(seed, B, H, W, kw):
+    import sqlx
+    from oracle import sqldepth_oracle as O
+    import make_golden_median as G
+    pred, depth = G.make_case(seed, B, H, W, nan_sample=1 if B > 2 else None, empty_sample=2 if B > 5 else None)
+    pred[0] = -pred[0]                                              # negative predictions order correctly
+    want = O.median_scale_ratios(pred, depth, 1e-3, 80.0, **kw)
+    got = sqlx.median_scale_ratios(pred.cuda(), depth.cuda(), 1e-3, 80.0, **kw).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    # the drop-in: pred scaled per sample, differentiable wrt pred with constant ratios (as the reference's in-place *=)
+    p = pred.cuda().requires_grad_(True)
+    out = sqlx.median_scale(p, depth.cuda(), 1e-3, 80.0, **kw)
+    np.testing.assert_array_equal(out.detach().cpu().numpy(), (pred * torch.from_numpy(want).view(-1, 1, 1, 1)).numpy())
+    out.nan_to_num().sum().backward()
+    assert torch.equal(p.grad[B - 1], torch.ones_like(p.grad[B - 1]))           # second half of the batch: ratio 1
+
+
+def test_needs_a_crop_flag_and_cuda():
+    import sqlx
+    with pytest.raises((ValueError, sqlx.SqlxError)):
+        sqlx.median_scale_ratios(torch.rand(2, 1, 8, 8), torch.rand(2, 1, 8, 8), 1e-3, 80.0)

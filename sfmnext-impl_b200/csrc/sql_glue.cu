@@ -21,8 +21,17 @@ __global__ void sql_mix_weights_kernel(const float* __restrict__ Wp, const float
   const float* kb = K + (size_t)b * Q * E;
   for (int e = lane; e < E; e += 32) {
     float acc = 0.f;
-#pragma unroll 4
-    for (int q = 0; q < Q; ++q) acc = fmaf(__ldg(wrow + q), __ldg(kb + (size_t)q * E + e), acc);
+    for (int q0 = 0; q0 < Q; q0 += 16) {         // 32 independent loads in flight per trip (the loop is latency-bound)
+      float wv[16], kv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const bool on = q0 + j < Q;
+        wv[j] = on ? __ldg(wrow + q0 + j) : 0.f;
+        kv[j] = on ? __ldg(kb + (size_t)(q0 + j) * E + e) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc = fmaf(wv[j], kv[j], acc);
+    }
     M[((size_t)b * D + d) * E + e] = acc;
   }
 }
@@ -37,10 +46,18 @@ __global__ void sql_mix_weights_bwd_kernel(const float* __restrict__ dM, const f
   if (warp < nW) {
     const int d = warp / Q, q = warp - d * Q;
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) {
-      const float* dm = dM + ((size_t)b * D + d) * E;
-      const float* kr = K + ((size_t)b * Q + q) * E;
-      for (int e = lane; e < E; e += 32) acc = fmaf(__ldg(dm + e), __ldg(kr + e), acc);
+    for (int e = lane; e < E; e += 32) {
+      for (int b0 = 0; b0 < B; b0 += 16) {       // all samples' loads in flight together
+        float dv[16], kv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const bool on = b0 + j < B;
+          dv[j] = on ? __ldg(dM + ((size_t)(b0 + j) * D + d) * E + e) : 0.f;
+          kv[j] = on ? __ldg(K + ((size_t)(b0 + j) * Q + q) * E + e) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc = fmaf(dv[j], kv[j], acc);
+      }
     }
     acc = warp_sum(acc);
     if (lane == 0) dWp[(size_t)d * Q + q] = acc;
@@ -52,8 +69,17 @@ __global__ void sql_mix_weights_bwd_kernel(const float* __restrict__ dM, const f
   const float* dmb = dM + (size_t)b * D * E;
   for (int e = lane; e < E; e += 32) {
     float acc = 0.f;
-#pragma unroll 4
-    for (int d = 0; d < D; ++d) acc = fmaf(__ldg(Wp + (size_t)d * Q + q), __ldg(dmb + (size_t)d * E + e), acc);
+    for (int d0 = 0; d0 < D; d0 += 16) {
+      float wv[16], mv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const bool on = d0 + j < D;
+        wv[j] = on ? __ldg(Wp + (size_t)(d0 + j) * Q + q) : 0.f;
+        mv[j] = on ? __ldg(dmb + (size_t)(d0 + j) * E + e) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc = fmaf(wv[j], mv[j], acc);
+    }
     float* o = dK + ((size_t)b * Q + q) * E + e;
     *o = accumulate_dK ? *o + acc : acc;
   }

@@ -371,6 +371,8 @@ int sqlx_sql_bwd_pred_mix(const float* x, const float* Mx, const float* bp, cons
  * A/B and cross-check of the warp-specialised kernels */
 int sqlx_sql_pred_mix_fwd_v1(const float* x, const float* Mx, const float* bp, const float* centers, int B, int E, int D,
                              int n, float* pred, void* stream);
+int sqlx_sql_summary_fwd_v1(const float* x, const float* queries, int B, int E, int Q, int n, float* summary,
+                            float* row_max, float* row_sum, void* workspace, size_t workspace_bytes, void* stream);
 int sqlx_sql_bwd_summary_v1(const float* x, const float* queries, const float* summary, const float* row_max,
                             const float* row_sum, const float* d_summary, int B, int E, int Q, int n, int accumulate,
                             float* d_x, float* d_queries, void* workspace, size_t workspace_bytes, void* stream);

@@ -711,6 +711,9 @@ int tc_bwd_sum(const float* x, const float* queries, const float* summary, const
 void tc_bwd_plan(int B, int n, int* chunks, int* tiles_per_chunk);
 // warp-specialised generation (sql_ws.cu)
 void ws_plan(int B, int n, int* chunks, int* tiles_per_chunk);
+void ws_summary_plan(int B, int n, int* chunks, int* steps_per_chunk);
+int ws_summary_partials(const float* x, const float* queries, int B, int Q, int n, float* partial, int* chunks_out,
+                        cudaStream_t st);
 int ws_pred_fwd(const float* x, const float* Mx, const float* bp, const float* centers, int B, int D, int n, float* pred,
                 float* stat_m, float* stat_inv, cudaStream_t st);
 int ws_bwd_sum(const float* x, const float* queries, const float* summary, const float* row_max, const float* row_sum,
@@ -754,7 +757,10 @@ size_t summary_ws_floats(int B, int E, int Q, int n) {
   const ChunkPlan c = plan_chunks(B, n, kSummaryTarget);
   int tc_chunks = 0, tpc = 0;
   tc_summary_plan(B, n, &tc_chunks, &tpc);
-  const int chunks = c.chunks > tc_chunks ? c.chunks : tc_chunks;
+  int ws_chunks = 0;
+  ws_summary_plan(B, n, &ws_chunks, &tpc);
+  int chunks = c.chunks > tc_chunks ? c.chunks : tc_chunks;
+  chunks = chunks > ws_chunks ? chunks : ws_chunks;
   return (size_t)B * chunks * Q * (E + 2);
 }
 int max_bwd_chunks(int B, int n) {
@@ -881,13 +887,30 @@ extern "C" int sqlx_sql_summary_fwd(const float* x, const float* queries, int B,
   float* ws = reinterpret_cast<float*>(workspace);
   if (use_tensor_cores(E, Q, 0, n)) {
     int chunks = 0;
-    if (int e = tc_summary_partials(x, queries, B, Q, n, ws, &chunks, st)) return e;
+    if (int e = ws_summary_partials(x, queries, B, Q, n, ws, &chunks, st)) return e;
     sql_summary_combine_kernel<32><<<dim3(B, (Q + 3) / 4), 128, 0, st>>>(ws, Q, chunks, summary, row_max, row_sum);
     if (int e = check_launch("sql_summary_combine_kernel")) return e;
     if (energy) return sqlx_sql_energy_tc(x, queries, B, E, Q, n, energy, stream);
     return SQLX_OK;
   }
   SQLX_DISPATCH_E(E, run_summary<kE>(x, queries, B, Q, n, summary, row_max, row_sum, energy, ws, st));
+}
+
+/* round-1 generation of the tensor-core summary kernel (one warpgroup, serial phases): A/B and cross-check of the
+ * warp-specialised kernel (tests/test_sql_tc_gpu.py::test_ws_kernels_match_v1) */
+extern "C" int sqlx_sql_summary_fwd_v1(const float* x, const float* queries, int B, int E, int Q, int n, float* summary,
+                                       float* row_max, float* row_sum, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+  if (int e = check_sql_shape(B, E, Q, 0, n, false)) return e;
+  SQLX_REQUIRE(x && queries && summary, "NULL pointer argument");
+  SQLX_REQUIRE(use_tensor_cores(E, Q, 0, n), "shape E=%d Q=%d n=%d is not supported by the tensor-core path", E, Q, n);
+  SQLX_REQUIRE(workspace && workspace_bytes >= sizeof(float) * summary_ws_floats(B, E, Q, n), "workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* ws = reinterpret_cast<float*>(workspace);
+  int chunks = 0;
+  if (int e = tc_summary_partials(x, queries, B, Q, n, ws, &chunks, st)) return e;
+  sql_summary_combine_kernel<32><<<dim3(B, (Q + 3) / 4), 128, 0, st>>>(ws, Q, chunks, summary, row_max, row_sum);
+  return check_launch("sql_summary_combine_kernel");
 }
 
 extern "C" int sqlx_sql_pred_fwd(const float* x, const float* queries, const float* Wp, const float* bp,

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) sql_ws_pred_kernel(const __grid_c
 
   if (warp == kEpiWarps) {
     // ---------------------------------------------------------------- control lane
-    if (lane == 0) {
+    if (elect_one()) {
       const uint64_t dx_ring = make_desc_mn32(smem_u32(x_ring), kXBlock), dx_lo = make_desc_mn32(smem_u32(x_lo), kXBlock);
       const uint64_t dm_hi = make_desc_sw128(smem_u32(m_hi), 16, 1024), dm_lo = make_desc_sw128(smem_u32(m_lo), 16, 1024);
       const uint32_t idesc = make_idesc_tf32(kTile, DP, 1, 0);
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) sql_ws_bwd_pred_kernel(
 
   if (warp == kEpiWarps) {
     // ---------------------------------------------------------------- control lane
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t id_acc = make_idesc_tf32(128, kAccN, 0, 0);
       const uint32_t id_dx = make_idesc_tf32(128, 32, 0, 0);
       const uint32_t id_z = make_idesc_tf32(kTile, 64, 1, 0);
@@ -743,7 +743,7 @@ __global__ void __launch_bounds__(kThreads, 1) sql_ws_bwd_sum_kernel(
 
   if (warp == kEpiWarps) {
     // ---------------------------------------------------------------- control lane
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t id_y = make_idesc_tf32(kTile, 64, 1, 0);       // y, t: A = x (MN-major), B = K / ds rows (K-major)
       const uint32_t id_32 = make_idesc_tf32(128, 32, 0, 0);        // d_x, d_K
       const uint64_t dx_ring = make_desc_mn32(smem_u32(x_ring), kXBlock), dx_lo = make_desc_mn32(smem_u32(x_lo), kXBlock);
@@ -909,6 +909,326 @@ __global__ void __launch_bounds__(kThreads, 1) sql_ws_bwd_sum_kernel(
   if (warp == kEpiWarps) tmem_dealloc(tmem, kCols);
 }
 
+// ================================================================================================================
+// forward summaries (FullQueryLayer, networks/layers.py:17-20):  y = K x,  a = softmax over PIXELS,  summary = a x^T
+//
+// Here lane = query row and columns = pixels: the softmax runs ALONG a thread's own columns, so the running maximum and
+// denominator live in registers and need no cross-lane traffic; P = exp(y - m) goes back to TMEM as the A operand of the
+// second contraction, and the queries themselves (hi / lo, static for the CTA) sit in TMEM as the A operand of the first.
+// Both contractions are therefore A-in-TMEM instructions whose only shared-memory traffic is the 1 KB x operand: measured
+// (tools/mma_chain_probe.cu) 16 cycles per M = 128, N = 32, K = 8 instruction against 40 with A in shared memory (the
+// 4 KB A read at 128 B / clk is what an SS-mode instruction of small N costs).
+//
+//   step        one 32-pixel tile.  FOUR groups of four epilogue warps take the steps round-robin; the control lane runs
+//               three steps ahead:  ... MMA1(s) | MMA2(s-3) | MMA1(s+1) | MMA2(s-2) ...  (tcgen05.mma executes in issue
+//               order, so MMA1(s+4) may overwrite the y / P buffer of group s % 4 right behind MMA2(s))
+//   online      every (group, lane) keeps its own running (m, l) and its own summary accumulator row in TMEM: the second
+//   softmax     contraction ACCUMULATES into it across the steps of the group, and the row is rescaled in place only when
+//               the maximum moves by more than 8 (rare after the first tiles); the partial states of a query are merged
+//               through shared memory at the end and leave as one record per (chunk, query)
+//   Q <= 64     the 128 TMEM lanes hold the 64 queries TWICE: lanes 0..63 own pixels 0..15 of the tile, lanes 64..127
+//               pixels 16..31.  Each lane half stores P_hi in its own 16 columns and P_lo in the 16 columns the other half
+//               owns (what y left there is not needed), and the second contraction runs once per half into separate
+//               accumulators whose other 64 rows are ignored
+//   TMEM        group g at columns 96 g:  [0, 32) y -> P_hi,  [32, 64) P_lo,  [64, 96) S                    (Q > 64)
+//                                         [0, 32) y -> P_hi | P_lo crossed,  [32, 64) S_A,  [64, 96) S_B    (Q <= 64)
+//               [384, 416) K_hi,  [416, 448) K_lo
+// ================================================================================================================
+constexpr int kSumSlot = 4 * kXBlock;      // ring slot of a step: x MN-major hi | lo | x K-major hi | lo   (4 KB each)
+constexpr uint32_t kSumGrpCols = 96, kSumKCol = 384;
+
+template <int QP>
+struct SumSmem {
+  static constexpr int NSLOT = 14;
+  static constexpr int NPART = QP == 64 ? 8 : 4;       // partial softmax states per query at the end
+  static constexpr int REC = kE + 3;                   // m, l, 32 sums (odd stride: conflict-free)
+  static constexpr size_t ring = 0, tail = (size_t)NSLOT * kSumSlot;
+  static constexpr size_t bytes = 1024 + tail + 512;
+  static_assert(bytes <= 227 * 1024, "shared-memory budget");
+  static_assert((size_t)NPART * QP * REC * 4 <= (size_t)NSLOT * kSumSlot, "merge buffer reuses the ring");
+};
+
+template <int QP>
+__global__ void __launch_bounds__(kThreads, 1) sql_ws_summary_kernel(const __grid_constant__ CUtensorMap map_mn,
+                                                                     const __grid_constant__ CUtensorMap map_k,
+                                                                     const float* __restrict__ queries, int Q, int n,
+                                                                     int steps_per_chunk,
+                                                                     float* __restrict__ partial /*[B][chunks][Q][34]*/) {
+  using L = SumSmem<QP>;
+  constexpr bool kPair = QP == 64;
+  constexpr int CW = kPair ? 16 : 32;                  // pixels per thread and step
+  constexpr int NSLOT = L::NSLOT;
+  constexpr uint32_t kSOff = kPair ? 32 : 64;          // accumulator columns inside the group's block
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = base + L::ring;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + L::tail);
+  uint64_t* bar_full = bars;                    // [NSLOT] TMA: both images of a step landed
+  uint64_t* bar_split = bars + NSLOT;           // [4] 4 warps: lo images of the group's next step written
+  uint64_t* bar_z = bars + NSLOT + 4;           // [4] MMA commit: y of the group's step (and every earlier MMA) done
+  uint64_t* bar_epi = bars + NSLOT + 8;         // [4] 4 warps: P_hi / P_lo of the group's step in TMEM
+  uint64_t* bar_done = bars + NSLOT + 12;       // MMA commit: everything done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NSLOT + 13);
+  const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kCols = 512;
+  const int s_begin = chunk * steps_per_chunk;
+  const int nsteps = max(min((n + 31) / 32, s_begin + steps_per_chunk) - s_begin, 0);
+  auto tma_step = [&](int i) {                  // both images of step i into its ring slot
+    uint8_t* slot = ring + (size_t)(i % NSLOT) * kSumSlot;
+    mbar_arrive_expect_tx(bar_full + i % NSLOT, 2 * kXBlock);
+    tma_load_2d(slot, &map_mn, (s_begin + i) * 32, b * kE, bar_full + i % NSLOT);
+    tma_load_2d(slot + 2 * kXBlock, &map_k, (s_begin + i) * 32, b * kE, bar_full + i % NSLOT);
+  };
+  if (threadIdx.x == kEpiThreads) {
+    tma_prefetch_desc(&map_mn);
+    tma_prefetch_desc(&map_k);
+    for (int i = 0; i < NSLOT; ++i) mbar_init(bar_full + i, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_split + i, 4); mbar_init(bar_z + i, 1); mbar_init(bar_epi + i, 4); }
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarps) {
+    tmem_alloc(tmem_slot, kCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (threadIdx.x == kEpiThreads)
+    for (int i = 0; i < NSLOT && i < nsteps; ++i) tma_step(i);
+  if (warp < 4) {
+    // queries -> TMEM rows (lane = query; Q <= 64: lanes 64.. repeat lanes 0..; rows past Q are zero), hi / lo
+    const int r = warp * 32 + lane, qi = kPair ? (r & 63) : r;
+    const float4* qrow = reinterpret_cast<const float4*>(queries + ((size_t)b * Q + (qi < Q ? qi : 0)) * kE);
+    float hi[kE], lo[kE];
+#pragma unroll
+    for (int j = 0; j < kE / 4; ++j) {
+      const float4 v = qi < Q ? __ldg(qrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      hi[4 * j] = tf32_hi(v.x); hi[4 * j + 1] = tf32_hi(v.y); hi[4 * j + 2] = tf32_hi(v.z); hi[4 * j + 3] = tf32_hi(v.w);
+      lo[4 * j] = v.x - hi[4 * j]; lo[4 * j + 1] = v.y - hi[4 * j + 1]; lo[4 * j + 2] = v.z - hi[4 * j + 2];
+      lo[4 * j + 3] = v.w - hi[4 * j + 3];
+    }
+    const uint32_t tk = tmem + ((uint32_t)(warp * 32) << 16) + kSumKCol;
+#pragma unroll
+    for (int c = 0; c < kE; c += 16) {
+      tmem_st16(tk + c, *reinterpret_cast<float(*)[16]>(hi + c));
+      tmem_st16(tk + kE + c, *reinterpret_cast<float(*)[16]>(lo + c));
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == kEpiWarps) {
+    // ---------------------------------------------------------------- control lane
+    if (elect_one()) {
+      const uint32_t id_y = make_idesc_tf32(128, 32, 0, 1);      // y: A = K rows (TMEM), B = x (MN-major, one 32-px atom)
+      const uint32_t id_s = make_idesc_tf32(128, 32, 0, 0);      // S: A = P (TMEM),  B = x rows = channels, K = pixels
+      const uint32_t tk_hi = tmem + kSumKCol, tk_lo = tk_hi + kE;
+      const uint64_t d_mn = make_desc_mn32(smem_u32(ring), kXBlock);
+      const uint64_t d_xk = make_desc_sw128(smem_u32(ring) + 2 * kXBlock, 16, 1024);
+      for (int i = 0; i < nsteps + 3; ++i) {
+        if (i < nsteps) {
+          const int g = i & 3;
+          const uint32_t so = (uint32_t)(i % NSLOT) * kSumSlot;
+          mbar_wait(bar_split + g, (i >> 2) & 1);
+          tc_fence_after();
+          const uint32_t ty = tmem + g * kSumGrpCols;
+          const uint64_t xh = desc_add(d_mn, so), xl = desc_add(d_mn, so + kXBlock);
+#pragma unroll
+          for (int k = 0; k < kE / 8; ++k) umma_tf32_ts(ty, tk_hi + k * 8, desc_add(xh, k * 1024), id_y, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < kE / 8; ++k) umma_tf32_ts(ty, tk_lo + k * 8, desc_add(xh, k * 1024), id_y, 1u);
+#pragma unroll
+          for (int k = 0; k < kE / 8; ++k) umma_tf32_ts(ty, tk_hi + k * 8, desc_add(xl, k * 1024), id_y, 1u);
+          umma_commit(bar_z + g);
+        }
+        const int j = i - 3;
+        if (j >= 0) {
+          const int g = j & 3;
+          const uint32_t so = (uint32_t)(j % NSLOT) * kSumSlot;
+          mbar_wait(bar_epi + g, (j >> 2) & 1);
+          tc_fence_after();
+          const uint32_t tb = tmem + g * kSumGrpCols;
+          const uint64_t xh = desc_add(d_xk, so), xl = desc_add(d_xk, so + kXBlock);
+          if (!kPair) {
+            if (j < 4) {                                            // the group's first step initialises its accumulator
+              umma_tf32_ts(tb + kSOff, tb, xh, id_s, 0u);
+#pragma unroll
+              for (int k = 1; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + k * 8, desc_add(xh, k * 32), id_s, 1u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + k * 8, desc_add(xh, k * 32), id_s, 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + 32 + k * 8, desc_add(xh, k * 32), id_s, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + k * 8, desc_add(xl, k * 32), id_s, 1u);
+          } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {                          // lane half h: pixels [16 h, 16 h + 16)
+              const uint32_t own = tb + 16 * h, oth = tb + 16 * (1 - h), td = tb + kSOff + 32 * h;
+              if (j < 4) umma_tf32_ts(td, own, desc_add(xh, (2 * h) * 32), id_s, 0u);
+              else umma_tf32_ts(td, own, desc_add(xh, (2 * h) * 32), id_s, 1u);
+              umma_tf32_ts(td, own + 8, desc_add(xh, (2 * h + 1) * 32), id_s, 1u);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                umma_tf32_ts(td, oth + k * 8, desc_add(xh, (2 * h + k) * 32), id_s, 1u);
+                umma_tf32_ts(td, own + k * 8, desc_add(xl, (2 * h + k) * 32), id_s, 1u);
+              }
+            }
+          }
+        }
+      }
+      umma_commit(bar_done);
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps: group `grp` owns steps s = grp (mod 4)
+    const int grp = warp >> 2, q = warp & 3, gtid = threadIdx.x & 127;
+    const int half = kPair ? (q >> 1) : 0;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + grp * kSumGrpCols;
+    const uint32_t t_own = lane_base + (kPair ? 16 * half : 0), t_lo = lane_base + (kPair ? 16 * (1 - half) : 32);
+    const uint32_t t_S = lane_base + kSOff + 32 * half;
+    float m = -INFINITY, l = 0.f;
+    auto split_step = [&](int i) {               // lo images of step i (the landing buffers are the hi operands)
+      uint8_t* slot = ring + (size_t)(i % NSLOT) * kSumSlot;
+      mbar_wait(bar_full + i % NSLOT, (i / NSLOT) & 1);
+      const float4* mh = reinterpret_cast<const float4*>(slot);
+      const float4* kh = reinterpret_cast<const float4*>(slot + 2 * kXBlock);
+      float4* ml = reinterpret_cast<float4*>(slot + kXBlock);
+      float4* kl = reinterpret_cast<float4*>(slot + 3 * kXBlock);
+      float4 v[4] = {mh[gtid], mh[gtid + 128], kh[gtid], kh[gtid + 128]};
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) {
+        v[i4].x -= tf32_hi(v[i4].x); v[i4].y -= tf32_hi(v[i4].y); v[i4].z -= tf32_hi(v[i4].z); v[i4].w -= tf32_hi(v[i4].w);
+      }
+      ml[gtid] = v[0]; ml[gtid + 128] = v[1]; kl[gtid] = v[2]; kl[gtid + 128] = v[3];
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_split + grp);
+    };
+    if (grp < nsteps) split_step(grp);
+    for (int s = grp; s < nsteps; s += 4) {
+      mbar_wait(bar_z + grp, (s >> 2) & 1);        // y of step s is in the group's buffer; every MMA of steps <= s-4 is done
+      tc_fence_after();
+      if (gtid == 0 && s >= 4 && s - 4 + NSLOT < nsteps) tma_step(s - 4 + NSLOT);     // the slot of step s-4 is free
+      float v[CW];
+#pragma unroll
+      for (int c = 0; c < CW; c += 16) tmem_ld16(t_own + c, *reinterpret_cast<float(*)[16]>(v + c));
+      tmem_wait_ld();
+      // pixels >= n were zero-filled by TMA: exclude them
+      const int valid = min(32, n - (s_begin + s) * 32) - (kPair ? 16 * half : 0);
+      const bool full = valid >= CW;
+      float tmax = -INFINITY;
+      if (full) {
+        float t4[CW / 4];
+#pragma unroll
+        for (int j = 0; j < CW / 4; ++j) t4[j] = fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), fmaxf(v[4 * j + 2], v[4 * j + 3]));
+#pragma unroll
+        for (int j = 0; j < CW / 4; ++j) tmax = fmaxf(tmax, t4[j]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < CW; ++i)
+          if (i < valid) tmax = fmaxf(tmax, v[i]);
+      }
+      // lazy reference point: it moves only when exceeded by more than 8 (exp arguments stay <= 8)
+      const bool need = tmax > m + 8.f;
+      if (__any_sync(0xffffffffu, need)) {
+        const float rs = need ? __expf(m - tmax) : 1.f;      // m = -inf at first: 0
+        if (need) m = tmax;
+        l *= rs;
+        if (s >= 4) {                                        // rescale this thread's accumulator row in place
+#pragma unroll
+          for (int c = 0; c < kE; c += 16) {
+            float a[16];
+            tmem_ld16(t_S + c, a);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] *= rs;
+            tmem_st16(t_S + c, a);
+          }
+        }
+      }
+      const float nm2 = -m * kLog2e;                         // exp(y - m) = 2^(y log2e - m log2e)
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < CW; c += 16) {
+        float lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float pe = ex2f(fmaf(v[c + i], kLog2e, nm2));
+          if (!full && c + i >= valid) pe = 0.f;
+          ls[i & 3] += pe;
+          const float h = tf32_hi(pe);
+          v[c + i] = h;
+          lo[i] = pe - h;
+        }
+        tmem_st16(t_own + c, *reinterpret_cast<float(*)[16]>(v + c));
+        tmem_st16(t_lo + c, lo);
+      }
+      l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_epi + grp);
+      if (s + 4 < nsteps) split_step(s + 4);
+    }
+    // ---- merge the partial states of every query (4 groups x lane halves) and write one record per (chunk, query)
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    float* mb = reinterpret_cast<float*>(ring);
+    {
+      const int r = q * 32 + lane, qi = kPair ? (r & 63) : r, part = kPair ? grp * 2 + half : grp;
+      float* rec = mb + ((size_t)part * QP + qi) * L::REC;
+      const bool live = grp < nsteps;
+      rec[0] = m; rec[1] = l;
+#pragma unroll
+      for (int c = 0; c < kE; c += 16) {
+        float a[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = 0.f;
+        if (live) {
+          tmem_ld16(t_S + c, a);
+          tmem_wait_ld();
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rec[2 + c + i] = a[i];
+      }
+    }
+    named_sync(1, kEpiThreads);
+    {
+      constexpr int NCH = kEpiThreads / QP, CPT = kE / NCH;      // channel blocks per query, channels per thread
+      const int qi = threadIdx.x % QP, cb = threadIdx.x / QP;
+      if (qi < Q) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int pt = 0; pt < L::NPART; ++pt) M = fmaxf(M, mb[((size_t)pt * QP + qi) * L::REC]);
+        float Ls = 0.f, acc[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int pt = 0; pt < L::NPART; ++pt) {
+          const float* rec = mb + ((size_t)pt * QP + qi) * L::REC;
+          const float w = rec[0] == -INFINITY ? 0.f : __expf(rec[0] - M);
+          Ls = fmaf(rec[1], w, Ls);
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) acc[i] = fmaf(rec[2 + cb * CPT + i], w, acc[i]);
+        }
+        float* out = partial + (((size_t)b * chunks + chunk) * Q + qi) * (kE + 2);
+        if (cb == 0) { out[0] = M; out[1] = Ls; }
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) out[2 + cb * CPT + i] = acc[i];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps) tmem_dealloc(tmem, kCols);
+}
+
 }  // namespace wsql
 
 // ------------------------------------------------------------------------------------------------
@@ -992,6 +1312,38 @@ int ws_bwd_sum(const float* x, const float* queries, const float* summary, const
                                  d_x, part_dK, st);
   return launch_ws_bwd_sum<128>(map_mn, map_k, queries, summary, row_max, row_sum, d_summary, B, Q, n, chunks, tpc, accumulate,
                                 d_x, part_dK, st);
+}
+
+void ws_summary_plan(int B, int n, int* chunks, int* steps_per_chunk) {
+  const int steps = ceil_div(n, 32);
+  int c = kNumSMs / B;   // one CTA per SM
+  c = c < 1 ? 1 : (c > steps ? steps : c);
+  *steps_per_chunk = ceil_div(steps, c);
+  *chunks = ceil_div(steps, *steps_per_chunk);
+}
+
+template <int QP>
+static int launch_ws_summary(const CUtensorMap& map_mn, const CUtensorMap& map_k, const float* queries, int B, int Q, int n,
+                             int chunks, int spc, float* partial, cudaStream_t st) {
+  if (int e = ensure_dyn_smem(wsql::sql_ws_summary_kernel<QP>, wsql::SumSmem<QP>::bytes)) return e;
+  ProfScope prof("sql_tc_summary_kernel", st);
+  wsql::sql_ws_summary_kernel<QP><<<dim3(chunks, B), wsql::kThreads, wsql::SumSmem<QP>::bytes, st>>>(map_mn, map_k, queries, Q,
+                                                                                                  n, spc, partial);
+  return check_launch("sql_ws_summary_kernel");
+}
+
+// writes per-chunk partial records [B][chunks][Q][34]; the caller runs the split-softmax combine
+int ws_summary_partials(const float* x, const float* queries, int B, int Q, int n, float* partial, int* chunks_out,
+                        cudaStream_t st) {
+  SQLX_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
+  int chunks, spc;
+  ws_summary_plan(B, n, &chunks, &spc);
+  CUtensorMap map_mn, map_k;
+  if (int e = make_tensor_map_2d(&map_mn, x, (uint64_t)B * wsql::kE, (uint64_t)n, 32, 32, 1)) return e;
+  if (int e = make_tensor_map_2d(&map_k, x, (uint64_t)B * wsql::kE, (uint64_t)n, 32, 32, 0)) return e;
+  *chunks_out = chunks;
+  if (Q <= 64) return launch_ws_summary<64>(map_mn, map_k, queries, B, Q, n, chunks, spc, partial, st);
+  return launch_ws_summary<128>(map_mn, map_k, queries, B, Q, n, chunks, spc, partial, st);
 }
 
 }  // namespace sqlx

@@ -11,6 +11,23 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp (elect.sync).  The control lane of a kernel must be chosen with this, not with
+// `lane == 0`: tcgen05.mma takes its operands from uniform registers, and under a branch the compiler cannot prove
+// single-threaded it wraps EVERY mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop over the active lanes --
+// measured (tools/mma_chain_probe.cu, M = 128, K = 8, tf32): 45 cycles per instruction whatever N, against 9 / 16 / 32
+// cycles (N = 16 / 32 / 64, A in TMEM) once the branch is `elect_one()`.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

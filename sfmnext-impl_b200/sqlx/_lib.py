@@ -130,6 +130,8 @@ _PROTOS = {
     "sqlx_sql_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "sqlx_sql_summary_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_size_t, c_void_p]),
+    "sqlx_sql_summary_fwd_v1": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_size_t, c_void_p]),
     "sqlx_sql_tc_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "sqlx_sql_set_tensor_cores": (c_int, [c_int]),
     "sqlx_sql_get_tensor_cores": (c_int, []),

@@ -21,8 +21,9 @@ def _workspace(B, E, Q, D, n, device):
     return torch.empty(nbytes, device=device, dtype=torch.uint8), nbytes
 
 
-def summary_fwd(x, queries, want_energy=False):
-    """x [B,E,h,w], queries [B,Q,E] -> summary [B,Q,E], row_max [B,Q], row_sum [B,Q], energy [B,Q,h,w] | None."""
+def summary_fwd(x, queries, want_energy=False, version=2):
+    """x [B,E,h,w], queries [B,Q,E] -> summary [B,Q,E], row_max [B,Q], row_sum [B,Q], energy [B,Q,h,w] | None.
+    version=1: the round-1 tensor-core kernel (cross-check of the warp-specialised one; no energy output)."""
     require_cuda(x, queries)
     B, E, h, w = x.shape
     Q = queries.shape[1]
@@ -36,6 +37,10 @@ def summary_fwd(x, queries, want_energy=False):
     row_sum = torch.empty(B, Q, device=dev, dtype=torch.float32)
     energy = torch.empty(B, Q, h, w, device=dev, dtype=torch.float32) if want_energy else None
     ws, nbytes = _workspace(B, E, Q, 0, n, dev)
+    if version == 1:
+        check(lib().sqlx_sql_summary_fwd_v1(ptr(x), ptr(queries), B, E, Q, n, ptr(summary), ptr(row_max), ptr(row_sum),
+                                            ptr(ws), nbytes, stream_ptr()), "sqlx_sql_summary_fwd_v1")
+        return summary, row_max, row_sum, None
     check(lib().sqlx_sql_summary_fwd(ptr(x), ptr(queries), B, E, Q, n, ptr(summary), ptr(row_max), ptr(row_sum),
                                      ptr(energy), ptr(ws), nbytes, stream_ptr()), "sqlx_sql_summary_fwd")
     return summary, row_max, row_sum, energy

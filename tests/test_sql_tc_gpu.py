@@ -176,3 +176,40 @@ def test_ws_kernels_match_v1(cfg):
             assert torch.isfinite(a).all(), (mode, nm)
             rel = float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
             assert rel < 1e-3, (mode, nm, rel)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, h=24, w=40, Q=64),
+    dict(B=1, h=17, w=20, Q=120),              # ragged last step (340 = 10 * 32 + 20), padded query rows
+    dict(B=3, h=8, w=12, Q=12),                # three steps: one group of epilogue warps stays idle
+    dict(B=5, h=3, w=4, Q=8),                  # one partial step (12 pixels: the upper lane half owns none of them)
+    dict(B=2, h=9, w=4, Q=40),                 # 36 pixels: the second step holds 4 (upper lane half empty)
+    dict(B=2, h=64, w=96, Q=64, qscale=6.0),   # energies spread over +-60: the running maximum keeps moving (rescale path)
+    dict(B=2, h=64, w=96, Q=128, qscale=6.0),
+    dict(B=150, h=8, w=16, Q=64),              # more samples than SMs: one chunk per sample
+    dict(B=12, h=96, w=320, Q=64),             # BASELINE config 2
+    dict(B=8, h=160, w=512, Q=128),            # BASELINE config 3
+    dict(B=2, h=320, w=1024, Q=128),           # BASELINE config 4 (two of its eight samples)
+])
+def test_ws_summary_matches_v1_and_fp64(cfg):
+    """Warp-specialised summary kernel (csrc/sql_ws.cu: lane = query, four groups of epilogue warps, accumulators resident in
+    TMEM, lazily rescaled) against the round-1 kernel and against an fp64 restatement of networks/layers.py:17-20
+    (softmax over the pixels of y = K x, summary = a x^T): 3xTF32 on both contractions, so 1e-5 of the largest summary."""
+    from sqlx import sql as S
+    B, h, w, Q = (cfg[k] for k in ("B", "h", "w", "Q"))
+    g = torch.Generator().manual_seed(11 + Q + h)
+    x = torch.randn(B, 32, h, w, generator=g).cuda()
+    q = (cfg.get("qscale", 1.0) * 0.4 * torch.randn(B, Q, 32, generator=g)).cuda()
+    s2, m2, l2, _ = S.summary_fwd(x, q)
+    s1, m1, l1, _ = S.summary_fwd(x, q, version=1)
+    xd, qd = x.double().flatten(2), q.double()
+    y = torch.bmm(qd, xd)                                         # [B, Q, n]
+    ref = torch.bmm(torch.softmax(y, dim=2), xd.transpose(1, 2))  # [B, Q, E]
+    scale = float(ref.abs().max())
+    assert torch.isfinite(s2).all()
+    assert float((s2.double() - ref).abs().max()) < 1e-5 * max(scale, 1.0), float((s2.double() - ref).abs().max())
+    assert float((s2 - s1).abs().max()) < 1e-5 * max(scale, 1.0)
+    # the saved row statistics describe the same softmax: log-sum-exp agrees with fp64
+    lse = torch.logsumexp(y, dim=2)
+    assert float(((m2.double() + l2.double().log()) - lse).abs().max()) < 1e-4
+    assert float(((m1.double() + l1.double().log()) - lse).abs().max()) < 1e-4

@@ -936,10 +936,18 @@ __global__ void __launch_bounds__(kThreads, 1) sql_ws_bwd_sum_kernel(
 // ================================================================================================================
 constexpr int kSumSlot = 4 * kXBlock;      // ring slot of a step: x MN-major hi | lo | x K-major hi | lo   (4 KB each)
 constexpr uint32_t kSumGrpCols = 96, kSumKCol = 384;
+constexpr int kSumSplitWarps = 3;          // warps 17..19: each writes the lo images of every third landed step (keeps the
+                                           // split and its fence.proxy.async off the epilogue groups' step cycle; one warp per
+                                           // step so that three steps' fences overlap).  20 warps: five per scheduler, 96
+                                           // registers per thread
+constexpr int kSumThreads = kThreads + 32 * kSumSplitWarps;
 
 template <int QP>
 struct SumSmem {
-  static constexpr int NSLOT = 14;
+#ifndef SQLX_SUM_NSLOT
+#define SQLX_SUM_NSLOT 14
+#endif
+  static constexpr int NSLOT = SQLX_SUM_NSLOT;
   static constexpr int NPART = QP == 64 ? 8 : 4;       // partial softmax states per query at the end
   static constexpr int REC = kE + 3;                   // m, l, 32 sums (odd stride: conflict-free)
   static constexpr size_t ring = 0, tail = (size_t)NSLOT * kSumSlot;
@@ -949,7 +957,7 @@ struct SumSmem {
 };
 
 template <int QP>
-__global__ void __launch_bounds__(kThreads, 1) sql_ws_summary_kernel(const __grid_constant__ CUtensorMap map_mn,
+__global__ void __launch_bounds__(kSumThreads, 1) sql_ws_summary_kernel(const __grid_constant__ CUtensorMap map_mn,
                                                                      const __grid_constant__ CUtensorMap map_k,
                                                                      const float* __restrict__ queries, int Q, int n,
                                                                      int steps_per_chunk,
@@ -964,11 +972,11 @@ __global__ void __launch_bounds__(kThreads, 1) sql_ws_summary_kernel(const __gri
   uint8_t* ring = base + L::ring;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + L::tail);
   uint64_t* bar_full = bars;                    // [NSLOT] TMA: both images of a step landed
-  uint64_t* bar_split = bars + NSLOT;           // [4] 4 warps: lo images of the group's next step written
-  uint64_t* bar_z = bars + NSLOT + 4;           // [4] MMA commit: y of the group's step (and every earlier MMA) done
-  uint64_t* bar_epi = bars + NSLOT + 8;         // [4] 4 warps: P_hi / P_lo of the group's step in TMEM
-  uint64_t* bar_done = bars + NSLOT + 12;       // MMA commit: everything done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NSLOT + 13);
+  uint64_t* bar_split = bars + NSLOT;           // [NSLOT] split warps: lo images of the step in the slot written
+  uint64_t* bar_z = bars + 2 * NSLOT;           // [4] MMA commit: y of the group's step (and every earlier MMA) done
+  uint64_t* bar_epi = bars + 2 * NSLOT + 4;     // [4] 4 warps: P_hi / P_lo of the group's step in TMEM
+  uint64_t* bar_done = bars + 2 * NSLOT + 8;    // MMA commit: everything done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 9);
   const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kCols = 512;
@@ -983,8 +991,8 @@ __global__ void __launch_bounds__(kThreads, 1) sql_ws_summary_kernel(const __gri
   if (threadIdx.x == kEpiThreads) {
     tma_prefetch_desc(&map_mn);
     tma_prefetch_desc(&map_k);
-    for (int i = 0; i < NSLOT; ++i) mbar_init(bar_full + i, 1);
-    for (int i = 0; i < 4; ++i) { mbar_init(bar_split + i, 4); mbar_init(bar_z + i, 1); mbar_init(bar_epi + i, 4); }
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_split + i, 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_z + i, 1); mbar_init(bar_epi + i, 4); }
     mbar_init(bar_done, 1);
     fence_barrier_init();
   }
@@ -1030,60 +1038,104 @@ __global__ void __launch_bounds__(kThreads, 1) sql_ws_summary_kernel(const __gri
       const uint32_t tk_hi = tmem + kSumKCol, tk_lo = tk_hi + kE;
       const uint64_t d_mn = make_desc_mn32(smem_u32(ring), kXBlock);
       const uint64_t d_xk = make_desc_sw128(smem_u32(ring) + 2 * kXBlock, 16, 1024);
-      for (int i = 0; i < nsteps + 3; ++i) {
-        if (i < nsteps) {
-          const int g = i & 3;
-          const uint32_t so = (uint32_t)(i % NSLOT) * kSumSlot;
-          mbar_wait(bar_split + g, (i >> 2) & 1);
-          tc_fence_after();
-          const uint32_t ty = tmem + g * kSumGrpCols;
-          const uint64_t xh = desc_add(d_mn, so), xl = desc_add(d_mn, so + kXBlock);
+      // The issuing thread must never let the tensor pipe drain: the tcgen05.mma queue is only a few instructions deep
+      // (issue time = execution time, tools/mma_chain_probe.cu) and even a SATISFIED mbarrier wait between two batches
+      // costs ~70 idle cycles (tools/mma_mix_probe.cu: 16 -> 22 cycles per instruction with one wait per 12).  So the
+      // barrier of the NEXT batch is probed (mbarrier.test_wait, non-blocking) BEFORE the current batch is issued, while
+      // the queue is still full, and the blocking wait runs only when that probe failed.
+      auto issue_mma1 = [&](int i, uint32_t so) {
+        const uint32_t ty = tmem + (i & 3) * kSumGrpCols;
+        const uint64_t xh = desc_add(d_mn, so), xl = desc_add(d_mn, so + kXBlock);
 #pragma unroll
-          for (int k = 0; k < kE / 8; ++k) umma_tf32_ts(ty, tk_hi + k * 8, desc_add(xh, k * 1024), id_y, k > 0 ? 1u : 0u);
+        for (int k = 0; k < kE / 8; ++k) umma_tf32_ts(ty, tk_hi + k * 8, desc_add(xh, k * 1024), id_y, k > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < kE / 8; ++k) umma_tf32_ts(ty, tk_lo + k * 8, desc_add(xh, k * 1024), id_y, 1u);
+        for (int k = 0; k < kE / 8; ++k) umma_tf32_ts(ty, tk_lo + k * 8, desc_add(xh, k * 1024), id_y, 1u);
 #pragma unroll
-          for (int k = 0; k < kE / 8; ++k) umma_tf32_ts(ty, tk_hi + k * 8, desc_add(xl, k * 1024), id_y, 1u);
-          umma_commit(bar_z + g);
-        }
-        const int j = i - 3;
-        if (j >= 0) {
-          const int g = j & 3;
-          const uint32_t so = (uint32_t)(j % NSLOT) * kSumSlot;
-          mbar_wait(bar_epi + g, (j >> 2) & 1);
-          tc_fence_after();
-          const uint32_t tb = tmem + g * kSumGrpCols;
-          const uint64_t xh = desc_add(d_xk, so), xl = desc_add(d_xk, so + kXBlock);
-          if (!kPair) {
-            if (j < 4) {                                            // the group's first step initialises its accumulator
-              umma_tf32_ts(tb + kSOff, tb, xh, id_s, 0u);
+        for (int k = 0; k < kE / 8; ++k) umma_tf32_ts(ty, tk_hi + k * 8, desc_add(xl, k * 1024), id_y, 1u);
+        umma_commit(bar_z + (i & 3));
+      };
+      auto issue_mma2 = [&](int j, uint32_t so) {
+        const uint32_t tb = tmem + (j & 3) * kSumGrpCols;
+        const uint64_t xh = desc_add(d_xk, so), xl = desc_add(d_xk, so + kXBlock);
+        if (!kPair) {
+          if (j < 4) {                                            // the group's first step initialises its accumulator
+            umma_tf32_ts(tb + kSOff, tb, xh, id_s, 0u);
 #pragma unroll
-              for (int k = 1; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + k * 8, desc_add(xh, k * 32), id_s, 1u);
-            } else {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + k * 8, desc_add(xh, k * 32), id_s, 1u);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + 32 + k * 8, desc_add(xh, k * 32), id_s, 1u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + k * 8, desc_add(xl, k * 32), id_s, 1u);
+            for (int k = 1; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + k * 8, desc_add(xh, k * 32), id_s, 1u);
           } else {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {                          // lane half h: pixels [16 h, 16 h + 16)
-              const uint32_t own = tb + 16 * h, oth = tb + 16 * (1 - h), td = tb + kSOff + 32 * h;
-              if (j < 4) umma_tf32_ts(td, own, desc_add(xh, (2 * h) * 32), id_s, 0u);
-              else umma_tf32_ts(td, own, desc_add(xh, (2 * h) * 32), id_s, 1u);
-              umma_tf32_ts(td, own + 8, desc_add(xh, (2 * h + 1) * 32), id_s, 1u);
+            for (int k = 0; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + k * 8, desc_add(xh, k * 32), id_s, 1u);
+          }
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                umma_tf32_ts(td, oth + k * 8, desc_add(xh, (2 * h + k) * 32), id_s, 1u);
-                umma_tf32_ts(td, own + k * 8, desc_add(xl, (2 * h + k) * 32), id_s, 1u);
-              }
+          for (int k = 0; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + 32 + k * 8, desc_add(xh, k * 32), id_s, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + k * 8, desc_add(xl, k * 32), id_s, 1u);
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {                          // lane half h: pixels [16 h, 16 h + 16)
+            const uint32_t own = tb + 16 * h, oth = tb + 16 * (1 - h), td = tb + kSOff + 32 * h;
+            if (j < 4) umma_tf32_ts(td, own, desc_add(xh, (2 * h) * 32), id_s, 0u);
+            else umma_tf32_ts(td, own, desc_add(xh, (2 * h) * 32), id_s, 1u);
+            umma_tf32_ts(td, own + 8, desc_add(xh, (2 * h + 1) * 32), id_s, 1u);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              umma_tf32_ts(td, oth + k * 8, desc_add(xh, (2 * h + k) * 32), id_s, 1u);
+              umma_tf32_ts(td, own + k * 8, desc_add(xl, (2 * h + k) * 32), id_s, 1u);
             }
           }
         }
+      };
+      // ring-slot cursors of step i, step i + 1 and step j = i - 3 (offset, phase parity)
+      uint32_t so_i = 0, so_n = kSumSlot, so_j = 0, ph_i = 0, ph_n = 0;
+      if (nsteps > 0) mbar_wait(bar_split, 0);
+      for (int i = 0; i < nsteps + 3; ++i) {
+        const int j = i - 3;
+        const bool has1 = i < nsteps, has2 = j >= 0, hasn = i + 1 < nsteps;
+        // probe what the next two batches need while the queue still holds the previous batch
+        const bool r_epi = has2 && mbar_test(bar_epi + (j & 3), (j >> 2) & 1);
+        if (has1) {
+          tc_fence_after();
+          issue_mma1(i, so_i);
+        }
+        const bool r_split = hasn && mbar_test(bar_split + so_n / kSumSlot, ph_n);
+        if (has2) {
+          if (!r_epi) mbar_wait(bar_epi + (j & 3), (j >> 2) & 1);
+          tc_fence_after();
+          issue_mma2(j, so_j);
+          so_j = so_j + kSumSlot == NSLOT * kSumSlot ? 0 : so_j + kSumSlot;
+        }
+        if (hasn && !r_split) mbar_wait(bar_split + so_n / kSumSlot, ph_n);
+        so_i = so_n; ph_i = ph_n;
+        if (so_n + kSumSlot == NSLOT * kSumSlot) { so_n = 0; ph_n ^= 1; } else so_n += kSumSlot;
       }
+      (void)ph_i;
       umma_commit(bar_done);
+    }
+  } else if (warp > kEpiWarps) {
+    // ---------------------------------------------------------------- split warps: lo images of the steps as they land
+    // (the landing buffers themselves are the hi operands)
+    constexpr int PER = 2 * kXBlock / 16 / 32;                               // float4 per thread and step
+    for (int i = warp - (kEpiWarps + 1); i < nsteps; i += kSumSplitWarps) {
+      uint8_t* slot = ring + (size_t)(i % NSLOT) * kSumSlot;
+      mbar_wait(bar_full + i % NSLOT, (i / NSLOT) & 1);
+#pragma unroll
+      for (int j0 = 0; j0 < PER; j0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int idx = lane + (j0 + j) * 32;                              // [0, 256): MN-major image, [256, 512): K-major
+          v[j] = *reinterpret_cast<const float4*>(slot + (idx >> 8) * 2 * kXBlock + (idx & 255) * 16);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int idx = lane + (j0 + j) * 32;
+          v[j].x -= tf32_hi(v[j].x); v[j].y -= tf32_hi(v[j].y); v[j].z -= tf32_hi(v[j].z); v[j].w -= tf32_hi(v[j].w);
+          *reinterpret_cast<float4*>(slot + kXBlock + (idx >> 8) * 2 * kXBlock + (idx & 255) * 16) = v[j];
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_split + i % NSLOT);
     }
   } else {
     // ---------------------------------------------------------------- epilogue warps: group `grp` owns steps s = grp (mod 4)
@@ -1093,24 +1145,6 @@ __global__ void __launch_bounds__(kThreads, 1) sql_ws_summary_kernel(const __gri
     const uint32_t t_own = lane_base + (kPair ? 16 * half : 0), t_lo = lane_base + (kPair ? 16 * (1 - half) : 32);
     const uint32_t t_S = lane_base + kSOff + 32 * half;
     float m = -INFINITY, l = 0.f;
-    auto split_step = [&](int i) {               // lo images of step i (the landing buffers are the hi operands)
-      uint8_t* slot = ring + (size_t)(i % NSLOT) * kSumSlot;
-      mbar_wait(bar_full + i % NSLOT, (i / NSLOT) & 1);
-      const float4* mh = reinterpret_cast<const float4*>(slot);
-      const float4* kh = reinterpret_cast<const float4*>(slot + 2 * kXBlock);
-      float4* ml = reinterpret_cast<float4*>(slot + kXBlock);
-      float4* kl = reinterpret_cast<float4*>(slot + 3 * kXBlock);
-      float4 v[4] = {mh[gtid], mh[gtid + 128], kh[gtid], kh[gtid + 128]};
-#pragma unroll
-      for (int i4 = 0; i4 < 4; ++i4) {
-        v[i4].x -= tf32_hi(v[i4].x); v[i4].y -= tf32_hi(v[i4].y); v[i4].z -= tf32_hi(v[i4].z); v[i4].w -= tf32_hi(v[i4].w);
-      }
-      ml[gtid] = v[0]; ml[gtid + 128] = v[1]; kl[gtid] = v[2]; kl[gtid + 128] = v[3];
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_split + grp);
-    };
-    if (grp < nsteps) split_step(grp);
     for (int s = grp; s < nsteps; s += 4) {
       mbar_wait(bar_z + grp, (s >> 2) & 1);        // y of step s is in the group's buffer; every MMA of steps <= s-4 is done
       tc_fence_after();
@@ -1174,7 +1208,6 @@ __global__ void __launch_bounds__(kThreads, 1) sql_ws_summary_kernel(const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_epi + grp);
-      if (s + 4 < nsteps) split_step(s + 4);
     }
     // ---- merge the partial states of every query (4 groups x lane halves) and write one record per (chunk, query)
     mbar_wait(bar_done, 0);
@@ -1327,7 +1360,7 @@ static int launch_ws_summary(const CUtensorMap& map_mn, const CUtensorMap& map_k
                              int chunks, int spc, float* partial, cudaStream_t st) {
   if (int e = ensure_dyn_smem(wsql::sql_ws_summary_kernel<QP>, wsql::SumSmem<QP>::bytes)) return e;
   ProfScope prof("sql_tc_summary_kernel", st);
-  wsql::sql_ws_summary_kernel<QP><<<dim3(chunks, B), wsql::kThreads, wsql::SumSmem<QP>::bytes, st>>>(map_mn, map_k, queries, Q,
+  wsql::sql_ws_summary_kernel<QP><<<dim3(chunks, B), wsql::kSumThreads, wsql::SumSmem<QP>::bytes, st>>>(map_mn, map_k, queries, Q,
                                                                                                   n, spc, partial);
   return check_launch("sql_ws_summary_kernel");
 }

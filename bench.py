@@ -316,7 +316,9 @@ def load_traffic():
             base = {"photo_fwd3_kernel": "photo_fwd_ms_kernel" if ms else "photo_fwd_kernel",
                     "photo_bwd3_kernel": "photo_bwd_ms_kernel" if ms else "photo_bwd_kernel",
                     "identity3_kernel": "identity_loss_kernel",
-                    "sql_tc_pred2_kernel": "sql_tc_pred_kernel"}.get(base, base)
+                    "sql_tc_pred2_kernel": "sql_tc_pred_kernel", "sql_ws_pred_kernel": "sql_tc_pred_kernel",
+                    "sql_ws_summary_kernel": "sql_tc_summary_kernel", "sql_ws_bwd_pred_kernel": "sql_tc_bwd_pred_kernel",
+                    "sql_ws_bwd_sum_kernel": "sql_tc_bwd_sum_kernel"}.get(base, base)
             d[base] = v["dram_bytes_per_launch"]
         out[ck] = d
     return out
@@ -343,7 +345,7 @@ def run_workload(cx, cfg_id, cfg, steps, warmup, full):
 
     def exchange(flat):
         """the path's one exchange step: ONE NCCL all-reduce (average) of the flat gradient bucket, in place"""
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        sqlx.dist.allreduce_flat_(flat)
 
     nslots = max(2, args.prefetch + 1)
     hp = HotPath(cfg, device=dev, use_graph=not args.no_graph, num_slots=nslots,

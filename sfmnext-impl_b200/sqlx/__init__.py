@@ -12,3 +12,4 @@ from .layers import (SSIM, BackprojectDepth, Project3D, get_smooth_loss, SILogLo
 from .trainer import FusedLossMixin, IndoorFusedLossMixin  # noqa: F401
 from .sql import (FullQueryLayer, Depth_Decoder_QueryTr, Lite_Depth_Decoder_QueryTr, sql_tail,  # noqa: F401
                   bin_centers, convert_depth_decoder, fuse_depth_decoder)
+from . import dist  # noqa: F401,E402

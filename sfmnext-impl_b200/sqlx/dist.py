@@ -22,8 +22,23 @@ def shard_batch(batch, rank, world):
     return out
 
 
+def allreduce_flat_(flat, group=None):
+    """The path's one exchange step: average, in place, the flat gradient bucket the kernels wrote into
+    (HotPath.grad_flat: every parameter gradient is a view of it, so there is no pack / unpack).  Capturable in a CUDA graph
+    with the NCCL backend."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return flat
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:                                       # gloo has no AVG
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(dist.get_world_size(group))
+    return flat
+
+
 class GradBucket:
-    """Flat fp32 bucket reused every step: pack -> all_reduce(AVG or SUM/world) -> unpack."""
+    """Flat fp32 bucket for gradients that live in separate tensors (e.g. the rest of the model under plain autograd):
+    pack -> all_reduce(AVG or SUM/world) -> unpack.  The hot path itself does not need it (allreduce_flat_)."""
 
     def __init__(self, tensors, group=None):
         self.sizes = [t.numel() for t in tensors]

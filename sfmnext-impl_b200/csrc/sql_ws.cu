@@ -945,7 +945,7 @@ constexpr int kSumThreads = kThreads + 32 * kSumSplitWarps;
 template <int QP>
 struct SumSmem {
 #ifndef SQLX_SUM_NSLOT
-#define SQLX_SUM_NSLOT 14
+#define SQLX_SUM_NSLOT 12
 #endif
   static constexpr int NSLOT = SQLX_SUM_NSLOT;
   static constexpr int NPART = QP == 64 ? 8 : 4;       // partial softmax states per query at the end
@@ -1054,18 +1054,13 @@ __global__ void __launch_bounds__(kSumThreads, 1) sql_ws_summary_kernel(const __
         for (int k = 0; k < kE / 8; ++k) umma_tf32_ts(ty, tk_hi + k * 8, desc_add(xl, k * 1024), id_y, 1u);
         umma_commit(bar_z + (i & 3));
       };
-      auto issue_mma2 = [&](int j, uint32_t so) {
+      auto issue_mma2 = [&](int j, uint32_t so, uint32_t first) {   // first = 0: the group's first step initialises its accumulator
         const uint32_t tb = tmem + (j & 3) * kSumGrpCols;
         const uint64_t xh = desc_add(d_xk, so), xl = desc_add(d_xk, so + kXBlock);
         if (!kPair) {
-          if (j < 4) {                                            // the group's first step initialises its accumulator
-            umma_tf32_ts(tb + kSOff, tb, xh, id_s, 0u);
+          umma_tf32_ts(tb + kSOff, tb, xh, id_s, first);
 #pragma unroll
-            for (int k = 1; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + k * 8, desc_add(xh, k * 32), id_s, 1u);
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + k * 8, desc_add(xh, k * 32), id_s, 1u);
-          }
+          for (int k = 1; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + k * 8, desc_add(xh, k * 32), id_s, 1u);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_tf32_ts(tb + kSOff, tb + 32 + k * 8, desc_add(xh, k * 32), id_s, 1u);
 #pragma unroll
@@ -1074,8 +1069,7 @@ __global__ void __launch_bounds__(kSumThreads, 1) sql_ws_summary_kernel(const __
 #pragma unroll
           for (int h = 0; h < 2; ++h) {                          // lane half h: pixels [16 h, 16 h + 16)
             const uint32_t own = tb + 16 * h, oth = tb + 16 * (1 - h), td = tb + kSOff + 32 * h;
-            if (j < 4) umma_tf32_ts(td, own, desc_add(xh, (2 * h) * 32), id_s, 0u);
-            else umma_tf32_ts(td, own, desc_add(xh, (2 * h) * 32), id_s, 1u);
+            umma_tf32_ts(td, own, desc_add(xh, (2 * h) * 32), id_s, first);
             umma_tf32_ts(td, own + 8, desc_add(xh, (2 * h + 1) * 32), id_s, 1u);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
@@ -1085,30 +1079,39 @@ __global__ void __launch_bounds__(kSumThreads, 1) sql_ws_summary_kernel(const __
           }
         }
       };
-      // ring-slot cursors of step i, step i + 1 and step j = i - 3 (offset, phase parity)
-      uint32_t so_i = 0, so_n = kSumSlot, so_j = 0, ph_i = 0, ph_n = 0;
+      // The loop is unrolled by the ring depth (a multiple of the four groups): slot offsets, TMEM columns and barrier
+      // addresses of every step of a round are compile-time constants, so between two tcgen05.mma there is nothing but
+      // one uniform 64-bit add per descriptor (the rolled loop spent ~380 of its 765 cycles per step in R2UR moves and
+      // slot arithmetic, with the tensor pipe idle: the queue drains while the issuing thread computes).  Measured
+      // 46 -> 40 us at config 2.  (Compile-time TMEM / shared-memory bases were tried on top: SLOWER, 47 us -- the inline
+      // PTX operands are "r" registers, so every constant is materialised in a vector register and moved with R2UR.)
+      static_assert(NSLOT % 4 == 0, "ring depth must be a multiple of the number of epilogue groups");
       if (nsteps > 0) mbar_wait(bar_split, 0);
-      for (int i = 0; i < nsteps + 3; ++i) {
-        const int j = i - 3;
-        const bool has1 = i < nsteps, has2 = j >= 0, hasn = i + 1 < nsteps;
-        // probe what the next two batches need while the queue still holds the previous batch
-        const bool r_epi = has2 && mbar_test(bar_epi + (j & 3), (j >> 2) & 1);
-        if (has1) {
-          tc_fence_after();
-          issue_mma1(i, so_i);
+      for (int base_i = 0; base_i < nsteps + 3; base_i += NSLOT) {
+        const uint32_t ph = (uint32_t)(base_i / NSLOT) & 1u;          // phase parity of the ring barriers in this round
+#pragma unroll
+        for (int u = 0; u < NSLOT; ++u) {
+          const int i = base_i + u, j = i - 3;
+          if (i >= nsteps + 3) break;
+          const bool has1 = i < nsteps, has2 = j >= 0, hasn = i + 1 < nsteps;
+          const int uj = (u + NSLOT - 3) % NSLOT, un = (u + 1) % NSLOT;      // slots of step j and step i + 1
+          const uint32_t ph_n = un == 0 ? ph ^ 1u : ph;
+          // probe what the next two batches need while the queue still holds the previous batch
+          const bool r_epi = has2 && mbar_test(bar_epi + (uj & 3), (uint32_t)(j >> 2) & 1u);
+          if (has1) {
+            tc_fence_after();
+            issue_mma1(u, (uint32_t)u * kSumSlot);
+          }
+          const bool r_split = hasn && mbar_test(bar_split + un, ph_n);
+          if (has2) {
+            if (!r_epi) mbar_wait(bar_epi + (uj & 3), (uint32_t)(j >> 2) & 1u);
+            tc_fence_after();
+            if (j < 4) issue_mma2(uj, (uint32_t)uj * kSumSlot, 0u);
+            else issue_mma2(uj, (uint32_t)uj * kSumSlot, 1u);
+          }
+          if (hasn && !r_split) mbar_wait(bar_split + un, ph_n);
         }
-        const bool r_split = hasn && mbar_test(bar_split + so_n / kSumSlot, ph_n);
-        if (has2) {
-          if (!r_epi) mbar_wait(bar_epi + (j & 3), (j >> 2) & 1);
-          tc_fence_after();
-          issue_mma2(j, so_j);
-          so_j = so_j + kSumSlot == NSLOT * kSumSlot ? 0 : so_j + kSumSlot;
-        }
-        if (hasn && !r_split) mbar_wait(bar_split + so_n / kSumSlot, ph_n);
-        so_i = so_n; ph_i = ph_n;
-        if (so_n + kSumSlot == NSLOT * kSumSlot) { so_n = 0; ph_n ^= 1; } else so_n += kSumSlot;
       }
-      (void)ph_i;
       umma_commit(bar_done);
     }
   } else if (warp > kEpiWarps) {

@@ -53,6 +53,9 @@ def parse():
                     help="N > 1: issue the gradient all-reduce after the step instead of inside it (A/B switch)")
     ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: where the unmodified reference runs (cpu = the contract's arm)")
+    ap.add_argument("--exchange-sms", type=int, default=-1,
+                    help="N > 1: SMs the summary-path backward leaves to the NCCL kernel of the in-step exchange "
+                         "(-1 = default 32)")
     ap.add_argument("--prefetch", type=int, default=2, help="batches in flight ahead of the step in the e2e loop")
     return ap.parse_args()
 
@@ -342,6 +345,7 @@ def run_workload(cx, cfg_id, cfg, steps, warmup, full):
                       "stereo": cfg.stereo, "parallelism": "dp%d" % world}}
     torch.manual_seed(0)
     exchange_in_step = world > 1 and not args.allreduce_after_step
+    sm_reserve = 32 if args.exchange_sms < 0 else args.exchange_sms
 
     def exchange(flat):
         """the path's one exchange step: ONE NCCL all-reduce (average) of the flat gradient bucket, in place"""
@@ -349,7 +353,7 @@ def run_workload(cx, cfg_id, cfg, steps, warmup, full):
 
     nslots = max(2, args.prefetch + 1)
     hp = HotPath(cfg, device=dev, use_graph=not args.no_graph, num_slots=nslots,
-                 grad_exchange=exchange if exchange_in_step else None)
+                 grad_exchange=exchange if exchange_in_step else None, exchange_sm_reserve=sm_reserve)
     state = head_state(cfg)                       # identical initial weights on every rank (seeded)
     hp.load_state_dict(state, strict=True)
     hb = make_host_batch(cfg, seed=1234 + rank, pin=True, u8_frames=not args.f32_frames)
@@ -712,6 +716,7 @@ def main():
     config["submission"] = "eager" if args.no_graph else "cuda_graph"
     if world > 1:
         config["grad_exchange"] = (
+            "(summary-path backward leaves %d SMs to the NCCL kernel) " % (32 if args.exchange_sms < 0 else args.exchange_sms) +
             "one NCCL all-reduce (average) of the flat gradient bucket per step (the kernels write the parameter gradients "
             "into views of it: no pack / unpack), issued inside the step on a communication stream when the last parameter "
             "gradient exists (overlaps the summary-path backward kernel; part of the CUDA graph)"

@@ -340,6 +340,9 @@ int sqlx_sql_tc_supported(int E, int Q, int D, int n);
 /* on = 0 forces the exact-fp32 CUDA-core kernels for every shape (A/B tests); returns the previous setting */
 int sqlx_sql_set_tensor_cores(int on);
 int sqlx_sql_get_tensor_cores(void);   /* current setting (read-only) */
+/* SMs the one-CTA-per-SM SQL kernels launched from now on may occupy (default all 148; clamped to [8, 148]); returns the
+ * previous budget.  For callers that run a communication kernel beside the summary-path backward. */
+int sqlx_sql_set_sm_budget(int sms);
 int sqlx_sql_energy_tc(const float* x, const float* queries, int B, int E, int Q, int n, float* energy, void* stream);
 
 /* Mixed-weight decomposition (tensor cores only; sqlx_sql_tc_supported must hold):

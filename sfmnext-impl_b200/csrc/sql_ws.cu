@@ -25,6 +25,8 @@
 
 #include <math.h>
 
+#include <atomic>
+
 namespace sqlx {
 namespace wsql {
 
@@ -1270,9 +1272,13 @@ __global__ void __launch_bounds__(kSumThreads, 1) sql_ws_summary_kernel(const __
 // ------------------------------------------------------------------------------------------------
 // launchers (called from the C ABI in sql_fp32.cu)
 // ------------------------------------------------------------------------------------------------
+// SMs the one-CTA-per-SM kernels may occupy (sqlx_sql_set_sm_budget): a caller that runs a communication kernel beside the
+// summary-path backward (the in-step gradient all-reduce) leaves it room instead of making it queue for SMs
+std::atomic<int> g_sm_budget{kNumSMs};
+
 void ws_plan(int B, int n, int* chunks, int* tiles_per_chunk) {
   const int tiles = ceil_div(n, wsql::kTile);
-  int c = kNumSMs / B;   // one CTA per SM
+  int c = g_sm_budget.load() / B;   // one CTA per SM
   c = c < 1 ? 1 : (c > tiles ? tiles : c);
   *tiles_per_chunk = ceil_div(tiles, c);
   *chunks = ceil_div(tiles, *tiles_per_chunk);
@@ -1383,3 +1389,10 @@ int ws_summary_partials(const float* x, const float* queries, int B, int Q, int 
 }
 
 }  // namespace sqlx
+
+/* Limit the grid of the one-CTA-per-SM SQL kernels launched from now on to `sms` SMs (clamped to [8, 148]); returns the
+ * previous budget.  Workspaces sized with the full budget stay sufficient. */
+extern "C" int sqlx_sql_set_sm_budget(int sms) {
+  sms = sms < 8 ? 8 : (sms > sqlx::kNumSMs ? sqlx::kNumSMs : sms);
+  return sqlx::g_sm_budget.exchange(sms);
+}

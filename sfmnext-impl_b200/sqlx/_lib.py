@@ -135,6 +135,7 @@ _PROTOS = {
     "sqlx_sql_tc_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "sqlx_sql_set_tensor_cores": (c_int, [c_int]),
     "sqlx_sql_get_tensor_cores": (c_int, []),
+    "sqlx_sql_set_sm_budget": (c_int, [c_int]),
     "sqlx_sql_energy_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sqlx_sql_mix_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "sqlx_sql_mix_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

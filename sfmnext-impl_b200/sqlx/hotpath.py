@@ -57,7 +57,7 @@ class HotPath(torch.nn.Module):
     """Parameters: the decoder's 1x1 conv (convert_to_prob.0) and bins_regressor.  Inputs live in static
     device buffers `self.inp[name]` (see HotPathConfig.input_shapes); `load()` copies a host batch into them."""
 
-    def __init__(self, cfg, device="cuda", use_graph=True, num_slots=1, grad_exchange=None):
+    def __init__(self, cfg, device="cuda", use_graph=True, num_slots=1, grad_exchange=None, exchange_sm_reserve=32):
         super().__init__()
         nn = torch.nn
         self.cfg = cfg
@@ -131,6 +131,9 @@ class HotPath(torch.nn.Module):
         # exists, so that it overlaps the summary-path backward kernel; the step (eager or captured graph, NCCL
         # collectives are capturable) ends with the main stream waiting for it.
         self.grad_exchange = grad_exchange
+        # SMs the summary-path backward leaves to the communication kernel while the exchange runs beside it (measured on
+        # 8 x B200, NCCL 2.28: exposed communication 88 us with 0, 35 us with 32, 53 us with 64; tools/nccl_sweep.sh)
+        self.exchange_sm_reserve = exchange_sm_reserve
         self.comm_stream = None
 
     # ------------------------------------------------------------------ data
@@ -214,6 +217,7 @@ class HotPath(torch.nn.Module):
             packed = [P.pack_rgba(src) for src in sources]
         gv = self.grad_views[slot]
         hook = (lambda grads: self._start_grad_exchange(slot)) if self.grad_exchange is not None else None
+        S.exchange_sm_reserve = self.exchange_sm_reserve if hook is not None else 0
         pred = S.sql_tail(I["x"], I["queries"], conv.weight.view(c.D, c.Q), conv.bias, self._centers_fn(slot), (),
                           on_param_grads=hook, head_grad_out=(gv[0].view(c.D, c.Q), gv[1]))
         main.wait_stream(side)

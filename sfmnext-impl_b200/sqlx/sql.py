@@ -351,7 +351,14 @@ class _SqlTail(torch.autograd.Function):
             # tail) is still to run: the caller's gradient exchange overlaps it
             join = ctx.on_param_grads([d_Wp, d_bp] + [g_ for g_ in grads[1:] if g_ is not None])
         if ctx.mix:
-            d_x, d_q = bwd_summary(xc, qc, summary, row_max, row_sum, _f32c(d_summary), d_x=d_x)
+            # beside a running exchange the summary-path kernel leaves `exchange_sm_reserve` SMs to the communication
+            # kernel (it would otherwise queue behind this kernel's one-CTA-per-SM grid and run exposed afterwards)
+            prev = lib().sqlx_sql_set_sm_budget(148 - exchange_sm_reserve) if (join is not None and exchange_sm_reserve) else None
+            try:
+                d_x, d_q = bwd_summary(xc, qc, summary, row_max, row_sum, _f32c(d_summary), d_x=d_x)
+            finally:
+                if prev is not None:
+                    lib().sqlx_sql_set_sm_budget(prev)
             if early:
                 mix_weights_bwd(d_M, qc, Wc, d_q, want_d_Wp=False)         # d_q += Wp^T dM
             else:
@@ -366,6 +373,11 @@ class _SqlTail(torch.autograd.Function):
         if out_Wp is not None:
             return (d_x, d_q, None, None, None, None, None, None) + d_params
         return (d_x, d_q, d_Wp.view_as(Wc), d_bp, None, None, None, None) + d_params
+
+
+# SMs left free for the communication kernel while the summary-path backward runs beside an in-step gradient exchange
+# (0 = none).  Set by the caller that owns the exchange (sqlx.hotpath.HotPath, bench.py --exchange-sms).
+exchange_sm_reserve = 0
 
 
 def sql_tail(x, queries, Wp, bp, centers_fn, params=(), on_param_grads=None, head_grad_out=None):

@@ -434,7 +434,8 @@ __global__ void __launch_bounds__(kThreads, 1) sql_ws_bwd_pred_kernel(
   if (warp == kEpiWarps) {
     // ---------------------------------------------------------------- control lane
     if (elect_one()) {
-      const uint32_t id_acc = make_idesc_tf32(128, kAccN, 0, 0);
+      const uint32_t id_acc = make_idesc_tf32(64, kAccN, 0, 0);      // M = 64: only the 64 bin rows of the half are read (the
+                                                                      // A read is what an SS instruction costs: 44 -> 28 cycles)
       const uint32_t id_dx = make_idesc_tf32(128, 32, 0, 0);
       const uint32_t id_z = make_idesc_tf32(kTile, 64, 1, 0);
       const uint64_t dx_ring = make_desc_mn32(smem_u32(x_ring), kXBlock), dx_lo = make_desc_mn32(smem_u32(x_lo), kXBlock);
@@ -576,12 +577,13 @@ __global__ void __launch_bounds__(kThreads, 1) sql_ws_bwd_pred_kernel(
     // every MMA has completed before the accumulators are read: the last commit covers all earlier ones
     named_sync(1, kEpiThreads);
     tc_fence_after();
-    // ---- accumulators: rows = bins of half h (TMEM lanes 0..63: q < 2), cols [0,32) dM, col 32 d_bp.  Warps (q < 2, cg)
-    // of group 0 read half 0, of group 1 half 1 (one half: group 0 only); three 16-column chunks per warp pair
+    // ---- accumulators: rows = bins of half h, cols [0,32) dM, col 32 d_bp.  An M = 64 accumulator keeps row m in TMEM lane
+    // 32 (m / 16) + m % 16 (tools/tc_probe3.cu): lanes 0..15 of every lane quarter.  Warps (q, cg) of group 0 read half 0,
+    // of group 1 half 1 (one half: group 0 only); three 16-column chunks per warp pair
     {
       const int h = grp;
-      if (h < NH && q < 2) {
-        const int d = h * 64 + q * 32 + lane;
+      if (h < NH) {
+        const int d = lane < 16 ? h * 64 + q * 16 + lane : D;
         for (int ch = cg; ch < 3; ch += 2) {
           float a[16];
           if (ntiles > 0) {
@@ -747,7 +749,8 @@ __global__ void __launch_bounds__(kThreads, 1) sql_ws_bwd_sum_kernel(
     // ---------------------------------------------------------------- control lane
     if (elect_one()) {
       const uint32_t id_y = make_idesc_tf32(kTile, 64, 1, 0);       // y, t: A = x (MN-major), B = K / ds rows (K-major)
-      const uint32_t id_32 = make_idesc_tf32(128, 32, 0, 0);        // d_x, d_K
+      const uint32_t id_32 = make_idesc_tf32(128, 32, 0, 0);        // d_x
+      const uint32_t id_dk = make_idesc_tf32(64, 32, 0, 0);         // d_K: M = 64, the 64 query rows of the half
       const uint64_t dx_ring = make_desc_mn32(smem_u32(x_ring), kXBlock), dx_lo = make_desc_mn32(smem_u32(x_lo), kXBlock);
       const uint64_t dk_hi = make_desc_sw128(smem_u32(k_hi), 16, 1024), dk_lo = make_desc_sw128(smem_u32(k_lo), 16, 1024);
       const uint64_t d_ds = make_desc_sw128(smem_u32(dsm), 16, 1024), d_kT = make_desc_sw128(smem_u32(kT), 16, 1024);
@@ -763,7 +766,7 @@ __global__ void __launch_bounds__(kThreads, 1) sql_ws_bwd_sum_kernel(
 #pragma unroll
         for (int k = 0; k < kTile / 8; ++k)       // d_K_h += dy_h^T x            (K = 128 pixels)
           umma_tf32_ss(t_dk, desc_add(d_dyT, (k >> 2) * 128 * 128 + (k & 3) * 32),
-                       desc_add(d_xk, (ti & 1) * kXTile + (k >> 2) * kXBlock + (k & 3) * 32), id_32, (ti > 0 || k > 0) ? 1u : 0u);
+                       desc_add(d_xk, (ti & 1) * kXTile + (k >> 2) * kXBlock + (k & 3) * 32), id_dk, (ti > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 64 / 8; ++k)          // d_x tile (+)= dy_h K_h        (K = 64 queries, A from TMEM)
           umma_tf32_ts(t_dx, t_dy + k * 8, desc_add(kt, (k >> 2) * 32 * 128 + (k & 3) * 32), id_32, (h > 0 || k > 0) ? 1u : 0u);
@@ -886,11 +889,12 @@ __global__ void __launch_bounds__(kThreads, 1) sql_ws_bwd_sum_kernel(
     }
     named_sync(1, kEpiThreads);
     tc_fence_after();
-    // ---- d_K accumulators: rows = queries of half h (TMEM lanes 0..63: q < 2); group h reads half h
+    // ---- d_K accumulators: rows = queries of half h; an M = 64 accumulator keeps row m in TMEM lane 32 (m / 16) + m % 16
+    // (lanes 0..15 of every lane quarter); group h reads half h
     {
       const int h = grp;
-      if (h < NH && q < 2) {
-        const int qq = h * 64 + q * 32 + lane;
+      if (h < NH) {
+        const int qq = lane < 16 ? h * 64 + q * 16 + lane : Q;
         float a[16];
         if (ntiles > 0) {
           tmem_ld16(lane_base + tm_dk + h * 32 + cg * 16, a);

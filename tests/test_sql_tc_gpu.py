@@ -213,3 +213,29 @@ def test_ws_summary_matches_v1_and_fp64(cfg):
     lse = torch.logsumexp(y, dim=2)
     assert float(((m2.double() + l2.double().log()) - lse).abs().max()) < 1e-4
     assert float(((m1.double() + l1.double().log()) - lse).abs().max()) < 1e-4
+
+
+def test_sm_budget_changes_grid_not_result():
+    """sqlx_sql_set_sm_budget (SMs left to the communication kernel beside the summary-path backward)
+    only changes how the tiles are dealt to CTAs: same gradients up to the summation order of the per-CTA partials."""
+    from sqlx import sql as S
+    from sqlx._lib import lib
+    g = torch.Generator().manual_seed(5)
+    B, h, w, Q = 12, 48, 160, 64
+    x = torch.randn(B, 32, h, w, generator=g).cuda()
+    q = (0.4 * torch.randn(B, Q, 32, generator=g)).cuda()
+    summ, mx, sm, _ = S.summary_fwd(x, q)
+    ds = torch.randn(summ.shape, generator=g).cuda()
+    ref = S.bwd_summary(x, q, summ, mx, sm, ds)
+    prev = lib().sqlx_sql_set_sm_budget(116)
+    try:
+        assert prev == 148
+        got = S.bwd_summary(x, q, summ, mx, sm, ds)
+        assert lib().sqlx_sql_set_sm_budget(3) == 116          # clamped to [8, 148]
+        assert lib().sqlx_sql_set_sm_budget(1000) == 8
+        assert lib().sqlx_sql_set_sm_budget(148) == 148
+    finally:
+        lib().sqlx_sql_set_sm_budget(148)
+    for a, b, nm in zip(got, ref, ("d_x", "d_queries")):
+        rel = float((a - b).abs().max() / b.abs().max())
+        assert rel < 1e-5, (nm, rel)

@@ -447,6 +447,8 @@ def run_workload(cx, cfg_id, cfg, steps, warmup, full):
         i = e2e_i[0]
         slot = i % nslots
         main.wait_event(ev_loaded[slot])
+        if ahead >= 2:                                  # the step also prepares the NEXT set's frame-only work
+            main.wait_event(ev_loaded[(slot + 1) % nslots])     # (HotPath.prepare_next): its frames must have landed
         hp.step(slot)
         allreduce_after()
         ev_done[slot].record(main)
@@ -714,6 +716,10 @@ def main():
     config["l2"] = ("no explicit flush: every step streams its inputs (frames, decoder features, noise: > 126 MB at every "
                     "workload) plus the saved planes of the loss scales through the 126 MB L2")
     config["submission"] = "eager" if args.no_graph else "cuda_graph"
+    config["frame_only_work"] = ("identity reprojection losses + pixel-interleaved source copies: every step computes them "
+                                 "for the NEXT input set inside its own graph, at low stream priority under its backward, "
+                                 "and consumes what the previous step prepared (HotPath.prepare_next; once per step, as "
+                                 "in the reference)")
     if world > 1:
         config["grad_exchange"] = (
             "(summary-path backward leaves %d SMs to the NCCL kernel) " % (32 if args.exchange_sms < 0 else args.exchange_sms) +

@@ -67,49 +67,56 @@ __device__ __forceinline__ float upsample_blocks(const float* __restrict__ lr, f
   const int f = F > 0 ? F : fr;
   const float rf = 1.f / (float)f;
   const int half = f >> 1;
-  const int rows_per_item = f <= 2 ? f : 1;
-  const int groups = f / rows_per_item;
-  const int items = h * w * groups;
   float s1 = 0.f;
-  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
-    const int cell = it / groups, grp = it - cell * groups;
-    const int i = cell / w, j = cell - i * w;
-    const int i1 = min(i + 1, h - 1), j1 = min(j + 1, w - 1);
-    const float a = __ldg(lr + i * w + j), bq = __ldg(lr + i * w + j1);
-    const float c = __ldg(lr + i1 * w + j), dq = __ldg(lr + i1 * w + j1);
-    if (F > 1 && i > 0 && j > 0 && i < h - 1 && j < w - 1) {
-      // interior cell: compile-time weights, no range checks
+  // A block walks whole rows of cells; a thread owns a cell column j and, when the row is narrower than the block, one of
+  // `nrg` interleaved subsets of the cell's F pixel rows: ONE index division per thread (not two per item as in the first
+  // version, 83 instructions per output pixel), and the F pixels of a row segment leave next to the neighbouring
+  // thread's.
+  const int nrg = w >= (int)blockDim.x ? 1 : min(f, (int)blockDim.x / w);
+  const int rg = nrg == 1 ? 0 : (int)threadIdx.x / w;
+  const int jstep = nrg == 1 ? (int)blockDim.x : w;
+  const int j0 = (int)threadIdx.x - rg * w;
+  if (rg >= nrg) return s1;
+  for (int i = blockIdx.x; i < h; i += gridDim.x) {
+    const int i1 = min(i + 1, h - 1);
+    const float* r0 = lr + (size_t)i * w;
+    const float* r1 = lr + (size_t)i1 * w;
+    for (int j = j0; j < w; j += jstep) {
+      const int j1 = min(j + 1, w - 1);
+      const float a = __ldg(r0 + j), bq = __ldg(r0 + j1), c = __ldg(r1 + j), dq = __ldg(r1 + j1);
+      if (F > 1 && i > 0 && j > 0 && i < h - 1 && j < w - 1) {
+        // interior cell: compile-time column weights, no range checks
+        float* blk = dup + (size_t)(F * i + half) * W + (F * j + half);
+        for (int r = rg; r < F; r += nrg) {
+          const float wy = ((float)r + 0.5f) * rf;
+          const float top = 1.f - wy;
+          float* row = blk + (size_t)r * W;
 #pragma unroll
-      for (int rr = 0; rr < (F <= 2 ? F : 1); ++rr) {
-        const int r = grp * rows_per_item + rr;
-        const float wy = ((float)r + 0.5f) * rf;
-        float* row = dup + (size_t)(F * i + half + r) * W + (F * j + half);
-#pragma unroll
-        for (int q = 0; q < F; ++q) {
-          const float wx = ((float)q + 0.5f) * rf;
-          const float d = (1.f - wy) * ((1.f - wx) * a + wx * bq) + wy * ((1.f - wx) * c + wx * dq);   // as upsample_at
-          row[q] = d;
+          for (int q = 0; q < F; ++q) {
+            const float wx = ((float)q + 0.5f) * rf;
+            const float d = top * ((1.f - wx) * a + wx * bq) + wy * ((1.f - wx) * c + wx * dq);   // as upsample_at
+            row[q] = d;
+            s1 += __fdividef(1.f, d);
+          }
+        }
+        continue;
+      }
+      // border cells (and the runtime-factor path): the first cell row / column also owns the clamped pixels before it
+      // (row-group 0 takes the extra rows)
+      const int c_lo = (j == 0) ? -half : 0;
+      for (int r = (i == 0 && rg == 0) ? -half : rg; r < f; r += (r < 0 ? 1 : nrg)) {
+        const int v = f * i + half + r;
+        if (v >= H) break;
+        const float wy = f == 1 ? 0.f : fmaxf(((float)r + 0.5f) * rf, 0.f);
+        float* row = dup + (size_t)v * W;
+        for (int q = c_lo; q < f; ++q) {
+          const int u = f * j + half + q;
+          if (u >= W) break;
+          const float wx = f == 1 ? 0.f : fmaxf(((float)q + 0.5f) * rf, 0.f);
+          const float d = (1.f - wy) * ((1.f - wx) * a + wx * bq) + wy * ((1.f - wx) * c + wx * dq);
+          row[u] = d;
           s1 += __fdividef(1.f, d);
         }
-      }
-      continue;
-    }
-    // border cells (and the runtime-factor path): the first cell row / column also owns the clamped pixels before it
-    int r_lo = grp * rows_per_item, r_hi = r_lo + rows_per_item;
-    if (i == 0 && grp == 0) r_lo = -half;
-    const int c_lo = (j == 0) ? -half : 0;
-    for (int r = r_lo; r < r_hi; ++r) {
-      const int v = f * i + half + r;
-      if (v >= H) break;
-      const float wy = f == 1 ? 0.f : fmaxf(((float)r + 0.5f) * rf, 0.f);
-      float* row = dup + (size_t)v * W;
-      for (int q = c_lo; q < f; ++q) {
-        const int u = f * j + half + q;
-        if (u >= W) break;
-        const float wx = f == 1 ? 0.f : fmaxf(((float)q + 0.5f) * rf, 0.f);
-        const float d = (1.f - wy) * ((1.f - wx) * a + wx * bq) + wy * ((1.f - wx) * c + wx * dq);
-        row[u] = d;
-        s1 += __fdividef(1.f, d);
       }
     }
   }
@@ -285,7 +292,28 @@ __global__ void ms_smooth_loss_kernel(MsShapes sh, float* __restrict__ spartial,
       float* o = spartial + (((size_t)sc * B + b) * kMsBlocks + blockIdx.x) * 3;
       o[0] = t0; o[1] = t1; o[2] = t2;
       __threadfence();
-      is_last = atomicAdd(counter, 1u) == gridDim.x * gridDim.y * gridDim.z - 1;
+      // two-level arrival: 1) the blocks of this (scale, sample) -- the counters the statistics kernel left zero --
+      // 2) the (scale, sample) groups of the launch.  (One counter for all ~1500 blocks of the launch serialised their
+      // atomics on one address and left every reduction to a single block.)
+      is_last = atomicAdd(&counter[64 + sc * B + b], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // last block of this (scale, sample): its three sums, fixed order (lane j owns partials j, j + 32, ...; shuffle tree)
+    if (threadIdx.x < 96) {
+      const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      const float* q = spartial + ((size_t)sc * B + b) * kMsBlocks * 3 + k;
+      float v = 0.f;
+      for (int j = lane; j < (int)gridDim.x; j += 32) v += __ldcg(q + j * 3);
+      v = warp_sum(v);
+      if (lane == 0) sums[((size_t)sc * B + b) * 3 + k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      counter[64 + sc * B + b] = 0u;
+      __threadfence();
+      is_last = atomicAdd(counter, 1u) == gridDim.y * gridDim.z - 1;
     }
     __syncthreads();
     if (!is_last) return;
@@ -293,14 +321,6 @@ __global__ void ms_smooth_loss_kernel(MsShapes sh, float* __restrict__ spartial,
   }
   // ---- last block of the launch: every reduction in a fixed order, spread over the block's threads
   const int ns = sh.ns;
-  for (int i = threadIdx.x; i < ns * B * 3; i += blockDim.x) {
-    const int k = i % 3, sb = i / 3;
-    const float* q = spartial + (size_t)sb * kMsBlocks * 3 + k;
-    float v = 0.f;
-#pragma unroll 8
-    for (int j = 0; j < (int)gridDim.x; ++j) v += __ldcg(q + j * 3);
-    sums[i] = v;
-  }
   // photometric per-CTA partials of every scale: strided double sums, one tree for all scales
   double acc[SQLX_MAX_SCALES];
 #pragma unroll
@@ -339,8 +359,9 @@ __global__ void ms_smooth_loss_kernel(MsShapes sh, float* __restrict__ spartial,
     const float Hc = (float)sh.Hc[s], Wc = (float)sh.Wc[s];
     const float rN = 1.f / (Hc * Wc), rNx = 1.f / ((float)B * Hc * (Wc - 1.f)), rNy = 1.f / ((float)B * (Hc - 1.f) * Wc);
     const float* q = sums + (size_t)i * 3;
-    const float inv = 1.f / (q[2] * rN + 1e-7f);
-    sterm[i] = (q[0] * inv) * rNx + (q[1] * inv) * rNy;
+    const float q0 = __ldcg(q), q1 = __ldcg(q + 1), q2 = __ldcg(q + 2);      // written by other blocks of this launch
+    const float inv = 1.f / (q2 * rN + 1e-7f);
+    sterm[i] = (q0 * inv) * rNx + (q1 * inv) * rNy;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -751,6 +772,14 @@ int ms_blocks(int H, int W) {
   if (k < 24) k = 24;
   return k > kMsBlocks ? kMsBlocks : k;
 }
+// the same, capped so that the (blocks, B, ns) grid of 256-thread blocks is ONE wave (8 blocks per SM): these kernels end
+// with a block-level reduction and an arrival counter, and a partial second wave doubled their elapsed time
+int ms_blocks_one_wave(int H, int W, int B, int ns) {
+  int k = ms_blocks(H, W);
+  const int cap = (8 * kNumSMs) / (B * ns > 0 ? B * ns : 1);
+  if (k > cap) k = cap;
+  return k < 4 ? 4 : k;
+}
 
 sqlx_photo_desc scale_photo_desc(const sqlx_ms_desc* d, int s) {
   sqlx_photo_desc pd = d->photo;
@@ -799,7 +828,7 @@ extern "C" int sqlx_ms_loss_fwd(const sqlx_ms_desc* d, const float* const* depth
     return check_launch("cudaMemsetAsync(counters)");
   {
     ProfScope prof("ms_stats_pose_kernel", st);
-    ms_stats_pose_kernel<<<dim3(ms_blocks(d->photo.H, d->photo.W), B, ns), 256, 0, st>>>(
+    ms_stats_pose_kernel<<<dim3(ms_blocks_one_wave(d->photo.H, d->photo.W, B, ns), B, ns), 256, 0, st>>>(
         sh, make_pose(poses, S, nullptr, nullptr), rescale, reinterpret_cast<float*>(ws + L.partial), counters + 64,
         stats, T);
     if (int e = check_launch("ms_stats_pose_kernel")) return e;
@@ -826,7 +855,7 @@ extern "C" int sqlx_ms_loss_fwd(const sqlx_ms_desc* d, const float* const* depth
   }
   {
     ProfScope prof("ms_smooth_loss_kernel", st);
-    ms_smooth_loss_kernel<<<dim3(ms_blocks(d->photo.H, d->photo.W), B, ns), 256, sizeof(float) * (size_t)ns * B, st>>>(sh, reinterpret_cast<float*>(ws + L.spartial), sums,
+    ms_smooth_loss_kernel<<<dim3(ms_blocks_one_wave(d->photo.H, d->photo.W, B, ns), B, ns), 256, sizeof(float) * (size_t)ns * B, st>>>(sh, reinterpret_cast<float*>(ws + L.spartial), sums,
                                                                   reinterpret_cast<float*>(ws + L.photo_partial),
                                                                   L.max_ctas, ctas, counters, loss);
     if (int e = check_launch("ms_smooth_loss_kernel")) return e;

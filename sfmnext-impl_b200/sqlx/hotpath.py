@@ -57,7 +57,8 @@ class HotPath(torch.nn.Module):
     """Parameters: the decoder's 1x1 conv (convert_to_prob.0) and bins_regressor.  Inputs live in static
     device buffers `self.inp[name]` (see HotPathConfig.input_shapes); `load()` copies a host batch into them."""
 
-    def __init__(self, cfg, device="cuda", use_graph=True, num_slots=1, grad_exchange=None, exchange_sm_reserve=32):
+    def __init__(self, cfg, device="cuda", use_graph=True, num_slots=1, grad_exchange=None, exchange_sm_reserve=32,
+                 prepare_next=True, prepare_fork="auto"):
         super().__init__()
         nn = torch.nn
         self.cfg = cfg
@@ -126,6 +127,31 @@ class HotPath(torch.nn.Module):
         self.loss = None
         self.pred = None
         self.side_stream = None
+        # Frame-only work of a step -- the identity reprojection losses (trainer.py:480-493) and the pixel-interleaved
+        # source copies: 87 us of full-GPU kernels at config 2 that depend on nothing but the input frames.  Run at the
+        # start of the step they compete with the decoder tail for SMs and barely overlap (measured: removing them takes
+        # the step from 1.039 to 0.955 ms).  With prepare_next, every step instead computes them for the NEXT input set
+        # (the one after `slot`, round-robin; the same set when there is one) on the side stream during its own backward
+        # tail (forked right after the regression-path kernel: partial sums, bins-head backward, glue kernels follow, ~70 us
+        # of grids that leave most SMs idle) into
+        # persistent per-set buffers, and consumes what the previous step prepared.  Every step still does this work
+        # exactly once, inside its own graph; a set whose frames changed after it was prepared (load) is re-prepared
+        # eagerly before its step.
+        self.prepare_next = prepare_next
+        # Where the preparation is forked.  The step is captured from a high-priority stream and the preparation runs at
+        # priority 0, but priorities only arbitrate FREE resources: a one-CTA-per-SM tcgen05 kernel (227 KB of shared
+        # memory) cannot displace a stream of small identity-loss CTAs that keep refilling the SM, so the preparation must
+        # not run beside those kernels for long.  Measured (ms/step, configs 2 / 3 / 4; no preparation overlap: 1.039 /
+        # 1.095 / 3.033):  "after_bwd_pred" (small grids follow for ~70 us) 1.002 / 1.079 / 3.025;  "start" (whole step)
+        # 1.010 / 1.051 / 2.982;  end of the forward 1.043 / 1.051 / 3.052;  start of the decoder-tail backward 1.031 /
+        # 1.095 / 3.033.  "auto": "start" for the 128-query shapes (longer small-grid stretches), else "after_bwd_pred".
+        assert prepare_fork in ("auto", "start", "after_bwd_pred")
+        self.prepare_fork = prepare_fork
+        self._prep = [None] * num_slots            # (identity [B,S,H,W] or None, [S x packed [B,H,W,4]])
+        self._prep_valid = [False] * num_slots
+        self._prep_forked = False
+        self._capture_stream = None
+        self._graph_prepares = [False] * num_slots   # whether the captured graph of a set prepares the next one
         # grad_exchange(flat gradient bucket): in-place data-parallel exchange (e.g. an NCCL all-reduce, average) of the
         # parameter gradients.  It is issued INSIDE the step, on a side stream, as soon as the last parameter gradient
         # exists, so that it overlaps the summary-path backward kernel; the step (eager or captured graph, NCCL
@@ -144,6 +170,7 @@ class HotPath(torch.nn.Module):
         conversion (transforms.ToTensor) on the host and ships four bytes per channel."""
         n = 0
         inp = self.slots[slot]
+        self._prep_valid[slot] = False
         with torch.no_grad():
             for k, v in host_batch.items():
                 inp[k].copy_(v, non_blocking=non_blocking)
@@ -182,6 +209,7 @@ class HotPath(torch.nn.Module):
         """Two host->device copies for a whole batch (pack_host layout) plus, for uint8 frames, ONE scaling kernel;
         returns the bytes copied."""
         fl = self.flat[slot]
+        self._prep_valid[slot] = False
         with torch.no_grad():
             fl["other"][:other.numel()].copy_(other, non_blocking=non_blocking)
             if frames.dtype == torch.uint8:
@@ -211,16 +239,33 @@ class HotPath(torch.nn.Module):
         if self.side_stream is None:
             self.side_stream = torch.cuda.Stream()
         side = self.side_stream
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            identity = P.identity_losses(I["target"], sources) if c.automask else None
-            packed = [P.pack_rgba(src) for src in sources]
+        if self.prepare_next:
+            # prepared by the previous step (or eagerly by step() / step_eager() when the set's frames are new)
+            identity, packed = self._prep[slot]
+            side = None
+        else:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                identity = P.identity_losses(I["target"], sources) if c.automask else None
+                packed = [P.pack_rgba(src) for src in sources]
         gv = self.grad_views[slot]
         hook = (lambda grads: self._start_grad_exchange(slot)) if self.grad_exchange is not None else None
         S.exchange_sm_reserve = self.exchange_sm_reserve if hook is not None else 0
+        nxt = (slot + 1) % len(self.slots)
+        stage = None
+        if self.prepare_next:
+            where = self.prepare_fork
+            if where == "auto":
+                where = "start" if c.Q > 64 else "after_bwd_pred"
+            if where == "start" and nxt != slot and torch.is_grad_enabled():
+                self._fork_prepare(nxt)        # another input set: its buffers are independent of this step
+            else:
+                # (always for the SAME set: its packed sources are read until the photometric backward is done)
+                stage = lambda name: self._fork_prepare(nxt) if name == "after_bwd_pred" else None  # noqa: E731
         pred = S.sql_tail(I["x"], I["queries"], conv.weight.view(c.D, c.Q), conv.bias, self._centers_fn(slot), (),
-                          on_param_grads=hook, head_grad_out=(gv[0].view(c.D, c.Q), gv[1]))
-        main.wait_stream(side)
+                          on_param_grads=hook, head_grad_out=(gv[0].view(c.D, c.Q), gv[1]), on_stage=stage)
+        if side is not None:
+            main.wait_stream(side)
         disps = {s: (pred if s == 0 else I["disp%d" % s]) for s in c.scales}
         target_pyr = {s: (I["target"] if s == 0 else I["target%d" % s]) for s in c.scales}
         poses = [{"axisangle": I["axisangle%d" % i], "translation": I["translation%d" % i], "invert": i == 0}
@@ -247,6 +292,47 @@ class HotPath(torch.nn.Module):
             self.grad_exchange(self.grad_flat[slot])
         return lambda: torch.cuda.current_stream().wait_stream(comm)
 
+    # ------------------------------------------------------------------ frame-only work (see prepare_next)
+    def _run_prepare(self, slot):
+        """identity losses + packed sources of input set `slot` into its persistent buffers, on the current stream"""
+        c, I = self.cfg, self.slots[slot]
+        sources = [I["source%d" % i] for i in range(c.S)]
+        if self._prep[slot] is None:
+            ident = torch.empty(c.B, c.S, c.H, c.W, device=self.device, dtype=torch.float32) if c.automask else None
+            packed = [torch.empty(c.B, c.H, c.W, 4, device=self.device, dtype=torch.float32) for _ in sources]
+            self._prep[slot] = (ident, packed)
+        ident, packed = self._prep[slot]
+        with torch.no_grad():
+            if ident is not None:
+                P.identity_losses(I["target"], sources, out=ident)
+            for src, out in zip(sources, packed):
+                P.pack_rgba(src, out=out)
+
+    def _fork_prepare(self, slot):
+        """backward hook: the photometric backward (the last reader of the packed sources) is enqueued; fork the
+        preparation of the next input set onto the side stream, under the decoder tail's backward"""
+        main = torch.cuda.current_stream()
+        if self.side_stream is None:
+            self.side_stream = torch.cuda.Stream()
+        self.side_stream.wait_stream(main)
+        with torch.cuda.stream(self.side_stream):
+            self._run_prepare(slot)
+        self._prep_forked = True
+        return None
+
+    def _join_prepare(self):
+        """join the forked preparation (if the backward hook fired); returns whether there was one"""
+        forked, self._prep_forked = self._prep_forked, False
+        if forked:
+            torch.cuda.current_stream().wait_stream(self.side_stream)
+        return forked
+
+    def _ensure_prepared(self, slot):
+        """eager preparation of a set whose frames were (re)loaded after the last step prepared it"""
+        if self.prepare_next and not self._prep_valid[slot]:
+            self._run_prepare(slot)
+            self._prep_valid[slot] = True
+
     def _zero_grads(self, slot=0):
         for k in self.grad_inputs:
             self.slots[slot][k].grad = None
@@ -257,8 +343,11 @@ class HotPath(torch.nn.Module):
 
     def step_eager(self, slot=0):
         self._zero_grads(slot)
+        self._ensure_prepared(slot)
         loss, pred = self.forward_loss(slot)
         torch.autograd.backward(loss, grad_tensors=self._one)     # (a static one: no fill kernel per step)
+        if self._join_prepare():
+            self._prep_valid[(slot + 1) % len(self.slots)] = True
         self._point_grads(slot)
         self.loss, self.pred = loss.detach(), pred.detach()
         self.losses[slot] = self.loss
@@ -277,10 +366,21 @@ class HotPath(torch.nn.Module):
         torch.cuda.synchronize()
         for k in self.grad_inputs:
             self.slots[slot][k].grad = None
+        if self.prepare_next:                       # the persistent buffers must exist before the capture
+            for sl in {slot, (slot + 1) % len(self.slots)}:
+                if self._prep[sl] is None:
+                    self._run_prepare(sl)
+                    self._prep_valid[sl] = True
+            torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # the step is captured from a HIGH-priority stream: the kernel nodes keep that priority, so whenever SM resources
+        # free up the step's own chain wins them over the side-stream work (next set's preparation, priority 0)
+        if self._capture_stream is None:
+            self._capture_stream = torch.cuda.Stream(priority=-1)
+        with torch.cuda.graph(g, stream=self._capture_stream):
             loss, pred = self.forward_loss(slot)
             torch.autograd.backward(loss, grad_tensors=self._one)
+            self._graph_prepares[slot] = self._join_prepare()
             self.losses[slot] = loss.detach()
             self.pred = pred.detach()
         self.graphs[slot] = g
@@ -295,7 +395,10 @@ class HotPath(torch.nn.Module):
         if self.use_graph:
             if self.graphs[slot] is None:
                 self.capture(slot=slot)
+            self._ensure_prepared(slot)
             self.graphs[slot].replay()
+            if self._graph_prepares[slot]:
+                self._prep_valid[(slot + 1) % len(self.slots)] = True
             self._point_grads(slot)
             self.loss = self.losses[slot]
             return self.loss

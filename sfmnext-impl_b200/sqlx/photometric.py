@@ -31,14 +31,17 @@ def _src_array(sources):
     return arr
 
 
-def pack_rgba(image):
+def pack_rgba(image, out=None):
     """[B,3,H,W] planar frame -> [B,H,W,4] pixel-interleaved frame (r,g,b,0): the layout the fused kernels gather
-    source frames from (one 128-bit load per bilinear tap).  Packed once per step, shared by all loss scales."""
+    source frames from (one 128-bit load per bilinear tap).  Packed once per step, shared by all loss scales.
+    out: optional preallocated [B,H,W,4] fp32 result buffer."""
     require_cuda(image)
     img = _f32c(image)
     B, C, H, W = img.shape
     assert C == 3
-    out = torch.empty(B, H, W, 4, device=img.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(B, H, W, 4, device=img.device, dtype=torch.float32)
+    assert out.shape == (B, H, W, 4) and out.dtype == torch.float32 and out.is_contiguous()
     check(lib().sqlx_pack_rgba(ptr(img), B, H, W, ptr(out), stream_ptr()), "sqlx_pack_rgba")
     return out
 
@@ -493,14 +496,17 @@ class _MultiScaleLoss(torch.autograd.Function):
             tuple(gr.reshape(sh) for gr, sh in zip(grads, pose_shapes))
 
 
-def identity_losses(target, sources, *, no_ssim=False, ssim_radius=3, w_ssim=0.85, w_l1=0.15):
-    """[B,S,H,W]: compute_reprojection_loss(source_f, target) for every source (trainer.py:480-493), no torch.cat."""
+def identity_losses(target, sources, *, no_ssim=False, ssim_radius=3, w_ssim=0.85, w_l1=0.15, out=None):
+    """[B,S,H,W]: compute_reprojection_loss(source_f, target) for every source (trainer.py:480-493), no torch.cat.
+    out: optional preallocated [B,S,H,W] fp32 result buffer."""
     require_cuda(target, *sources)
     tgt = _f32c(target)
     srcs = [_f32c(x) for x in sources]
     B, _, H, W = tgt.shape
     S = len(srcs)
-    out = torch.empty(B, S, H, W, device=tgt.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(B, S, H, W, device=tgt.device, dtype=torch.float32)
+    assert out.shape == (B, S, H, W) and out.dtype == torch.float32 and out.is_contiguous()
     check(lib().sqlx_identity_losses_fwd(ptr(tgt), _src_array(srcs), S, B, H, W, ssim_radius, w_ssim, w_l1, int(no_ssim),
                                          ptr(out), stream_ptr()), "sqlx_identity_losses_fwd")
     return out

@@ -297,9 +297,10 @@ class _SqlTail(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, queries, Wp, bp, centers_fn, n_params, on_param_grads, head_grad_out, *params):
+    def forward(ctx, x, queries, Wp, bp, centers_fn, n_params, on_param_grads, head_grad_out, on_stage, *params):
         ctx.set_materialize_grads(False)
         ctx.head_grad_out = head_grad_out
+        ctx.on_stage = on_stage
         xc, qc, Wc, bc = _f32c(x), _f32c(queries), _f32c(Wp), _f32c(bp)
         summary, row_max, row_sum, _ = summary_fwd(xc, qc)
         with torch.enable_grad():
@@ -323,7 +324,7 @@ class _SqlTail(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_pred):
         s_leaf, centers = ctx.graph
-        none = (None,) * (8 + len(ctx.params))
+        none = (None,) * (9 + len(ctx.params))
         if g_pred is None:
             return none
         g = _f32c(g_pred)
@@ -334,9 +335,13 @@ class _SqlTail(torch.autograd.Function):
         if ctx.mix:
             xc, qc, Wc, bc, cc, summary, row_max, row_sum, Mx, pred, stats = ctx.saved_tensors
             d_M, d_bp, d_centers, d_x = bwd_pred_mix(xc, Mx, bc, cc, g, pred, stats, d_bp=out_bp)
+            if ctx.on_stage is not None:
+                ctx.on_stage("after_bwd_pred")     # what follows is ~70 us of small grids (partial sums, bins-head backward)
         else:
             xc, qc, Wc, bc, cc, summary, row_max, row_sum = ctx.saved_tensors
             d_centers, d_Wp, d_bp = bwd_reduce(xc, qc, Wc, bc, cc, g)
+            if ctx.on_stage is not None:
+                ctx.on_stage("after_bwd_pred")
             if out_Wp is not None:
                 out_Wp.copy_(d_Wp.view_as(out_Wp)); out_bp.copy_(d_bp)
                 d_Wp, d_bp = out_Wp, out_bp
@@ -371,8 +376,8 @@ class _SqlTail(torch.autograd.Function):
         d_params = tuple((next(it) if p.requires_grad else None) for p in ctx.params)
         ctx.graph = None
         if out_Wp is not None:
-            return (d_x, d_q, None, None, None, None, None, None) + d_params
-        return (d_x, d_q, d_Wp.view_as(Wc), d_bp, None, None, None, None) + d_params
+            return (d_x, d_q, None, None, None, None, None, None, None) + d_params
+        return (d_x, d_q, d_Wp.view_as(Wc), d_bp, None, None, None, None, None) + d_params
 
 
 # SMs left free for the communication kernel while the summary-path backward runs beside an in-step gradient exchange
@@ -380,16 +385,18 @@ class _SqlTail(torch.autograd.Function):
 exchange_sm_reserve = 0
 
 
-def sql_tail(x, queries, Wp, bp, centers_fn, params=(), on_param_grads=None, head_grad_out=None):
+def sql_tail(x, queries, Wp, bp, centers_fn, params=(), on_param_grads=None, head_grad_out=None, on_stage=None):
     """pred [B,1,h,w] = sum_d softmax_d(Wp (x^T K) + bp) * centers_fn(summary(x, K)).
 
     on_param_grads(list of gradient tensors) -> join callable or None: called in the backward as soon as the gradients
     of Wp, bp and `params` exist (before the summary-path kernel runs), e.g. to start their all-reduce on a side
     stream; the returned callable is invoked once the remaining backward kernels are enqueued.
     head_grad_out = (d_Wp [D,Q], d_bp [D]) buffers: the gradients of Wp / bp are written there instead of being
-    returned to autograd (views of a flat gradient bucket: no pack / unpack around the all-reduce)."""
+    returned to autograd (views of a flat gradient bucket: no pack / unpack around the all-reduce).
+    on_stage(name): optional callback at points of the backward where a caller may fork independent work onto another
+    stream; "after_bwd_pred" = the regression-path kernel is enqueued and a stretch of small grids follows."""
     params = tuple(params)
-    return _SqlTail.apply(x, queries, Wp, bp, centers_fn, len(params), on_param_grads, head_grad_out, *params)
+    return _SqlTail.apply(x, queries, Wp, bp, centers_fn, len(params), on_param_grads, head_grad_out, on_stage, *params)
 
 
 class Depth_Decoder_QueryTr(torch.nn.Module):

@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--exchange-sms", type=int, default=-1,
                     help="N > 1: SMs the summary-path backward leaves to the NCCL kernel of the in-step exchange "
                          "(-1 = default 32)")
+    ap.add_argument("--prepare-fork", default="auto", choices=["auto", "start", "after_bwd_pred", "off"],
+                    help="where the step forks the next input set's frame-only work (HotPath.prepare_fork; off = computed "
+                         "at the start of the step it belongs to, as in round 1)")
     ap.add_argument("--prefetch", type=int, default=2, help="batches in flight ahead of the step in the e2e loop")
     return ap.parse_args()
 
@@ -353,7 +356,9 @@ def run_workload(cx, cfg_id, cfg, steps, warmup, full):
 
     nslots = max(2, args.prefetch + 1)
     hp = HotPath(cfg, device=dev, use_graph=not args.no_graph, num_slots=nslots,
-                 grad_exchange=exchange if exchange_in_step else None, exchange_sm_reserve=sm_reserve)
+                 grad_exchange=exchange if exchange_in_step else None, exchange_sm_reserve=sm_reserve,
+                 prepare_next=args.prepare_fork != "off",
+                 prepare_fork=args.prepare_fork if args.prepare_fork != "off" else "auto")
     state = head_state(cfg)                       # identical initial weights on every rank (seeded)
     hp.load_state_dict(state, strict=True)
     hb = make_host_batch(cfg, seed=1234 + rank, pin=True, u8_frames=not args.f32_frames)

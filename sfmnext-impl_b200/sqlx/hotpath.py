@@ -144,7 +144,9 @@ class HotPath(torch.nn.Module):
         # not run beside those kernels for long.  Measured (ms/step, configs 2 / 3 / 4; no preparation overlap: 1.039 /
         # 1.095 / 3.033):  "after_bwd_pred" (small grids follow for ~70 us) 1.002 / 1.079 / 3.025;  "start" (whole step)
         # 1.010 / 1.051 / 2.982;  end of the forward 1.043 / 1.051 / 3.052;  start of the decoder-tail backward 1.031 /
-        # 1.095 / 3.033.  "auto": "start" for the 128-query shapes (longer small-grid stretches), else "after_bwd_pred".
+        # 1.095 / 3.033.  With an in-step gradient exchange the window after the regression-path kernel belongs to the
+        # collective (2 x B200, config 2: "after_bwd_pred" 1.051 ms with 49 us of exposed communication, "start" 1.039 ms
+        # with 15 us).  "auto": "start" for the 128-query shapes and whenever there is an exchange, else "after_bwd_pred".
         assert prepare_fork in ("auto", "start", "after_bwd_pred")
         self.prepare_fork = prepare_fork
         self._prep = [None] * num_slots            # (identity [B,S,H,W] or None, [S x packed [B,H,W,4]])
@@ -256,7 +258,7 @@ class HotPath(torch.nn.Module):
         if self.prepare_next:
             where = self.prepare_fork
             if where == "auto":
-                where = "start" if c.Q > 64 else "after_bwd_pred"
+                where = "start" if (c.Q > 64 or self.grad_exchange is not None) else "after_bwd_pred"
             if where == "start" and nxt != slot and torch.is_grad_enabled():
                 self._fork_prepare(nxt)        # another input set: its buffers are independent of this step
             else:
@@ -285,7 +287,9 @@ class HotPath(torch.nn.Module):
         enqueued so far; returns the join"""
         main = torch.cuda.current_stream()
         if self.comm_stream is None:
-            self.comm_stream = torch.cuda.Stream()
+            # high priority, like the step itself: the collective's CTAs spin on their peers and must not queue behind
+            # the low-priority preparation of the next input set
+            self.comm_stream = torch.cuda.Stream(priority=-1)
         comm = self.comm_stream
         comm.wait_stream(main)
         with torch.cuda.stream(comm):

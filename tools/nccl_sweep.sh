@@ -3,11 +3,12 @@
 #   gpurun --gpus 8 --timeout 600 -- 'bash tools/nccl_sweep.sh 8 "0 8 16 32"'
 N=${1:-8}
 SWEEP=${2:-"0 8 16 32"}
+FORK=${3:-auto}
 mkdir -p gpurun_out
 run() {
   tag=$1; sms=$2; shift; shift
   env "$@" timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
-    bench.py --gpus $N --steps 100 --warmup 10 --no-extras --no-parity --no-cpu-baseline --workloads "" --exchange-sms $sms \
+    bench.py --gpus $N --steps 100 --warmup 10 --no-extras --no-parity --no-cpu-baseline --workloads "" --exchange-sms $sms --prepare-fork $FORK \
     > gpurun_out/nccl_${tag}.json 2> gpurun_out/nccl_${tag}.err
   python - "$tag" <<'PY'
 import json, sys
@@ -19,4 +20,4 @@ except Exception as e:
     print(tag, "failed", e)
 PY
 }
-for s in $SWEEP; do run n${N}_reserve$s $s NCCL_DEBUG=WARN; done
+for s in $SWEEP; do run n${N}_reserve${s}_${FORK} $s NCCL_DEBUG=WARN; done

@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--exchange-sms", type=int, default=-1,
                     help="N > 1: SMs the summary-path backward leaves to the NCCL kernel of the in-step exchange "
                          "(-1 = default 32)")
-    ap.add_argument("--prepare-fork", default="auto", choices=["auto", "start", "after_bwd_pred", "off"],
+    ap.add_argument("--prepare-fork", default="auto", choices=["auto", "start", "after_pred_fwd", "after_bwd_pred", "off"],
                     help="where the step forks the next input set's frame-only work (HotPath.prepare_fork; off = computed "
                          "at the start of the step it belongs to, as in round 1)")
     ap.add_argument("--prefetch", type=int, default=2, help="batches in flight ahead of the step in the e2e loop")

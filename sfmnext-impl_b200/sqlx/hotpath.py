@@ -141,13 +141,17 @@ class HotPath(torch.nn.Module):
         # Where the preparation is forked.  The step is captured from a high-priority stream and the preparation runs at
         # priority 0, but priorities only arbitrate FREE resources: a one-CTA-per-SM tcgen05 kernel (227 KB of shared
         # memory) cannot displace a stream of small identity-loss CTAs that keep refilling the SM, so the preparation must
-        # not run beside those kernels for long.  Measured (ms/step, configs 2 / 3 / 4; no preparation overlap: 1.039 /
-        # 1.095 / 3.033):  "after_bwd_pred" (small grids follow for ~70 us) 1.002 / 1.079 / 3.025;  "start" (whole step)
-        # 1.010 / 1.051 / 2.982;  end of the forward 1.043 / 1.051 / 3.052;  start of the decoder-tail backward 1.031 /
-        # 1.095 / 3.033.  With an in-step gradient exchange the window after the regression-path kernel belongs to the
-        # collective (2 x B200, config 2: "after_bwd_pred" 1.051 ms with 49 us of exposed communication, "start" 1.039 ms
-        # with 15 us).  "auto": "start" for the 128-query shapes and whenever there is an exchange, else "after_bwd_pred".
-        assert prepare_fork in ("auto", "start", "after_bwd_pred")
+        # not start while such kernels are still to come soon.  Measured on one B200 (ms/step, configs 2 / 3 / 4; frame-only
+        # work at the start of its own step as in round 1: 1.039 / 1.095 / 3.033):
+        #   "after_pred_fwd"  (the forward's last tcgen05 kernel is enqueued; the work then fills the wave tails of the
+        #                     photometric kernels, the reduction tails and the single-block pose backward)  1.001 / 1.024 / 2.928
+        #   "after_bwd_pred"  (~70 us of small grids follow)                                                 1.002 / 1.079 / 3.025
+        #   "start"                                                                                          1.010 / 1.051 / 2.982
+        #   end of the forward 1.043 / 1.051 / 3.052;  start of the decoder-tail backward 1.031 / 1.095 / 3.033
+        # With an in-step gradient exchange the window after the regression-path backward belongs to the collective
+        # (2 x B200, config 2: "after_bwd_pred" 1.051 ms with 49 us of exposed communication, "start" 1.039 ms with 15 us).
+        # "auto" = "after_pred_fwd"; preparing the SAME set (one input set) always waits for "after_bwd_pred".
+        assert prepare_fork in ("auto", "start", "after_pred_fwd", "after_bwd_pred")
         self.prepare_fork = prepare_fork
         self._prep = [None] * num_slots            # (identity [B,S,H,W] or None, [S x packed [B,H,W,4]])
         self._prep_valid = [False] * num_slots
@@ -258,12 +262,13 @@ class HotPath(torch.nn.Module):
         if self.prepare_next:
             where = self.prepare_fork
             if where == "auto":
-                where = "start" if (c.Q > 64 or self.grad_exchange is not None) else "after_bwd_pred"
-            if where == "start" and nxt != slot and torch.is_grad_enabled():
+                where = "after_pred_fwd"
+            if nxt == slot or not torch.is_grad_enabled():
+                where = "after_bwd_pred"       # the SAME set: its packed sources are read until the photometric backward is done
+            if where == "start":
                 self._fork_prepare(nxt)        # another input set: its buffers are independent of this step
             else:
-                # (always for the SAME set: its packed sources are read until the photometric backward is done)
-                stage = lambda name: self._fork_prepare(nxt) if name == "after_bwd_pred" else None  # noqa: E731
+                stage = lambda name: self._fork_prepare(nxt) if name == where else None  # noqa: E731
         pred = S.sql_tail(I["x"], I["queries"], conv.weight.view(c.D, c.Q), conv.bias, self._centers_fn(slot), (),
                           on_param_grads=hook, head_grad_out=(gv[0].view(c.D, c.Q), gv[1]), on_stage=stage)
         if side is not None:

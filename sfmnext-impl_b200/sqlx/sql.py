@@ -319,6 +319,8 @@ class _SqlTail(torch.autograd.Function):
         ctx.graph = (s_leaf, centers)
         ctx.params = params
         ctx.on_param_grads = on_param_grads
+        if on_stage is not None:
+            on_stage("after_pred_fwd")         # the last one-CTA-per-SM kernel of the forward is enqueued
         return pred
 
     @staticmethod
@@ -394,7 +396,8 @@ def sql_tail(x, queries, Wp, bp, centers_fn, params=(), on_param_grads=None, hea
     head_grad_out = (d_Wp [D,Q], d_bp [D]) buffers: the gradients of Wp / bp are written there instead of being
     returned to autograd (views of a flat gradient bucket: no pack / unpack around the all-reduce).
     on_stage(name): optional callback at points of the backward where a caller may fork independent work onto another
-    stream; "after_bwd_pred" = the regression-path kernel is enqueued and a stretch of small grids follows."""
+    stream; "after_pred_fwd" = the forward's last kernel is enqueued; "after_bwd_pred" = the regression-path backward
+    kernel is enqueued and a stretch of small grids follows."""
     params = tuple(params)
     return _SqlTail.apply(x, queries, Wp, bp, centers_fn, len(params), on_param_grads, head_grad_out, on_stage, *params)
 

@@ -21,7 +21,7 @@ def _grads(hp):
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
-@pytest.mark.parametrize("num_slots,fork", [(1, "auto"), (2, "after_bwd_pred"), (3, "start")])
+@pytest.mark.parametrize("num_slots,fork", [(1, "auto"), (2, "after_bwd_pred"), (3, "start"), (2, "after_pred_fwd")])
 def test_prepare_next_matches_in_step_preparation(use_graph, num_slots, fork):
     cfg = baseline_config(2, B=2)
     batches = [make_host_batch(cfg, seed=100 + i) for i in range(4)]

@@ -66,29 +66,43 @@ __global__ void __launch_bounds__(128) head_linear_fwd_kernel(const float* __res
 
 // Backward of one Linear layer in ONE launch (both halves only need dy, y, x, W):
 //   dz[b,n] = dy[b,n] * act'(y[b,n]);  dW[n,k] = sum_b dz[b,n] x[b,k];  db[n] = sum_b dz[b,n];  dx[b,k] = sum_n dz[b,n] W[n,k]
-// The first `nx` CTAs compute dx (the critical path of the backward chain: the next layer waits for it), the
-// following N CTAs one row of dW each; the two halves overlap on the machine instead of running back to back.
-//   dx CTA: 32 input features k (lane = k: W rows are read as coalesced 128-byte segments); the 8 warps split the
-//           output rows n, dz is derived from (dy, y) and staged once per CTA as [n][16 samples] (128-bit broadcast
-//           loads), partial sums meet in shared memory: no atomics, fixed summation order.
-//   dW CTA: x staged once in shared memory, then one row per warp: 128-bit stores against all samples at once.
-constexpr int kHeadXWarps = 8;
+// The first `nx` CTAs compute dx (the critical path of the backward chain: the next layer waits for it), the others dW;
+// both halves fit two CTAs per SM so that the whole grid is ONE wave and the halves overlap on the machine.
+//   dx CTA: 32 input features k (lane = k: W rows are read as coalesced 128-byte segments); the 16 warps split the
+//           output rows n (16 rows in flight each), dz is derived from (dy, y) and staged once per CTA as [n][Bp samples]
+//           (128-bit broadcast loads), partial sums meet in shared memory: no atomics, fixed summation order.
+//   dW CTA: a (1024-column slab, 16..64-row chunk) block of dW (chunk sized so that the grid fills the machine once): the slab of x is staged once in shared memory (every sample's
+//           loads in flight together), then one row per warp at a time: 128-bit stores against all samples at once.
+// (Round 2, first version: the dW CTAs staged ALL of x -- 128 KB, one load in flight per thread and trip -- and the 128 KB
+// of either half allowed one CTA per SM, i.e. two waves: 75 us for the 2048 x 4096 layer under ncu.)
+constexpr int kHeadXWarps = 16;
 constexpr int kHeadBwdThreads = 32 * kHeadXWarps;
+constexpr int kHeadSlab = 1024;      // dW: columns per CTA
+constexpr size_t kHeadPartBytes = sizeof(float) * kHeadXWarps * kHeadMaxB * 33;
+
 __global__ void __launch_bounds__(kHeadBwdThreads) head_linear_bwd_kernel(
     const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, const float* __restrict__ W,
-    int B, int N, int K, int leaky, int nx, float* __restrict__ dz, float* __restrict__ dW, float* __restrict__ db,
-    float* __restrict__ dx) {
-  extern __shared__ __align__(16) float sdz[];             // dx CTAs: [N][16]
-  __shared__ float part[kHeadXWarps][kHeadMaxB][33];
+    int B, int Bp, int N, int K, int leaky, int nx, int nslab, int rows_per_cta, float* __restrict__ dz, float* __restrict__ dW,
+    float* __restrict__ db, float* __restrict__ dx) {
+  extern __shared__ __align__(16) float smem[];           // dx CTAs: dz [N][Bp], then the partial sums; dW CTAs: x slab
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if ((int)blockIdx.x >= nx) {
-    // ---- rows of dW (and db, dz): x [B,K] staged once per CTA, one weight-gradient row per warp at a time
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int K4 = K >> 2;
-    float4* sx4 = reinterpret_cast<float4*>(sdz);
-    for (int i = threadIdx.x; i < B * K4; i += kHeadBwdThreads) sx4[i] = __ldg(reinterpret_cast<const float4*>(x) + i);
+    // ---- a (slab, chunk) block of dW (and, from the CTAs of slab 0, db and dz)
+    const int id = blockIdx.x - nx, slab = id % nslab, chunk = id / nslab;
+    const int k0 = slab * kHeadSlab, kw4 = min(kHeadSlab, K - k0) >> 2;
+    float4* sx4 = reinterpret_cast<float4*>(smem);          // [B][kw4]
+    for (int c = threadIdx.x; c < kw4; c += kHeadBwdThreads) {
+      float4 v[kHeadMaxB];
+#pragma unroll
+      for (int b = 0; b < kHeadMaxB; ++b)
+        if (b < B) v[b] = __ldg(reinterpret_cast<const float4*>(x + (size_t)b * K + k0) + c);
+#pragma unroll
+      for (int b = 0; b < kHeadMaxB; ++b)
+        if (b < B) sx4[b * kw4 + c] = v[b];
+    }
     __syncthreads();
-    const int nw = gridDim.x - nx;                       // CTAs of this half
-    for (int n = (blockIdx.x - nx) * kHeadXWarps + warp; n < N; n += nw * kHeadXWarps) {
+    const int n_end = min(N, (chunk + 1) * rows_per_cta);
+    for (int n = chunk * rows_per_cta + warp; n < n_end; n += kHeadXWarps) {
       float g[kHeadMaxB];
       float bsum = 0.f;
 #pragma unroll
@@ -101,20 +115,22 @@ __global__ void __launch_bounds__(kHeadBwdThreads) head_linear_bwd_kernel(
           bsum += v;
         }
       }
-      if (lane < B) {
-        float mine = 0.f;
+      if (slab == 0) {
+        if (lane < B) {
+          float mine = 0.f;
 #pragma unroll
-        for (int b = 0; b < kHeadMaxB; ++b) mine = (b == lane) ? g[b] : mine;
-        dz[(size_t)lane * N + n] = mine;
+          for (int b = 0; b < kHeadMaxB; ++b) mine = (b == lane) ? g[b] : mine;
+          dz[(size_t)lane * N + n] = mine;
+        }
+        if (lane == 0) db[n] = bsum;
       }
-      if (lane == 0) db[n] = bsum;
-      float4* out = reinterpret_cast<float4*>(dW + (size_t)n * K);
-      for (int k4 = lane; k4 < K4; k4 += 32) {
+      float4* out = reinterpret_cast<float4*>(dW + (size_t)n * K + k0);
+      for (int k4 = lane; k4 < kw4; k4 += 32) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int b = 0; b < kHeadMaxB; ++b) {
           if (b < B) {
-            const float4 xv = sx4[b * K4 + k4];
+            const float4 xv = sx4[b * kw4 + k4];
             a.x = fmaf(g[b], xv.x, a.x); a.y = fmaf(g[b], xv.y, a.y); a.z = fmaf(g[b], xv.z, a.z); a.w = fmaf(g[b], xv.w, a.w);
           }
         }
@@ -124,10 +140,10 @@ __global__ void __launch_bounds__(kHeadBwdThreads) head_linear_bwd_kernel(
     return;
   }
   // ---- 32 columns of dx
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sdz = smem;
   const int k = blockIdx.x * 32 + lane;
   // dz staging: one output row n per thread and trip, all samples' dy (and y) loads in flight together; every load is
-  // coalesced across the threads (consecutive n), the 16 values of a row leave as four 128-bit shared stores
+  // coalesced across the threads (consecutive n), the Bp values of a row leave as 128-bit shared stores
   for (int n = threadIdx.x; n < N; n += kHeadBwdThreads) {
     float v[kHeadMaxB], a[kHeadMaxB];
 #pragma unroll
@@ -137,9 +153,10 @@ __global__ void __launch_bounds__(kHeadBwdThreads) head_linear_bwd_kernel(
     }
 #pragma unroll
     for (int b = 0; b < kHeadMaxB; ++b) v[b] = (a[b] > 0.f) ? v[b] : v[b] * kLeakySlope;
-    float4* dst = reinterpret_cast<float4*>(sdz + (size_t)n * kHeadMaxB);
+    float4* dst = reinterpret_cast<float4*>(sdz + (size_t)n * Bp);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < 4; ++q)
+      if (4 * q < Bp) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
   __syncthreads();
   float acc[kHeadMaxB];
@@ -156,23 +173,26 @@ __global__ void __launch_bounds__(kHeadBwdThreads) head_linear_bwd_kernel(
 #pragma unroll
     for (int j = 0; j < kRows; ++j) {
       if (nb + j >= n1) break;
-      const float4* zr = reinterpret_cast<const float4*>(sdz + (size_t)(nb + j) * kHeadMaxB);
+      const float4* zr = reinterpret_cast<const float4*>(sdz + (size_t)(nb + j) * Bp);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
+        if (4 * q >= Bp) break;
         const float4 z = zr[q];
         acc[4 * q] = fmaf(z.x, wv[j], acc[4 * q]); acc[4 * q + 1] = fmaf(z.y, wv[j], acc[4 * q + 1]);
         acc[4 * q + 2] = fmaf(z.z, wv[j], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(z.w, wv[j], acc[4 * q + 3]);
       }
     }
   }
+  __syncthreads();                              // every warp is done with the staged dz: its memory holds the partials now
+  float* part = smem;                           // [warps][kHeadMaxB][33]
 #pragma unroll
-  for (int b = 0; b < kHeadMaxB; ++b) part[warp][b][lane] = acc[b];
+  for (int b = 0; b < kHeadMaxB; ++b) part[(warp * kHeadMaxB + b) * 33 + lane] = acc[b];
   __syncthreads();
   for (int i = threadIdx.x; i < B * 32; i += kHeadBwdThreads) {
     const int b = i >> 5, l = i & 31;
     float t = 0.f;
 #pragma unroll
-    for (int w2 = 0; w2 < kHeadXWarps; ++w2) t += part[w2][b][l];
+    for (int w2 = 0; w2 < kHeadXWarps; ++w2) t += part[(w2 * kHeadMaxB + b) * 33 + l];
     if (blockIdx.x * 32 + l < K) dx[(size_t)b * K + blockIdx.x * 32 + l] = t;
   }
 }
@@ -262,14 +282,23 @@ extern "C" int sqlx_head_linear_bwd(const float* W, const float* x, const float*
   SQLX_REQUIRE(((reinterpret_cast<uintptr_t>(dW) | reinterpret_cast<uintptr_t>(x)) & 15) == 0, "dW and x must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nx = dx ? ceil_div(K, 32) : 0;
-  const size_t smem_dx = dx ? sizeof(float) * (size_t)N * kHeadMaxB : 0, smem_dw = sizeof(float) * (size_t)B * K;
-  const size_t smem = smem_dx > smem_dw ? smem_dx : smem_dw;
+  const int Bp = (B + 3) / 4 * 4;
+  const int nslab = ceil_div(K, kHeadSlab);
+  // rows per dW CTA: a multiple of the 16 warps, as small as keeps the whole grid within one wave of two CTAs per SM
+  int target = 2 * kNumSMs - nx;
+  target = target < 64 ? 64 : target;
+  int rows_per_cta = kHeadXWarps * ceil_div(N * nslab, kHeadXWarps * target);
+  rows_per_cta = rows_per_cta > 64 ? 64 : rows_per_cta;
+  const int nchunk = ceil_div(N, rows_per_cta);
+  const size_t smem_dx = dx ? sizeof(float) * (size_t)N * Bp : 0;
+  const size_t smem_dw = sizeof(float) * (size_t)B * (K < kHeadSlab ? K : kHeadSlab);
+  size_t smem = smem_dx > smem_dw ? smem_dx : smem_dw;
+  smem = smem > kHeadPartBytes ? smem : kHeadPartBytes;
   SQLX_REQUIRE(smem <= 200 * 1024, "layer %d x %d too large for the shared-memory staging", N, K);
   if (int e = ensure_dyn_smem(head_linear_bwd_kernel, 200 * 1024)) return e;   // the cap checked above, once per device
-  int nw = ceil_div(N, kHeadXWarps);
-  nw = nw > kNumSMs ? kNumSMs : nw;
   ProfScope prof("head_linear_bwd_kernel", st);
-  head_linear_bwd_kernel<<<nx + nw, kHeadBwdThreads, smem, st>>>(dy, y, x, W, B, N, K, leaky, nx, dz, dW, db, dx);
+  head_linear_bwd_kernel<<<nx + nslab * nchunk, kHeadBwdThreads, smem, st>>>(dy, y, x, W, B, Bp, N, K, leaky, nx, nslab, rows_per_cta, dz,
+                                                                           dW, db, dx);
   return check_launch("head_linear_bwd_kernel");
 }
 

@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
                     help="headline workload = BASELINE config (default 2: the configuration the metric is quoted on "
                          "that fits one GPU step for step with the reference's CPU-runnable case)")
-    ap.add_argument("--workloads", default="3,4",
+    ap.add_argument("--workloads", default="3,4,5",
                     help="further BASELINE configs measured into the same JSON line under 'workloads' ('' = none)")
     ap.add_argument("--batch", type=int, default=0, help="override the batch per GPU of the headline workload")
     ap.add_argument("--no-graph", action="store_true", help="submit the step eagerly instead of replaying a CUDA graph")
@@ -328,6 +328,154 @@ def load_traffic():
             d[base] = v["dram_bytes_per_launch"]
         out[ck] = d
     return out
+
+
+# --------------------------------------------------------------------------------------------- the fine-tune workload
+def run_finetune_workload(cx, steps, warmup):
+    """BASELINE config 5 (ConvNeXt-L 320x1024 metric-depth fine-tune, SURVEY 8 table: B = 8, x0 32x160x512, Q = D = 64):
+    the supervised step of finetune/train_ft_SQLdepth.py:232-278 behind the model's backbone -- SQL decoder tail ->
+    align_corners=True resize to the ground truth -> per-sample median scaling -> SILog -> backward -- as one CUDA graph.
+    value: inputs resident; e2e: decoder features, queries and the ground-truth depth map copied from pinned host memory
+    every step (copy of batch i+1 under the step on batch i) + loss read-back."""
+    import sqlx
+    from sqlx import sql as S
+    from sqlx.hotpath import HotPath, HotPathConfig
+    from _workload import head_state
+    dev, world, rank, dist = cx.dev, cx.world, cx.rank, cx.dist
+    B, H, W, h, w, Q, D, E = 8, 320, 1024, 160, 512, 64, 64, 32
+    min_depth, max_depth = 1e-3, 80.0
+    cfg = HotPathConfig(B=B, H=H, W=W, h=h, w=w, E=E, Q=Q, D=D, S=2, scales=(0,), min_depth=min_depth, max_depth=max_depth)
+    hp = HotPath(cfg, device=dev, use_graph=False, num_slots=2, prepare_next=False)     # owns the head and the flat gradient bucket
+    hp.load_state_dict(head_state(cfg), strict=True)
+    conv = hp.convert_to_prob[0]
+    g = torch.Generator().manual_seed(4321 + rank)
+    host = {"x": torch.randn(B, E, h, w, generator=g).pin_memory(),
+            "queries": (0.4 * torch.randn(B, Q, E, generator=g)).pin_memory()}
+    gt = 1.0 + 79.0 * torch.rand(B, 1, H, W, generator=g)
+    gt[torch.rand(B, 1, H, W, generator=g) < 0.8] = 0.0               # sparse LiDAR ground truth: ~20 % of the pixels valid
+    host["depth"] = gt.pin_memory()
+    sets = [{k: v.to(dev) for k, v in host.items()} for _ in range(2)]
+    for st in sets:
+        st["x"].requires_grad_(True)
+        st["queries"].requires_grad_(True)
+    one = torch.ones((), device=dev)
+    losses = [None, None]
+
+    def step_fn(slot):
+        I, gv = sets[slot], hp.grad_views[slot]
+        I["x"].grad = None
+        I["queries"].grad = None
+        pred = S.sql_tail(I["x"], I["queries"], conv.weight.view(D, Q), conv.bias, hp._centers_fn(slot), (),
+                          head_grad_out=(gv[0].view(D, Q), gv[1]))
+        loss = sqlx.finetune_loss(pred, I["depth"], min_depth, min_depth, max_depth, garg_crop=True)
+        torch.autograd.backward(loss, grad_tensors=one)
+        return loss.detach(), pred.detach()
+
+    graphs = []
+    for slot in range(2):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step_fn(slot)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            losses[slot], pred0 = step_fn(slot)
+        graphs.append(gr)
+    from sqlx import _lib
+    _lib.profile_enable(True)
+    for _ in range(5):
+        step_fn(0)
+    torch.cuda.synchronize()
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / k
+
+    for _ in range(max(warmup, 3)):
+        graphs[0].replay()
+    ms_dev = timed(lambda: graphs[0].replay(), steps)
+    # end to end: two input sets, the copy of batch i+1 on a copy stream under the step on batch i
+    copy_stream, main = torch.cuda.Stream(), torch.cuda.current_stream()
+    ev_loaded = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    loss_ring = [torch.zeros(1).pin_memory() for _ in range(2)]
+    idx = [0]
+    e2e_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def enqueue(slot):
+        copy_stream.wait_event(ev_done[slot])
+        with torch.cuda.stream(copy_stream), torch.no_grad():
+            for k, v in host.items():
+                sets[slot][k].copy_(v, non_blocking=True)
+            ev_loaded[slot].record(copy_stream)
+
+    def e2e_step():
+        slot = idx[0] % 2
+        main.wait_event(ev_loaded[slot])
+        graphs[slot].replay()
+        ev_done[slot].record(main)
+        loss_ring[slot].copy_(losses[slot].reshape(1), non_blocking=True)
+        enqueue((slot + 1) % 2)
+        idx[0] += 1
+
+    for ev in ev_done:
+        ev.record(main)
+    enqueue(0)
+    for _ in range(3):
+        e2e_step()
+    ms_e2e = timed(e2e_step, steps)
+    copy_stream.synchronize()
+    res = {"config": {"workload": "BASELINE config 5 hot path: SQL decoder tail (x0 32x%dx%d, Q=%d, D=%d) + supervised "
+                                  "fine-tune loss (resize to the %dx%d ground truth, per-sample median scaling of the first "
+                                  "B/2 samples, SILog), forward+backward" % (h, w, Q, D, H, W),
+                      "batch_per_gpu": B, "global_batch": B * world, "height": H, "width": W, "parallelism": "dp%d" % world,
+                      "submission": "cuda_graph"},
+           "value": B * world / (ms_dev * 1e-3), "unit": UNIT, "ms_per_step": ms_dev,
+           "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": int(e2e_bytes), "d2h_bytes_per_step": 4},
+           "loss": float(losses[0]),
+           "kernels": {k: {"launches_per_step": v[0] / 5.0, "us_per_launch": 1e3 * v[1] / max(1, v[0])}
+                       for k, v in sorted(prof.items())}}
+    if rank == 0 and not cx.args.no_parity:
+        # parity of the timed batch against the float64 oracle on the host (forward: depth, ratios, loss)
+        from oracle import sqldepth_oracle as O
+        t0 = time.time()
+        state = {k: v.detach().double().cpu() for k, v in hp.state_dict().items()}
+        mlp = [state["bins_regressor.%d.%s" % (i, k)] for i in (0, 2, 4) for k in ("weight", "bias")]
+        with torch.no_grad():
+            graphs[0].replay()
+            torch.cuda.synchronize()
+            # (set 0 holds the host batch after the e2e loop: the same values the oracle sees)
+            tail = O.sql_tail(host["x"].double(), host["queries"].double(), mlp,
+                              state["convert_to_prob.0.weight"].view(D, Q), state["convert_to_prob.0.bias"], min_depth, max_depth)
+            ref_loss, ref_ratio = O.finetune_loss(tail["pred"], host["depth"].double(), min_depth, min_depth, max_depth,
+                                                  garg_crop=True)
+        res["parity"] = {"loss_gpu": float(losses[0]), "loss_oracle_fp64": float(ref_loss),
+                         "abs_diff": abs(float(losses[0]) - float(ref_loss)), "bar": 1e-5,
+                         "depth_max_rel": float(((pred0.double().cpu() - tail["pred"]) / tail["pred"]).abs().max()),
+                         "oracle": "oracle/sqldepth_oracle.py in float64 on the host CPU, forward only, %.1f s" % (time.time() - t0)}
+    graphs.clear()
+    return res
 
 
 # --------------------------------------------------------------------------------------------- one workload on the GPU
@@ -689,6 +837,9 @@ def main():
     for tok in [t for t in args.workloads.split(",") if t.strip()]:
         n = int(tok)
         if n == args.config:
+            continue
+        if n == 5:
+            extra["config5"] = run_finetune_workload(cx, max(20, min(args.steps, 100)), max(args.warmup, 3))
             continue
         r = run_workload(cx, n, baseline_config(n), max(20, min(args.steps, 100)), max(args.warmup, 3), full=False)
         if r is not None:

@@ -270,6 +270,11 @@ size_t sqlx_median_ratio_workspace_bytes(int B);
 int sqlx_median_ratio(const float* pred, const float* depth, int B, int H, int W, int count, float min_depth_eval,
                       float max_depth_eval, int r0, int r1, int c0, int c1, float* ratio, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* The same with pred [B,h,w] at its own resolution, read through the bilinear align_corners=True resize to H x W of
+ * finetune/train_ft_SQLdepth.py:235 (the resized map is never materialised). */
+int sqlx_median_ratio_resized(const float* pred, int h, int w, const float* depth, int B, int H, int W, int count,
+                              float min_depth_eval, float max_depth_eval, int r0, int r1, int c0, int c1, float* ratio,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 size_t sqlx_silog_workspace_bytes(void);
 int sqlx_silog_fwd(const float* pred, const float* gt, const uint8_t* mask, int B, int h, int w, int H, int W,

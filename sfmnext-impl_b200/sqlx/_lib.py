@@ -106,6 +106,8 @@ _PROTOS = {
     "sqlx_median_ratio_workspace_bytes": (c_size_t, [c_int]),
     "sqlx_median_ratio": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sqlx_median_ratio_resized": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
+                                          c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sqlx_silog_workspace_bytes": (c_size_t, []),
     "sqlx_silog_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                c_void_p, c_size_t, c_void_p]),

@@ -249,9 +249,12 @@ def median_scale_ratios(pred, depth, min_depth_eval, max_depth_eval, garg_crop=F
     """The per-sample factors of finetune/train_ft_SQLdepth.py:236-266 in ONE kernel launch on the tensors' device
     (csrc/median.cu: exact radix select of numpy.median's two middle order statistics over the valid pixels):
     ratio_i = median(depth_i[valid]) / median(pred_i[valid]) for the first `count` (default B // 2, :236) samples,
-    1 where either median is NaN (:261-264), 1 for the remaining samples.  pred, depth: [B,1,H,W] -> [B] (detached)."""
+    1 where either median is NaN (:261-264), 1 for the remaining samples.  depth: [B,1,H,W]; pred: [B,1,H,W], or
+    [B,1,h,w] at the network's resolution -- the kernel then reads it through the align_corners=True bilinear resize of
+    :235 without materialising the resized map.  Returns [B] (detached)."""
     require_cuda(pred, depth)
-    B, _, H, W = pred.shape
+    B, _, H, W = depth.shape
+    h, w = pred.shape[-2:]
     count = B // 2 if count is None else count
     r0, r1, c0, c1 = _crop_box(H, W, garg_crop, eigen_crop, dataset)
     p, d = _f32c(pred), _f32c(depth)
@@ -260,8 +263,9 @@ def median_scale_ratios(pred, depth, min_depth_eval, max_depth_eval, garg_crop=F
     ws = _median_ws.get(key)
     if ws is None:                                  # arrival counters: zeroed once, the kernel leaves them zero
         ws = _median_ws[key] = torch.zeros(lib().sqlx_median_ratio_workspace_bytes(B), device=p.device, dtype=torch.uint8)
-    check(lib().sqlx_median_ratio(ptr(p), ptr(d), B, H, W, int(count), float(min_depth_eval), float(max_depth_eval), r0, r1,
-                                  c0, c1, ptr(ratio), ptr(ws), ws.numel(), stream_ptr()), "sqlx_median_ratio")
+    check(lib().sqlx_median_ratio_resized(ptr(p), h, w, ptr(d), B, H, W, int(count), float(min_depth_eval),
+                                          float(max_depth_eval), r0, r1, c0, c1, ptr(ratio), ptr(ws), ws.numel(),
+                                          stream_ptr()), "sqlx_median_ratio_resized")
     return ratio
 
 
@@ -273,6 +277,20 @@ def median_scale(pred, depth, min_depth_eval, max_depth_eval, garg_crop=False, e
     require_cuda(pred, depth)
     ratio = median_scale_ratios(pred, depth, min_depth_eval, max_depth_eval, garg_crop, eigen_crop, dataset, count)
     return pred * ratio.view(-1, 1, 1, 1)
+
+
+def finetune_loss(pred, depth, min_depth, min_depth_eval, max_depth_eval, garg_crop=False, eigen_crop=False,
+                  dataset="kitti", variance_focus=0.15, mask=None):
+    """The supervised fine-tuning step of finetune/train_ft_SQLdepth.py:232-274 after the model forward, on the device:
+    pred [B,1,h,w] (the decoder output) is NOT resized: the median-ratio kernel and the SILog kernel both read it through
+    the align_corners=True bilinear resize to the ground truth's shape (:235), and the per-sample scaling commutes with
+    that (linear) resize.  mask defaults to depth > min_depth (:271).  Returns the SILog loss (:274), differentiable wrt
+    pred with the ratios as constants, exactly like `pred[i] *= ratio` in the reference."""
+    require_cuda(pred, depth)
+    ratio = median_scale_ratios(pred.detach(), depth, min_depth_eval, max_depth_eval, garg_crop, eigen_crop, dataset)
+    if mask is None:
+        mask = depth > min_depth
+    return _SILogFn.apply(pred * ratio.view(-1, 1, 1, 1), depth, mask, variance_focus)
 
 
 # ----------------------------------------------------------------------------- indoor rectification warp (N4)

@@ -75,3 +75,29 @@ def test_needs_a_crop_flag_and_cuda():
     import sqlx
     with pytest.raises((ValueError, sqlx.SqlxError)):
         sqlx.median_scale_ratios(torch.rand(2, 1, 8, 8), torch.rand(2, 1, 8, 8), 1e-3, 80.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(4, 24, 80, 47, 156), (6, 40, 128, 93, 310), (2, 16, 16, 16, 16)])
+def test_finetune_loss_matches_oracle(shape):
+    """sqlx.finetune_loss (median ratios and SILog both read the low-resolution prediction through the align_corners=True
+    resize; nothing of ground-truth size is materialised) against the fp64 oracle of train_ft_SQLdepth.py:232-274: same
+    ratios (float32 resize arithmetic: 1e-5), loss 1e-5, gradient 1e-4 of its largest entry."""
+    import sqlx
+    from oracle import sqldepth_oracle as O
+    B, h, w, H, W = shape
+    g = torch.Generator().manual_seed(B + h)
+    pred = (0.5 + 20 * torch.rand(B, 1, h, w, generator=g)).requires_grad_(True)
+    depth = 80 * torch.rand(B, 1, H, W, generator=g)
+    depth[torch.rand(B, 1, H, W, generator=g) < 0.6] = 0.0          # sparse ground truth
+    ref_loss, ref_ratio = O.finetune_loss(pred.double(), depth.double(), 1e-3, 1e-3, 80.0, garg_crop=True)
+    ref_grad, = torch.autograd.grad(ref_loss, pred)
+    pc = pred.detach().cuda().requires_grad_(True)
+    dc = depth.cuda()
+    ratio = sqlx.median_scale_ratios(pc.detach(), dc, 1e-3, 80.0, garg_crop=True)
+    assert float((ratio.cpu().double() - ref_ratio.double()).abs().max()) < 1e-5 * float(ref_ratio.abs().max())
+    loss = sqlx.finetune_loss(pc, dc, 1e-3, 1e-3, 80.0, garg_crop=True)
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) < 1e-5 * max(1.0, abs(float(ref_loss)))
+    gd = (pc.grad.cpu().double() - ref_grad.double()).abs().max()
+    assert float(gd) < 1e-4 * float(ref_grad.abs().max())

@@ -456,7 +456,7 @@ def run_finetune_workload(cx, steps, warmup):
            "loss": float(losses[0]),
            "kernels": {k: {"launches_per_step": v[0] / 5.0, "us_per_launch": 1e3 * v[1] / max(1, v[0])}
                        for k, v in sorted(prof.items())}}
-    if rank == 0 and not cx.args.no_parity:
+    if world == 1 and not cx.args.no_parity:
         # parity of the timed batch against the float64 oracle on the host (forward: depth, ratios, loss)
         from oracle import sqldepth_oracle as O
         t0 = time.time()
@@ -839,7 +839,10 @@ def main():
         if n == args.config:
             continue
         if n == 5:
-            extra["config5"] = run_finetune_workload(cx, max(20, min(args.steps, 100)), max(args.warmup, 3))
+            # single-GPU leg only: under torchrun the line carries the self-supervised workloads (whose in-step gradient
+            # exchange is the multi-GPU path that is measured); nothing rank-dependent may run between collectives
+            if world == 1:
+                extra["config5"] = run_finetune_workload(cx, max(20, min(args.steps, 100)), max(args.warmup, 3))
             continue
         r = run_workload(cx, n, baseline_config(n), max(20, min(args.steps, 100)), max(args.warmup, 3), full=False)
         if r is not None:

@@ -58,8 +58,16 @@ def _worker(rank, world, port, ret):
     assert shard["x"].shape[0] == 2
     loss, grads = _loss_and_grads(shard, params)
     grads = [g.float().contiguous() for g in grads]
+    # the hot path's form: every gradient is a view of ONE flat buffer that is averaged in place (no pack / unpack)
+    from sqlx.dist import allreduce_flat_
+    sizes = [g.numel() for g in grads]
+    flat = torch.cat([g.reshape(-1) for g in grads]).clone()
+    views = [v.view_as(g) for v, g in zip(flat.split(sizes), grads)]
+    allreduce_flat_(flat)
     bucket = GradBucket(grads)
     bucket.allreduce_(grads)
+    for v, g in zip(views, grads):
+        assert torch.equal(v, g), "flat in-place exchange and the packed bucket must agree bit for bit"
     lt = loss.clone().float().reshape(1)
     dist.all_reduce(lt)
     if rank == 0:

@@ -264,8 +264,9 @@ int sqlx_rotation_warp_bwd(const float* img, const float* P, const float* K3, co
  *   ratio[i] = median(depth_i[valid]) / median(pred_i[valid]) for i < count (1 when either median is NaN), 1 for i >= count
  *   valid = min_depth_eval < depth < max_depth_eval inside the crop rows [r0,r1) x columns [c0,c1) (garg / eigen crop)
  * pred, depth [B,H,W] fp32 (pred already resized to the ground truth, :235).  Exact radix select of the two middle order
- * statistics (numpy.median); replaces one device->host->device round trip per sample.  workspace: zero-initialised ONCE by
- * the caller (the kernel leaves it zero); B <= 64. */
+ * statistics (numpy.median): four 8-bit digit passes + one "next key" pass, five launches of (slices x 2 arrays x count)
+ * CTAs whose shared-memory histograms are merged into global ones; replaces one device->host->device round trip per
+ * sample.  workspace: scratch of sqlx_median_ratio_workspace_bytes(B) bytes, cleared by the call itself. */
 size_t sqlx_median_ratio_workspace_bytes(int B);
 int sqlx_median_ratio(const float* pred, const float* depth, int B, int H, int W, int count, float min_depth_eval,
                       float max_depth_eval, int r0, int r1, int c0, int c1, float* ratio, void* workspace,

@@ -832,8 +832,66 @@ def main():
     cx.tf32_peak = 0.5 * float(peaks.get("bf16_tflops_sustained", 1422.0))
     cx.traffic = load_traffic()
 
+    def build_line(res, extra):
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+        config = res.pop("config")
+        config["l2"] = ("no explicit flush: every step streams its inputs (frames, decoder features, noise: > 126 MB at every "
+                        "workload) plus the saved planes of the loss scales through the 126 MB L2")
+        config["submission"] = "eager" if args.no_graph else "cuda_graph"
+        config["frame_only_work"] = ("identity reprojection losses + pixel-interleaved source copies: every step computes them "
+                                     "for the NEXT input set inside its own graph, at low stream priority under its backward, "
+                                     "and consumes what the previous step prepared (HotPath.prepare_next; once per step, as "
+                                     "in the reference)")
+        if world > 1:
+            config["grad_exchange"] = (
+                "(summary-path backward leaves %d SMs to the NCCL kernel) " % (32 if args.exchange_sms < 0 else args.exchange_sms) +
+                "one NCCL all-reduce (average) of the flat gradient bucket per step (the kernels write the parameter gradients "
+                "into views of it: no pack / unpack), issued inside the step on a communication stream when the last parameter "
+                "gradient exists (overlaps the summary-path backward kernel; part of the CUDA graph)"
+                if not args.allreduce_after_step else
+                "one NCCL all-reduce (average) of the flat gradient bucket after the step")
+        config["e2e_pipeline"] = ("H2D of the next %d batches on a copy stream overlaps the step on batch i (%d device input "
+                                  "sets); tie-break noise drawn on the device instead of copied from the host; the loss of "
+                                  "every step is copied to pinned host memory and read by the host one step later; frames "
+                                  "shipped as %s" % (max(1, args.prefetch), max(2, args.prefetch + 1),
+                                                     "float32" if args.f32_frames else "uint8 and scaled to [0,1] on the device"))
+        config["cpu_binding"] = binding
+        line["config"] = config
+        line["e2e"] = res.pop("e2e")
+        line["gpu_launches"] = res["gpu_launches_per_step"] * args.steps
+        for k in ("gpu_launches_per_step", "clocks", "roofline", "step_roofline", "kernels", "kernel_ms_per_step", "loss",
+                  "parity", "selection", "reprojection_dominant", "exposed_comm_ms", "ms_per_step_without_exchange"):
+            if k in res:
+                line[k] = res[k]
+        line["workloads"] = extra
+        return line
+
     res = run_workload(cx, args.config, cfg, args.steps, args.warmup, full=True)
     extra = {}
+    # N > 1 insurance: the headline workload is measured; should a later workload of this launch stall (a collective one
+    # rank never enters cannot be caught as an exception), every rank leaves after `bail_after` seconds and rank 0 prints
+    # the line it has, with the reason under "workloads"
+    emitted = threading.Event()
+    bail_after = 240.0
+    watchdog = None
+    if world > 1 and args.workloads.strip():
+        def bail():
+            if rank == 0 and not emitted.is_set():
+                emitted.set()
+                try:
+                    partial = build_line(dict(res), {"aborted": "a further workload did not finish within %.0f s; "
+                                                                "headline workload only" % bail_after})
+                    partial["cpu_baseline"] = None
+                    print(json.dumps(partial))
+                    sys.stdout.flush()
+                except Exception:
+                    pass
+            os._exit(0)
+        watchdog = threading.Timer(bail_after, bail)
+        watchdog.daemon = True
+        watchdog.start()
     for tok in [t for t in args.workloads.split(",") if t.strip()]:
         n = int(tok)
         if n == args.config:
@@ -847,6 +905,8 @@ def main():
         r = run_workload(cx, n, baseline_config(n), max(20, min(args.steps, 100)), max(args.warmup, 3), full=False)
         if r is not None:
             extra["config%d" % n] = r
+    if watchdog is not None:
+        watchdog.cancel()
 
     def finish():
         """N > 1 teardown: the graphs holding captured collectives are gone (run_workload drops them), drain the device
@@ -868,39 +928,11 @@ def main():
         finish()
         return
 
-    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
-    config = res.pop("config")
-    config["l2"] = ("no explicit flush: every step streams its inputs (frames, decoder features, noise: > 126 MB at every "
-                    "workload) plus the saved planes of the loss scales through the 126 MB L2")
-    config["submission"] = "eager" if args.no_graph else "cuda_graph"
-    config["frame_only_work"] = ("identity reprojection losses + pixel-interleaved source copies: every step computes them "
-                                 "for the NEXT input set inside its own graph, at low stream priority under its backward, "
-                                 "and consumes what the previous step prepared (HotPath.prepare_next; once per step, as "
-                                 "in the reference)")
-    if world > 1:
-        config["grad_exchange"] = (
-            "(summary-path backward leaves %d SMs to the NCCL kernel) " % (32 if args.exchange_sms < 0 else args.exchange_sms) +
-            "one NCCL all-reduce (average) of the flat gradient bucket per step (the kernels write the parameter gradients "
-            "into views of it: no pack / unpack), issued inside the step on a communication stream when the last parameter "
-            "gradient exists (overlaps the summary-path backward kernel; part of the CUDA graph)"
-            if not args.allreduce_after_step else
-            "one NCCL all-reduce (average) of the flat gradient bucket after the step")
-    config["e2e_pipeline"] = ("H2D of the next %d batches on a copy stream overlaps the step on batch i (%d device input "
-                              "sets); tie-break noise drawn on the device instead of copied from the host; the loss of "
-                              "every step is copied to pinned host memory and read by the host one step later; frames "
-                              "shipped as %s" % (max(1, args.prefetch), max(2, args.prefetch + 1),
-                                                 "float32" if args.f32_frames else "uint8 and scaled to [0,1] on the device"))
-    config["cpu_binding"] = binding
-    line["config"] = config
-    line["e2e"] = res.pop("e2e")
-    line["gpu_launches"] = res["gpu_launches_per_step"] * args.steps
-    for k in ("gpu_launches_per_step", "clocks", "roofline", "step_roofline", "kernels", "kernel_ms_per_step", "loss",
-              "parity", "selection", "reprojection_dominant", "exposed_comm_ms", "ms_per_step_without_exchange"):
-        if k in res:
-            line[k] = res[k]
-    line["workloads"] = extra
+    if emitted.is_set():          # the watchdog already printed (cannot happen after cancel(); belt and braces)
+        finish()
+        return
+    emitted.set()
+    line = build_line(res, extra)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:          # reported beside the N = 1 line only

@@ -874,7 +874,7 @@ def main():
     # rank never enters cannot be caught as an exception), every rank leaves after `bail_after` seconds and rank 0 prints
     # the line it has, with the reason under "workloads"
     emitted = threading.Event()
-    bail_after = 240.0
+    bail_after = float(os.environ.get("SQLX_BENCH_BAIL_AFTER", "240"))
     watchdog = None
     if world > 1 and args.workloads.strip():
         def bail():

@@ -101,3 +101,20 @@ def test_finetune_loss_matches_oracle(shape):
     assert abs(float(loss) - float(ref_loss)) < 1e-5 * max(1.0, abs(float(ref_loss)))
     gd = (pc.grad.cpu().double() - ref_grad.double()).abs().max()
     assert float(gd) < 1e-4 * float(ref_grad.abs().max())
+
+
+@pytest.mark.parametrize("case", ["kitti_garg", "kitti_eigen"])
+def test_oracle_finetune_step_matches_reference_fixture(case):
+    """oracle.finetune_loss against tests/golden/finetune_step.npz, produced with the reference's own SILogLoss class and
+    resize call (oracle/make_golden_finetune.py): ratios exact, loss and gradient at float32 round-off."""
+    import numpy as np
+    from oracle import sqldepth_oracle as O
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "finetune_step.npz"))
+    pred = torch.from_numpy(z[case + "/pred"]).requires_grad_(True)
+    depth = torch.from_numpy(z[case + "/depth"])
+    kw = dict(garg_crop=bool(z[case + "/garg"]), eigen_crop=bool(z[case + "/eigen"]), dataset="kitti")
+    loss, ratio = O.finetune_loss(pred, depth, 1e-3, 1e-3, 80.0, **kw)
+    grad, = torch.autograd.grad(loss, pred)
+    assert np.array_equal(ratio.numpy(), z[case + "/ratios"])
+    assert abs(float(loss) - float(z[case + "/loss"])) < 1e-6 * max(1.0, abs(float(z[case + "/loss"])))
+    assert float((grad - torch.from_numpy(z[case + "/grad"])).abs().max()) < 1e-6 * float(np.abs(z[case + "/grad"]).max())
